@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the EOL-Cloth hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sheet1024|sheet256|ensemble64]
+
+A "step" is one Forces::fill (f, M, MDK into the fixed CSR pattern) of one synthetic cloth sheet per GPU.
+Default workload = BASELINE.json configs[3]: regular2 1024x1024 sheet (2,093,058 triangles + 3,137,541 interior edges
+= 5,230,599 element assemblies per fill).  N > 1 runs one independent replica (own state seed) per GPU — a single mesh
+does not shard: weak scaling, no collective on the data path; NCCL is only used for the barrier and the
+max-over-ranks of the device time.
+
+  value        element assemblies / s with x, X resident in HBM (device-pointer C-ABI entry, CUDA events on the ctx stream)
+  e2e          the same through the host-buffer C-ABI entry (eolc_forces_fill): pinned x/X H2D + f/M/MDK D2H every step
+  roofline     algorithmic bytes of one fill (24N+16N+12F+16Ei+24N+8nnz(M)+8nnz(MDK)) / device time of one fill
+  cpu_baseline the oracle (reference Compute*.cpp object code + restated Forces.cpp glue), 1 thread, bounded sample
+  cd           secondary metric contacts/s: CD2 on the 512x512 box scene (BASELINE configs[2]), device + D2H of the list
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAT = (0.05, 50.0, 0.01, 1.0e-5, 0.0, 1.0)   # simulationSettings.json:27-33
+GRAV = (0.0, 0.0, -9.8)
+H = 0.5e-2
+METRIC = "element f+K assemblies/sec"
+UNIT = "elements/s"
+
+
+# ---------------------------------------------------------------------------------------------- helpers (CPU-testable)
+def shard_range(n_units, rank, world):
+    """Contiguous shard [lo, hi) of n_units independent scenes for `rank` of `world`."""
+    per, rem = divmod(n_units, world)
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def max_over_ranks(v, device):
+    import torch
+    d = _dist()
+    if d is None:
+        return float(v)
+    t = torch.tensor([float(v)], dtype=torch.float64, device=device)
+    d.all_reduce(t, op=d.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(v, device):
+    import torch
+    d = _dist()
+    if d is None:
+        return float(v)
+    t = torch.tensor([float(v)], dtype=torch.float64, device=device)
+    d.all_reduce(t, op=d.ReduceOp.SUM)
+    return float(t.item())
+
+
+def algorithmic_bytes(N, F, Ei, nnzM, nnzK):
+    """x + X + face idx + edge stencil idx + f + M values + MDK values."""
+    return 24 * N + 16 * N + 12 * F + 16 * Ei + 24 * N + 8 * nnzM + 8 * nnzK
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def __enter__(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+        return self
+
+    def __exit__(self, *a):
+        if self.p is not None:
+            time.sleep(0.15)
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        try:
+            self.f.flush()
+            rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+            sm = [float(r[1]) for r in rows]
+            out["sm_mhz"] = statistics.median(sm) if sm else None
+            out["sm_max_mhz"] = float(rows[0][2]) if rows else None
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = set()
+            for r in rows:
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            out["reasons"] = sorted(reasons)
+            out["samples"] = len(rows)
+        except Exception as e:  # clocks are evidence, never fatal
+            out["error"] = str(e)
+        finally:
+            try:
+                os.unlink(self.f.name)
+            except Exception:
+                pass
+        return out
+
+
+def make_sheet(n, seed):
+    import eol_cloth_b200 as E
+    X, fn = E.meshgen.regular2(n)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    x = E.meshgen.drape_state(X, seed=seed)
+    return X, fn, es, x
+
+
+# ---------------------------------------------------------------------------------------------- CPU legs
+def cpu_forces_sample(n=256, repeats=3):
+    """Oracle Forces::fill on a bounded sample (regular2 n x n), single thread, best of `repeats`."""
+    from oracle import oracle as O
+    X, fn, es, x = make_sheet(n, 0)
+    elements = fn.shape[0] + int((es[:, 3] >= 0).sum())
+    best = None
+    for _ in range(repeats):
+        t = time.perf_counter()
+        O.forces_fill(fn, es, x, X, MAT, GRAV, H)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return elements / best, elements, best
+
+
+def run_reference(args):
+    """--impl reference: the reference CPU path (oracle) on the same metric, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    n = 256
+    X, fn, es, x = make_sheet(n, 0)
+    elements = fn.shape[0] + int((es[:, 3] >= 0).sum())
+    for _ in range(max(1, min(args.warmup, 1))):
+        O.forces_fill(fn, es, x, X, MAT, GRAV, H)
+    steps = max(1, min(args.steps, 10))
+    t = time.perf_counter()
+    for _ in range(steps):
+        O.forces_fill(fn, es, x, X, MAT, GRAV, H)
+    dt = (time.perf_counter() - t) / steps
+    value = elements / dt
+    sample = f"regular2 n={n} sheet ({elements} elements) per step; the 1024x1024 workload needs >25 GB of triplets on the reference path"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                             "note": "reference Compute*.cpp object code (oracle/_ref) + Eigen-free restatement of Forces.cpp glue; the reference is single-threaded"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name(w):
+    return {"sheet1024": "regular2 1024x1024 sheet, Forces::fill (f+M+MDK) into fixed CSR pattern (BASELINE configs[3])",
+            "sheet256": "regular2 256x256 sheet, Forces::fill (BASELINE configs[1])",
+            "ensemble64": "ensemble of 4096 regular2 64x64 scenes, Forces::fill batched (BASELINE configs[4])"}[w]
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import eol_cloth_b200 as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = E.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    if args.workload == "ensemble64":
+        n, total_scenes = 64, 4096
+        lo, hi = shard_range(total_scenes, rank, world)
+        S = hi - lo
+        scaling = "strong"
+    else:
+        n = 1024 if args.workload == "sheet1024" else 256
+        S, lo = 1, rank
+        scaling = "weak"
+    X, fn, es, _ = make_sheet(n, 0)
+    N, F = X.shape[0], fn.shape[0]
+    plan = E.ForcesPlan(ctx, N, fn, es, X_hint=X)
+    Ei = plan.n_interior_edges
+    elements = F + Ei
+    nnzM, nnzK = plan.nnz
+    abytes = algorithmic_bytes(N, F, Ei, nnzM, nnzK)
+
+    xs = np.stack([E.meshgen.drape_state(X, seed=lo + s) for s in range(S)]) if S <= 64 else None
+    if xs is None:   # big ensembles: perturb per scene on the device-side copy (seeded, cheap)
+        base = E.meshgen.drape_state(X, seed=0)
+        rng = np.random.default_rng(lo)
+        xs = base[None] + rng.uniform(-1e-3, 1e-3, size=(S,) + base.shape)
+    x_d = torch.from_numpy(xs).to(dev)
+    X_d = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(X, (S,) + X.shape))).to(dev)
+    f_d = torch.empty((S, 3 * N), dtype=torch.float64, device=dev)
+    M_d = torch.empty((S, nnzM), dtype=torch.float64, device=dev)
+    K_d = torch.empty((S, nnzK), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step_dev():
+        plan.fill_dev(x_d.data_ptr(), X_d.data_ptr(), MAT, GRAV, H, f_d.data_ptr(), M_d.data_ptr(), K_d.data_ptr(), n_scenes=S)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_dev()
+        ev1.record(stream)
+        barrier()
+    ms_local = ev0.elapsed_time(ev1) / args.steps
+    clocks = clk.summary()
+    ms = max_over_ranks(ms_local, dev)
+    total_elements = sum_over_ranks(float(elements * S), dev)
+    value = total_elements / (ms * 1e-3)
+    checksum = float(K_d[0].sum().item()) + float(f_d[0].sum().item())
+
+    # ---- e2e: host-buffer C-ABI entry, pinned host arrays, one scene per step per rank
+    x_h = torch.from_numpy(xs[0].copy()).pin_memory()
+    X_h = torch.from_numpy(X.copy()).pin_memory()
+    f_h = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+    M_h = torch.empty(nnzM, dtype=torch.float64).pin_memory()
+    K_h = torch.empty(nnzK, dtype=torch.float64).pin_memory()
+    xa, Xa, fa, Ma, Ka = (t.numpy() for t in (x_h, X_h, f_h, M_h, K_h))
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def step_host():
+        plan.fill_into(xa, Xa, MAT, GRAV, H, fa, Ma, Ka)
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3, dev)
+    e2e_value = sum_over_ranks(float(elements), dev) / (e2e_ms * 1e-3)
+    h2d = 8 * (3 * N + 2 * N)
+    d2h = 8 * (3 * N + nnzM + nnzK)
+
+    peak, peak_src = measured_peak()
+    achieved = abytes * S / (ms_local * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "mesh": f"regular2 n={n}", "scenes_per_gpu": S, "nodes": N,
+                   "faces": F, "interior_edges": Ei, "nnz_M": nnzM, "nnz_MDK": nnzK, "parallelism": f"replicas x{world}",
+                   "l2_policy": "working set per step (%.0f MB) exceeds the 126 MB L2" % (abytes * S / 1e6)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "eolc_forces_fill (host buffers, pinned)"},
+        "gpu_launches": args.steps * plan.launches_per_fill * (1 if S == 1 else 1),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_fill": abytes,
+                     "kernel": "whole fill (all kernels of one step)", "ms": ms_local},
+        "checksum": checksum,
+    }
+
+    if rank == 0 and not args.no_cpu:
+        v, el, dt = cpu_forces_sample(256, 3)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"regular2 n=256 sheet ({el} elements), best of 3, {dt:.2f} s per fill",
+                                "note": "reference Compute*.cpp object code + restated Forces.cpp glue incl. triplets + setFromTriplets; single thread like the reference"}
+    if rank == 0 and not args.no_cd:
+        line["cd"] = bench_cd(ctx, dev, stream)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def bench_cd(ctx, dev, stream):
+    """Secondary metric: CD2 narrow phase on the 512x512 box scene (BASELINE configs[2])."""
+    import torch
+    import eol_cloth_b200 as E
+    from eol_cloth_b200.collisions import make_obstacles
+    X, fn = E.meshgen.regular2(512)
+    x = E.meshgen.box_scene_state(X, seed=0)
+    obs = make_obstacles(E.meshgen.BOX_THRESHOLD, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame()[None])
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, E.meshgen.BOX_THRESHOLD)
+    x_d = torch.from_numpy(x).to(dev)
+    torch.cuda.synchronize()
+    cap = X.shape[0] + 4096
+    for _ in range(3):
+        c, _ = plan.run(x_d.data_ptr(), obs, 0, 0, capacity=cap, x_is_device_ptr=True)
+    reps = 10
+    t = time.perf_counter()
+    for _ in range(reps):
+        c, _ = plan.run(x_d.data_ptr(), obs, 0, 0, capacity=cap, x_is_device_ptr=True)
+    dt = (time.perf_counter() - t) / reps
+    pair_tests, launches = plan.stats()
+    out = {"workload": "CD2, regular2 512x512 over the simulationSettingsBox.json box (BASELINE configs[2])",
+           "contacts": int(len(c)), "ms_per_call": dt * 1e3, "contacts_per_s": len(c) / dt,
+           "pair_tests_per_s": pair_tests / dt, "launches_per_call": launches,
+           "timing": "wall clock around eolc_cd_run_dev incl. D2H of the contact list and the host post-pass"}
+    try:
+        from oracle import oracle as O
+        t = time.perf_counter()
+        ref = O.cd(fn, x, E.meshgen.BOX_THRESHOLD, None, None, obs.box_whd, obs.box_E, 0, 0)
+        dtc = time.perf_counter() - t
+        out["cpu_baseline"] = {"contacts_per_s": len(ref) / dtc, "ms_per_call": dtc * 1e3, "cores": 1, "kind": "port"}
+    except Exception as e:
+        out["cpu_baseline"] = {"error": str(e)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sheet1024", choices=["sheet1024", "sheet256", "ensemble64"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cd", action="store_true", help="skip the secondary CD measurement")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,116 @@
+"""Host-side mirror of the reference's CD / CD2 (/root/reference/src/Collisions.h:9-11) over the C ABI."""
+import ctypes
+from collections import namedtuple
+
+import numpy as np
+
+from . import capi
+
+# POD mirror of btc::Collision (include/eolc.h eolc_contact)
+CONTACT_DTYPE = np.dtype([
+    ("dist", "f8"), ("nor1", "f8", 3), ("nor2", "f8", 3), ("pos1", "f8", 3), ("pos2", "f8", 3), ("pos1_", "f8", 3),
+    ("weights1", "f8", 3), ("weights2", "f8", 3), ("edgeDir", "f8", 3),
+    ("count1", "i4"), ("count2", "i4"), ("verts1", "i4", 3), ("verts2", "i4", 3), ("tri1", "i4"), ("tri2", "i4"),
+    ("edge1", "i4", 3), ("n_edge1", "i4"), ("edge2", "i4"), ("reserved", "i4"),
+])
+assert CONTACT_DTYPE.itemsize == 264
+
+# what CD/CD2 read from `Obstacles` (Obstacles.h, Points.h, Box.h): cdthreshold, points->pxyz/norms, boxes[b]->dim/E1
+Obstacles = namedtuple("Obstacles", "cdthreshold pxyz pnorms box_whd box_E")
+
+
+def make_obstacles(cdthreshold, pxyz=None, pnorms=None, box_whd=None, box_E=None):
+    z3 = np.zeros((0, 3))
+    return Obstacles(float(cdthreshold),
+                     capi.f64(z3 if pxyz is None else pxyz).reshape(-1, 3),
+                     capi.f64(z3 if pnorms is None else pnorms).reshape(-1, 3),
+                     capi.f64(z3 if box_whd is None else box_whd).reshape(-1, 3),
+                     capi.f64(np.zeros((0, 16)) if box_E is None else box_E).reshape(-1, 16))
+
+
+class CollisionPlan:
+    """eolc_cd_plan: btc edge table (createEdges order) + perturbation table for (N, threshold)."""
+
+    def __init__(self, ctx, n_nodes, face_nodes, threshold):
+        self.ctx = ctx
+        self._h = capi.c_vp()
+        fn = capi.i32(face_nodes).reshape(-1, 3)
+        capi.check(capi.lib().eolc_cd_plan_create(ctx.handle, int(n_nodes), fn.shape[0], capi.iptr(fn), float(threshold),
+                                                  ctypes.byref(self._h)))
+        self.N, self.F, self.threshold = int(n_nodes), fn.shape[0], float(threshold)
+        self.E = capi.lib().eolc_cd_edge_count(self._h)
+
+    def edge_table(self):
+        out = np.empty((max(self.E, 1), 6), dtype=np.int32)
+        capi.check(capi.lib().eolc_cd_edge_table(self._h, capi.iptr(out)))
+        return out[:self.E].copy()
+
+    def run(self, x, obs, point_eol_flag, remap, capacity=None, x_is_device_ptr=False, n_scenes=1):
+        if capacity is None:
+            capacity = n_scenes * (self.N + 64) + 4096
+        nP, nB = obs.pxyz.shape[0], obs.box_whd.shape[0]
+        L = capi.lib()
+        while True:
+            out = np.empty(capacity, dtype=CONTACT_DTYPE)
+            if x_is_device_ptr:
+                off = np.zeros(n_scenes + 1, dtype=np.int32)
+                rc = L.eolc_cd_run_batched_dev(self._h, int(n_scenes), x, nP, capi.dptr(obs.pxyz), capi.dptr(obs.pnorms), nB,
+                                               capi.dptr(obs.box_whd), capi.dptr(obs.box_E), int(point_eol_flag), int(remap),
+                                               out.ctypes.data_as(capi.c_vp), capacity, capi.iptr(off))
+                n = int(off[-1])
+            else:
+                xx = capi.f64(x).reshape(-1)
+                if xx.size != 3 * self.N:
+                    raise capi.EolcError("x must hold 3N doubles")
+                nn = ctypes.c_int32(0)
+                rc = L.eolc_cd_run(self._h, capi.dptr(xx), nP, capi.dptr(obs.pxyz), capi.dptr(obs.pnorms), nB,
+                                   capi.dptr(obs.box_whd), capi.dptr(obs.box_E), int(point_eol_flag), int(remap),
+                                   out.ctypes.data_as(capi.c_vp), capacity, ctypes.byref(nn))
+                n, off = nn.value, None
+            if rc == -3:       # EOLC_ERR_CAPACITY: n holds the required size
+                capacity = n
+                continue
+            capi.check(rc)
+            return (out[:n], off) if x_is_device_ptr else out[:n]
+
+    def stats(self):
+        pt, ln = ctypes.c_int64(), ctypes.c_int32()
+        capi.check(capi.lib().eolc_cd_last_stats(self._h, ctypes.byref(pt), ctypes.byref(ln)))
+        return pt.value, ln.value
+
+    def close(self):
+        if self._h:
+            capi.lib().eolc_cd_plan_destroy(self._h)
+            self._h = capi.c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_PLANS = {}
+
+
+def _plan_for(ctx, mesh, obs):
+    fn = capi.i32(mesh["face_nodes"]).reshape(-1, 3)
+    N = np.asarray(mesh["x"]).reshape(-1, 3).shape[0]
+    key = (id(ctx), N, fn.shape[0], hash(fn.tobytes()), obs.cdthreshold)
+    p = _PLANS.get(key)
+    if p is None:
+        if len(_PLANS) > 8:
+            _PLANS.clear()
+        p = _PLANS[key] = CollisionPlan(ctx, N, fn, obs.cdthreshold)
+    return p
+
+
+def CD(ctx, mesh, obs, cls):
+    """void CD(const Mesh&, shared_ptr<Obstacles>, vector<shared_ptr<btc::Collision>>& cls) — Collisions.cpp:11-53.
+    Appends to the list `cls` (records of dtype CONTACT_DTYPE)."""
+    cls.extend(_plan_for(ctx, mesh, obs).run(mesh["x"], obs, point_eol_flag=1, remap=1))
+
+
+def CD2(ctx, mesh, obs, cls):
+    """void CD2(...) — Collisions.cpp:55-78."""
+    cls.extend(_plan_for(ctx, mesh, obs).run(mesh["x"], obs, point_eol_flag=0, remap=0))

@@ -1,0 +1,901 @@
+// cd.cu — collision narrow phase on the GPU (include/eolc.h, "CD / CD2" section).
+//
+// Replaces /root/reference/src/Collisions.cpp:11-78 (CD, CD2) and src/boxTriCollision.cpp:617-1063
+// (boxTriCollision), :1067-1224 (pointTriCollision), :141-231 (createEdges), raytri.cpp:260-316.
+//
+// Structure of one run (S scenes, P obstacle points, B boxes):
+//   cd_prepare      perturbed verts (:648-659), perturbed + unperturbed face normals (:233-247, :193-214),
+//                   per-scene cloth AABB (:425-433)
+//   "sections"      every ordered piece of the reference's contact list is a section of items:
+//                     PE  cloth vertex  vs obstacle points   (pointTriCollision :1099-1139, CD only)
+//                     PT  obstacle point vs cloth triangles  (:1142-1213)  warp-cooperative lexicographic argmin
+//                     A   cloth vertex  vs 24 box triangles  (:675-764)
+//                     Bc  box corner    vs cloth triangles   (:771-845)    warp-cooperative lexicographic argmin
+//                     C   cloth edge    vs 12 box edges      (:849-1017)
+//                   pass 1 stores a small per-item result (winner id / 12-bit hit mask) and per-256-item counts,
+//                   one exclusive scan over the counts gives every item's slot in the FINAL list order
+//                   (scene, PE, PT, box0{A,Bc,C}, box1{...}), pass 2 re-derives the records of the hits and writes
+//                   them to their slots (ballot/popc + warp-shuffle prefix inside a block). No atomics.
+//   host post-pass  step (D) corner de-duplication (:1022-1052, literal forward swap-delete) and the CD index
+//                   remap (Collisions.cpp:39-48) run over the (small) contact list while it is copied out.
+//
+// O(1) obstacle setup (createBox: 14 verts, 24 face normals, vertex normals with acos, :400-420) is evaluated on
+// the host per call with libm, exactly as the reference does, and shipped to the device as a constant table.
+#include "common.h"
+#include "cd_math.cuh"
+#include <algorithm>
+#include <random>
+
+using namespace eolc;
+using namespace cdm;
+
+namespace {
+
+// ---- static box tables (data of boxTriCollision.cpp:289-398) --------------------------------------
+__constant__ int c_faces1[24][3] = {{0, 8, 2},  {1, 8, 0},  {3, 8, 1},  {2, 8, 3},  {4, 10, 0}, {5, 10, 4}, {1, 10, 5}, {0, 10, 1},
+                                    {6, 9, 4},  {7, 9, 6},  {5, 9, 7},  {4, 9, 5},  {2, 11, 6}, {3, 11, 2}, {7, 11, 3}, {6, 11, 7},
+                                    {1, 13, 3}, {5, 13, 1}, {7, 13, 5}, {3, 13, 7}, {0, 12, 4}, {2, 12, 0}, {6, 12, 2}, {4, 12, 6}};
+__constant__ int c_edgeVerts1[12][4] = {{0, 1, 8, 10}, {2, 0, 8, 12}, {1, 3, 8, 13}, {3, 2, 8, 11}, {0, 4, 10, 12}, {5, 1, 10, 13},
+                                        {4, 5, 10, 9}, {6, 2, 11, 12}, {4, 6, 9, 12}, {3, 7, 11, 13}, {7, 5, 9, 13}, {6, 7, 9, 11}};
+__constant__ int c_vertEdges1[8][3] = {{0, 1, 4}, {0, 2, 5}, {1, 3, 7}, {2, 3, 9}, {4, 6, 8}, {5, 6, 10}, {7, 8, 11}, {9, 10, 11}};
+__constant__ int c_edgeFaces1[12][2] = {{1, 7}, {0, 21}, {2, 16}, {3, 13}, {4, 20}, {6, 17}, {5, 11}, {12, 22}, {8, 23}, {14, 19}, {10, 18}, {9, 15}};
+
+const double h_unitVerts[14][3] = {{-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1},
+                                   {1, 1, 1},    {-1, 0, 0},  {1, 0, 0},   {0, -1, 0}, {0, 1, 0},   {0, 0, -1}, {0, 0, 1}};
+const int h_faces1[24][3] = {{0, 8, 2},  {1, 8, 0},  {3, 8, 1},  {2, 8, 3},  {4, 10, 0}, {5, 10, 4}, {1, 10, 5}, {0, 10, 1},
+                             {6, 9, 4},  {7, 9, 6},  {5, 9, 7},  {4, 9, 5},  {2, 11, 6}, {3, 11, 2}, {7, 11, 3}, {6, 11, 7},
+                             {1, 13, 3}, {5, 13, 1}, {7, 13, 5}, {3, 13, 7}, {0, 12, 4}, {2, 12, 0}, {6, 12, 2}, {4, 12, 6}};
+const int h_edgeVerts1[12][4] = {{0, 1, 8, 10}, {2, 0, 8, 12}, {1, 3, 8, 13}, {3, 2, 8, 11}, {0, 4, 10, 12}, {5, 1, 10, 13},
+                                 {4, 5, 10, 9}, {6, 2, 11, 12}, {4, 6, 9, 12}, {3, 7, 11, 13}, {7, 5, 9, 13}, {6, 7, 9, 11}};
+const int h_edgeFaces1[12][2] = {{1, 7}, {0, 21}, {2, 16}, {3, 13}, {4, 20}, {6, 17}, {5, 11}, {12, 22}, {8, 23}, {14, 19}, {10, 18}, {9, 15}};
+
+// Per-box constants produced by createBox (:400-420) and hoisted loop invariants of :849-915.
+struct BoxData {
+    double verts1[14][3];
+    double faceNors1[24][3];
+    double vertNors1[14][3];
+    double aabbB1[6];
+    double aabbF1[24][6];
+    double edgeAngle[12];    // e1->angle
+    double angleCD[12];      // acos(n1c.n1d)  (:906)
+    double dx1[12][3], len1[12], tan1[12][3], nor1e[12][3];   // x1b-x1a, |dx1|, dx1/len1, normalized(n1c+n1d)
+};
+
+V3 hcol(const double (*M)[3], int i) { return mk(M[i][0], M[i][1], M[i][2]); }
+
+// createBox + createFaceNormals + createVertNormals on the host (libm acos, as the reference)
+void make_box(BoxData &B, const double *whd, const double *E1) {
+    double S[4] = {0.5 * whd[0], 0.5 * whd[1], 0.5 * whd[2], 1.0};
+    double E[16];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) {
+            double acc = E1[0 * 4 + r] * (c == 0 ? S[0] : 0.0);
+            acc = acc + E1[1 * 4 + r] * (c == 1 ? S[1] : 0.0);
+            acc = acc + E1[2 * 4 + r] * (c == 2 ? S[2] : 0.0);
+            acc = acc + E1[3 * 4 + r] * (c == 3 ? S[3] : 0.0);
+            E[c * 4 + r] = acc;
+        }
+    for (int i = 0; i < 14; ++i)
+        for (int r = 0; r < 3; ++r) {
+            double acc = E[0 * 4 + r] * h_unitVerts[i][0];
+            acc = acc + E[1 * 4 + r] * h_unitVerts[i][1];
+            acc = acc + E[2 * 4 + r] * h_unitVerts[i][2];
+            acc = acc + E[3 * 4 + r] * 1.0;
+            B.verts1[i][r] = acc;
+        }
+    double vn[14][3] = {}, angles[14] = {};
+    for (int k = 0; k < 24; ++k) {
+        const int *f = h_faces1[k];
+        V3 xa = hcol(B.verts1, f[0]), xb = hcol(B.verts1, f[1]), xc = hcol(B.verts1, f[2]);
+        V3 dba = xb - xa, dcb = xc - xb, dac = xa - xc;
+        V3 nor = normalized(cross(dba, neg(dac)));
+        B.faceNors1[k][0] = nor.x; B.faceNors1[k][1] = nor.y; B.faceNors1[k][2] = nor.z;
+        dba = normalized(dba); dcb = normalized(dcb); dac = normalized(dac);
+        double a1 = acos(dot(dba, neg(dac))), a2 = acos(dot(dcb, neg(dba))), a3 = acos(dot(dac, neg(dcb)));
+        double an[3] = {a1, a2, a3};
+        for (int v = 0; v < 3; ++v) {
+            vn[f[v]][0] += an[v] * nor.x; vn[f[v]][1] += an[v] * nor.y; vn[f[v]][2] += an[v] * nor.z;
+            angles[f[v]] += an[v];
+        }
+        for (int i = 0; i < 3; ++i) {   // build_AABB_F :436-452
+            double a = B.verts1[f[0]][i], b = B.verts1[f[1]][i], c = B.verts1[f[2]][i];
+            B.aabbF1[k][i] = std::min(c, std::min(b, a));
+            B.aabbF1[k][i + 3] = std::max(c, std::max(b, a));
+        }
+    }
+    for (int k = 0; k < 14; ++k) {
+        V3 nor = normalized(divs(mk(vn[k][0], vn[k][1], vn[k][2]), angles[k]));
+        B.vertNors1[k][0] = nor.x; B.vertNors1[k][1] = nor.y; B.vertNors1[k][2] = nor.z;
+    }
+    for (int r = 0; r < 3; ++r) {
+        double mn = B.verts1[0][r], mx = B.verts1[0][r];
+        for (int i = 1; i < 14; ++i) { mn = std::min(mn, B.verts1[i][r]); mx = std::max(mx, B.verts1[i][r]); }
+        B.aabbB1[r] = mn; B.aabbB1[3 + r] = mx;
+    }
+    for (int k = 0; k < 12; ++k) {
+        V3 n1c = hcol(B.faceNors1, h_edgeFaces1[k][0]), n1d = hcol(B.faceNors1, h_edgeFaces1[k][1]);
+        B.edgeAngle[k] = acos(dot(n1c, n1d));
+        B.angleCD[k] = acos(dot(n1c, n1d));
+        V3 x1a = hcol(B.verts1, h_edgeVerts1[k][0]), x1b = hcol(B.verts1, h_edgeVerts1[k][1]);
+        V3 dx1 = x1b - x1a;
+        double len1 = norm(dx1);
+        V3 tan1 = divs(dx1, len1);
+        V3 nor1 = normalized(n1c + n1d);
+        B.dx1[k][0] = dx1.x; B.dx1[k][1] = dx1.y; B.dx1[k][2] = dx1.z;
+        B.len1[k] = len1;
+        B.tan1[k][0] = tan1.x; B.tan1[k][1] = tan1.y; B.tan1[k][2] = tan1.z;
+        B.nor1e[k][0] = nor1.x; B.nor1e[k][1] = nor1.y; B.nor1e[k][2] = nor1.z;
+    }
+}
+
+// ---- device helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ V3 dcol(const double *M, int i) { return mk(M[3 * (size_t)i], M[3 * (size_t)i + 1], M[3 * (size_t)i + 2]); }
+__device__ __forceinline__ V3 bcol(const double (*M)[3], int i) { return mk(M[i][0], M[i][1], M[i][2]); }
+
+__device__ __forceinline__ void zero_contact(eolc_contact &c) {
+    c.dist = 0;
+    for (int i = 0; i < 3; ++i) {
+        c.nor1[i] = c.nor2[i] = c.pos1[i] = c.pos2[i] = c.pos1_[i] = c.weights1[i] = c.weights2[i] = c.edgeDir[i] = 0.0;
+        c.verts1[i] = c.verts2[i] = 0; c.edge1[i] = -1;
+    }
+    c.count1 = c.count2 = 0; c.tri1 = c.tri2 = -1; c.n_edge1 = 0; c.edge2 = -1; c.reserved = 0;
+}
+// step (E): pos1_ = pos1 - snapDepth*nor1 (:1057-1060, :1218-1221)
+__device__ __forceinline__ void finish_contact(eolc_contact &c, double threshold) {
+    double snap = mul(0.1, threshold);
+    for (int i = 0; i < 3; ++i) c.pos1_[i] = sub(c.pos1[i], mul(snap, c.nor1[i]));
+}
+
+// ---- prepare -------------------------------------------------------------------------------------
+__global__ void k_perturb(int N, const double *__restrict__ x, const double *__restrict__ r, double *__restrict__ xp, size_t stride) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * (size_t)N) return;
+    size_t o = blockIdx.y * stride;
+    xp[o + i] = add(x[o + i], r[i]);   // verts2.block<3,1>(0,i2) += r
+}
+
+// face normals of the perturbed verts (createFaceNormals :233-247: dba.cross(-dac)) and of the unperturbed verts
+// (createEdges :193-214: (xb-xa).cross(xc-xa)); -(xa-xc) == xc-xa exactly, so both use the same expression.
+__global__ void k_face_normals(int F, const int32_t *__restrict__ fn, const double *__restrict__ x, const double *__restrict__ xp,
+                               double *__restrict__ fn0, double *__restrict__ fnp, size_t xstride, size_t fstride) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F) return;
+    size_t xo = blockIdx.y * xstride, fo = blockIdx.y * fstride;
+    int a = fn[3 * k], b = fn[3 * k + 1], c = fn[3 * k + 2];
+    {
+        V3 xa = dcol(x + xo, a), xb = dcol(x + xo, b), xc = dcol(x + xo, c);
+        st(fn0 + fo + 3 * (size_t)k, normalized(cross(xb - xa, xc - xa)));
+    }
+    {
+        V3 xa = dcol(xp + xo, a), xb = dcol(xp + xo, b), xc = dcol(xp + xo, c);
+        st(fnp + fo + 3 * (size_t)k, normalized(cross(xb - xa, neg(xa - xc))));
+    }
+}
+
+// per-scene AABB of the perturbed verts (build_AABB_B :425-433); one block per scene, min/max are order independent
+__global__ void __launch_bounds__(1024) k_aabb(int N, const double *__restrict__ xp, double *__restrict__ aabb, size_t stride) {
+    const double *v = xp + blockIdx.x * stride;
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+        for (int r = 0; r < 3; ++r) { double q = v[3 * (size_t)i + r]; mn[r] = fmin(mn[r], q); mx[r] = fmax(mx[r], q); }
+    __shared__ double s[6][32];
+    for (int r = 0; r < 3; ++r)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[r] = fmin(mn[r], __shfl_xor_sync(0xffffffffu, mn[r], o));
+            mx[r] = fmax(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+        }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) for (int r = 0; r < 3; ++r) { s[r][w] = mn[r]; s[3 + r][w] = mx[r]; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = blockDim.x >> 5;
+        for (int r = 0; r < 3; ++r) {
+            double a = l < nw ? s[r][l] : INFINITY, b = l < nw ? s[3 + r][l] : -INFINITY;
+            for (int o = 16; o > 0; o >>= 1) { a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+            if (l == 0) { aabb[6 * blockIdx.x + r] = a; aabb[6 * blockIdx.x + 3 + r] = b; }
+        }
+    }
+}
+
+// ---- section bookkeeping ---------------------------------------------------------------------------
+// info[] holds one int per item, sections are padded to 256 items; blocksum[] one count per 256 items.
+__device__ __forceinline__ void block_count_store(int cnt, int *blocksum, size_t blk) {
+    // 256 threads: warp reduce + smem
+    __shared__ int s[8];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 8; ++i) t += s[i]; blocksum[blk] = t; }
+}
+// exclusive prefix of cnt over the 256 threads of the block (thread order), warp-shuffle scan
+__device__ __forceinline__ int block_excl_prefix(int cnt) {
+    __shared__ int s[8];
+    int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
+    if (l == 31) s[w] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int i = 0; i < w; ++i) base += s[i];
+    return base + inc - cnt;
+}
+
+// single-block exclusive scan of blocksum[0..n) -> blockoff[0..n], blockoff[n] = total
+__global__ void __launch_bounds__(1024) k_scan(size_t n, const int *__restrict__ in, int *__restrict__ out) {
+    __shared__ int s[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (size_t base = 0; base < n; base += 1024) {
+        size_t i = base + threadIdx.x;
+        int v = i < n ? in[i] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
+        if (l == 31) s[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int t = s[l];
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, t, o); if (l >= o) t += u; }
+            s[l] = t;
+        }
+        __syncthreads();
+        int wbase = w > 0 ? s[w - 1] : 0;
+        int c = carry;
+        if (i < n) out[i] = c + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + wbase + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+// ---- section A: cloth vertex vs box (boxTriCollision.cpp:675-764) -----------------------------------
+// returns winning j1 (or -1) and, if rec != NULL, fills the record
+__device__ int test_vertex_box(int i2, int F, V3 x2, const double *__restrict__ fnp, const BoxData &B, double threshold, eolc_contact *rec) {
+    if (!check_aabb_point(x2, B.aabbB1)) return -1;
+    for (int j1 = 0; j1 < 24; ++j1) {
+        V3 x1a = bcol(B.verts1, c_faces1[j1][0]);
+        if (dot(bcol(B.faceNors1, j1), x2 - x1a) > 0.0) return -1;
+    }
+    int best = -1;
+    double bestd = 0.0;
+    const double lim = mul(5.0, threshold);
+    for (int j1 = 0; j1 < 24; ++j1) {
+        V3 x1a = bcol(B.verts1, c_faces1[j1][0]), x1b = bcol(B.verts1, c_faces1[j1][1]), x1c = bcol(B.verts1, c_faces1[j1][2]);
+        V3 nor1 = bcol(B.faceNors1, j1);
+        double proj = dot(nor1, x2 - x1a);
+        if (proj > 0.0) continue;
+        V3 x1 = x2 - scale(proj, nor1);
+        double dist = norm(x2 - x1);
+        if (dist > lim) continue;
+        double u, v;
+        barycentric(u, v, x1a, x1b, x1c, x1);
+        double w = sub(sub(1.0, u), v);
+        if (u < 0.0 || 1.0 < u || v < 0.0 || 1.0 < v || w < 0.0 || 1.0 < w) continue;
+        if (best < 0 || dist < bestd) {
+            best = j1; bestd = dist;
+            if (rec) {
+                // faceNors2.col(i2): indexed with the VERTEX id (reference quirk, :731); out of range -> zero
+                V3 nor2 = i2 < F ? dcol(fnp, i2) : mk(0, 0, 0);
+                if (dot(nor2, nor1) < 0.0) nor2 = neg(nor2);
+                zero_contact(*rec);
+                rec->dist = dist;
+                st(rec->nor1, nor1); st(rec->nor2, nor2); st(rec->pos1, x1); st(rec->pos2, x2);
+                rec->count1 = 3; rec->count2 = 1;
+                rec->verts1[0] = c_faces1[j1][0]; rec->verts1[1] = c_faces1[j1][1]; rec->verts1[2] = c_faces1[j1][2];
+                rec->verts2[0] = i2; rec->verts2[1] = -1; rec->verts2[2] = -1;
+                rec->weights1[0] = u; rec->weights1[1] = v; rec->weights1[2] = w;
+                rec->weights2[0] = 1.0; rec->weights2[1] = 0.0; rec->weights2[2] = 0.0;
+                rec->tri1 = j1; rec->tri2 = -1;
+            }
+        }
+    }
+    return best;
+}
+
+// grid: (ceil(N/256), S*B)
+__global__ void __launch_bounds__(256) k_A_count(int N, int F, int nB, const double *__restrict__ xp, const double *__restrict__ fnp,
+                                                 const BoxData *__restrict__ boxes, double threshold, int *__restrict__ info,
+                                                 int *__restrict__ blocksum, size_t xstride, size_t fstride,
+                                                 size_t scene_items, size_t box_items, size_t secA_off) {
+    int s = blockIdx.y / nB, b = blockIdx.y % nB;
+    int i2 = blockIdx.x * 256 + threadIdx.x;
+    int j1 = -1;
+    if (i2 < N) j1 = test_vertex_box(i2, F, dcol(xp + s * xstride, i2), fnp + s * fstride, boxes[b], threshold, nullptr);
+    size_t item0 = s * scene_items + secA_off + b * box_items;
+    info[item0 + blockIdx.x * 256 + threadIdx.x] = j1;
+    block_count_store(j1 >= 0 ? 1 : 0, blocksum, item0 / 256 + blockIdx.x);
+}
+__global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, const double *__restrict__ xp, const double *__restrict__ fnp,
+                                                 const BoxData *__restrict__ boxes, double threshold, const int *__restrict__ info,
+                                                 const int *__restrict__ blockoff, eolc_contact *__restrict__ out, size_t xstride,
+                                                 size_t fstride, size_t scene_items, size_t box_items, size_t secA_off) {
+    int s = blockIdx.y / nB, b = blockIdx.y % nB;
+    size_t item0 = s * scene_items + secA_off + b * box_items;
+    int i2 = blockIdx.x * 256 + threadIdx.x;
+    int j1 = info[item0 + i2];
+    int pre = block_excl_prefix(j1 >= 0 ? 1 : 0);
+    if (j1 < 0) return;
+    eolc_contact rec;
+    test_vertex_box(i2, F, dcol(xp + s * xstride, i2), fnp + s * fstride, boxes[b], threshold, &rec);
+    finish_contact(rec, threshold);
+    out[blockoff[item0 / 256 + blockIdx.x] + pre] = rec;
+}
+
+// ---- sections Bc / PT: point (box corner or obstacle point) vs all cloth triangles -------------------
+// (:771-845 and :1142-1213): strict-min over j2 ascending == lexicographic min of (dist, j2)
+struct Cand { double dist; int j2; };
+__device__ __forceinline__ bool better(double d, int j, const Cand &c) { return c.j2 < 0 || d < c.dist || (d == c.dist && j < c.j2); }
+
+__device__ __forceinline__ bool test_point_tri(V3 x1, V3 nor1, int j2, const int32_t *__restrict__ fn, const double *__restrict__ xp,
+                                               const double *__restrict__ fnp, double lim, double &dist, V3 &nor2, V3 &x2,
+                                               double &u, double &v, double &w) {
+    V3 x2a = dcol(xp, fn[3 * (size_t)j2]), x2b = dcol(xp, fn[3 * (size_t)j2 + 1]), x2c = dcol(xp, fn[3 * (size_t)j2 + 2]);
+    nor2 = dcol(fnp, j2);
+    if (dot(nor1, nor2) < 0.0) nor2 = neg(nor2);
+    double proj = dot(x1 - x2a, nor2);
+    if (proj < 0.0) return false;
+    x2 = x1 - scale(proj, nor2);
+    dist = norm(x2 - x1);
+    if (dist > lim) return false;
+    barycentric(u, v, x2a, x2b, x2c, x1);   // the unprojected point is passed (:808)
+    w = sub(sub(1.0, u), v);
+    if (u < 0.0 || 1.0 < u || v < 0.0 || 1.0 < v || w < 0.0 || 1.0 < w) return false;
+    return true;
+}
+
+// which point: box mode (boxes != NULL): point id = blockIdx.y % 8 of box (blockIdx.y / 8) % nB ; point mode: pxyz/pnorms
+// grid: (nchunk, S * npts) ; partial[(s*npts + pt) * nchunk + chunk]
+__global__ void __launch_bounds__(256) k_PT_partial(int F, int npts_per_scene, int nB, const BoxData *__restrict__ boxes,
+                                                    const double *__restrict__ pxyz, const double *__restrict__ pnorms,
+                                                    const int32_t *__restrict__ fn, const double *__restrict__ xp,
+                                                    const double *__restrict__ fnp, const double *__restrict__ aabbB2,
+                                                    double threshold, Cand *__restrict__ partial, size_t xstride, size_t fstride) {
+    int s = blockIdx.y / npts_per_scene, pt = blockIdx.y % npts_per_scene;
+    V3 x1, nor1;
+    if (boxes) { const BoxData &B = boxes[pt / 8]; x1 = bcol(B.verts1, pt % 8); nor1 = bcol(B.vertNors1, pt % 8); }
+    else { x1 = dcol(pxyz, pt); nor1 = dcol(pnorms, pt); }
+    Cand best; best.dist = 0.0; best.j2 = -1;
+    if (check_aabb_point(x1, aabbB2 + 6 * s)) {
+        const double lim = mul(5.0, threshold);
+        const double *xs = xp + s * xstride, *fs = fnp + s * fstride;
+        for (int j2 = blockIdx.x * 256 + threadIdx.x; j2 < F; j2 += gridDim.x * 256) {
+            double dist, u, v, w; V3 nor2, x2;
+            if (test_point_tri(x1, nor1, j2, fn, xs, fs, lim, dist, nor2, x2, u, v, w) && better(dist, j2, best)) { best.dist = dist; best.j2 = j2; }
+        }
+    }
+    // warp-cooperative lexicographic (dist, j2) min
+    for (int o = 16; o > 0; o >>= 1) {
+        double d = __shfl_xor_sync(0xffffffffu, best.dist, o);
+        int j = __shfl_xor_sync(0xffffffffu, best.j2, o);
+        if (j >= 0 && better(d, j, best)) { best.dist = d; best.j2 = j; }
+    }
+    __shared__ Cand sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Cand b0 = sm[0];
+        for (int i = 1; i < 8; ++i) if (sm[i].j2 >= 0 && better(sm[i].dist, sm[i].j2, b0)) b0 = sm[i];
+        partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = b0;
+    }
+}
+// one warp per (scene, point): reduce the partials, store winner j2 in info[], count in blocksum (section <= 256 items)
+// grid: S * nsec blocks of 256 threads; section sec of scene s holds pts_per_sec points (8 per box, or P)
+__global__ void __launch_bounds__(256) k_PT_final(int nchunk, int pts_per_sec, int nsec, const Cand *__restrict__ partial,
+                                                  int *__restrict__ info, int *__restrict__ blocksum, size_t scene_items,
+                                                  size_t sec0_off, size_t sec_stride) {
+    int s = blockIdx.x / nsec, sec = blockIdx.x % nsec;
+    size_t item0 = s * scene_items + sec0_off + sec * sec_stride;
+    int total = 0;
+    for (int base = 0; base < pts_per_sec; base += 256) {
+        int pt = base + threadIdx.x;
+        int j2 = -1;
+        if (pt < pts_per_sec) {
+            const Cand *p = partial + ((size_t)(s * nsec + sec) * pts_per_sec + pt) * nchunk;
+            Cand best; best.dist = 0.0; best.j2 = -1;
+            for (int c = 0; c < nchunk; ++c) if (p[c].j2 >= 0 && better(p[c].dist, p[c].j2, best)) best = p[c];
+            j2 = best.j2;
+        }
+        info[item0 + base + threadIdx.x] = j2;
+        int cnt = j2 >= 0 ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        __shared__ int sm[8];
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 8; ++i) t += sm[i]; blocksum[item0 / 256 + base / 256] = t; total += t; }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) k_PT_write(int F, int pts_per_sec, int nsec, const BoxData *__restrict__ boxes,
+                                                  const double *__restrict__ pxyz, const double *__restrict__ pnorms,
+                                                  const int32_t *__restrict__ fn, const double *__restrict__ xp,
+                                                  const double *__restrict__ fnp, double threshold, const int *__restrict__ info,
+                                                  const int *__restrict__ blockoff, eolc_contact *__restrict__ out, size_t xstride,
+                                                  size_t fstride, size_t scene_items, size_t sec0_off, size_t sec_stride) {
+    int s = blockIdx.y / nsec, sec = blockIdx.y % nsec;
+    size_t item0 = s * scene_items + sec0_off + sec * sec_stride;
+    int pt = blockIdx.x * 256 + threadIdx.x;
+    int j2 = info[item0 + pt];
+    int pre = block_excl_prefix(j2 >= 0 ? 1 : 0);
+    if (j2 < 0) return;
+    V3 x1, nor1;
+    if (boxes) { const BoxData &B = boxes[sec]; x1 = bcol(B.verts1, pt); nor1 = bcol(B.vertNors1, pt); }
+    else { x1 = dcol(pxyz, pt); nor1 = dcol(pnorms, pt); }
+    double dist, u, v, w; V3 nor2, x2;
+    test_point_tri(x1, nor1, j2, fn, xp + s * xstride, fnp + s * fstride, mul(5.0, threshold), dist, nor2, x2, u, v, w);
+    eolc_contact rec;
+    zero_contact(rec);
+    rec.dist = dist;
+    st(rec.nor1, nor1); st(rec.nor2, nor2); st(rec.pos1, x1); st(rec.pos2, x2);
+    rec.count1 = 1; rec.count2 = 3;
+    rec.verts1[0] = pt; rec.verts1[1] = -1; rec.verts1[2] = -1;
+    rec.verts2[0] = fn[3 * (size_t)j2]; rec.verts2[1] = fn[3 * (size_t)j2 + 1]; rec.verts2[2] = fn[3 * (size_t)j2 + 2];
+    rec.weights1[0] = 1.0; rec.weights1[1] = 0.0; rec.weights1[2] = 0.0;
+    rec.weights2[0] = u; rec.weights2[1] = v; rec.weights2[2] = w;
+    if (boxes) { rec.edge1[0] = c_vertEdges1[pt][0]; rec.edge1[1] = c_vertEdges1[pt][1]; rec.edge1[2] = c_vertEdges1[pt][2]; rec.n_edge1 = 3; }
+    rec.tri1 = -1; rec.tri2 = j2;
+    finish_contact(rec, threshold);
+    out[blockoff[item0 / 256 + blockIdx.x] + pre] = rec;
+}
+
+// ---- section PE: cloth vertex vs obstacle points (pointTriCollision :1099-1139, EOL == true) ----------
+__device__ __forceinline__ int test_vertex_points(V3 x2, int P, const double *__restrict__ pxyz, double threshold, double &bestd) {
+    int best = -1;
+    bestd = 0.0;
+    for (int i1 = 0; i1 < P; ++i1) {
+        double dist = norm(x2 - dcol(pxyz, i1));
+        if (dist < threshold && (best < 0 || dist < bestd)) { best = i1; bestd = dist; }
+    }
+    return best;
+}
+__global__ void __launch_bounds__(256) k_PE_count(int N, int P, const double *__restrict__ pxyz, const double *__restrict__ xp,
+                                                  double threshold, int *__restrict__ info, int *__restrict__ blocksum,
+                                                  size_t xstride, size_t scene_items, size_t sec_off) {
+    int s = blockIdx.y;
+    int i2 = blockIdx.x * 256 + threadIdx.x;
+    int i1 = -1;
+    double d;
+    if (i2 < N) i1 = test_vertex_points(dcol(xp + s * xstride, i2), P, pxyz, threshold, d);
+    size_t item0 = s * scene_items + sec_off;
+    info[item0 + i2] = i1;
+    block_count_store(i1 >= 0 ? 1 : 0, blocksum, item0 / 256 + blockIdx.x);
+}
+__global__ void __launch_bounds__(256) k_PE_write(int N, int P, const double *__restrict__ pxyz, const double *__restrict__ pnorms,
+                                                  const double *__restrict__ xp, double threshold, const int *__restrict__ info,
+                                                  const int *__restrict__ blockoff, eolc_contact *__restrict__ out, size_t xstride,
+                                                  size_t scene_items, size_t sec_off) {
+    int s = blockIdx.y;
+    size_t item0 = s * scene_items + sec_off;
+    int i2 = blockIdx.x * 256 + threadIdx.x;
+    int i1 = info[item0 + i2];
+    int pre = block_excl_prefix(i1 >= 0 ? 1 : 0);
+    if (i1 < 0) return;
+    V3 x2 = dcol(xp + s * xstride, i2), x1 = dcol(pxyz, i1), nor1 = dcol(pnorms, i1);
+    eolc_contact rec;
+    zero_contact(rec);
+    rec.dist = norm(x2 - x1);
+    st(rec.nor1, nor1); st(rec.nor2, nor1); st(rec.pos1, x1); st(rec.pos2, x2);
+    rec.count1 = 3; rec.count2 = 1;
+    rec.verts1[0] = i1; rec.verts1[1] = -1; rec.verts1[2] = -1;
+    rec.verts2[0] = i2; rec.verts2[1] = -1; rec.verts2[2] = -1;
+    rec.weights1[0] = 1.0; rec.weights2[0] = 1.0;
+    rec.tri1 = -1; rec.tri2 = -1;
+    finish_contact(rec, threshold);
+    out[blockoff[item0 / 256 + blockIdx.x] + pre] = rec;
+}
+
+// ---- section C: cloth edge vs box edge (boxTriCollision.cpp:849-1017) ----------------------------------
+struct EdgeRec { int32_t v[4]; int32_t f[2]; };
+
+__device__ bool test_edge_edge(int k1, const BoxData &B, V3 x2a, V3 x2b, V3 dx2, double len2, V3 nor2, const double *aabbE2k,
+                               double threshold, eolc_contact *rec, const EdgeRec &e2, int k2) {
+    if (B.edgeAngle[k1] < M_PI / 6.0) return false;   // soft edge
+    if (!check_aabb(B.aabbF1[c_edgeFaces1[k1][0]], aabbE2k) && !check_aabb(B.aabbF1[c_edgeFaces1[k1][1]], aabbE2k)) return false;
+    V3 x1a = bcol(B.verts1, c_edgeVerts1[k1][0]), x1b = bcol(B.verts1, c_edgeVerts1[k1][1]);
+    V3 dx1 = bcol(B.dx1, k1);
+    double len1 = B.len1[k1];
+    V3 tan1 = bcol(B.tan1, k1);
+    const double threshAng = 2.0 * M_PI / 180.0;
+    double angle = acos(dot(tan1, nor2));
+    if (fabs(angle) < threshAng || fabs(sub(M_PI, angle)) < threshAng) return false;
+    angle = acos(dv(dot(tan1, dx2), len2));
+    if (fabs(angle) < threshAng || fabs(sub(M_PI, angle)) < threshAng) return false;
+    V3 nor = normalized(cross(dx1, dx2));
+    V3 x1c = bcol(B.verts1, c_edgeVerts1[k1][2]), x1d = bcol(B.verts1, c_edgeVerts1[k1][3]);
+    V3 n1c = bcol(B.faceNors1, c_edgeFaces1[k1][0]), n1d = bcol(B.faceNors1, c_edgeFaces1[k1][1]);
+    V3 nor1 = bcol(B.nor1e, k1);
+    if (dot(nor, nor1) < 0.0) nor = neg(nor);
+    double angleCD = B.angleCD[k1];
+    double angleCN = acos(dot(n1c, nor));
+    if (angleCD < 0.0) { angleCD = -angleCD; angleCN = -angleCN; }
+    if (angleCN < -threshAng || sub(angleCN, angleCD) > threshAng) return false;
+    double u2c, u2d;
+    int i2c = intersect_square(x2a, dx2, x1a, x1b, x1c, u2c);
+    int i2d = intersect_square(x2a, dx2, x1b, x1a, x1d, u2d);
+    i2c = i2c && (0.0 <= u2c && u2c <= 1.0);
+    i2d = i2d && (0.0 <= u2d && u2d <= 1.0);
+    double u1, u2;
+    lineline(u1, u2, x1a, x1b, x2a, x2b);
+    double thresh1 = dv(mul(1.0, threshold), len1), thresh2 = dv(mul(1.0, threshold), len2);
+    if (u1 < -thresh1 || u1 > add(1.0, thresh1) || u2 < -thresh2 || u2 > add(1.0, thresh2)) return false;
+    V3 x1, x2;
+    if (i2c && i2d) {
+        x1 = scale(sub(1.0, u1), x1a) + scale(u1, x1b);
+        x2 = scale(sub(1.0, u2), x2a) + scale(u2, x2b);
+    } else if (i2c && !i2d) {
+        if (dot(x2a - x1a, n1c) < 0.0) u2 = fmax(0.0, fmin(u2c, u2));
+        else u2 = fmax(u2c, fmin(1.0, u2));
+        x2 = scale(sub(1.0, u2), x2a) + scale(u2, x2b);
+        u1 = linepoint(x1a, x1b, x2);
+        x1 = scale(sub(1.0, u1), x1a) + scale(u1, x1b);
+    } else if (!i2c && i2d) {
+        if (dot(x2a - x1b, n1d) < 0.0) u2 = fmax(0.0, fmin(u2d, u2));
+        else u2 = fmax(u2d, fmin(1.0, u2));
+        x2 = scale(sub(1.0, u2), x2a) + scale(u2, x2b);
+        u1 = linepoint(x1a, x1b, x2);
+        x1 = scale(sub(1.0, u1), x1a) + scale(u1, x1b);
+    } else {
+        return false;
+    }
+    if (u1 < -thresh1 || u1 > add(1.0, thresh1) || u2 < -thresh2 || u2 > add(1.0, thresh2)) return false;
+    V3 dx = x2 - x1;
+    double thresh = mul(2.0, threshold);
+    if (dot(dx, dx) > mul(thresh, thresh)) return false;
+    if (rec) {
+        zero_contact(*rec);
+        rec->dist = norm(dx);
+        st(rec->nor1, nor1); st(rec->nor2, nor); st(rec->pos1, x1); st(rec->pos2, x2);
+        rec->count1 = 2; rec->count2 = 2;
+        rec->verts1[0] = c_edgeVerts1[k1][0]; rec->verts1[1] = c_edgeVerts1[k1][1]; rec->verts1[2] = -1;
+        rec->verts2[0] = e2.v[0]; rec->verts2[1] = e2.v[1]; rec->verts2[2] = -1;
+        rec->weights1[0] = sub(1.0, u1); rec->weights1[1] = u1; rec->weights1[2] = 0.0;
+        rec->weights2[0] = sub(1.0, u2); rec->weights2[1] = u2; rec->weights2[2] = 0.0;
+        rec->edge1[0] = k1; rec->n_edge1 = 1;
+        rec->edge2 = k2;
+        st(rec->edgeDir, tan1);
+    }
+    return true;
+}
+
+// shared per-edge setup (:851-856, build_AABB_E :455-468)
+__device__ __forceinline__ void edge_setup(const EdgeRec &e2, const double *__restrict__ xp, const double *__restrict__ fn0,
+                                           V3 &x2a, V3 &x2b, V3 &dx2, double &len2, V3 &nor2, double *aabbE) {
+    x2a = dcol(xp, e2.v[0]); x2b = dcol(xp, e2.v[1]);
+    dx2 = x2b - x2a;
+    len2 = norm(dx2);
+    V3 n0 = dcol(fn0, e2.f[0]);
+    V3 n1 = e2.f[1] >= 0 ? dcol(fn0, e2.f[1]) : mk(0, 0, 0);   // boundary: normals[1] stays zero (:94-95)
+    nor2 = normalized(n0 + n1);
+    aabbE[0] = fmin(x2b.x, x2a.x); aabbE[1] = fmin(x2b.y, x2a.y); aabbE[2] = fmin(x2b.z, x2a.z);
+    aabbE[3] = fmax(x2b.x, x2a.x); aabbE[4] = fmax(x2b.y, x2a.y); aabbE[5] = fmax(x2b.z, x2a.z);
+}
+
+__global__ void __launch_bounds__(256) k_C_count(int E, int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
+                                                 const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
+                                                 int *__restrict__ info, int *__restrict__ blocksum, size_t xstride, size_t fstride,
+                                                 size_t scene_items, size_t box_items, size_t secC_off) {
+    int s = blockIdx.y / nB, b = blockIdx.y % nB;
+    int k2 = blockIdx.x * 256 + threadIdx.x;
+    int mask = 0;
+    if (k2 < E) {
+        EdgeRec e2 = edges[k2];
+        V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
+        edge_setup(e2, xp + s * xstride, fn0 + s * fstride, x2a, x2b, dx2, len2, nor2, aabbE);
+        const BoxData &B = boxes[b];
+        // whole-box cull first: an edge outside the padded box AABB fails all 24 face-AABB tests
+        if (check_aabb(B.aabbB1, aabbE))
+            for (int k1 = 0; k1 < 12; ++k1)
+                if (test_edge_edge(k1, B, x2a, x2b, dx2, len2, nor2, aabbE, threshold, nullptr, e2, k2)) mask |= 1 << k1;
+    }
+    size_t item0 = s * scene_items + secC_off + b * box_items;
+    info[item0 + k2] = mask;
+    block_count_store(__popc(mask), blocksum, item0 / 256 + blockIdx.x);
+}
+__global__ void __launch_bounds__(256) k_C_write(int E, int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
+                                                 const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
+                                                 const int *__restrict__ info, const int *__restrict__ blockoff,
+                                                 eolc_contact *__restrict__ out, size_t xstride, size_t fstride, size_t scene_items,
+                                                 size_t box_items, size_t secC_off) {
+    int s = blockIdx.y / nB, b = blockIdx.y % nB;
+    size_t item0 = s * scene_items + secC_off + b * box_items;
+    int k2 = blockIdx.x * 256 + threadIdx.x;
+    int mask = info[item0 + k2];
+    int pre = block_excl_prefix(__popc(mask));
+    if (!mask) return;
+    EdgeRec e2 = edges[k2];
+    V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
+    edge_setup(e2, xp + s * xstride, fn0 + s * fstride, x2a, x2b, dx2, len2, nor2, aabbE);
+    eolc_contact *dst = out + blockoff[item0 / 256 + blockIdx.x] + pre;
+    for (int k1 = 0; k1 < 12; ++k1)
+        if (mask & (1 << k1)) {
+            eolc_contact rec;
+            test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, aabbE, threshold, &rec, e2, k2);
+            finish_contact(rec, threshold);
+            *dst++ = rec;
+        }
+}
+
+inline size_t pad256(size_t n) { return (n + 255) / 256 * 256; }
+
+}  // namespace
+
+struct eolc_cd_plan {
+    eolc_ctx *ctx = nullptr;
+    int32_t N = 0, F = 0, E = 0;
+    double threshold = 0;
+    std::vector<EdgeRec> h_edges;
+    DevBuf<int32_t> d_fn;
+    DevBuf<EdgeRec> d_edges;
+    DevBuf<double> d_r;                 // perturbation table, 3N
+    // per-run buffers
+    DevBuf<double> d_x, d_xp, d_fn0, d_fnp, d_aabb, d_pxyz, d_pnorms;
+    DevBuf<BoxData> d_boxes;
+    DevBuf<int> d_info, d_blocksum, d_blockoff;
+    DevBuf<Cand> d_partial;
+    DevBuf<eolc_contact> d_out;
+    PinnedBuf<eolc_contact> p_out;
+    PinnedBuf<int> p_blockoff;
+    PinnedBuf<double> p_x;
+    int64_t last_pair_tests = 0;
+    int32_t last_launches = 0;
+};
+
+extern "C" {
+
+int eolc_cd_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face_nodes, double threshold, eolc_cd_plan **out) {
+    EOLC_REQUIRE(ctx && out, "ctx/out is NULL");
+    *out = nullptr;
+    EOLC_REQUIRE(N >= 0 && F >= 0 && (F == 0 || face_nodes), "bad arguments");
+    for (int64_t i = 0; i < 3 * (int64_t)F; ++i) EOLC_REQUIRE(face_nodes[i] >= 0 && face_nodes[i] < N, "face node index out of range");
+    EOLC_CUDA(cudaSetDevice(ctx->device));
+    eolc_cd_plan *P = new eolc_cd_plan;
+    P->ctx = ctx; P->N = N; P->F = F; P->threshold = threshold;
+    // createEdges (:141-231) with an int64 key: stable sort of the 3F half-edges by (max+1)*(3F+1) + (min+1)
+    {
+        struct HE { int64_t key; int32_t face; int8_t i; };
+        const int64_t n = 3 * (int64_t)F;
+        std::vector<HE> tmp((size_t)n);
+        for (int32_t k = 0; k < F; ++k)
+            for (int i = 0; i < 3; ++i) {
+                int32_t a = face_nodes[3 * (size_t)k + i], b = face_nodes[3 * (size_t)k + (i + 1) % 3];
+                int64_t kmin = std::min(a, b) + 1, kmax = std::max(a, b) + 1;
+                tmp[3 * (size_t)k + i] = {kmin + (n + 1) * kmax, k, (int8_t)i};
+            }
+        std::stable_sort(tmp.begin(), tmp.end(), [](const HE &a, const HE &b) { return a.key < b.key; });
+        int64_t k = 0;
+        while (k < n) {
+            const HE &h0 = tmp[k];
+            const int32_t *f0 = face_nodes + 3 * (size_t)h0.face;
+            EdgeRec e;
+            e.v[0] = f0[h0.i]; e.v[1] = f0[(h0.i + 1) % 3]; e.v[2] = f0[(h0.i + 2) % 3];
+            e.f[0] = h0.face;
+            if (k < n - 1 && tmp[k].key == tmp[k + 1].key) {
+                const HE &h1 = tmp[k + 1];
+                e.v[3] = face_nodes[3 * (size_t)h1.face + (h1.i + 2) % 3];
+                e.f[1] = h1.face;
+                k += 2;
+            } else {
+                e.v[3] = -1; e.f[1] = -1;
+                k += 1;
+            }
+            P->h_edges.push_back(e);
+        }
+        P->E = (int32_t)P->h_edges.size();
+    }
+    // perturbation table (:648-659): libstdc++ mt19937 seed 1 + uniform_real_distribution(-1,1), r = dis*thr*1e-3
+    std::vector<double> r(3 * (size_t)N);
+    {
+        std::mt19937 gen;
+        std::uniform_real_distribution<> dis(-1.0, 1.0);
+        gen.seed(1);
+        for (size_t i = 0; i < r.size(); ++i) r[i] = dis(gen) * threshold * 1e-3;
+    }
+    cudaStream_t st = ctx->stream;
+    std::vector<int32_t> fnv(face_nodes, face_nodes + 3 * (size_t)F);
+    cudaError_t ce = P->d_fn.upload(fnv, st);
+    if (ce == cudaSuccess) ce = P->d_edges.upload(P->h_edges, st);
+    if (ce == cudaSuccess) ce = P->d_r.upload(r, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { delete P; set_error("cd plan upload failed: %s", cudaGetErrorString(ce)); return EOLC_ERR_CUDA; }
+    *out = P;
+    return EOLC_OK;
+}
+
+void eolc_cd_plan_destroy(eolc_cd_plan *plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->ctx->device);
+    delete plan;
+}
+
+int eolc_cd_edge_count(const eolc_cd_plan *plan) { return plan ? plan->E : 0; }
+
+int eolc_cd_edge_table(const eolc_cd_plan *plan, int32_t *out6E) {
+    EOLC_REQUIRE(plan && out6E, "NULL argument");
+    for (int32_t k = 0; k < plan->E; ++k) {
+        for (int i = 0; i < 4; ++i) out6E[6 * (size_t)k + i] = plan->h_edges[k].v[i];
+        out6E[6 * (size_t)k + 4] = plan->h_edges[k].f[0]; out6E[6 * (size_t)k + 5] = plan->h_edges[k].f[1];
+    }
+    return EOLC_OK;
+}
+
+int eolc_cd_last_stats(const eolc_cd_plan *plan, int64_t *pair_tests, int32_t *launches) {
+    EOLC_REQUIRE(plan, "plan is NULL");
+    if (pair_tests) *pair_tests = plan->last_pair_tests;
+    if (launches) *launches = plan->last_launches;
+    return EOLC_OK;
+}
+
+int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32_t n_points, const double *pxyz,
+                            const double *pnorms, int32_t n_boxes, const double *box_whd, const double *box_E,
+                            int point_eol_flag, int remap_box_indices, eolc_contact *out, int32_t capacity,
+                            int32_t *scene_offset) {
+    EOLC_REQUIRE(plan && scene_offset, "NULL argument");
+    eolc_cd_plan *P = plan;
+    EOLC_REQUIRE(S >= 1 && n_points >= 0 && n_boxes >= 0 && capacity >= 0, "bad sizes");
+    EOLC_REQUIRE(P->N == 0 || x_dev, "x_dev is NULL");
+    EOLC_REQUIRE(n_points == 0 || (pxyz && pnorms), "pxyz/pnorms is NULL");
+    EOLC_REQUIRE(n_boxes == 0 || (box_whd && box_E), "box_whd/box_E is NULL");
+    EOLC_REQUIRE(capacity == 0 || out, "out is NULL");
+    EOLC_REQUIRE((int64_t)S * std::max(n_boxes, 1) <= 65535 && (int64_t)S * std::max(8 * n_boxes, n_points) <= 65535,
+                 "too many scenes*boxes for one launch; split the batch");
+    EOLC_CUDA(cudaSetDevice(P->ctx->device));
+    cudaStream_t st = P->ctx->stream;
+    const int N = P->N, F = P->F, E = P->E, nB = n_boxes, nP = n_points;
+    const double thr = P->threshold;
+    int launches = 0;
+    // ---- item layout of one scene: [PE: pad(N)] [PT: pad(P)] then per box [A: pad(N)] [Bc: 256] [C: pad(E)]
+    const bool doPE = point_eol_flag && nP > 0;   // with no points the PE loop emits nothing
+    const size_t secPE = 0, nPE = doPE ? pad256(N) : 0;
+    const size_t secPT = secPE + nPE, nPT = nP > 0 ? pad256(nP) : 0;
+    const size_t secBox = secPT + nPT;
+    const size_t nA = pad256(N), nBc = 256, nC = pad256(E);
+    const size_t box_items = nA + nBc + nC;
+    const size_t scene_items = secBox + (size_t)nB * box_items;
+    const size_t total_items = scene_items * S;
+    const size_t nblocks = total_items / 256;
+    for (int s = 0; s <= S; ++s) scene_offset[s] = 0;
+    if (total_items == 0 || N == 0) { P->last_pair_tests = 0; P->last_launches = 0; return EOLC_OK; }
+    EOLC_REQUIRE(nblocks < ((size_t)1 << 31), "batch too large");
+
+    // ---- constants to the device
+    std::vector<BoxData> hb((size_t)nB);
+    for (int b = 0; b < nB; ++b) make_box(hb[b], box_whd + 3 * b, box_E + 16 * b);
+    EOLC_CUDA(P->d_boxes.ensure(std::max(nB, 1)));
+    if (nB) EOLC_CUDA(cudaMemcpyAsync(P->d_boxes.p, hb.data(), sizeof(BoxData) * nB, cudaMemcpyHostToDevice, st));
+    EOLC_CUDA(P->d_pxyz.ensure(3 * (size_t)std::max(nP, 1))); EOLC_CUDA(P->d_pnorms.ensure(3 * (size_t)std::max(nP, 1)));
+    if (nP) {
+        EOLC_CUDA(cudaMemcpyAsync(P->d_pxyz.p, pxyz, sizeof(double) * 3 * nP, cudaMemcpyHostToDevice, st));
+        EOLC_CUDA(cudaMemcpyAsync(P->d_pnorms.p, pnorms, sizeof(double) * 3 * nP, cudaMemcpyHostToDevice, st));
+    }
+    const size_t xs = 3 * (size_t)N, fs = 3 * (size_t)F;
+    EOLC_CUDA(P->d_xp.ensure(xs * S)); EOLC_CUDA(P->d_fn0.ensure(std::max<size_t>(fs * S, 1))); EOLC_CUDA(P->d_fnp.ensure(std::max<size_t>(fs * S, 1)));
+    EOLC_CUDA(P->d_aabb.ensure(6 * (size_t)S));
+    EOLC_CUDA(P->d_info.ensure(total_items)); EOLC_CUDA(P->d_blocksum.ensure(nblocks)); EOLC_CUDA(P->d_blockoff.ensure(nblocks + 1));
+
+    // ---- prepare
+    k_perturb<<<dim3((unsigned)((xs + 255) / 256), S), 256, 0, st>>>(N, x_dev, P->d_r.p, P->d_xp.p, xs); ++launches;
+    if (F) { k_face_normals<<<dim3((F + 255) / 256, S), 256, 0, st>>>(F, P->d_fn.p, x_dev, P->d_xp.p, P->d_fn0.p, P->d_fnp.p, xs, fs); ++launches; }
+    k_aabb<<<S, 1024, 0, st>>>(N, P->d_xp.p, P->d_aabb.p, xs); ++launches;
+
+    // ---- pass 1
+    const int nchunk = std::max(1, std::min((F + 256 * 8 - 1) / (256 * 8), 2 * P->ctx->sm_count));
+    const size_t npart = (size_t)S * std::max(8 * nB, nP) * nchunk;
+    EOLC_CUDA(P->d_partial.ensure(std::max<size_t>(npart, 1)));
+    if (doPE) { k_PE_count<<<dim3((unsigned)(nPE / 256), S), 256, 0, st>>>(N, nP, P->d_pxyz.p, P->d_xp.p, thr, P->d_info.p, P->d_blocksum.p, xs, scene_items, secPE); ++launches; }
+    if (nP) {
+        k_PT_partial<<<dim3(nchunk, S * nP), 256, 0, st>>>(F, nP, 0, nullptr, P->d_pxyz.p, P->d_pnorms.p, P->d_fn.p, P->d_xp.p, P->d_fnp.p, P->d_aabb.p, thr, P->d_partial.p, xs, fs);
+        k_PT_final<<<S, 256, 0, st>>>(nchunk, nP, 1, P->d_partial.p, P->d_info.p, P->d_blocksum.p, scene_items, secPT, 0);
+        launches += 2;
+    }
+    if (nB) {
+        k_A_count<<<dim3((unsigned)(nA / 256), S * nB), 256, 0, st>>>(N, F, nB, P->d_xp.p, P->d_fnp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, xs, fs, scene_items, box_items, secBox);
+        k_PT_partial<<<dim3(nchunk, S * nB * 8), 256, 0, st>>>(F, nB * 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, P->d_fnp.p, P->d_aabb.p, thr, P->d_partial.p, xs, fs);
+        k_PT_final<<<S * nB, 256, 0, st>>>(nchunk, 8, nB, P->d_partial.p, P->d_info.p, P->d_blocksum.p, scene_items, secBox + nA, box_items);
+        k_C_count<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, xs, fs, scene_items, box_items, secBox + nA + nBc);
+        launches += 4;
+    }
+    k_scan<<<1, 1024, 0, st>>>(nblocks, P->d_blocksum.p, P->d_blockoff.p); ++launches;
+    EOLC_CUDA(P->p_blockoff.ensure(nblocks + 1));
+    EOLC_CUDA(cudaMemcpyAsync(P->p_blockoff.p, P->d_blockoff.p, sizeof(int) * (nblocks + 1), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));
+    const int total = P->p_blockoff.p[nblocks];
+
+    // ---- pass 2
+    EOLC_CUDA(P->d_out.ensure(std::max(total, 1)));
+    EOLC_CUDA(P->p_out.ensure(std::max(total, 1)));
+    if (total > 0) {
+        if (doPE) { k_PE_write<<<dim3((unsigned)(nPE / 256), S), 256, 0, st>>>(N, nP, P->d_pxyz.p, P->d_pnorms.p, P->d_xp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, scene_items, secPE); ++launches; }
+        if (nP) { k_PT_write<<<dim3((unsigned)(nPT / 256), S), 256, 0, st>>>(F, nP, 1, nullptr, P->d_pxyz.p, P->d_pnorms.p, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secPT, 0); ++launches; }
+        if (nB) {
+            k_A_write<<<dim3((unsigned)(nA / 256), S * nB), 256, 0, st>>>(N, F, nB, P->d_xp.p, P->d_fnp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox);
+            k_PT_write<<<dim3(1, S * nB), 256, 0, st>>>(F, 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secBox + nA, box_items);
+            k_C_write<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox + nA + nBc);
+            launches += 3;
+        }
+        EOLC_CUDA(cudaMemcpyAsync(P->p_out.p, P->d_out.p, sizeof(eolc_contact) * total, cudaMemcpyDeviceToHost, st));
+        EOLC_CUDA(cudaStreamSynchronize(st));
+    }
+    EOLC_CUDA(cudaGetLastError());
+    P->last_launches = launches;
+    P->last_pair_tests = (int64_t)S * ((doPE ? (int64_t)N * nP : 0) + (int64_t)nP * F + (int64_t)nB * ((int64_t)N * 24 + 8 * (int64_t)F + (int64_t)E * 12));
+
+    // ---- host post-pass over the (small) list: step (D) per box, CD remap, copy-out
+    const int *bo = P->p_blockoff.p;
+    int n_out = 0;
+    bool overflow = false;
+    std::vector<eolc_contact> lst;
+    for (int s = 0; s < S; ++s) {
+        scene_offset[s] = n_out;
+        const size_t sb = (size_t)s * scene_items / 256;
+        // points first (PE, PT): [begin, end)
+        {
+            int begin = bo[sb], end = bo[sb + secBox / 256];
+            for (int k = begin; k < end; ++k) { if (n_out < capacity) out[n_out] = P->p_out.p[k]; else overflow = true; ++n_out; }
+        }
+        for (int b = 0; b < nB; ++b) {
+            const size_t bb = sb + (secBox + (size_t)b * box_items) / 256;
+            int begin = bo[bb], end = bo[bb + box_items / 256];
+            lst.assign(P->p_out.p + begin, P->p_out.p + end);
+            // (D) :1022-1052 — per corner keep the closest count1==1 record; forward swap-with-back deletes, literally
+            for (int i1 = 0; i1 < 8; ++i1) {
+                V3 x1 = mk(hb[b].verts1[i1][0], hb[b].verts1[i1][1], hb[b].verts1[i1][2]);
+                int kmin = -1;
+                double dmin = 1e9;
+                for (int k = 0; k < (int)lst.size(); ++k)
+                    if (lst[k].count1 == 1 && lst[k].verts1[0] == i1) {
+                        V3 dx = ld(lst[k].pos2) - x1;
+                        double d = dot(dx, dx);
+                        if (d < dmin) { kmin = k; dmin = d; }
+                    }
+                if (kmin != -1) {
+                    std::vector<int> dlist;
+                    for (int k = 0; k < (int)lst.size(); ++k)
+                        if (lst[k].count1 == 1 && lst[k].verts1[0] == i1 && k != kmin) dlist.push_back(k);
+                    for (int kdel : dlist) { lst[kdel] = lst.back(); lst.pop_back(); }
+                }
+            }
+            for (auto &c : lst) {
+                if (remap_box_indices) {   // Collisions.cpp:39-48 ; Box::num_points = 8, num_edges = 12
+                    if (c.count1 == 1 && c.count2 == 3) c.verts1[0] = nP + (b * 8) + (b * 12) + c.verts1[0];
+                    for (int e = 0; e < c.n_edge1; ++e) c.edge1[e] = nP + (b * 8) + (b * 12) + (8 + c.edge1[e]);
+                }
+                if (n_out < capacity) out[n_out] = c; else overflow = true;
+                ++n_out;
+            }
+        }
+    }
+    scene_offset[S] = n_out;
+    if (overflow) { set_error("contact buffer too small: need %d, capacity %d", n_out, capacity); return EOLC_ERR_CAPACITY; }
+    return EOLC_OK;
+}
+
+int eolc_cd_run_dev(eolc_cd_plan *plan, const double *x_dev, int32_t n_points, const double *pxyz, const double *pnorms,
+                    int32_t n_boxes, const double *box_whd, const double *box_E, int point_eol_flag, int remap_box_indices,
+                    eolc_contact *out, int32_t capacity, int32_t *n_out) {
+    EOLC_REQUIRE(n_out, "n_out is NULL");
+    int32_t off[2] = {0, 0};
+    int rc = eolc_cd_run_batched_dev(plan, 1, x_dev, n_points, pxyz, pnorms, n_boxes, box_whd, box_E, point_eol_flag,
+                                     remap_box_indices, out, capacity, off);
+    *n_out = off[1];
+    return rc;
+}
+
+int eolc_cd_run(eolc_cd_plan *plan, const double *x, int32_t n_points, const double *pxyz, const double *pnorms,
+                int32_t n_boxes, const double *box_whd, const double *box_E, int point_eol_flag, int remap_box_indices,
+                eolc_contact *out, int32_t capacity, int32_t *n_out) {
+    EOLC_REQUIRE(plan && n_out, "NULL argument");
+    EOLC_REQUIRE(plan->N == 0 || x, "x is NULL");
+    EOLC_CUDA(cudaSetDevice(plan->ctx->device));
+    const size_t n = 3 * (size_t)plan->N;
+    EOLC_CUDA(plan->d_x.ensure(std::max<size_t>(n, 1)));
+    EOLC_CUDA(plan->p_x.ensure(std::max<size_t>(n, 1)));
+    if (n) {
+        memcpy(plan->p_x.p, x, n * sizeof(double));
+        EOLC_CUDA(cudaMemcpyAsync(plan->d_x.p, plan->p_x.p, n * sizeof(double), cudaMemcpyHostToDevice, plan->ctx->stream));
+    }
+    return eolc_cd_run_dev(plan, plan->d_x.p, n_points, pxyz, pnorms, n_boxes, box_whd, box_E, point_eol_flag,
+                           remap_box_indices, out, capacity, n_out);
+}
+
+}  // extern "C"

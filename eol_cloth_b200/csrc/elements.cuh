@@ -1,0 +1,244 @@
+// elements.cuh — per-element FP64 arithmetic of the Forces::fill hot path, hand-derived.
+//
+// Replaces (same results to rounding, far fewer operations, no spills):
+//   faceBasedF frame + poldec       /root/reference/src/Forces.cpp:357-372, :33-52
+//   ComputeMembrane                 /root/reference/src/ComputeMembrane.cpp:17-319   (~1040 flop -> ~250)
+//   ComputeInertial                 /root/reference/src/ComputeInertial.cpp:15-135
+//   ComputeBending (K only)         /root/reference/src/ComputeBending.cpp:30-737    (~6500 flop -> ~900)
+//
+// The generated reference code is the exact derivative of closed-form energies, so it can be
+// re-derived in matrix form:
+//
+//  membrane:  R = Q^T P (2x3), F = Dx DX^-1 (3x2), E = R F - I, S = 2 mu E + lambda tr(E) I,
+//             W = A (mu |E|^2 + lambda/2 tr(E)^2),   f_i = -A R^T S gradN_i,
+//             K_ij = A ( 2 mu (gradN_i . gradN_j) R^T R + lambda (R^T gradN_i)(R^T gradN_j)^T )
+//             with A = t7/2 (signed rest area), mu = e/(2(1+nu)), lambda = e nu/((1+nu)(1-2nu)).
+//  inertial:  t8 = rho * t7 ; f_i = t8 g / 6 ; M_ii = t8/12 I ; M_ij = t8/24 I.
+//  bending:   W = c (1 - u.v), c = 3/2 beta |X1-X0|^2 / (A0+A1), u = n0/|n0|, v = n1/|n1|,
+//             n0 = (x1-x0) x (x2-x0), n1 = (x3-x0) x (x1-x0).  With D = u.v,
+//             w0 = (x2-x1, x0-x2, x1-x0, 0), w1 = (x1-x3, x3-x0, 0, x0-x1)  (dn0/dx_i = [w0_i]x, dn1/dx_i = [w1_i]x),
+//             U_i = u x w0_i, Y_i = v x w0_i, V_i = v x w1_i, Z_i = u x w1_i :
+//             Hess(D)_ij = -1/|n0|^2 [ U_i Y_j^T + Y_i U_j^T - 3D U_i U_j^T + D((w0_i.w0_j) I - w0_j w0_i^T) ]
+//                          -1/|n1|^2 [ V_i Z_j^T + Z_i V_j^T - 3D V_i V_j^T + D((w1_i.w1_j) I - w1_j w1_i^T) ]
+//                          +1/(|n0||n1|) [ (w0_i.w1_j) I - w1_j w0_i^T - Y_i V_j^T - U_i (Z_j - D V_j)^T ]
+//                          +1/(|n0||n1|) [ (w1_i.w0_j) I - w0_j w1_i^T - V_i Y_j^T - (Z_i - D V_i) U_j^T ]
+//                          + k0_ij [g0]x + k1_ij [g1]x ,   g0 = (v - D u)/|n0|, g1 = (u - D v)/|n1|,
+//             K = -c Hess(D).   Verified against the reference object code to <1e-15 of the block scale
+//             (tests/test_element_math.py).
+//
+// The same source compiles for the device (nvcc) and for the host unit-test shim (g++), via EOLC_HD.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define EOLC_HD __host__ __device__ __forceinline__
+#else
+#define EOLC_HD inline
+#endif
+
+namespace eolc {
+
+struct v3 { double x, y, z; };
+EOLC_HD v3 mk3(double x, double y, double z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+EOLC_HD v3 operator+(v3 a, v3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+EOLC_HD v3 operator-(v3 a, v3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+EOLC_HD v3 operator*(double s, v3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+EOLC_HD double dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+EOLC_HD v3 cross(v3 a, v3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+
+// 3x3 block, row-major: B[3*r + c]
+struct blk3 { double m[9]; };
+// B += a b^T
+EOLC_HD void add_outer(blk3 &B, v3 a, v3 b) {
+    B.m[0] += a.x * b.x; B.m[1] += a.x * b.y; B.m[2] += a.x * b.z;
+    B.m[3] += a.y * b.x; B.m[4] += a.y * b.y; B.m[5] += a.y * b.z;
+    B.m[6] += a.z * b.x; B.m[7] += a.z * b.y; B.m[8] += a.z * b.z;
+}
+EOLC_HD void add_diag(blk3 &B, double d) { B.m[0] += d; B.m[4] += d; B.m[8] += d; }
+// B += s [g]x
+EOLC_HD void add_skew(blk3 &B, double s, v3 g) {
+    B.m[1] -= s * g.z; B.m[2] += s * g.y; B.m[3] += s * g.z; B.m[5] -= s * g.x; B.m[6] -= s * g.y; B.m[7] += s * g.x;
+}
+
+struct FaceOut {
+    double fa[3], fb[3], fc[3];   // fm + fi per vertex (Forces.cpp:500-502)
+    double t8;                    // rho * 2A(signed): M_ii = t8/12, M_ij = t8/24 (ComputeInertial.cpp:33,44-47)
+    // MDK contribution blocks Mi + dhh*Km: order aa, bb, cc, ab, ac, bc  (Forces.cpp:504-517)
+    blk3 K[6];
+};
+
+// One triangle: frame, polar decomposition, membrane f/K, inertial f/M.
+EOLC_HD void face_element(v3 xa, v3 xb, v3 xc, double Xax, double Xay, double Xbx, double Xby, double Xcx, double Xcy,
+                          double e, double nu, double rho, v3 g, double dhh, FaceOut &o) {
+    // frame (Forces.cpp:357-366)
+    v3 d1 = xb - xa, d2 = xc - xa;
+    v3 nrm = cross(d1, d2);
+    double il1 = 1.0 / sqrt(dot(d1, d1));
+    v3 Px = il1 * d1;
+    v3 Py = cross(nrm, Px);
+    double il2 = 1.0 / sqrt(dot(Py, Py));
+    Py = il2 * Py;
+    // rest-shape gradients (ComputeMembrane.cpp:43,52-70,101-110): rows of DX^-1
+    double t7 = Xax * Xby - Xax * Xcy - Xbx * Xay + Xcx * Xay + Xbx * Xcy - Xcx * Xby;
+    double t17 = 1.0 / t7;
+    double gb0 = t17 * (Xcy - Xay), gb1 = t17 * (Xax - Xcx);
+    double gc0 = t17 * (Xay - Xby), gc1 = t17 * (Xbx - Xax);
+    double ga0 = -gb0 - gc0, ga1 = -gb1 - gc1;
+    // F = Dx DX^-1 (3x2) and Fbar = P F (Forces.cpp:367-368)
+    v3 F0 = gb0 * d1 + gc0 * d2, F1 = gb1 * d1 + gc1 * d2;
+    double m11 = dot(Px, F0), m21 = dot(Py, F0), m12 = dot(Px, F1), m22 = dot(Py, F1);
+    // poldec (Forces.cpp:33-52)
+    double detM = m11 * m22 - m12 * m21;
+    double sg = detM < 0.0 ? -1.0 : (detM == 0.0 ? 0.0 : 1.0);
+    double q00 = m11 + sg * m22, q01 = m12 - sg * m21, q10 = m21 - sg * m12, q11 = m22 + sg * m11;
+    double icl = 1.0 / sqrt(q00 * q00 + q10 * q10);
+    q00 *= icl; q01 *= icl; q10 *= icl; q11 *= icl;
+    // R = Q^T P : rows r0, r1 (ComputeMembrane.cpp:47-69: t15,t29,t40 / t53,t57,t61)
+    v3 r0 = q00 * Px + q10 * Py, r1 = q01 * Px + q11 * Py;
+    // E = R F - I
+    double E00 = dot(r0, F0) - 1.0, E10 = dot(r1, F0), E01 = dot(r0, F1), E11 = dot(r1, F1) - 1.0;
+    double mu = e / (1.0 + nu) * 0.5;                              // t12
+    double lam = e * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));         // t88*t93
+    double A = 0.5 * t7;                                           // t8 of ComputeMembrane
+    double tr = E00 + E11;
+    double S00 = 2.0 * mu * E00 + lam * tr, S01 = 2.0 * mu * E01, S10 = 2.0 * mu * E10, S11 = 2.0 * mu * E11 + lam * tr;
+    // f_i = -A R^T S gradN_i  + gravity  t8 g/6 (ComputeInertial.cpp:33-37)
+    double t8 = rho * t7;
+    v3 fg = (t8 / 6.0) * g;
+    {
+        v3 fa = (-A * (S00 * ga0 + S01 * ga1)) * r0 + (-A * (S10 * ga0 + S11 * ga1)) * r1;
+        v3 fb = (-A * (S00 * gb0 + S01 * gb1)) * r0 + (-A * (S10 * gb0 + S11 * gb1)) * r1;
+        v3 fc = (-A * (S00 * gc0 + S01 * gc1)) * r0 + (-A * (S10 * gc0 + S11 * gc1)) * r1;
+        o.fa[0] = fa.x + fg.x; o.fa[1] = fa.y + fg.y; o.fa[2] = fa.z + fg.z;
+        o.fb[0] = fb.x + fg.x; o.fb[1] = fb.y + fg.y; o.fb[2] = fb.z + fg.z;
+        o.fc[0] = fc.x + fg.x; o.fc[1] = fc.y + fg.y; o.fc[2] = fc.z + fg.z;
+    }
+    o.t8 = t8;
+    // K_ij = A(2mu (gi.gj) R^T R + lam q_i q_j^T),  MDK block = M_ij + dhh K_ij
+    double RR[6] = {r0.x * r0.x + r1.x * r1.x, r0.x * r0.y + r1.x * r1.y, r0.x * r0.z + r1.x * r1.z,
+                    r0.y * r0.y + r1.y * r1.y, r0.y * r0.z + r1.y * r1.z, r0.z * r0.z + r1.z * r1.z};
+    v3 qa = ga0 * r0 + ga1 * r1, qb = gb0 * r0 + gb1 * r1, qc = gc0 * r0 + gc1 * r1;
+    const double a2mu = dhh * A * 2.0 * mu, alam = dhh * A * lam;
+    const double md = t8 / 12.0, mo = t8 / 24.0;
+    auto block = [&](blk3 &B, double gg, v3 qi, v3 qj, double mass) {
+        double s = a2mu * gg;
+        v3 ql = alam * qi;
+        B.m[0] = mass + (s * RR[0] + ql.x * qj.x); B.m[1] = s * RR[1] + ql.x * qj.y; B.m[2] = s * RR[2] + ql.x * qj.z;
+        B.m[3] = s * RR[1] + ql.y * qj.x; B.m[4] = mass + (s * RR[3] + ql.y * qj.y); B.m[5] = s * RR[4] + ql.y * qj.z;
+        B.m[6] = s * RR[2] + ql.z * qj.x; B.m[7] = s * RR[4] + ql.z * qj.y; B.m[8] = mass + (s * RR[5] + ql.z * qj.z);
+    };
+    block(o.K[0], ga0 * ga0 + ga1 * ga1, qa, qa, md);
+    block(o.K[1], gb0 * gb0 + gb1 * gb1, qb, qb, md);
+    block(o.K[2], gc0 * gc0 + gc1 * gc1, qc, qc, md);
+    block(o.K[3], ga0 * gb0 + ga1 * gb1, qa, qb, mo);
+    block(o.K[4], ga0 * gc0 + ga1 * gc1, qa, qc, mo);
+    block(o.K[5], gb0 * gc0 + gb1 * gc1, qb, qc, mo);
+}
+
+// rho * 2A(signed) of one face, for the mass matrix (ComputeInertial.cpp:33)
+EOLC_HD double face_t8(double Xax, double Xay, double Xbx, double Xby, double Xcx, double Xcy, double rho) {
+    return rho * (Xax * Xby - Xax * Xcy - Xbx * Xay + Xcx * Xay + Xbx * Xcy - Xcx * Xby);
+}
+
+// One interior edge: the 10 upper 3x3 blocks of dhh * Kb, order 00,11,22,33,01,02,03,12,13,23
+// (Forces.cpp:885-906).  The bending force is not produced: the non-EOL branch discards it.
+struct EdgeOut { blk3 K[10]; };
+
+EOLC_HD void edge_element(v3 x0, v3 x1, v3 x2, v3 x3, double X0x, double X0y, double X1x, double X1y, double X2x,
+                          double X2y, double X3x, double X3y, double beta, double dhh, EdgeOut &o) {
+    // c = 3/2 * t6 * t17 (ComputeBending.cpp:50-53,102)
+    double ex = X1x - X0x, ey = X1y - X0y;
+    double t6 = beta * (ex * ex + ey * ey);
+    double den = 0.5 * (-X0x * X2y + X2x * X0y + X1x * X2y - X2x * X1y + X0x * X3y - X3x * X0y - X1x * X3y + X3x * X1y);
+    double c = 1.5 * t6 / den;
+    v3 e = x1 - x0, a = x2 - x0, b = x3 - x0;
+    v3 n0 = cross(e, a), n1 = cross(b, e);
+    double s0 = 1.0 / dot(n0, n0), s1 = 1.0 / dot(n1, n1);
+    double il0 = sqrt(s0), il1 = sqrt(s1);
+    v3 u = il0 * n0, v = il1 * n1;
+    double D = dot(u, v);
+    const double kk = -c * dhh;                  // K*dhh = kk * Hess(D)
+    const double k0 = -kk * s0, k1 = -kk * s1, k01 = kk * il0 * il1;
+    // w vectors
+    v3 w00 = x2 - x1, w01 = x0 - x2, w02 = e;
+    v3 w10 = x1 - x3, w11 = b, w13 = x0 - x1;
+    // crosses
+    v3 U0 = cross(u, w00), U1 = cross(u, w01), U2 = cross(u, w02);
+    v3 Y0 = cross(v, w00), Y1 = cross(v, w01), Y2 = cross(v, w02);
+    v3 V0 = cross(v, w10), V1 = cross(v, w11), V3 = cross(v, w13);
+    v3 Z0 = cross(u, w10), Z1 = cross(u, w11), Z3 = cross(u, w13);
+    // second-order vectors kk*g0, kk*g1
+    v3 g0 = (kk * il0) * (v - D * u), g1 = (kk * il1) * (u - D * v);
+
+    // --- triangle-0 term: k0 [ U_i T_j^T + Y_i U_j^T + D (w0i.w0j) I - D w0j w0i^T ],  T_j = Y_j - 3D U_j
+    // --- triangle-1 term: k1 [ V_i T'_j^T + Z_i V_j^T + D (w1i.w1j) I - D w1j w1i^T ],  T'_j = Z_j - 3D V_j
+    // --- cross terms:     k01 [ (w0i.w1j) I - w1j w0i^T - Y_i V_j^T - U_i ZZ_j^T ]  (+ transpose of (j,i)),  ZZ_j = Z_j - D V_j
+    const double D3 = 3.0 * D;
+    v3 T0 = Y0 - D3 * U0, T1 = Y1 - D3 * U1, T2 = Y2 - D3 * U2;
+    v3 Tp0 = Z0 - D3 * V0, Tp1 = Z1 - D3 * V1, Tp3 = Z3 - D3 * V3;
+    v3 ZZ0 = Z0 - D * V0, ZZ1 = Z1 - D * V1, ZZ3 = Z3 - D * V3;
+    // pre-scaled left factors
+    v3 kU0 = k0 * U0, kU1 = k0 * U1, kU2 = k0 * U2, kY0 = k0 * Y0, kY1 = k0 * Y1, kY2 = k0 * Y2;
+    v3 kV0 = k1 * V0, kV1 = k1 * V1, kV3 = k1 * V3, kZ0 = k1 * Z0, kZ1 = k1 * Z1, kZ3 = k1 * Z3;
+    const double k0D = k0 * D, k1D = k1 * D;
+    v3 dw00 = k0D * w00, dw01 = k0D * w01, dw02 = k0D * w02;
+    v3 dw10 = k1D * w10, dw11 = k1D * w11, dw13 = k1D * w13;
+    v3 cY0 = k01 * Y0, cY1 = k01 * Y1, cY2 = k01 * Y2, cU0 = k01 * U0, cU1 = k01 * U1, cU2 = k01 * U2;
+    v3 cw00 = k01 * w00, cw01 = k01 * w01, cw02 = k01 * w02;
+
+#define EOLC_ZERO(B) { for (int q_ = 0; q_ < 9; ++q_) (B).m[q_] = 0.0; }
+    // tri0(i,j): B += kU_i T_j^T + kY_i U_j^T + (dw0i.w0j) I - w0j dw0i^T
+#define EOLC_TRI0(B, kUi, kYi, dwi, Tj, Uj, wj) { add_outer(B, kUi, Tj); add_outer(B, kYi, Uj); add_diag(B, dot(dwi, wj)); add_outer(B, -1.0 * (wj), dwi); }
+#define EOLC_TRI1(B, kVi, kZi, dwi, Tpj, Vj, wj) { add_outer(B, kVi, Tpj); add_outer(B, kZi, Vj); add_diag(B, dot(dwi, wj)); add_outer(B, -1.0 * (wj), dwi); }
+    // cross01(i,j): B += (cw0i.w1j) I - w1j cw0i^T - cY_i V_j^T - cU_i ZZ_j^T
+#define EOLC_X01(B, cwi, cYi, cUi, w1j, Vj, ZZj) { add_diag(B, dot(cwi, w1j)); add_outer(B, -1.0 * (w1j), cwi); add_outer(B, -1.0 * (cYi), Vj); add_outer(B, -1.0 * (cUi), ZZj); }
+    // cross10(i,j) = cross01(j,i)^T: B += (w1i.cw0j) I - cw0j w1i^T - V_i cY_j^T - ZZ_i cU_j^T
+#define EOLC_X10(B, w1i, Vi, ZZi, cwj, cYj, cUj) { add_diag(B, dot(w1i, cwj)); add_outer(B, -1.0 * (cwj), w1i); add_outer(B, -1.0 * (Vi), cYj); add_outer(B, -1.0 * (ZZi), cUj); }
+
+    blk3 B;
+    // (0,0)
+    EOLC_ZERO(B); EOLC_TRI0(B, kU0, kY0, dw00, T0, U0, w00); EOLC_TRI1(B, kV0, kZ0, dw10, Tp0, V0, w10);
+    EOLC_X01(B, cw00, cY0, cU0, w10, V0, ZZ0); EOLC_X10(B, w10, V0, ZZ0, cw00, cY0, cU0);
+    o.K[0] = B;
+    // (1,1)
+    EOLC_ZERO(B); EOLC_TRI0(B, kU1, kY1, dw01, T1, U1, w01); EOLC_TRI1(B, kV1, kZ1, dw11, Tp1, V1, w11);
+    EOLC_X01(B, cw01, cY1, cU1, w11, V1, ZZ1); EOLC_X10(B, w11, V1, ZZ1, cw01, cY1, cU1);
+    o.K[1] = B;
+    // (2,2)
+    EOLC_ZERO(B); EOLC_TRI0(B, kU2, kY2, dw02, T2, U2, w02);
+    o.K[2] = B;
+    // (3,3)
+    EOLC_ZERO(B); EOLC_TRI1(B, kV3, kZ3, dw13, Tp3, V3, w13);
+    o.K[3] = B;
+    // (0,1): second-order  -G0 + G1
+    EOLC_ZERO(B); EOLC_TRI0(B, kU0, kY0, dw00, T1, U1, w01); EOLC_TRI1(B, kV0, kZ0, dw10, Tp1, V1, w11);
+    EOLC_X01(B, cw00, cY0, cU0, w11, V1, ZZ1); EOLC_X10(B, w10, V0, ZZ0, cw01, cY1, cU1);
+    add_skew(B, -1.0, g0); add_skew(B, 1.0, g1);
+    o.K[4] = B;
+    // (0,2): +G0
+    EOLC_ZERO(B); EOLC_TRI0(B, kU0, kY0, dw00, T2, U2, w02); EOLC_X10(B, w10, V0, ZZ0, cw02, cY2, cU2);
+    add_skew(B, 1.0, g0);
+    o.K[5] = B;
+    // (0,3): -G1
+    EOLC_ZERO(B); EOLC_TRI1(B, kV0, kZ0, dw10, Tp3, V3, w13); EOLC_X01(B, cw00, cY0, cU0, w13, V3, ZZ3);
+    add_skew(B, -1.0, g1);
+    o.K[6] = B;
+    // (1,2): -G0
+    EOLC_ZERO(B); EOLC_TRI0(B, kU1, kY1, dw01, T2, U2, w02); EOLC_X10(B, w11, V1, ZZ1, cw02, cY2, cU2);
+    add_skew(B, -1.0, g0);
+    o.K[7] = B;
+    // (1,3): +G1
+    EOLC_ZERO(B); EOLC_TRI1(B, kV1, kZ1, dw11, Tp3, V3, w13); EOLC_X01(B, cw01, cY1, cU1, w13, V3, ZZ3);
+    add_skew(B, 1.0, g1);
+    o.K[8] = B;
+    // (2,3): cross term only
+    EOLC_ZERO(B); EOLC_X01(B, cw02, cY2, cU2, w13, V3, ZZ3);
+    o.K[9] = B;
+#undef EOLC_ZERO
+#undef EOLC_TRI0
+#undef EOLC_TRI1
+#undef EOLC_X01
+#undef EOLC_X10
+}
+
+}  // namespace eolc

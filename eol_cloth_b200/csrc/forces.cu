@@ -1,0 +1,511 @@
+// forces.cu — Forces::fill on the GPU (include/eolc.h, "Forces::fill" section).
+//
+// Replaces /root/reference/src/Forces.cpp:912-930 (fill), :331-520 (faceBasedF, non-EOL branch),
+// :685-910 (edgeBasedF, non-EOL branch) and Eigen's setFromTriplets.
+//
+// Pipeline "gather" (v1):   [face_kernel] [edge_kernel] -> element blocks in HBM scratch (SoA)
+//                           [gather_mdk] [gather_m] [gather_f] -> fixed CSR slots, pull-style:
+// every output 3x3 block sums its contributions in the reference's triplet insertion order (faces ascending,
+// then edges ascending, Forces.cpp:922-923), left to right, exactly like collapseDuplicates — no atomics,
+// bit-reproducible run to run.
+#include "common.h"
+#include "elements.cuh"
+#include <algorithm>
+#include <numeric>
+
+using namespace eolc;
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct eolc_forces_plan {
+    eolc_ctx *ctx = nullptr;
+    int32_t N = 0, F = 0, E = 0, Ei = 0, dof = 0;
+    int64_t nnzM = 0, nnzK = 0, nblkM = 0, nblkK = 0;
+    // host topology
+    std::vector<int32_t> h_face_nodes, h_iedge;   // h_iedge: 4 per INTERIOR edge, ascending mesh edge order
+    std::vector<int64_t> h_blkptrM, h_blkptrK;    // N+1: first block of node a
+    std::vector<int32_t> h_nbrM, h_nbrK;          // neighbour node per block (ascending within a node)
+    std::vector<int32_t> h_outerM, h_innerM, h_outerK, h_innerK;  // lazily built Eigen-style arrays
+    // device topology
+    DevBuf<int32_t> d_face_nodes, d_iedge;
+    DevBuf<int64_t> d_blkptrM, d_blkptrK;
+    DevBuf<int32_t> d_blknodeM, d_blknodeK;       // owning (row) node of each block
+    DevBuf<int32_t> d_nbrM;                       // column node of each M block
+    DevBuf<int64_t> d_cptrM, d_cptrK, d_cptrF;    // contribution list offsets per block / per node
+    DevBuf<int32_t> d_contribM, d_contribK, d_contribF;
+    // scratch (per scene chunk)
+    DevBuf<double> d_face_scr, d_edge_scr;
+    int32_t scratch_scenes = 0;
+    // staging for the host entry point
+    DevBuf<double> d_x, d_X, d_f, d_Mv, d_Kv;
+    PinnedBuf<double> p_in, p_out;
+};
+
+namespace {
+
+constexpr int FACE_SCR = 64;   // doubles per face: 54 K + 9 f + 1 t8
+constexpr int EDGE_SCR = 90;   // doubles per interior edge: 10 blocks x 9
+
+// contribution code: bits 0-3 local block id, bit 4 transposed, bit 5 edge (else face), bits 6.. element index
+__host__ __device__ inline int32_t mk_code(int32_t elem, int is_edge, int blk, int tr) {
+    return (elem << 6) | (is_edge << 5) | (tr << 4) | blk;
+}
+
+__global__ void __launch_bounds__(128) face_kernel(int F, const int32_t *__restrict__ fn, const double *__restrict__ x,
+                                                   const double *__restrict__ X, double e, double nu, double rho,
+                                                   double gx, double gy, double gz, double dhh, double *__restrict__ scr,
+                                                   size_t x_stride, size_t X_stride, size_t scr_stride) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F) return;
+    const int s = blockIdx.y;
+    x += s * x_stride; X += s * X_stride; scr += s * scr_stride;
+    int a = fn[3 * i], b = fn[3 * i + 1], c = fn[3 * i + 2];
+    FaceOut o;
+    face_element(mk3(x[3 * a], x[3 * a + 1], x[3 * a + 2]), mk3(x[3 * b], x[3 * b + 1], x[3 * b + 2]),
+                 mk3(x[3 * c], x[3 * c + 1], x[3 * c + 2]), X[2 * a], X[2 * a + 1], X[2 * b], X[2 * b + 1], X[2 * c],
+                 X[2 * c + 1], e, nu, rho, mk3(gx, gy, gz), dhh, o);
+    // SoA: scr[k*F + i]
+#pragma unroll
+    for (int bk = 0; bk < 6; ++bk)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) scr[(size_t)(bk * 9 + k) * F + i] = o.K[bk].m[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        scr[(size_t)(54 + k) * F + i] = o.fa[k];
+        scr[(size_t)(57 + k) * F + i] = o.fb[k];
+        scr[(size_t)(60 + k) * F + i] = o.fc[k];
+    }
+    scr[(size_t)63 * F + i] = o.t8;
+}
+
+__global__ void __launch_bounds__(128) edge_kernel(int Ei, const int32_t *__restrict__ st, const double *__restrict__ x,
+                                                   const double *__restrict__ X, double beta, double dhh,
+                                                   double *__restrict__ scr, size_t x_stride, size_t X_stride,
+                                                   size_t scr_stride) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ei) return;
+    const int s = blockIdx.y;
+    x += s * x_stride; X += s * X_stride; scr += s * scr_stride;
+    int n0 = st[4 * i], n1 = st[4 * i + 1], n2 = st[4 * i + 2], n3 = st[4 * i + 3];
+    EdgeOut o;
+    edge_element(mk3(x[3 * n0], x[3 * n0 + 1], x[3 * n0 + 2]), mk3(x[3 * n1], x[3 * n1 + 1], x[3 * n1 + 2]),
+                 mk3(x[3 * n2], x[3 * n2 + 1], x[3 * n2 + 2]), mk3(x[3 * n3], x[3 * n3 + 1], x[3 * n3 + 2]), X[2 * n0],
+                 X[2 * n0 + 1], X[2 * n1], X[2 * n1 + 1], X[2 * n2], X[2 * n2 + 1], X[2 * n3], X[2 * n3 + 1], beta, dhh, o);
+#pragma unroll
+    for (int bk = 0; bk < 10; ++bk)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) scr[(size_t)(bk * 9 + k) * Ei + i] = o.K[bk].m[k];
+}
+
+// one thread per MDK block (a, p): vals[rowstart(3a+j) + 3p + k], rowstart(3a+j) = 9*blkptr[a] + j*3*deg(a)
+__global__ void __launch_bounds__(256) gather_mdk(int64_t nblk, const int32_t *__restrict__ blknode,
+                                                  const int64_t *__restrict__ blkptr, const int64_t *__restrict__ cptr,
+                                                  const int32_t *__restrict__ contrib, int F, int Ei,
+                                                  const double *__restrict__ fscr, const double *__restrict__ escr,
+                                                  double *__restrict__ vals, size_t fscr_stride, size_t escr_stride,
+                                                  size_t vals_stride) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nblk) return;
+    const int s = blockIdx.y;
+    fscr += s * fscr_stride; escr += s * escr_stride; vals += s * vals_stride;
+    double acc[9];
+    bool first = true;
+    for (int64_t c = cptr[t]; c < cptr[t + 1]; ++c) {
+        int32_t code = contrib[c];
+        int blk = code & 15, tr = (code >> 4) & 1, is_edge = (code >> 5) & 1;
+        int32_t el = code >> 6;
+        const double *src = is_edge ? escr + (size_t)(blk * 9) * Ei + el : fscr + (size_t)(blk * 9) * F + el;
+        size_t st = is_edge ? (size_t)Ei : (size_t)F;
+        double v[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = src[k * st];
+        if (tr) { double q; q = v[1]; v[1] = v[3]; v[3] = q; q = v[2]; v[2] = v[6]; v[6] = q; q = v[5]; v[5] = v[7]; v[7] = q; }
+        if (first) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[k] = v[k];
+            first = false;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[k] = acc[k] + v[k];
+        }
+    }
+    int a = blknode[t];
+    int64_t b0 = blkptr[a];
+    int deg = (int)(blkptr[a + 1] - b0);
+    int p = (int)(t - b0);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double *row = vals + 9 * b0 + (int64_t)j * 3 * deg + 3 * p;
+        row[0] = acc[3 * j]; row[1] = acc[3 * j + 1]; row[2] = acc[3 * j + 2];
+    }
+}
+
+// one thread per M block: sum over faces of t8/12 (a == b) or t8/24, on the block diagonal; explicit zeros elsewhere
+__global__ void __launch_bounds__(256) gather_m(int64_t nblk, const int32_t *__restrict__ blknode,
+                                                const int64_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
+                                                const int64_t *__restrict__ cptr, const int32_t *__restrict__ contrib,
+                                                int F, const double *__restrict__ fscr, double *__restrict__ vals,
+                                                size_t fscr_stride, size_t vals_stride) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nblk) return;
+    const int s = blockIdx.y;
+    fscr += s * fscr_stride; vals += s * vals_stride;
+    int a = blknode[t];
+    const bool diag = nbr[t] == a;
+    double acc = 0.0;
+    bool first = true;
+    for (int64_t c = cptr[t]; c < cptr[t + 1]; ++c) {
+        double t8 = fscr[(size_t)63 * F + contrib[c]];
+        double m = diag ? t8 / 12.0 : t8 / 24.0;
+        acc = first ? m : acc + m;
+        first = false;
+    }
+    int64_t b0 = blkptr[a];
+    int deg = (int)(blkptr[a + 1] - b0);
+    int p = (int)(t - b0);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double *row = vals + 9 * b0 + (int64_t)j * 3 * deg + 3 * p;
+        row[0] = j == 0 ? acc : 0.0; row[1] = j == 1 ? acc : 0.0; row[2] = j == 2 ? acc : 0.0;
+    }
+}
+
+// one thread per node: f[3a..3a+2] = sum over incident faces (ascending) of (fm + fi) of that vertex
+__global__ void __launch_bounds__(256) gather_f(int N, const int64_t *__restrict__ cptr, const int32_t *__restrict__ contrib,
+                                                int F, const double *__restrict__ fscr, double *__restrict__ f,
+                                                size_t fscr_stride, size_t f_stride) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= N) return;
+    const int s = blockIdx.y;
+    fscr += s * fscr_stride; f += s * f_stride;
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0;   // f.setZero() then +=  (Forces.cpp:915, :500-502)
+    for (int64_t c = cptr[a]; c < cptr[a + 1]; ++c) {
+        int32_t code = contrib[c];
+        int lv = code & 3;
+        int32_t face = code >> 2;
+        const double *src = fscr + (size_t)(54 + 3 * lv) * F + face;
+        f0 += src[0]; f1 += src[(size_t)F]; f2 += src[2 * (size_t)F];
+    }
+    f[3 * a] = f0; f[3 * a + 1] = f1; f[3 * a + 2] = f2;
+}
+
+int build_pattern(eolc_forces_plan *P) {
+    const int32_t N = P->N, F = P->F;
+    const int32_t Ei = P->Ei;
+    const int32_t *fn = P->h_face_nodes.data();
+    const int32_t *ie = P->h_iedge.data();
+    // adjacency via counting
+    std::vector<int64_t> cntM(N + 1, 0), cntK(N + 1, 0);
+    for (int32_t a = 0; a < N; ++a) { cntM[a + 1] = 1; cntK[a + 1] = 1; }  // self (isolated nodes get no block: fix below)
+    std::vector<char> used(N, 0);
+    for (int32_t i = 0; i < F; ++i)
+        for (int v = 0; v < 3; ++v) { used[fn[3 * i + v]] = 1; cntM[fn[3 * i + v] + 1] += 2; cntK[fn[3 * i + v] + 1] += 2; }
+    for (int32_t i = 0; i < Ei; ++i)
+        for (int v = 0; v < 4; ++v) cntK[ie[4 * i + v] + 1] += 3;
+    for (int32_t a = 0; a < N; ++a) if (!used[a]) { cntM[a + 1] = 0; cntK[a + 1] = 0; }
+    for (int32_t a = 0; a < N; ++a) { cntM[a + 1] += cntM[a]; cntK[a + 1] += cntK[a]; }
+    std::vector<int32_t> rawM(cntM[N]), rawK(cntK[N]);
+    std::vector<int64_t> pM(cntM.begin(), cntM.end() - 1), pK(cntK.begin(), cntK.end() - 1);
+    for (int32_t a = 0; a < N; ++a) if (used[a]) { rawM[pM[a]++] = a; rawK[pK[a]++] = a; }
+    for (int32_t i = 0; i < F; ++i)
+        for (int v = 0; v < 3; ++v) {
+            int32_t a = fn[3 * i + v];
+            for (int w = 0; w < 3; ++w) if (w != v) { rawM[pM[a]++] = fn[3 * i + w]; rawK[pK[a]++] = fn[3 * i + w]; }
+        }
+    for (int32_t i = 0; i < Ei; ++i)
+        for (int v = 0; v < 4; ++v) {
+            int32_t a = ie[4 * i + v];
+            for (int w = 0; w < 4; ++w) if (w != v) rawK[pK[a]++] = ie[4 * i + w];
+        }
+    auto compress = [&](std::vector<int64_t> &cnt, std::vector<int32_t> &raw, std::vector<int64_t> &blkptr, std::vector<int32_t> &nbr) {
+        blkptr.assign(N + 1, 0);
+        nbr.clear();
+        nbr.reserve(raw.size() / 2);
+        for (int32_t a = 0; a < N; ++a) {
+            auto b = raw.begin() + cnt[a], e = raw.begin() + cnt[a + 1];
+            std::sort(b, e);
+            auto u = std::unique(b, e);
+            nbr.insert(nbr.end(), b, u);
+            blkptr[a + 1] = (int64_t)nbr.size();
+        }
+    };
+    compress(cntM, rawM, P->h_blkptrM, P->h_nbrM);
+    compress(cntK, rawK, P->h_blkptrK, P->h_nbrK);
+    P->nblkM = P->h_blkptrM[N]; P->nblkK = P->h_blkptrK[N];
+    P->nnzM = 9 * P->nblkM; P->nnzK = 9 * P->nblkK;
+    if (P->nnzK > (int64_t)INT32_MAX) { set_error("nnz(MDK) exceeds int32 (Eigen StorageIndex is int)"); return EOLC_ERR_UNSUPPORTED; }
+    return EOLC_OK;
+}
+
+inline int64_t find_block(const std::vector<int64_t> &blkptr, const std::vector<int32_t> &nbr, int32_t a, int32_t b) {
+    auto beg = nbr.begin() + blkptr[a], end = nbr.begin() + blkptr[a + 1];
+    return std::lower_bound(beg, end, b) - nbr.begin();
+}
+
+// local block id of (vi, vj), vi <= vj, in the element's emitted block order
+const int kFaceBlk[3][3] = {{0, 3, 4}, {3, 1, 5}, {4, 5, 2}};
+const int kEdgeBlk[4][4] = {{0, 4, 5, 6}, {4, 1, 7, 8}, {5, 7, 2, 9}, {6, 8, 9, 3}};
+
+int build_contribs(eolc_forces_plan *P, cudaStream_t st) {
+    const int32_t N = P->N, F = P->F, Ei = P->Ei;
+    const int32_t *fn = P->h_face_nodes.data();
+    const int32_t *ie = P->h_iedge.data();
+    // ---- MDK: count then fill; element order = faces ascending then interior edges ascending
+    std::vector<int64_t> cK(P->nblkK + 1, 0), cM(P->nblkM + 1, 0), cF(N + 1, 0);
+    for (int32_t i = 0; i < F; ++i)
+        for (int v = 0; v < 3; ++v) {
+            cF[fn[3 * i + v] + 1]++;
+            for (int w = 0; w < 3; ++w) {
+                cK[find_block(P->h_blkptrK, P->h_nbrK, fn[3 * i + v], fn[3 * i + w]) + 1]++;
+                cM[find_block(P->h_blkptrM, P->h_nbrM, fn[3 * i + v], fn[3 * i + w]) + 1]++;
+            }
+        }
+    for (int32_t i = 0; i < Ei; ++i)
+        for (int v = 0; v < 4; ++v)
+            for (int w = 0; w < 4; ++w) cK[find_block(P->h_blkptrK, P->h_nbrK, ie[4 * i + v], ie[4 * i + w]) + 1]++;
+    for (int64_t b = 0; b < P->nblkK; ++b) cK[b + 1] += cK[b];
+    for (int64_t b = 0; b < P->nblkM; ++b) cM[b + 1] += cM[b];
+    for (int32_t a = 0; a < N; ++a) cF[a + 1] += cF[a];
+    std::vector<int32_t> lK(cK[P->nblkK]), lM(cM[P->nblkM]), lF(cF[N]);
+    std::vector<int64_t> pK(cK.begin(), cK.end() - 1), pM(cM.begin(), cM.end() - 1), pF(cF.begin(), cF.end() - 1);
+    for (int32_t i = 0; i < F; ++i)
+        for (int v = 0; v < 3; ++v) {
+            lF[pF[fn[3 * i + v]]++] = (i << 2) | v;
+            for (int w = 0; w < 3; ++w) {
+                int lo = v < w ? v : w, hi = v < w ? w : v;
+                int64_t bk = find_block(P->h_blkptrK, P->h_nbrK, fn[3 * i + v], fn[3 * i + w]);
+                lK[pK[bk]++] = mk_code(i, 0, kFaceBlk[lo][hi], v > w ? 1 : 0);
+                int64_t bm = find_block(P->h_blkptrM, P->h_nbrM, fn[3 * i + v], fn[3 * i + w]);
+                lM[pM[bm]++] = i;
+            }
+        }
+    for (int32_t i = 0; i < Ei; ++i)
+        for (int v = 0; v < 4; ++v)
+            for (int w = 0; w < 4; ++w) {
+                int lo = v < w ? v : w, hi = v < w ? w : v;
+                int64_t bk = find_block(P->h_blkptrK, P->h_nbrK, ie[4 * i + v], ie[4 * i + w]);
+                lK[pK[bk]++] = mk_code(i, 1, kEdgeBlk[lo][hi], v > w ? 1 : 0);
+            }
+    std::vector<int32_t> bnM(P->nblkM), bnK(P->nblkK);
+    for (int32_t a = 0; a < N; ++a) {
+        for (int64_t b = P->h_blkptrM[a]; b < P->h_blkptrM[a + 1]; ++b) bnM[b] = a;
+        for (int64_t b = P->h_blkptrK[a]; b < P->h_blkptrK[a + 1]; ++b) bnK[b] = a;
+    }
+    EOLC_CUDA(P->d_cptrK.upload(cK, st)); EOLC_CUDA(P->d_contribK.upload(lK, st));
+    EOLC_CUDA(P->d_cptrM.upload(cM, st)); EOLC_CUDA(P->d_contribM.upload(lM, st));
+    EOLC_CUDA(P->d_cptrF.upload(cF, st)); EOLC_CUDA(P->d_contribF.upload(lF, st));
+    EOLC_CUDA(P->d_blknodeM.upload(bnM, st)); EOLC_CUDA(P->d_blknodeK.upload(bnK, st));
+    EOLC_CUDA(P->d_blkptrM.upload(P->h_blkptrM, st)); EOLC_CUDA(P->d_blkptrK.upload(P->h_blkptrK, st));
+    EOLC_CUDA(P->d_nbrM.upload(P->h_nbrM, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));  // host vectors die at scope exit
+    return EOLC_OK;
+}
+
+void build_eigen_arrays(int32_t N, const std::vector<int64_t> &blkptr, const std::vector<int32_t> &nbr,
+                        std::vector<int32_t> &outer, std::vector<int32_t> &inner) {
+    outer.assign(3 * (size_t)N + 1, 0);
+    inner.resize(9 * (size_t)blkptr[N]);
+    for (int32_t a = 0; a < N; ++a) {
+        int64_t b0 = blkptr[a];
+        int deg = (int)(blkptr[a + 1] - b0);
+        for (int j = 0; j < 3; ++j) {
+            int64_t rs = 9 * b0 + (int64_t)j * 3 * deg;
+            outer[3 * (size_t)a + j] = (int32_t)rs;
+            for (int p = 0; p < deg; ++p)
+                for (int k = 0; k < 3; ++k) inner[rs + 3 * p + k] = 3 * nbr[b0 + p] + k;
+        }
+    }
+    outer[3 * (size_t)N] = (int32_t)(9 * blkptr[N]);
+}
+
+int ensure_scratch(eolc_forces_plan *P, int32_t scenes) {
+    if (scenes <= P->scratch_scenes) return EOLC_OK;
+    EOLC_CUDA(P->d_face_scr.alloc((size_t)scenes * FACE_SCR * P->F));
+    EOLC_CUDA(P->d_edge_scr.alloc((size_t)scenes * EDGE_SCR * P->Ei));
+    P->scratch_scenes = scenes;
+    return EOLC_OK;
+}
+
+int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X, const eolc_material *mat,
+                const double *grav, double h, double *f, double *Mv, double *Kv) {
+    cudaStream_t st = P->ctx->stream;
+    const double dhh = mat->dampingB * h * h;   // damping(1)*h*h, Forces.cpp:105
+    // scene chunks bounded by the scratch budget (~4 GB)
+    size_t per_scene = ((size_t)FACE_SCR * P->F + (size_t)EDGE_SCR * P->Ei) * sizeof(double);
+    int32_t chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)4 << 30) / std::max<size_t>(per_scene, 1)));
+    chunk = std::min<int32_t>(chunk, 65535);
+    int rc = ensure_scratch(P, chunk);
+    if (rc) return rc;
+    const size_t fs = (size_t)FACE_SCR * P->F, es = (size_t)EDGE_SCR * P->Ei;
+    for (int32_t s0 = 0; s0 < S; s0 += chunk) {
+        int32_t sc = std::min(chunk, S - s0);
+        const double *xs = x + (size_t)s0 * 3 * P->N, *Xs = X + (size_t)s0 * 2 * P->N;
+        if (P->F > 0)
+            face_kernel<<<dim3((P->F + 127) / 128, sc), 128, 0, st>>>(P->F, P->d_face_nodes.p, xs, Xs, mat->e, mat->nu, mat->density,
+                                                                      grav[0], grav[1], grav[2], dhh, P->d_face_scr.p,
+                                                                      (size_t)3 * P->N, (size_t)2 * P->N, fs);
+        if (P->Ei > 0)
+            edge_kernel<<<dim3((P->Ei + 127) / 128, sc), 128, 0, st>>>(P->Ei, P->d_iedge.p, xs, Xs, mat->beta, dhh, P->d_edge_scr.p,
+                                                                       (size_t)3 * P->N, (size_t)2 * P->N, es);
+        if (P->nblkK > 0)
+            gather_mdk<<<dim3((unsigned)((P->nblkK + 255) / 256), sc), 256, 0, st>>>(
+                P->nblkK, P->d_blknodeK.p, P->d_blkptrK.p, P->d_cptrK.p, P->d_contribK.p, P->F, P->Ei, P->d_face_scr.p,
+                P->d_edge_scr.p, Kv + (size_t)s0 * P->nnzK, fs, es, (size_t)P->nnzK);
+        if (P->nblkM > 0)
+            gather_m<<<dim3((unsigned)((P->nblkM + 255) / 256), sc), 256, 0, st>>>(
+                P->nblkM, P->d_blknodeM.p, P->d_blkptrM.p, P->d_nbrM.p, P->d_cptrM.p, P->d_contribM.p, P->F, P->d_face_scr.p,
+                Mv + (size_t)s0 * P->nnzM, fs, (size_t)P->nnzM);
+        if (P->N > 0)
+            gather_f<<<dim3((P->N + 255) / 256, sc), 256, 0, st>>>(P->N, P->d_cptrF.p, P->d_contribF.p, P->F, P->d_face_scr.p,
+                                                                   f + (size_t)s0 * P->dof, fs, (size_t)P->dof);
+    }
+    EOLC_CUDA(cudaGetLastError());
+    return EOLC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face_nodes, int32_t E,
+                            const int32_t *edge_stencil, const int32_t *eol_index, const double *X_hint,
+                            eolc_forces_plan **out) {
+    (void)X_hint;
+    EOLC_REQUIRE(ctx && out, "ctx/out is NULL");
+    *out = nullptr;
+    EOLC_REQUIRE(N >= 0 && F >= 0 && E >= 0, "negative size");
+    EOLC_REQUIRE(F == 0 || face_nodes, "face_nodes is NULL");
+    EOLC_REQUIRE(E == 0 || edge_stencil, "edge_stencil is NULL");
+    EOLC_REQUIRE((int64_t)N * 3 < INT32_MAX && (int64_t)F < (1 << 25) && (int64_t)E < (1 << 25), "mesh too large for int32 indexing");
+    if (eol_index)
+        for (int32_t a = 0; a < N; ++a)
+            if (eol_index[a] >= 0) {
+                set_error("node %d is an EOL node: only the Lagrangian branch of Forces::fill is implemented", a);
+                return EOLC_ERR_UNSUPPORTED;
+            }
+    for (int64_t i = 0; i < 3 * (int64_t)F; ++i) EOLC_REQUIRE(face_nodes[i] >= 0 && face_nodes[i] < N, "face node index out of range");
+    for (int32_t i = 0; i < F; ++i) {
+        const int32_t *v = face_nodes + 3 * (size_t)i;
+        EOLC_REQUIRE(v[0] != v[1] && v[1] != v[2] && v[0] != v[2], "degenerate face (repeated node)");
+    }
+    EOLC_CUDA(cudaSetDevice(ctx->device));
+    eolc_forces_plan *P = new eolc_forces_plan;
+    P->ctx = ctx; P->N = N; P->F = F; P->E = E; P->dof = 3 * N;
+    P->h_face_nodes.assign(face_nodes, face_nodes + 3 * (size_t)F);
+    for (int32_t e = 0; e < E; ++e) {
+        const int32_t *s = edge_stencil + 4 * (size_t)e;
+        if (s[2] < 0 || s[3] < 0) continue;  // boundary edge, Forces.cpp:688-690
+        for (int v = 0; v < 4; ++v)
+            if (s[v] >= N) { delete P; set_error("edge stencil index out of range"); return EOLC_ERR_ARG; }
+        if (s[0] < 0 || s[1] < 0) { delete P; set_error("edge stencil index out of range"); return EOLC_ERR_ARG; }
+        P->h_iedge.insert(P->h_iedge.end(), s, s + 4);
+    }
+    P->Ei = (int32_t)(P->h_iedge.size() / 4);
+    int rc = build_pattern(P);
+    if (rc) { delete P; return rc; }
+    cudaStream_t st = ctx->stream;
+    cudaError_t ce = P->d_face_nodes.upload(P->h_face_nodes, st);
+    if (ce == cudaSuccess) ce = P->d_iedge.upload(P->h_iedge, st);
+    if (ce != cudaSuccess) { delete P; set_error("upload failed: %s", cudaGetErrorString(ce)); return EOLC_ERR_CUDA; }
+    rc = build_contribs(P, st);
+    if (rc) { delete P; return rc; }
+    *out = P;
+    return EOLC_OK;
+}
+
+void eolc_forces_plan_destroy(eolc_forces_plan *plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->ctx->device);
+    delete plan;
+}
+
+int eolc_forces_pattern(const eolc_forces_plan *plan, int which, int32_t *dof, int64_t *nnz, const int32_t **outer,
+                        const int32_t **inner) {
+    EOLC_REQUIRE(plan && (which == 0 || which == 1), "bad arguments");
+    eolc_forces_plan *P = const_cast<eolc_forces_plan *>(plan);
+    if (dof) *dof = P->dof;
+    if (nnz) *nnz = which ? P->nnzK : P->nnzM;
+    if (outer || inner) {
+        std::vector<int32_t> &o = which ? P->h_outerK : P->h_outerM, &in = which ? P->h_innerK : P->h_innerM;
+        if (o.empty()) build_eigen_arrays(P->N, which ? P->h_blkptrK : P->h_blkptrM, which ? P->h_nbrK : P->h_nbrM, o, in);
+        if (outer) *outer = o.data();
+        if (inner) *inner = in.data();
+    }
+    return EOLC_OK;
+}
+
+int eolc_forces_counts(const eolc_forces_plan *plan, int32_t *n_faces, int32_t *n_interior_edges) {
+    EOLC_REQUIRE(plan, "plan is NULL");
+    if (n_faces) *n_faces = plan->F;
+    if (n_interior_edges) *n_interior_edges = plan->Ei;
+    return EOLC_OK;
+}
+
+int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return plan ? 5 : 0; }
+
+int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
+                                 const eolc_material *mat, const double grav[3], double h, double *f_dev,
+                                 double *M_vals_dev, double *MDK_vals_dev) {
+    EOLC_REQUIRE(plan && mat && grav, "NULL argument");
+    EOLC_REQUIRE(n_scenes >= 1, "n_scenes must be >= 1");
+    EOLC_REQUIRE(plan->N == 0 || (x_dev && X_dev && f_dev), "NULL device pointer");
+    EOLC_REQUIRE(plan->nnzM == 0 || (M_vals_dev && MDK_vals_dev), "NULL device pointer");
+    EOLC_CUDA(cudaSetDevice(plan->ctx->device));
+    return launch_fill(plan, n_scenes, x_dev, X_dev, mat, grav, h, f_dev, M_vals_dev, MDK_vals_dev);
+}
+
+int eolc_forces_fill_dev(eolc_forces_plan *plan, const double *x_dev, const double *X_dev, const eolc_material *mat,
+                         const double grav[3], double h, double *f_dev, double *M_vals_dev, double *MDK_vals_dev) {
+    return eolc_forces_fill_batched_dev(plan, 1, x_dev, X_dev, mat, grav, h, f_dev, M_vals_dev, MDK_vals_dev);
+}
+
+int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
+                     const double grav[3], double h, double *f, double *M_vals, double *MDK_vals) {
+    EOLC_REQUIRE(plan && mat && grav, "NULL argument");
+    eolc_forces_plan *P = plan;
+    EOLC_REQUIRE(P->N == 0 || (x && X && f), "NULL host pointer");
+    EOLC_REQUIRE(P->nnzM == 0 || (M_vals && MDK_vals), "NULL host pointer");
+    EOLC_CUDA(cudaSetDevice(P->ctx->device));
+    cudaStream_t st = P->ctx->stream;
+    const size_t N = P->N;
+    if (N == 0) return EOLC_OK;
+    EOLC_CUDA(P->d_x.ensure(3 * N)); EOLC_CUDA(P->d_X.ensure(2 * N)); EOLC_CUDA(P->d_f.ensure(3 * N));
+    EOLC_CUDA(P->d_Mv.ensure(P->nnzM)); EOLC_CUDA(P->d_Kv.ensure(P->nnzK));
+    // pinned (or registered) caller buffers are DMA'd directly; pageable ones go through the plan's pinned staging
+    auto pinned = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool in_pinned = pinned(x) && pinned(X);
+    const bool out_pinned = pinned(f) && pinned(M_vals) && pinned(MDK_vals);
+    const double *hx = x, *hX = X;
+    if (!in_pinned) {
+        EOLC_CUDA(P->p_in.ensure(5 * N));
+        memcpy(P->p_in.p, x, 3 * N * sizeof(double));
+        memcpy(P->p_in.p + 3 * N, X, 2 * N * sizeof(double));
+        hx = P->p_in.p; hX = P->p_in.p + 3 * N;
+    }
+    EOLC_CUDA(cudaMemcpyAsync(P->d_x.p, hx, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    EOLC_CUDA(cudaMemcpyAsync(P->d_X.p, hX, 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = launch_fill(P, 1, P->d_x.p, P->d_X.p, mat, grav, h, P->d_f.p, P->d_Mv.p, P->d_Kv.p);
+    if (rc) return rc;
+    double *hf = f, *hM = M_vals, *hK = MDK_vals;
+    if (!out_pinned) {
+        EOLC_CUDA(P->p_out.ensure(3 * N + P->nnzM + P->nnzK));
+        hf = P->p_out.p; hM = P->p_out.p + 3 * N; hK = P->p_out.p + 3 * N + P->nnzM;
+    }
+    EOLC_CUDA(cudaMemcpyAsync(hf, P->d_f.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaMemcpyAsync(hM, P->d_Mv.p, P->nnzM * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaMemcpyAsync(hK, P->d_Kv.p, P->nnzK * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));
+    if (!out_pinned) {
+        memcpy(f, hf, 3 * N * sizeof(double));
+        memcpy(M_vals, hM, P->nnzM * sizeof(double));
+        memcpy(MDK_vals, hK, P->nnzK * sizeof(double));
+    }
+    return EOLC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+"""Host-side mirror of the reference's `Forces` class (/root/reference/src/Forces.h:26-45) over the C ABI.
+
+    forces = Forces(ctx)
+    forces.fill(mesh_arrays, material, grav, h)      # == Forces::fill(mesh, mat, grav, h), Forces.cpp:912-930
+    forces.f, forces.M, forces.MDK, forces.EoL_cutoff
+
+`M` / `MDK` are (outer, inner, values) triples laid out exactly like the reference's column-major
+Eigen::SparseMatrix<double> (outerIndexPtr / innerIndexPtr / valuePtr).
+"""
+import ctypes
+from collections import namedtuple
+
+import numpy as np
+
+from . import capi
+
+Material = namedtuple("Material", "density e nu beta dampingA dampingB")
+# simulationSettings.json:27-33
+Material.DEFAULT = Material(0.05, 50.0, 0.01, 1.0e-5, 0.0, 1.0)
+
+
+def _matc(mat):
+    return capi.MaterialC(*[float(v) for v in mat])
+
+
+class ForcesPlan:
+    """eolc_forces_plan: the fixed CSR pattern + element->slot maps; rebuild only after a remesh."""
+
+    def __init__(self, ctx, n_nodes, face_nodes, edge_stencil, eol_index=None, X_hint=None):
+        self.ctx = ctx
+        self._h = capi.c_vp()
+        fn = capi.i32(face_nodes).reshape(-1, 3)
+        es = capi.i32(edge_stencil).reshape(-1, 4)
+        eol = None if eol_index is None else capi.i32(eol_index)
+        xh = None if X_hint is None else capi.f64(X_hint)
+        capi.check(capi.lib().eolc_forces_plan_create(
+            ctx.handle, int(n_nodes), fn.shape[0], capi.iptr(fn), es.shape[0], capi.iptr(es),
+            None if eol is None else capi.iptr(eol), None if xh is None else capi.dptr(xh), ctypes.byref(self._h)))
+        self.N = int(n_nodes)
+        self.dof = 3 * self.N
+        nf, ne = ctypes.c_int32(), ctypes.c_int32()
+        capi.check(capi.lib().eolc_forces_counts(self._h, ctypes.byref(nf), ctypes.byref(ne)))
+        self.n_faces, self.n_interior_edges = nf.value, ne.value
+        self.nnz = [self._nnz(0), self._nnz(1)]
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _nnz(self, which):
+        nnz = ctypes.c_int64()
+        capi.check(capi.lib().eolc_forces_pattern(self._h, which, None, ctypes.byref(nnz), None, None))
+        return nnz.value
+
+    def pattern(self, which):
+        """(outer, inner) int32 arrays == Eigen outerIndexPtr()/innerIndexPtr() of M (0) or MDK (1)."""
+        dof, nnz = ctypes.c_int32(), ctypes.c_int64()
+        outer, inner = capi.c_ip(), capi.c_ip()
+        capi.check(capi.lib().eolc_forces_pattern(self._h, which, ctypes.byref(dof), ctypes.byref(nnz),
+                                                  ctypes.byref(outer), ctypes.byref(inner)))
+        o = np.ctypeslib.as_array(outer, (dof.value + 1,)).copy()
+        i = np.ctypeslib.as_array(inner, (max(nnz.value, 1),))[:nnz.value].copy()
+        return o, i
+
+    @property
+    def launches_per_fill(self):
+        return capi.lib().eolc_forces_launches_per_fill(self._h)
+
+    def fill(self, x, X, mat, grav, h):
+        """Host arrays in, host arrays out (H2D / D2H inside): returns f, M_vals, MDK_vals."""
+        x = capi.f64(x).reshape(-1)
+        X = capi.f64(X).reshape(-1)
+        if x.size != 3 * self.N or X.size != 2 * self.N:
+            raise capi.EolcError("x must hold 3N and X 2N doubles")
+        g = capi.f64(grav)
+        f = np.empty(self.dof)
+        Mv = np.empty(self.nnz[0])
+        Kv = np.empty(self.nnz[1])
+        m = _matc(mat)
+        capi.check(capi.lib().eolc_forces_fill(self._h, capi.dptr(x), capi.dptr(X), ctypes.byref(m), capi.dptr(g),
+                                               float(h), capi.dptr(f), capi.dptr(Mv), capi.dptr(Kv)))
+        return f, Mv, Kv
+
+    def fill_into(self, x, X, mat, grav, h, f, Mv, Kv):
+        """Same as fill() but into caller-provided contiguous float64 arrays (no allocation in the timed region)."""
+        g = capi.f64(grav)
+        m = _matc(mat)
+        capi.check(capi.lib().eolc_forces_fill(self._h, capi.dptr(x), capi.dptr(X), ctypes.byref(m), capi.dptr(g),
+                                               float(h), capi.dptr(f), capi.dptr(Mv), capi.dptr(Kv)))
+
+    def fill_dev(self, x_ptr, X_ptr, mat, grav, h, f_ptr, Mv_ptr, Kv_ptr, n_scenes=1):
+        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on ctx.stream."""
+        g = capi.f64(grav)
+        m = _matc(mat)
+        capi.check(capi.lib().eolc_forces_fill_batched_dev(self._h, int(n_scenes), x_ptr, X_ptr, ctypes.byref(m),
+                                                           capi.dptr(g), float(h), f_ptr, Mv_ptr, Kv_ptr))
+
+    def close(self):
+        if self._h:
+            capi.lib().eolc_forces_plan_destroy(self._h)
+            self._h = capi.c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Forces:
+    """Mirror of `class Forces` (Forces.h:26-45): members f, M, MDK, EoL_cutoff; method fill()."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.f = None
+        self.M = None
+        self.MDK = None
+        self.EoL_cutoff = 0
+        self._plan = None
+        self._topo_key = None
+
+    def fill(self, mesh, mat, grav, h):
+        """mesh: dict(x (N,3), X (N,2), face_nodes (F,3), edge_stencil (E,4)) — the flattened ArcSim mesh
+        (SURVEY Appendix B).  The topology plan is cached and rebuilt when the topology arrays change (remesh)."""
+        fn = capi.i32(mesh["face_nodes"]).reshape(-1, 3)
+        es = capi.i32(mesh["edge_stencil"]).reshape(-1, 4)
+        N = np.asarray(mesh["x"]).reshape(-1, 3).shape[0]
+        key = (N, fn.shape[0], es.shape[0], hash(fn.tobytes()), hash(es.tobytes()))
+        if key != self._topo_key:
+            if self._plan is not None:
+                self._plan.close()
+            self._plan = ForcesPlan(self.ctx, N, fn, es, mesh.get("eol_index"), mesh.get("X"))
+            self._topo_key = key
+            self._pat = [self._plan.pattern(0), self._plan.pattern(1)]
+        f, Mv, Kv = self._plan.fill(mesh["x"], mesh["X"], mat, grav, h)
+        self.f = f
+        self.M = (self._pat[0][0], self._pat[0][1], Mv)
+        self.MDK = (self._pat[1][0], self._pat[1][1], Kv)
+        self.EoL_cutoff = 3 * N           # Forces.cpp:919
+        return self

@@ -1,0 +1,145 @@
+/* eolc.h — C ABI of the B200-native EOL-Cloth hot path (libeolc_b200.so).
+ *
+ * This is the drop-in boundary under the reference's three C++ entry points
+ *   Forces::fill   /root/reference/src/Forces.h:40     (body: src/Forces.cpp:912-930)
+ *   CD             /root/reference/src/Collisions.h:9  (body: src/Collisions.cpp:11-53)
+ *   CD2            /root/reference/src/Collisions.h:11 (body: src/Collisions.cpp:55-78)
+ * whose call sites (src/Cloth.cpp:365, src/Scene.cpp:83, src/Constraints.cpp:423) stay
+ * unchanged; the C++ adapter bodies that forward to these functions are shown in
+ * INTEGRATION.md.  Plain pointers and sizes only; no C++/torch types cross this ABI.
+ *
+ * Conventions: every function returns 0 on success and a negative eolc_status on
+ * error; eolc_last_error() returns the message of the last failure on this thread.
+ * Arrays are caller-owned HOST pointers unless the function name ends in _dev.
+ * A ctx binds one CUDA device; it must be used from one host thread at a time
+ * (the reference has a single simulation thread, src/runner.cpp:58-63,121-129).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails
+ * with EOLC_ERR_CUDA.
+ *
+ * Simplifying assumption (true for Cloth::build, src/Cloth.cpp:73-90): one Vert per
+ * Node, so the material coordinate X = node->verts[0]->u is per node.
+ * Only the Lagrangian (non-EOL) branch of Forces::fill is implemented
+ * (mesh.EoL_Count == 0, every BASELINE config); plan creation rejects EOL nodes.
+ */
+#ifndef EOLC_H_
+#define EOLC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    EOLC_OK = 0,
+    EOLC_ERR_ARG = -1,      /* bad argument (NULL, negative size, index out of range) */
+    EOLC_ERR_CUDA = -2,     /* CUDA runtime failure / no device */
+    EOLC_ERR_CAPACITY = -3, /* caller buffer too small (n_out still reports the needed size) */
+    EOLC_ERR_UNSUPPORTED = -4
+} eolc_status;
+
+typedef struct eolc_ctx eolc_ctx;
+typedef struct eolc_forces_plan eolc_forces_plan;
+typedef struct eolc_cd_plan eolc_cd_plan;
+
+/* mirrors `struct Material`, src/Cloth.h:28-35 (dampingA is never read by Forces.cpp) */
+typedef struct {
+    double density, e, nu, beta, dampingA, dampingB;
+} eolc_material;
+
+/* POD mirror of btc::Collision, src/boxTriCollision.h:49-110 (ctor boxTriCollision.cpp:103-120).
+ * edge1 is a std::vector<int> of size 0, 1 or 3 in the reference -> edge1[3] + n_edge1. */
+typedef struct {
+    double dist;
+    double nor1[3], nor2[3], pos1[3], pos2[3], pos1_[3];
+    double weights1[3], weights2[3];
+    double edgeDir[3];
+    int32_t count1, count2;
+    int32_t verts1[3], verts2[3];
+    int32_t tri1, tri2;
+    int32_t edge1[3];
+    int32_t n_edge1;
+    int32_t edge2;
+    int32_t reserved;
+} eolc_contact;
+
+/* ---- context ---------------------------------------------------------------------- */
+int eolc_ctx_create(int device, eolc_ctx **out);
+void eolc_ctx_destroy(eolc_ctx *ctx);
+const char *eolc_last_error(void);
+int eolc_device_count(void);
+/* the CUDA stream all work of this ctx is launched on (a cudaStream_t), for event timing */
+void *eolc_ctx_stream(eolc_ctx *ctx);
+
+/* ---- mesh flattening helper --------------------------------------------------------- */
+/* Reproduces the edge list ArcSim builds while faces are added (Mesh::add(Face),
+ * src/external/ArcSim/mesh.cpp:356-378): edge order = creation order, n[0]->n[1] = direction of
+ * the creating face, adjf[0] = creating face.  Writes 4 ints per edge:
+ * (n0, n1, opp(adjf[0]), opp(adjf[1])), -1 where the face is absent — exactly the stencil
+ * edgeBasedF reads (src/Forces.cpp:688-697).  edge_stencil must hold 4*3F ints. */
+int eolc_mesh_edge_stencils(int32_t N, int32_t F, const int32_t *face_nodes, int32_t *E_out, int32_t *edge_stencil);
+
+/* ---- Forces::fill ------------------------------------------------------------------- */
+/* Topology plan: CSR pattern of M and MDK + element->slot maps. Rebuild only after a remesh /
+ * set_indices (src/Scene.cpp:87-90).  X_hint (2N, may be NULL) is used only to group nodes into
+ * spatially compact tiles; results do not depend on it. eol_index (N, may be NULL): -1 = Lagrangian. */
+int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face_nodes, int32_t E,
+                            const int32_t *edge_stencil, const int32_t *eol_index, const double *X_hint,
+                            eolc_forces_plan **out);
+void eolc_forces_plan_destroy(eolc_forces_plan *plan);
+/* which: 0 = M, 1 = MDK.  outer (dof+1) / inner (nnz, ascending) are host arrays owned by the plan and are
+ * identical to Eigen's outerIndexPtr()/innerIndexPtr() of the column-major matrices the reference builds with
+ * setFromTriplets (src/Forces.cpp:928-929); both matrices are symmetric, so CSC == CSR. */
+int eolc_forces_pattern(const eolc_forces_plan *plan, int which, int32_t *dof, int64_t *nnz, const int32_t **outer,
+                        const int32_t **inner);
+/* counts for the metric: faces + interior edges assembled per fill */
+int eolc_forces_counts(const eolc_forces_plan *plan, int32_t *n_faces, int32_t *n_interior_edges);
+/* One Forces::fill.  x: 3N (Node::x), X: 2N (verts[0]->u), outputs f (dof), M_vals (nnz(M)), MDK_vals (nnz(MDK)).
+ * Host version copies x/X in and f/M/MDK out (pinned staging inside the plan). */
+int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
+                     const double grav[3], double h, double *f, double *M_vals, double *MDK_vals);
+/* Same, every pointer is a DEVICE pointer on the plan's device; asynchronous on eolc_ctx_stream(). */
+int eolc_forces_fill_dev(eolc_forces_plan *plan, const double *x_dev, const double *X_dev, const eolc_material *mat,
+                         const double grav[3], double h, double *f_dev, double *M_vals_dev, double *MDK_vals_dev);
+/* Ensemble: n_scenes independent states sharing the plan's topology; scene s reads x_dev + s*3N, X_dev + s*2N and
+ * writes f_dev + s*dof, M_vals_dev + s*nnz(M), MDK_vals_dev + s*nnz(MDK). */
+int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
+                                 const eolc_material *mat, const double grav[3], double h, double *f_dev,
+                                 double *M_vals_dev, double *MDK_vals_dev);
+/* number of kernels one fill launches (for bench accounting) */
+int eolc_forces_launches_per_fill(const eolc_forces_plan *plan);
+
+/* ---- CD / CD2 ----------------------------------------------------------------------- */
+/* Builds the btc edge table in createEdges order (src/boxTriCollision.cpp:141-231, 64-bit sort key — see
+ * DESIGN.md) and the perturbation table for (N, threshold) (std::mt19937 seed 1, :648-659). */
+int eolc_cd_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face_nodes, double threshold,
+                        eolc_cd_plan **out);
+void eolc_cd_plan_destroy(eolc_cd_plan *plan);
+int eolc_cd_edge_count(const eolc_cd_plan *plan);
+/* host copy of the btc edge table: 4 verts + 2 faces per edge (6 ints), createEdges order */
+int eolc_cd_edge_table(const eolc_cd_plan *plan, int32_t *out6E);
+/* CD  = eolc_cd_run(..., point_eol_flag=1, remap_box_indices=1)   (src/Collisions.cpp:30,39-48)
+ * CD2 = eolc_cd_run(..., point_eol_flag=0, remap_box_indices=0)   (src/Collisions.cpp:71)
+ * pxyz / pnorms: 3 x n_points column-major (Points::pxyz / norms); box_whd: 3 per box (Box::dim);
+ * box_E: 16 per box, column-major 4x4 (Box::E1).  Contacts are written in the reference's list order.
+ * On EOLC_ERR_CAPACITY *n_out holds the required capacity. */
+int eolc_cd_run(eolc_cd_plan *plan, const double *x, int32_t n_points, const double *pxyz, const double *pnorms,
+                int32_t n_boxes, const double *box_whd, const double *box_E, int point_eol_flag, int remap_box_indices,
+                eolc_contact *out, int32_t capacity, int32_t *n_out);
+/* x_dev is a device pointer (3N); contacts still land in host memory (the list is small). */
+int eolc_cd_run_dev(eolc_cd_plan *plan, const double *x_dev, int32_t n_points, const double *pxyz, const double *pnorms,
+                    int32_t n_boxes, const double *box_whd, const double *box_E, int point_eol_flag,
+                    int remap_box_indices, eolc_contact *out, int32_t capacity, int32_t *n_out);
+/* Ensemble: n_scenes states (x_dev + s*3N) against the same obstacles.  Contacts of scene s are written to
+ * out[scene_offset[s] .. scene_offset[s+1]) ; scene_offset has n_scenes+1 entries. */
+int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t n_scenes, const double *x_dev, int32_t n_points,
+                            const double *pxyz, const double *pnorms, int32_t n_boxes, const double *box_whd,
+                            const double *box_E, int point_eol_flag, int remap_box_indices, eolc_contact *out,
+                            int32_t capacity, int32_t *scene_offset);
+/* counters of the last run: candidate pair tests executed on the device (A: N*24, B: 8*F, C: E*12 after culls) */
+int eolc_cd_last_stats(const eolc_cd_plan *plan, int64_t *pair_tests, int32_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EOLC_H_ */

@@ -1,0 +1,297 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+//
+// CPU restatement of the reference's Forces::fill (non-EOL branch) over flat
+// arrays, Eigen-free, single-threaded, linking the reference's own generated
+// arithmetic (ComputeMembrane.cpp / ComputeBending.cpp / ComputeInertial.cpp,
+// compiled UNMODIFIED from /root/reference/src into oracle/_ref/ by
+// oracle/Makefile).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this.
+//
+// PARITY UNPINNED by the reference's own tests: the reference ships no tests or
+// golden vectors and Eigen is absent, so Forces.cpp itself cannot be
+// compiled here.  What IS pinned: the three Compute* kernels are the reference's
+// own object code, and the known-answer vectors of SURVEY.md §8c are checked in
+// tests/test_oracle.py.  The glue below follows the reference line by line:
+//
+//   poldec            src/Forces.cpp:33-52
+//   faceBasedF        src/Forces.cpp:331-397 (frame, F, Fbar, Q) and :498-518 (non-EOL scatter)
+//   fillxMI/fillxxMI  src/Forces.cpp:103-125
+//   edgeBasedF        src/Forces.cpp:685-744 and :885-908 (non-EOL scatter)
+//   fillxB/fillxxB    src/Forces.cpp:522-539
+//   Forces::fill      src/Forces.cpp:912-930
+//   setFromTriplets   Eigen 3.3 SparseMatrix.h set_from_triplets (external, restated
+//                     from its published algorithm: bucket by row in insertion order,
+//                     collapse duplicates onto the first occurrence left-to-right,
+//                     transposed copy -> column-major with sorted inner indices;
+//                     explicit zeros are kept).
+//
+// Eigen small-vector arithmetic conventions restated here (Eigen 3.3.x, SSE2,
+// EIGEN_DONT_ALIGN_STATICALLY — Forces.h:13): a 3-vector dot/squaredNorm is the
+// linear-vectorised redux  (p0 + p1) + p2 ;  v / s is a true division per
+// component; cross is the textbook formula; DX.inverse() (dynamic 2x2, Eigen uses
+// PartialPivLU) is restated in closed form (adjugate / det) — an O(1 ulp)
+// difference, inside the 1e-10 budget (SURVEY.md §8c rule 4).
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <chrono>
+
+// reference prototypes, exactly as in src/Compute*.h (C++ linkage)
+void ComputeMembrane(const double *xa, const double *xb, const double *xc,
+                     const double *Xa, const double *Xb, const double *Xc,
+                     double e, double nu, const double *P, const double *Q,
+                     double *W, double *f, double *K);
+void ComputeBending(const double *x0, const double *x1, const double *x2, const double *x3,
+                    const double *X0, const double *X1, const double *X2, const double *X3,
+                    double beta, double *W, double *f, double *K);
+void ComputeInertial(const double *xa, const double *xb, const double *xc,
+                     const double *Xa, const double *Xb, const double *Xc,
+                     const double *g, double rho, double *W, double *f, double *M);
+
+namespace {
+
+struct Trip { int32_t r, c; double v; };
+
+inline double dot3(const double *a, const double *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+inline void cross3(double *d, const double *a, const double *b) {
+    d[0] = a[1] * b[2] - a[2] * b[1];
+    d[1] = a[2] * b[0] - a[0] * b[2];
+    d[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// Forces.cpp:33-52 ; M and Q column-major 2x2
+void poldec(const double *M, double *Q) {
+    double m11 = M[0], m21 = M[1], m12 = M[2], m22 = M[3];
+    double detM = m11 * m22 - m12 * m21;
+    int sign = 1;
+    if (detM < 0) sign = -1;
+    else if (detM == 0) sign = 0;
+    // MM << m22, -m21, -m12, m11  (row-major fill): MM(0,0)=m22 MM(0,1)=-m21 MM(1,0)=-m12 MM(1,1)=m11
+    double q00 = m11 + sign * m22;
+    double q01 = m12 + sign * (-m21);
+    double q10 = m21 + sign * (-m12);
+    double q11 = m22 + sign * m11;
+    double clen = std::sqrt(q00 * q00 + q10 * q10);
+    Q[0] = q00 / clen; Q[1] = q10 / clen; Q[2] = q01 / clen; Q[3] = q11 / clen;
+}
+
+struct Csc {
+    int64_t nnz = 0;
+    std::vector<int32_t> outer, inner;
+    std::vector<double> vals;
+};
+
+// Eigen 3.3 set_from_triplets, restated.  Result: column-major compressed.
+void set_from_triplets(int dof, const std::vector<Trip> &T, Csc &out) {
+    // pass 1: count per row (trMat is row-major)
+    std::vector<int64_t> start(dof + 1, 0);
+    for (const Trip &t : T) start[t.r + 1]++;
+    for (int i = 0; i < dof; ++i) start[i + 1] += start[i];
+    // pass 2: insertBackUncompressed -> each row keeps insertion order
+    std::vector<int32_t> tc(T.size());
+    std::vector<double> tv(T.size());
+    {
+        std::vector<int64_t> fillp(start.begin(), start.end() - 1);
+        for (const Trip &t : T) { int64_t p = fillp[t.r]++; tc[p] = t.c; tv[p] = t.v; }
+    }
+    // pass 3: collapseDuplicates: per row, first occurrence keeps the slot, later ones add into it
+    std::vector<int64_t> wi(dof, -1);
+    std::vector<int64_t> rstart(dof + 1, 0);
+    int64_t count = 0;
+    for (int r = 0; r < dof; ++r) {
+        int64_t s = count;
+        rstart[r] = s;
+        for (int64_t k = start[r]; k < start[r + 1]; ++k) {
+            int32_t c = tc[k];
+            if (wi[c] >= s) {
+                tv[wi[c]] = tv[wi[c]] + tv[k];   // dup_func = scalar_sum_op: old + new
+            } else {
+                tv[count] = tv[k]; tc[count] = c; wi[c] = count; ++count;
+            }
+        }
+    }
+    rstart[dof] = count;
+    // pass 4: mat = trMat (transposed copy): column-major, rows ascending within a column
+    out.nnz = count;
+    out.outer.assign(dof + 1, 0);
+    for (int64_t k = 0; k < count; ++k) out.outer[tc[k] + 1]++;
+    for (int i = 0; i < dof; ++i) out.outer[i + 1] += out.outer[i];
+    out.inner.resize(count); out.vals.resize(count);
+    std::vector<int32_t> pos(out.outer.begin(), out.outer.end() - 1);
+    for (int r = 0; r < dof; ++r)
+        for (int64_t k = rstart[r]; k < rstart[r + 1]; ++k) {
+            int32_t p = pos[tc[k]]++;
+            out.inner[p] = r; out.vals[p] = tv[k];
+        }
+}
+
+struct Result {
+    int dof = 0;
+    std::vector<double> f;
+    Csc M, MDK;
+    double seconds_elements = 0, seconds_assembly = 0;
+};
+
+}  // namespace
+
+extern "C" {
+
+// mat = {density, e, nu, beta, dampingA, dampingB}  (src/Cloth.h:28-35)
+// edge_stencil: 4 ints per mesh edge (n0, n1, opp(adjf0), opp(adjf1)); -1 in slot 2/3 = boundary.
+// flags bit0: skip the assembly (setFromTriplets) — used only by the cpu_baseline timing split.
+void *oracle_forces_fill(int N, int F, const int32_t *face_nodes, int E, const int32_t *edge_stencil,
+                         const double *x, const double *X, const double *mat, const double *grav, double h,
+                         int flags) {
+    auto t0 = std::chrono::steady_clock::now();
+    Result *R = new Result;
+    const int dof = 3 * N;  // EoL_Count == 0 (non-EOL branch only)
+    R->dof = dof;
+    R->f.assign(dof, 0.0);                       // Forces.cpp:914-915
+    std::vector<Trip> M_, MDK_;                  // :916-917
+    const double density = mat[0], e = mat[1], nu = mat[2], beta = mat[3], dampingB = mat[5];
+
+    // ---- faceBasedF, Forces.cpp:331-520 ----
+    for (int i = 0; i < F; ++i) {
+        const int ia = face_nodes[3 * i], ib = face_nodes[3 * i + 1], ic = face_nodes[3 * i + 2];
+        const double *xa = x + 3 * ia, *xb = x + 3 * ib, *xc = x + 3 * ic;
+        const double *Xa = X + 2 * ia, *Xb = X + 2 * ib, *Xc = X + 2 * ic;
+        double PP[6], QQ[4], Wi[1], Wm[1];
+        double d1[3] = {xb[0] - xa[0], xb[1] - xa[1], xb[2] - xa[2]};   // Dxt col 0
+        double d2[3] = {xc[0] - xa[0], xc[1] - xa[1], xc[2] - xa[2]};   // Dxt col 1
+        double DX[4] = {Xb[0] - Xa[0], Xb[1] - Xa[1], Xc[0] - Xa[0], Xc[1] - Xa[1]};  // col-major
+        double normm[3]; cross3(normm, d1, d2);                          // :361
+        double l1 = std::sqrt(dot3(d1, d1));
+        double Pxm[3] = {d1[0] / l1, d1[1] / l1, d1[2] / l1};            // :362
+        double Pym[3]; cross3(Pym, normm, Pxm);                          // :363
+        double l2 = std::sqrt(dot3(Pym, Pym));
+        Pym[0] /= l2; Pym[1] /= l2; Pym[2] /= l2;                        // :364
+        // DX.inverse(), closed form
+        double det = DX[0] * DX[3] - DX[2] * DX[1];
+        double inv[4] = {DX[3] / det, -DX[1] / det, -DX[2] / det, DX[0] / det};  // col-major
+        // Fm = Dxt * inv  (3x2), col-major
+        double Fm[6];
+        for (int r = 0; r < 3; ++r) {
+            Fm[r] = d1[r] * inv[0] + d2[r] * inv[1];
+            Fm[3 + r] = d1[r] * inv[2] + d2[r] * inv[3];
+        }
+        // Fbarm = Pm * Fm (2x2), col-major
+        double Fb[4] = {dot3(Pxm, Fm), dot3(Pym, Fm), dot3(Pxm, Fm + 3), dot3(Pym, Fm + 3)};
+        poldec(Fb, QQ);                                                  // :369
+        // PP column-major 2x3                                            // :371
+        PP[0] = Pxm[0]; PP[1] = Pym[0]; PP[2] = Pxm[1]; PP[3] = Pym[1]; PP[4] = Pxm[2]; PP[5] = Pym[2];
+        double fm[9], Km[81], fi[9], Mi[81];
+        ComputeMembrane(xa, xb, xc, Xa, Xb, Xc, e, nu, PP, QQ, Wm, fm, Km);   // :389
+        ComputeInertial(xa, xb, xc, Xa, Xb, Xc, grav, density, Wi, fi, Mi);   // :390
+        // Kme(r,c) = Km[c*9+r] (column-major Map, :393)
+        const int idx[3] = {3 * ia, 3 * ib, 3 * ic};
+        for (int v = 0; v < 3; ++v)                                           // :500-502
+            for (int j = 0; j < 3; ++j) R->f[idx[v] + j] += fm[3 * v + j] + fi[3 * v + j];
+        const double dhh = dampingB * h * h;                                  // damping(1)*h*h, :105
+        auto Kme = [&](int r, int c) { return Km[c * 9 + r]; };
+        auto Mie = [&](int r, int c) { return Mi[c * 9 + r]; };
+        // fillxMI  :103-112   (diag blocks a, b, c  :504-510)
+        for (int v = 0; v < 3; ++v)
+            for (int j = 0; j < 3; ++j)
+                for (int k = 0; k < 3; ++k) {
+                    double m = Mie(3 * v + j, 3 * v + k);
+                    double mdk = m + dhh * Kme(3 * v + j, 3 * v + k);
+                    M_.push_back({idx[v] + j, idx[v] + k, m});
+                    MDK_.push_back({idx[v] + j, idx[v] + k, mdk});
+                }
+        // fillxxMI :114-125   (off-diag (a,b), (a,c), (b,c)  :512-517)
+        const int pr[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+        for (int p = 0; p < 3; ++p) {
+            int v0 = pr[p][0], v1 = pr[p][1];
+            for (int j = 0; j < 3; ++j)
+                for (int k = 0; k < 3; ++k) {
+                    double m = Mie(3 * v0 + j, 3 * v1 + k);
+                    double mdk = m + dhh * Kme(3 * v0 + j, 3 * v1 + k);
+                    M_.push_back({idx[v0] + j, idx[v1] + k, m});
+                    M_.push_back({idx[v1] + k, idx[v0] + j, m});
+                    MDK_.push_back({idx[v0] + j, idx[v1] + k, mdk});
+                    MDK_.push_back({idx[v1] + k, idx[v0] + j, mdk});
+                }
+        }
+    }
+
+    // ---- edgeBasedF, Forces.cpp:685-910 ----
+    for (int ed = 0; ed < E; ++ed) {
+        const int32_t *s = edge_stencil + 4 * ed;
+        if (s[2] < 0 || s[3] < 0) continue;                                   // :688-690
+        double Wb[1], fb[12], Kb[144];
+        ComputeBending(x + 3 * s[0], x + 3 * s[1], x + 3 * s[2], x + 3 * s[3],
+                       X + 2 * s[0], X + 2 * s[1], X + 2 * s[2], X + 2 * s[3], beta, Wb, fb, Kb);  // :741
+        const double dhh = dampingB * h * h;
+        auto Kbe = [&](int r, int c) { return Kb[c * 12 + r]; };              // :744
+        const int idx[4] = {3 * s[0], 3 * s[1], 3 * s[2], 3 * s[3]};
+        for (int v = 0; v < 4; ++v)                                           // fillxB :886-893
+            for (int j = 0; j < 3; ++j)
+                for (int k = 0; k < 3; ++k)
+                    MDK_.push_back({idx[v] + j, idx[v] + k, dhh * Kbe(3 * v + j, 3 * v + k)});
+        const int pr[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};  // fillxxB :895-906
+        for (int p = 0; p < 6; ++p) {
+            int v0 = pr[p][0], v1 = pr[p][1];
+            for (int j = 0; j < 3; ++j)
+                for (int k = 0; k < 3; ++k) {
+                    double kv = dhh * Kbe(3 * v0 + j, 3 * v1 + k);
+                    MDK_.push_back({idx[v0] + j, idx[v1] + k, kv});
+                    MDK_.push_back({idx[v1] + k, idx[v0] + j, kv});
+                }
+        }
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (!(flags & 1)) {
+        set_from_triplets(dof, M_, R->M);                                     // :928
+        set_from_triplets(dof, MDK_, R->MDK);                                 // :929
+    }
+    auto t2 = std::chrono::steady_clock::now();
+    R->seconds_elements = std::chrono::duration<double>(t1 - t0).count();
+    R->seconds_assembly = std::chrono::duration<double>(t2 - t1).count();
+    return R;
+}
+
+int oracle_forces_dof(void *r) { return ((Result *)r)->dof; }
+const double *oracle_forces_f(void *r) { return ((Result *)r)->f.data(); }
+int64_t oracle_forces_nnz(void *r, int which) { return (which ? ((Result *)r)->MDK : ((Result *)r)->M).nnz; }
+const int32_t *oracle_forces_outer(void *r, int which) { return (which ? ((Result *)r)->MDK : ((Result *)r)->M).outer.data(); }
+const int32_t *oracle_forces_inner(void *r, int which) { return (which ? ((Result *)r)->MDK : ((Result *)r)->M).inner.data(); }
+const double *oracle_forces_vals(void *r, int which) { return (which ? ((Result *)r)->MDK : ((Result *)r)->M).vals.data(); }
+double oracle_forces_seconds(void *r, int which) { return which ? ((Result *)r)->seconds_assembly : ((Result *)r)->seconds_elements; }
+void oracle_forces_free(void *r) { delete (Result *)r; }
+
+// thin pass-throughs so tests can pin the reference kernels against SURVEY §8c known answers
+void oracle_compute_membrane(const double *xa, const double *xb, const double *xc, const double *Xa, const double *Xb,
+                             const double *Xc, double e, double nu, const double *P, const double *Q, double *W,
+                             double *f, double *K) { ComputeMembrane(xa, xb, xc, Xa, Xb, Xc, e, nu, P, Q, W, f, K); }
+void oracle_compute_bending(const double *x0, const double *x1, const double *x2, const double *x3, const double *X0,
+                            const double *X1, const double *X2, const double *X3, double beta, double *W, double *f,
+                            double *K) { ComputeBending(x0, x1, x2, x3, X0, X1, X2, X3, beta, W, f, K); }
+void oracle_compute_inertial(const double *xa, const double *xb, const double *xc, const double *Xa, const double *Xb,
+                             const double *Xc, const double *g, double rho, double *W, double *f, double *M) {
+    ComputeInertial(xa, xb, xc, Xa, Xb, Xc, g, rho, W, f, M);
+}
+// frame + polar decomposition of one face, for unit tests (Forces.cpp:357-372)
+void oracle_face_frame(const double *xa, const double *xb, const double *xc, const double *Xa, const double *Xb,
+                       const double *Xc, double *PP, double *QQ) {
+    double d1[3] = {xb[0] - xa[0], xb[1] - xa[1], xb[2] - xa[2]};
+    double d2[3] = {xc[0] - xa[0], xc[1] - xa[1], xc[2] - xa[2]};
+    double DX[4] = {Xb[0] - Xa[0], Xb[1] - Xa[1], Xc[0] - Xa[0], Xc[1] - Xa[1]};
+    double normm[3]; cross3(normm, d1, d2);
+    double l1 = std::sqrt(dot3(d1, d1));
+    double Pxm[3] = {d1[0] / l1, d1[1] / l1, d1[2] / l1};
+    double Pym[3]; cross3(Pym, normm, Pxm);
+    double l2 = std::sqrt(dot3(Pym, Pym));
+    Pym[0] /= l2; Pym[1] /= l2; Pym[2] /= l2;
+    double det = DX[0] * DX[3] - DX[2] * DX[1];
+    double inv[4] = {DX[3] / det, -DX[1] / det, -DX[2] / det, DX[0] / det};
+    double Fm[6];
+    for (int r = 0; r < 3; ++r) { Fm[r] = d1[r] * inv[0] + d2[r] * inv[1]; Fm[3 + r] = d1[r] * inv[2] + d2[r] * inv[3]; }
+    double Fb[4] = {dot3(Pxm, Fm), dot3(Pym, Fm), dot3(Pxm, Fm + 3), dot3(Pym, Fm + 3)};
+    poldec(Fb, QQ);
+    PP[0] = Pxm[0]; PP[1] = Pym[0]; PP[2] = Pxm[1]; PP[3] = Pym[1]; PP[4] = Pxm[2]; PP[5] = Pym[2];
+}
+
+}  // extern "C"

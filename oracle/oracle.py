@@ -1,0 +1,226 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (eol_cloth_b200) never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_dp = ctypes.POINTER(ctypes.c_double)
+c_ip = ctypes.POINTER(ctypes.c_int32)
+
+
+class Contact(ctypes.Structure):
+    """POD mirror of include/eolc.h eolc_contact (btc::Collision, boxTriCollision.h:49-110)."""
+    _fields_ = [
+        ("dist", ctypes.c_double),
+        ("nor1", ctypes.c_double * 3), ("nor2", ctypes.c_double * 3),
+        ("pos1", ctypes.c_double * 3), ("pos2", ctypes.c_double * 3), ("pos1_", ctypes.c_double * 3),
+        ("weights1", ctypes.c_double * 3), ("weights2", ctypes.c_double * 3),
+        ("edgeDir", ctypes.c_double * 3),
+        ("count1", ctypes.c_int32), ("count2", ctypes.c_int32),
+        ("verts1", ctypes.c_int32 * 3), ("verts2", ctypes.c_int32 * 3),
+        ("tri1", ctypes.c_int32), ("tri2", ctypes.c_int32),
+        ("edge1", ctypes.c_int32 * 3),
+        ("n_edge1", ctypes.c_int32),
+        ("edge2", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+CONTACT_DTYPE = np.dtype([
+    ("dist", "f8"), ("nor1", "f8", 3), ("nor2", "f8", 3), ("pos1", "f8", 3), ("pos2", "f8", 3), ("pos1_", "f8", 3),
+    ("weights1", "f8", 3), ("weights2", "f8", 3), ("edgeDir", "f8", 3),
+    ("count1", "i4"), ("count2", "i4"), ("verts1", "i4", 3), ("verts2", "i4", 3), ("tri1", "i4"), ("tri2", "i4"),
+    ("edge1", "i4", 3), ("n_edge1", "i4"), ("edge2", "i4"), ("reserved", "i4"),
+])
+assert CONTACT_DTYPE.itemsize == ctypes.sizeof(Contact) == 264
+
+
+def build():
+    """Compile oracle/liboracle.so (and oracle/_ref/ when /root/reference is present)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "liboracle.so")
+    if not os.path.exists(path):
+        build()
+    L = ctypes.CDLL(path)
+    L.oracle_forces_fill.restype = ctypes.c_void_p
+    L.oracle_forces_fill.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_int, c_ip, c_dp, c_dp, c_dp, c_dp,
+                                     ctypes.c_double, ctypes.c_int]
+    L.oracle_forces_dof.argtypes = [ctypes.c_void_p]
+    L.oracle_forces_f.restype = c_dp
+    L.oracle_forces_f.argtypes = [ctypes.c_void_p]
+    L.oracle_forces_nnz.restype = ctypes.c_int64
+    L.oracle_forces_nnz.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.oracle_forces_outer.restype = c_ip
+    L.oracle_forces_outer.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.oracle_forces_inner.restype = c_ip
+    L.oracle_forces_inner.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.oracle_forces_vals.restype = c_dp
+    L.oracle_forces_vals.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.oracle_forces_seconds.restype = ctypes.c_double
+    L.oracle_forces_seconds.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.oracle_forces_free.argtypes = [ctypes.c_void_p]
+    L.oracle_cd.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, ctypes.c_double, ctypes.c_int, c_dp, c_dp,
+                            ctypes.c_int, c_dp, c_dp, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                            ctypes.POINTER(ctypes.c_int)]
+    L.oracle_cd_edges.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_ip, c_dp]
+    L.oracle_perturbation.argtypes = [ctypes.c_int, ctypes.c_double, c_dp]
+    L.oracle_rng_raw.argtypes = [ctypes.c_int, c_dp]
+    L.oracle_raytri.argtypes = [c_dp] * 6
+    L.oracle_box.argtypes = [c_dp] * 6
+    L.oracle_face_frame.argtypes = [c_dp] * 8
+    _LIB = L
+    return L
+
+
+def _d(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+MATERIAL_DEFAULT = (0.05, 50.0, 0.01, 1.0e-5, 0.0, 1.0)  # simulationSettings.json:27-33
+GRAV_DEFAULT = (0.0, 0.0, -9.8)
+H_DEFAULT = 0.5e-2
+
+
+def forces_fill(face_nodes, edge_stencil, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_DEFAULT, h=H_DEFAULT,
+                skip_assembly=False):
+    """Reference Forces::fill on flat arrays.  Returns dict(f, M=(outer, inner, vals), MDK=..., seconds=(el, asm))."""
+    L = lib()
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    edge_stencil = _i32(edge_stencil).reshape(-1, 4)
+    x = _f64(x).reshape(-1, 3)
+    X = _f64(X).reshape(-1, 2)
+    N = x.shape[0]
+    matv = _f64(mat)
+    gv = _f64(grav)
+    r = L.oracle_forces_fill(N, face_nodes.shape[0], _i(face_nodes), edge_stencil.shape[0], _i(edge_stencil), _d(x),
+                             _d(X), _d(matv), _d(gv), float(h), 1 if skip_assembly else 0)
+    try:
+        dof = L.oracle_forces_dof(r)
+        out = {"dof": dof, "f": np.ctypeslib.as_array(L.oracle_forces_f(r), (dof,)).copy(),
+               "seconds": (L.oracle_forces_seconds(r, 0), L.oracle_forces_seconds(r, 1))}
+        if not skip_assembly:
+            for which, name in ((0, "M"), (1, "MDK")):
+                nnz = L.oracle_forces_nnz(r, which)
+                outer = np.ctypeslib.as_array(L.oracle_forces_outer(r, which), (dof + 1,)).copy()
+                inner = np.ctypeslib.as_array(L.oracle_forces_inner(r, which), (nnz,)).copy()
+                vals = np.ctypeslib.as_array(L.oracle_forces_vals(r, which), (nnz,)).copy()
+                out[name] = (outer, inner, vals)
+    finally:
+        L.oracle_forces_free(r)
+    return out
+
+
+def cd(face_nodes, x, threshold, pxyz=None, pnorms=None, box_whd=None, box_E=None, point_eol_flag=0, remap=0,
+       capacity=None):
+    """Reference CD (point_eol_flag=1, remap=1) / CD2 (0, 0) on flat arrays -> structured array of contacts."""
+    L = lib()
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    N, F = x.shape[0], face_nodes.shape[0]
+    pxyz = _f64(np.zeros((0, 3)) if pxyz is None else pxyz).reshape(-1, 3)
+    pnorms = _f64(np.zeros((0, 3)) if pnorms is None else pnorms).reshape(-1, 3)
+    box_whd = _f64(np.zeros((0, 3)) if box_whd is None else box_whd).reshape(-1, 3)
+    box_E = _f64(np.zeros((0, 16)) if box_E is None else box_E).reshape(-1, 16)
+    if capacity is None:
+        capacity = N + 8 * (1 + box_whd.shape[0]) + pxyz.shape[0] + 4096
+    while True:
+        out = np.zeros(capacity, dtype=CONTACT_DTYPE)
+        n = ctypes.c_int(0)
+        rc = L.oracle_cd(N, F, _i(face_nodes), _d(x), float(threshold), pxyz.shape[0], _d(pxyz), _d(pnorms),
+                         box_whd.shape[0], _d(box_whd), _d(box_E), int(point_eol_flag), int(remap),
+                         out.ctypes.data_as(ctypes.c_void_p), capacity, ctypes.byref(n))
+        if rc == 0:
+            return out[:n.value].copy()
+        capacity = n.value
+
+
+def cd_edges(face_nodes, x):
+    L = lib()
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    F = face_nodes.shape[0]
+    tab = np.zeros((3 * F, 6), dtype=np.int32)
+    nrm = np.zeros((3 * F, 6), dtype=np.float64)
+    E = L.oracle_cd_edges(x.shape[0], F, _i(face_nodes), _d(x), _i(tab), _d(nrm))
+    return tab[:E].copy(), nrm[:E].copy()
+
+
+def perturbation(n, threshold):
+    out = np.zeros((n, 3))
+    lib().oracle_perturbation(n, float(threshold), _d(out))
+    return out
+
+
+def rng_raw(n):
+    out = np.zeros(n)
+    lib().oracle_rng_raw(n, _d(out))
+    return out
+
+
+def raytri(orig, dirv, v0, v1, v2):
+    tuv = np.zeros(3)
+    hit = lib().oracle_raytri(_d(_f64(orig)), _d(_f64(dirv)), _d(_f64(v0)), _d(_f64(v1)), _d(_f64(v2)), _d(tuv))
+    return hit, tuv
+
+
+def box(whd, E1):
+    v, fn, vn, ang = np.zeros((14, 3)), np.zeros((24, 3)), np.zeros((14, 3)), np.zeros(12)
+    lib().oracle_box(_d(_f64(whd)), _d(_f64(E1)), _d(v), _d(fn), _d(vn), _d(ang))
+    return v, fn, vn, ang
+
+
+def compute_membrane(xa, xb, xc, Xa, Xb, Xc, e, nu, P, Q):
+    L = lib()
+    L.oracle_compute_membrane.argtypes = [c_dp] * 6 + [ctypes.c_double] * 2 + [c_dp] * 5
+    W, f, K = np.zeros(1), np.zeros(9), np.zeros(81)
+    L.oracle_compute_membrane(*[_d(_f64(a)) for a in (xa, xb, xc, Xa, Xb, Xc)], e, nu, _d(_f64(P)), _d(_f64(Q)),
+                              _d(W), _d(f), _d(K))
+    return W[0], f, K.reshape(9, 9)
+
+
+def compute_bending(x0, x1, x2, x3, X0, X1, X2, X3, beta):
+    L = lib()
+    L.oracle_compute_bending.argtypes = [c_dp] * 8 + [ctypes.c_double] + [c_dp] * 3
+    W, f, K = np.zeros(1), np.zeros(12), np.zeros(144)
+    L.oracle_compute_bending(*[_d(_f64(a)) for a in (x0, x1, x2, x3, X0, X1, X2, X3)], beta, _d(W), _d(f), _d(K))
+    return W[0], f, K.reshape(12, 12)
+
+
+def compute_inertial(xa, xb, xc, Xa, Xb, Xc, g, rho):
+    L = lib()
+    L.oracle_compute_inertial.argtypes = [c_dp] * 7 + [ctypes.c_double] + [c_dp] * 3
+    W, f, M = np.zeros(1), np.zeros(9), np.zeros(81)
+    L.oracle_compute_inertial(*[_d(_f64(a)) for a in (xa, xb, xc, Xa, Xb, Xc, g)], rho, _d(W), _d(f), _d(M))
+    return W[0], f, M.reshape(9, 9)
+
+
+def face_frame(xa, xb, xc, Xa, Xb, Xc):
+    PP, QQ = np.zeros(6), np.zeros(4)
+    lib().oracle_face_frame(*[_d(_f64(a)) for a in (xa, xb, xc, Xa, Xb, Xc)], _d(PP), _d(QQ))
+    return PP, QQ

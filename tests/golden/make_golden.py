@@ -1,0 +1,50 @@
+"""Generates tests/golden/*.npz from the CPU oracle (reference Compute*.cpp / raytri.cpp object code + restated glue).
+
+Run in the build container (where /root/reference exists):  python tests/golden/make_golden.py
+The fixtures pin (a) the oracle against silent drift and (b) the CUDA path on the GPU box, where the reference
+sources are absent.  Inputs are regenerated from seeds by the tests; only outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+import eol_cloth_b200 as E  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def forces_case(gen, n, seed):
+    X, fn = getattr(E.meshgen, gen)(n)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    x = E.meshgen.drape_state(X, seed=seed)
+    r = O.forces_fill(fn, es, x, X)
+    return dict(f=r["f"], M_outer=r["M"][0], M_inner=r["M"][1], M_vals=r["M"][2], K_outer=r["MDK"][0],
+                K_inner=r["MDK"][1], K_vals=r["MDK"][2])
+
+
+def cd_case(gen, n, centre, seed, rot=None, points=False):
+    X, fn = getattr(E.meshgen, gen)(n)
+    x = E.meshgen.box_scene_state(X, seed=seed, centre=np.asarray(centre))
+    pxyz = pn = None
+    if points:
+        pxyz = np.array([[0.25, 0.25, x[:, 2].max() - 4e-3], [0.1, 0.8, -0.2], x[5] + 1e-3])
+        pn = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0]])
+    out = {}
+    for name, flag, remap in (("cd", 1, 1), ("cd2", 0, 0)):
+        out[name] = O.cd(fn, x, E.meshgen.BOX_THRESHOLD, pxyz, pn, E.meshgen.BOX_WHD[None], E.meshgen.box_frame(centre, rot)[None], flag, remap)
+    return out
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "forces_regular2_n12.npz"), **forces_case("regular2", 12, 0))
+    np.savez_compressed(os.path.join(HERE, "forces_build4_n7.npz"), **forces_case("build4", 7, 1))
+    np.savez_compressed(os.path.join(HERE, "cd_regular2_n24.npz"), **cd_case("regular2", 24, E.meshgen.BOX_CENTRE, 0))
+    c3b = np.array([0.9175, -0.25, -0.549])
+    np.savez_compressed(os.path.join(HERE, "cd_build4_n16_corner.npz"), **cd_case("build4", 16, c3b, 1, points=True))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

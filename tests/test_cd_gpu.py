@@ -1,0 +1,131 @@
+"""Parity of the CUDA narrow phase (through the C ABI) against the CPU oracle and golden fixtures: identical count,
+order and every integer field bit-for-bit; real fields within 1e-12 (they are in fact bit-identical except where
+libm and CUDA acos differ, which only feeds comparisons)."""
+import os
+
+import numpy as np
+import pytest
+
+import eol_cloth_b200 as E
+from eol_cloth_b200.collisions import make_obstacles
+from util import assert_contacts_equal, bit_identical_fraction
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+THR = E.meshgen.BOX_THRESHOLD
+
+
+def _rot(axis, ang):
+    axis = np.asarray(axis, float) / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+
+def _both(ctx, oracle, fn, x, obs, what):
+    mesh = dict(x=x, face_nodes=fn)
+    for fnc, flag, remap in ((E.CD, 1, 1), (E.CD2, 0, 0)):
+        cls = []
+        fnc(ctx, mesh, obs, cls)
+        got = np.array(cls, dtype=E.CONTACT_DTYPE) if cls else np.zeros(0, E.CONTACT_DTYPE)
+        ref = oracle.cd(fn, x, obs.cdthreshold, obs.pxyz, obs.pnorms, obs.box_whd, obs.box_E, flag, remap)
+        assert_contacts_equal(got, ref, what=f"{what} {fnc.__name__}")
+    return got, ref
+
+
+CASES = [
+    ("regular2", 24, tuple(E.meshgen.BOX_CENTRE), None, 0),
+    ("build4", 16, (0.9175, -0.25, -0.549), None, 1),
+    ("regular2", 40, (0.9175, -0.25, -0.549), None, 2),
+    ("regular2", 33, (0.7, 0.3, -0.549), ((0, 0, 1), 0.3), 3),          # rotated box, corners + edges under the cloth
+    ("build4", 21, (0.5, 0.5, -0.549), ((1, 2, 0.5), 0.05), 4),
+]
+
+
+@pytest.mark.parametrize("gen,n,centre,rot,seed", CASES)
+def test_box_scene_matches_oracle(ctx, oracle, gen, n, centre, rot, seed):
+    X, fn = getattr(E.meshgen, gen)(n)
+    x = E.meshgen.box_scene_state(X, seed=seed, centre=np.asarray(centre))
+    R = None if rot is None else _rot(*rot)
+    obs = make_obstacles(THR, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(np.asarray(centre), R)[None])
+    got, ref = _both(ctx, oracle, fn, x, obs, f"{gen}{n}")
+    assert len(ref) > 0
+
+
+def test_points_and_two_boxes(ctx, oracle):
+    X, fn = E.meshgen.regular2(30)
+    x = E.meshgen.box_scene_state(X, seed=5, centre=np.array([0.9175, -0.25, -0.549]))
+    pxyz = np.array([[0.25, 0.25, x[:, 2].max() - 4e-3], [0.1, 0.8, -0.2], x[5] + 1e-3, x[100] - 2e-3])
+    pn = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0], [0, 0.6, 0.8]])
+    whd = np.stack([E.meshgen.BOX_WHD, [0.3, 0.3, 0.3]])
+    Em = np.stack([E.meshgen.box_frame(np.array([0.9175, -0.25, -0.549])), E.meshgen.box_frame(np.array([0.15, 0.8, -0.36]))])
+    obs = make_obstacles(THR, pxyz, pn, whd, Em)
+    got, ref = _both(ctx, oracle, fn, x, obs, "points+2boxes")
+    assert {(1, 3), (2, 2), (3, 1)} <= set(zip(ref["count1"].tolist(), ref["count2"].tolist()))
+
+
+def test_no_contacts_and_no_obstacles(ctx, oracle):
+    X, fn = E.meshgen.regular2(8)
+    x = np.c_[X, np.full(len(X), 5.0)]
+    obs = make_obstacles(THR, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame()[None])
+    cls = []
+    E.CD(ctx, dict(x=x, face_nodes=fn), obs, cls)
+    assert cls == []
+    E.CD2(ctx, dict(x=x, face_nodes=fn), make_obstacles(THR), cls)
+    assert cls == []
+
+
+@pytest.mark.parametrize("name,gen,n,centre,seed,points", [
+    ("cd_regular2_n24", "regular2", 24, tuple(E.meshgen.BOX_CENTRE), 0, False),
+    ("cd_build4_n16_corner", "build4", 16, (0.9175, -0.25, -0.549), 1, True)])
+def test_matches_golden(ctx, name, gen, n, centre, seed, points):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    X, fn = getattr(E.meshgen, gen)(n)
+    x = E.meshgen.box_scene_state(X, seed=seed, centre=np.asarray(centre))
+    pxyz = pn = None
+    if points:
+        pxyz = np.array([[0.25, 0.25, x[:, 2].max() - 4e-3], [0.1, 0.8, -0.2], x[5] + 1e-3])
+        pn = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0]])
+    obs = make_obstacles(THR, pxyz, pn, E.meshgen.BOX_WHD[None], E.meshgen.box_frame(np.asarray(centre))[None])
+    for key, fnc in (("cd", E.CD), ("cd2", E.CD2)):
+        cls = []
+        fnc(ctx, dict(x=x, face_nodes=fn), obs, cls)
+        got = np.array(cls, dtype=E.CONTACT_DTYPE)
+        assert_contacts_equal(got, g[key], what=f"{name} {key}")
+        assert bit_identical_fraction(got, g[key]) == 1.0
+
+
+def test_edge_table_matches_oracle(ctx, oracle):
+    X, fn = E.meshgen.build4(11)
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, THR)
+    tab, _ = oracle.cd_edges(fn, np.c_[X, np.zeros(len(X))])
+    assert np.array_equal(plan.edge_table(), tab)
+
+
+def test_box_scene_512_bit_exact(ctx, oracle):
+    """BASELINE config 3: simulationSettingsBox.json geometry scaled to a 512x512 cloth, full list comparison."""
+    X, fn = E.meshgen.regular2(512)
+    x = E.meshgen.box_scene_state(X, seed=0)
+    obs = make_obstacles(THR, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame()[None])
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, THR)
+    got = plan.run(x, obs, 0, 0)
+    ref = oracle.cd(fn, x, THR, None, None, obs.box_whd, obs.box_E, 0, 0)
+    assert_contacts_equal(got, ref, what="512 box scene")
+    nA = int(((ref["count1"] == 3) & (ref["count2"] == 1)).sum())
+    assert 0.6 * len(X) < nA < 0.75 * len(X)           # ~0.68 N type-(A) records
+    assert int((ref["count1"] == 2).sum()) > 0          # band of type-(C) records along x = 0.3175
+    assert bit_identical_fraction(got, ref) > 0.999999
+
+
+def test_batched_scenes_equal_single(ctx):
+    import torch
+    X, fn = E.meshgen.regular2(20)
+    c = np.array([0.9175, -0.25, -0.549])
+    obs = make_obstacles(THR, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(c)[None])
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, THR)
+    xs = np.stack([E.meshgen.box_scene_state(X, seed=s, centre=c) for s in range(5)])
+    xd = torch.from_numpy(xs).to(torch.device("cuda", ctx.device))
+    torch.cuda.synchronize()
+    allc, off = plan.run(xd.data_ptr(), obs, 0, 0, x_is_device_ptr=True, n_scenes=5)
+    for s in range(5):
+        single = plan.run(xs[s], obs, 0, 0)
+        assert allc[off[s]:off[s + 1]].tobytes() == single.tobytes()

@@ -1,0 +1,156 @@
+"""Parity of the CUDA Forces::fill (through the C ABI) against the CPU oracle and the golden fixtures.
+Tolerance (BASELINE north_star / SURVEY §8c rule 5): |a-b| <= 1e-10 * max(|a|, |b|, s), s = max |entry| of the
+node's 3-row block of the oracle matrix."""
+import os
+
+import numpy as np
+import pytest
+
+import eol_cloth_b200 as E
+from util import assert_close_tol, block_row_scale
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MAT = E.Material.DEFAULT
+GRAV = (0.0, 0.0, -9.8)
+H = 0.5e-2
+TOL = 1e-10
+
+
+def _mesh(gen, n, seed=0):
+    X, fn = getattr(E.meshgen, gen)(n)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    return dict(x=E.meshgen.drape_state(X, seed=seed), X=X, face_nodes=fn, edge_stencil=es)
+
+
+def _check(forces, ref, N, what):
+    fscale = max(np.abs(ref["f"]).max(), 1e-300)
+    assert_close_tol(forces.f, ref["f"], fscale, TOL, what + " f")
+    for name, got in (("M", forces.M), ("MDK", forces.MDK)):
+        o, i, v = ref[name]
+        assert np.array_equal(got[0], o), what + f" {name} outer"
+        assert np.array_equal(got[1], i), what + f" {name} inner"
+        assert_close_tol(got[2], v, block_row_scale(o, v, N), TOL, what + f" {name} values")
+
+
+@pytest.mark.parametrize("gen,n", [("regular2", 2), ("regular2", 3), ("build4", 3), ("regular2", 17), ("build4", 9), ("regular2", 64)])
+def test_fill_matches_oracle(ctx, oracle, gen, n):
+    mesh = _mesh(gen, n, seed=n)
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    ref = oracle.forces_fill(mesh["face_nodes"], mesh["edge_stencil"], mesh["x"], mesh["X"], tuple(MAT), GRAV, H)
+    assert forces.EoL_cutoff == 3 * mesh["x"].shape[0]
+    _check(forces, ref, mesh["x"].shape[0], f"{gen}{n}")
+
+
+def test_fill_256_matches_oracle(ctx, oracle):
+    """BASELINE config 2: 256x256 regular sheet, full f / M / MDK comparison."""
+    mesh = _mesh("regular2", 256)
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    ref = oracle.forces_fill(mesh["face_nodes"], mesh["edge_stencil"], mesh["x"], mesh["X"], tuple(MAT), GRAV, H)
+    assert forces.M[2].size == 4110354 and forces.MDK[2].size == 7612524
+    _check(forces, ref, 65536, "regular2-256")
+
+
+def test_other_material_and_large_deformation(ctx, oracle):
+    mesh = _mesh("regular2", 20, seed=5)
+    rng = np.random.default_rng(7)
+    mesh["x"] = mesh["x"] * 1.3 + 0.02 * rng.standard_normal(mesh["x"].shape)
+    mat = E.Material(0.2, 1000.0, 0.3, 1e-3, 0.0, 0.7)
+    forces = E.Forces(ctx).fill(mesh, mat, (0.1, -0.2, -9.8), 1e-2)
+    ref = oracle.forces_fill(mesh["face_nodes"], mesh["edge_stencil"], mesh["x"], mesh["X"], tuple(mat), (0.1, -0.2, -9.8), 1e-2)
+    _check(forces, ref, mesh["x"].shape[0], "material")
+
+
+@pytest.mark.parametrize("name,gen,n,seed", [("forces_regular2_n12", "regular2", 12, 0), ("forces_build4_n7", "build4", 7, 1)])
+def test_fill_matches_golden(ctx, name, gen, n, seed):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    mesh = _mesh(gen, n, seed=seed)
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    ref = dict(f=g["f"], M=(g["M_outer"], g["M_inner"], g["M_vals"]), MDK=(g["K_outer"], g["K_inner"], g["K_vals"]))
+    _check(forces, ref, mesh["x"].shape[0], name)
+
+
+def test_shuffled_node_order_and_isolated_node(ctx, oracle):
+    """Arbitrary (remeshed-like) numbering + a node no face references (its rows stay empty, f = 0)."""
+    X, fn = E.meshgen.regular2(9)
+    rng = np.random.default_rng(11)
+    N = X.shape[0] + 1
+    perm = rng.permutation(N)                # old -> new, last old index is the isolated node
+    Xn = np.zeros((N, 2)); Xn[perm[:-1]] = X; Xn[perm[-1]] = (5.0, 5.0)
+    fnn = perm[fn].astype(np.int32)
+    fnn = fnn[rng.permutation(len(fnn))]
+    es = E.meshgen.edge_stencils(N, fnn)
+    mesh = dict(x=E.meshgen.drape_state(Xn, seed=2), X=Xn, face_nodes=fnn, edge_stencil=es)
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    ref = oracle.forces_fill(fnn, es, mesh["x"], Xn, tuple(MAT), GRAV, H)
+    _check(forces, ref, N, "shuffled")
+    assert np.all(forces.f[3 * perm[-1]:3 * perm[-1] + 3] == 0)
+
+
+def test_empty_and_single_face(ctx, oracle):
+    f0 = E.Forces(ctx).fill(dict(x=np.zeros((0, 3)), X=np.zeros((0, 2)), face_nodes=np.zeros((0, 3), np.int32),
+                                 edge_stencil=np.zeros((0, 4), np.int32)), MAT, GRAV, H)
+    assert f0.f.size == 0 and f0.M[2].size == 0 and f0.MDK[2].size == 0
+    X = np.array([[0.0, 0], [1, 0], [0, 1]]); fn = np.array([[0, 1, 2]], np.int32)
+    es = E.meshgen.edge_stencils(3, fn)
+    mesh = dict(x=np.c_[X, [0.0, 0.1, -0.1]], X=X, face_nodes=fn, edge_stencil=es)
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    ref = oracle.forces_fill(fn, es, mesh["x"], X, tuple(MAT), GRAV, H)
+    _check(forces, ref, 3, "single face")
+
+
+def test_errors(ctx):
+    with pytest.raises(E.EolcError):
+        E.ForcesPlan(ctx, 3, np.array([[0, 1, 3]], np.int32), np.zeros((0, 4), np.int32))     # index out of range
+    with pytest.raises(E.EolcError):
+        E.ForcesPlan(ctx, 3, np.array([[0, 1, 1]], np.int32), np.zeros((0, 4), np.int32))     # degenerate face
+    with pytest.raises(E.EolcError):
+        E.ForcesPlan(ctx, 3, np.array([[0, 1, 2]], np.int32), np.zeros((0, 4), np.int32), eol_index=np.array([-1, 0, -1], np.int32))
+
+
+def test_reproducible_and_dev_equals_host(ctx):
+    """Run-to-run bit reproducibility (no float atomics) and device-pointer API == host API == batched API."""
+    import torch
+    mesh = _mesh("regular2", 96, seed=3)
+    N = mesh["x"].shape[0]
+    plan = E.ForcesPlan(ctx, N, mesh["face_nodes"], mesh["edge_stencil"], X_hint=mesh["X"])
+    f1, M1, K1 = plan.fill(mesh["x"], mesh["X"], MAT, GRAV, H)
+    f2, M2, K2 = plan.fill(mesh["x"], mesh["X"], MAT, GRAV, H)
+    assert f1.tobytes() == f2.tobytes() and M1.tobytes() == M2.tobytes() and K1.tobytes() == K2.tobytes()
+    dev = torch.device("cuda", ctx.device)
+    S = 3
+    xs = np.stack([mesh["x"], E.meshgen.drape_state(mesh["X"], seed=8), E.meshgen.drape_state(mesh["X"], seed=9)])
+    xd = torch.from_numpy(xs).to(dev)
+    Xd = torch.from_numpy(np.broadcast_to(mesh["X"], (S,) + mesh["X"].shape).copy()).to(dev)
+    fd = torch.empty((S, 3 * N), dtype=torch.float64, device=dev)
+    Md = torch.empty((S, plan.nnz[0]), dtype=torch.float64, device=dev)
+    Kd = torch.empty((S, plan.nnz[1]), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, fd.data_ptr(), Md.data_ptr(), Kd.data_ptr(), n_scenes=S)
+    torch.cuda.synchronize()
+    assert fd[0].cpu().numpy().tobytes() == f1.tobytes() and Kd[0].cpu().numpy().tobytes() == K1.tobytes()
+    assert Md[0].cpu().numpy().tobytes() == M1.tobytes()
+    f3, M3, K3 = plan.fill(xs[2], mesh["X"], MAT, GRAV, H)
+    assert Kd[2].cpu().numpy().tobytes() == K3.tobytes() and fd[2].cpu().numpy().tobytes() == f3.tobytes()
+
+
+def test_fullsize_1024_properties(ctx):
+    """BASELINE config 4 at full size (oracle too slow): size-independent properties.
+    (1) pattern sizes of SURVEY §8; (2) exact symmetry of M and MDK; (3) K has translation null space, so the three
+    row-block sums of MDK equal those of M; (4) sum(M) = 3 rho * area = 3 * 0.05; (5) sum f = total weight."""
+    import scipy.sparse as sp
+    mesh = _mesh("regular2", 1024)
+    N = mesh["x"].shape[0]
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    assert forces.M[2].size == 65986578 and forces.MDK[2].size == 122462316
+    M = sp.csc_matrix((forces.M[2], forces.M[1], forces.M[0]), shape=(3 * N, 3 * N))
+    K = sp.csc_matrix((forces.MDK[2], forces.MDK[1], forces.MDK[0]), shape=(3 * N, 3 * N))
+    assert abs(M - M.T).max() == 0.0
+    assert abs(K - K.T).max() == 0.0
+    T = sp.csr_matrix(np.tile(np.eye(3), (N, 1)))       # translations
+    dK = (K - M) @ T
+    scale = abs(K).max()
+    assert abs(dK).max() < 1e-9 * scale
+    assert abs(M.sum() - 3 * 0.05 * 1.0) < 1e-12
+    fz = forces.f.reshape(-1, 3).sum(axis=0)
+    assert abs(fz[2] - (-9.8 * 0.05)) < 1e-9 and abs(fz[0]) < 1e-9 and abs(fz[1]) < 1e-9

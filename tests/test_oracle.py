@@ -1,0 +1,153 @@
+"""Pins the CPU oracle: reference object code vs SURVEY §8c known answers, RNG / raytri KATs, FD identities,
+pattern sizes, and the committed golden fixtures (tests/golden, made by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import eol_cloth_b200 as E
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+x0 = (0, 0, 0); x1 = (1.1, 0.05, 0.1); x2 = (-0.02, 0.9, -0.05); x3 = (1, -1, 0.2)
+X0 = (0, 0); X1 = (1, 0); X2 = (0, 1); X3 = (1, -1)
+
+
+def test_known_answers_membrane(oracle):
+    W, f, K = oracle.compute_membrane(x0, x1, x2, X0, X1, X2, 50, 0.01, [1, 0, 0, 1, 0, 0], [1, 0, 0, 1])
+    assert W == 0.28341584158415856
+    assert f[0] == 1.9801980198019824
+    assert K[0, 0] == 49.757526773085473
+    assert K[0, 8] == 0 and np.signbit(K[0, 8])
+    assert abs(np.abs(K).sum() - 400.08082440897147) < 1e-11
+    assert np.array_equal(K, K.T)
+
+
+def test_known_answers_bending(oracle):
+    W, f, K = oracle.compute_bending(x0, x1, x2, x3, X0, X1, X2, X3, 1e-5)
+    assert W == 1.9012987629236648e-08
+    assert f[0] == -8.5073508439304069e-08 and f[11] == -7.1163691863669505e-07
+    assert K[0, 0] == 3.3642796219437894e-07 and K[0, 11] == 1.5876586965473499e-06
+    assert abs(np.abs(K).sum() - 0.00034194309149763314) < 1e-17
+    assert np.array_equal(K, K.T)
+
+
+def test_known_answers_inertial(oracle):
+    W, f, M = oracle.compute_inertial(x0, x1, x2, X0, X1, X2, (0, 0, -9.8), 0.05)
+    assert W == 0.0040833333333333372
+    assert f[2] == -0.081666666666666679
+    assert M[0, 0] == 0.0041666666666666666 and M[0, 3] == 0.0020833333333333333 and M[0, 1] == 0
+
+
+def test_fd_identities(oracle):
+    """f = -dW/dx and K = -df/dx for the reference kernels (central differences)."""
+    rng = np.random.default_rng(3)
+    X = np.array([[0, 0], [1, 0], [0.2, 0.9], [0.7, -0.8]]) + 0.05 * rng.standard_normal((4, 2))
+    x = np.c_[X, np.zeros(4)] + 0.05 * rng.standard_normal((4, 3))
+    h = 1e-6
+    W, f, K = oracle.compute_bending(*x, *X, 1e-2)
+    for i in range(12):
+        xp = x.copy().reshape(-1); xm = xp.copy(); xp[i] += h; xm[i] -= h
+        Wp, fp, _ = oracle.compute_bending(*xp.reshape(4, 3), *X, 1e-2)
+        Wm, fm, _ = oracle.compute_bending(*xm.reshape(4, 3), *X, 1e-2)
+        assert abs(-(Wp - Wm) / (2 * h) - f[i]) < 1e-7 * max(1, np.abs(f).max())
+        assert np.abs(-(fp - fm) / (2 * h) - K[:, i]).max() < 1e-6 * np.abs(K).max()
+    P, Q = oracle.face_frame(*x[:3], *X[:3])
+    W, f, K = oracle.compute_membrane(*x[:3], *X[:3], 50.0, 0.3, P, Q)
+    for i in range(9):
+        xp = x[:3].copy().reshape(-1); xm = xp.copy(); xp[i] += h; xm[i] -= h
+        Wp, fp, _ = oracle.compute_membrane(*xp.reshape(3, 3), *X[:3], 50.0, 0.3, P, Q)   # frozen frame
+        Wm, fm, _ = oracle.compute_membrane(*xm.reshape(3, 3), *X[:3], 50.0, 0.3, P, Q)
+        assert abs(-(Wp - Wm) / (2 * h) - f[i]) < 1e-6 * max(1, np.abs(f).max())
+        assert np.abs(-(fp - fm) / (2 * h) - K[:, i]).max() < 1e-6 * np.abs(K).max()
+
+
+def test_rng_known_answer(oracle):
+    want = [0.99436961646053112, 0.86511472273633094, -0.74375110445538795, 0.99808103093054723,
+            -0.52782204740366157, -0.20683854767478138]
+    got = oracle.rng_raw(6)
+    assert got.tolist() == want
+    assert got[:1].view(np.uint64)[0] == 0x3FEFD1E03ADAB07E
+    p = oracle.perturbation(2, 5e-3)
+    assert p[0, 0] == want[0] * 5e-3 * 1e-3
+
+
+def test_raytri_borders(oracle):
+    """ZERO = -EPSILON makes the borders inset by 1e-6 (scaled by det), SURVEY §8a row 16."""
+    v0, v1, v2 = (0, 0, 0), (1, 0, 0), (0, 1, 0)
+    d = (0, 0, -1)
+    assert oracle.raytri((0.25, 0.25, 1), d, v0, v1, v2)[0] == 1
+    assert oracle.raytri((0.5, 0.0, 1), d, v0, v1, v2)[0] == 0          # on an edge
+    assert oracle.raytri((0.5, 5e-7, 1), d, v0, v1, v2)[0] == 0         # 5e-7 inside
+    assert oracle.raytri((0.5, 2e-6, 1), d, v0, v1, v2)[0] == 1         # 2e-6 inside
+    hit, tuv = oracle.raytri((0.25, 0.25, 1), d, v0, v1, v2)
+    assert tuv[0] == 1.0
+
+
+@pytest.mark.parametrize("gen,n,nnzM,nnzK", [("regular2", 3, 369, 513), ("build4", 3, 621, 837)])
+def test_pattern_sizes_small(oracle, gen, n, nnzM, nnzK):
+    X, fn = getattr(E.meshgen, gen)(n)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    r = oracle.forces_fill(fn, es, E.meshgen.drape_state(X), X)
+    assert r["M"][2].size == nnzM and r["MDK"][2].size == nnzK
+    # Eigen-compressed invariants: sorted inner indices, exact symmetry
+    for name in ("M", "MDK"):
+        outer, inner, vals = r[name]
+        for c in range(outer.size - 1):
+            seg = inner[outer[c]:outer[c + 1]]
+            assert np.all(np.diff(seg) > 0)
+
+
+def test_survey_counts_64(oracle):
+    X, fn = E.meshgen.regular2(64)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    assert X.shape[0] == 4096 and fn.shape[0] == 7938 and int((es[:, 3] >= 0).sum()) == 11781
+    r = oracle.forces_fill(fn, es, E.meshgen.drape_state(X), X)
+    assert r["M"][2].size == 253458 and r["MDK"][2].size == 465516
+
+
+@pytest.mark.parametrize("name,gen,n,seed", [("forces_regular2_n12", "regular2", 12, 0), ("forces_build4_n7", "build4", 7, 1)])
+def test_golden_forces(oracle, name, gen, n, seed):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    X, fn = getattr(E.meshgen, gen)(n)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    r = oracle.forces_fill(fn, es, E.meshgen.drape_state(X, seed=seed), X)
+    assert np.array_equal(r["f"], g["f"])
+    for k, nm in (("M", "M"), ("K", "MDK")):
+        assert np.array_equal(r[nm][0], g[k + "_outer"]) and np.array_equal(r[nm][1], g[k + "_inner"])
+        assert np.array_equal(r[nm][2], g[k + "_vals"])
+
+
+def _cd_inputs(gen, n, centre, seed, points):
+    X, fn = getattr(E.meshgen, gen)(n)
+    x = E.meshgen.box_scene_state(X, seed=seed, centre=np.asarray(centre))
+    pxyz = pn = None
+    if points:
+        pxyz = np.array([[0.25, 0.25, x[:, 2].max() - 4e-3], [0.1, 0.8, -0.2], x[5] + 1e-3])
+        pn = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0]])
+    return X, fn, x, pxyz, pn
+
+
+CD_CASES = [("cd_regular2_n24", "regular2", 24, tuple(E.meshgen.BOX_CENTRE), 0, False),
+            ("cd_build4_n16_corner", "build4", 16, (0.9175, -0.25, -0.549), 1, True)]
+
+
+@pytest.mark.parametrize("name,gen,n,centre,seed,points", CD_CASES)
+def test_golden_cd(oracle, name, gen, n, centre, seed, points):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    X, fn, x, pxyz, pn = _cd_inputs(gen, n, centre, seed, points)
+    for key, flag, remap in (("cd", 1, 1), ("cd2", 0, 0)):
+        got = oracle.cd(fn, x, E.meshgen.BOX_THRESHOLD, pxyz, pn, E.meshgen.BOX_WHD[None], E.meshgen.box_frame(centre)[None], flag, remap)
+        assert got.tobytes() == g[key].tobytes()
+    types = set(zip(g["cd"]["count1"].tolist(), g["cd"]["count2"].tolist()))
+    if points:
+        assert types == {(1, 3), (2, 2), (3, 1)}     # all three contact types are covered
+
+
+def test_cd_edge_table_matches_createEdges_order(oracle):
+    X, fn = E.meshgen.regular2(5)
+    tab, _ = oracle.cd_edges(fn, np.c_[X, np.zeros(len(X))])
+    # sorted by (max, min) of the edge's endpoints
+    key = np.maximum(tab[:, 0], tab[:, 1]).astype(np.int64) * 10**6 + np.minimum(tab[:, 0], tab[:, 1])
+    assert np.all(np.diff(key) > 0)
+    assert tab.shape[0] == 3 * 16 + 2 * 4
