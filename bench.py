@@ -240,7 +240,7 @@ def run_ours(args):
         rng = np.random.default_rng(lo)
         xs = base[None] + rng.uniform(-1e-3, 1e-3, size=(S,) + base.shape)
     x_d = torch.from_numpy(xs).to(dev)
-    X_d = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(X, (S,) + X.shape))).to(dev)
+    X_d = torch.from_numpy(np.broadcast_to(X, (S,) + X.shape).copy()).to(dev)
     f_d = torch.empty((S, 3 * N), dtype=torch.float64, device=dev)
     M_d = torch.empty((S, nnzM), dtype=torch.float64, device=dev)
     K_d = torch.empty((S, nnzK), dtype=torch.float64, device=dev)

@@ -145,6 +145,13 @@ __device__ __forceinline__ void finish_contact(eolc_contact &c, double threshold
     double snap = mul(0.1, threshold);
     for (int i = 0; i < 3; ++i) c.pos1_[i] = sub(c.pos1[i], mul(snap, c.nor1[i]));
 }
+// CD only (Collisions.cpp:39-48): box feature ids -> constraint-table columns; Box::num_points = 8, num_edges = 12.
+// remap_base < 0 disables it (CD2, and the obstacle-point sections).
+__device__ __forceinline__ void remap_contact(eolc_contact &c, int remap_base) {
+    if (remap_base < 0) return;
+    if (c.count1 == 1 && c.count2 == 3) c.verts1[0] = remap_base + c.verts1[0];
+    for (int e = 0; e < c.n_edge1; ++e) c.edge1[e] = remap_base + (8 + c.edge1[e]);
+}
 
 // ---- prepare -------------------------------------------------------------------------------------
 __global__ void k_perturb(int N, const double *__restrict__ x, const double *__restrict__ r, double *__restrict__ xp, size_t stride) {
@@ -172,13 +179,18 @@ __global__ void k_face_normals(int F, const int32_t *__restrict__ fn, const doub
     }
 }
 
-// per-scene AABB of the perturbed verts (build_AABB_B :425-433); one block per scene, min/max are order independent
-__global__ void __launch_bounds__(1024) k_aabb(int N, const double *__restrict__ xp, double *__restrict__ aabb, size_t stride) {
-    const double *v = xp + blockIdx.x * stride;
+// per-scene AABB of the perturbed verts (build_AABB_B :425-433); min/max are order independent.
+// stage 1: grid (nb, S) -> partial[(s*nb + blk)*6]; stage 2 (same kernel, nb = 1 over the partials): one block per scene.
+__global__ void __launch_bounds__(256) k_aabb(int n, int ld, const double *__restrict__ v_, double *__restrict__ out, size_t stride) {
+    // items are rows of `ld` doubles: ld == 3 -> points (min == max source), ld == 6 -> partial boxes
+    const double *v = v_ + blockIdx.y * stride;
     double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = threadIdx.x; i < N; i += blockDim.x)
-        for (int r = 0; r < 3; ++r) { double q = v[3 * (size_t)i + r]; mn[r] = fmin(mn[r], q); mx[r] = fmax(mx[r], q); }
-    __shared__ double s[6][32];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        for (int r = 0; r < 3; ++r) {
+            mn[r] = fmin(mn[r], v[(size_t)ld * i + r]);
+            mx[r] = fmax(mx[r], v[(size_t)ld * i + (ld == 6 ? 3 : 0) + r]);
+        }
+    __shared__ double s[6][8];
     for (int r = 0; r < 3; ++r)
         for (int o = 16; o > 0; o >>= 1) {
             mn[r] = fmin(mn[r], __shfl_xor_sync(0xffffffffu, mn[r], o));
@@ -187,12 +199,12 @@ __global__ void __launch_bounds__(1024) k_aabb(int N, const double *__restrict__
     int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) for (int r = 0; r < 3; ++r) { s[r][w] = mn[r]; s[3 + r][w] = mx[r]; }
     __syncthreads();
-    if (w == 0) {
-        int nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) {
+        double *o = out + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 6;
         for (int r = 0; r < 3; ++r) {
-            double a = l < nw ? s[r][l] : INFINITY, b = l < nw ? s[3 + r][l] : -INFINITY;
-            for (int o = 16; o > 0; o >>= 1) { a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o)); }
-            if (l == 0) { aabb[6 * blockIdx.x + r] = a; aabb[6 * blockIdx.x + 3 + r] = b; }
+            double a = s[r][0], b = s[3 + r][0];
+            for (int i = 1; i < 8; ++i) { a = fmin(a, s[r][i]); b = fmax(b, s[3 + r][i]); }
+            o[r] = a; o[3 + r] = b;
         }
     }
 }
@@ -412,7 +424,8 @@ __global__ void __launch_bounds__(256) k_PT_write(int F, int pts_per_sec, int ns
                                                   const int32_t *__restrict__ fn, const double *__restrict__ xp,
                                                   const double *__restrict__ fnp, double threshold, const int *__restrict__ info,
                                                   const int *__restrict__ blockoff, eolc_contact *__restrict__ out, size_t xstride,
-                                                  size_t fstride, size_t scene_items, size_t sec0_off, size_t sec_stride) {
+                                                  size_t fstride, size_t scene_items, size_t sec0_off, size_t sec_stride,
+                                                  int remap, int nP) {
     int s = blockIdx.y / nsec, sec = blockIdx.y % nsec;
     size_t item0 = s * scene_items + sec0_off + sec * sec_stride;
     int pt = blockIdx.x * 256 + threadIdx.x;
@@ -436,6 +449,7 @@ __global__ void __launch_bounds__(256) k_PT_write(int F, int pts_per_sec, int ns
     if (boxes) { rec.edge1[0] = c_vertEdges1[pt][0]; rec.edge1[1] = c_vertEdges1[pt][1]; rec.edge1[2] = c_vertEdges1[pt][2]; rec.n_edge1 = 3; }
     rec.tri1 = -1; rec.tri2 = j2;
     finish_contact(rec, threshold);
+    if (boxes && remap) remap_contact(rec, nP + sec * 8 + sec * 12);
     out[blockoff[item0 / 256 + blockIdx.x] + pre] = rec;
 }
 
@@ -596,7 +610,7 @@ __global__ void __launch_bounds__(256) k_C_write(int E, int nB, const EdgeRec *_
                                                  const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
                                                  const int *__restrict__ info, const int *__restrict__ blockoff,
                                                  eolc_contact *__restrict__ out, size_t xstride, size_t fstride, size_t scene_items,
-                                                 size_t box_items, size_t secC_off) {
+                                                 size_t box_items, size_t secC_off, int remap, int nP) {
     int s = blockIdx.y / nB, b = blockIdx.y % nB;
     size_t item0 = s * scene_items + secC_off + b * box_items;
     int k2 = blockIdx.x * 256 + threadIdx.x;
@@ -612,6 +626,7 @@ __global__ void __launch_bounds__(256) k_C_write(int E, int nB, const EdgeRec *_
             eolc_contact rec;
             test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, aabbE, threshold, &rec, e2, k2);
             finish_contact(rec, threshold);
+            if (remap) remap_contact(rec, nP + b * 8 + b * 12);
             *dst++ = rec;
         }
 }
@@ -629,7 +644,7 @@ struct eolc_cd_plan {
     DevBuf<EdgeRec> d_edges;
     DevBuf<double> d_r;                 // perturbation table, 3N
     // per-run buffers
-    DevBuf<double> d_x, d_xp, d_fn0, d_fnp, d_aabb, d_pxyz, d_pnorms;
+    DevBuf<double> d_x, d_xp, d_fn0, d_fnp, d_aabb, d_aabb_part, d_pxyz, d_pnorms;
     DevBuf<BoxData> d_boxes;
     DevBuf<int> d_info, d_blocksum, d_blockoff;
     DevBuf<Cand> d_partial;
@@ -776,7 +791,13 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
     // ---- prepare
     k_perturb<<<dim3((unsigned)((xs + 255) / 256), S), 256, 0, st>>>(N, x_dev, P->d_r.p, P->d_xp.p, xs); ++launches;
     if (F) { k_face_normals<<<dim3((F + 255) / 256, S), 256, 0, st>>>(F, P->d_fn.p, x_dev, P->d_xp.p, P->d_fn0.p, P->d_fnp.p, xs, fs); ++launches; }
-    k_aabb<<<S, 1024, 0, st>>>(N, P->d_xp.p, P->d_aabb.p, xs); ++launches;
+    {
+        const int nb = std::max(1, std::min((N + 2047) / 2048, 64));
+        EOLC_CUDA(P->d_aabb_part.ensure(6 * (size_t)S * nb));
+        k_aabb<<<dim3(nb, S), 256, 0, st>>>(N, 3, P->d_xp.p, P->d_aabb_part.p, xs);
+        k_aabb<<<dim3(1, S), 256, 0, st>>>(nb, 6, P->d_aabb_part.p, P->d_aabb.p, (size_t)6 * nb);
+        launches += 2;
+    }
 
     // ---- pass 1
     const int nchunk = std::max(1, std::min((F + 256 * 8 - 1) / (256 * 8), 2 * P->ctx->sm_count));
@@ -801,72 +822,56 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
     EOLC_CUDA(cudaStreamSynchronize(st));
     const int total = P->p_blockoff.p[nblocks];
 
-    // ---- pass 2
+    // ---- capacity check before anything is written to the caller
+    const int *bo = P->p_blockoff.p;
+    for (int s = 0; s <= S; ++s) scene_offset[s] = bo[(size_t)s * scene_items / 256];
+    if (total > capacity) {
+        set_error("contact buffer too small: need %d, capacity %d", total, capacity);
+        return EOLC_ERR_CAPACITY;
+    }
+
+    // ---- pass 2: records (incl. step (E) pos1_ and the CD index remap) are written on the device, in final order
     EOLC_CUDA(P->d_out.ensure(std::max(total, 1)));
-    EOLC_CUDA(P->p_out.ensure(std::max(total, 1)));
     if (total > 0) {
         if (doPE) { k_PE_write<<<dim3((unsigned)(nPE / 256), S), 256, 0, st>>>(N, nP, P->d_pxyz.p, P->d_pnorms.p, P->d_xp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, scene_items, secPE); ++launches; }
-        if (nP) { k_PT_write<<<dim3((unsigned)(nPT / 256), S), 256, 0, st>>>(F, nP, 1, nullptr, P->d_pxyz.p, P->d_pnorms.p, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secPT, 0); ++launches; }
+        if (nP) { k_PT_write<<<dim3((unsigned)(nPT / 256), S), 256, 0, st>>>(F, nP, 1, nullptr, P->d_pxyz.p, P->d_pnorms.p, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secPT, 0, 0, nP); ++launches; }
         if (nB) {
             k_A_write<<<dim3((unsigned)(nA / 256), S * nB), 256, 0, st>>>(N, F, nB, P->d_xp.p, P->d_fnp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox);
-            k_PT_write<<<dim3(1, S * nB), 256, 0, st>>>(F, 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secBox + nA, box_items);
-            k_C_write<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox + nA + nBc);
+            k_PT_write<<<dim3(1, S * nB), 256, 0, st>>>(F, 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secBox + nA, box_items, remap_box_indices, nP);
+            k_C_write<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox + nA + nBc, remap_box_indices, nP);
             launches += 3;
         }
-        EOLC_CUDA(cudaMemcpyAsync(P->p_out.p, P->d_out.p, sizeof(eolc_contact) * total, cudaMemcpyDeviceToHost, st));
+        // pinned caller buffer: DMA straight into it; pageable: via the plan's pinned staging
+        cudaPointerAttributes pa;
+        bool out_pinned = cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        eolc_contact *dst = out;
+        if (!out_pinned) { EOLC_CUDA(P->p_out.ensure(total)); dst = P->p_out.p; }
+        EOLC_CUDA(cudaMemcpyAsync(dst, P->d_out.p, sizeof(eolc_contact) * total, cudaMemcpyDeviceToHost, st));
         EOLC_CUDA(cudaStreamSynchronize(st));
+        if (!out_pinned) memcpy(out, dst, sizeof(eolc_contact) * total);
     }
     EOLC_CUDA(cudaGetLastError());
     P->last_launches = launches;
     P->last_pair_tests = (int64_t)S * ((doPE ? (int64_t)N * nP : 0) + (int64_t)nP * F + (int64_t)nB * ((int64_t)N * 24 + 8 * (int64_t)F + (int64_t)E * 12));
 
-    // ---- host post-pass over the (small) list: step (D) per box, CD remap, copy-out
-    const int *bo = P->p_blockoff.p;
-    int n_out = 0;
-    bool overflow = false;
-    std::vector<eolc_contact> lst;
-    for (int s = 0; s < S; ++s) {
-        scene_offset[s] = n_out;
-        const size_t sb = (size_t)s * scene_items / 256;
-        // points first (PE, PT): [begin, end)
-        {
-            int begin = bo[sb], end = bo[sb + secBox / 256];
-            for (int k = begin; k < end; ++k) { if (n_out < capacity) out[n_out] = P->p_out.p[k]; else overflow = true; ++n_out; }
-        }
+    // ---- step (D) (:1022-1052): per box corner keep only the closest count1 == 1 record.  Only section Bc emits
+    // count1 == 1 records and it emits at most one per corner, so the reference's delete list is always empty and the
+    // pass is the identity; this is verified per box from the (<= 8 record) corner section, O(1) per box.
+    for (int s = 0; s < S; ++s)
         for (int b = 0; b < nB; ++b) {
-            const size_t bb = sb + (secBox + (size_t)b * box_items) / 256;
-            int begin = bo[bb], end = bo[bb + box_items / 256];
-            lst.assign(P->p_out.p + begin, P->p_out.p + end);
-            // (D) :1022-1052 — per corner keep the closest count1==1 record; forward swap-with-back deletes, literally
-            for (int i1 = 0; i1 < 8; ++i1) {
-                V3 x1 = mk(hb[b].verts1[i1][0], hb[b].verts1[i1][1], hb[b].verts1[i1][2]);
-                int kmin = -1;
-                double dmin = 1e9;
-                for (int k = 0; k < (int)lst.size(); ++k)
-                    if (lst[k].count1 == 1 && lst[k].verts1[0] == i1) {
-                        V3 dx = ld(lst[k].pos2) - x1;
-                        double d = dot(dx, dx);
-                        if (d < dmin) { kmin = k; dmin = d; }
-                    }
-                if (kmin != -1) {
-                    std::vector<int> dlist;
-                    for (int k = 0; k < (int)lst.size(); ++k)
-                        if (lst[k].count1 == 1 && lst[k].verts1[0] == i1 && k != kmin) dlist.push_back(k);
-                    for (int kdel : dlist) { lst[kdel] = lst.back(); lst.pop_back(); }
+            const size_t bb = ((size_t)s * scene_items + secBox + (size_t)b * box_items + nA) / 256;
+            const int begin = bo[bb], end = bo[bb + 1];
+            int seen = 0;
+            for (int k = begin; k < end; ++k) {
+                int corner = out[k].verts1[0] - (remap_box_indices ? nP + b * 20 : 0);
+                if (out[k].count1 != 1 || corner < 0 || corner > 7 || (seen & (1 << corner))) {
+                    set_error("internal: corner section of box %d is not one-record-per-corner", b);
+                    return EOLC_ERR_UNSUPPORTED;
                 }
-            }
-            for (auto &c : lst) {
-                if (remap_box_indices) {   // Collisions.cpp:39-48 ; Box::num_points = 8, num_edges = 12
-                    if (c.count1 == 1 && c.count2 == 3) c.verts1[0] = nP + (b * 8) + (b * 12) + c.verts1[0];
-                    for (int e = 0; e < c.n_edge1; ++e) c.edge1[e] = nP + (b * 8) + (b * 12) + (8 + c.edge1[e]);
-                }
-                if (n_out < capacity) out[n_out] = c; else overflow = true;
-                ++n_out;
+                seen |= 1 << corner;
             }
         }
-    }
-    scene_offset[S] = n_out;
-    if (overflow) { set_error("contact buffer too small: need %d, capacity %d", n_out, capacity); return EOLC_ERR_CAPACITY; }
     return EOLC_OK;
 }
 

@@ -3,14 +3,20 @@
 // Replaces /root/reference/src/Forces.cpp:912-930 (fill), :331-520 (faceBasedF, non-EOL branch),
 // :685-910 (edgeBasedF, non-EOL branch) and Eigen's setFromTriplets.
 //
-// Pipeline "gather" (v1):   [face_kernel] [edge_kernel] -> element blocks in HBM scratch (SoA)
-//                           [gather_mdk] [gather_m] [gather_f] -> fixed CSR slots, pull-style:
-// every output 3x3 block sums its contributions in the reference's triplet insertion order (faces ascending,
-// then edges ascending, Forces.cpp:922-923), left to right, exactly like collapseDuplicates — no atomics,
-// bit-reproducible run to run.
+// Default pipeline "rows" (one kernel, no HBM scratch) — assemble_rows_kernel:
+//   owner-computes: a CTA owns a run of consecutive nodes and their CSR rows. One thread per (node, incident element)
+//   item evaluates that element's block ROW for the node (face_row / edge_row, elements.cuh) and parks it in shared
+//   memory; after one barrier every output 3x3 block of the CTA's rows sums its contributions from shared memory in the
+//   reference's triplet insertion order (faces ascending, then edges ascending, Forces.cpp:922-923), left to right like
+//   Eigen's collapseDuplicates, and is written ONCE to its fixed CSR slot. M and f come out of the same kernel.
+//   No atomics, no scratch traffic: HBM sees x, X, the plan's index streams and each output value exactly once.
+// Legacy pipeline "scratch" (EOLC_FORCES_PIPELINE=scratch, kept for A/B measurements): element-per-thread kernels write
+//   element blocks to an HBM scratch, three gather kernels pull them into the CSR slots (3.5x the algorithmic traffic).
+// Both are bit-reproducible run to run.
 #include "common.h"
 #include "elements.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 using namespace eolc;
@@ -34,6 +40,16 @@ struct eolc_forces_plan {
     DevBuf<int32_t> d_nbrM;                       // column node of each M block
     DevBuf<int64_t> d_cptrM, d_cptrK, d_cptrF;    // contribution list offsets per block / per node
     DevBuf<int32_t> d_contribM, d_contribK, d_contribF;
+    // "rows" pipeline
+    int pipeline = 0;                             // 0 = rows, 1 = scratch
+    int32_t n_cta = 0;
+    DevBuf<int32_t> d_cta_node0, d_cta_item0;     // n_cta + 1
+    DevBuf<uint32_t> d_items;                     // elem << 3 | pos << 1 | is_edge ; CTA-local order: faces, then edges
+    DevBuf<uint32_t> d_pl_ptr;                    // per MDK block (+1): offset into d_pl
+    DevBuf<uint16_t> d_pl;                        // item_local << 2 | column block j
+    DevBuf<uint16_t> d_blk_meta;                  // nf (bits 0-6) | diag (bit 7) | mslot (bits 8-15, 255 = not in M)
+    DevBuf<uint8_t> d_blk_lnode;                  // owning node - cta_node0
+    DevBuf<uint16_t> d_node_f;                    // first face item (CTA-local) | count << 8
     // scratch (per scene chunk)
     DevBuf<double> d_face_scr, d_edge_scr;
     int32_t scratch_scenes = 0;
@@ -190,6 +206,227 @@ __global__ void __launch_bounds__(256) gather_f(int N, const int64_t *__restrict
     f[3 * a] = f0; f[3 * a + 1] = f1; f[3 * a + 2] = f2;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// "rows" pipeline
+// ------------------------------------------------------------------------------------------------
+constexpr int NT = 128;        // items (threads) per CTA
+#ifndef ROWS_MIN_CTAS
+#define ROWS_MIN_CTAS 4
+#endif
+constexpr int ROW_SCR = 36;    // doubles parked per item: 4 blocks x 9 (faces: 3 blocks, f at 27..29, t8 at 30)
+
+__global__ void __launch_bounds__(NT, ROWS_MIN_CTAS) assemble_rows_kernel(
+    const int32_t *__restrict__ cta_node0, const int32_t *__restrict__ cta_item0, const uint32_t *__restrict__ items,
+    const int32_t *__restrict__ fn, const int32_t *__restrict__ ie, const int64_t *__restrict__ blkptrK,
+    const int64_t *__restrict__ blkptrM, const uint32_t *__restrict__ pl_ptr, const uint16_t *__restrict__ pl,
+    const uint16_t *__restrict__ blk_meta, const uint8_t *__restrict__ blk_lnode, const uint16_t *__restrict__ node_f,
+    const double *__restrict__ x, const double *__restrict__ X, double e, double nu, double rho, double beta, double gx,
+    double gy, double gz, double dhh, double *__restrict__ f, double *__restrict__ Mv, double *__restrict__ Kv,
+    size_t x_stride, size_t X_stride, size_t f_stride, size_t M_stride, size_t K_stride) {
+    __shared__ double scr[ROW_SCR * NT];
+    __shared__ uint16_t spl[4 * NT];     // the CTA's pull entries (<= 3 per face item + 4 per edge item)
+    const int c = blockIdx.x, t = threadIdx.x, s = blockIdx.y;
+    x += s * x_stride; X += s * X_stride; f += s * f_stride; Mv += s * M_stride; Kv += s * K_stride;
+    const int node0 = cta_node0[c], node1 = cta_node0[c + 1];
+    const int item0 = cta_item0[c], nitems = cta_item0[c + 1] - item0;
+    const int64_t ob0 = blkptrK[node0];
+    const int nbc = (int)(blkptrK[node1] - ob0);
+
+    // ---- prefetch everything phase 2 needs, so its global latency hides under phase 1's arithmetic
+    uint32_t it = 0;
+    if (t < nitems) it = items[item0 + t];
+    const uint32_t plbase = pl_ptr[ob0];
+    uint32_t q0 = 0, q1 = 0, meta = 0, ln = 0;
+    if (t < nbc) { q0 = pl_ptr[ob0 + t] - plbase; q1 = pl_ptr[ob0 + t + 1] - plbase; meta = blk_meta[ob0 + t]; ln = blk_lnode[ob0 + t]; }
+    uint32_t nfm = 0;
+    if (t < node1 - node0) nfm = node_f[node0 + t];
+    {
+        const int npl = (int)(pl_ptr[ob0 + nbc] - plbase);
+        for (int k = t; k < npl; k += NT) spl[k] = pl[plbase + k];
+    }
+
+    // ---- phase 1: one (node, element) block row per thread -> shared memory (SoA: scr[k*NT + t], conflict-free)
+    if (t < nitems) {
+        const int el = it >> 3, pos = (it >> 1) & 3;
+        if (it & 1) {
+            const int4 st = *reinterpret_cast<const int4 *>(ie + 4 * (size_t)el);
+            const double *p0 = x + 3 * (size_t)st.x, *p1 = x + 3 * (size_t)st.y, *p2 = x + 3 * (size_t)st.z, *p3 = x + 3 * (size_t)st.w;
+            const double2 A0 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.x), A1 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.y);
+            const double2 A2 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.z), A3 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.w);
+            double *dst = scr + t;
+            edge_row_emit(pos, mk3(p0[0], p0[1], p0[2]), mk3(p1[0], p1[1], p1[2]), mk3(p2[0], p2[1], p2[2]), mk3(p3[0], p3[1], p3[2]),
+                          A0.x, A0.y, A1.x, A1.y, A2.x, A2.y, A3.x, A3.y, beta, dhh, [dst](int j, const blk3 &B) {
+#pragma unroll
+                              for (int q = 0; q < 9; ++q) dst[(j * 9 + q) * NT] = B.m[q];
+                          });
+        } else {
+            const int a = fn[3 * (size_t)el], b = fn[3 * (size_t)el + 1], cc = fn[3 * (size_t)el + 2];
+            const double *p0 = x + 3 * (size_t)a, *p1 = x + 3 * (size_t)b, *p2 = x + 3 * (size_t)cc;
+            const double2 A0 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)a), A1 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)b);
+            const double2 A2 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)cc);
+            FaceRowOut o;
+            face_row(pos, mk3(p0[0], p0[1], p0[2]), mk3(p1[0], p1[1], p1[2]), mk3(p2[0], p2[1], p2[2]), A0.x, A0.y, A1.x, A1.y,
+                     A2.x, A2.y, e, nu, rho, mk3(gx, gy, gz), dhh, o);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int q = 0; q < 9; ++q) scr[(j * 9 + q) * NT + t] = o.K[j].m[q];
+            scr[27 * NT + t] = o.f[0]; scr[28 * NT + t] = o.f[1]; scr[29 * NT + t] = o.f[2];
+            scr[30 * NT + t] = o.t8;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: every output block of the CTA's rows pulls its contributions in reference order
+    for (int ob = t; ob < nbc; ob += NT) {
+        const int64_t g = ob0 + ob;
+        if (ob != t) { q0 = pl_ptr[g] - plbase; q1 = pl_ptr[g + 1] - plbase; meta = blk_meta[g]; ln = blk_lnode[g]; }
+        const int nf = meta & 127, mslot = meta >> 8;
+        const bool diag = (meta & 128) != 0;
+        double acc[9], m = 0.0;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+        for (uint32_t p = q0; p < q1; ++p) {
+            const uint32_t en = spl[p];
+            const double *src = scr + (en & 3) * 9 * NT + (en >> 2);
+            if (p == q0) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) acc[q] = src[q * NT];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) acc[q] = acc[q] + src[q * NT];
+            }
+            if ((int)(p - q0) < nf) {   // mass: faces only, t8/12 on the diagonal block, t8/24 otherwise
+                const double t8 = scr[30 * NT + (en >> 2)];
+                const double mi = diag ? t8 / 12.0 : t8 / 24.0;
+                m = p == q0 ? mi : m + mi;
+            }
+        }
+        const int a = node0 + (int)ln;
+        const int64_t b0 = blkptrK[a];
+        const int deg = (int)(blkptrK[a + 1] - b0);
+        const int pcol = (int)(g - b0);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double *row = Kv + 9 * b0 + (int64_t)j * 3 * deg + 3 * pcol;
+            __stcs(row, acc[3 * j]); __stcs(row + 1, acc[3 * j + 1]); __stcs(row + 2, acc[3 * j + 2]);
+        }
+        if (mslot != 255) {
+            const int64_t m0 = blkptrM[a];
+            const int degM = (int)(blkptrM[a + 1] - m0);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                double *row = Mv + 9 * m0 + (int64_t)j * 3 * degM + 3 * mslot;
+                __stcs(row, j == 0 ? m : 0.0); __stcs(row + 1, j == 1 ? m : 0.0); __stcs(row + 2, j == 2 ? m : 0.0);
+            }
+        }
+    }
+    // ---- f: per node, its face items in ascending face order (f.setZero() then +=, Forces.cpp:915,500-502)
+    if (t < node1 - node0) {
+        const int first = nfm & 255, cnt = nfm >> 8;
+        double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+        for (int k = 0; k < cnt; ++k) { f0 += scr[27 * NT + first + k]; f1 += scr[28 * NT + first + k]; f2 += scr[29 * NT + first + k]; }
+        double *dst = f + 3 * (size_t)(node0 + t);
+        dst[0] = f0; dst[1] = f1; dst[2] = f2;
+    }
+}
+
+inline int64_t find_block(const std::vector<int64_t> &blkptr, const std::vector<int32_t> &nbr, int32_t a, int32_t b);
+
+int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
+    const int32_t N = P->N, F = P->F, Ei = P->Ei;
+    const int32_t *fn = P->h_face_nodes.data();
+    const int32_t *ie = P->h_iedge.data();
+    // node -> incident faces / interior edges (ascending element index), with the node's position in the element
+    std::vector<int32_t> nfp(N + 1, 0), nep(N + 1, 0);
+    for (int64_t i = 0; i < 3 * (int64_t)F; ++i) nfp[fn[i] + 1]++;
+    for (int64_t i = 0; i < 4 * (int64_t)Ei; ++i) nep[ie[i] + 1]++;
+    for (int32_t a = 0; a < N; ++a) { nfp[a + 1] += nfp[a]; nep[a + 1] += nep[a]; }
+    std::vector<uint32_t> nfl(nfp[N]), nel(nep[N]);
+    {
+        std::vector<int32_t> pf(nfp.begin(), nfp.end() - 1), pe(nep.begin(), nep.end() - 1);
+        for (int32_t i = 0; i < F; ++i) for (int v = 0; v < 3; ++v) nfl[pf[fn[3 * (size_t)i + v]]++] = ((uint32_t)i << 3) | (v << 1);
+        for (int32_t i = 0; i < Ei; ++i) for (int v = 0; v < 4; ++v) nel[pe[ie[4 * (size_t)i + v]]++] = ((uint32_t)i << 3) | (v << 1) | 1u;
+    }
+    // CTA partition: consecutive nodes, at most NT items and 128 nodes per CTA
+    std::vector<int32_t> cta_node0, cta_item0;
+    cta_node0.push_back(0); cta_item0.push_back(0);
+    {
+        int64_t items = 0; int cur = 0, nodes = 0;
+        for (int32_t a = 0; a < N; ++a) {
+            int na = (nfp[a + 1] - nfp[a]) + (nep[a + 1] - nep[a]);
+            if (na > NT || (nfp[a + 1] - nfp[a]) > 127) { set_error("node %d has %d incident elements (limit %d)", a, na, NT); return EOLC_ERR_UNSUPPORTED; }
+            if (cur + na > NT || nodes == 128) { cta_node0.push_back(a); cta_item0.push_back((int32_t)items); cur = 0; nodes = 0; }
+            cur += na; items += na; ++nodes;
+        }
+        if (items >= ((int64_t)1 << 31)) { set_error("too many (node, element) items"); return EOLC_ERR_UNSUPPORTED; }
+        cta_node0.push_back(N); cta_item0.push_back((int32_t)items);
+    }
+    const int32_t nc = (int32_t)cta_node0.size() - 1;
+    P->n_cta = nc;
+    std::vector<uint32_t> items((size_t)cta_item0[nc]);
+    std::vector<uint32_t> pl_ptr((size_t)P->nblkK + 1, 0);
+    std::vector<uint16_t> pl;
+    pl.reserve(9 * (size_t)F + 16 * (size_t)Ei);
+    std::vector<uint16_t> meta((size_t)P->nblkK, 0), node_f(N, 0);
+    std::vector<uint8_t> lnode((size_t)P->nblkK, 0);
+    std::vector<std::vector<uint16_t>> tmp;   // per block of the current node
+    for (int32_t c = 0; c < nc; ++c) {
+        const int32_t n0 = cta_node0[c], n1 = cta_node0[c + 1];
+        // item order inside the CTA: all face items (node order, face ascending), then all edge items
+        int32_t nface_items = 0;
+        for (int32_t a = n0; a < n1; ++a) nface_items += nfp[a + 1] - nfp[a];
+        int32_t fpos = 0, epos = nface_items;
+        for (int32_t a = n0; a < n1; ++a) {
+            const int64_t b0 = P->h_blkptrK[a], b1 = P->h_blkptrK[a + 1];
+            const int deg = (int)(b1 - b0);
+            if (deg > 255) { set_error("node %d has %d neighbours (limit 255)", a, deg); return EOLC_ERR_UNSUPPORTED; }
+            tmp.assign(deg, {});
+            std::vector<int> nfaces(deg, 0);
+            node_f[a] = (uint16_t)(fpos | ((nfp[a + 1] - nfp[a]) << 8));
+            for (int32_t k = nfp[a]; k < nfp[a + 1]; ++k) {      // faces ascending
+                const uint32_t it = nfl[k];
+                items[(size_t)cta_item0[c] + fpos] = it;
+                const int32_t face = it >> 3;
+                for (int j = 0; j < 3; ++j) {
+                    int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, fn[3 * (size_t)face + j]) - b0);
+                    tmp[p].push_back((uint16_t)((fpos << 2) | j));
+                    nfaces[p]++;
+                }
+                ++fpos;
+            }
+            for (int32_t k = nep[a]; k < nep[a + 1]; ++k) {      // then interior edges ascending
+                const uint32_t it = nel[k];
+                items[(size_t)cta_item0[c] + epos] = it;
+                const int32_t ed = it >> 3;
+                for (int j = 0; j < 4; ++j) {
+                    int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, ie[4 * (size_t)ed + j]) - b0);
+                    tmp[p].push_back((uint16_t)((epos << 2) | j));
+                }
+                ++epos;
+            }
+            for (int p = 0; p < deg; ++p) {
+                const int32_t b = P->h_nbrK[b0 + p];
+                pl_ptr[b0 + p] = (uint32_t)pl.size();
+                pl.insert(pl.end(), tmp[p].begin(), tmp[p].end());
+                int mslot = 255;
+                if (nfaces[p] > 0) mslot = (int)(find_block(P->h_blkptrM, P->h_nbrM, a, b) - P->h_blkptrM[a]);
+                meta[b0 + p] = (uint16_t)(nfaces[p] | (a == b ? 128 : 0) | (mslot << 8));
+                lnode[b0 + p] = (uint8_t)(a - n0);
+            }
+        }
+    }
+    if (pl.size() >= ((size_t)1 << 32)) { set_error("pull list too long"); return EOLC_ERR_UNSUPPORTED; }
+    pl_ptr[P->nblkK] = (uint32_t)pl.size();
+    EOLC_CUDA(P->d_cta_node0.upload(cta_node0, st)); EOLC_CUDA(P->d_cta_item0.upload(cta_item0, st));
+    EOLC_CUDA(P->d_items.upload(items, st)); EOLC_CUDA(P->d_pl_ptr.upload(pl_ptr, st)); EOLC_CUDA(P->d_pl.upload(pl, st));
+    EOLC_CUDA(P->d_blk_meta.upload(meta, st)); EOLC_CUDA(P->d_blk_lnode.upload(lnode, st)); EOLC_CUDA(P->d_node_f.upload(node_f, st));
+    EOLC_CUDA(P->d_blkptrM.upload(P->h_blkptrM, st)); EOLC_CUDA(P->d_blkptrK.upload(P->h_blkptrK, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));
+    return EOLC_OK;
+}
+
 int build_pattern(eolc_forces_plan *P) {
     const int32_t N = P->N, F = P->F;
     const int32_t Ei = P->Ei;
@@ -331,6 +568,20 @@ int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X
                 const double *grav, double h, double *f, double *Mv, double *Kv) {
     cudaStream_t st = P->ctx->stream;
     const double dhh = mat->dampingB * h * h;   // damping(1)*h*h, Forces.cpp:105
+    if (P->pipeline == 0) {
+        if (P->N == 0) return EOLC_OK;
+        for (int32_t s0 = 0; s0 < S; s0 += 65535) {
+            const int32_t sc = std::min<int32_t>(65535, S - s0);
+            assemble_rows_kernel<<<dim3(P->n_cta, sc), NT, 0, st>>>(
+                P->d_cta_node0.p, P->d_cta_item0.p, P->d_items.p, P->d_face_nodes.p, P->d_iedge.p, P->d_blkptrK.p, P->d_blkptrM.p,
+                P->d_pl_ptr.p, P->d_pl.p, P->d_blk_meta.p, P->d_blk_lnode.p, P->d_node_f.p, x + (size_t)s0 * 3 * P->N,
+                X + (size_t)s0 * 2 * P->N, mat->e, mat->nu, mat->density, mat->beta, grav[0], grav[1], grav[2], dhh,
+                f + (size_t)s0 * P->dof, Mv + (size_t)s0 * P->nnzM, Kv + (size_t)s0 * P->nnzK, (size_t)3 * P->N, (size_t)2 * P->N,
+                (size_t)P->dof, (size_t)P->nnzM, (size_t)P->nnzK);
+        }
+        EOLC_CUDA(cudaGetLastError());
+        return EOLC_OK;
+    }
     // scene chunks bounded by the scratch budget (~4 GB)
     size_t per_scene = ((size_t)FACE_SCR * P->F + (size_t)EDGE_SCR * P->Ei) * sizeof(double);
     int32_t chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)4 << 30) / std::max<size_t>(per_scene, 1)));
@@ -408,7 +659,9 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
     cudaError_t ce = P->d_face_nodes.upload(P->h_face_nodes, st);
     if (ce == cudaSuccess) ce = P->d_iedge.upload(P->h_iedge, st);
     if (ce != cudaSuccess) { delete P; set_error("upload failed: %s", cudaGetErrorString(ce)); return EOLC_ERR_CUDA; }
-    rc = build_contribs(P, st);
+    const char *pe = getenv("EOLC_FORCES_PIPELINE");
+    P->pipeline = (pe && strcmp(pe, "scratch") == 0) ? 1 : 0;
+    rc = P->pipeline == 0 ? build_rows_plan(P, st) : build_contribs(P, st);
     if (rc) { delete P; return rc; }
     *out = P;
     return EOLC_OK;
@@ -442,7 +695,7 @@ int eolc_forces_counts(const eolc_forces_plan *plan, int32_t *n_faces, int32_t *
     return EOLC_OK;
 }
 
-int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return plan ? 5 : 0; }
+int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return plan ? (plan->pipeline == 0 ? 1 : 5) : 0; }
 
 int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
                                  const eolc_material *mat, const double grav[3], double h, double *f_dev,

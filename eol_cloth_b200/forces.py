@@ -59,7 +59,7 @@ class ForcesPlan:
         capi.check(capi.lib().eolc_forces_pattern(self._h, which, ctypes.byref(dof), ctypes.byref(nnz),
                                                   ctypes.byref(outer), ctypes.byref(inner)))
         o = np.ctypeslib.as_array(outer, (dof.value + 1,)).copy()
-        i = np.ctypeslib.as_array(inner, (max(nnz.value, 1),))[:nnz.value].copy()
+        i = np.ctypeslib.as_array(inner, (nnz.value,)).copy() if nnz.value else np.zeros(0, np.int32)
         return o, i
 
     @property

@@ -136,7 +136,7 @@ def test_reproducible_and_dev_equals_host(ctx):
 
 def test_fullsize_1024_properties(ctx):
     """BASELINE config 4 at full size (oracle too slow): size-independent properties.
-    (1) pattern sizes of SURVEY §8; (2) exact symmetry of M and MDK; (3) K has translation null space, so the three
+    (1) pattern sizes of SURVEY §8; (2) symmetry of M (exact) and MDK (to rounding); (3) K has translation null space, so the three
     row-block sums of MDK equal those of M; (4) sum(M) = 3 rho * area = 3 * 0.05; (5) sum f = total weight."""
     import scipy.sparse as sp
     mesh = _mesh("regular2", 1024)
@@ -146,10 +146,11 @@ def test_fullsize_1024_properties(ctx):
     M = sp.csc_matrix((forces.M[2], forces.M[1], forces.M[0]), shape=(3 * N, 3 * N))
     K = sp.csc_matrix((forces.MDK[2], forces.MDK[1], forces.MDK[0]), shape=(3 * N, 3 * N))
     assert abs(M - M.T).max() == 0.0
-    assert abs(K - K.T).max() == 0.0
+    scale = abs(K).max()
+    # MDK: rows are assembled independently (owner-computes), so (r,c) and (c,r) agree to rounding, not bitwise
+    assert abs(K - K.T).max() <= 1e-13 * scale
     T = sp.csr_matrix(np.tile(np.eye(3), (N, 1)))       # translations
     dK = (K - M) @ T
-    scale = abs(K).max()
     assert abs(dK).max() < 1e-9 * scale
     assert abs(M.sum() - 3 * 0.05 * 1.0) < 1e-12
     fz = forces.f.reshape(-1, 3).sum(axis=0)
