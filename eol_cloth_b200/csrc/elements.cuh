@@ -38,6 +38,15 @@
 
 namespace eolc {
 
+// 1/sqrt(x): one MUFU + Newton steps on the device (<= 2 ulp, far inside the 1e-10 budget) instead of sqrt + divide
+EOLC_HD double rsq(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 struct v3 { double x, y, z; };
 EOLC_HD v3 mk3(double x, double y, double z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
 EOLC_HD v3 operator+(v3 a, v3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -268,20 +277,21 @@ EOLC_HD void edge_element(v3 x0, v3 x1, v3 x2, v3 x3, double X0x, double X0y, do
 //       B_ij = [j in t0] (a U_j^T + b Y_j^T - w0_j c^T + (c.w0_j) I) + [j in t1] (a' V_j^T + b' Z_j^T - w1_j c'^T + (c'.w1_j) I)
 //              + s0_ij [kk g0]x + s1_ij [kk g1]x,      k0 = c dhh/|n0|^2, k1 = c dhh/|n1|^2, k01 = -c dhh/(|n0||n1|), kk = -c dhh
 //  The code is uniform in v / i (selects, no branches), so a warp may mix rows.
-struct FaceRowOut { blk3 K[3]; double f[3]; double t8; };
+struct FaceRowOut { blk3 K[3]; double f[3]; double md, mo; };   // md = t8/12, mo = t8/24 (ComputeInertial.cpp:44-47)
 
 EOLC_HD v3 sel3(int i, v3 a, v3 b, v3 c) { return i == 0 ? a : (i == 1 ? b : c); }
 EOLC_HD v3 sel4(int i, v3 a, v3 b, v3 c, v3 d) { return i == 0 ? a : (i == 1 ? b : (i == 2 ? c : d)); }
+// Lame-type constants of ComputeMembrane.cpp:46,84-87 (evaluated once per fill on the host)
+inline double membrane_mu(double e, double nu) { return e / (1.0 + nu) * 0.5; }
+inline double membrane_lambda(double e, double nu) { return e * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)); }
 
 EOLC_HD void face_row(int v, v3 xa, v3 xb, v3 xc, double Xax, double Xay, double Xbx, double Xby, double Xcx, double Xcy,
-                      double e, double nu, double rho, v3 g, double dhh, FaceRowOut &o) {
+                      double mu, double lam, double rho, v3 g, double dhh, FaceRowOut &o) {
     v3 d1 = xb - xa, d2 = xc - xa;
     v3 nrm = cross(d1, d2);
-    double il1 = 1.0 / sqrt(dot(d1, d1));
-    v3 Px = il1 * d1;
+    v3 Px = rsq(dot(d1, d1)) * d1;
     v3 Py = cross(nrm, Px);
-    double il2 = 1.0 / sqrt(dot(Py, Py));
-    Py = il2 * Py;
+    Py = rsq(dot(Py, Py)) * Py;
     double t7 = Xax * Xby - Xax * Xcy - Xbx * Xay + Xcx * Xay + Xbx * Xcy - Xcx * Xby;
     double t17 = 1.0 / t7;
     double gb0 = t17 * (Xcy - Xay), gb1 = t17 * (Xax - Xcx);
@@ -292,12 +302,10 @@ EOLC_HD void face_row(int v, v3 xa, v3 xb, v3 xc, double Xax, double Xay, double
     double detM = m11 * m22 - m12 * m21;
     double sg = detM < 0.0 ? -1.0 : (detM == 0.0 ? 0.0 : 1.0);
     double q00 = m11 + sg * m22, q01 = m12 - sg * m21, q10 = m21 - sg * m12, q11 = m22 + sg * m11;
-    double icl = 1.0 / sqrt(q00 * q00 + q10 * q10);
+    double icl = rsq(q00 * q00 + q10 * q10);
     q00 *= icl; q01 *= icl; q10 *= icl; q11 *= icl;
     v3 r0 = q00 * Px + q10 * Py, r1 = q01 * Px + q11 * Py;
     double E00 = dot(r0, F0) - 1.0, E10 = dot(r1, F0), E01 = dot(r0, F1), E11 = dot(r1, F1) - 1.0;
-    double mu = e / (1.0 + nu) * 0.5;
-    double lam = e * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
     double A = 0.5 * t7;
     double tr = E00 + E11;
     double S00 = 2.0 * mu * E00 + lam * tr, S01 = 2.0 * mu * E01, S10 = 2.0 * mu * E10, S11 = 2.0 * mu * E11 + lam * tr;
@@ -305,16 +313,16 @@ EOLC_HD void face_row(int v, v3 xa, v3 xb, v3 xc, double Xax, double Xay, double
     const double gv0 = v == 0 ? ga0 : (v == 1 ? gb0 : gc0), gv1 = v == 0 ? ga1 : (v == 1 ? gb1 : gc1);
     {
         v3 fv = (-A * (S00 * gv0 + S01 * gv1)) * r0 + (-A * (S10 * gv0 + S11 * gv1)) * r1;
-        double s6 = t8 / 6.0;
+        double s6 = t8 * (1.0 / 6.0);
         o.f[0] = fv.x + s6 * g.x; o.f[1] = fv.y + s6 * g.y; o.f[2] = fv.z + s6 * g.z;
     }
-    o.t8 = t8;
+    const double md = t8 / 12.0, mo = 0.5 * md;   // t8/24 == (t8/12)/2 exactly
+    o.md = md; o.mo = mo;
     double RR[6] = {r0.x * r0.x + r1.x * r1.x, r0.x * r0.y + r1.x * r1.y, r0.x * r0.z + r1.x * r1.z,
                     r0.y * r0.y + r1.y * r1.y, r0.y * r0.z + r1.y * r1.z, r0.z * r0.z + r1.z * r1.z};
     v3 qa = ga0 * r0 + ga1 * r1, qb = gb0 * r0 + gb1 * r1, qc = gc0 * r0 + gc1 * r1;
     v3 qv = sel3(v, qa, qb, qc);
     const double a2mu = dhh * A * 2.0 * mu, alam = dhh * A * lam;
-    const double md = t8 / 12.0, mo = t8 / 24.0;
     // products q_v[p]*q_j[q] are formed first (commutative), so B_vj of this row and B_jv of row j are exact transposes
     auto block = [&](blk3 &B, double gj0, double gj1, v3 qj, double mass) {
         double s = a2mu * (gv0 * gj0 + gv1 * gj1);
@@ -344,13 +352,12 @@ EOLC_HD void edge_row_emit(int i, v3 x0, v3 x1, v3 x2, v3 x3, double X0x, double
     {
         v3 e = x1 - x0;
         v3 n0 = cross(e, x2 - x0), n1 = cross(x3 - x0, e);
-        double s0 = 1.0 / dot(n0, n0), s1 = 1.0 / dot(n1, n1);
-        double il0 = sqrt(s0), il1 = sqrt(s1);
+        double il0 = rsq(dot(n0, n0)), il1 = rsq(dot(n1, n1));
         u = il0 * n0; v = il1 * n1;
         D = dot(u, v);
         const double kk = -c * dhh;
-        k0 = -kk * s0; k1 = -kk * s1; k01 = kk * il0 * il1;
         kg0 = kk * il0; kg1 = kk * il1;
+        k0 = -kg0 * il0; k1 = -kg1 * il1; k01 = kg0 * il1;
     }
     const v3 z = mk3(0.0, 0.0, 0.0);
     // the row's vectors: w0_i in (x2-x1, x0-x2, x1-x0, 0), w1_i in (x1-x3, x3-x0, 0, x0-x1)

@@ -43,11 +43,12 @@ struct eolc_forces_plan {
     // "rows" pipeline
     int pipeline = 0;                             // 0 = rows, 1 = scratch
     int32_t n_cta = 0;
-    DevBuf<int32_t> d_cta_node0, d_cta_item0;     // n_cta + 1
-    DevBuf<uint32_t> d_items;                     // elem << 3 | pos << 1 | is_edge ; CTA-local order: faces, then edges
+    DevBuf<int32_t> d_cta_node0;                  // n_cta + 1
+    DevBuf<uint32_t> d_items;                     // NT slots per CTA: elem << 3 | pos << 1 | is_edge, NO_ITEM = empty
     DevBuf<uint32_t> d_pl_ptr;                    // per MDK block (+1): offset into d_pl
     DevBuf<uint16_t> d_pl;                        // item_local << 2 | column block j
     DevBuf<uint16_t> d_blk_meta;                  // nf (bits 0-6) | diag (bit 7) | mslot (bits 8-15, 255 = not in M)
+    DevBuf<uint16_t> d_blk_order;                 // per CTA: its blocks by descending contribution count
     DevBuf<uint8_t> d_blk_lnode;                  // owning node - cta_node0
     DevBuf<uint16_t> d_node_f;                    // first face item (CTA-local) | count << 8
     // scratch (per scene chunk)
@@ -210,35 +211,48 @@ __global__ void __launch_bounds__(256) gather_f(int N, const int64_t *__restrict
 // ------------------------------------------------------------------------------------------------
 // "rows" pipeline
 // ------------------------------------------------------------------------------------------------
-constexpr int NT = 128;        // items (threads) per CTA
+constexpr int FACE_SLOTS = 32;                     // warp 0: (node, face) items
+constexpr int EDGE_SLOTS = 64;                     // warps 1-2: (node, interior edge) items
+constexpr int NT = FACE_SLOTS + EDGE_SLOTS;        // threads per CTA; kinds are warp aligned, so no warp diverges
+constexpr int ITEM_STRIDE = 42;                    // doubles parked per item: block j at 10*j (16 B aligned, 9 used);
+                                                   // faces: f at 30..32, t8/12 at 33, t8/24 at 34.  Stride 42 makes the
+                                                   // quarter-warp STS.128 pattern bank-conflict free (84 words = 20 mod 32).
+constexpr uint32_t NO_ITEM = 0xFFFFFFFFu;
 #ifndef ROWS_MIN_CTAS
-#define ROWS_MIN_CTAS 4
+#define ROWS_MIN_CTAS 5
 #endif
-constexpr int ROW_SCR = 36;    // doubles parked per item: 4 blocks x 9 (faces: 3 blocks, f at 27..29, t8 at 30)
+
+__device__ __forceinline__ void park_block(double *dst, const blk3 &B) {
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    d2[0] = make_double2(B.m[0], B.m[1]); d2[1] = make_double2(B.m[2], B.m[3]);
+    d2[2] = make_double2(B.m[4], B.m[5]); d2[3] = make_double2(B.m[6], B.m[7]);
+    dst[8] = B.m[8];
+}
 
 __global__ void __launch_bounds__(NT, ROWS_MIN_CTAS) assemble_rows_kernel(
-    const int32_t *__restrict__ cta_node0, const int32_t *__restrict__ cta_item0, const uint32_t *__restrict__ items,
-    const int32_t *__restrict__ fn, const int32_t *__restrict__ ie, const int64_t *__restrict__ blkptrK,
-    const int64_t *__restrict__ blkptrM, const uint32_t *__restrict__ pl_ptr, const uint16_t *__restrict__ pl,
-    const uint16_t *__restrict__ blk_meta, const uint8_t *__restrict__ blk_lnode, const uint16_t *__restrict__ node_f,
-    const double *__restrict__ x, const double *__restrict__ X, double e, double nu, double rho, double beta, double gx,
+    const int32_t *__restrict__ cta_node0, const uint32_t *__restrict__ items, const int32_t *__restrict__ fn,
+    const int32_t *__restrict__ ie, const int64_t *__restrict__ blkptrK, const int64_t *__restrict__ blkptrM,
+    const uint32_t *__restrict__ pl_ptr, const uint16_t *__restrict__ pl, const uint16_t *__restrict__ blk_meta,
+    const uint8_t *__restrict__ blk_lnode, const uint16_t *__restrict__ blk_order, const uint16_t *__restrict__ node_f,
+    const double *__restrict__ x, const double *__restrict__ X, double mu, double lam, double rho, double beta, double gx,
     double gy, double gz, double dhh, double *__restrict__ f, double *__restrict__ Mv, double *__restrict__ Kv,
     size_t x_stride, size_t X_stride, size_t f_stride, size_t M_stride, size_t K_stride) {
-    __shared__ double scr[ROW_SCR * NT];
-    __shared__ uint16_t spl[4 * NT];     // the CTA's pull entries (<= 3 per face item + 4 per edge item)
+    __shared__ __align__(16) double scr[ITEM_STRIDE * NT];
+    __shared__ uint16_t spl[3 * FACE_SLOTS + 4 * EDGE_SLOTS];   // the CTA's pull entries
     const int c = blockIdx.x, t = threadIdx.x, s = blockIdx.y;
     x += s * x_stride; X += s * X_stride; f += s * f_stride; Mv += s * M_stride; Kv += s * K_stride;
     const int node0 = cta_node0[c], node1 = cta_node0[c + 1];
-    const int item0 = cta_item0[c], nitems = cta_item0[c + 1] - item0;
     const int64_t ob0 = blkptrK[node0];
     const int nbc = (int)(blkptrK[node1] - ob0);
 
     // ---- prefetch everything phase 2 needs, so its global latency hides under phase 1's arithmetic
-    uint32_t it = 0;
-    if (t < nitems) it = items[item0 + t];
+    const uint32_t it = items[(size_t)c * NT + t];
     const uint32_t plbase = pl_ptr[ob0];
-    uint32_t q0 = 0, q1 = 0, meta = 0, ln = 0;
-    if (t < nbc) { q0 = pl_ptr[ob0 + t] - plbase; q1 = pl_ptr[ob0 + t + 1] - plbase; meta = blk_meta[ob0 + t]; ln = blk_lnode[ob0 + t]; }
+    uint32_t q0 = 0, q1 = 0, meta = 0, ln = 0, ob = 0;
+    if (t < nbc) {
+        ob = blk_order[ob0 + t];
+        q0 = pl_ptr[ob0 + ob] - plbase; q1 = pl_ptr[ob0 + ob + 1] - plbase; meta = blk_meta[ob0 + ob]; ln = blk_lnode[ob0 + ob];
+    }
     uint32_t nfm = 0;
     if (t < node1 - node0) nfm = node_f[node0 + t];
     {
@@ -246,20 +260,18 @@ __global__ void __launch_bounds__(NT, ROWS_MIN_CTAS) assemble_rows_kernel(
         for (int k = t; k < npl; k += NT) spl[k] = pl[plbase + k];
     }
 
-    // ---- phase 1: one (node, element) block row per thread -> shared memory (SoA: scr[k*NT + t], conflict-free)
-    if (t < nitems) {
+    // ---- phase 1: one (node, element) block row per thread -> shared memory
+    if (it != NO_ITEM) {
         const int el = it >> 3, pos = (it >> 1) & 3;
-        if (it & 1) {
+        double *dst = scr + ITEM_STRIDE * t;
+        if (t >= FACE_SLOTS) {
             const int4 st = *reinterpret_cast<const int4 *>(ie + 4 * (size_t)el);
             const double *p0 = x + 3 * (size_t)st.x, *p1 = x + 3 * (size_t)st.y, *p2 = x + 3 * (size_t)st.z, *p3 = x + 3 * (size_t)st.w;
             const double2 A0 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.x), A1 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.y);
             const double2 A2 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.z), A3 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.w);
-            double *dst = scr + t;
             edge_row_emit(pos, mk3(p0[0], p0[1], p0[2]), mk3(p1[0], p1[1], p1[2]), mk3(p2[0], p2[1], p2[2]), mk3(p3[0], p3[1], p3[2]),
-                          A0.x, A0.y, A1.x, A1.y, A2.x, A2.y, A3.x, A3.y, beta, dhh, [dst](int j, const blk3 &B) {
-#pragma unroll
-                              for (int q = 0; q < 9; ++q) dst[(j * 9 + q) * NT] = B.m[q];
-                          });
+                          A0.x, A0.y, A1.x, A1.y, A2.x, A2.y, A3.x, A3.y, beta, dhh,
+                          [dst](int j, const blk3 &B) { park_block(dst + 10 * j, B); });
         } else {
             const int a = fn[3 * (size_t)el], b = fn[3 * (size_t)el + 1], cc = fn[3 * (size_t)el + 2];
             const double *p0 = x + 3 * (size_t)a, *p1 = x + 3 * (size_t)b, *p2 = x + 3 * (size_t)cc;
@@ -267,66 +279,72 @@ __global__ void __launch_bounds__(NT, ROWS_MIN_CTAS) assemble_rows_kernel(
             const double2 A2 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)cc);
             FaceRowOut o;
             face_row(pos, mk3(p0[0], p0[1], p0[2]), mk3(p1[0], p1[1], p1[2]), mk3(p2[0], p2[1], p2[2]), A0.x, A0.y, A1.x, A1.y,
-                     A2.x, A2.y, e, nu, rho, mk3(gx, gy, gz), dhh, o);
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-#pragma unroll
-                for (int q = 0; q < 9; ++q) scr[(j * 9 + q) * NT + t] = o.K[j].m[q];
-            scr[27 * NT + t] = o.f[0]; scr[28 * NT + t] = o.f[1]; scr[29 * NT + t] = o.f[2];
-            scr[30 * NT + t] = o.t8;
+                     A2.x, A2.y, mu, lam, rho, mk3(gx, gy, gz), dhh, o);
+            park_block(dst, o.K[0]); park_block(dst + 10, o.K[1]); park_block(dst + 20, o.K[2]);
+            dst[30] = o.f[0]; dst[31] = o.f[1]; dst[32] = o.f[2]; dst[33] = o.md; dst[34] = o.mo;
         }
     }
     __syncthreads();
 
-    // ---- phase 2: every output block of the CTA's rows pulls its contributions in reference order
-    for (int ob = t; ob < nbc; ob += NT) {
-        const int64_t g = ob0 + ob;
-        if (ob != t) { q0 = pl_ptr[g] - plbase; q1 = pl_ptr[g + 1] - plbase; meta = blk_meta[g]; ln = blk_lnode[g]; }
-        const int nf = meta & 127, mslot = meta >> 8;
-        const bool diag = (meta & 128) != 0;
-        double acc[9], m = 0.0;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) acc[q] = 0.0;
-        for (uint32_t p = q0; p < q1; ++p) {
+    // ---- phase 2: every output block of the CTA's rows pulls its contributions in reference order.
+    // blk_order hands the blocks out by descending contribution count, so the lanes of a warp run similar trip counts.
+    for (int k = t; k < nbc; k += NT) {
+        if (k != t) {
+            ob = blk_order[ob0 + k];
+            q0 = pl_ptr[ob0 + ob] - plbase; q1 = pl_ptr[ob0 + ob + 1] - plbase; meta = blk_meta[ob0 + ob]; ln = blk_lnode[ob0 + ob];
+        }
+        double a0, a1, a2, a3, a4, a5, a6, a7, a8;
+        {
+            const uint32_t en = spl[q0];
+            const double *src = scr + ITEM_STRIDE * (en >> 2) + 10 * (en & 3);
+            const double2 *s2 = reinterpret_cast<const double2 *>(src);
+            double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3_ = s2[3];
+            a0 = v0.x; a1 = v0.y; a2 = v1.x; a3 = v1.y; a4 = v2.x; a5 = v2.y; a6 = v3_.x; a7 = v3_.y; a8 = src[8];
+        }
+        for (uint32_t p = q0 + 1; p < q1; ++p) {
             const uint32_t en = spl[p];
-            const double *src = scr + (en & 3) * 9 * NT + (en >> 2);
-            if (p == q0) {
-#pragma unroll
-                for (int q = 0; q < 9; ++q) acc[q] = src[q * NT];
-            } else {
-#pragma unroll
-                for (int q = 0; q < 9; ++q) acc[q] = acc[q] + src[q * NT];
-            }
-            if ((int)(p - q0) < nf) {   // mass: faces only, t8/12 on the diagonal block, t8/24 otherwise
-                const double t8 = scr[30 * NT + (en >> 2)];
-                const double mi = diag ? t8 / 12.0 : t8 / 24.0;
-                m = p == q0 ? mi : m + mi;
-            }
+            const double *src = scr + ITEM_STRIDE * (en >> 2) + 10 * (en & 3);
+            const double2 *s2 = reinterpret_cast<const double2 *>(src);
+            double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3_ = s2[3];
+            double v8 = src[8];
+            a0 = a0 + v0.x; a1 = a1 + v0.y; a2 = a2 + v1.x; a3 = a3 + v1.y; a4 = a4 + v2.x; a5 = a5 + v2.y;
+            a6 = a6 + v3_.x; a7 = a7 + v3_.y; a8 = a8 + v8;
         }
         const int a = node0 + (int)ln;
         const int64_t b0 = blkptrK[a];
         const int deg = (int)(blkptrK[a + 1] - b0);
-        const int pcol = (int)(g - b0);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            double *row = Kv + 9 * b0 + (int64_t)j * 3 * deg + 3 * pcol;
-            __stcs(row, acc[3 * j]); __stcs(row + 1, acc[3 * j + 1]); __stcs(row + 2, acc[3 * j + 2]);
+        const int pcol = (int)(ob0 + ob - b0);
+        {
+            double *row = Kv + 9 * b0 + 3 * pcol;
+            __stcs(row, a0); __stcs(row + 1, a1); __stcs(row + 2, a2);
+            row += 3 * deg;
+            __stcs(row, a3); __stcs(row + 1, a4); __stcs(row + 2, a5);
+            row += 3 * deg;
+            __stcs(row, a6); __stcs(row + 1, a7); __stcs(row + 2, a8);
         }
-        if (mslot != 255) {
+        const int mslot = meta >> 8;
+        if (mslot != 255) {   // mass: the block's face contributions only (they lead the list), t8/12 on the diagonal block
+            const int nf = meta & 127, moff = (meta & 128) ? 33 : 34;
+            double m = scr[ITEM_STRIDE * (spl[q0] >> 2) + moff];
+            for (int r = 1; r < nf; ++r) m = m + scr[ITEM_STRIDE * (spl[q0 + r] >> 2) + moff];
             const int64_t m0 = blkptrM[a];
             const int degM = (int)(blkptrM[a + 1] - m0);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                double *row = Mv + 9 * m0 + (int64_t)j * 3 * degM + 3 * mslot;
-                __stcs(row, j == 0 ? m : 0.0); __stcs(row + 1, j == 1 ? m : 0.0); __stcs(row + 2, j == 2 ? m : 0.0);
-            }
+            double *row = Mv + 9 * m0 + 3 * mslot;
+            __stcs(row, m); __stcs(row + 1, 0.0); __stcs(row + 2, 0.0);
+            row += 3 * degM;
+            __stcs(row, 0.0); __stcs(row + 1, m); __stcs(row + 2, 0.0);
+            row += 3 * degM;
+            __stcs(row, 0.0); __stcs(row + 1, 0.0); __stcs(row + 2, m);
         }
     }
     // ---- f: per node, its face items in ascending face order (f.setZero() then +=, Forces.cpp:915,500-502)
     if (t < node1 - node0) {
         const int first = nfm & 255, cnt = nfm >> 8;
         double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-        for (int k = 0; k < cnt; ++k) { f0 += scr[27 * NT + first + k]; f1 += scr[28 * NT + first + k]; f2 += scr[29 * NT + first + k]; }
+        for (int k = 0; k < cnt; ++k) {
+            const double *src = scr + ITEM_STRIDE * (first + k) + 30;
+            f0 += src[0]; f1 += src[1]; f2 += src[2];
+        }
         double *dst = f + 3 * (size_t)(node0 + t);
         dst[0] = f0; dst[1] = f1; dst[2] = f2;
     }
@@ -349,35 +367,37 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
         for (int32_t i = 0; i < F; ++i) for (int v = 0; v < 3; ++v) nfl[pf[fn[3 * (size_t)i + v]]++] = ((uint32_t)i << 3) | (v << 1);
         for (int32_t i = 0; i < Ei; ++i) for (int v = 0; v < 4; ++v) nel[pe[ie[4 * (size_t)i + v]]++] = ((uint32_t)i << 3) | (v << 1) | 1u;
     }
-    // CTA partition: consecutive nodes, at most NT items and 128 nodes per CTA
-    std::vector<int32_t> cta_node0, cta_item0;
-    cta_node0.push_back(0); cta_item0.push_back(0);
+    // CTA partition: consecutive nodes while the face items fit warp 0 and the edge items fit warps 1-2
+    std::vector<int32_t> cta_node0;
+    cta_node0.push_back(0);
     {
-        int64_t items = 0; int cur = 0, nodes = 0;
+        int cf = 0, ce = 0, nodes = 0;
         for (int32_t a = 0; a < N; ++a) {
-            int na = (nfp[a + 1] - nfp[a]) + (nep[a + 1] - nep[a]);
-            if (na > NT || (nfp[a + 1] - nfp[a]) > 127) { set_error("node %d has %d incident elements (limit %d)", a, na, NT); return EOLC_ERR_UNSUPPORTED; }
-            if (cur + na > NT || nodes == 128) { cta_node0.push_back(a); cta_item0.push_back((int32_t)items); cur = 0; nodes = 0; }
-            cur += na; items += na; ++nodes;
+            const int nf = nfp[a + 1] - nfp[a], ne = nep[a + 1] - nep[a];
+            if (nf > FACE_SLOTS || ne > EDGE_SLOTS) {
+                set_error("node %d has %d faces / %d bending stencils (limits %d / %d)", a, nf, ne, FACE_SLOTS, EDGE_SLOTS);
+                return EOLC_ERR_UNSUPPORTED;
+            }
+            if (cf + nf > FACE_SLOTS || ce + ne > EDGE_SLOTS || nodes == NT) { cta_node0.push_back(a); cf = ce = nodes = 0; }
+            cf += nf; ce += ne; ++nodes;
         }
-        if (items >= ((int64_t)1 << 31)) { set_error("too many (node, element) items"); return EOLC_ERR_UNSUPPORTED; }
-        cta_node0.push_back(N); cta_item0.push_back((int32_t)items);
+        cta_node0.push_back(N);
     }
     const int32_t nc = (int32_t)cta_node0.size() - 1;
     P->n_cta = nc;
-    std::vector<uint32_t> items((size_t)cta_item0[nc]);
+    std::vector<uint32_t> items((size_t)nc * NT, NO_ITEM);
     std::vector<uint32_t> pl_ptr((size_t)P->nblkK + 1, 0);
     std::vector<uint16_t> pl;
     pl.reserve(9 * (size_t)F + 16 * (size_t)Ei);
-    std::vector<uint16_t> meta((size_t)P->nblkK, 0), node_f(N, 0);
+    std::vector<uint16_t> meta((size_t)P->nblkK, 0), order((size_t)P->nblkK, 0), node_f(N, 0);
     std::vector<uint8_t> lnode((size_t)P->nblkK, 0);
     std::vector<std::vector<uint16_t>> tmp;   // per block of the current node
+    std::vector<std::pair<int, int>> cnt_ob;  // (-count, local block) of the current CTA
     for (int32_t c = 0; c < nc; ++c) {
         const int32_t n0 = cta_node0[c], n1 = cta_node0[c + 1];
-        // item order inside the CTA: all face items (node order, face ascending), then all edge items
-        int32_t nface_items = 0;
-        for (int32_t a = n0; a < n1; ++a) nface_items += nfp[a + 1] - nfp[a];
-        int32_t fpos = 0, epos = nface_items;
+        int32_t fpos = 0, epos = FACE_SLOTS;
+        cnt_ob.clear();
+        const int64_t cb0 = P->h_blkptrK[n0];
         for (int32_t a = n0; a < n1; ++a) {
             const int64_t b0 = P->h_blkptrK[a], b1 = P->h_blkptrK[a + 1];
             const int deg = (int)(b1 - b0);
@@ -387,7 +407,7 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
             node_f[a] = (uint16_t)(fpos | ((nfp[a + 1] - nfp[a]) << 8));
             for (int32_t k = nfp[a]; k < nfp[a + 1]; ++k) {      // faces ascending
                 const uint32_t it = nfl[k];
-                items[(size_t)cta_item0[c] + fpos] = it;
+                items[(size_t)c * NT + fpos] = it;
                 const int32_t face = it >> 3;
                 for (int j = 0; j < 3; ++j) {
                     int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, fn[3 * (size_t)face + j]) - b0);
@@ -398,7 +418,7 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
             }
             for (int32_t k = nep[a]; k < nep[a + 1]; ++k) {      // then interior edges ascending
                 const uint32_t it = nel[k];
-                items[(size_t)cta_item0[c] + epos] = it;
+                items[(size_t)c * NT + epos] = it;
                 const int32_t ed = it >> 3;
                 for (int j = 0; j < 4; ++j) {
                     int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, ie[4 * (size_t)ed + j]) - b0);
@@ -414,14 +434,18 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
                 if (nfaces[p] > 0) mslot = (int)(find_block(P->h_blkptrM, P->h_nbrM, a, b) - P->h_blkptrM[a]);
                 meta[b0 + p] = (uint16_t)(nfaces[p] | (a == b ? 128 : 0) | (mslot << 8));
                 lnode[b0 + p] = (uint8_t)(a - n0);
+                cnt_ob.push_back({-(int)tmp[p].size(), (int)(b0 + p - cb0)});
             }
         }
+        std::sort(cnt_ob.begin(), cnt_ob.end());   // descending count, ties by block index: deterministic
+        for (size_t k = 0; k < cnt_ob.size(); ++k) order[cb0 + k] = (uint16_t)cnt_ob[k].second;
     }
     if (pl.size() >= ((size_t)1 << 32)) { set_error("pull list too long"); return EOLC_ERR_UNSUPPORTED; }
     pl_ptr[P->nblkK] = (uint32_t)pl.size();
-    EOLC_CUDA(P->d_cta_node0.upload(cta_node0, st)); EOLC_CUDA(P->d_cta_item0.upload(cta_item0, st));
+    EOLC_CUDA(P->d_cta_node0.upload(cta_node0, st));
     EOLC_CUDA(P->d_items.upload(items, st)); EOLC_CUDA(P->d_pl_ptr.upload(pl_ptr, st)); EOLC_CUDA(P->d_pl.upload(pl, st));
-    EOLC_CUDA(P->d_blk_meta.upload(meta, st)); EOLC_CUDA(P->d_blk_lnode.upload(lnode, st)); EOLC_CUDA(P->d_node_f.upload(node_f, st));
+    EOLC_CUDA(P->d_blk_meta.upload(meta, st)); EOLC_CUDA(P->d_blk_lnode.upload(lnode, st)); EOLC_CUDA(P->d_blk_order.upload(order, st));
+    EOLC_CUDA(P->d_node_f.upload(node_f, st));
     EOLC_CUDA(P->d_blkptrM.upload(P->h_blkptrM, st)); EOLC_CUDA(P->d_blkptrK.upload(P->h_blkptrK, st));
     EOLC_CUDA(cudaStreamSynchronize(st));
     return EOLC_OK;
@@ -573,9 +597,10 @@ int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X
         for (int32_t s0 = 0; s0 < S; s0 += 65535) {
             const int32_t sc = std::min<int32_t>(65535, S - s0);
             assemble_rows_kernel<<<dim3(P->n_cta, sc), NT, 0, st>>>(
-                P->d_cta_node0.p, P->d_cta_item0.p, P->d_items.p, P->d_face_nodes.p, P->d_iedge.p, P->d_blkptrK.p, P->d_blkptrM.p,
-                P->d_pl_ptr.p, P->d_pl.p, P->d_blk_meta.p, P->d_blk_lnode.p, P->d_node_f.p, x + (size_t)s0 * 3 * P->N,
-                X + (size_t)s0 * 2 * P->N, mat->e, mat->nu, mat->density, mat->beta, grav[0], grav[1], grav[2], dhh,
+                P->d_cta_node0.p, P->d_items.p, P->d_face_nodes.p, P->d_iedge.p, P->d_blkptrK.p, P->d_blkptrM.p,
+                P->d_pl_ptr.p, P->d_pl.p, P->d_blk_meta.p, P->d_blk_lnode.p, P->d_blk_order.p, P->d_node_f.p,
+                x + (size_t)s0 * 3 * P->N, X + (size_t)s0 * 2 * P->N, membrane_mu(mat->e, mat->nu), membrane_lambda(mat->e, mat->nu),
+                mat->density, mat->beta, grav[0], grav[1], grav[2], dhh,
                 f + (size_t)s0 * P->dof, Mv + (size_t)s0 * P->nnzM, Kv + (size_t)s0 * P->nnzK, (size_t)3 * P->N, (size_t)2 * P->N,
                 (size_t)P->dof, (size_t)P->nnzM, (size_t)P->nnzK);
         }

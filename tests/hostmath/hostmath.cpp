@@ -26,9 +26,9 @@ void hostmath_face_row(int v, const double *xa, const double *xb, const double *
                        double *f3, double *t8, double *K3x9) {
     FaceRowOut o;
     face_row(v, mk3(xa[0], xa[1], xa[2]), mk3(xb[0], xb[1], xb[2]), mk3(xc[0], xc[1], xc[2]), Xa[0], Xa[1], Xb[0], Xb[1],
-             Xc[0], Xc[1], e, nu, rho, mk3(g[0], g[1], g[2]), dhh, o);
+             Xc[0], Xc[1], membrane_mu(e, nu), membrane_lambda(e, nu), rho, mk3(g[0], g[1], g[2]), dhh, o);
     for (int i = 0; i < 3; ++i) f3[i] = o.f[i];
-    *t8 = o.t8;
+    *t8 = o.md * 12.0;
     for (int b = 0; b < 3; ++b) for (int k = 0; k < 9; ++k) K3x9[9 * b + k] = o.K[b].m[k];
 }
 void hostmath_edge_row(int i, const double *x0, const double *x1, const double *x2, const double *x3, const double *X0,

@@ -94,7 +94,7 @@ def test_row_forms(oracle, hostmath):
             rows.append(R)
             worstF = max(worstF, np.abs(R - ref[3 * v:3 * v + 3]).max() / np.abs(ref).max())
             worstf = max(worstf, np.abs(f3 - (fm + fi)[3 * v:3 * v + 3]).max() / max(np.abs(fm).max(), np.abs(fi).max()))
-            assert t8[0] / 12 == Mi[0, 0]
+            assert abs(t8[0] / 12 - Mi[0, 0]) <= 1e-15 * abs(Mi[0, 0])
         full = np.vstack(rows)
         assert np.array_equal(full, full.T)          # face rows are exact transposes of each other
     assert worstE < 1e-12 and worstF < 1e-12 and worstf < 1e-11, (worstE, worstF, worstf)
