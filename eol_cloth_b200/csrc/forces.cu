@@ -43,13 +43,12 @@ struct eolc_forces_plan {
     // "rows" pipeline
     int pipeline = 0;                             // 0 = rows, 1 = scratch
     int32_t n_cta = 0;
-    DevBuf<int32_t> d_cta_node0;                  // n_cta + 1
-    DevBuf<uint32_t> d_items;                     // NT slots per CTA: elem << 3 | pos << 1 | is_edge, NO_ITEM = empty
-    DevBuf<uint32_t> d_pl_ptr;                    // per MDK block (+1): offset into d_pl
+    bool smem_attr_set = false;
+    DevBuf<uint4> d_cta_hdr;                      // 2 x uint4 per CTA (CtaHeader)
+    DevBuf<unsigned long long> d_slot;            // per CTA slot (aligned with the block index): packed SlotRec
+    DevBuf<uint32_t> d_items;                     // NT slots per CTA: pack_item(local ids, pos), 0 = empty
+    DevBuf<int32_t> d_tile_nodes;                 // TILE_NODES slots per CTA: the tile's distinct global node ids
     DevBuf<uint16_t> d_pl;                        // item_local << 2 | column block j
-    DevBuf<uint16_t> d_blk_meta;                  // nf (bits 0-6) | diag (bit 7) | mslot (bits 8-15, 255 = not in M)
-    DevBuf<uint16_t> d_blk_order;                 // per CTA: its blocks by descending contribution count
-    DevBuf<uint8_t> d_blk_lnode;                  // owning node - cta_node0
     DevBuf<uint16_t> d_node_f;                    // first face item (CTA-local) | count << 8
     // scratch (per scene chunk)
     DevBuf<double> d_face_scr, d_edge_scr;
@@ -217,9 +216,8 @@ constexpr int NT = FACE_SLOTS + EDGE_SLOTS;        // threads per CTA; kinds are
 constexpr int ITEM_STRIDE = 42;                    // doubles parked per item: block j at 10*j (16 B aligned, 9 used);
                                                    // faces: f at 30..32, t8/12 at 33, t8/24 at 34.  Stride 42 makes the
                                                    // quarter-warp STS.128 pattern bank-conflict free (84 words = 20 mod 32).
-constexpr uint32_t NO_ITEM = 0xFFFFFFFFu;
 #ifndef ROWS_MIN_CTAS
-#define ROWS_MIN_CTAS 5
+#define ROWS_MIN_CTAS 4
 #endif
 
 __device__ __forceinline__ void park_block(double *dst, const blk3 &B) {
@@ -229,124 +227,219 @@ __device__ __forceinline__ void park_block(double *dst, const blk3 &B) {
     dst[8] = B.m[8];
 }
 
-__global__ void __launch_bounds__(NT, ROWS_MIN_CTAS) assemble_rows_kernel(
-    const int32_t *__restrict__ cta_node0, const uint32_t *__restrict__ items, const int32_t *__restrict__ fn,
-    const int32_t *__restrict__ ie, const int64_t *__restrict__ blkptrK, const int64_t *__restrict__ blkptrM,
-    const uint32_t *__restrict__ pl_ptr, const uint16_t *__restrict__ pl, const uint16_t *__restrict__ blk_meta,
-    const uint8_t *__restrict__ blk_lnode, const uint16_t *__restrict__ blk_order, const uint16_t *__restrict__ node_f,
-    const double *__restrict__ x, const double *__restrict__ X, double mu, double lam, double rho, double beta, double gx,
-    double gy, double gz, double dhh, double *__restrict__ f, double *__restrict__ Mv, double *__restrict__ Kv,
-    size_t x_stride, size_t X_stride, size_t f_stride, size_t M_stride, size_t K_stride) {
-    __shared__ __align__(16) double scr[ITEM_STRIDE * NT];
-    __shared__ uint16_t spl[3 * FACE_SLOTS + 4 * EDGE_SLOTS];   // the CTA's pull entries
-    const int c = blockIdx.x, t = threadIdx.x, s = blockIdx.y;
-    x += s * x_stride; X += s * X_stride; f += s * f_stride; Mv += s * M_stride; Kv += s * K_stride;
-    const int node0 = cta_node0[c], node1 = cta_node0[c + 1];
-    const int64_t ob0 = blkptrK[node0];
-    const int nbc = (int)(blkptrK[node1] - ob0);
+// One 32-byte header per CTA: everything later loads depend on, fetched with two 128-bit loads.
+struct CtaHeader {
+    int32_t node0, nnodes;       // the CTA's run of consecutive nodes
+    uint32_t plbase;             // first pull entry in d_pl
+    uint16_t npl, nbc;           // pull entries / output blocks of the CTA
+    long long kbase, mbase;      // offsets (in doubles) of the CTA's first MDK / M block row
+};
+static_assert(sizeof(CtaHeader) == 32, "CtaHeader must be 32 bytes");
+// One 64-bit record per output block, in the order threads take them (descending contribution count):
+//  q0:9 first pull entry | cnt:7 entries | nf:6 leading face entries | diag:1 | koff:11 | deg:8 | hasm:1 | moff:11 | degM:8
+// koff/moff: offset of the block's first row from kbase/mbase in units of 3 doubles; rows are 3*deg (3*degM) apart.
+__host__ __device__ inline unsigned long long pack_slot(unsigned q0, unsigned cnt, unsigned nf, unsigned diag, unsigned koff,
+                                                        unsigned deg, unsigned hasm, unsigned moff, unsigned degM) {
+    return (unsigned long long)q0 | ((unsigned long long)cnt << 9) | ((unsigned long long)nf << 16) | ((unsigned long long)diag << 22) |
+           ((unsigned long long)koff << 23) | ((unsigned long long)deg << 34) | ((unsigned long long)hasm << 42) |
+           ((unsigned long long)moff << 43) | ((unsigned long long)degM << 54);
+}
 
-    // ---- prefetch everything phase 2 needs, so its global latency hides under phase 1's arithmetic
-    const uint32_t it = items[(size_t)c * NT + t];
-    const uint32_t plbase = pl_ptr[ob0];
-    uint32_t q0 = 0, q1 = 0, meta = 0, ln = 0, ob = 0;
-    if (t < nbc) {
-        ob = blk_order[ob0 + t];
-        q0 = pl_ptr[ob0 + ob] - plbase; q1 = pl_ptr[ob0 + ob + 1] - plbase; meta = blk_meta[ob0 + ob]; ln = blk_lnode[ob0 + ob];
-    }
-    uint32_t nfm = 0;
-    if (t < node1 - node0) nfm = node_f[node0 + t];
-    {
-        const int npl = (int)(pl_ptr[ob0 + nbc] - plbase);
-        for (int k = t; k < npl; k += NT) spl[k] = pl[plbase + k];
+// Persistent, warp-specialised: warps 0-2 (NT threads) compute and assemble; warp 3 is a loader that stages the inputs
+// of the tiles AHEAD (ring of RING stages) in shared memory, so the FP64 pipe never waits on HBM/L2 latency.
+// A tile's inputs are its (<= TILE_NODES) distinct nodes: the loader reads the tile's node table, then x / X of those
+// nodes once (two dependent global latencies); items address them with 6-bit tile-local ids.
+//   loader :  for each tile: wait EMPTY[s] -> fetch -> arrive FULL[s]
+//   compute:  wait FULL[s] -> phase 1 (rows -> scr) -> bar(compute) -> phase 2 (pull + store) -> arrive EMPTY[s] -> bar(compute)
+constexpr int NTHREADS = NT + 32;
+constexpr int TILE_NODES = 64;
+constexpr int RING = 4;
+// item word: local ids n0..n3 (6 bits each, bits 0-23) | pos (bits 24-25) | valid (bit 26)
+__host__ __device__ inline uint32_t pack_item(int n0, int n1, int n2, int n3, int pos) {
+    return (uint32_t)n0 | ((uint32_t)n1 << 6) | ((uint32_t)n2 << 12) | ((uint32_t)n3 << 18) | ((uint32_t)pos << 24) | (1u << 26);
+}
+
+struct TileStage {
+    CtaHeader hdr;
+    double x[TILE_NODES * 3];
+    double X[TILE_NODES * 2];
+    uint32_t item[NT];
+    uint16_t pl[3 * FACE_SLOTS + 4 * EDGE_SLOTS];
+    uint16_t nf[NT];
+};
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+constexpr int BAR_COMPUTE = 1, BAR_FULL0 = 2, BAR_EMPTY0 = 2 + RING;
+
+__device__ __forceinline__ void loader_fetch(int lane, long long tile, int n_cta, const uint4 *__restrict__ cta_hdr,
+                                             const uint32_t *__restrict__ items, const int32_t *__restrict__ tile_nodes,
+                                             const uint16_t *__restrict__ pl, const uint16_t *__restrict__ node_f,
+                                             const double *__restrict__ x, const double *__restrict__ X, size_t x_stride,
+                                             size_t X_stride, TileStage *__restrict__ S) {
+    const int c = (int)(tile % n_cta);
+    const size_t sc = (size_t)(tile / n_cta);
+    x += sc * x_stride; X += sc * X_stride;
+    // level 1: header, node table, items (all independent)
+    const uint4 h0 = cta_hdr[2 * (size_t)c], h1 = cta_hdr[2 * (size_t)c + 1];
+    const int ntab = (int)(h0.y >> 8) & 255;
+    int g0 = -1, g1 = -1;
+    if (lane < ntab) g0 = tile_nodes[(size_t)c * TILE_NODES + lane];
+    if (lane + 32 < ntab) g1 = tile_nodes[(size_t)c * TILE_NODES + 32 + lane];
+    uint32_t it[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) it[k] = items[(size_t)c * NT + lane + 32 * k];
+    CtaHeader H;
+    H.node0 = (int)h0.x; H.nnodes = (int)(h0.y & 255); H.plbase = h0.z; H.npl = (uint16_t)(h0.w & 0xffff); H.nbc = (uint16_t)(h0.w >> 16);
+    H.kbase = (long long)(((unsigned long long)h1.y << 32) | h1.x); H.mbase = (long long)(((unsigned long long)h1.w << 32) | h1.z);
+    // level 2: positions of the tile's distinct nodes; pull entries and per-node face ranges ride along
+    double xa[3] = {0, 0, 0}, xb[3] = {0, 0, 0};
+    double2 Xa = make_double2(0, 0), Xb = make_double2(0, 0);
+    if (g0 >= 0) { const double *p = x + 3 * (size_t)g0; xa[0] = p[0]; xa[1] = p[1]; xa[2] = p[2]; Xa = *reinterpret_cast<const double2 *>(X + 2 * (size_t)g0); }
+    if (g1 >= 0) { const double *p = x + 3 * (size_t)g1; xb[0] = p[0]; xb[1] = p[1]; xb[2] = p[2]; Xb = *reinterpret_cast<const double2 *>(X + 2 * (size_t)g1); }
+    // pull entries: each tile's segment is padded to 16 bytes by the plan -> two 128-bit loads per lane, issued together
+    const uint4 *plsrc = reinterpret_cast<const uint4 *>(pl + H.plbase);
+    const int nchunk = (H.npl + 7) >> 3;
+    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+    if (lane < nchunk) c0 = plsrc[lane];
+    if (lane + 32 < nchunk) c1 = plsrc[lane + 32];
+    uint16_t nf0 = 0, nf1 = 0, nf2 = 0;
+    if (lane < H.nnodes) nf0 = node_f[H.node0 + lane];
+    if (lane + 32 < H.nnodes) nf1 = node_f[H.node0 + lane + 32];
+    if (lane + 64 < H.nnodes) nf2 = node_f[H.node0 + lane + 64];
+    if (lane == 0) S->hdr = H;
+    reinterpret_cast<uint4 *>(S->pl)[lane] = c0;
+    if (lane + 32 < (3 * FACE_SLOTS + 4 * EDGE_SLOTS) / 8) reinterpret_cast<uint4 *>(S->pl)[lane + 32] = c1;
+    S->nf[lane] = nf0; S->nf[lane + 32] = nf1; S->nf[lane + 64] = nf2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) S->item[lane + 32 * k] = it[k];
+    S->x[3 * lane] = xa[0]; S->x[3 * lane + 1] = xa[1]; S->x[3 * lane + 2] = xa[2];
+    S->x[3 * (lane + 32)] = xb[0]; S->x[3 * (lane + 32) + 1] = xb[1]; S->x[3 * (lane + 32) + 2] = xb[2];
+    reinterpret_cast<double2 *>(S->X)[lane] = Xa; reinterpret_cast<double2 *>(S->X)[lane + 32] = Xb;
+}
+
+__global__ void __launch_bounds__(NTHREADS, ROWS_MIN_CTAS) assemble_rows_kernel(
+    long long n_tiles, int n_cta, const uint4 *__restrict__ cta_hdr, const uint32_t *__restrict__ items,
+    const int32_t *__restrict__ tile_nodes, const unsigned long long *__restrict__ slot, const uint16_t *__restrict__ pl,
+    const uint16_t *__restrict__ node_f, const double *__restrict__ x, const double *__restrict__ X, double mu, double lam,
+    double rho, double beta, double gx, double gy, double gz, double dhh, double *__restrict__ f, double *__restrict__ Mv,
+    double *__restrict__ Kv, size_t x_stride, size_t X_stride, size_t f_stride, size_t M_stride, size_t K_stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];      // > 48 KB: dynamic shared memory
+    double *scr = reinterpret_cast<double *>(smem_raw);
+    TileStage *ring = reinterpret_cast<TileStage *>(scr + ITEM_STRIDE * NT);
+    const int t = threadIdx.x;
+
+    if (t >= NT) {
+        // ================= loader warp =================
+        const int lane = t - NT;
+        int s = 0;
+        long long k = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            if (k >= RING) bar_sync(BAR_EMPTY0 + s, NTHREADS);          // consumers released this stage
+            loader_fetch(lane, tile, n_cta, cta_hdr, items, tile_nodes, pl, node_f, x, X, x_stride, X_stride, &ring[s]);
+            __threadfence_block();
+            bar_arrive(BAR_FULL0 + s, NTHREADS);
+            s = s + 1 == RING ? 0 : s + 1;
+        }
+        return;
     }
 
-    // ---- phase 1: one (node, element) block row per thread -> shared memory
-    if (it != NO_ITEM) {
-        const int el = it >> 3, pos = (it >> 1) & 3;
-        double *dst = scr + ITEM_STRIDE * t;
-        if (t >= FACE_SLOTS) {
-            const int4 st = *reinterpret_cast<const int4 *>(ie + 4 * (size_t)el);
-            const double *p0 = x + 3 * (size_t)st.x, *p1 = x + 3 * (size_t)st.y, *p2 = x + 3 * (size_t)st.z, *p3 = x + 3 * (size_t)st.w;
-            const double2 A0 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.x), A1 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.y);
-            const double2 A2 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.z), A3 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)st.w);
-            edge_row_emit(pos, mk3(p0[0], p0[1], p0[2]), mk3(p1[0], p1[1], p1[2]), mk3(p2[0], p2[1], p2[2]), mk3(p3[0], p3[1], p3[2]),
-                          A0.x, A0.y, A1.x, A1.y, A2.x, A2.y, A3.x, A3.y, beta, dhh,
-                          [dst](int j, const blk3 &B) { park_block(dst + 10 * j, B); });
-        } else {
-            const int a = fn[3 * (size_t)el], b = fn[3 * (size_t)el + 1], cc = fn[3 * (size_t)el + 2];
-            const double *p0 = x + 3 * (size_t)a, *p1 = x + 3 * (size_t)b, *p2 = x + 3 * (size_t)cc;
-            const double2 A0 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)a), A1 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)b);
-            const double2 A2 = *reinterpret_cast<const double2 *>(X + 2 * (size_t)cc);
-            FaceRowOut o;
-            face_row(pos, mk3(p0[0], p0[1], p0[2]), mk3(p1[0], p1[1], p1[2]), mk3(p2[0], p2[1], p2[2]), A0.x, A0.y, A1.x, A1.y,
-                     A2.x, A2.y, mu, lam, rho, mk3(gx, gy, gz), dhh, o);
-            park_block(dst, o.K[0]); park_block(dst + 10, o.K[1]); park_block(dst + 20, o.K[2]);
-            dst[30] = o.f[0]; dst[31] = o.f[1]; dst[32] = o.f[2]; dst[33] = o.md; dst[34] = o.mo;
+    // ================= compute warps =================
+    int s = 0;
+    long long kt = 0;
+    long long my_tiles = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++my_tiles;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++kt) {
+        bar_sync(BAR_FULL0 + s, NTHREADS);                              // stage s holds this tile
+        const TileStage &St = ring[s];
+        const CtaHeader H = St.hdr;
+        const uint32_t it = St.item[t];
+        const long long sbase = H.kbase / 9;
+        unsigned long long rec = 0;
+        if (t < H.nbc) rec = slot[sbase + t];                           // latency hides under phase 1
+        const size_t sc = (size_t)(tile / n_cta);
+        double *fs = f + sc * f_stride, *Ms = Mv + sc * M_stride, *Ks = Kv + sc * K_stride;
+        // ---- phase 1: one (node, element) block row per thread -> shared memory
+        if (it & (1u << 26)) {
+            const int pos = (it >> 24) & 3;
+            const double *q0 = St.x + 3 * (it & 63), *q1 = St.x + 3 * ((it >> 6) & 63), *q2 = St.x + 3 * ((it >> 12) & 63);
+            const double *Q0 = St.X + 2 * (it & 63), *Q1 = St.X + 2 * ((it >> 6) & 63), *Q2 = St.X + 2 * ((it >> 12) & 63);
+            double *dst = scr + ITEM_STRIDE * t;
+            if (t >= FACE_SLOTS) {
+                const double *q3 = St.x + 3 * ((it >> 18) & 63), *Q3 = St.X + 2 * ((it >> 18) & 63);
+                edge_row_emit(pos, mk3(q0[0], q0[1], q0[2]), mk3(q1[0], q1[1], q1[2]), mk3(q2[0], q2[1], q2[2]), mk3(q3[0], q3[1], q3[2]),
+                              Q0[0], Q0[1], Q1[0], Q1[1], Q2[0], Q2[1], Q3[0], Q3[1], beta, dhh,
+                              [dst](int j, const blk3 &B) { park_block(dst + 10 * j, B); });
+            } else {
+                FaceRowOut o;
+                face_row(pos, mk3(q0[0], q0[1], q0[2]), mk3(q1[0], q1[1], q1[2]), mk3(q2[0], q2[1], q2[2]), Q0[0], Q0[1], Q1[0], Q1[1],
+                         Q2[0], Q2[1], mu, lam, rho, mk3(gx, gy, gz), dhh, o);
+                park_block(dst, o.K[0]); park_block(dst + 10, o.K[1]); park_block(dst + 20, o.K[2]);
+                dst[30] = o.f[0]; dst[31] = o.f[1]; dst[32] = o.f[2]; dst[33] = o.md; dst[34] = o.mo;
+            }
         }
-    }
-    __syncthreads();
-
-    // ---- phase 2: every output block of the CTA's rows pulls its contributions in reference order.
-    // blk_order hands the blocks out by descending contribution count, so the lanes of a warp run similar trip counts.
-    for (int k = t; k < nbc; k += NT) {
-        if (k != t) {
-            ob = blk_order[ob0 + k];
-            q0 = pl_ptr[ob0 + ob] - plbase; q1 = pl_ptr[ob0 + ob + 1] - plbase; meta = blk_meta[ob0 + ob]; ln = blk_lnode[ob0 + ob];
+        bar_sync(BAR_COMPUTE, NT);
+        // ---- phase 2: every output block of the tile's rows pulls its contributions in reference order.
+        // Slots are handed out by descending contribution count, so the lanes of a warp run similar trip counts.
+        const uint16_t *spl = St.pl;
+        for (int k = t; k < H.nbc; k += NT) {
+            if (k != t) rec = slot[sbase + k];
+            const uint32_t q0 = (uint32_t)(rec & 511), cnt = (uint32_t)(rec >> 9) & 127;
+            double a0, a1, a2, a3, a4, a5, a6, a7, a8;
+            {
+                const uint32_t en = spl[q0];
+                const double *src = scr + ITEM_STRIDE * (en >> 2) + 10 * (en & 3);
+                const double2 *s2 = reinterpret_cast<const double2 *>(src);
+                double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3_ = s2[3];
+                a0 = v0.x; a1 = v0.y; a2 = v1.x; a3 = v1.y; a4 = v2.x; a5 = v2.y; a6 = v3_.x; a7 = v3_.y; a8 = src[8];
+            }
+            for (uint32_t p = q0 + 1; p < q0 + cnt; ++p) {
+                const uint32_t en = spl[p];
+                const double *src = scr + ITEM_STRIDE * (en >> 2) + 10 * (en & 3);
+                const double2 *s2 = reinterpret_cast<const double2 *>(src);
+                double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3_ = s2[3];
+                double v8 = src[8];
+                a0 = a0 + v0.x; a1 = a1 + v0.y; a2 = a2 + v1.x; a3 = a3 + v1.y; a4 = a4 + v2.x; a5 = a5 + v2.y;
+                a6 = a6 + v3_.x; a7 = a7 + v3_.y; a8 = a8 + v8;
+            }
+            {
+                const uint32_t koff = (uint32_t)(rec >> 23) & 2047, deg = (uint32_t)(rec >> 34) & 255;
+                double *row = Ks + H.kbase + 3 * (size_t)koff;
+                __stcs(row, a0); __stcs(row + 1, a1); __stcs(row + 2, a2);
+                row += 3 * deg;
+                __stcs(row, a3); __stcs(row + 1, a4); __stcs(row + 2, a5);
+                row += 3 * deg;
+                __stcs(row, a6); __stcs(row + 1, a7); __stcs(row + 2, a8);
+            }
+            if ((rec >> 42) & 1) {   // mass: the block's face contributions only (they lead the list); t8/12 on the diagonal
+                const int nf = (int)(rec >> 16) & 63, mo_ = ((rec >> 22) & 1) ? 33 : 34;
+                double m = scr[ITEM_STRIDE * (spl[q0] >> 2) + mo_];
+                for (int r = 1; r < nf; ++r) m = m + scr[ITEM_STRIDE * (spl[q0 + r] >> 2) + mo_];
+                const uint32_t moff = (uint32_t)(rec >> 43) & 2047, degM = (uint32_t)(rec >> 54) & 255;
+                double *row = Ms + H.mbase + 3 * (size_t)moff;
+                __stcs(row, m); __stcs(row + 1, 0.0); __stcs(row + 2, 0.0);
+                row += 3 * degM;
+                __stcs(row, 0.0); __stcs(row + 1, m); __stcs(row + 2, 0.0);
+                row += 3 * degM;
+                __stcs(row, 0.0); __stcs(row + 1, 0.0); __stcs(row + 2, m);
+            }
         }
-        double a0, a1, a2, a3, a4, a5, a6, a7, a8;
-        {
-            const uint32_t en = spl[q0];
-            const double *src = scr + ITEM_STRIDE * (en >> 2) + 10 * (en & 3);
-            const double2 *s2 = reinterpret_cast<const double2 *>(src);
-            double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3_ = s2[3];
-            a0 = v0.x; a1 = v0.y; a2 = v1.x; a3 = v1.y; a4 = v2.x; a5 = v2.y; a6 = v3_.x; a7 = v3_.y; a8 = src[8];
+        // ---- f: per node, its face items in ascending face order (f.setZero() then +=, Forces.cpp:915,500-502)
+        if (t < H.nnodes) {
+            const uint32_t nfm = St.nf[t];
+            const int first = nfm & 255, cnt = nfm >> 8;
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+            for (int k = 0; k < cnt; ++k) {
+                const double *src = scr + ITEM_STRIDE * (first + k) + 30;
+                f0 += src[0]; f1 += src[1]; f2 += src[2];
+            }
+            double *dst = fs + 3 * (size_t)(H.node0 + t);
+            dst[0] = f0; dst[1] = f1; dst[2] = f2;
         }
-        for (uint32_t p = q0 + 1; p < q1; ++p) {
-            const uint32_t en = spl[p];
-            const double *src = scr + ITEM_STRIDE * (en >> 2) + 10 * (en & 3);
-            const double2 *s2 = reinterpret_cast<const double2 *>(src);
-            double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3_ = s2[3];
-            double v8 = src[8];
-            a0 = a0 + v0.x; a1 = a1 + v0.y; a2 = a2 + v1.x; a3 = a3 + v1.y; a4 = a4 + v2.x; a5 = a5 + v2.y;
-            a6 = a6 + v3_.x; a7 = a7 + v3_.y; a8 = a8 + v8;
-        }
-        const int a = node0 + (int)ln;
-        const int64_t b0 = blkptrK[a];
-        const int deg = (int)(blkptrK[a + 1] - b0);
-        const int pcol = (int)(ob0 + ob - b0);
-        {
-            double *row = Kv + 9 * b0 + 3 * pcol;
-            __stcs(row, a0); __stcs(row + 1, a1); __stcs(row + 2, a2);
-            row += 3 * deg;
-            __stcs(row, a3); __stcs(row + 1, a4); __stcs(row + 2, a5);
-            row += 3 * deg;
-            __stcs(row, a6); __stcs(row + 1, a7); __stcs(row + 2, a8);
-        }
-        const int mslot = meta >> 8;
-        if (mslot != 255) {   // mass: the block's face contributions only (they lead the list), t8/12 on the diagonal block
-            const int nf = meta & 127, moff = (meta & 128) ? 33 : 34;
-            double m = scr[ITEM_STRIDE * (spl[q0] >> 2) + moff];
-            for (int r = 1; r < nf; ++r) m = m + scr[ITEM_STRIDE * (spl[q0 + r] >> 2) + moff];
-            const int64_t m0 = blkptrM[a];
-            const int degM = (int)(blkptrM[a + 1] - m0);
-            double *row = Mv + 9 * m0 + 3 * mslot;
-            __stcs(row, m); __stcs(row + 1, 0.0); __stcs(row + 2, 0.0);
-            row += 3 * degM;
-            __stcs(row, 0.0); __stcs(row + 1, m); __stcs(row + 2, 0.0);
-            row += 3 * degM;
-            __stcs(row, 0.0); __stcs(row + 1, 0.0); __stcs(row + 2, m);
-        }
-    }
-    // ---- f: per node, its face items in ascending face order (f.setZero() then +=, Forces.cpp:915,500-502)
-    if (t < node1 - node0) {
-        const int first = nfm & 255, cnt = nfm >> 8;
-        double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-        for (int k = 0; k < cnt; ++k) {
-            const double *src = scr + ITEM_STRIDE * (first + k) + 30;
-            f0 += src[0]; f1 += src[1]; f2 += src[2];
-        }
-        double *dst = f + 3 * (size_t)(node0 + t);
-        dst[0] = f0; dst[1] = f1; dst[2] = f2;
+        // release the stage to the loader only if it will be refilled (keeps arrive/sync counts matched)
+        if (kt + RING < my_tiles) bar_arrive(BAR_EMPTY0 + s, NTHREADS);
+        bar_sync(BAR_COMPUTE, NT);                                      // scr is free for the next tile
+        s = s + 1 == RING ? 0 : s + 1;
     }
 }
 
@@ -361,43 +454,73 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
     for (int64_t i = 0; i < 3 * (int64_t)F; ++i) nfp[fn[i] + 1]++;
     for (int64_t i = 0; i < 4 * (int64_t)Ei; ++i) nep[ie[i] + 1]++;
     for (int32_t a = 0; a < N; ++a) { nfp[a + 1] += nfp[a]; nep[a + 1] += nep[a]; }
-    std::vector<uint32_t> nfl(nfp[N]), nel(nep[N]);
+    std::vector<uint32_t> nfl(nfp[N]), nel(nep[N]);   // elem << 2 | pos
     {
         std::vector<int32_t> pf(nfp.begin(), nfp.end() - 1), pe(nep.begin(), nep.end() - 1);
-        for (int32_t i = 0; i < F; ++i) for (int v = 0; v < 3; ++v) nfl[pf[fn[3 * (size_t)i + v]]++] = ((uint32_t)i << 3) | (v << 1);
-        for (int32_t i = 0; i < Ei; ++i) for (int v = 0; v < 4; ++v) nel[pe[ie[4 * (size_t)i + v]]++] = ((uint32_t)i << 3) | (v << 1) | 1u;
+        for (int32_t i = 0; i < F; ++i) for (int v = 0; v < 3; ++v) nfl[pf[fn[3 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
+        for (int32_t i = 0; i < Ei; ++i) for (int v = 0; v < 4; ++v) nel[pe[ie[4 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
     }
-    // CTA partition: consecutive nodes while the face items fit warp 0 and the edge items fit warps 1-2
+    // ---- tiles: runs of consecutive nodes whose face items fit warp 0, edge items fit warps 1-2 and whose elements touch
+    // at most TILE_NODES distinct nodes
     std::vector<int32_t> cta_node0;
-    cta_node0.push_back(0);
+    std::vector<int32_t> stamp(N, -1);          // stamp[g] == tile -> g is in the tile's node table
     {
-        int cf = 0, ce = 0, nodes = 0;
+        int cf = 0, ce = 0, nodes = 0, ndist = 0, tile = 0;
+        std::vector<int32_t> fresh;
+        cta_node0.push_back(0);
         for (int32_t a = 0; a < N; ++a) {
             const int nf = nfp[a + 1] - nfp[a], ne = nep[a + 1] - nep[a];
-            if (nf > FACE_SLOTS || ne > EDGE_SLOTS) {
-                set_error("node %d has %d faces / %d bending stencils (limits %d / %d)", a, nf, ne, FACE_SLOTS, EDGE_SLOTS);
-                return EOLC_ERR_UNSUPPORTED;
+            auto collect = [&]() {
+                fresh.clear();
+                auto touch = [&](int32_t g) { if (stamp[g] != tile) { stamp[g] = tile; fresh.push_back(g); } };
+                touch(a);
+                for (int32_t k = nfp[a]; k < nfp[a + 1]; ++k) for (int j = 0; j < 3; ++j) touch(fn[3 * (size_t)(nfl[k] >> 2) + j]);
+                for (int32_t k = nep[a]; k < nep[a + 1]; ++k) for (int j = 0; j < 4; ++j) touch(ie[4 * (size_t)(nel[k] >> 2) + j]);
+            };
+            collect();
+            if (cf + nf > FACE_SLOTS || ce + ne > EDGE_SLOTS || nodes == NT || ndist + (int)fresh.size() > TILE_NODES) {
+                if (nodes == 0) {
+                    set_error("node %d: %d faces / %d bending stencils / %d stencil nodes exceed the tile limits (%d / %d / %d)", a, nf, ne,
+                              (int)fresh.size(), FACE_SLOTS, EDGE_SLOTS, TILE_NODES);
+                    return EOLC_ERR_UNSUPPORTED;
+                }
+                cta_node0.push_back(a);
+                ++tile; cf = ce = nodes = ndist = 0;
+                collect();
+                if (nf > FACE_SLOTS || ne > EDGE_SLOTS || (int)fresh.size() > TILE_NODES) {
+                    set_error("node %d: %d faces / %d bending stencils / %d stencil nodes exceed the tile limits (%d / %d / %d)", a, nf, ne,
+                              (int)fresh.size(), FACE_SLOTS, EDGE_SLOTS, TILE_NODES);
+                    return EOLC_ERR_UNSUPPORTED;
+                }
             }
-            if (cf + nf > FACE_SLOTS || ce + ne > EDGE_SLOTS || nodes == NT) { cta_node0.push_back(a); cf = ce = nodes = 0; }
-            cf += nf; ce += ne; ++nodes;
+            cf += nf; ce += ne; ++nodes; ndist += (int)fresh.size();
         }
         cta_node0.push_back(N);
     }
-    const int32_t nc = (int32_t)cta_node0.size() - 1;
+    const int32_t nc = N > 0 ? (int32_t)cta_node0.size() - 1 : 0;
     P->n_cta = nc;
-    std::vector<uint32_t> items((size_t)nc * NT, NO_ITEM);
-    std::vector<uint32_t> pl_ptr((size_t)P->nblkK + 1, 0);
+    std::vector<uint32_t> items((size_t)nc * NT, 0u);
+    std::vector<int32_t> tile_nodes((size_t)nc * TILE_NODES, 0);
     std::vector<uint16_t> pl;
     pl.reserve(9 * (size_t)F + 16 * (size_t)Ei);
-    std::vector<uint16_t> meta((size_t)P->nblkK, 0), order((size_t)P->nblkK, 0), node_f(N, 0);
-    std::vector<uint8_t> lnode((size_t)P->nblkK, 0);
+    std::vector<uint16_t> node_f(N, 0);
+    std::vector<unsigned long long> slots((size_t)P->nblkK, 0);
+    std::vector<CtaHeader> hdr((size_t)nc);
     std::vector<std::vector<uint16_t>> tmp;   // per block of the current node
-    std::vector<std::pair<int, int>> cnt_ob;  // (-count, local block) of the current CTA
+    struct SlotTmp { int cnt; unsigned long long rec; };
+    std::vector<SlotTmp> cslots;              // slot records of the current tile
+    std::vector<int32_t> local(N, -1);        // global -> tile-local id, valid while lstamp[g] == c
+    std::vector<int32_t> lstamp(N, -1);
     for (int32_t c = 0; c < nc; ++c) {
         const int32_t n0 = cta_node0[c], n1 = cta_node0[c + 1];
-        int32_t fpos = 0, epos = FACE_SLOTS;
-        cnt_ob.clear();
-        const int64_t cb0 = P->h_blkptrK[n0];
+        int32_t fpos = 0, epos = FACE_SLOTS, ntab = 0;
+        auto lid = [&](int32_t g) {
+            if (lstamp[g] != c) { lstamp[g] = c; local[g] = ntab; tile_nodes[(size_t)c * TILE_NODES + ntab] = g; ++ntab; }
+            return local[g];
+        };
+        cslots.clear();
+        const int64_t cb0 = P->h_blkptrK[n0], cm0 = P->h_blkptrM[n0];
+        const size_t plbase = pl.size();
         for (int32_t a = n0; a < n1; ++a) {
             const int64_t b0 = P->h_blkptrK[a], b1 = P->h_blkptrK[a + 1];
             const int deg = (int)(b1 - b0);
@@ -406,47 +529,63 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
             std::vector<int> nfaces(deg, 0);
             node_f[a] = (uint16_t)(fpos | ((nfp[a + 1] - nfp[a]) << 8));
             for (int32_t k = nfp[a]; k < nfp[a + 1]; ++k) {      // faces ascending
-                const uint32_t it = nfl[k];
-                items[(size_t)c * NT + fpos] = it;
-                const int32_t face = it >> 3;
+                const int32_t face = nfl[k] >> 2;
+                const int32_t *v = fn + 3 * (size_t)face;
+                items[(size_t)c * NT + fpos] = pack_item(lid(v[0]), lid(v[1]), lid(v[2]), 0, nfl[k] & 3);
                 for (int j = 0; j < 3; ++j) {
-                    int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, fn[3 * (size_t)face + j]) - b0);
+                    int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, v[j]) - b0);
                     tmp[p].push_back((uint16_t)((fpos << 2) | j));
                     nfaces[p]++;
                 }
                 ++fpos;
             }
             for (int32_t k = nep[a]; k < nep[a + 1]; ++k) {      // then interior edges ascending
-                const uint32_t it = nel[k];
-                items[(size_t)c * NT + epos] = it;
-                const int32_t ed = it >> 3;
+                const int32_t ed = nel[k] >> 2;
+                const int32_t *v = ie + 4 * (size_t)ed;
+                items[(size_t)c * NT + epos] = pack_item(lid(v[0]), lid(v[1]), lid(v[2]), lid(v[3]), nel[k] & 3);
                 for (int j = 0; j < 4; ++j) {
-                    int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, ie[4 * (size_t)ed + j]) - b0);
+                    int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, v[j]) - b0);
                     tmp[p].push_back((uint16_t)((epos << 2) | j));
                 }
                 ++epos;
             }
+            const int64_t m0 = P->h_blkptrM[a];
+            const int degM = (int)(P->h_blkptrM[a + 1] - m0);
             for (int p = 0; p < deg; ++p) {
                 const int32_t b = P->h_nbrK[b0 + p];
-                pl_ptr[b0 + p] = (uint32_t)pl.size();
+                const unsigned q0 = (unsigned)(pl.size() - plbase);
                 pl.insert(pl.end(), tmp[p].begin(), tmp[p].end());
-                int mslot = 255;
-                if (nfaces[p] > 0) mslot = (int)(find_block(P->h_blkptrM, P->h_nbrM, a, b) - P->h_blkptrM[a]);
-                meta[b0 + p] = (uint16_t)(nfaces[p] | (a == b ? 128 : 0) | (mslot << 8));
-                lnode[b0 + p] = (uint8_t)(a - n0);
-                cnt_ob.push_back({-(int)tmp[p].size(), (int)(b0 + p - cb0)});
+                unsigned hasm = 0, moff = 0;
+                if (nfaces[p] > 0) { hasm = 1; moff = (unsigned)(3 * (m0 - cm0) + (find_block(P->h_blkptrM, P->h_nbrM, a, b) - m0)); }
+                const unsigned koff = (unsigned)(3 * (b0 - cb0) + p);
+                if (q0 > 511 || tmp[p].size() > 127 || nfaces[p] > 63 || koff > 2047 || moff > 2047 || degM > 255) {
+                    set_error("internal: slot record overflow at node %d", a);
+                    return EOLC_ERR_UNSUPPORTED;
+                }
+                cslots.push_back({(int)tmp[p].size(), pack_slot(q0, (unsigned)tmp[p].size(), (unsigned)nfaces[p], a == b ? 1u : 0u, koff,
+                                                                (unsigned)deg, hasm, moff, hasm ? (unsigned)degM : 0u)});
             }
         }
-        std::sort(cnt_ob.begin(), cnt_ob.end());   // descending count, ties by block index: deterministic
-        for (size_t k = 0; k < cnt_ob.size(); ++k) order[cb0 + k] = (uint16_t)cnt_ob[k].second;
+        if (ntab > TILE_NODES) { set_error("internal: tile node table overflow"); return EOLC_ERR_UNSUPPORTED; }
+        const uint16_t npl_true = (uint16_t)(pl.size() - plbase);
+        while ((pl.size() - plbase) % 8) pl.push_back(0);   // 16-byte granules for the loader's 128-bit copies
+        // descending contribution count, ties keep block order: deterministic
+        std::stable_sort(cslots.begin(), cslots.end(), [](const SlotTmp &u, const SlotTmp &v) { return u.cnt > v.cnt; });
+        for (size_t k = 0; k < cslots.size(); ++k) slots[cb0 + k] = cslots[k].rec;
+        CtaHeader &H = hdr[c];
+        H.node0 = n0; H.nnodes = (n1 - n0) | (ntab << 8); H.plbase = (uint32_t)plbase; H.npl = npl_true;
+        H.nbc = (uint16_t)cslots.size(); H.kbase = 9 * cb0; H.mbase = 9 * cm0;
+        if (pl.size() >= ((size_t)1 << 32)) { set_error("pull list too long"); return EOLC_ERR_UNSUPPORTED; }
     }
-    if (pl.size() >= ((size_t)1 << 32)) { set_error("pull list too long"); return EOLC_ERR_UNSUPPORTED; }
-    pl_ptr[P->nblkK] = (uint32_t)pl.size();
-    EOLC_CUDA(P->d_cta_node0.upload(cta_node0, st));
-    EOLC_CUDA(P->d_items.upload(items, st)); EOLC_CUDA(P->d_pl_ptr.upload(pl_ptr, st)); EOLC_CUDA(P->d_pl.upload(pl, st));
-    EOLC_CUDA(P->d_blk_meta.upload(meta, st)); EOLC_CUDA(P->d_blk_lnode.upload(lnode, st)); EOLC_CUDA(P->d_blk_order.upload(order, st));
+    {
+        std::vector<uint4> hraw(2 * (size_t)nc);
+        static_assert(sizeof(CtaHeader) == 2 * sizeof(uint4), "header layout");
+        if (nc) memcpy(hraw.data(), hdr.data(), sizeof(CtaHeader) * (size_t)nc);
+        EOLC_CUDA(P->d_cta_hdr.upload(hraw, st));
+    }
+    EOLC_CUDA(P->d_items.upload(items, st)); EOLC_CUDA(P->d_tile_nodes.upload(tile_nodes, st)); EOLC_CUDA(P->d_pl.upload(pl, st));
+    EOLC_CUDA(P->d_slot.upload(slots, st));
     EOLC_CUDA(P->d_node_f.upload(node_f, st));
-    EOLC_CUDA(P->d_blkptrM.upload(P->h_blkptrM, st)); EOLC_CUDA(P->d_blkptrK.upload(P->h_blkptrK, st));
     EOLC_CUDA(cudaStreamSynchronize(st));
     return EOLC_OK;
 }
@@ -594,15 +733,18 @@ int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X
     const double dhh = mat->dampingB * h * h;   // damping(1)*h*h, Forces.cpp:105
     if (P->pipeline == 0) {
         if (P->N == 0) return EOLC_OK;
-        for (int32_t s0 = 0; s0 < S; s0 += 65535) {
-            const int32_t sc = std::min<int32_t>(65535, S - s0);
-            assemble_rows_kernel<<<dim3(P->n_cta, sc), NT, 0, st>>>(
-                P->d_cta_node0.p, P->d_items.p, P->d_face_nodes.p, P->d_iedge.p, P->d_blkptrK.p, P->d_blkptrM.p,
-                P->d_pl_ptr.p, P->d_pl.p, P->d_blk_meta.p, P->d_blk_lnode.p, P->d_blk_order.p, P->d_node_f.p,
-                x + (size_t)s0 * 3 * P->N, X + (size_t)s0 * 2 * P->N, membrane_mu(mat->e, mat->nu), membrane_lambda(mat->e, mat->nu),
-                mat->density, mat->beta, grav[0], grav[1], grav[2], dhh,
-                f + (size_t)s0 * P->dof, Mv + (size_t)s0 * P->nnzM, Kv + (size_t)s0 * P->nnzK, (size_t)3 * P->N, (size_t)2 * P->N,
-                (size_t)P->dof, (size_t)P->nnzM, (size_t)P->nnzK);
+        {
+            const long long n_tiles = (long long)P->n_cta * S;
+            const int grid = (int)std::min<long long>(n_tiles, (long long)P->ctx->sm_count * ROWS_MIN_CTAS);
+            const size_t smem = sizeof(double) * ITEM_STRIDE * NT + RING * sizeof(TileStage);
+            if (!P->smem_attr_set) {   // per device; plans are per ctx/device
+                EOLC_CUDA(cudaFuncSetAttribute(assemble_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                P->smem_attr_set = true;
+            }
+            assemble_rows_kernel<<<grid, NTHREADS, smem, st>>>(
+                n_tiles, P->n_cta, P->d_cta_hdr.p, P->d_items.p, P->d_tile_nodes.p, P->d_slot.p, P->d_pl.p, P->d_node_f.p, x, X,
+                membrane_mu(mat->e, mat->nu), membrane_lambda(mat->e, mat->nu), mat->density, mat->beta, grav[0], grav[1], grav[2],
+                dhh, f, Mv, Kv, (size_t)3 * P->N, (size_t)2 * P->N, (size_t)P->dof, (size_t)P->nnzM, (size_t)P->nnzK);
         }
         EOLC_CUDA(cudaGetLastError());
         return EOLC_OK;
