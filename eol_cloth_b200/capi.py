@@ -23,7 +23,8 @@ class MaterialC(ctypes.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libeolc_b200.so")
+    # EOLC_LIB: developer knob to A/B an alternative build of the same library (scripts/gpu_variants.sh)
+    return os.environ.get("EOLC_LIB") or os.path.join(_HERE, "libeolc_b200.so")
 
 
 def lib():

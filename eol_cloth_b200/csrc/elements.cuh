@@ -267,6 +267,237 @@ EOLC_HD void edge_element(v3 x0, v3 x1, v3 x2, v3 x3, double X0x, double X0y, do
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tile forms ("tiles" pipeline): each element is evaluated ONCE per tile and parked in shared memory in a compact layout
+// (symmetric diagonal blocks as 6 doubles, off-diagonal blocks as 8 + 1 doubles, 16-byte aligned).
+//
+//  bending, reduced coordinates.  D depends on x only through e = x1-x0, a = x2-x0, b = x3-x0 (translation invariance),
+//  n0 = e x a, n1 = b x e.  With H00, H01, H11 the blocks of the Hessian of D with respect to (n0, n1)
+//       H00 = -1/|n0|^2 (q u^T + u q^T + D (I - u u^T)),  q = v - D u         (symmetric)
+//       H11 = -1/|n1|^2 (r v^T + v r^T + D (I - v v^T)),  r = u - D v         (symmetric)
+//       H01 =  1/(|n0||n1|) (I - u u^T - v v^T + D u v^T)
+//  and dn0 = -[a]x de + [e]x da, dn1 = [b]x de - [e]x db, d2n0 = 2 de x da, d2n1 = 2 db x de, g0 = q/|n0|, g1 = r/|n1|:
+//       H_aa = -[e]x H00 [e]x      H_ab = [e]x H01 [e]x      H_bb = -[e]x H11 [e]x
+//       H_ea =  [a]x H00 [e]x - [b]x H01^T [e]x - [g0]x      H_eb = -[a]x H01 [e]x + [b]x H11 [e]x + [g1]x
+//       H_ee = -[a]x H00 [a]x + S + S^T - [b]x H11 [b]x,     S = [a]x H01 [b]x
+//  K_11 = H_ee, K_12 = H_ea, K_13 = H_eb, K_22 = H_aa, K_23 = H_ab, K_33 = H_bb and, because every row of K sums to zero,
+//       K_0j = -(K_1j + K_2j + K_3j),  K_00 = -(K_01 + K_02 + K_03).
+//  About 560 FP64 instructions instead of ~1000 for the outer-product form above; verified against the reference's
+//  generated ComputeBending to < 1e-12 of the block scale (tests/test_element_math.py).
+// ------------------------------------------------------------------------------------------------
+struct sym3 { double xx, xy, xz, yy, yz, zz; };
+// rows of M [w]x : M_r x w
+EOLC_HD void mul_skew_r(const blk3 &M, v3 w, blk3 &R) {
+    v3 r0 = cross(mk3(M.m[0], M.m[1], M.m[2]), w), r1 = cross(mk3(M.m[3], M.m[4], M.m[5]), w), r2 = cross(mk3(M.m[6], M.m[7], M.m[8]), w);
+    R.m[0] = r0.x; R.m[1] = r0.y; R.m[2] = r0.z; R.m[3] = r1.x; R.m[4] = r1.y; R.m[5] = r1.z; R.m[6] = r2.x; R.m[7] = r2.y; R.m[8] = r2.z;
+}
+EOLC_HD void sym_mul_skew_r(const sym3 &S, v3 w, blk3 &R) {
+    v3 r0 = cross(mk3(S.xx, S.xy, S.xz), w), r1 = cross(mk3(S.xy, S.yy, S.yz), w), r2 = cross(mk3(S.xz, S.yz, S.zz), w);
+    R.m[0] = r0.x; R.m[1] = r0.y; R.m[2] = r0.z; R.m[3] = r1.x; R.m[4] = r1.y; R.m[5] = r1.z; R.m[6] = r2.x; R.m[7] = r2.y; R.m[8] = r2.z;
+}
+// B (+)= s * [w]x M   (columns: w x M_col), written so that every term contracts into one FMA
+template <bool ACC>
+EOLC_HD void skew_l(blk3 &B, double s, v3 w, const blk3 &M) {
+    const v3 sw = s * w;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double cx = M.m[c], cy = M.m[3 + c], cz = M.m[6 + c];
+        double rx = ACC ? B.m[c] : 0.0, ry = ACC ? B.m[3 + c] : 0.0, rz = ACC ? B.m[6 + c] : 0.0;
+        if (ACC) { rx += sw.y * cz; ry += sw.z * cx; rz += sw.x * cy; } else { rx = sw.y * cz; ry = sw.z * cx; rz = sw.x * cy; }
+        rx -= sw.z * cy; ry -= sw.x * cz; rz -= sw.y * cx;
+        B.m[c] = rx; B.m[3 + c] = ry; B.m[6 + c] = rz;
+    }
+}
+EOLC_HD void add_skew_l(blk3 &B, double s, v3 w, const blk3 &M) { skew_l<true>(B, s, w, M); }
+EOLC_HD void set_skew_l(blk3 &B, double s, v3 w, const blk3 &M) { skew_l<false>(B, s, w, M); }
+// upper triangle of S (+)= s * [w]x M, for products known to be symmetric
+template <bool ACC>
+EOLC_HD void skew_l_sym(sym3 &S, double s, v3 w, const blk3 &M) {
+    const v3 sw = s * w;
+    if (ACC) {
+        S.xx += sw.y * M.m[6]; S.xy += sw.y * M.m[7]; S.xz += sw.y * M.m[8]; S.yy += sw.z * M.m[1]; S.yz += sw.z * M.m[2]; S.zz += sw.x * M.m[5];
+    } else {
+        S.xx = sw.y * M.m[6]; S.xy = sw.y * M.m[7]; S.xz = sw.y * M.m[8]; S.yy = sw.z * M.m[1]; S.yz = sw.z * M.m[2]; S.zz = sw.x * M.m[5];
+    }
+    S.xx -= sw.z * M.m[3]; S.xy -= sw.z * M.m[4]; S.xz -= sw.z * M.m[5]; S.yy -= sw.x * M.m[7]; S.yz -= sw.x * M.m[8]; S.zz -= sw.y * M.m[2];
+}
+EOLC_HD void add_skew_l_sym(sym3 &S, double s, v3 w, const blk3 &M) { skew_l_sym<true>(S, s, w, M); }
+EOLC_HD void set_skew_l_sym(sym3 &S, double s, v3 w, const blk3 &M) { skew_l_sym<false>(S, s, w, M); }
+
+// emit.diag(i, sym3) for K_ii (i = 0..3), emit.off(k, blk3) for k = 0..5: K_01, K_02, K_03, K_12, K_13, K_23.
+// All blocks are already multiplied by dhh = dampingB h^2 (Forces.cpp:885-906).
+template <typename Emit>
+EOLC_HD void edge_element_tile(v3 x0, v3 x1, v3 x2, v3 x3, double X0x, double X0y, double X1x, double X1y, double X2x, double X2y,
+                               double X3x, double X3y, double beta, double dhh, Emit &emit) {
+    // c = 3/2 t6 t17 (ComputeBending.cpp:50-53,102);  K dhh = kk Hess(D), kk = -c dhh
+    const double ex = X1x - X0x, ey = X1y - X0y;
+    const double t6 = beta * (ex * ex + ey * ey);
+    const double den = 0.5 * (-X0x * X2y + X2x * X0y + X1x * X2y - X2x * X1y + X0x * X3y - X3x * X0y - X1x * X3y + X3x * X1y);
+    const double kk = -(1.5 * t6 / den) * dhh;
+    const v3 e = x1 - x0, a = x2 - x0, b = x3 - x0;
+    const v3 n0 = cross(e, a), n1 = cross(b, e);
+    const double il0 = rsq(dot(n0, n0)), il1 = rsq(dot(n1, n1));
+    const v3 u = il0 * n0, v = il1 * n1;
+    const double D = dot(u, v);
+    const v3 q = v - D * u, r = u - D * v;
+    const double c0 = -kk * il0 * il0, c1 = -kk * il1 * il1, c01 = kk * il0 * il1;
+    sym3 H00, H11;
+    {
+        const v3 cu = c0 * u, cDu = (c0 * D) * u;
+        H00.xx = 2.0 * (cu.x * q.x) - cDu.x * u.x + c0 * D; H00.xy = cu.x * q.y + cu.y * q.x - cDu.x * u.y;
+        H00.xz = cu.x * q.z + cu.z * q.x - cDu.x * u.z;     H00.yy = 2.0 * (cu.y * q.y) - cDu.y * u.y + c0 * D;
+        H00.yz = cu.y * q.z + cu.z * q.y - cDu.y * u.z;     H00.zz = 2.0 * (cu.z * q.z) - cDu.z * u.z + c0 * D;
+        const v3 cv = c1 * v, cDv = (c1 * D) * v;
+        H11.xx = 2.0 * (cv.x * r.x) - cDv.x * v.x + c1 * D; H11.xy = cv.x * r.y + cv.y * r.x - cDv.x * v.y;
+        H11.xz = cv.x * r.z + cv.z * r.x - cDv.x * v.z;     H11.yy = 2.0 * (cv.y * r.y) - cDv.y * v.y + c1 * D;
+        H11.yz = cv.y * r.z + cv.z * r.y - cDv.y * v.z;     H11.zz = 2.0 * (cv.z * r.z) - cDv.z * v.z + c1 * D;
+    }
+    blk3 H01;   // c01 (I - u u^T - v v^T + D u v^T) = c01 (I - v v^T) - (c01 u) r^T
+    {
+        const v3 cu = c01 * u, cv = c01 * v;
+        H01.m[0] = c01 - cv.x * v.x - cu.x * r.x; H01.m[1] = -cv.x * v.y - cu.x * r.y; H01.m[2] = -cv.x * v.z - cu.x * r.z;
+        H01.m[3] = -cv.y * v.x - cu.y * r.x; H01.m[4] = c01 - cv.y * v.y - cu.y * r.y; H01.m[5] = -cv.y * v.z - cu.y * r.z;
+        H01.m[6] = -cv.z * v.x - cu.z * r.x; H01.m[7] = -cv.z * v.y - cu.z * r.y; H01.m[8] = c01 - cv.z * v.z - cu.z * r.z;
+    }
+    const v3 g0 = (kk * il0) * q, g1 = (kk * il1) * r;
+    blk3 T, Hea, Heb, K02, K03;
+    sym3 S, K00;
+    // ---- H00: H_aa, first part of H_ea, first part of H_ee
+    sym_mul_skew_r(H00, e, T);                                    // P0 = H00 [e]x
+    set_skew_l_sym(S, -1.0, e, T);                                // H_aa = -[e]x P0
+    emit.diag(2, S);
+    set_skew_l(Hea, 1.0, a, T);                                   // [a]x P0
+    K02.m[0] = S.xx; K02.m[1] = S.xy; K02.m[2] = S.xz; K02.m[3] = S.xy; K02.m[4] = S.yy; K02.m[5] = S.yz; K02.m[6] = S.xz; K02.m[7] = S.yz; K02.m[8] = S.zz;
+    sym3 Hee;
+    sym_mul_skew_r(H00, a, T);                                    // R0 = H00 [a]x
+    set_skew_l_sym(Hee, -1.0, a, T);
+    // ---- H01^T: rest of H_ea
+    {
+        blk3 H10;
+        H10.m[0] = H01.m[0]; H10.m[1] = H01.m[3]; H10.m[2] = H01.m[6]; H10.m[3] = H01.m[1]; H10.m[4] = H01.m[4]; H10.m[5] = H01.m[7];
+        H10.m[6] = H01.m[2]; H10.m[7] = H01.m[5]; H10.m[8] = H01.m[8];
+        mul_skew_r(H10, e, T);                                    // P1 = H10 [e]x
+    }
+    add_skew_l(Hea, -1.0, b, T);
+    add_skew(Hea, -1.0, g0);
+    emit.off(3, Hea);                                             // K_12
+    for (int k = 0; k < 9; ++k) K02.m[k] += Hea.m[k];
+    // ---- H01: H_ab, first part of H_eb, cross part of H_ee
+    mul_skew_r(H01, e, T);                                        // Q0 = H01 [e]x
+    blk3 Hab;
+    set_skew_l(Hab, 1.0, e, T);                                   // H_ab = [e]x Q0
+    emit.off(5, Hab);                                             // K_23
+    set_skew_l(Heb, -1.0, a, T);
+    // K_02 = -(K_12 + K_22 + K_32) = -(H_ea + H_aa + H_ab^T)
+    K02.m[0] = -K02.m[0] - Hab.m[0]; K02.m[1] = -K02.m[1] - Hab.m[3]; K02.m[2] = -K02.m[2] - Hab.m[6]; K02.m[3] = -K02.m[3] - Hab.m[1];
+    K02.m[4] = -K02.m[4] - Hab.m[4]; K02.m[5] = -K02.m[5] - Hab.m[7]; K02.m[6] = -K02.m[6] - Hab.m[2]; K02.m[7] = -K02.m[7] - Hab.m[5];
+    K02.m[8] = -K02.m[8] - Hab.m[8];
+    emit.off(1, K02);
+    K00.xx = -K02.m[0]; K00.xy = -K02.m[1]; K00.xz = -K02.m[2]; K00.yy = -K02.m[4]; K00.yz = -K02.m[5]; K00.zz = -K02.m[8];
+    for (int k = 0; k < 9; ++k) K03.m[k] = Hab.m[k];
+    {
+        blk3 Sx;
+        mul_skew_r(H01, b, T);                                    // R1 = H01 [b]x
+        set_skew_l(Sx, 1.0, a, T);                                // S = [a]x R1 ; H_ee += S + S^T
+        Hee.xx += 2.0 * Sx.m[0]; Hee.xy += Sx.m[1] + Sx.m[3]; Hee.xz += Sx.m[2] + Sx.m[6];
+        Hee.yy += 2.0 * Sx.m[4]; Hee.yz += Sx.m[5] + Sx.m[7]; Hee.zz += 2.0 * Sx.m[8];
+    }
+    // ---- H11: H_bb, rest of H_eb, rest of H_ee
+    sym_mul_skew_r(H11, e, T);                                    // Q1 = H11 [e]x
+    set_skew_l_sym(S, -1.0, e, T);                                // H_bb = -[e]x Q1
+    emit.diag(3, S);
+    add_skew_l(Heb, 1.0, b, T);
+    add_skew(Heb, 1.0, g1);
+    emit.off(4, Heb);                                             // K_13
+    // K_03 = -(K_13 + K_23 + K_33) = -(H_eb + H_ab + H_bb)
+    K03.m[0] += S.xx; K03.m[1] += S.xy; K03.m[2] += S.xz; K03.m[3] += S.xy; K03.m[4] += S.yy; K03.m[5] += S.yz; K03.m[6] += S.xz; K03.m[7] += S.yz; K03.m[8] += S.zz;
+    for (int k = 0; k < 9; ++k) K03.m[k] = -K03.m[k] - Heb.m[k];
+    emit.off(2, K03);
+    K00.xx -= K03.m[0]; K00.xy -= K03.m[1]; K00.xz -= K03.m[2]; K00.yy -= K03.m[4]; K00.yz -= K03.m[5]; K00.zz -= K03.m[8];
+    sym_mul_skew_r(H11, b, T);                                    // R2 = H11 [b]x
+    add_skew_l_sym(Hee, -1.0, b, T);
+    emit.diag(1, Hee);                                            // K_11
+    // K_01 = -(K_11 + K_21 + K_31) = -(H_ee + H_ea^T + H_eb^T)
+    blk3 K01;
+    K01.m[0] = -(Hee.xx + Hea.m[0] + Heb.m[0]); K01.m[1] = -(Hee.xy + Hea.m[3] + Heb.m[3]); K01.m[2] = -(Hee.xz + Hea.m[6] + Heb.m[6]);
+    K01.m[3] = -(Hee.xy + Hea.m[1] + Heb.m[1]); K01.m[4] = -(Hee.yy + Hea.m[4] + Heb.m[4]); K01.m[5] = -(Hee.yz + Hea.m[7] + Heb.m[7]);
+    K01.m[6] = -(Hee.xz + Hea.m[2] + Heb.m[2]); K01.m[7] = -(Hee.yz + Hea.m[5] + Heb.m[5]); K01.m[8] = -(Hee.zz + Hea.m[8] + Heb.m[8]);
+    emit.off(0, K01);
+    // K_00 = -(K_01 + K_02 + K_03): the sum is symmetric, only its upper triangle is formed
+    K00.xx -= K01.m[0]; K00.xy -= K01.m[1]; K00.xz -= K01.m[2]; K00.yy -= K01.m[4]; K00.yz -= K01.m[5]; K00.zz -= K01.m[8];
+    emit.diag(0, K00);
+}
+
+// One triangle for the tiles pipeline: emit.diag(i, sym3) i = 0..2 (K_aa, K_bb, K_cc incl. the mass diagonal),
+// emit.off(k, blk3) k = 0..2 (K_ab, K_ac, K_bc), emit.force(i, v3) = fm + fi of vertex i, emit.mass(t8).
+template <typename Emit>
+EOLC_HD void face_element_tile(v3 xa, v3 xb, v3 xc, double Xax, double Xay, double Xbx, double Xby, double Xcx, double Xcy, double mu,
+                               double lam, double rho, v3 g, double dhh, Emit &emit) {
+    const v3 d1 = xb - xa, d2 = xc - xa;
+    const v3 nrm = cross(d1, d2);
+    const v3 Px = rsq(dot(d1, d1)) * d1;
+    v3 Py = cross(nrm, Px);
+    Py = rsq(dot(Py, Py)) * Py;
+    const double t7 = Xax * Xby - Xax * Xcy - Xbx * Xay + Xcx * Xay + Xbx * Xcy - Xcx * Xby;
+    const double t17 = 1.0 / t7;
+    const double gb0 = t17 * (Xcy - Xay), gb1 = t17 * (Xax - Xcx);
+    const double gc0 = t17 * (Xay - Xby), gc1 = t17 * (Xbx - Xax);
+    const double ga0 = -gb0 - gc0, ga1 = -gb1 - gc1;
+    const v3 F0 = gb0 * d1 + gc0 * d2, F1 = gb1 * d1 + gc1 * d2;
+    const double m11 = dot(Px, F0), m21 = dot(Py, F0), m12 = dot(Px, F1), m22 = dot(Py, F1);
+    const double detM = m11 * m22 - m12 * m21;
+    const double sg = detM < 0.0 ? -1.0 : (detM == 0.0 ? 0.0 : 1.0);
+    double q00 = m11 + sg * m22, q01 = m12 - sg * m21, q10 = m21 - sg * m12, q11 = m22 + sg * m11;
+    const double icl = rsq(q00 * q00 + q10 * q10);
+    q00 *= icl; q01 *= icl; q10 *= icl; q11 *= icl;
+    const v3 r0 = q00 * Px + q10 * Py, r1 = q01 * Px + q11 * Py;
+    const double E00 = dot(r0, F0) - 1.0, E10 = dot(r1, F0), E01 = dot(r0, F1), E11 = dot(r1, F1) - 1.0;
+    const double A = 0.5 * t7;
+    const double tr = E00 + E11;
+    const double S00 = 2.0 * mu * E00 + lam * tr, S01 = 2.0 * mu * E01, S10 = 2.0 * mu * E10, S11 = 2.0 * mu * E11 + lam * tr;
+    const double t8 = rho * t7;
+    {
+        const v3 fg = (t8 * (1.0 / 6.0)) * g;
+        const v3 s0 = (-A) * r0, s1 = (-A) * r1;
+        emit.force(0, (S00 * ga0 + S01 * ga1) * s0 + (S10 * ga0 + S11 * ga1) * s1 + fg);
+        emit.force(1, (S00 * gb0 + S01 * gb1) * s0 + (S10 * gb0 + S11 * gb1) * s1 + fg);
+        emit.force(2, (S00 * gc0 + S01 * gc1) * s0 + (S10 * gc0 + S11 * gc1) * s1 + fg);
+    }
+    emit.mass(t8);
+    const double a2mu = dhh * A * 2.0 * mu, alam = dhh * A * lam;
+    const double RR0 = a2mu * (r0.x * r0.x + r1.x * r1.x), RR1 = a2mu * (r0.x * r0.y + r1.x * r1.y), RR2 = a2mu * (r0.x * r0.z + r1.x * r1.z),
+                 RR3 = a2mu * (r0.y * r0.y + r1.y * r1.y), RR4 = a2mu * (r0.y * r0.z + r1.y * r1.z), RR5 = a2mu * (r0.z * r0.z + r1.z * r1.z);
+    const v3 qa = ga0 * r0 + ga1 * r1, qb = gb0 * r0 + gb1 * r1, qc = gc0 * r0 + gc1 * r1;
+    const v3 la = alam * qa, lb = alam * qb, lc = alam * qc;
+    const double md = t8 / 12.0, mo = 0.5 * md;
+    {
+        sym3 Sd;
+        double s = ga0 * ga0 + ga1 * ga1;
+        Sd.xx = md + (s * RR0 + la.x * qa.x); Sd.xy = s * RR1 + la.x * qa.y; Sd.xz = s * RR2 + la.x * qa.z;
+        Sd.yy = md + (s * RR3 + la.y * qa.y); Sd.yz = s * RR4 + la.y * qa.z; Sd.zz = md + (s * RR5 + la.z * qa.z);
+        emit.diag(0, Sd);
+        s = gb0 * gb0 + gb1 * gb1;
+        Sd.xx = md + (s * RR0 + lb.x * qb.x); Sd.xy = s * RR1 + lb.x * qb.y; Sd.xz = s * RR2 + lb.x * qb.z;
+        Sd.yy = md + (s * RR3 + lb.y * qb.y); Sd.yz = s * RR4 + lb.y * qb.z; Sd.zz = md + (s * RR5 + lb.z * qb.z);
+        emit.diag(1, Sd);
+        s = gc0 * gc0 + gc1 * gc1;
+        Sd.xx = md + (s * RR0 + lc.x * qc.x); Sd.xy = s * RR1 + lc.x * qc.y; Sd.xz = s * RR2 + lc.x * qc.z;
+        Sd.yy = md + (s * RR3 + lc.y * qc.y); Sd.yz = s * RR4 + lc.y * qc.z; Sd.zz = md + (s * RR5 + lc.z * qc.z);
+        emit.diag(2, Sd);
+    }
+    {
+        blk3 B;
+        auto off = [&](double s, v3 li, v3 qj) {
+            B.m[0] = mo + (s * RR0 + li.x * qj.x); B.m[1] = s * RR1 + li.x * qj.y; B.m[2] = s * RR2 + li.x * qj.z;
+            B.m[3] = s * RR1 + li.y * qj.x; B.m[4] = mo + (s * RR3 + li.y * qj.y); B.m[5] = s * RR4 + li.y * qj.z;
+            B.m[6] = s * RR2 + li.z * qj.x; B.m[7] = s * RR4 + li.z * qj.y; B.m[8] = mo + (s * RR5 + li.z * qj.z);
+        };
+        off(ga0 * gb0 + ga1 * gb1, la, qb); emit.off(0, B);
+        off(ga0 * gc0 + ga1 * gc1, la, qc); emit.off(1, B);
+        off(gb0 * gc0 + gb1 * gc1, lb, qc); emit.off(2, B);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row forms (owner-computes assembly): the 3x3 blocks of ONE block-row of an element matrix, i.e. what one element
 // contributes to the CSR rows of ONE of its nodes.  Same closed forms as above, grouped by the row vertex:
 //

@@ -3,18 +3,22 @@
 // Replaces /root/reference/src/Forces.cpp:912-930 (fill), :331-520 (faceBasedF, non-EOL branch),
 // :685-910 (edgeBasedF, non-EOL branch) and Eigen's setFromTriplets.
 //
-// Default pipeline "rows" (one kernel, no HBM scratch) — assemble_rows_kernel:
-//   owner-computes: a CTA owns a run of consecutive nodes and their CSR rows. One thread per (node, incident element)
-//   item evaluates that element's block ROW for the node (face_row / edge_row, elements.cuh) and parks it in shared
-//   memory; after one barrier every output 3x3 block of the CTA's rows sums its contributions from shared memory in the
-//   reference's triplet insertion order (faces ascending, then edges ascending, Forces.cpp:922-923), left to right like
-//   Eigen's collapseDuplicates, and is written ONCE to its fixed CSR slot. M and f come out of the same kernel.
-//   No atomics, no scratch traffic: HBM sees x, X, the plan's index streams and each output value exactly once.
-// Legacy pipeline "scratch" (EOLC_FORCES_PIPELINE=scratch, kept for A/B measurements): element-per-thread kernels write
-//   element blocks to an HBM scratch, three gather kernels pull them into the CSR slots (3.5x the algorithmic traffic).
+// Default pipeline "tiles" (one persistent kernel, no HBM scratch) — assemble_tiles_kernel:
+//   the nodes are partitioned into spatially compact tiles (forces_plan.h).  One CTA per SM walks its tiles; for each tile
+//   phase 1 evaluates every face / bending stencil touching the tile ONCE (one element per thread, FP64, elements.cuh) and
+//   parks the element blocks in shared memory; after one barrier, phase 2 lets every output 3x3 block of the tile's CSR rows
+//   pull its contributions from shared memory in a fixed order and writes it ONCE to its fixed CSR slot (tile_exec.cuh).
+//   M and f come out of the same kernel.  No atomics, no scratch traffic: HBM sees x, X, the plan's index streams and each
+//   output value exactly once.  The inputs of the NEXT tile (node table, x / X gathers, template) are staged with cp.async
+//   while the current tile computes.
+// Alternative pipeline "rows" (EOLC_FORCES_PIPELINE=rows, the previous design, kept for A/B measurements): a CTA owns a run
+//   of consecutive nodes, one thread per (node, incident element) evaluates that element's block ROW — every element is
+//   re-evaluated once per node it touches (3x / 4x), which made the kernel FP64-issue bound (profiles/r01).
 // Both are bit-reproducible run to run.
 #include "common.h"
 #include "elements.cuh"
+#include "forces_plan.h"
+#include "tile_exec.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <numeric>
@@ -27,32 +31,26 @@ using namespace eolc;
 struct eolc_forces_plan {
     eolc_ctx *ctx = nullptr;
     int32_t N = 0, F = 0, E = 0, Ei = 0, dof = 0;
-    int64_t nnzM = 0, nnzK = 0, nblkM = 0, nblkK = 0;
+    int64_t nnzM = 0, nnzK = 0;
     // host topology
     std::vector<int32_t> h_face_nodes, h_iedge;   // h_iedge: 4 per INTERIOR edge, ascending mesh edge order
-    std::vector<int64_t> h_blkptrM, h_blkptrK;    // N+1: first block of node a
-    std::vector<int32_t> h_nbrM, h_nbrK;          // neighbour node per block (ascending within a node)
+    Pattern pat;                                  // block pattern of M and MDK
     std::vector<int32_t> h_outerM, h_innerM, h_outerK, h_innerK;  // lazily built Eigen-style arrays
-    // device topology
-    DevBuf<int32_t> d_face_nodes, d_iedge;
-    DevBuf<int64_t> d_blkptrM, d_blkptrK;
-    DevBuf<int32_t> d_blknodeM, d_blknodeK;       // owning (row) node of each block
-    DevBuf<int32_t> d_nbrM;                       // column node of each M block
-    DevBuf<int64_t> d_cptrM, d_cptrK, d_cptrF;    // contribution list offsets per block / per node
-    DevBuf<int32_t> d_contribM, d_contribK, d_contribF;
-    // "rows" pipeline
-    int pipeline = 0;                             // 0 = rows, 1 = scratch
-    int32_t n_cta = 0;
+    int pipeline = 0;                             // 0 = tiles, 1 = rows
     bool smem_attr_set = false;
+    // "tiles" pipeline
+    int32_t n_tiles = 0, n_templates = 0;
+    uint32_t geo16 = 0, tmplA16 = 0, tmplB16 = 0, loc_max = 0, scr_doubles = 0, kstage = 0, mstage = 0;
+    int64_t elem_evals = 0, geo_bytes = 0, tmpl_bytes = 0;
+    DevBuf<uint4> d_geo, d_tmpl;
+    // "rows" pipeline
+    int32_t n_cta = 0;
     DevBuf<uint4> d_cta_hdr;                      // 2 x uint4 per CTA (CtaHeader)
     DevBuf<unsigned long long> d_slot;            // per CTA slot (aligned with the block index): packed SlotRec
     DevBuf<uint32_t> d_items;                     // NT slots per CTA: pack_item(local ids, pos), 0 = empty
     DevBuf<int32_t> d_tile_nodes;                 // TILE_NODES slots per CTA: the tile's distinct global node ids
     DevBuf<uint16_t> d_pl;                        // item_local << 2 | column block j
     DevBuf<uint16_t> d_node_f;                    // first face item (CTA-local) | count << 8
-    // scratch (per scene chunk)
-    DevBuf<double> d_face_scr, d_edge_scr;
-    int32_t scratch_scenes = 0;
     // staging for the host entry point
     DevBuf<double> d_x, d_X, d_f, d_Mv, d_Kv;
     PinnedBuf<double> p_in, p_out;
@@ -60,150 +58,164 @@ struct eolc_forces_plan {
 
 namespace {
 
-constexpr int FACE_SCR = 64;   // doubles per face: 54 K + 9 f + 1 t8
-constexpr int EDGE_SCR = 90;   // doubles per interior edge: 10 blocks x 9
+// ------------------------------------------------------------------------------------------------
+// "tiles" pipeline
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// contribution code: bits 0-3 local block id, bit 4 transposed, bit 5 edge (else face), bits 6.. element index
-__host__ __device__ inline int32_t mk_code(int32_t elem, int is_edge, int blk, int tr) {
-    return (elem << 6) | (is_edge << 5) | (tr << 4) | blk;
+// Shared memory: [scr: parked element blocks][staged MDK rows][staged M rows][staged f][template A x 2][template B]
+// [geometry x 4][x x 2][X x 2]; work item w = scene * n_tiles + tile.
+//   at the start of tile k:  geometry(k+2), template A(k+1), the x / X gathers of tile k+1 and template B(k) are issued
+//                            (cp.async, one group)
+//   phase 1(k)  ->  wait group + barrier  ->  phase 2(k)  ->  barrier  ->  copy-out(k), which overlaps phase 1(k+1) of faster warps
+struct TilesSmem {
+    uint32_t scr, kst, mst, fst, tmplA, tmplB, geo, x, X, total;   // byte offsets
+};
+__host__ __device__ inline TilesSmem tiles_smem_layout(uint32_t scr_doubles, uint32_t kstage, uint32_t mstage, uint32_t tmplA16, uint32_t tmplB16,
+                                                       uint32_t geo16, uint32_t loc_max) {
+    TilesSmem L;
+    uint32_t o = 0;
+    auto take = [&](uint32_t bytes) { uint32_t at = o; o += (bytes + 15u) & ~15u; return at; };
+    L.scr = take(8 * scr_doubles); L.kst = take(8 * kstage); L.mst = take(8 * mstage); L.fst = take(8 * 3 * tiles::MAX_OWN);
+    L.tmplA = take(2 * 16 * tmplA16); L.tmplB = take(16 * tmplB16); L.geo = take(4 * 16 * geo16);
+    L.x = take(2 * 8 * 3 * loc_max); L.X = take(2 * 8 * 2 * loc_max);
+    L.total = o;
+    return L;
 }
 
-__global__ void __launch_bounds__(128) face_kernel(int F, const int32_t *__restrict__ fn, const double *__restrict__ x,
-                                                   const double *__restrict__ X, double e, double nu, double rho,
-                                                   double gx, double gy, double gz, double dhh, double *__restrict__ scr,
-                                                   size_t x_stride, size_t X_stride, size_t scr_stride) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= F) return;
-    const int s = blockIdx.y;
-    x += s * x_stride; X += s * X_stride; scr += s * scr_stride;
-    int a = fn[3 * i], b = fn[3 * i + 1], c = fn[3 * i + 2];
-    FaceOut o;
-    face_element(mk3(x[3 * a], x[3 * a + 1], x[3 * a + 2]), mk3(x[3 * b], x[3 * b + 1], x[3 * b + 2]),
-                 mk3(x[3 * c], x[3 * c + 1], x[3 * c + 2]), X[2 * a], X[2 * a + 1], X[2 * b], X[2 * b + 1], X[2 * c],
-                 X[2 * c + 1], e, nu, rho, mk3(gx, gy, gz), dhh, o);
-    // SoA: scr[k*F + i]
-#pragma unroll
-    for (int bk = 0; bk < 6; ++bk)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) scr[(size_t)(bk * 9 + k) * F + i] = o.K[bk].m[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        scr[(size_t)(54 + k) * F + i] = o.fa[k];
-        scr[(size_t)(57 + k) * F + i] = o.fb[k];
-        scr[(size_t)(60 + k) * F + i] = o.fc[k];
-    }
-    scr[(size_t)63 * F + i] = o.t8;
-}
+struct TilesArgs {
+    long long n_work;
+    int n_tiles;
+    uint32_t geo16, tmplA16, tmplB16, loc_max, scr_doubles, kstage, mstage;
+    const uint4 *geo, *tmpl;
+    const double *x, *X;
+    double *f, *Mv, *Kv;
+    size_t x_stride, X_stride, f_stride, M_stride, K_stride;
+    tiles::FillParams prm;
+};
 
-__global__ void __launch_bounds__(128) edge_kernel(int Ei, const int32_t *__restrict__ st, const double *__restrict__ x,
-                                                   const double *__restrict__ X, double beta, double dhh,
-                                                   double *__restrict__ scr, size_t x_stride, size_t X_stride,
-                                                   size_t scr_stride) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Ei) return;
-    const int s = blockIdx.y;
-    x += s * x_stride; X += s * X_stride; scr += s * scr_stride;
-    int n0 = st[4 * i], n1 = st[4 * i + 1], n2 = st[4 * i + 2], n3 = st[4 * i + 3];
-    EdgeOut o;
-    edge_element(mk3(x[3 * n0], x[3 * n0 + 1], x[3 * n0 + 2]), mk3(x[3 * n1], x[3 * n1 + 1], x[3 * n1 + 2]),
-                 mk3(x[3 * n2], x[3 * n2 + 1], x[3 * n2 + 2]), mk3(x[3 * n3], x[3 * n3 + 1], x[3 * n3 + 2]), X[2 * n0],
-                 X[2 * n0 + 1], X[2 * n1], X[2 * n1 + 1], X[2 * n2], X[2 * n2 + 1], X[2 * n3], X[2 * n3 + 1], beta, dhh, o);
-#pragma unroll
-    for (int bk = 0; bk < 10; ++bk)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) scr[(size_t)(bk * 9 + k) * Ei + i] = o.K[bk].m[k];
-}
+__global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemble_tiles_kernel(const __grid_constant__ TilesArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TilesSmem L = tiles_smem_layout(A.scr_doubles, A.kstage, A.mstage, A.tmplA16, A.tmplB16, A.geo16, A.loc_max);
+    double *scr = reinterpret_cast<double *>(smem_raw + L.scr);
+    uint4 *TAst = reinterpret_cast<uint4 *>(smem_raw + L.tmplA);
+    uint4 *TBst = reinterpret_cast<uint4 *>(smem_raw + L.tmplB);
+    uint4 *Gst = reinterpret_cast<uint4 *>(smem_raw + L.geo);
+    double *xst = reinterpret_cast<double *>(smem_raw + L.x);
+    double *Xst = reinterpret_cast<double *>(smem_raw + L.X);
+    const int tid = threadIdx.x;
+    const uint32_t geo16 = A.geo16, tmplA16 = A.tmplA16, loc_max = A.loc_max;
+    const int n_tiles = A.n_tiles;
+    constexpr int NT = tiles::CTA_THREADS;
+    constexpr int GSTAGES = 4;
 
-// one thread per MDK block (a, p): vals[rowstart(3a+j) + 3p + k], rowstart(3a+j) = 9*blkptr[a] + j*3*deg(a)
-__global__ void __launch_bounds__(256) gather_mdk(int64_t nblk, const int32_t *__restrict__ blknode,
-                                                  const int64_t *__restrict__ blkptr, const int64_t *__restrict__ cptr,
-                                                  const int32_t *__restrict__ contrib, int F, int Ei,
-                                                  const double *__restrict__ fscr, const double *__restrict__ escr,
-                                                  double *__restrict__ vals, size_t fscr_stride, size_t escr_stride,
-                                                  size_t vals_stride) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nblk) return;
-    const int s = blockIdx.y;
-    fscr += s * fscr_stride; escr += s * escr_stride; vals += s * vals_stride;
-    double acc[9];
-    bool first = true;
-    for (int64_t c = cptr[t]; c < cptr[t + 1]; ++c) {
-        int32_t code = contrib[c];
-        int blk = code & 15, tr = (code >> 4) & 1, is_edge = (code >> 5) & 1;
-        int32_t el = code >> 6;
-        const double *src = is_edge ? escr + (size_t)(blk * 9) * Ei + el : fscr + (size_t)(blk * 9) * F + el;
-        size_t st = is_edge ? (size_t)Ei : (size_t)F;
-        double v[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) v[k] = src[k * st];
-        if (tr) { double q; q = v[1]; v[1] = v[3]; v[3] = q; q = v[2]; v[2] = v[6]; v[6] = q; q = v[5]; v[5] = v[7]; v[7] = q; }
-        if (first) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) acc[k] = v[k];
-            first = false;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) acc[k] = acc[k] + v[k];
+    auto load_geo = [&](long long w, int stage) {
+        const uint4 *src = A.geo + (size_t)(w % n_tiles) * geo16;
+        for (uint32_t i = tid; i < geo16; i += NT) cp16(Gst + (size_t)stage * geo16 + i, src + i);
+    };
+    auto load_tmplA = [&](int gstage, int tstage) {
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(Gst + (size_t)gstage * geo16);
+        const uint4 *src = A.tmpl + g[0];
+        const uint32_t n = g[2] & 0xffffu;
+        for (uint32_t i = tid; i < n; i += NT) cp16(TAst + (size_t)tstage * tmplA16 + i, src + i);
+    };
+    auto load_tmplB = [&](int gstage) {
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(Gst + (size_t)gstage * geo16);
+        const uint4 *src = A.tmpl + g[0] + (g[2] & 0xffffu);
+        const uint32_t n = g[2] >> 16;
+        for (uint32_t i = tid; i < n; i += NT) cp16(TBst + i, src + i);
+    };
+    auto gather = [&](long long w, int gstage, int xstage) {
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(Gst + (size_t)gstage * geo16);
+        const uint32_t nOwn = g[1] & 255u, nLoc = (g[1] >> 8) & 255u;
+        const uint32_t *loc = g + 4 + 4 * nOwn;
+        const size_t sc = (size_t)(w / n_tiles);
+        const double *xs = A.x + sc * A.x_stride, *Xs = A.X + sc * A.X_stride;
+        double *xd = xst + (size_t)xstage * 3 * loc_max, *Xd = Xst + (size_t)xstage * 2 * loc_max;
+        for (uint32_t i = tid; i < 4 * nLoc; i += NT) {
+            const uint32_t l = i >> 2, part = i & 3u;
+            const size_t gid = loc[l];
+            if (part < 3) cp8(xd + 3 * l + part, xs + 3 * gid + part);
+            else cp16(Xd + 2 * l, Xs + 2 * gid);
         }
-    }
-    int a = blknode[t];
-    int64_t b0 = blkptr[a];
-    int deg = (int)(blkptr[a + 1] - b0);
-    int p = (int)(t - b0);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        double *row = vals + 9 * b0 + (int64_t)j * 3 * deg + 3 * p;
-        row[0] = acc[3 * j]; row[1] = acc[3 * j + 1]; row[2] = acc[3 * j + 2];
+    };
+
+    const long long w0 = blockIdx.x, step = gridDim.x;
+    if (w0 >= A.n_work) return;
+    if (tid < tiles::ZPAD) scr[tid] = 0.0;   // the zero block padded pull lists point at (never written again)
+    load_geo(w0, 0);
+    if (w0 + step < A.n_work) load_geo(w0 + step, 1);
+    cp_commit(); cp_wait_all();
+    __syncthreads();
+    load_tmplA(0, 0);
+    gather(w0, 0, 0);
+    cp_commit(); cp_wait_all();
+    __syncthreads();
+    tiles::TileView V;
+    V.scr = scr;
+    V.kst = reinterpret_cast<double *>(smem_raw + L.kst);
+    V.mst = reinterpret_cast<double *>(smem_raw + L.mst);
+    V.fst = reinterpret_cast<double *>(smem_raw + L.fst);
+    V.tmplB = reinterpret_cast<const uint32_t *>(TBst);
+    int gs = 0, ts = 0;
+    for (long long w = w0; w < A.n_work; w += step) {
+        const int gs1 = (gs + 1) & (GSTAGES - 1), gs2 = (gs + 2) & (GSTAGES - 1);
+        // stage reuse: geometry(k+2) overwrites the stage of tile k-2 (copy-out(k-2) finished before the barriers of tile k-1);
+        // template B(k) overwrites B(k-1), last read in phase 2(k-1), i.e. before the barrier every thread has passed
+        if (w + 2 * step < A.n_work) load_geo(w + 2 * step, gs2);
+        if (w + step < A.n_work) { load_tmplA(gs1, ts ^ 1); gather(w + step, gs1, ts ^ 1); }
+        load_tmplB(gs);
+        cp_commit();
+        V.geo = reinterpret_cast<const uint32_t *>(Gst + (size_t)gs * geo16);
+        V.tmpl = reinterpret_cast<const uint32_t *>(TAst + (size_t)ts * tmplA16);
+        V.xs = xst + (size_t)ts * 3 * loc_max;
+        V.Xs = Xst + (size_t)ts * 2 * loc_max;
+        tiles::phase1(tid, V, A.prm);
+        cp_wait_all();
+        __syncthreads();                 // elements parked, staged inputs landed, previous copy-out done
+        tiles::phase2(tid, NT, V);
+        __syncthreads();                 // staged rows complete; the scratch may be overwritten by the next phase 1
+        const size_t sc = (size_t)(w / n_tiles);
+        tiles::copy_out(tid, NT, V, A.f + sc * A.f_stride, A.Mv + sc * A.M_stride, A.Kv + sc * A.K_stride);
+        gs = gs1; ts ^= 1;
     }
 }
 
-// one thread per M block: sum over faces of t8/12 (a == b) or t8/24, on the block diagonal; explicit zeros elsewhere
-__global__ void __launch_bounds__(256) gather_m(int64_t nblk, const int32_t *__restrict__ blknode,
-                                                const int64_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
-                                                const int64_t *__restrict__ cptr, const int32_t *__restrict__ contrib,
-                                                int F, const double *__restrict__ fscr, double *__restrict__ vals,
-                                                size_t fscr_stride, size_t vals_stride) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nblk) return;
-    const int s = blockIdx.y;
-    fscr += s * fscr_stride; vals += s * vals_stride;
-    int a = blknode[t];
-    const bool diag = nbr[t] == a;
-    double acc = 0.0;
-    bool first = true;
-    for (int64_t c = cptr[t]; c < cptr[t + 1]; ++c) {
-        double t8 = fscr[(size_t)63 * F + contrib[c]];
-        double m = diag ? t8 / 12.0 : t8 / 24.0;
-        acc = first ? m : acc + m;
-        first = false;
-    }
-    int64_t b0 = blkptr[a];
-    int deg = (int)(blkptr[a + 1] - b0);
-    int p = (int)(t - b0);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        double *row = vals + 9 * b0 + (int64_t)j * 3 * deg + 3 * p;
-        row[0] = j == 0 ? acc : 0.0; row[1] = j == 1 ? acc : 0.0; row[2] = j == 2 ? acc : 0.0;
-    }
+size_t tiles_smem_bytes(const eolc_forces_plan *P) {
+    return tiles_smem_layout(P->scr_doubles, P->kstage, P->mstage, P->tmplA16, P->tmplB16, P->geo16, P->loc_max).total;
 }
 
-// one thread per node: f[3a..3a+2] = sum over incident faces (ascending) of (fm + fi) of that vertex
-__global__ void __launch_bounds__(256) gather_f(int N, const int64_t *__restrict__ cptr, const int32_t *__restrict__ contrib,
-                                                int F, const double *__restrict__ fscr, double *__restrict__ f,
-                                                size_t fscr_stride, size_t f_stride) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= N) return;
-    const int s = blockIdx.y;
-    fscr += s * fscr_stride; f += s * f_stride;
-    double f0 = 0.0, f1 = 0.0, f2 = 0.0;   // f.setZero() then +=  (Forces.cpp:915, :500-502)
-    for (int64_t c = cptr[a]; c < cptr[a + 1]; ++c) {
-        int32_t code = contrib[c];
-        int lv = code & 3;
-        int32_t face = code >> 2;
-        const double *src = fscr + (size_t)(54 + 3 * lv) * F + face;
-        f0 += src[0]; f1 += src[(size_t)F]; f2 += src[2 * (size_t)F];
+int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st) {
+    tiles::Plan tp;
+    const char *dd = getenv("EOLC_FORCES_DEDUP");
+    const bool dedup = !(dd && strcmp(dd, "0") == 0);
+    if (!tiles::build(P->N, P->F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), P->pat, X_hint, dedup, tp)) {
+        set_error("tile plan: %s", tp.error.c_str());
+        return EOLC_ERR_UNSUPPORTED;
     }
-    f[3 * a] = f0; f[3 * a + 1] = f1; f[3 * a + 2] = f2;
+    P->n_tiles = tp.n_tiles; P->n_templates = tp.n_templates;
+    P->geo16 = tp.max_geo16; P->tmplA16 = tp.max_tmplA16; P->tmplB16 = tp.max_tmplB16;
+    P->loc_max = (tp.max_loc + 1) & ~1u;
+    P->scr_doubles = (tp.max_scratch + 1) & ~1u;
+    P->kstage = (tp.max_kstage + 1) & ~1u; P->mstage = (tp.max_mstage + 1) & ~1u;
+    P->elem_evals = tp.elem_evals;
+    P->geo_bytes = (int64_t)tp.geo.size() * 4; P->tmpl_bytes = (int64_t)tp.tmpl.size() * 4;
+    if (tiles_smem_bytes(P) > (size_t)(tiles::CTAS_PER_SM == 1 ? 227 : 113) * 1024) { set_error("tile plan needs %zu bytes of shared memory", tiles_smem_bytes(P)); return EOLC_ERR_UNSUPPORTED; }
+    static_assert(sizeof(uint4) == 16, "uint4");
+    EOLC_CUDA(P->d_geo.alloc(tp.geo.size() / 4));
+    EOLC_CUDA(P->d_tmpl.alloc(tp.tmpl.size() / 4));
+    if (!tp.geo.empty()) EOLC_CUDA(cudaMemcpyAsync(P->d_geo.p, tp.geo.data(), tp.geo.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!tp.tmpl.empty()) EOLC_CUDA(cudaMemcpyAsync(P->d_tmpl.p, tp.tmpl.data(), tp.tmpl.size() * 4, cudaMemcpyHostToDevice, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));   // tp dies at scope exit
+    return EOLC_OK;
 }
 
 
@@ -443,8 +455,6 @@ __global__ void __launch_bounds__(NTHREADS, ROWS_MIN_CTAS) assemble_rows_kernel(
     }
 }
 
-inline int64_t find_block(const std::vector<int64_t> &blkptr, const std::vector<int32_t> &nbr, int32_t a, int32_t b);
-
 int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
     const int32_t N = P->N, F = P->F, Ei = P->Ei;
     const int32_t *fn = P->h_face_nodes.data();
@@ -504,7 +514,7 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
     std::vector<uint16_t> pl;
     pl.reserve(9 * (size_t)F + 16 * (size_t)Ei);
     std::vector<uint16_t> node_f(N, 0);
-    std::vector<unsigned long long> slots((size_t)P->nblkK, 0);
+    std::vector<unsigned long long> slots((size_t)P->pat.nblkK, 0);
     std::vector<CtaHeader> hdr((size_t)nc);
     std::vector<std::vector<uint16_t>> tmp;   // per block of the current node
     struct SlotTmp { int cnt; unsigned long long rec; };
@@ -519,10 +529,10 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
             return local[g];
         };
         cslots.clear();
-        const int64_t cb0 = P->h_blkptrK[n0], cm0 = P->h_blkptrM[n0];
+        const int64_t cb0 = P->pat.blkptrK[n0], cm0 = P->pat.blkptrM[n0];
         const size_t plbase = pl.size();
         for (int32_t a = n0; a < n1; ++a) {
-            const int64_t b0 = P->h_blkptrK[a], b1 = P->h_blkptrK[a + 1];
+            const int64_t b0 = P->pat.blkptrK[a], b1 = P->pat.blkptrK[a + 1];
             const int deg = (int)(b1 - b0);
             if (deg > 255) { set_error("node %d has %d neighbours (limit 255)", a, deg); return EOLC_ERR_UNSUPPORTED; }
             tmp.assign(deg, {});
@@ -533,7 +543,7 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
                 const int32_t *v = fn + 3 * (size_t)face;
                 items[(size_t)c * NT + fpos] = pack_item(lid(v[0]), lid(v[1]), lid(v[2]), 0, nfl[k] & 3);
                 for (int j = 0; j < 3; ++j) {
-                    int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, v[j]) - b0);
+                    int p = (int)(find_block(P->pat.blkptrK, P->pat.nbrK, a, v[j]) - b0);
                     tmp[p].push_back((uint16_t)((fpos << 2) | j));
                     nfaces[p]++;
                 }
@@ -544,19 +554,19 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
                 const int32_t *v = ie + 4 * (size_t)ed;
                 items[(size_t)c * NT + epos] = pack_item(lid(v[0]), lid(v[1]), lid(v[2]), lid(v[3]), nel[k] & 3);
                 for (int j = 0; j < 4; ++j) {
-                    int p = (int)(find_block(P->h_blkptrK, P->h_nbrK, a, v[j]) - b0);
+                    int p = (int)(find_block(P->pat.blkptrK, P->pat.nbrK, a, v[j]) - b0);
                     tmp[p].push_back((uint16_t)((epos << 2) | j));
                 }
                 ++epos;
             }
-            const int64_t m0 = P->h_blkptrM[a];
-            const int degM = (int)(P->h_blkptrM[a + 1] - m0);
+            const int64_t m0 = P->pat.blkptrM[a];
+            const int degM = (int)(P->pat.blkptrM[a + 1] - m0);
             for (int p = 0; p < deg; ++p) {
-                const int32_t b = P->h_nbrK[b0 + p];
+                const int32_t b = P->pat.nbrK[b0 + p];
                 const unsigned q0 = (unsigned)(pl.size() - plbase);
                 pl.insert(pl.end(), tmp[p].begin(), tmp[p].end());
                 unsigned hasm = 0, moff = 0;
-                if (nfaces[p] > 0) { hasm = 1; moff = (unsigned)(3 * (m0 - cm0) + (find_block(P->h_blkptrM, P->h_nbrM, a, b) - m0)); }
+                if (nfaces[p] > 0) { hasm = 1; moff = (unsigned)(3 * (m0 - cm0) + (find_block(P->pat.blkptrM, P->pat.nbrM, a, b) - m0)); }
                 const unsigned koff = (unsigned)(3 * (b0 - cb0) + p);
                 if (q0 > 511 || tmp[p].size() > 127 || nfaces[p] > 63 || koff > 2047 || moff > 2047 || degM > 255) {
                     set_error("internal: slot record overflow at node %d", a);
@@ -590,193 +600,43 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
     return EOLC_OK;
 }
 
-int build_pattern(eolc_forces_plan *P) {
-    const int32_t N = P->N, F = P->F;
-    const int32_t Ei = P->Ei;
-    const int32_t *fn = P->h_face_nodes.data();
-    const int32_t *ie = P->h_iedge.data();
-    // adjacency via counting
-    std::vector<int64_t> cntM(N + 1, 0), cntK(N + 1, 0);
-    for (int32_t a = 0; a < N; ++a) { cntM[a + 1] = 1; cntK[a + 1] = 1; }  // self (isolated nodes get no block: fix below)
-    std::vector<char> used(N, 0);
-    for (int32_t i = 0; i < F; ++i)
-        for (int v = 0; v < 3; ++v) { used[fn[3 * i + v]] = 1; cntM[fn[3 * i + v] + 1] += 2; cntK[fn[3 * i + v] + 1] += 2; }
-    for (int32_t i = 0; i < Ei; ++i)
-        for (int v = 0; v < 4; ++v) cntK[ie[4 * i + v] + 1] += 3;
-    for (int32_t a = 0; a < N; ++a) if (!used[a]) { cntM[a + 1] = 0; cntK[a + 1] = 0; }
-    for (int32_t a = 0; a < N; ++a) { cntM[a + 1] += cntM[a]; cntK[a + 1] += cntK[a]; }
-    std::vector<int32_t> rawM(cntM[N]), rawK(cntK[N]);
-    std::vector<int64_t> pM(cntM.begin(), cntM.end() - 1), pK(cntK.begin(), cntK.end() - 1);
-    for (int32_t a = 0; a < N; ++a) if (used[a]) { rawM[pM[a]++] = a; rawK[pK[a]++] = a; }
-    for (int32_t i = 0; i < F; ++i)
-        for (int v = 0; v < 3; ++v) {
-            int32_t a = fn[3 * i + v];
-            for (int w = 0; w < 3; ++w) if (w != v) { rawM[pM[a]++] = fn[3 * i + w]; rawK[pK[a]++] = fn[3 * i + w]; }
-        }
-    for (int32_t i = 0; i < Ei; ++i)
-        for (int v = 0; v < 4; ++v) {
-            int32_t a = ie[4 * i + v];
-            for (int w = 0; w < 4; ++w) if (w != v) rawK[pK[a]++] = ie[4 * i + w];
-        }
-    auto compress = [&](std::vector<int64_t> &cnt, std::vector<int32_t> &raw, std::vector<int64_t> &blkptr, std::vector<int32_t> &nbr) {
-        blkptr.assign(N + 1, 0);
-        nbr.clear();
-        nbr.reserve(raw.size() / 2);
-        for (int32_t a = 0; a < N; ++a) {
-            auto b = raw.begin() + cnt[a], e = raw.begin() + cnt[a + 1];
-            std::sort(b, e);
-            auto u = std::unique(b, e);
-            nbr.insert(nbr.end(), b, u);
-            blkptr[a + 1] = (int64_t)nbr.size();
-        }
-    };
-    compress(cntM, rawM, P->h_blkptrM, P->h_nbrM);
-    compress(cntK, rawK, P->h_blkptrK, P->h_nbrK);
-    P->nblkM = P->h_blkptrM[N]; P->nblkK = P->h_blkptrK[N];
-    P->nnzM = 9 * P->nblkM; P->nnzK = 9 * P->nblkK;
-    if (P->nnzK > (int64_t)INT32_MAX) { set_error("nnz(MDK) exceeds int32 (Eigen StorageIndex is int)"); return EOLC_ERR_UNSUPPORTED; }
-    return EOLC_OK;
-}
-
-inline int64_t find_block(const std::vector<int64_t> &blkptr, const std::vector<int32_t> &nbr, int32_t a, int32_t b) {
-    auto beg = nbr.begin() + blkptr[a], end = nbr.begin() + blkptr[a + 1];
-    return std::lower_bound(beg, end, b) - nbr.begin();
-}
-
-// local block id of (vi, vj), vi <= vj, in the element's emitted block order
-const int kFaceBlk[3][3] = {{0, 3, 4}, {3, 1, 5}, {4, 5, 2}};
-const int kEdgeBlk[4][4] = {{0, 4, 5, 6}, {4, 1, 7, 8}, {5, 7, 2, 9}, {6, 8, 9, 3}};
-
-int build_contribs(eolc_forces_plan *P, cudaStream_t st) {
-    const int32_t N = P->N, F = P->F, Ei = P->Ei;
-    const int32_t *fn = P->h_face_nodes.data();
-    const int32_t *ie = P->h_iedge.data();
-    // ---- MDK: count then fill; element order = faces ascending then interior edges ascending
-    std::vector<int64_t> cK(P->nblkK + 1, 0), cM(P->nblkM + 1, 0), cF(N + 1, 0);
-    for (int32_t i = 0; i < F; ++i)
-        for (int v = 0; v < 3; ++v) {
-            cF[fn[3 * i + v] + 1]++;
-            for (int w = 0; w < 3; ++w) {
-                cK[find_block(P->h_blkptrK, P->h_nbrK, fn[3 * i + v], fn[3 * i + w]) + 1]++;
-                cM[find_block(P->h_blkptrM, P->h_nbrM, fn[3 * i + v], fn[3 * i + w]) + 1]++;
-            }
-        }
-    for (int32_t i = 0; i < Ei; ++i)
-        for (int v = 0; v < 4; ++v)
-            for (int w = 0; w < 4; ++w) cK[find_block(P->h_blkptrK, P->h_nbrK, ie[4 * i + v], ie[4 * i + w]) + 1]++;
-    for (int64_t b = 0; b < P->nblkK; ++b) cK[b + 1] += cK[b];
-    for (int64_t b = 0; b < P->nblkM; ++b) cM[b + 1] += cM[b];
-    for (int32_t a = 0; a < N; ++a) cF[a + 1] += cF[a];
-    std::vector<int32_t> lK(cK[P->nblkK]), lM(cM[P->nblkM]), lF(cF[N]);
-    std::vector<int64_t> pK(cK.begin(), cK.end() - 1), pM(cM.begin(), cM.end() - 1), pF(cF.begin(), cF.end() - 1);
-    for (int32_t i = 0; i < F; ++i)
-        for (int v = 0; v < 3; ++v) {
-            lF[pF[fn[3 * i + v]]++] = (i << 2) | v;
-            for (int w = 0; w < 3; ++w) {
-                int lo = v < w ? v : w, hi = v < w ? w : v;
-                int64_t bk = find_block(P->h_blkptrK, P->h_nbrK, fn[3 * i + v], fn[3 * i + w]);
-                lK[pK[bk]++] = mk_code(i, 0, kFaceBlk[lo][hi], v > w ? 1 : 0);
-                int64_t bm = find_block(P->h_blkptrM, P->h_nbrM, fn[3 * i + v], fn[3 * i + w]);
-                lM[pM[bm]++] = i;
-            }
-        }
-    for (int32_t i = 0; i < Ei; ++i)
-        for (int v = 0; v < 4; ++v)
-            for (int w = 0; w < 4; ++w) {
-                int lo = v < w ? v : w, hi = v < w ? w : v;
-                int64_t bk = find_block(P->h_blkptrK, P->h_nbrK, ie[4 * i + v], ie[4 * i + w]);
-                lK[pK[bk]++] = mk_code(i, 1, kEdgeBlk[lo][hi], v > w ? 1 : 0);
-            }
-    std::vector<int32_t> bnM(P->nblkM), bnK(P->nblkK);
-    for (int32_t a = 0; a < N; ++a) {
-        for (int64_t b = P->h_blkptrM[a]; b < P->h_blkptrM[a + 1]; ++b) bnM[b] = a;
-        for (int64_t b = P->h_blkptrK[a]; b < P->h_blkptrK[a + 1]; ++b) bnK[b] = a;
-    }
-    EOLC_CUDA(P->d_cptrK.upload(cK, st)); EOLC_CUDA(P->d_contribK.upload(lK, st));
-    EOLC_CUDA(P->d_cptrM.upload(cM, st)); EOLC_CUDA(P->d_contribM.upload(lM, st));
-    EOLC_CUDA(P->d_cptrF.upload(cF, st)); EOLC_CUDA(P->d_contribF.upload(lF, st));
-    EOLC_CUDA(P->d_blknodeM.upload(bnM, st)); EOLC_CUDA(P->d_blknodeK.upload(bnK, st));
-    EOLC_CUDA(P->d_blkptrM.upload(P->h_blkptrM, st)); EOLC_CUDA(P->d_blkptrK.upload(P->h_blkptrK, st));
-    EOLC_CUDA(P->d_nbrM.upload(P->h_nbrM, st));
-    EOLC_CUDA(cudaStreamSynchronize(st));  // host vectors die at scope exit
-    return EOLC_OK;
-}
-
-void build_eigen_arrays(int32_t N, const std::vector<int64_t> &blkptr, const std::vector<int32_t> &nbr,
-                        std::vector<int32_t> &outer, std::vector<int32_t> &inner) {
-    outer.assign(3 * (size_t)N + 1, 0);
-    inner.resize(9 * (size_t)blkptr[N]);
-    for (int32_t a = 0; a < N; ++a) {
-        int64_t b0 = blkptr[a];
-        int deg = (int)(blkptr[a + 1] - b0);
-        for (int j = 0; j < 3; ++j) {
-            int64_t rs = 9 * b0 + (int64_t)j * 3 * deg;
-            outer[3 * (size_t)a + j] = (int32_t)rs;
-            for (int p = 0; p < deg; ++p)
-                for (int k = 0; k < 3; ++k) inner[rs + 3 * p + k] = 3 * nbr[b0 + p] + k;
-        }
-    }
-    outer[3 * (size_t)N] = (int32_t)(9 * blkptr[N]);
-}
-
-int ensure_scratch(eolc_forces_plan *P, int32_t scenes) {
-    if (scenes <= P->scratch_scenes) return EOLC_OK;
-    EOLC_CUDA(P->d_face_scr.alloc((size_t)scenes * FACE_SCR * P->F));
-    EOLC_CUDA(P->d_edge_scr.alloc((size_t)scenes * EDGE_SCR * P->Ei));
-    P->scratch_scenes = scenes;
-    return EOLC_OK;
-}
-
 int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X, const eolc_material *mat,
                 const double *grav, double h, double *f, double *Mv, double *Kv) {
     cudaStream_t st = P->ctx->stream;
     const double dhh = mat->dampingB * h * h;   // damping(1)*h*h, Forces.cpp:105
+    if (P->N == 0) return EOLC_OK;
     if (P->pipeline == 0) {
-        if (P->N == 0) return EOLC_OK;
-        {
-            const long long n_tiles = (long long)P->n_cta * S;
-            const int grid = (int)std::min<long long>(n_tiles, (long long)P->ctx->sm_count * ROWS_MIN_CTAS);
-            const size_t smem = sizeof(double) * ITEM_STRIDE * NT + RING * sizeof(TileStage);
-            if (!P->smem_attr_set) {   // per device; plans are per ctx/device
-                EOLC_CUDA(cudaFuncSetAttribute(assemble_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                P->smem_attr_set = true;
-            }
-            assemble_rows_kernel<<<grid, NTHREADS, smem, st>>>(
-                n_tiles, P->n_cta, P->d_cta_hdr.p, P->d_items.p, P->d_tile_nodes.p, P->d_slot.p, P->d_pl.p, P->d_node_f.p, x, X,
-                membrane_mu(mat->e, mat->nu), membrane_lambda(mat->e, mat->nu), mat->density, mat->beta, grav[0], grav[1], grav[2],
-                dhh, f, Mv, Kv, (size_t)3 * P->N, (size_t)2 * P->N, (size_t)P->dof, (size_t)P->nnzM, (size_t)P->nnzK);
+        EOLC_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0, "x must be 8-byte and X 16-byte aligned");
+        const long long n_work = (long long)P->n_tiles * S;
+        const int grid = (int)std::min<long long>(n_work, (long long)P->ctx->sm_count * tiles::CTAS_PER_SM);
+        const size_t smem = tiles_smem_bytes(P);
+        if (!P->smem_attr_set) {
+            EOLC_CUDA(cudaFuncSetAttribute(assemble_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            P->smem_attr_set = true;
         }
+        TilesArgs A;
+        A.n_work = n_work; A.n_tiles = P->n_tiles; A.geo16 = P->geo16; A.tmplA16 = P->tmplA16; A.tmplB16 = P->tmplB16; A.loc_max = P->loc_max;
+        A.scr_doubles = P->scr_doubles; A.kstage = P->kstage; A.mstage = P->mstage; A.geo = P->d_geo.p; A.tmpl = P->d_tmpl.p; A.x = x; A.X = X;
+        A.f = f; A.Mv = Mv; A.Kv = Kv; A.x_stride = (size_t)3 * P->N; A.X_stride = (size_t)2 * P->N; A.f_stride = (size_t)P->dof;
+        A.M_stride = (size_t)P->nnzM; A.K_stride = (size_t)P->nnzK;
+        A.prm.mu = membrane_mu(mat->e, mat->nu); A.prm.lam = membrane_lambda(mat->e, mat->nu); A.prm.rho = mat->density; A.prm.beta = mat->beta;
+        A.prm.gx = grav[0]; A.prm.gy = grav[1]; A.prm.gz = grav[2]; A.prm.dhh = dhh;
+        assemble_tiles_kernel<<<grid, tiles::CTA_THREADS, smem, st>>>(A);
         EOLC_CUDA(cudaGetLastError());
         return EOLC_OK;
     }
-    // scene chunks bounded by the scratch budget (~4 GB)
-    size_t per_scene = ((size_t)FACE_SCR * P->F + (size_t)EDGE_SCR * P->Ei) * sizeof(double);
-    int32_t chunk = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)S, ((size_t)4 << 30) / std::max<size_t>(per_scene, 1)));
-    chunk = std::min<int32_t>(chunk, 65535);
-    int rc = ensure_scratch(P, chunk);
-    if (rc) return rc;
-    const size_t fs = (size_t)FACE_SCR * P->F, es = (size_t)EDGE_SCR * P->Ei;
-    for (int32_t s0 = 0; s0 < S; s0 += chunk) {
-        int32_t sc = std::min(chunk, S - s0);
-        const double *xs = x + (size_t)s0 * 3 * P->N, *Xs = X + (size_t)s0 * 2 * P->N;
-        if (P->F > 0)
-            face_kernel<<<dim3((P->F + 127) / 128, sc), 128, 0, st>>>(P->F, P->d_face_nodes.p, xs, Xs, mat->e, mat->nu, mat->density,
-                                                                      grav[0], grav[1], grav[2], dhh, P->d_face_scr.p,
-                                                                      (size_t)3 * P->N, (size_t)2 * P->N, fs);
-        if (P->Ei > 0)
-            edge_kernel<<<dim3((P->Ei + 127) / 128, sc), 128, 0, st>>>(P->Ei, P->d_iedge.p, xs, Xs, mat->beta, dhh, P->d_edge_scr.p,
-                                                                       (size_t)3 * P->N, (size_t)2 * P->N, es);
-        if (P->nblkK > 0)
-            gather_mdk<<<dim3((unsigned)((P->nblkK + 255) / 256), sc), 256, 0, st>>>(
-                P->nblkK, P->d_blknodeK.p, P->d_blkptrK.p, P->d_cptrK.p, P->d_contribK.p, P->F, P->Ei, P->d_face_scr.p,
-                P->d_edge_scr.p, Kv + (size_t)s0 * P->nnzK, fs, es, (size_t)P->nnzK);
-        if (P->nblkM > 0)
-            gather_m<<<dim3((unsigned)((P->nblkM + 255) / 256), sc), 256, 0, st>>>(
-                P->nblkM, P->d_blknodeM.p, P->d_blkptrM.p, P->d_nbrM.p, P->d_cptrM.p, P->d_contribM.p, P->F, P->d_face_scr.p,
-                Mv + (size_t)s0 * P->nnzM, fs, (size_t)P->nnzM);
-        if (P->N > 0)
-            gather_f<<<dim3((P->N + 255) / 256, sc), 256, 0, st>>>(P->N, P->d_cptrF.p, P->d_contribF.p, P->F, P->d_face_scr.p,
-                                                                   f + (size_t)s0 * P->dof, fs, (size_t)P->dof);
+    {
+        const long long n_tiles = (long long)P->n_cta * S;
+        const int grid = (int)std::min<long long>(n_tiles, (long long)P->ctx->sm_count * ROWS_MIN_CTAS);
+        const size_t smem = sizeof(double) * ITEM_STRIDE * NT + RING * sizeof(TileStage);
+        if (!P->smem_attr_set) {   // per device; plans are per ctx/device
+            EOLC_CUDA(cudaFuncSetAttribute(assemble_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            P->smem_attr_set = true;
+        }
+        assemble_rows_kernel<<<grid, NTHREADS, smem, st>>>(
+            n_tiles, P->n_cta, P->d_cta_hdr.p, P->d_items.p, P->d_tile_nodes.p, P->d_slot.p, P->d_pl.p, P->d_node_f.p, x, X,
+            membrane_mu(mat->e, mat->nu), membrane_lambda(mat->e, mat->nu), mat->density, mat->beta, grav[0], grav[1], grav[2],
+            dhh, f, Mv, Kv, (size_t)3 * P->N, (size_t)2 * P->N, (size_t)P->dof, (size_t)P->nnzM, (size_t)P->nnzK);
     }
     EOLC_CUDA(cudaGetLastError());
     return EOLC_OK;
@@ -789,7 +649,6 @@ extern "C" {
 int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face_nodes, int32_t E,
                             const int32_t *edge_stencil, const int32_t *eol_index, const double *X_hint,
                             eolc_forces_plan **out) {
-    (void)X_hint;
     EOLC_REQUIRE(ctx && out, "ctx/out is NULL");
     *out = nullptr;
     EOLC_REQUIRE(N >= 0 && F >= 0 && E >= 0, "negative size");
@@ -820,15 +679,13 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
         P->h_iedge.insert(P->h_iedge.end(), s, s + 4);
     }
     P->Ei = (int32_t)(P->h_iedge.size() / 4);
-    int rc = build_pattern(P);
-    if (rc) { delete P; return rc; }
+    build_pattern(N, F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), P->pat);
+    P->nnzM = 9 * P->pat.nblkM; P->nnzK = 9 * P->pat.nblkK;
+    if (P->nnzK > (int64_t)INT32_MAX) { delete P; set_error("nnz(MDK) exceeds int32 (Eigen StorageIndex is int)"); return EOLC_ERR_UNSUPPORTED; }
     cudaStream_t st = ctx->stream;
-    cudaError_t ce = P->d_face_nodes.upload(P->h_face_nodes, st);
-    if (ce == cudaSuccess) ce = P->d_iedge.upload(P->h_iedge, st);
-    if (ce != cudaSuccess) { delete P; set_error("upload failed: %s", cudaGetErrorString(ce)); return EOLC_ERR_CUDA; }
     const char *pe = getenv("EOLC_FORCES_PIPELINE");
-    P->pipeline = (pe && strcmp(pe, "scratch") == 0) ? 1 : 0;
-    rc = P->pipeline == 0 ? build_rows_plan(P, st) : build_contribs(P, st);
+    P->pipeline = (pe && strcmp(pe, "rows") == 0) ? 1 : 0;
+    int rc = P->pipeline == 0 ? build_tiles_plan(P, X_hint, st) : build_rows_plan(P, st);
     if (rc) { delete P; return rc; }
     *out = P;
     return EOLC_OK;
@@ -848,7 +705,7 @@ int eolc_forces_pattern(const eolc_forces_plan *plan, int which, int32_t *dof, i
     if (nnz) *nnz = which ? P->nnzK : P->nnzM;
     if (outer || inner) {
         std::vector<int32_t> &o = which ? P->h_outerK : P->h_outerM, &in = which ? P->h_innerK : P->h_innerM;
-        if (o.empty()) build_eigen_arrays(P->N, which ? P->h_blkptrK : P->h_blkptrM, which ? P->h_nbrK : P->h_nbrM, o, in);
+        if (o.empty()) build_eigen_arrays(P->N, which ? P->pat.blkptrK : P->pat.blkptrM, which ? P->pat.nbrK : P->pat.nbrM, o, in);
         if (outer) *outer = o.data();
         if (inner) *inner = in.data();
     }
@@ -862,7 +719,7 @@ int eolc_forces_counts(const eolc_forces_plan *plan, int32_t *n_faces, int32_t *
     return EOLC_OK;
 }
 
-int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return plan ? (plan->pipeline == 0 ? 1 : 5) : 0; }
+int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return plan ? 1 : 0; }
 
 int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
                                  const eolc_material *mat, const double grav[3], double h, double *f_dev,

@@ -15,6 +15,6 @@ timeout 600 python bench.py --workload sheet256 --steps 50 --warmup 5 --no-cpu -
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 # full capture of the fill kernel
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:assemble_rows -s 3 -c 1 -o $OUT/prof_fill \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:assemble_ -s 3 -c 1 -o $OUT/prof_fill \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-cd > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 tail -c 1500 $OUT/bench.json

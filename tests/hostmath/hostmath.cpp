@@ -2,6 +2,8 @@
 // for the host, so the hand-derived formulas can be checked against the oracle without a GPU.
 // Test infrastructure only — never linked into libeolc_b200.so.
 #include "../../eol_cloth_b200/csrc/elements.cuh"
+#include "../../eol_cloth_b200/csrc/forces_plan.h"
+#include "../../eol_cloth_b200/csrc/tile_exec.cuh"
 using namespace eolc;
 extern "C" {
 void hostmath_face(const double *xa, const double *xb, const double *xc, const double *Xa, const double *Xb,
@@ -37,5 +39,96 @@ void hostmath_edge_row(int i, const double *x0, const double *x1, const double *
     edge_row(i, mk3(x0[0], x0[1], x0[2]), mk3(x1[0], x1[1], x1[2]), mk3(x2[0], x2[1], x2[2]), mk3(x3[0], x3[1], x3[2]),
              X0[0], X0[1], X1[0], X1[1], X2[0], X2[1], X3[0], X3[1], beta, dhh, o);
     for (int b = 0; b < 4; ++b) for (int k = 0; k < 9; ++k) K4x9[9 * b + k] = o.K[b].m[k];
+}
+
+// tiles pipeline element forms
+struct CollectEdge {
+    double *K;   // 10 x 9: 00,11,22,33,01,02,03,12,13,23
+    void diag(int i, const sym3 &S) { double *d = K + 9 * i; d[0] = S.xx; d[1] = S.xy; d[2] = S.xz; d[3] = S.xy; d[4] = S.yy; d[5] = S.yz; d[6] = S.xz; d[7] = S.yz; d[8] = S.zz; }
+    void off(int k, const blk3 &B) { for (int q = 0; q < 9; ++q) K[9 * (4 + k) + q] = B.m[q]; }
+};
+void hostmath_edge_tile(const double *x0, const double *x1, const double *x2, const double *x3, const double *X0,
+                        const double *X1, const double *X2, const double *X3, double beta, double dhh, double *K10x9) {
+    CollectEdge c{K10x9};
+    edge_element_tile(mk3(x0[0], x0[1], x0[2]), mk3(x1[0], x1[1], x1[2]), mk3(x2[0], x2[1], x2[2]), mk3(x3[0], x3[1], x3[2]),
+                      X0[0], X0[1], X1[0], X1[1], X2[0], X2[1], X3[0], X3[1], beta, dhh, c);
+}
+struct CollectFace {
+    double *K, *f, *t8;   // K: 6 x 9: aa,bb,cc,ab,ac,bc
+    void diag(int i, const sym3 &S) { double *d = K + 9 * i; d[0] = S.xx; d[1] = S.xy; d[2] = S.xz; d[3] = S.xy; d[4] = S.yy; d[5] = S.yz; d[6] = S.xz; d[7] = S.yz; d[8] = S.zz; }
+    void off(int k, const blk3 &B) { for (int q = 0; q < 9; ++q) K[9 * (3 + k) + q] = B.m[q]; }
+    void force(int i, v3 v) { f[3 * i] = v.x; f[3 * i + 1] = v.y; f[3 * i + 2] = v.z; }
+    void mass(double m) { *t8 = m; }
+};
+void hostmath_face_tile(const double *xa, const double *xb, const double *xc, const double *Xa, const double *Xb,
+                        const double *Xc, double e, double nu, double rho, const double *g, double dhh,
+                        double *f9, double *t8, double *K6x9) {
+    CollectFace c{K6x9, f9, t8};
+    face_element_tile(mk3(xa[0], xa[1], xa[2]), mk3(xb[0], xb[1], xb[2]), mk3(xc[0], xc[1], xc[2]), Xa[0], Xa[1], Xb[0], Xb[1],
+                      Xc[0], Xc[1], membrane_mu(e, nu), membrane_lambda(e, nu), rho, mk3(g[0], g[1], g[2]), dhh, c);
+}
+
+// ---- host emulation of the "tiles" kernel: same plan builder (forces_plan.h), same per-thread phases (tile_exec.cuh),
+// threads run one after the other, the barrier between the phases is the loop boundary.
+struct HmPlan {
+    int32_t N, F, Ei;
+    std::vector<int32_t> fn, ie;
+    Pattern pat;
+    tiles::Plan tp;
+};
+void *hm_plan_create(int32_t N, int32_t F, const int32_t *fn, int32_t E, const int32_t *es, const double *X_hint, int dedup, char *err, int errlen) {
+    HmPlan *P = new HmPlan;
+    P->N = N; P->F = F;
+    P->fn.assign(fn, fn + 3 * (size_t)F);
+    if (!extract_interior_edges(N, E, es, P->ie)) { snprintf(err, errlen, "bad stencil"); delete P; return nullptr; }
+    P->Ei = (int32_t)(P->ie.size() / 4);
+    build_pattern(N, F, P->fn.data(), P->Ei, P->ie.data(), P->pat);
+    if (!tiles::build(N, F, P->fn.data(), P->Ei, P->ie.data(), P->pat, X_hint, dedup != 0, P->tp)) {
+        snprintf(err, errlen, "%s", P->tp.error.c_str());
+        delete P;
+        return nullptr;
+    }
+    return P;
+}
+void hm_plan_destroy(void *p) { delete (HmPlan *)p; }
+// info: nnzM, nnzK, n_tiles, n_templates, elem_evals, geo bytes, template bytes, max scratch doubles, max loc
+void hm_plan_info(void *p, int64_t *info) {
+    HmPlan *P = (HmPlan *)p;
+    info[0] = 9 * P->pat.nblkM; info[1] = 9 * P->pat.nblkK; info[2] = P->tp.n_tiles; info[3] = P->tp.n_templates; info[4] = P->tp.elem_evals;
+    info[5] = (int64_t)P->tp.geo.size() * 4; info[6] = (int64_t)P->tp.tmpl.size() * 4; info[7] = P->tp.max_scratch; info[8] = P->tp.max_loc;
+    info[9] = P->Ei;
+}
+void hm_plan_pattern(void *p, int which, int32_t *outer, int32_t *inner) {
+    HmPlan *P = (HmPlan *)p;
+    std::vector<int32_t> o, in;
+    build_eigen_arrays(P->N, which ? P->pat.blkptrK : P->pat.blkptrM, which ? P->pat.nbrK : P->pat.nbrM, o, in);
+    memcpy(outer, o.data(), o.size() * 4);
+    if (!in.empty()) memcpy(inner, in.data(), in.size() * 4);
+}
+void hm_plan_fill(void *p, const double *x, const double *X, const double *mat6, const double *grav, double h, double *f, double *Mv, double *Kv) {
+    HmPlan *P = (HmPlan *)p;
+    tiles::FillParams prm;
+    prm.mu = membrane_mu(mat6[1], mat6[2]); prm.lam = membrane_lambda(mat6[1], mat6[2]); prm.rho = mat6[0]; prm.beta = mat6[3];
+    prm.gx = grav[0]; prm.gy = grav[1]; prm.gz = grav[2]; prm.dhh = mat6[5] * h * h;
+    std::vector<double> scr(P->tp.max_scratch + 16, 0.0), xs(3 * (size_t)P->tp.max_loc + 4), Xs(2 * (size_t)P->tp.max_loc + 4);
+    for (int32_t t = 0; t < P->tp.n_tiles; ++t) {
+        const uint32_t *geo = P->tp.geo.data() + (size_t)t * P->tp.max_geo16 * 4;
+        const int nOwn = geo[1] & 255, nLoc = (geo[1] >> 8) & 255;
+        const uint32_t *loc = geo + 4 + 4 * nOwn;
+        for (int l = 0; l < nLoc; ++l) {
+            for (int k = 0; k < 3; ++k) xs[3 * l + k] = x[3 * (size_t)loc[l] + k];
+            for (int k = 0; k < 2; ++k) Xs[2 * l + k] = X[2 * (size_t)loc[l] + k];
+        }
+        for (auto &v : scr) v = 1e300;   // poison: a pull from an unparked slot shows up immediately
+        for (int z = 0; z < tiles::ZPAD; ++z) scr[z] = 0.0;   // the zero block the padded pull lists point at
+        tiles::TileView V;
+        V.geo = geo; V.tmpl = P->tp.tmpl.data() + (size_t)geo[0] * 4; V.tmplB = V.tmpl + (size_t)(geo[2] & 0xffffu) * 4;
+        V.xs = xs.data(); V.Xs = Xs.data(); V.scr = scr.data();
+        std::vector<double> kst(P->tp.max_kstage + 2, 1e300), mst(P->tp.max_mstage + 2, 1e300), fst(3 * tiles::MAX_OWN, 1e300);
+        V.kst = kst.data(); V.mst = mst.data(); V.fst = fst.data();
+        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase1(tid, V, prm);
+        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase2(tid, tiles::NTHREADS, V);
+        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::copy_out(tid, tiles::NTHREADS, V, f, Mv, Kv);
+    }
 }
 }

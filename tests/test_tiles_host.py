@@ -1,0 +1,128 @@
+"""The "tiles" Forces::fill pipeline WITHOUT a GPU: the plan builder (csrc/forces_plan.h) and the two per-thread phases
+(csrc/tile_exec.cuh) are the same source the CUDA kernel compiles; here they are compiled for the host and the threads of a
+tile run one after the other (tests/hostmath/hostmath.cpp).  Checked against the oracle to the GPU tolerance (1e-10)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import eol_cloth_b200 as E
+from util import assert_close_tol, block_row_scale
+
+MAT = E.Material.DEFAULT
+GRAV = (0.0, 0.0, -9.8)
+H = 0.5e-2
+ip = ctypes.POINTER(ctypes.c_int32)
+dp = ctypes.POINTER(ctypes.c_double)
+lp = ctypes.POINTER(ctypes.c_int64)
+
+
+class HostTiles:
+    def __init__(self, L, N, fn, es, X_hint=None, dedup=True):
+        self.L = L
+        L.hm_plan_create.restype = ctypes.c_void_p
+        L.hm_plan_create.argtypes = [ctypes.c_int32, ctypes.c_int32, ip, ctypes.c_int32, ip, dp, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+        L.hm_plan_destroy.argtypes = [ctypes.c_void_p]
+        L.hm_plan_info.argtypes = [ctypes.c_void_p, lp]
+        L.hm_plan_pattern.argtypes = [ctypes.c_void_p, ctypes.c_int, ip, ip]
+        L.hm_plan_fill.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, ctypes.c_double, dp, dp, dp]
+        fn = np.ascontiguousarray(fn, np.int32).reshape(-1, 3)
+        es = np.ascontiguousarray(es, np.int32).reshape(-1, 4)
+        err = ctypes.create_string_buffer(256)
+        xh = None if X_hint is None else np.ascontiguousarray(X_hint, np.float64)
+        self.h = L.hm_plan_create(N, len(fn), fn.ctypes.data_as(ip), len(es), es.ctypes.data_as(ip),
+                                  None if xh is None else xh.ctypes.data_as(dp), int(dedup), err, 256)
+        if not self.h:
+            raise RuntimeError(err.value.decode())
+        info = np.zeros(10, np.int64)
+        L.hm_plan_info(self.h, info.ctypes.data_as(lp))
+        self.info = dict(zip("nnzM nnzK n_tiles n_templates elem_evals geo_bytes tmpl_bytes max_scratch max_loc Ei".split(), info.tolist()))
+        self.N = N
+
+    def pattern(self, which):
+        nnz = self.info["nnzK" if which else "nnzM"]
+        o, i = np.zeros(3 * self.N + 1, np.int32), np.zeros(max(nnz, 1), np.int32)
+        self.L.hm_plan_pattern(self.h, which, o.ctypes.data_as(ip), i.ctypes.data_as(ip))
+        return o, i[:nnz]
+
+    def fill(self, x, X, mat=MAT, grav=GRAV, h=H):
+        x = np.ascontiguousarray(x, np.float64); X = np.ascontiguousarray(X, np.float64)
+        f = np.full(3 * self.N, np.nan); Mv = np.full(self.info["nnzM"], np.nan); Kv = np.full(self.info["nnzK"], np.nan)
+        m = np.array(mat, np.float64); g = np.array(grav, np.float64)
+        self.L.hm_plan_fill(self.h, x.ctypes.data_as(dp), X.ctypes.data_as(dp), m.ctypes.data_as(dp), g.ctypes.data_as(dp), h,
+                            f.ctypes.data_as(dp), Mv.ctypes.data_as(dp), Kv.ctypes.data_as(dp))
+        return f, Mv, Kv
+
+    def close(self):
+        self.L.hm_plan_destroy(self.h)
+
+
+def _check(T, fn, es, x, X, oracle, what, mat=MAT, grav=GRAV, h=H):
+    f, Mv, Kv = T.fill(x, X, mat, grav, h)
+    assert not np.isnan(f).any() and not np.isnan(Mv).any() and not np.isnan(Kv).any(), what + ": an output slot was never written"
+    ref = oracle.forces_fill(fn, es, x, X, tuple(mat), grav, h)
+    N = x.shape[0]
+    assert_close_tol(f, ref["f"], max(np.abs(ref["f"]).max(), 1e-300), 1e-10, what + " f")
+    for name, which, got in (("M", 0, Mv), ("MDK", 1, Kv)):
+        o, i, v = ref[name]
+        po, pi = T.pattern(which)
+        assert np.array_equal(po, o) and np.array_equal(pi, i), what + f" {name} pattern"
+        assert_close_tol(got, v, block_row_scale(o, v, N), 1e-10, what + f" {name} values")
+    return f, Mv, Kv
+
+
+@pytest.mark.parametrize("gen,n,hint,dedup", [("regular2", 2, True, True), ("regular2", 3, True, True), ("build4", 3, True, False),
+                                              ("regular2", 17, True, True), ("build4", 9, False, True), ("regular2", 40, True, True),
+                                              ("regular2", 33, False, False)])
+def test_tiles_host_matches_oracle(oracle, hostmath, gen, n, hint, dedup):
+    X, fn = getattr(E.meshgen, gen)(n)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    x = E.meshgen.drape_state(X, seed=n)
+    T = HostTiles(hostmath, X.shape[0], fn, es, X if hint else None, dedup)
+    _check(T, fn, es, x, X, oracle, f"{gen}{n}")
+    assert T.info["elem_evals"] >= len(fn) + T.info["Ei"]
+    T.close()
+
+
+def test_tiles_host_dedup_and_tiling_quality(hostmath):
+    """A 128x128 regular sheet: 8x4-node tiles, interior tiles share one template, halo re-evaluation stays below 1.6x."""
+    X, fn = E.meshgen.regular2(128)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    T = HostTiles(hostmath, X.shape[0], fn, es, X, True)
+    i = T.info
+    assert i["n_tiles"] == 128 * 128 // 32
+    assert i["n_templates"] < 60, i
+    assert i["elem_evals"] < 1.6 * (len(fn) + i["Ei"]), i
+    assert i["max_scratch"] * 8 <= 160 * 1024
+    T2 = HostTiles(hostmath, X.shape[0], fn, es, X, False)
+    assert T2.info["n_templates"] == T2.info["n_tiles"]
+    x = E.meshgen.drape_state(X, seed=1)
+    a, b = T.fill(x, X), T2.fill(x, X)
+    for u, v in zip(a, b):
+        assert u.tobytes() == v.tobytes()      # templates are an encoding detail: bit-identical results
+    T.close(); T2.close()
+
+
+def test_tiles_host_shuffled_isolated_material(oracle, hostmath):
+    X, fn = E.meshgen.regular2(9)
+    rng = np.random.default_rng(11)
+    N = X.shape[0] + 1
+    perm = rng.permutation(N)
+    Xn = np.zeros((N, 2)); Xn[perm[:-1]] = X; Xn[perm[-1]] = (5.0, 5.0)
+    fnn = perm[fn].astype(np.int32)
+    fnn = fnn[rng.permutation(len(fnn))]
+    es = E.meshgen.edge_stencils(N, fnn)
+    x = E.meshgen.drape_state(Xn, seed=2)
+    T = HostTiles(hostmath, N, fnn, es, Xn, True)
+    mat = E.Material(0.2, 1000.0, 0.3, 1e-3, 0.0, 0.7)
+    f, _, _ = _check(T, fnn, es, x * 1.3, Xn, oracle, "shuffled", mat, (0.1, -0.2, -9.8), 1e-2)
+    assert np.all(f[3 * perm[-1]:3 * perm[-1] + 3] == 0)
+    T.close()
+
+
+def test_tiles_host_rejects_nonmanifold(hostmath):
+    # two faces glued along an edge AND sharing the opposite vertex: the bending stencil repeats a node
+    fn = np.array([[0, 1, 2], [1, 0, 2]], np.int32)
+    es = np.array([[0, 1, 2, 2]], np.int32)
+    with pytest.raises(RuntimeError):
+        HostTiles(hostmath, 3, fn, es, None, True)
