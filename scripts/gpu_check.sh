@@ -11,6 +11,7 @@ timeout 600 python bench.py --steps 20 --warmup 5 > $OUT/bench.json 2> $OUT/benc
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "bench ref rc=$?"
 timeout 600 python bench.py --workload ensemble64 --steps 10 --warmup 3 --no-cpu --no-cd > $OUT/bench_ens.json 2> $OUT/bench_ens.err; echo "ens rc=$?"
 timeout 600 python bench.py --workload sheet256 --steps 50 --warmup 5 --no-cpu --no-cd > $OUT/bench_256.json 2> $OUT/bench_256.err; echo "256 rc=$?"
+EOLC_FORCES_PIPELINE=rows timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-cd > $OUT/bench_rows.json 2> $OUT/bench_rows.err; echo "rows A/B rc=$?"
 # launch list of the same bench command (cold-cache, serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
