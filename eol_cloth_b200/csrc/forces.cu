@@ -54,6 +54,10 @@ struct eolc_forces_plan {
     // staging for the host entry point
     DevBuf<double> d_x, d_X, d_f, d_Mv, d_Kv;
     PinnedBuf<double> p_in, p_out;
+#ifdef EOLC_TILE_CLOCKS
+    DevBuf<unsigned long long> d_dbg;
+    int dbg_grid = 0;
+#endif
 };
 
 namespace {
@@ -73,9 +77,10 @@ __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_grou
 
 // Shared memory: [scr: parked element blocks][staged MDK rows][staged M rows][staged f][template A x 2][template B]
 // [geometry x 4][x x 2][X x 2]; work item w = scene * n_tiles + tile.
-//   at the start of tile k:  geometry(k+2), template A(k+1), the x / X gathers of tile k+1 and template B(k) are issued
-//                            (cp.async, one group)
-//   phase 1(k)  ->  wait group + barrier  ->  phase 2(k)  ->  barrier  ->  copy-out(k), which overlaps phase 1(k+1) of faster warps
+//   at the start of tile k:  geometry(k+2), template A(k+1) and B(k) (only if they differ from the resident ones), and the
+//                            x / X gathers of tile k+1 are issued (cp.async, one group)
+//   phase 1(k) -> wait (inputs landed, bulk copy-out(k-1) has read its staging) + barrier -> phase 2(k) -> proxy fence + barrier
+//   -> one warp issues the bulk copies of tile k's staged runs (cp.async.bulk shared -> global); they drain during phase 1(k+1)
 struct TilesSmem {
     uint32_t scr, kst, mst, fst, tmplA, tmplB, geo, x, X, total;   // byte offsets
 };
@@ -84,7 +89,8 @@ __host__ __device__ inline TilesSmem tiles_smem_layout(uint32_t scr_doubles, uin
     TilesSmem L;
     uint32_t o = 0;
     auto take = [&](uint32_t bytes) { uint32_t at = o; o += (bytes + 15u) & ~15u; return at; };
-    L.scr = take(8 * scr_doubles); L.kst = take(8 * kstage); L.mst = take(8 * mstage); L.fst = take(8 * 3 * tiles::MAX_OWN);
+    // + 2 doubles per staging array: the arrays are shifted by the 16-byte phase of the scene's output pointers
+    L.scr = take(8 * scr_doubles); L.kst = take(8 * (kstage + 2)); L.mst = take(8 * (mstage + 2)); L.fst = take(8 * (tiles::MAX_FSTAGE + 2));
     L.tmplA = take(2 * 16 * tmplA16); L.tmplB = take(16 * tmplB16); L.geo = take(4 * 16 * geo16);
     L.x = take(2 * 8 * 3 * loc_max); L.X = take(2 * 8 * 2 * loc_max);
     L.total = o;
@@ -92,18 +98,40 @@ __host__ __device__ inline TilesSmem tiles_smem_layout(uint32_t scr_doubles, uin
 }
 
 struct TilesArgs {
-    long long n_work;
-    int n_tiles;
+    uint32_t n_work, n_tiles, step_q, step_r;   // step = gridDim.x = step_q * n_tiles + step_r
     uint32_t geo16, tmplA16, tmplB16, loc_max, scr_doubles, kstage, mstage;
     const uint4 *geo, *tmpl;
     const double *x, *X;
     double *f, *Mv, *Kv;
     size_t x_stride, X_stride, f_stride, M_stride, K_stride;
     tiles::FillParams prm;
+#ifdef EOLC_TILE_CLOCKS
+    unsigned long long *dbg;   // per (CTA, warp): clocks spent in [prefetch issue, phase 1, wait+barrier, phase 2, barrier, copy-out], tiles
+#endif
 };
+#ifdef EOLC_TILE_CLOCKS
+#define EOLC_CLK(i) { const long long now_ = clock64(); clk_acc[i] += now_ - clk_last; clk_last = now_; }
+// a barrier whose completion the NEXT instruction depends on (a plain __syncthreads() defers the blocking, which would move the wait
+// into whatever region follows)
+#define EOLC_SYNC() { if (__syncthreads_or(0)) clk_acc[6] += 1000000; }
+#else
+#define EOLC_CLK(i)
+#define EOLC_SYNC() __syncthreads()
+#endif
+
+struct BulkStore {   // one asynchronous bulk copy shared -> global; both addresses and the size are multiples of 16 bytes
+    __device__ __forceinline__ void operator()(double *dst, const double *src, uint32_t bytes) const {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    }
+};
+
+// Register budget: the kernel is launched with 384 threads (ptxas cap 168 registers); the two compute warpgroups then take 216
+// registers per thread and the service warpgroup drops to 64 (setmaxnreg): the pool is the CTA's own 384 x 168 allocation, and 256 x 216 + 128 x 64 = 63488 fits it.
+constexpr int COMPUTE_REGS = 216, SERVICE_REGS = 64;
 
 __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemble_tiles_kernel(const __grid_constant__ TilesArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t ctl[2];          // service -> compute warps: [0] template A buffer of the NEXT tile, [1] m_full of the current tile
     const TilesSmem L = tiles_smem_layout(A.scr_doubles, A.kstage, A.mstage, A.tmplA16, A.tmplB16, A.geo16, A.loc_max);
     double *scr = reinterpret_cast<double *>(smem_raw + L.scr);
     uint4 *TAst = reinterpret_cast<uint4 *>(smem_raw + L.tmplA);
@@ -111,82 +139,171 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
     uint4 *Gst = reinterpret_cast<uint4 *>(smem_raw + L.geo);
     double *xst = reinterpret_cast<double *>(smem_raw + L.x);
     double *Xst = reinterpret_cast<double *>(smem_raw + L.X);
-    const int tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t geo16 = A.geo16, tmplA16 = A.tmplA16, loc_max = A.loc_max;
-    const int n_tiles = A.n_tiles;
-    constexpr int NT = tiles::CTA_THREADS;
+    const uint32_t n_tiles = A.n_tiles, n_work = A.n_work, step = gridDim.x;
+    constexpr uint32_t NC = tiles::NTHREADS, NCW = NC / 32;   // compute threads / warps; warps NCW .. NCW+3 are the service warpgroup
     constexpr int GSTAGES = 4;
 
-    auto load_geo = [&](long long w, int stage) {
-        const uint4 *src = A.geo + (size_t)(w % n_tiles) * geo16;
-        for (uint32_t i = tid; i < geo16; i += NT) cp16(Gst + (size_t)stage * geo16 + i, src + i);
+    auto geo_hdr = [&](int stage) { return reinterpret_cast<const uint32_t *>(Gst + (uint32_t)stage * geo16); };
+    // work items of this CTA: w = blockIdx.x + k * step; (tile, scene) advance without divisions
+    auto advance = [&](uint32_t &tile, uint32_t &scene) {
+        tile += A.step_r; scene += A.step_q;
+        if (tile >= n_tiles) { tile -= n_tiles; ++scene; }
     };
-    auto load_tmplA = [&](int gstage, int tstage) {
-        const uint32_t *g = reinterpret_cast<const uint32_t *>(Gst + (size_t)gstage * geo16);
-        const uint4 *src = A.tmpl + g[0];
-        const uint32_t n = g[2] & 0xffffu;
-        for (uint32_t i = tid; i < n; i += NT) cp16(TAst + (size_t)tstage * tmplA16 + i, src + i);
-    };
-    auto load_tmplB = [&](int gstage) {
-        const uint32_t *g = reinterpret_cast<const uint32_t *>(Gst + (size_t)gstage * geo16);
-        const uint4 *src = A.tmpl + g[0] + (g[2] & 0xffffu);
-        const uint32_t n = g[2] >> 16;
-        for (uint32_t i = tid; i < n; i += NT) cp16(TBst + i, src + i);
-    };
-    auto gather = [&](long long w, int gstage, int xstage) {
-        const uint32_t *g = reinterpret_cast<const uint32_t *>(Gst + (size_t)gstage * geo16);
-        const uint32_t nOwn = g[1] & 255u, nLoc = (g[1] >> 8) & 255u;
-        const uint32_t *loc = g + 4 + 4 * nOwn;
-        const size_t sc = (size_t)(w / n_tiles);
-        const double *xs = A.x + sc * A.x_stride, *Xs = A.X + sc * A.X_stride;
-        double *xd = xst + (size_t)xstage * 3 * loc_max, *Xd = Xst + (size_t)xstage * 2 * loc_max;
-        for (uint32_t i = tid; i < 4 * nLoc; i += NT) {
-            const uint32_t l = i >> 2, part = i & 3u;
-            const size_t gid = loc[l];
-            if (part < 3) cp8(xd + 3 * l + part, xs + 3 * gid + part);
-            else cp16(Xd + 2 * l, Xs + 2 * gid);
-        }
-    };
-
-    const long long w0 = blockIdx.x, step = gridDim.x;
-    if (w0 >= A.n_work) return;
-    if (tid < tiles::ZPAD) scr[tid] = 0.0;   // the zero block padded pull lists point at (never written again)
-    load_geo(w0, 0);
-    if (w0 + step < A.n_work) load_geo(w0 + step, 1);
-    cp_commit(); cp_wait_all();
-    __syncthreads();
-    load_tmplA(0, 0);
-    gather(w0, 0, 0);
-    cp_commit(); cp_wait_all();
-    __syncthreads();
+    if (blockIdx.x >= n_work) return;
+    uint32_t w = blockIdx.x;
+    uint32_t tile0 = w % n_tiles, scene0 = w / n_tiles;      // once per CTA
     tiles::TileView V;
     V.scr = scr;
-    V.kst = reinterpret_cast<double *>(smem_raw + L.kst);
-    V.mst = reinterpret_cast<double *>(smem_raw + L.mst);
-    V.fst = reinterpret_cast<double *>(smem_raw + L.fst);
     V.tmplB = reinterpret_cast<const uint32_t *>(TBst);
-    int gs = 0, ts = 0;
-    for (long long w = w0; w < A.n_work; w += step) {
-        const int gs1 = (gs + 1) & (GSTAGES - 1), gs2 = (gs + 2) & (GSTAGES - 1);
-        // stage reuse: geometry(k+2) overwrites the stage of tile k-2 (copy-out(k-2) finished before the barriers of tile k-1);
-        // template B(k) overwrites B(k-1), last read in phase 2(k-1), i.e. before the barrier every thread has passed
-        if (w + 2 * step < A.n_work) load_geo(w + 2 * step, gs2);
-        if (w + step < A.n_work) { load_tmplA(gs1, ts ^ 1); gather(w + step, gs1, ts ^ 1); }
-        load_tmplB(gs);
-        cp_commit();
-        V.geo = reinterpret_cast<const uint32_t *>(Gst + (size_t)gs * geo16);
-        V.tmpl = reinterpret_cast<const uint32_t *>(TAst + (size_t)ts * tmplA16);
-        V.xs = xst + (size_t)ts * 3 * loc_max;
-        V.Xs = Xst + (size_t)ts * 2 * loc_max;
-        tiles::phase1(tid, V, A.prm);
-        cp_wait_all();
-        __syncthreads();                 // elements parked, staged inputs landed, previous copy-out done
-        tiles::phase2(tid, NT, V);
-        __syncthreads();                 // staged rows complete; the scratch may be overwritten by the next phase 1
-        const size_t sc = (size_t)(w / n_tiles);
-        tiles::copy_out(tid, NT, V, A.f + sc * A.f_stride, A.Mv + sc * A.M_stride, A.Kv + sc * A.K_stride);
-        gs = gs1; ts ^= 1;
+    double *const kst16 = reinterpret_cast<double *>(smem_raw + L.kst), *const mst16 = reinterpret_cast<double *>(smem_raw + L.mst),
+                 *const fst16 = reinterpret_cast<double *>(smem_raw + L.fst);
+    int gs = 0, ta = 0, xs_ = 0;
+#ifdef EOLC_TILE_CLOCKS
+    long long clk_acc[7] = {0, 0, 0, 0, 0, 0, 0}, clk_last = clock64();
+#endif
+    auto set_view = [&](double *fs, double *Ms, double *Ks) {
+        V.geo = geo_hdr(gs);
+        V.tmpl = reinterpret_cast<const uint32_t *>(TAst + (uint32_t)ta * tmplA16);
+        V.xs = xst + (uint32_t)xs_ * 3 * loc_max;
+        V.Xs = Xst + (uint32_t)xs_ * 2 * loc_max;
+        V.kst = kst16 + ((uint32_t)(reinterpret_cast<uintptr_t>(Ks) >> 3) & 1u);
+        V.mst = mst16 + ((uint32_t)(reinterpret_cast<uintptr_t>(Ms) >> 3) & 1u);
+        V.fst = fst16 + ((uint32_t)(reinterpret_cast<uintptr_t>(fs) >> 3) & 1u);
+    };
+
+    if (warp >= NCW) {
+        // =============================== service warpgroup ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(SERVICE_REGS));
+        const uint32_t role = warp - NCW;    // 0: geometry / template blobs + control words, 1: x / X gathers, 2 and 3: bulk copy-out
+        auto load_geo = [&](uint32_t tile, int stage) {
+            const uint4 *src = A.geo + (size_t)tile * geo16;
+            uint4 *dst = Gst + (uint32_t)stage * geo16;
+            for (uint32_t i = lane; i < geo16; i += 32) cp16(dst + i, src + i);
+        };
+        auto load_tmplA = [&](int gstage, int tstage) {
+            const uint32_t *g = geo_hdr(gstage);
+            const uint4 *src = A.tmpl + g[0];
+            uint4 *dst = TAst + (uint32_t)tstage * tmplA16;
+            const uint32_t n = g[2] & 0xffffu;
+            for (uint32_t i = lane; i < n; i += 32) cp16(dst + i, src + i);
+        };
+        auto load_tmplB = [&](int gstage) {
+            const uint32_t *g = geo_hdr(gstage);
+            const uint4 *src = A.tmpl + g[0] + (g[2] & 0xffffu);
+            const uint32_t n = g[2] >> 16;
+            for (uint32_t i = lane; i < n; i += 32) cp16(TBst + i, src + i);
+        };
+        auto gather = [&](uint32_t scene, int gstage, int xstage) {
+            const uint32_t *g = geo_hdr(gstage);
+            const uint32_t nLoc = (g[1] >> 8) & 255u;
+            const uint32_t *loc = g + 4;
+            const double *xs = A.x + (size_t)scene * A.x_stride, *Xs = A.X + (size_t)scene * A.X_stride;
+            double *xd = xst + (uint32_t)xstage * 3 * loc_max, *Xd = Xst + (uint32_t)xstage * 2 * loc_max;
+            for (uint32_t l = lane; l < nLoc; l += 32) {
+                const size_t gid = loc[l];
+                cp8(xd + 3 * l, xs + 3 * gid); cp8(xd + 3 * l + 1, xs + 3 * gid + 1); cp8(xd + 3 * l + 2, xs + 3 * gid + 2);
+                cp16(Xd + 2 * l, Xs + 2 * gid);
+            }
+        };
+        uint32_t tile1 = tile0, scene1 = scene0;
+        advance(tile1, scene1);
+        uint32_t tile2 = tile1, scene2 = scene1;
+        advance(tile2, scene2);
+        if (role == 0) {
+            load_geo(tile0, 0);
+            if (w + step < n_work) load_geo(tile1, 1);
+            cp_commit(); cp_wait_all();
+            __syncwarp();
+            load_tmplA(0, 0);
+            gather(scene0, 0, 0);
+            cp_commit(); cp_wait_all();
+        }
+        __syncthreads();                 // [P] first tile staged
+        // role 0 state: template held by A buffer 0 / 1 and by the B buffer; template / pointer phase the M staging zeros belong to
+        uint32_t tA_id0 = geo_hdr(0)[0], tA_id1 = 0xffffffffu, tB_id = 0xffffffffu, tM_id = 0xffffffffu, tM_pb = 2;
+        for (; w < n_work; w += step) {
+            const int gs1 = (gs + 1) & (GSTAGES - 1), gs2 = (gs + 2) & (GSTAGES - 1);
+            double *const fs = A.f + (size_t)scene0 * A.f_stride, *const Ms = A.Mv + (size_t)scene0 * A.M_stride, *const Ks = A.Kv + (size_t)scene0 * A.K_stride;
+            int ta1 = ta;
+            if (role == 0) {
+                // stage reuse: geometry(k+2) overwrites the stage of tile k-2 (its copy-out was issued before the barriers of tile k-1);
+                // template B(k) overwrites B(k-1), last read in phase 2(k-1), i.e. before a barrier every thread has passed
+                const uint32_t pbM = (uint32_t)(reinterpret_cast<uintptr_t>(Ms) >> 3) & 1u;
+                if (w + 2 * step < n_work) load_geo(tile2, gs2);
+                if (w + step < n_work) {
+                    const uint32_t id1 = geo_hdr(gs1)[0];
+                    if (id1 != (ta ? tA_id1 : tA_id0)) {
+                        ta1 = ta ^ 1;
+                        if (id1 != (ta1 ? tA_id1 : tA_id0)) { load_tmplA(gs1, ta1); if (ta1) tA_id1 = id1; else tA_id0 = id1; }
+                    }
+                }
+                const uint32_t id0 = geo_hdr(gs)[0];
+                if (id0 != tB_id) { load_tmplB(gs); tB_id = id0; }
+                cp_commit();
+                if (lane == 0) { ctl[0] = (uint32_t)ta1; ctl[1] = (id0 != tM_id || pbM != tM_pb) ? 1u : 0u; }
+                tM_id = id0; tM_pb = pbM;
+                cp_wait_all();
+            } else if (role == 1) {
+#ifndef EOLC_DEBUG_NO_GATHER
+                if (w + step < n_work) gather(scene1, gs1, xs_ ^ 1);
+#endif
+                cp_commit(); cp_wait_all();
+            } else {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // copy-out(k-1) has read its staging
+            }
+            EOLC_CLK(0)
+            EOLC_SYNC();                 // [B1] elements parked, staged inputs landed, staging free
+            EOLC_CLK(2)
+            ta1 = (int)ctl[0];
+            EOLC_SYNC();                 // [B2] staged rows complete
+            EOLC_CLK(4)
+#ifndef EOLC_DEBUG_NO_COPYOUT
+            if (role >= 2) {
+                set_view(fs, Ms, Ks);
+                tiles::copy_out_runs((int)(2 * lane + (role - 2)), 64, V, fs, Ms, Ks, BulkStore());
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+#endif
+            EOLC_CLK(5)
+#ifdef EOLC_TILE_CLOCKS
+            clk_acc[6] += 1;
+#endif
+            gs = gs1; ta = ta1; xs_ ^= 1;
+            tile0 = tile1; scene0 = scene1; tile1 = tile2; scene1 = scene2;
+            advance(tile2, scene2);
+        }
+        if (role >= 2) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last bulk copies
+    } else {
+        // =============================== compute warpgroups ===============================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(COMPUTE_REGS));
+        if (tid < tiles::ZPAD) scr[tid] = 0.0;   // the zero block padded pull entries point at (never written again)
+        __syncthreads();                 // [P]
+        for (; w < n_work; w += step) {
+            double *const fs = A.f + (size_t)scene0 * A.f_stride, *const Ms = A.Mv + (size_t)scene0 * A.M_stride, *const Ks = A.Kv + (size_t)scene0 * A.K_stride;
+            set_view(fs, Ms, Ks);
+            tiles::phase1((int)tid, V, A.prm);
+            EOLC_CLK(1)
+            EOLC_SYNC();                 // [B1]
+            EOLC_CLK(2)
+            const int ta1 = (int)ctl[0];
+            tiles::phase2((int)tid, (int)NC, V, ctl[1] != 0u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk-copy engine
+            EOLC_CLK(3)
+            EOLC_SYNC();                 // [B2] the scratch may be overwritten by the next phase 1
+            EOLC_CLK(4)
+#ifdef EOLC_TILE_CLOCKS
+            clk_acc[6] += 1;
+#endif
+            gs = (gs + 1) & (GSTAGES - 1); ta = ta1; xs_ ^= 1;
+            advance(tile0, scene0);
+        }
     }
+#ifdef EOLC_TILE_CLOCKS
+    if (lane == 0)
+        for (int i = 0; i < 7; ++i) A.dbg[((size_t)blockIdx.x * (tiles::CTA_THREADS / 32) + warp) * 7 + i] = (unsigned long long)clk_acc[i];
+#endif
 }
 
 size_t tiles_smem_bytes(const eolc_forces_plan *P) {
@@ -208,7 +325,7 @@ int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st)
     P->kstage = (tp.max_kstage + 1) & ~1u; P->mstage = (tp.max_mstage + 1) & ~1u;
     P->elem_evals = tp.elem_evals;
     P->geo_bytes = (int64_t)tp.geo.size() * 4; P->tmpl_bytes = (int64_t)tp.tmpl.size() * 4;
-    if (tiles_smem_bytes(P) > (size_t)(tiles::CTAS_PER_SM == 1 ? 227 : 113) * 1024) { set_error("tile plan needs %zu bytes of shared memory", tiles_smem_bytes(P)); return EOLC_ERR_UNSUPPORTED; }
+    if (tiles_smem_bytes(P) > (size_t)227 * 1024) { set_error("tile plan needs %zu bytes of shared memory", tiles_smem_bytes(P)); return EOLC_ERR_UNSUPPORTED; }
     static_assert(sizeof(uint4) == 16, "uint4");
     EOLC_CUDA(P->d_geo.alloc(tp.geo.size() / 4));
     EOLC_CUDA(P->d_tmpl.alloc(tp.tmpl.size() / 4));
@@ -607,7 +724,9 @@ int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X
     if (P->N == 0) return EOLC_OK;
     if (P->pipeline == 0) {
         EOLC_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0, "x must be 8-byte and X 16-byte aligned");
+        EOLC_REQUIRE(((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(Mv) | reinterpret_cast<uintptr_t>(Kv)) & 7) == 0, "outputs must be 8-byte aligned");
         const long long n_work = (long long)P->n_tiles * S;
+        EOLC_REQUIRE(n_work < (1ll << 31), "too many (scene, tile) work items for one launch");
         const int grid = (int)std::min<long long>(n_work, (long long)P->ctx->sm_count * tiles::CTAS_PER_SM);
         const size_t smem = tiles_smem_bytes(P);
         if (!P->smem_attr_set) {
@@ -615,12 +734,18 @@ int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X
             P->smem_attr_set = true;
         }
         TilesArgs A;
-        A.n_work = n_work; A.n_tiles = P->n_tiles; A.geo16 = P->geo16; A.tmplA16 = P->tmplA16; A.tmplB16 = P->tmplB16; A.loc_max = P->loc_max;
+        A.n_work = (uint32_t)n_work; A.n_tiles = (uint32_t)P->n_tiles; A.step_q = (uint32_t)grid / (uint32_t)P->n_tiles; A.step_r = (uint32_t)grid % (uint32_t)P->n_tiles;
+        A.geo16 = P->geo16; A.tmplA16 = P->tmplA16; A.tmplB16 = P->tmplB16; A.loc_max = P->loc_max;
         A.scr_doubles = P->scr_doubles; A.kstage = P->kstage; A.mstage = P->mstage; A.geo = P->d_geo.p; A.tmpl = P->d_tmpl.p; A.x = x; A.X = X;
         A.f = f; A.Mv = Mv; A.Kv = Kv; A.x_stride = (size_t)3 * P->N; A.X_stride = (size_t)2 * P->N; A.f_stride = (size_t)P->dof;
         A.M_stride = (size_t)P->nnzM; A.K_stride = (size_t)P->nnzK;
         A.prm.mu = membrane_mu(mat->e, mat->nu); A.prm.lam = membrane_lambda(mat->e, mat->nu); A.prm.rho = mat->density; A.prm.beta = mat->beta;
         A.prm.gx = grav[0]; A.prm.gy = grav[1]; A.prm.gz = grav[2]; A.prm.dhh = dhh;
+#ifdef EOLC_TILE_CLOCKS
+        EOLC_CUDA(P->d_dbg.ensure((size_t)grid * (tiles::CTA_THREADS / 32) * 7));
+        P->dbg_grid = grid;
+        A.dbg = P->d_dbg.p;
+#endif
         assemble_tiles_kernel<<<grid, tiles::CTA_THREADS, smem, st>>>(A);
         EOLC_CUDA(cudaGetLastError());
         return EOLC_OK;
@@ -718,6 +843,17 @@ int eolc_forces_counts(const eolc_forces_plan *plan, int32_t *n_faces, int32_t *
     if (n_interior_edges) *n_interior_edges = plan->Ei;
     return EOLC_OK;
 }
+
+#ifdef EOLC_TILE_CLOCKS
+// developer build only (scripts/tile_clocks.py): per (CTA, warp) clock totals of the last fill; returns the number of rows of 7
+int eolc_debug_tile_clocks(eolc_forces_plan *plan, unsigned long long *out, int max_rows) {
+    const int rows = plan->dbg_grid * (tiles::CTA_THREADS / 32);
+    if (rows > max_rows) return -1;
+    cudaStreamSynchronize(plan->ctx->stream);
+    cudaMemcpy(out, plan->d_dbg.p, (size_t)rows * 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    return rows;
+}
+#endif
 
 int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return plan ? 1 : 0; }
 

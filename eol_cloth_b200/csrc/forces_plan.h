@@ -118,27 +118,21 @@ namespace tiles {
 #ifndef EOLC_TILE_OWN
 #define EOLC_TILE_OWN 32
 #endif
-#ifndef EOLC_TILE_CTAS
-#define EOLC_TILE_CTAS 1
-#endif
-#ifndef EOLC_TILE_THREADS
-#define EOLC_TILE_THREADS 256
-#endif
-constexpr int NTHREADS = 256;        // element slots per tile (phase 1 uses the first NTHREADS threads)
-constexpr int CTA_THREADS = EOLC_TILE_THREADS;   // threads per CTA (>= NTHREADS); all of them work in phase 2 and in the prefetch
-constexpr int CTAS_PER_SM = EOLC_TILE_CTAS;
-constexpr int MAX_OWN = EOLC_TILE_OWN;   // nodes owned by a tile (<= 32: 5-bit fields)
+constexpr int NTHREADS = 256;        // compute threads per CTA = element slots per tile (phase 1: stencil warps first, then face warps)
+constexpr int CTA_THREADS = NTHREADS + 128;   // + one service warpgroup: stages the inputs of the tiles ahead, issues the bulk copy-out
+constexpr int CTAS_PER_SM = 1;
+constexpr int MAX_OWN = EOLC_TILE_OWN;   // nodes owned by a tile (<= 63: 6-bit fields)
 constexpr int MAX_LOC = 128;         // distinct nodes referenced by a tile's elements (8-bit local ids)
 constexpr int EDGE_STRIDE = 86;      // doubles parked per bending stencil: 4 diagonal blocks x 6, 6 off-diagonal x 10 (+2: bank spread)
 constexpr int FACE_STRIDE = 62;      // doubles parked per face: 3 x (diag 6 + force 3 + pad) + 3 x (off 9 + pad), t8 in the first pad
 constexpr int FACE_T8 = 39;          // offset of t8 (rho * 2A) inside a face slot
-constexpr int ZPAD = 16;             // doubles at the start of the scratch that stay zero: pull lists are padded to an even length
-                                     // with offset 0, so the pull loops take two contributions per trip without a tail test
-constexpr int MAX_SCRATCH_DOUBLES = CTAS_PER_SM == 1 ? 20480 : 12288;   // 160 KB (96 KB with two CTAs per SM) of parked blocks per tile
-constexpr int MAX_KSTAGE = 4096;     // doubles of MDK rows one tile stages in shared memory before the coalesced copy-out (32 KB)
-constexpr int MAX_MSTAGE = 2304;     // doubles of M rows one tile stages (expanded blocks: m on the block diagonal, explicit zeros off it)
-constexpr int COPY_CHUNK = 256;      // doubles per copy-out chunk of staged MDK rows
-constexpr int MAX_COUNT = 63;        // PAIRS of contributions per loop of one output block (6-bit fields)
+constexpr int ZPAD = 16;             // doubles at the start of the scratch that stay zero: padded pull entries (offset 0) read the zero block
+constexpr int MAX_SCRATCH_DOUBLES = 20480;   // 160 KB of parked blocks per tile
+constexpr int MAX_KSTAGE = 4096 + 2 * MAX_OWN;   // doubles of MDK rows one tile stages in shared memory before the bulk copy-out
+constexpr int MAX_MSTAGE = 2304 + 2 * MAX_OWN;   // doubles of M rows one tile stages (expanded blocks: m on the block diagonal, explicit zeros off it)
+constexpr int MAX_FSTAGE = 4 * MAX_OWN + 4;        // doubles of f one tile stages
+constexpr int MAX_ITER = 255;        // PAIRS of contributions per loop of one phase-2 group (8-bit fields)
+constexpr int GROUP = 32;            // phase-2 records per group (one warp)
 
 // smem offsets (in doubles) of the parked blocks inside an element slot
 inline int edge_diag_off(int i) { return 6 * i; }
@@ -146,34 +140,39 @@ inline int edge_off_off(int lo, int hi) { static const int k[4][4] = {{-1, 0, 1,
 inline int face_diag_off(int v) { return 10 * v; }
 inline int face_off_off(int lo, int hi) { static const int k[3][3] = {{-1, 0, 1}, {0, -1, 2}, {1, 2, -1}}; return 30 + 10 * k[lo][hi]; }
 
-// 64-bit record of one phase-2 work item:
-//   q0:16 first pull entry (even) | c0:6 | c1:6 | p:8 block position in the node's row | own:5 | p2:8 | own2:5 | has2:1 | flag:1
-//   c0 / c1 count PAIRS of pull entries (lists are padded to an even length with offset 0 = the zero block).
-//   D (diagonal MDK block + f): c0 = faces, c1 = stencils.
-//   O (off-diagonal MDK block (own, p)): c0 = contributions parked in this orientation, c1 = parked transposed.  If the
-//     column node is owned by the same tile (has2), the item also writes the mirrored block (own2, p2) = transpose, and the
-//     mirrored pair has no item of its own.
-//   M (mass block): c0 = faces, flag = diagonal block, has2 as for O.
-inline uint64_t pack_rec(unsigned q0, unsigned c0, unsigned c1, unsigned p, unsigned own, unsigned p2, unsigned own2, unsigned has2, unsigned flag) {
-    return (uint64_t)q0 | ((uint64_t)c0 << 16) | ((uint64_t)c1 << 22) | ((uint64_t)p << 28) | ((uint64_t)own << 36) | ((uint64_t)p2 << 41) |
-           ((uint64_t)own2 << 49) | ((uint64_t)has2 << 54) | ((uint64_t)flag << 55);
+// Phase 2 works in GROUPS of 32 records of one kind (one warp per group, one record per lane); every lane of a group runs the
+// group's trip counts (shorter lists are padded with offset 0 = the zero block), so the loops are warp-uniform and the pull
+// entries are stored transposed: entry of (trip r, lane l) at pulls[base + 32 r + l] (conflict-free, two 16-bit offsets each).
+//   kind D (diagonal MDK block + f of an owned node): loop A = face pairs (6 + 3 doubles each), loop B = stencil pairs (6 doubles)
+//   kind O (off-diagonal MDK block (own, p)): loop A = contributions parked in this orientation, loop B = parked transposed.  If the
+//          column node is owned by the same tile (has2) the record also writes the mirrored block (own2, p2) = transpose, and
+//          the mirrored pair has no record of its own.
+//   kind M (mass block): loop A = t8 of the faces shared by the pair; flag = diagonal block (t8/12, else t8/24); has2 as for O.
+// 64-bit record: p:8 | own:6 | p2:8 | own2:6 | has2:1 | flag:1 | valid:1
+inline uint64_t pack_rec(unsigned p, unsigned own, unsigned p2, unsigned own2, unsigned has2, unsigned flag) {
+    return (uint64_t)p | ((uint64_t)own << 8) | ((uint64_t)p2 << 14) | ((uint64_t)own2 << 22) | ((uint64_t)has2 << 28) | ((uint64_t)flag << 29) | (1ull << 30);
 }
+enum { KIND_D = 0, KIND_O = 1, KIND_M = 2 };
 
-// Template header (4 x u32) + items + row sizes (degK | degM << 8 per owned node) + staging offsets (MDK rows | mass scalars
-// << 16 per owned node) + records + pull entries, every part padded to 16 bytes:
-//   w0 = nE | nEpad << 8 | nF << 16     (stencil slots [0, nE), face slots [nEpad, nEpad + nF))
-//   w1 = nD | nDpad << 16               (D records [0, nD), padded to a warp)
-//   w2 = nO | nOpad << 16               (O records [nDpad, nDpad + nO))
-//   w3 = nM | npull16 << 16             (M records [nDpad + nOpad, ... + nM); npull16 = pull entries / 8, rounded up)
-// Geometry header (4 x u32) + (kbase, mbase) int64 pairs per owned node + local->global node table:
-//   w0 = template offset (16-byte units)   w1 = nOwn | nLoc << 8   w2 = size of part A | size of part B << 16 (16-byte units)
-//   w3 = number of copy-out chunks;   ... + the copy-out chunks (see below), offsets and lengths in doubles
+// Template = part A (phase 1) + part B (phase 2), u32 words, every section padded to 16 bytes:
+//   A: [nE | nF << 16, 0, 0, 0] [items: nE stencils (4 local ids, 8 bits each) then nF faces (3 local ids)]
+//      stencil slot s is evaluated by thread s, face slot s by thread roundup32(nE) + s (kinds are warp aligned)
+//   B: [nOwn | nGroups << 8, 0, 0, 0] [degs: degK | degM << 8 per owned node] [offsKM: staging offset of the node's MDK rows | M rows << 16]
+//      [offsF: staging offset of the node's f] [groups: 4 words each: kind | nA << 8 | nB << 16, pull base, 0, 0] [records: 32 x u64 per
+//      group] [pulls]
+//      groups are sorted by descending cost; warp w takes groups w, 15 - w, 16 + w, 31 - w, ... (snake order)
+// Staging offsets follow the PARITY of the global destination (offset of a run's first double in its value array, mod 2), so that
+// staged rows and global rows are 16-byte aligned together and whole runs leave with one bulk copy (cp.async.bulk).
+// Geometry blob (per tile): [template offset (16-byte units), nOwn | nLoc << 8, size A | size B << 16 (16-byte units), nRuns]
+//   [local -> global node table] [runs: 4 words each: destination offset (u64, doubles) | kind << 62 (0 = MDK, 1 = M, 2 = f),
+//   staging offset, length (doubles)]
 struct Plan {
     int32_t n_tiles = 0, n_templates = 0;
     std::vector<uint32_t> geo;         // geometry blobs (u32 words), tile t at t * 4 * max_geo16 (fixed stride: no offset lookup)
     std::vector<uint32_t> tmpl;        // template blobs (u32 words)
-    uint32_t max_geo16 = 0, max_tmplA16 = 0, max_tmplB16 = 0, max_loc = 0, max_scratch = 0, max_kstage = 0, max_mstage = 0;   // per-tile maxima
+    uint32_t max_geo16 = 0, max_tmplA16 = 0, max_tmplB16 = 0, max_loc = 0, max_scratch = 0, max_kstage = 0, max_mstage = 0, max_fstage = 0;
     int64_t elem_evals = 0;            // element evaluations per fill (>= F + Ei because of halo re-evaluation)
+    int64_t n_runs = 0, n_groups = 0, pull_rows = 0;   // statistics
     std::string error;
 };
 
@@ -210,10 +209,10 @@ struct Builder {
         }
         const int nE = (int)edges.size(), nF = (int)faces.size();
         const int nEpad = (nE + 31) / 32 * 32;
-        if (n_own > MAX_OWN || nEpad + nF > NTHREADS || nEpad > 255) return false;
-        if (ZPAD + (int64_t)nEpad * EDGE_STRIDE + (int64_t)nF * FACE_STRIDE > MAX_SCRATCH_DOUBLES) return false;
+        if (n_own > MAX_OWN || nEpad + nF > NTHREADS) return false;
+        if (ZPAD + (int64_t)nE * EDGE_STRIDE + (int64_t)nF * FACE_STRIDE > MAX_SCRATCH_DOUBLES) return false;
         int64_t kst = 0, mst = 0;
-        for (int o = 0; o < n_own; ++o) { kst += 9 * (pat.blkptrK[own[o] + 1] - pat.blkptrK[own[o]]); mst += 9 * (pat.blkptrM[own[o] + 1] - pat.blkptrM[own[o]]); }
+        for (int o = 0; o < n_own; ++o) { kst += 9 * (pat.blkptrK[own[o] + 1] - pat.blkptrK[own[o]]) + 2; mst += 9 * (pat.blkptrM[own[o] + 1] - pat.blkptrM[own[o]]) + 2; }
         if (kst > MAX_KSTAGE || mst > MAX_MSTAGE) return false;
         int nloc = 0;
         auto touch = [&](int32_t g) { if (lstamp[g] != stamp) { lstamp[g] = stamp; ++nloc; } };
@@ -245,6 +244,12 @@ inline void rcb(std::vector<int32_t> &idx, size_t lo, size_t hi, size_t leaves, 
     rcb(idx, lo, mid, lleaves, cx, cy, out);
     rcb(idx, mid, hi, leaves - lleaves, cx, cy, out);
 }
+
+// one phase-2 record under construction
+struct RecTmp {
+    uint64_t rec;
+    std::vector<uint16_t> A, B;    // pull offsets of loop A / loop B (single entries, paired when serialised)
+};
 
 inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie, const Pattern &pat, const double *X_hint, bool dedup,
                   Plan &P) {
@@ -310,11 +315,11 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
     geo_off.reserve(leaves.size() + 1);
     std::unordered_map<uint64_t, std::vector<uint32_t>> seen;   // hash -> template offsets (16-byte units)
     std::vector<uint32_t> T;                                   // template under construction
-    std::vector<uint64_t> recD, recO, recM;
-    std::vector<uint16_t> pull;
-    struct OTmp { int cnt; uint64_t rec; };
-    std::vector<OTmp> otmp, mtmp;
-    std::vector<uint16_t> listN, listT, listF;
+    std::vector<RecTmp> recs[3];
+    struct Run { uint64_t dst; uint32_t kind, src, len; };
+    std::vector<Run> runs;
+    struct Grp { int kind, nA, nB, first; long cost; };
+    std::vector<Grp> groups;
     for (size_t t = 0; t < leaves.size(); ++t) {
         int32_t *own = idx.data() + leaves[t].first;
         const int n_own = (int)(leaves[t].second - leaves[t].first);
@@ -322,8 +327,8 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         B.fits(own, n_own, faces, edges);
         std::sort(faces.begin(), faces.end());
         std::sort(edges.begin(), edges.end());
-        const int nE = (int)edges.size(), nF = (int)faces.size(), nEpad = (nE + 31) / 32 * 32;
-        const int fbase = ZPAD + nEpad * EDGE_STRIDE;
+        const int nE = (int)edges.size(), nF = (int)faces.size();
+        const int fbase = ZPAD + nE * EDGE_STRIDE;
         P.elem_evals += nE + nF;
         P.max_scratch = std::max<uint32_t>(P.max_scratch, (uint32_t)(fbase + nF * FACE_STRIDE));
         // local node table: owned nodes first (ascending), then halo nodes by first appearance; element -> slot maps
@@ -334,7 +339,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             return (uint32_t)B.local[g];
         };
         for (int o = 0; o < n_own; ++o) lid(own[o]);
-        std::vector<uint32_t> items((size_t)nEpad + nF, 0u);
+        std::vector<uint32_t> items((size_t)nE + nF, 0u);
         for (int s = 0; s < nE; ++s) {
             const int32_t *v = ie + 4 * (size_t)edges[s];
             items[s] = lid(v[0]) | (lid(v[1]) << 8) | (lid(v[2]) << 16) | (lid(v[3]) << 24);
@@ -342,16 +347,41 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         }
         for (int s = 0; s < nF; ++s) {
             const int32_t *v = fn + 3 * (size_t)faces[s];
-            items[nEpad + s] = lid(v[0]) | (lid(v[1]) << 8) | (lid(v[2]) << 16);
+            items[nE + s] = lid(v[0]) | (lid(v[1]) << 8) | (lid(v[2]) << 16);
             B.fslot[faces[s]] = s;
         }
         P.max_loc = std::max<uint32_t>(P.max_loc, (uint32_t)loc.size());
-        // ---- phase-2 work items
-        recD.clear(); otmp.clear(); mtmp.clear(); pull.clear();
-        std::vector<uint32_t> degs((size_t)n_own, 0u), offs((size_t)n_own, 0u);   // row sizes / staging offsets per owned node
-        uint32_t kstage = 0, mstage = 0;
-        bool overflow = false;
-        auto pad2 = [](std::vector<uint16_t> &l) { if (l.size() & 1) l.push_back(0); };
+        // ---- runs of owned nodes with consecutive ids (adjacent rows in the global arrays) and the staging offsets, which follow
+        //      the parity of the run's destination so that one bulk copy moves the run
+        std::vector<uint32_t> degs((size_t)n_own, 0u), offsKM((size_t)n_own, 0u), offsF((size_t)n_own, 0u);
+        runs.clear();
+        uint32_t stage_end[3] = {0, 0, 0};
+        for (int kind = 0; kind < 3; ++kind) {
+            uint32_t cur = 0;
+            int o = 0;
+            while (o < n_own) {
+                auto len_of = [&](int q) {
+                    return kind == 0 ? 9u * (uint32_t)(pat.blkptrK[own[q] + 1] - pat.blkptrK[own[q]])
+                         : kind == 1 ? 9u * (uint32_t)(pat.blkptrM[own[q] + 1] - pat.blkptrM[own[q]]) : 3u;
+                };
+                const uint64_t dst = kind == 0 ? (uint64_t)(9 * pat.blkptrK[own[o]]) : kind == 1 ? (uint64_t)(9 * pat.blkptrM[own[o]]) : (uint64_t)3 * (uint64_t)own[o];
+                cur = ((cur + 1u) & ~1u) + (uint32_t)(dst & 1u);      // even slot + the destination's parity
+                const uint32_t src = cur;
+                int o1 = o;
+                for (;;) {
+                    if (kind == 0) offsKM[o1] |= cur; else if (kind == 1) offsKM[o1] |= cur << 16; else offsF[o1] = cur;
+                    cur += len_of(o1);
+                    if (o1 + 1 < n_own && own[o1 + 1] == own[o1] + 1) ++o1; else break;
+                }
+                if (cur - src) runs.push_back({dst, (uint32_t)kind, src, cur - src});
+                o = o1 + 1;
+            }
+            stage_end[kind] = cur;
+        }
+        if (stage_end[0] > 0xffffu || stage_end[1] > 0xffffu) { P.error = "tile " + std::to_string(t) + ": staging overflow"; return false; }
+        P.max_kstage = std::max(P.max_kstage, stage_end[0]); P.max_mstage = std::max(P.max_mstage, stage_end[1]); P.max_fstage = std::max(P.max_fstage, stage_end[2]);
+        // ---- phase-2 records
+        for (auto &r : recs) r.clear();
         auto owned_index = [&](int32_t g) { return (B.lstamp[g] == B.stamp && B.local[g] < n_own) ? B.local[g] : -1; };
         for (int o = 0; o < n_own; ++o) {
             const int32_t a = own[o];
@@ -359,25 +389,22 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             const int deg = (int)(pat.blkptrK[a + 1] - b0), degM = (int)(pat.blkptrM[a + 1] - m0);
             if (deg > 255) { P.error = "node " + std::to_string(a) + " has more than 255 neighbours"; return false; }
             degs[o] = (uint32_t)deg | ((uint32_t)degM << 8);
-            offs[o] = kstage | (mstage << 16);
-            kstage += 9u * (uint32_t)deg; mstage += 9u * (uint32_t)degM;
             for (int p = 0; p < std::max(deg, 1); ++p) {
                 const int32_t b = deg ? pat.nbrK[b0 + p] : a;
                 const int ob = b == a ? -1 : owned_index(b);
-                if (ob >= 0 && b < a) continue;      // the pair is assembled by the item of (b, a), which mirrors it into this row
-                listN.clear(); listT.clear(); listF.clear();
-                std::vector<uint16_t> listE;         // diagonal block: stencil entries, kept apart from the face entries
+                if (ob >= 0 && b < a) continue;      // the pair is assembled by the record of (b, a), which mirrors it into this row
+                RecTmp R, Rm;
                 // faces ascending, then stencils ascending
                 for (int32_t k = B.nfp[a]; k < B.nfp[a + 1]; ++k) {
                     const int32_t f = B.nfl[k] >> 2;
                     const int va = B.nfl[k] & 3, sf = B.fslot[f];
                     const int32_t *v = fn + 3 * (size_t)f;
                     const int base = fbase + sf * FACE_STRIDE;
-                    if (b == a) { listN.push_back((uint16_t)(base + face_diag_off(va))); listF.push_back((uint16_t)(base + FACE_T8)); continue; }
+                    if (b == a) { R.A.push_back((uint16_t)(base + face_diag_off(va))); Rm.A.push_back((uint16_t)(base + FACE_T8)); continue; }
                     for (int vj = 0; vj < 3; ++vj)
                         if (v[vj] == b) {
-                            (va < vj ? listN : listT).push_back((uint16_t)(base + face_off_off(std::min(va, vj), std::max(va, vj))));
-                            listF.push_back((uint16_t)(base + FACE_T8));
+                            (va < vj ? R.A : R.B).push_back((uint16_t)(base + face_off_off(std::min(va, vj), std::max(va, vj))));
+                            Rm.A.push_back((uint16_t)(base + FACE_T8));
                         }
                 }
                 for (int32_t k = B.nep[a]; k < B.nep[a + 1]; ++k) {
@@ -385,80 +412,86 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                     const int ia = B.nel[k] & 3, se = B.eslot[e];
                     const int32_t *v = ie + 4 * (size_t)e;
                     const int base = ZPAD + se * EDGE_STRIDE;
-                    if (b == a) { listE.push_back((uint16_t)(base + edge_diag_off(ia))); continue; }
+                    if (b == a) { R.B.push_back((uint16_t)(base + edge_diag_off(ia))); continue; }   // D: loop B = stencils
                     for (int ij = 0; ij < 4; ++ij)
-                        if (v[ij] == b) (ia < ij ? listN : listT).push_back((uint16_t)(base + edge_off_off(std::min(ia, ij), std::max(ia, ij))));
+                        if (v[ij] == b) (ia < ij ? R.A : R.B).push_back((uint16_t)(base + edge_off_off(std::min(ia, ij), std::max(ia, ij))));
                 }
-                const unsigned q0 = (unsigned)pull.size();
                 unsigned p2 = 0, own2 = 0, has2 = 0;
                 if (ob >= 0) { has2 = 1; own2 = (unsigned)ob; p2 = (unsigned)(find_block(pat.blkptrK, pat.nbrK, b, a) - pat.blkptrK[b]); }
-                if (b == a) {
-                    pad2(listN); pad2(listE);
-                    if (listN.size() / 2 > (size_t)MAX_COUNT || listE.size() / 2 > (size_t)MAX_COUNT) overflow = true;
-                    pull.insert(pull.end(), listN.begin(), listN.end());
-                    pull.insert(pull.end(), listE.begin(), listE.end());
-                    recD.push_back(pack_rec(q0, (unsigned)listN.size() / 2, (unsigned)listE.size() / 2, (unsigned)p, (unsigned)o, 0, 0, 0, 0));
-                } else {
-                    pad2(listN); pad2(listT);
-                    if (listN.size() / 2 > (size_t)MAX_COUNT || listT.size() / 2 > (size_t)MAX_COUNT) overflow = true;
-                    pull.insert(pull.end(), listN.begin(), listN.end());
-                    pull.insert(pull.end(), listT.begin(), listT.end());
-                    otmp.push_back({(int)(listN.size() + listT.size()),
-                                    pack_rec(q0, (unsigned)listN.size() / 2, (unsigned)listT.size() / 2, (unsigned)p, (unsigned)o, p2, own2, has2, 0)});
-                }
-                if (!listF.empty()) {   // the pair shares a face -> mass block
-                    pad2(listF);
-                    const unsigned qm = (unsigned)pull.size();
-                    if (listF.size() / 2 > (size_t)MAX_COUNT) overflow = true;
-                    pull.insert(pull.end(), listF.begin(), listF.end());
+                R.rec = pack_rec((unsigned)p, (unsigned)o, p2, own2, has2, 0);
+                recs[b == a ? KIND_D : KIND_O].push_back(std::move(R));
+                if (!Rm.A.empty()) {   // the pair shares a face -> mass block
                     const unsigned pM = (unsigned)(find_block(pat.blkptrM, pat.nbrM, a, b) - m0);
                     const unsigned pM2 = has2 ? (unsigned)(find_block(pat.blkptrM, pat.nbrM, b, a) - pat.blkptrM[b]) : 0u;
-                    mtmp.push_back({(int)listF.size(), pack_rec(qm, (unsigned)listF.size() / 2, 0, pM, (unsigned)o, pM2, own2, has2, b == a ? 1u : 0u)});
+                    Rm.rec = pack_rec(pM, (unsigned)o, pM2, own2, has2, b == a ? 1u : 0u);
+                    recs[KIND_M].push_back(std::move(Rm));
                 }
             }
         }
-        if (getenv("EOLC_TILES_DEBUG_CONFLICT_FREE")) {
-            // TIMING EXPERIMENT ONLY (wrong results): every item reads bank-conflict-free addresses, to bound what a
-            // bank-aware ordering of the pull lists could gain
-            auto fix = [&](uint64_t rec, int lane) {
-                const unsigned q0 = (unsigned)(rec & 0xffffu), n = 2 * ((unsigned)((rec >> 16) & 63u) + (unsigned)((rec >> 22) & 63u));
-                for (unsigned k = 0; k < n; ++k) if (pull[q0 + k]) pull[q0 + k] = (uint16_t)(ZPAD + 2 * (lane & 7) + 16 * (k & 15));
-            };
-            for (size_t k = 0; k < recD.size(); ++k) fix(recD[k], (int)k);
-            for (size_t k = 0; k < otmp.size(); ++k) fix(otmp[k].rec, (int)k);
+        // ---- groups: records of one kind, sorted by trip counts (stable) so that the lanes of a group run similar lists
+        auto pairs = [](const std::vector<uint16_t> &l) { return (int)(l.size() + 1) / 2; };
+        groups.clear();
+        for (int kind = 0; kind < 3; ++kind) {
+            auto &rv = recs[kind];
+            if (kind != KIND_D)
+                std::stable_sort(rv.begin(), rv.end(), [&](const RecTmp &u, const RecTmp &v) {
+                    const int cu = pairs(u.A) + pairs(u.B), cv = pairs(v.A) + pairs(v.B);
+                    if (cu != cv) return cu > cv;
+                    return pairs(u.A) > pairs(v.A);
+                });
+            for (size_t g0 = 0; g0 < rv.size(); g0 += GROUP) {
+                Grp G{kind, 0, 0, (int)g0, 0};
+                for (size_t k = g0; k < std::min(rv.size(), g0 + GROUP); ++k) { G.nA = std::max(G.nA, pairs(rv[k].A)); G.nB = std::max(G.nB, pairs(rv[k].B)); }
+                if (G.nA > MAX_ITER || G.nB > MAX_ITER) { P.error = "tile " + std::to_string(t) + ": contribution list overflow"; return false; }
+                G.cost = kind == KIND_D ? 10 + 10L * G.nA + 6L * G.nB : kind == KIND_O ? 18 + 10L * (G.nA + G.nB) : 6 + 2L * G.nA;
+                groups.push_back(G);
+            }
         }
-        if (overflow || pull.size() > 65535) { P.error = "tile " + std::to_string(t) + ": contribution list overflow"; return false; }
-        // heavier items first (stable): the lanes of a warp run similar trip counts
-        std::stable_sort(otmp.begin(), otmp.end(), [](const OTmp &u, const OTmp &v) { return u.cnt > v.cnt; });
-        std::stable_sort(mtmp.begin(), mtmp.end(), [](const OTmp &u, const OTmp &v) { return u.cnt > v.cnt; });
-        const unsigned nD = (unsigned)recD.size(), nDpad = (nD + 31) / 32 * 32, nO = (unsigned)otmp.size(), nOpad = (nO + 31) / 32 * 32,
-                       nM = (unsigned)mtmp.size();
-        const unsigned npull16 = (unsigned)((pull.size() + 7) / 8);
-        // ---- serialise the template: part A (phase 1: header + items), part B (phase 2: header + row sizes + staging offsets +
-        //      records + pull entries); A is staged one tile ahead, B only while its own tile is being assembled
+        std::stable_sort(groups.begin(), groups.end(), [](const Grp &u, const Grp &v) { return u.cost > v.cost; });
+        if (groups.size() > 255) { P.error = "tile " + std::to_string(t) + ": too many phase-2 groups"; return false; }
+        // ---- serialise the template
         T.clear();
-        T.push_back((uint32_t)nE | ((uint32_t)nEpad << 8) | ((uint32_t)nF << 16));
+        T.push_back((uint32_t)nE | ((uint32_t)nF << 16));
         T.push_back(0); T.push_back(0); T.push_back(0);
         T.insert(T.end(), items.begin(), items.end());
         while (T.size() % 4) T.push_back(0);
         const uint32_t sizeA16 = (uint32_t)(T.size() / 4);
-        T.push_back(nD | (nDpad << 16));
-        T.push_back(nO | (nOpad << 16));
-        T.push_back(nM | (npull16 << 16));
-        T.push_back(0);
-        T.insert(T.end(), degs.begin(), degs.end());
+        T.push_back((uint32_t)n_own | ((uint32_t)groups.size() << 8));
+        T.push_back(0); T.push_back(0); T.push_back(0);
+        auto push_padded = [&](const std::vector<uint32_t> &v) { T.insert(T.end(), v.begin(), v.end()); while (T.size() % 4) T.push_back(0); };
+        push_padded(degs); push_padded(offsKM); push_padded(offsF);
+        {
+            uint32_t pbase = 0;
+            for (const Grp &G : groups) {
+                T.push_back((uint32_t)G.kind | ((uint32_t)G.nA << 8) | ((uint32_t)G.nB << 16));
+                T.push_back(pbase); T.push_back(0); T.push_back(0);
+                pbase += (uint32_t)(G.nA + G.nB) * GROUP;
+            }
+            P.pull_rows += pbase / GROUP;
+        }
+        for (const Grp &G : groups) {
+            const auto &rv = recs[G.kind];
+            for (int l = 0; l < GROUP; ++l) {
+                const uint64_t r = (size_t)G.first + l < rv.size() ? rv[G.first + l].rec : 0ull;
+                T.push_back((uint32_t)r); T.push_back((uint32_t)(r >> 32));
+            }
+        }
+        for (const Grp &G : groups) {
+            const auto &rv = recs[G.kind];
+            for (int loop = 0; loop < 2; ++loop)
+                for (int r = 0; r < (loop ? G.nB : G.nA); ++r)
+                    for (int l = 0; l < GROUP; ++l) {
+                        uint32_t e = 0;
+                        if ((size_t)G.first + l < rv.size()) {
+                            const std::vector<uint16_t> &L = loop ? rv[G.first + l].B : rv[G.first + l].A;
+                            if ((size_t)2 * r < L.size()) e = L[2 * r];
+                            if ((size_t)2 * r + 1 < L.size()) e |= (uint32_t)L[2 * r + 1] << 16;
+                        }
+                        T.push_back(e);
+                    }
+        }
         while (T.size() % 4) T.push_back(0);
-        T.insert(T.end(), offs.begin(), offs.end());
-        while (T.size() % 4) T.push_back(0);
-        P.max_kstage = std::max(P.max_kstage, kstage); P.max_mstage = std::max(P.max_mstage, mstage);
-        auto push64 = [&](uint64_t r) { T.push_back((uint32_t)r); T.push_back((uint32_t)(r >> 32)); };
-        for (unsigned k = 0; k < nDpad; ++k) push64(k < nD ? recD[k] : 0);
-        for (unsigned k = 0; k < nOpad; ++k) push64(k < nO ? otmp[k].rec : 0);
-        for (unsigned k = 0; k < nM; ++k) push64(mtmp[k].rec);
-        while (T.size() % 4) T.push_back(0);
-        pull.resize((size_t)npull16 * 8, 0);
-        for (size_t k = 0; k < pull.size(); k += 2) T.push_back((uint32_t)pull[k] | ((uint32_t)pull[k + 1] << 16));
-        while (T.size() % 4) T.push_back(0);
+        P.n_groups += (int64_t)groups.size();
         const uint32_t sizeB16 = (uint32_t)(T.size() / 4) - sizeA16;
         if (sizeA16 > 0xffffu || sizeB16 > 0xffffu) { P.error = "tile " + std::to_string(t) + ": template too large"; return false; }
         P.max_tmplA16 = std::max(P.max_tmplA16, sizeA16); P.max_tmplB16 = std::max(P.max_tmplB16, sizeB16);
@@ -487,39 +520,15 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         P.geo.push_back(toff);
         P.geo.push_back((uint32_t)n_own | ((uint32_t)loc.size() << 8));
         P.geo.push_back(sizeA16 | (sizeB16 << 16));
-        P.geo.push_back(0);
-        for (int o = 0; o < n_own; ++o) {
-            const int64_t kb = 9 * pat.blkptrK[own[o]], mb = 9 * pat.blkptrM[own[o]];
-            P.geo.push_back((uint32_t)(uint64_t)kb); P.geo.push_back((uint32_t)((uint64_t)kb >> 32));
-            P.geo.push_back((uint32_t)(uint64_t)mb); P.geo.push_back((uint32_t)((uint64_t)mb >> 32));
-        }
+        P.geo.push_back((uint32_t)runs.size());
         P.geo.insert(P.geo.end(), loc.begin(), loc.end());
         while (P.geo.size() % 4) P.geo.push_back(0);
-        {
-            // copy-out chunks: owned nodes with consecutive ids have adjacent rows in the global arrays as well, so the staged
-            // rows form a few long runs; runs are cut into chunks of <= COPY_CHUNK doubles (one warp each).
-            // chunk = u64 (destination offset | kind << 62; kind 0 = MDK values, 1 = M values, 2 = f), u32 staging offset, u32 length
-            uint32_t nchunks = 0;
-            for (int kind = 0; kind < 3; ++kind) {
-                int o = 0;
-                while (o < n_own) {
-                    auto len_of = [&](int q) { return kind == 0 ? 9u * (degs[q] & 255u) : kind == 1 ? 9u * (degs[q] >> 8) : 3u; };
-                    int o1 = o;
-                    uint32_t len = len_of(o);
-                    while (o1 + 1 < n_own && own[o1 + 1] == own[o1] + 1) { ++o1; len += len_of(o1); }
-                    const uint64_t dst = kind == 0 ? (uint64_t)(9 * pat.blkptrK[own[o]]) : kind == 1 ? (uint64_t)(9 * pat.blkptrM[own[o]]) : (uint64_t)3 * (uint64_t)own[o];
-                    const uint32_t src = kind == 0 ? (offs[o] & 0xffffu) : kind == 1 ? (offs[o] >> 16) : 3u * (uint32_t)o;
-                    for (uint32_t c = 0; c < len; c += COPY_CHUNK) {
-                        const uint64_t d = (dst + c) | ((uint64_t)kind << 62);
-                        P.geo.push_back((uint32_t)d); P.geo.push_back((uint32_t)(d >> 32));
-                        P.geo.push_back(src + c); P.geo.push_back(std::min<uint32_t>(COPY_CHUNK, len - c));
-                        ++nchunks;
-                    }
-                    o = o1 + 1;
-                }
-            }
-            P.geo[g0 + 3] = nchunks;
+        for (const Run &r : runs) {
+            const uint64_t d = r.dst | ((uint64_t)r.kind << 62);
+            P.geo.push_back((uint32_t)d); P.geo.push_back((uint32_t)(d >> 32));
+            P.geo.push_back(r.src); P.geo.push_back(r.len);
         }
+        P.n_runs += (int64_t)runs.size();
         P.max_geo16 = std::max<uint32_t>(P.max_geo16, (uint32_t)((P.geo.size() - g0) / 4));
         if (P.geo.size() / 4 >= ((size_t)1 << 32) || P.tmpl.size() / 4 >= ((size_t)1 << 32)) { P.error = "plan too large"; return false; }
     }

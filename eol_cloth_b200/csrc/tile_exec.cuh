@@ -1,10 +1,11 @@
 // tile_exec.cuh — the two per-thread phases of the "tiles" assembly of Forces::fill, written once for the device
 // (forces.cu: assemble_tiles_kernel) and for the host emulation the CPU tests run (tests/hostmath/hostmath.cpp).
 //
-//   phase 1   thread t < nE evaluates bending stencil t, thread nEpad <= t < nEpad + nF evaluates face t - nEpad
+//   phase 1   thread t < nE evaluates bending stencil t, thread nEpad <= t < nEpad + nF evaluates face t - nEpad (nEpad = nE rounded up to a warp)
 //             (elements.cuh: edge_element_tile / face_element_tile) and parks the element blocks in `scr`
-//   phase 2   every output block of the tile's nodes pulls its contributions from `scr` in the plan's fixed order and is
-//             written once to its CSR slot (D: diagonal MDK block + f, O: off-diagonal MDK block, M: mass block)
+//   phase 2   every output block of the tile's nodes pulls its contributions from `scr` in the plan's fixed order into staged
+//             rows (D: diagonal MDK block + f, O: off-diagonal MDK block, M: mass block)
+//   copy-out  runs of staged rows leave for their CSR slots with one bulk copy each
 // Data layouts: forces_plan.h.  Replaces Forces.cpp:333-397,498-518 (faces), :687-744,885-908 (edges), :925-929 (assembly).
 #pragma once
 #include <stdint.h>
@@ -24,15 +25,15 @@ namespace tiles {
 struct FillParams { double mu, lam, rho, beta, gx, gy, gz, dhh; };
 
 struct TileView {
-    const uint32_t *geo;    // geometry blob: header, (kbase, mbase) pairs, local -> global node table, copy-out chunks
+    const uint32_t *geo;    // geometry blob: header, local -> global node table, copy-out runs
     const uint32_t *tmpl;   // template part A: header, items
-    const uint32_t *tmplB;  // template part B: header, row sizes, staging offsets, records, pull entries
+    const uint32_t *tmplB;  // template part B: header, row sizes, staging offsets, groups, records, pull entries
     const double *xs;       // staged Node::x of the tile's local nodes, 3 per node
     const double *Xs;       // staged material coordinates, 2 per node
     double *scr;            // parked element blocks
-    double *kst;            // staged MDK rows of the tile's nodes, laid out exactly like the global value array
+    double *kst;            // staged MDK rows of the tile's nodes, laid out like the global value array (same 16-byte phase)
     double *mst;            // staged M rows, same
-    double *fst;            // staged f, 3 per owned node
+    double *fst;            // staged f, same
 };
 
 EOLC_HD void st2(double *p, double a, double b) {
@@ -82,7 +83,7 @@ EOLC_HD v3 ldx(const double *xs, uint32_t l) { return mk3(xs[3 * l], xs[3 * l + 
 
 EOLC_HD void phase1(int tid, const TileView &V, const FillParams &P) {
     const uint32_t w0 = V.tmpl[0];
-    const int nE = (int)(w0 & 255u), nEpad = (int)((w0 >> 8) & 255u), nF = (int)(w0 >> 16);
+    const int nE = (int)(w0 & 0xffffu), nF = (int)(w0 >> 16), nEpad = (nE + 31) & ~31;
     if (tid < nE) {
         const uint32_t it = V.tmpl[4 + tid];
         const uint32_t l0 = it & 255u, l1 = (it >> 8) & 255u, l2 = (it >> 16) & 255u, l3 = it >> 24;
@@ -91,173 +92,182 @@ EOLC_HD void phase1(int tid, const TileView &V, const FillParams &P) {
         ParkEdge park{V.scr + ZPAD + EDGE_STRIDE * tid};
         edge_element_tile(ldx(V.xs, l0), ldx(V.xs, l1), ldx(V.xs, l2), ldx(V.xs, l3), X0x, X0y, X1x, X1y, X2x, X2y, X3x, X3y, P.beta, P.dhh, park);
     } else if (tid >= nEpad && tid < nEpad + nF) {
-        const uint32_t it = V.tmpl[4 + tid];
+        const int s = tid - nEpad;
+        const uint32_t it = V.tmpl[4 + nE + s];
         const uint32_t l0 = it & 255u, l1 = (it >> 8) & 255u, l2 = (it >> 16) & 255u;
         double Xax, Xay, Xbx, Xby, Xcx, Xcy;
         ld2(V.Xs + 2 * l0, Xax, Xay); ld2(V.Xs + 2 * l1, Xbx, Xby); ld2(V.Xs + 2 * l2, Xcx, Xcy);
-        ParkFace park{V.scr + ZPAD + EDGE_STRIDE * nEpad + FACE_STRIDE * (tid - nEpad)};
+        ParkFace park{V.scr + ZPAD + EDGE_STRIDE * nE + FACE_STRIDE * s};
         face_element_tile(ldx(V.xs, l0), ldx(V.xs, l1), ldx(V.xs, l2), Xax, Xay, Xbx, Xby, Xcx, Xcy, P.mu, P.lam, P.rho, mk3(P.gx, P.gy, P.gz),
                           P.dhh, park);
     }
 }
 
-// Unpacks two 16-bit pull entries (offsets in doubles into scr; 0 = the zero block).
-EOLC_HD void pull2(const uint16_t *pl, const double *scr, const double *&s0, const double *&s1) {
-    const uint32_t e = *reinterpret_cast<const uint32_t *>(pl);
+// Unpacks two 16-bit pull offsets (in doubles into scr; 0 = the zero block).
+EOLC_HD void pull2(uint32_t e, const double *scr, const double *&s0, const double *&s1) {
     s0 = scr + (e & 0xffffu);
     s1 = scr + (e >> 16);
 }
 
-// Phase 2: every output block of the tile's nodes sums its contributions and lands in the staging rows (shared memory).
-EOLC_HD void phase2(int tid, int nthreads, const TileView &V) {
-    const uint32_t w1 = V.tmplB[0], w2 = V.tmplB[1], w3 = V.tmplB[2];
-    const int nD = (int)(w1 & 0xffffu), nDpad = (int)(w1 >> 16), nO = (int)(w2 & 0xffffu), nOpad = (int)(w2 >> 16), nM = (int)(w3 & 0xffffu);
-    const int nd4 = (nD + 3) & ~3;
-    const uint32_t *degs = V.tmplB + 4;                              // degK | degM << 8 per owned node (nD == owned nodes)
-    const uint32_t *offs = degs + nd4;                               // staging offsets: MDK rows | M rows << 16
-    const unsigned long long *recs = reinterpret_cast<const unsigned long long *>(offs + nd4);
-    const int nrec = nDpad + nOpad + nM;
-    const uint16_t *pull = reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint32_t *>(recs) + 2 * ((nrec + 1) & ~1));
+// Phase 2: the tile's records, in groups of 32 of one kind (forces_plan.h).  Warp `warp` of `nwarps` takes groups
+// warp, 2 nwarps - 1 - warp, 2 nwarps + warp, ... (the plan sorted the groups by descending cost, so this "snake" balances the warps).
+// Every lane of a group runs the same trip counts; the sums land in the staging rows (shared memory), laid out like the
+// global rows.  m_full: the M staging rows do not hold this template's explicit zeros yet (first tile / template or parity
+// changed), so mass records write whole 3x3 blocks; otherwise only the three diagonal entries change.
+EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const uint32_t h0 = V.tmplB[0];
+    const int nOwn = (int)(h0 & 255u), nG = (int)((h0 >> 8) & 255u), n4 = (nOwn + 3) & ~3;
+    const uint32_t *degs = V.tmplB + 4, *offsKM = degs + n4, *offsF = offsKM + n4, *grp = offsF + n4;
+    const unsigned long long *recs = reinterpret_cast<const unsigned long long *>(grp + 4 * nG);
+    const uint32_t *pulls = reinterpret_cast<const uint32_t *>(recs + (size_t)GROUP * nG);
     const double *scr = V.scr;
-    for (int i = tid; i < nrec; i += nthreads) {
-        const unsigned long long rec = recs[i];
-        const uint32_t c0 = (uint32_t)(rec >> 16) & 63u, c1 = (uint32_t)(rec >> 22) & 63u;
-        const uint32_t p = (uint32_t)(rec >> 28) & 255u, own = (uint32_t)(rec >> 36) & 31u;
-        const uint16_t *pl = pull + (uint32_t)(rec & 0xffffu);
-        if (i < nDpad) {
-            if (i >= nD) continue;
-            // ---- diagonal MDK block (symmetric) + f of the node: faces (f.setZero() then +=, Forces.cpp:915,500-502), then stencils
-            double xx = 0.0, xy = 0.0, xz = 0.0, yy = 0.0, yz = 0.0, zz = 0.0, f0 = 0.0, f1 = 0.0, f2 = 0.0;
-            EOLC_UNROLL_P2
-            for (uint32_t k = 0; k < c0; ++k, pl += 2) {
-                const double *s0, *s1;
-                pull2(pl, scr, s0, s1);
-                double a, b, c, d, e, g, h, j, a1, b1, c1_, d1, e1, g1, h1, j1;
-                ld2(s0, a, b); ld2(s0 + 2, c, d); ld2(s0 + 4, e, g); ld2(s0 + 6, h, j);
-                ld2(s1, a1, b1); ld2(s1 + 2, c1_, d1); ld2(s1 + 4, e1, g1); ld2(s1 + 6, h1, j1);
-                const double q = s0[8], q1 = s1[8];
-                xx += a; xy += b; xz += c; yy += d; yz += e; zz += g; f0 += h; f1 += j; f2 += q;
-                xx += a1; xy += b1; xz += c1_; yy += d1; yz += e1; zz += g1; f0 += h1; f1 += j1; f2 += q1;
-            }
-            EOLC_UNROLL_P2
-            for (uint32_t k = 0; k < c1; ++k, pl += 2) {
-                const double *s0, *s1;
-                pull2(pl, scr, s0, s1);
-                double a, b, c, d, e, g, a1, b1, c1_, d1, e1, g1;
-                ld2(s0, a, b); ld2(s0 + 2, c, d); ld2(s0 + 4, e, g);
-                ld2(s1, a1, b1); ld2(s1 + 2, c1_, d1); ld2(s1 + 4, e1, g1);
-                xx += a; xy += b; xz += c; yy += d; yz += e; zz += g;
-                xx += a1; xy += b1; xz += c1_; yy += d1; yz += e1; zz += g1;
-            }
-            double *fo = V.fst + 3 * own;
-            fo[0] = f0; fo[1] = f1; fo[2] = f2;
-            const uint32_t deg = degs[own] & 255u;
-            if (deg) {
-                double *row = V.kst + (offs[own] & 0xffffu) + 3 * p;
-                row[0] = xx; row[1] = xy; row[2] = xz;
-                row += 3 * deg;
-                row[0] = xy; row[1] = yy; row[2] = yz;
-                row += 3 * deg;
-                row[0] = xz; row[1] = yz; row[2] = zz;
-            }
-        } else if (i < nDpad + nOpad) {
-            if (i >= nDpad + nO) continue;
-            // ---- off-diagonal MDK block: contributions are parked as K_(lo,hi) of the element; the ones whose row vertex comes
-            //      after the column vertex are added transposed (the transposition is just the choice of accumulator)
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0, a8 = 0.0;
-            EOLC_UNROLL_P2
-            for (uint32_t k = 0; k < c0; ++k, pl += 2) {
-                const double *s0, *s1;
-                pull2(pl, scr, s0, s1);
-                double b0, b1, b2, b3, b4, b5, b6, b7, d0, d1, d2, d3, d4, d5, d6, d7;
-                ld2(s0, b0, b1); ld2(s0 + 2, b2, b3); ld2(s0 + 4, b4, b5); ld2(s0 + 6, b6, b7);
-                ld2(s1, d0, d1); ld2(s1 + 2, d2, d3); ld2(s1 + 4, d4, d5); ld2(s1 + 6, d6, d7);
-                const double b8 = s0[8], d8 = s1[8];
-                a0 += b0; a1 += b1; a2 += b2; a3 += b3; a4 += b4; a5 += b5; a6 += b6; a7 += b7; a8 += b8;
-                a0 += d0; a1 += d1; a2 += d2; a3 += d3; a4 += d4; a5 += d5; a6 += d6; a7 += d7; a8 += d8;
-            }
-            EOLC_UNROLL_P2
-            for (uint32_t k = 0; k < c1; ++k, pl += 2) {
-                const double *s0, *s1;
-                pull2(pl, scr, s0, s1);
-                double b0, b1, b2, b3, b4, b5, b6, b7, d0, d1, d2, d3, d4, d5, d6, d7;
-                ld2(s0, b0, b1); ld2(s0 + 2, b2, b3); ld2(s0 + 4, b4, b5); ld2(s0 + 6, b6, b7);
-                ld2(s1, d0, d1); ld2(s1 + 2, d2, d3); ld2(s1 + 4, d4, d5); ld2(s1 + 6, d6, d7);
-                const double b8 = s0[8], d8 = s1[8];
-                a0 += b0; a3 += b1; a6 += b2; a1 += b3; a4 += b4; a7 += b5; a2 += b6; a5 += b7; a8 += b8;
-                a0 += d0; a3 += d1; a6 += d2; a1 += d3; a4 += d4; a7 += d5; a2 += d6; a5 += d7; a8 += d8;
-            }
-            {
-                const uint32_t deg = degs[own] & 255u;
-                double *row = V.kst + (offs[own] & 0xffffu) + 3 * p;
-                row[0] = a0; row[1] = a1; row[2] = a2;
-                row += 3 * deg;
-                row[0] = a3; row[1] = a4; row[2] = a5;
-                row += 3 * deg;
-                row[0] = a6; row[1] = a7; row[2] = a8;
-            }
-            if ((rec >> 54) & 1ull) {   // the column node is owned too: its row gets the transposed block
-                const uint32_t own2 = (uint32_t)(rec >> 49) & 31u, p2 = (uint32_t)(rec >> 41) & 255u;
-                const uint32_t deg = degs[own2] & 255u;
-                double *row = V.kst + (offs[own2] & 0xffffu) + 3 * p2;
-                row[0] = a0; row[1] = a3; row[2] = a6;
-                row += 3 * deg;
-                row[0] = a1; row[1] = a4; row[2] = a7;
-                row += 3 * deg;
-                row[0] = a2; row[1] = a5; row[2] = a8;
-            }
-        } else {
-            // ---- mass block: sum of rho 2A over the faces shared by the pair; /12 on the diagonal block, /24 off it
-            //      (ComputeInertial.cpp:33,44-47)
-            double m = 0.0;
-            EOLC_UNROLL_P2
-            for (uint32_t k = 0; k < c0; ++k, pl += 2) {
-                const double *s0, *s1;
-                pull2(pl, scr, s0, s1);
-                m += *s0;
-                m += *s1;
-            }
-            m *= ((rec >> 55) & 1ull) ? (1.0 / 12.0) : (1.0 / 24.0);
-            {
-                const uint32_t deg = degs[own] >> 8;
-                double *row = V.mst + (offs[own] >> 16) + 3 * p;
-                row[0] = m; row[1] = 0.0; row[2] = 0.0;
-                row += 3 * deg;
-                row[0] = 0.0; row[1] = m; row[2] = 0.0;
-                row += 3 * deg;
-                row[0] = 0.0; row[1] = 0.0; row[2] = m;
-            }
-            if ((rec >> 54) & 1ull) {
-                const uint32_t own2 = (uint32_t)(rec >> 49) & 31u, p2 = (uint32_t)(rec >> 41) & 255u;
-                const uint32_t deg = degs[own2] >> 8;
-                double *row = V.mst + (offs[own2] >> 16) + 3 * p2;
-                row[0] = m; row[1] = 0.0; row[2] = 0.0;
-                row += 3 * deg;
-                row[0] = 0.0; row[1] = m; row[2] = 0.0;
-                row += 3 * deg;
-                row[0] = 0.0; row[1] = 0.0; row[2] = m;
+    for (int g0 = 0; g0 < nG; g0 += 2 * nwarps) {
+        for (int half = 0; half < 2; ++half) {
+            const int g = g0 + (half ? 2 * nwarps - 1 - warp : warp);
+            if (g >= nG) continue;
+            const uint32_t gw = grp[4 * g];
+            const int kind = (int)(gw & 255u), nA = (int)((gw >> 8) & 255u), nB = (int)((gw >> 16) & 255u);
+            const uint32_t *pl = pulls + grp[4 * g + 1] + lane;
+            const unsigned long long rec = recs[(size_t)GROUP * g + lane];
+            const uint32_t p = (uint32_t)rec & 255u, own = (uint32_t)(rec >> 8) & 63u;
+            const bool valid = (rec >> 30) & 1ull, has2 = (rec >> 28) & 1ull;
+            if (kind == KIND_D) {
+                // ---- diagonal MDK block (symmetric) + f of the node: faces (f.setZero() then +=, Forces.cpp:915,500-502), then stencils
+                double xx = 0.0, xy = 0.0, xz = 0.0, yy = 0.0, yz = 0.0, zz = 0.0, f0 = 0.0, f1 = 0.0, f2 = 0.0;
+                EOLC_UNROLL_P2
+                for (int k = 0; k < nA; ++k, pl += GROUP) {
+                    const double *s0, *s1;
+                    pull2(*pl, scr, s0, s1);
+                    double a, b, c, d, e, g_, h, j, a1, b1, c1_, d1, e1, g1, h1, j1;
+                    ld2(s0, a, b); ld2(s0 + 2, c, d); ld2(s0 + 4, e, g_); ld2(s0 + 6, h, j);
+                    ld2(s1, a1, b1); ld2(s1 + 2, c1_, d1); ld2(s1 + 4, e1, g1); ld2(s1 + 6, h1, j1);
+                    const double q = s0[8], q1 = s1[8];
+                    xx += a; xy += b; xz += c; yy += d; yz += e; zz += g_; f0 += h; f1 += j; f2 += q;
+                    xx += a1; xy += b1; xz += c1_; yy += d1; yz += e1; zz += g1; f0 += h1; f1 += j1; f2 += q1;
+                }
+                EOLC_UNROLL_P2
+                for (int k = 0; k < nB; ++k, pl += GROUP) {
+                    const double *s0, *s1;
+                    pull2(*pl, scr, s0, s1);
+                    double a, b, c, d, e, g_, a1, b1, c1_, d1, e1, g1;
+                    ld2(s0, a, b); ld2(s0 + 2, c, d); ld2(s0 + 4, e, g_);
+                    ld2(s1, a1, b1); ld2(s1 + 2, c1_, d1); ld2(s1 + 4, e1, g1);
+                    xx += a; xy += b; xz += c; yy += d; yz += e; zz += g_;
+                    xx += a1; xy += b1; xz += c1_; yy += d1; yz += e1; zz += g1;
+                }
+                if (valid) {
+                    double *fo = V.fst + offsF[own];
+                    fo[0] = f0; fo[1] = f1; fo[2] = f2;
+                    const uint32_t deg = degs[own] & 255u;
+                    if (deg) {
+                        double *row = V.kst + (offsKM[own] & 0xffffu) + 3 * p;
+                        row[0] = xx; row[1] = xy; row[2] = xz;
+                        row += 3 * deg;
+                        row[0] = xy; row[1] = yy; row[2] = yz;
+                        row += 3 * deg;
+                        row[0] = xz; row[1] = yz; row[2] = zz;
+                    }
+                }
+            } else if (kind == KIND_O) {
+                // ---- off-diagonal MDK block: contributions are parked as K_(lo,hi) of the element; the ones whose row vertex comes
+                //      after the column vertex are added transposed (the transposition is just the choice of accumulator)
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0, a8 = 0.0;
+                EOLC_UNROLL_P2
+                for (int k = 0; k < nA; ++k, pl += GROUP) {
+                    const double *s0, *s1;
+                    pull2(*pl, scr, s0, s1);
+                    double b0, b1, b2, b3, b4, b5, b6, b7, d0, d1, d2, d3, d4, d5, d6, d7;
+                    ld2(s0, b0, b1); ld2(s0 + 2, b2, b3); ld2(s0 + 4, b4, b5); ld2(s0 + 6, b6, b7);
+                    ld2(s1, d0, d1); ld2(s1 + 2, d2, d3); ld2(s1 + 4, d4, d5); ld2(s1 + 6, d6, d7);
+                    const double b8 = s0[8], d8 = s1[8];
+                    a0 += b0; a1 += b1; a2 += b2; a3 += b3; a4 += b4; a5 += b5; a6 += b6; a7 += b7; a8 += b8;
+                    a0 += d0; a1 += d1; a2 += d2; a3 += d3; a4 += d4; a5 += d5; a6 += d6; a7 += d7; a8 += d8;
+                }
+                EOLC_UNROLL_P2
+                for (int k = 0; k < nB; ++k, pl += GROUP) {
+                    const double *s0, *s1;
+                    pull2(*pl, scr, s0, s1);
+                    double b0, b1, b2, b3, b4, b5, b6, b7, d0, d1, d2, d3, d4, d5, d6, d7;
+                    ld2(s0, b0, b1); ld2(s0 + 2, b2, b3); ld2(s0 + 4, b4, b5); ld2(s0 + 6, b6, b7);
+                    ld2(s1, d0, d1); ld2(s1 + 2, d2, d3); ld2(s1 + 4, d4, d5); ld2(s1 + 6, d6, d7);
+                    const double b8 = s0[8], d8 = s1[8];
+                    a0 += b0; a3 += b1; a6 += b2; a1 += b3; a4 += b4; a7 += b5; a2 += b6; a5 += b7; a8 += b8;
+                    a0 += d0; a3 += d1; a6 += d2; a1 += d3; a4 += d4; a7 += d5; a2 += d6; a5 += d7; a8 += d8;
+                }
+                if (valid) {
+                    const uint32_t deg = degs[own] & 255u;
+                    double *row = V.kst + (offsKM[own] & 0xffffu) + 3 * p;
+                    row[0] = a0; row[1] = a1; row[2] = a2;
+                    row += 3 * deg;
+                    row[0] = a3; row[1] = a4; row[2] = a5;
+                    row += 3 * deg;
+                    row[0] = a6; row[1] = a7; row[2] = a8;
+                    if (has2) {   // the column node is owned too: its row gets the transposed block
+                        const uint32_t own2 = (uint32_t)(rec >> 22) & 63u, p2 = (uint32_t)(rec >> 14) & 255u;
+                        const uint32_t deg2 = degs[own2] & 255u;
+                        double *r2 = V.kst + (offsKM[own2] & 0xffffu) + 3 * p2;
+                        r2[0] = a0; r2[1] = a3; r2[2] = a6;
+                        r2 += 3 * deg2;
+                        r2[0] = a1; r2[1] = a4; r2[2] = a7;
+                        r2 += 3 * deg2;
+                        r2[0] = a2; r2[1] = a5; r2[2] = a8;
+                    }
+                }
+            } else {
+                // ---- mass block: sum of rho 2A over the faces shared by the pair; /12 on the diagonal block, /24 off it
+                //      (ComputeInertial.cpp:33,44-47)
+                double m = 0.0;
+                for (int k = 0; k < nA; ++k, pl += GROUP) {
+                    const double *s0, *s1;
+                    pull2(*pl, scr, s0, s1);
+                    m += *s0;
+                    m += *s1;
+                }
+                if (valid) {
+                    m *= ((rec >> 29) & 1ull) ? (1.0 / 12.0) : (1.0 / 24.0);
+                    for (int side = 0; side < 2; ++side) {
+                        if (side && !has2) break;
+                        const uint32_t o_ = side ? (uint32_t)(rec >> 22) & 63u : own, p_ = side ? (uint32_t)(rec >> 14) & 255u : p;
+                        const uint32_t deg = degs[o_] >> 8;
+                        double *row = V.mst + (offsKM[o_] >> 16) + 3 * p_;
+                        if (m_full) {
+                            row[0] = m; row[1] = 0.0; row[2] = 0.0;
+                            row += 3 * deg;
+                            row[0] = 0.0; row[1] = m; row[2] = 0.0;
+                            row += 3 * deg;
+                            row[0] = 0.0; row[1] = 0.0; row[2] = m;
+                        } else {
+                            row[0] = m; row[3 * deg + 1] = m; row[6 * deg + 2] = m;
+                        }
+                    }
+                }
             }
         }
     }
 }
 
-// Copy-out: the staged rows go to their CSR slots chunk by chunk (a warp per chunk, consecutive lanes on consecutive
-// addresses: full 32-byte sectors instead of scattered 8-byte stores).  The mass blocks were staged expanded,
-// (m, 0, 0; 0, m, 0; 0, 0, m): the six off-axis entries are the reference's explicit zeros (ComputeInertial.cpp:45-46, kept by
-// setFromTriplets).  f, Mv, Kv: outputs of the tile's scene.
-EOLC_HD void copy_out(int tid, int nthreads, const TileView &V, double *__restrict__ f, double *__restrict__ Mv, double *__restrict__ Kv) {
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+// Copy-out: every run of staged rows (rows of owned nodes with consecutive ids) goes to its CSR slot with ONE bulk copy
+// (device: cp.async.bulk shared -> global, asynchronous; host emulation: memcpy).  Staged and global rows share their
+// 16-byte phase (forces_plan.h + the parity of the output pointers added to V.kst / V.mst / V.fst by the caller), so only a
+// misaligned first / last double is stored separately.  The mass rows were staged expanded, (m, 0, 0; 0, m, 0; 0, 0, m): the six
+// off-axis entries are the reference's explicit zeros (ComputeInertial.cpp:45-46, kept by setFromTriplets).
+// Lane `lane` of `nlanes` takes runs lane, lane + nlanes, ...; f, Mv, Kv: outputs of the tile's scene.
+template <typename Bulk>
+EOLC_HD void copy_out_runs(int lane, int nlanes, const TileView &V, double *__restrict__ f, double *__restrict__ Mv, double *__restrict__ Kv, Bulk bulk) {
     const uint32_t g1 = V.geo[1];
-    const uint32_t *chunks = V.geo + 4 + 4 * (g1 & 255u) + ((((g1 >> 8) & 255u) + 3u) & ~3u);
-    const int nchunks = (int)V.geo[3];
-    for (int r = warp; r < nchunks; r += nwarps) {
-        const uint32_t *c = chunks + 4 * r;
+    const uint32_t *runs = V.geo + 4 + ((((g1 >> 8) & 255u) + 3u) & ~3u);
+    const int nruns = (int)V.geo[3];
+    for (int r = lane; r < nruns; r += nlanes) {
+        const uint32_t *c = runs + 4 * r;
         const uint32_t hi = c[1], kind = hi >> 30;
         double *dst = (kind == 0 ? Kv : kind == 1 ? Mv : f) + (((unsigned long long)(hi & 0x3fffffffu) << 32) | c[0]);
         const double *src = (kind == 0 ? V.kst : kind == 1 ? V.mst : V.fst) + c[2];
-        const int n = (int)c[3];
-#pragma unroll 4
-        for (int i = lane; i < n; i += 32) stg(dst + i, src[i]);
+        uint32_t n = c[3];
+        if ((uint32_t)(reinterpret_cast<uintptr_t>(dst) >> 3) & 1u) { stg(dst, *src); ++dst; ++src; --n; }
+        const uint32_t nb = n & ~1u;
+        if (nb) bulk(dst, src, nb * 8u);
+        if (n & 1u) stg(dst + nb, src[nb]);
     }
 }
 

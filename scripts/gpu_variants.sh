@@ -5,8 +5,8 @@ shift
 for so in "$@"; do
   name=$(basename $so .so)
   if [ "$so" = "default" ]; then unset EOLC_LIB; name=default; else export EOLC_LIB=$(pwd)/$so; fi
-  timeout 600 python -m pytest tests/test_forces_gpu.py -x -q -k "256 or golden or shuffled" > $OUT/pytest_$name.log 2>&1; echo "$name pytest rc=$? $(tail -1 $OUT/pytest_$name.log)"
-  timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-cd > $OUT/bench_$name.json 2> $OUT/bench_$name.err
+  timeout 120 python -m pytest tests/test_forces_gpu.py -x -q -k "256 or golden or shuffled" > $OUT/pytest_$name.log 2>&1; echo "$name pytest rc=$? $(tail -1 $OUT/pytest_$name.log)"
+  timeout 180 python bench.py --steps 20 --warmup 5 --no-cpu --no-cd > $OUT/bench_$name.json 2> $OUT/bench_$name.err
   python - <<PY
 import json
 try:

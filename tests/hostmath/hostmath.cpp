@@ -91,12 +91,12 @@ void *hm_plan_create(int32_t N, int32_t F, const int32_t *fn, int32_t E, const i
     return P;
 }
 void hm_plan_destroy(void *p) { delete (HmPlan *)p; }
-// info: nnzM, nnzK, n_tiles, n_templates, elem_evals, geo bytes, template bytes, max scratch doubles, max loc
+// info[16]: nnzM, nnzK, n_tiles, n_templates, elem_evals, geo bytes, template bytes, max scratch doubles, max loc, Ei, runs, groups, pull rows, max staging
 void hm_plan_info(void *p, int64_t *info) {
     HmPlan *P = (HmPlan *)p;
     info[0] = 9 * P->pat.nblkM; info[1] = 9 * P->pat.nblkK; info[2] = P->tp.n_tiles; info[3] = P->tp.n_templates; info[4] = P->tp.elem_evals;
     info[5] = (int64_t)P->tp.geo.size() * 4; info[6] = (int64_t)P->tp.tmpl.size() * 4; info[7] = P->tp.max_scratch; info[8] = P->tp.max_loc;
-    info[9] = P->Ei;
+    info[9] = P->Ei; info[10] = P->tp.n_runs; info[11] = P->tp.n_groups; info[12] = P->tp.pull_rows; info[13] = P->tp.max_kstage; info[14] = P->tp.max_mstage;
 }
 void hm_plan_pattern(void *p, int which, int32_t *outer, int32_t *inner) {
     HmPlan *P = (HmPlan *)p;
@@ -105,30 +105,49 @@ void hm_plan_pattern(void *p, int which, int32_t *outer, int32_t *inner) {
     memcpy(outer, o.data(), o.size() * 4);
     if (!in.empty()) memcpy(inner, in.data(), in.size() * 4);
 }
-void hm_plan_fill(void *p, const double *x, const double *X, const double *mat6, const double *grav, double h, double *f, double *Mv, double *Kv) {
+struct HostBulk {   // host stand-in of the device's bulk copy: same alignment contract
+    bool *ok;
+    void operator()(double *dst, const double *src, uint32_t bytes) const {
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || (bytes & 15)) *ok = false;
+        memcpy(dst, src, bytes);
+    }
+};
+// returns 0, or -1 if a bulk copy was issued with a misaligned address / size
+int hm_plan_fill(void *p, const double *x, const double *X, const double *mat6, const double *grav, double h, double *f, double *Mv, double *Kv) {
     HmPlan *P = (HmPlan *)p;
     tiles::FillParams prm;
     prm.mu = membrane_mu(mat6[1], mat6[2]); prm.lam = membrane_lambda(mat6[1], mat6[2]); prm.rho = mat6[0]; prm.beta = mat6[3];
     prm.gx = grav[0]; prm.gy = grav[1]; prm.gz = grav[2]; prm.dhh = mat6[5] * h * h;
     std::vector<double> scr(P->tp.max_scratch + 16, 0.0), xs(3 * (size_t)P->tp.max_loc + 4), Xs(2 * (size_t)P->tp.max_loc + 4);
+    // staging arrays: 16-byte aligned, shifted by the phase of the output pointers like the kernel does; persistent across tiles
+    std::vector<double> kbuf(P->tp.max_kstage + 6, 1e300), mbuf(P->tp.max_mstage + 6, 1e300), fbuf(tiles::MAX_FSTAGE + 6, 1e300);
+    auto align16 = [](double *q) { return (reinterpret_cast<uintptr_t>(q) & 15) ? q + 1 : q; };
+    auto phase = [](const double *q) { return (int)((reinterpret_cast<uintptr_t>(q) >> 3) & 1); };
+    bool ok = true;
+    uint32_t tM_id = 0xffffffffu;
     for (int32_t t = 0; t < P->tp.n_tiles; ++t) {
         const uint32_t *geo = P->tp.geo.data() + (size_t)t * P->tp.max_geo16 * 4;
-        const int nOwn = geo[1] & 255, nLoc = (geo[1] >> 8) & 255;
-        const uint32_t *loc = geo + 4 + 4 * nOwn;
+        const int nLoc = (geo[1] >> 8) & 255;
+        const uint32_t *loc = geo + 4;
         for (int l = 0; l < nLoc; ++l) {
             for (int k = 0; k < 3; ++k) xs[3 * l + k] = x[3 * (size_t)loc[l] + k];
             for (int k = 0; k < 2; ++k) Xs[2 * l + k] = X[2 * (size_t)loc[l] + k];
         }
         for (auto &v : scr) v = 1e300;   // poison: a pull from an unparked slot shows up immediately
-        for (int z = 0; z < tiles::ZPAD; ++z) scr[z] = 0.0;   // the zero block the padded pull lists point at
+        for (int z = 0; z < tiles::ZPAD; ++z) scr[z] = 0.0;   // the zero block the padded pull entries point at
         tiles::TileView V;
         V.geo = geo; V.tmpl = P->tp.tmpl.data() + (size_t)geo[0] * 4; V.tmplB = V.tmpl + (size_t)(geo[2] & 0xffffu) * 4;
         V.xs = xs.data(); V.Xs = Xs.data(); V.scr = scr.data();
-        std::vector<double> kst(P->tp.max_kstage + 2, 1e300), mst(P->tp.max_mstage + 2, 1e300), fst(3 * tiles::MAX_OWN, 1e300);
-        V.kst = kst.data(); V.mst = mst.data(); V.fst = fst.data();
+        V.kst = align16(kbuf.data()) + phase(Kv); V.mst = align16(mbuf.data()) + phase(Mv); V.fst = align16(fbuf.data()) + phase(f);
+        for (auto &v : kbuf) v = 1e300;
+        for (auto &v : fbuf) v = 1e300;
+        const bool m_full = geo[0] != tM_id;   // like the kernel: the M staging keeps the explicit zeros of the resident template
+        tM_id = geo[0];
+        if (m_full) for (auto &v : mbuf) v = 1e300;
         for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase1(tid, V, prm);
-        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase2(tid, tiles::NTHREADS, V);
-        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::copy_out(tid, tiles::NTHREADS, V, f, Mv, Kv);
+        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase2(tid, tiles::NTHREADS, V, m_full);
+        for (int lane = 0; lane < 32; ++lane) tiles::copy_out_runs(lane, 32, V, f, Mv, Kv, HostBulk{&ok});
     }
+    return ok ? 0 : -1;
 }
 }

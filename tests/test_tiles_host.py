@@ -25,6 +25,7 @@ class HostTiles:
         L.hm_plan_destroy.argtypes = [ctypes.c_void_p]
         L.hm_plan_info.argtypes = [ctypes.c_void_p, lp]
         L.hm_plan_pattern.argtypes = [ctypes.c_void_p, ctypes.c_int, ip, ip]
+        L.hm_plan_fill.restype = ctypes.c_int
         L.hm_plan_fill.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, ctypes.c_double, dp, dp, dp]
         fn = np.ascontiguousarray(fn, np.int32).reshape(-1, 3)
         es = np.ascontiguousarray(es, np.int32).reshape(-1, 4)
@@ -34,9 +35,9 @@ class HostTiles:
                                   None if xh is None else xh.ctypes.data_as(dp), int(dedup), err, 256)
         if not self.h:
             raise RuntimeError(err.value.decode())
-        info = np.zeros(10, np.int64)
+        info = np.zeros(16, np.int64)
         L.hm_plan_info(self.h, info.ctypes.data_as(lp))
-        self.info = dict(zip("nnzM nnzK n_tiles n_templates elem_evals geo_bytes tmpl_bytes max_scratch max_loc Ei".split(), info.tolist()))
+        self.info = dict(zip("nnzM nnzK n_tiles n_templates elem_evals geo_bytes tmpl_bytes max_scratch max_loc Ei n_runs n_groups pull_rows max_kstage max_mstage".split(), info.tolist()))
         self.N = N
 
     def pattern(self, which):
@@ -45,20 +46,31 @@ class HostTiles:
         self.L.hm_plan_pattern(self.h, which, o.ctypes.data_as(ip), i.ctypes.data_as(ip))
         return o, i[:nnz]
 
-    def fill(self, x, X, mat=MAT, grav=GRAV, h=H):
+    def fill(self, x, X, mat=MAT, grav=GRAV, h=H, phases=(0, 0, 0)):
+        """phases: 16-byte phase (0 / 1 doubles) of the f, M, MDK output pointers — the bulk copy-out must cope with all of them."""
         x = np.ascontiguousarray(x, np.float64); X = np.ascontiguousarray(X, np.float64)
-        f = np.full(3 * self.N, np.nan); Mv = np.full(self.info["nnzM"], np.nan); Kv = np.full(self.info["nnzK"], np.nan)
+
+        def out(n, ph):
+            buf = np.full(n + 3, np.nan)
+            off = ((-buf.ctypes.data // 8) % 2 + ph) % 2 if buf.ctypes.data % 16 in (0, 8) else 0
+            return buf, buf[off:off + n]
+        (fb, f), (Mb, Mv), (Kb, Kv) = out(3 * self.N, phases[0]), out(self.info["nnzM"], phases[1]), out(self.info["nnzK"], phases[2])
+        for a, ph in ((f, phases[0]), (Mv, phases[1]), (Kv, phases[2])):
+            assert (a.ctypes.data // 8) % 2 == ph
         m = np.array(mat, np.float64); g = np.array(grav, np.float64)
-        self.L.hm_plan_fill(self.h, x.ctypes.data_as(dp), X.ctypes.data_as(dp), m.ctypes.data_as(dp), g.ctypes.data_as(dp), h,
-                            f.ctypes.data_as(dp), Mv.ctypes.data_as(dp), Kv.ctypes.data_as(dp))
+        rc = self.L.hm_plan_fill(self.h, x.ctypes.data_as(dp), X.ctypes.data_as(dp), m.ctypes.data_as(dp), g.ctypes.data_as(dp), h,
+                                 f.ctypes.data_as(dp), Mv.ctypes.data_as(dp), Kv.ctypes.data_as(dp))
+        assert rc == 0, "a bulk copy was issued with a misaligned address or size"
+        for b, a in ((fb, f), (Mb, Mv), (Kb, Kv)):   # nothing written outside the arrays
+            assert np.isnan(b).sum() == b.size - a.size + np.isnan(a).sum()
         return f, Mv, Kv
 
     def close(self):
         self.L.hm_plan_destroy(self.h)
 
 
-def _check(T, fn, es, x, X, oracle, what, mat=MAT, grav=GRAV, h=H):
-    f, Mv, Kv = T.fill(x, X, mat, grav, h)
+def _check(T, fn, es, x, X, oracle, what, mat=MAT, grav=GRAV, h=H, phases=(0, 0, 0)):
+    f, Mv, Kv = T.fill(x, X, mat, grav, h, phases)
     assert not np.isnan(f).any() and not np.isnan(Mv).any() and not np.isnan(Kv).any(), what + ": an output slot was never written"
     ref = oracle.forces_fill(fn, es, x, X, tuple(mat), grav, h)
     N = x.shape[0]
@@ -80,6 +92,8 @@ def test_tiles_host_matches_oracle(oracle, hostmath, gen, n, hint, dedup):
     x = E.meshgen.drape_state(X, seed=n)
     T = HostTiles(hostmath, X.shape[0], fn, es, X if hint else None, dedup)
     _check(T, fn, es, x, X, oracle, f"{gen}{n}")
+    _check(T, fn, es, x, X, oracle, f"{gen}{n} odd phases", phases=(1, 1, 1))
+    _check(T, fn, es, x, X, oracle, f"{gen}{n} mixed phases", phases=(0, 1, 0))
     assert T.info["elem_evals"] >= len(fn) + T.info["Ei"]
     T.close()
 
