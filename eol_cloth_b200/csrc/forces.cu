@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
             EOLC_CLK(2)
             const int ta1 = (int)ctl[0];
             tiles::phase2((int)tid, (int)NC, V, ctl[1] != 0u);
+            asm volatile("bar.sync 1, %0;" ::"n"(tiles::NTHREADS) : "memory");   // compute warps only: off-diagonal and mass blocks staged
+            tiles::phase3((int)tid, V);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk-copy engine
             EOLC_CLK(3)
             EOLC_SYNC();                 // [B2] the scratch may be overwritten by the next phase 1

@@ -14,6 +14,7 @@
 // Tiles with identical local structure (all interior tiles of a regular sheet) share one template.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -123,27 +124,28 @@ constexpr int CTA_THREADS = NTHREADS + 128;   // + one service warpgroup: stages
 constexpr int CTAS_PER_SM = 1;
 constexpr int MAX_OWN = EOLC_TILE_OWN;   // nodes owned by a tile (<= 63: 6-bit fields)
 constexpr int MAX_LOC = 128;         // distinct nodes referenced by a tile's elements (8-bit local ids)
-constexpr int EDGE_STRIDE = 86;      // doubles parked per bending stencil: 4 diagonal blocks x 6, 6 off-diagonal x 10 (+2: bank spread)
-constexpr int FACE_STRIDE = 62;      // doubles parked per face: 3 x (diag 6 + force 3 + pad) + 3 x (off 9 + pad), t8 in the first pad
-constexpr int FACE_T8 = 39;          // offset of t8 (rho * 2A) inside a face slot
+// Only OFF-DIAGONAL element blocks are parked: every element matrix has zero row sums (translation invariance; the mass part sums
+// to t8/6 per row), so the diagonal block of a node is  2 M_aa - sum of the off-diagonal blocks of its row  (phase 3).
+constexpr int EDGE_STRIDE = 62;      // doubles parked per bending stencil: 6 off-diagonal blocks x 10 (9 + pad) (+2: odd number of 16-byte units)
+constexpr int FACE_STRIDE = 42;      // doubles parked per face: 3 off-diagonal blocks x 10, forces 3 x 4 (3 + pad), t8 in the first force pad
+constexpr int FACE_T8 = 33;          // offset of t8 (rho * 2A) inside a face slot
 constexpr int ZPAD = 16;             // doubles at the start of the scratch that stay zero: padded pull entries (offset 0) read the zero block
 constexpr int MAX_SCRATCH_DOUBLES = 20480;   // 160 KB of parked blocks per tile
-constexpr int MAX_KSTAGE = 4096 + 2 * MAX_OWN;   // doubles of MDK rows one tile stages in shared memory before the bulk copy-out
-constexpr int MAX_MSTAGE = 2304 + 2 * MAX_OWN;   // doubles of M rows one tile stages (expanded blocks: m on the block diagonal, explicit zeros off it)
+constexpr int MAX_KSTAGE = 130 * MAX_OWN;          // doubles of MDK rows one tile stages in shared memory before the bulk copy-out
+constexpr int MAX_MSTAGE = 74 * MAX_OWN;           // doubles of M rows one tile stages (expanded blocks: m on the block diagonal, explicit zeros off it)
 constexpr int MAX_FSTAGE = 4 * MAX_OWN + 4;        // doubles of f one tile stages
 constexpr int MAX_ITER = 255;        // PAIRS of contributions per loop of one phase-2 group (8-bit fields)
 constexpr int GROUP = 32;            // phase-2 records per group (one warp)
 
 // smem offsets (in doubles) of the parked blocks inside an element slot
-inline int edge_diag_off(int i) { return 6 * i; }
-inline int edge_off_off(int lo, int hi) { static const int k[4][4] = {{-1, 0, 1, 2}, {0, -1, 3, 4}, {1, 3, -1, 5}, {2, 4, 5, -1}}; return 24 + 10 * k[lo][hi]; }
-inline int face_diag_off(int v) { return 10 * v; }
-inline int face_off_off(int lo, int hi) { static const int k[3][3] = {{-1, 0, 1}, {0, -1, 2}, {1, 2, -1}}; return 30 + 10 * k[lo][hi]; }
+inline int edge_off_off(int lo, int hi) { static const int k[4][4] = {{-1, 0, 1, 2}, {0, -1, 3, 4}, {1, 3, -1, 5}, {2, 4, 5, -1}}; return 10 * k[lo][hi]; }
+inline int face_off_off(int lo, int hi) { static const int k[3][3] = {{-1, 0, 1}, {0, -1, 2}, {1, 2, -1}}; return 10 * k[lo][hi]; }
+inline int face_force_off(int v) { return 30 + 4 * v; }
 
 // Phase 2 works in GROUPS of 32 records of one kind (one warp per group, one record per lane); every lane of a group runs the
 // group's trip counts (shorter lists are padded with offset 0 = the zero block), so the loops are warp-uniform and the pull
 // entries are stored transposed: entry of (trip r, lane l) at pulls[base + 32 r + l] (conflict-free, two 16-bit offsets each).
-//   kind D (diagonal MDK block + f of an owned node): loop A = face pairs (6 + 3 doubles each), loop B = stencil pairs (6 doubles)
+//   kind D (f of an owned node): loop A = the forces of its faces (3 doubles each).  Its diagonal MDK block comes from phase 3.
 //   kind O (off-diagonal MDK block (own, p)): loop A = contributions parked in this orientation, loop B = parked transposed.  If the
 //          column node is owned by the same tile (has2) the record also writes the mirrored block (own2, p2) = transpose, and
 //          the mirrored pair has no record of its own.
@@ -157,7 +159,8 @@ enum { KIND_D = 0, KIND_O = 1, KIND_M = 2 };
 // Template = part A (phase 1) + part B (phase 2), u32 words, every section padded to 16 bytes:
 //   A: [nE | nF << 16, 0, 0, 0] [items: nE stencils (4 local ids, 8 bits each) then nF faces (3 local ids)]
 //      stencil slot s is evaluated by thread s, face slot s by thread roundup32(nE) + s (kinds are warp aligned)
-//   B: [nOwn | nGroups << 8, 0, 0, 0] [degs: degK | degM << 8 per owned node] [offsKM: staging offset of the node's MDK rows | M rows << 16]
+//   B: [nOwn | nGroups << 8, 0, 0, 0] [degs: degK | degM << 8 | position of the diagonal block in the MDK row << 16 | in the M row << 24
+//      per owned node] [offsKM: staging offset of the node's MDK rows | M rows << 16]
 //      [offsF: staging offset of the node's f] [groups: 4 words each: kind | nA << 8 | nB << 16, pull base, 0, 0] [records: 32 x u64 per
 //      group] [pulls]
 //      groups are sorted by descending cost; warp w takes groups w, 15 - w, 16 + w, 31 - w, ... (snake order)
@@ -287,7 +290,47 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
     std::vector<int32_t> idx(N);
     for (int32_t a = 0; a < N; ++a) idx[a] = a;
     std::vector<std::pair<size_t, size_t>> leaves;
-    rcb(idx, 0, (size_t)N, ((size_t)N + MAX_OWN - 1) / MAX_OWN, cx.data(), cy.data(), leaves);
+    if ((MAX_OWN & (MAX_OWN - 1)) == 0 || !X_hint) {
+        rcb(idx, 0, (size_t)N, ((size_t)N + MAX_OWN - 1) / MAX_OWN, cx.data(), cy.data(), leaves);
+    } else {
+        // Tile sizes that are not a power of two: bisection leaves ragged tiles on structured meshes.  Snapped strip tiling instead:
+        // strips of ~sqrt(MAX_OWN) node columns along x, cut into chunks of <= MAX_OWN nodes along y; every cut moves to the nearest
+        // place where the sort coordinate changes (structured meshes: whole columns / rows), if there is one close by.
+        auto snapped_cuts = [&](size_t lo, size_t hi, double want, const double *c, std::vector<size_t> &cuts) {
+            cuts.clear();
+            cuts.push_back(lo);
+            const size_t n = hi - lo;
+            const size_t parts = std::max<size_t>(1, (size_t)((double)n / want + 0.999));
+            for (size_t k = 1; k < parts; ++k) {
+                size_t at = lo + (size_t)((double)n * (double)k / (double)parts + 0.5);
+                const size_t reach = (size_t)(want / 3.0) + 1;
+                size_t best = at;
+                bool found = false;
+                for (size_t d = 0; d <= reach && !found; ++d) {
+                    if (at + d < hi && at + d > lo && c[idx[at + d]] != c[idx[at + d - 1]]) { best = at + d; found = true; }
+                    else if (at >= lo + d + 1 && at - d > lo && c[idx[at - d]] != c[idx[at - d - 1]]) { best = at - d; found = true; }
+                }
+                if (best > cuts.back() && best < hi) cuts.push_back(best);
+            }
+            cuts.push_back(hi);
+        };
+        std::sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { if (cx[a] != cx[b]) return cx[a] < cx[b]; if (cy[a] != cy[b]) return cy[a] < cy[b]; return a < b; });
+        // nodes per strip: (number of distinct-ish columns per strip) x (nodes per column); estimate the column population from the data
+        size_t ncol = 1;
+        for (int32_t i = 1; i < N; ++i) if (cx[idx[i]] != cx[idx[i - 1]]) ++ncol;
+        const double per_col = (double)N / (double)ncol;
+        int side = 1;
+        while ((side + 1) * (side + 1) <= MAX_OWN) ++side;
+        const double strip_nodes = ncol * 4 >= (size_t)N ? (double)side * std::max(1.0, std::sqrt((double)N)) : (double)side * per_col;
+        std::vector<size_t> scuts, ccuts;
+        snapped_cuts(0, (size_t)N, strip_nodes, cx.data(), scuts);
+        for (size_t s = 0; s + 1 < scuts.size(); ++s) {
+            const size_t lo = scuts[s], hi = scuts[s + 1];
+            std::sort(idx.begin() + lo, idx.begin() + hi, [&](int32_t a, int32_t b) { if (cy[a] != cy[b]) return cy[a] < cy[b]; if (cx[a] != cx[b]) return cx[a] < cx[b]; return a < b; });
+            snapped_cuts(lo, hi, (double)MAX_OWN, cy.data(), ccuts);
+            for (size_t c = 0; c + 1 < ccuts.size(); ++c) leaves.push_back({ccuts[c], ccuts[c + 1]});
+        }
+    }
     // ---- split leaves that exceed the kernel's capacities
     std::vector<int32_t> faces, edges;
     {
@@ -389,6 +432,8 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             const int deg = (int)(pat.blkptrK[a + 1] - b0), degM = (int)(pat.blkptrM[a + 1] - m0);
             if (deg > 255) { P.error = "node " + std::to_string(a) + " has more than 255 neighbours"; return false; }
             degs[o] = (uint32_t)deg | ((uint32_t)degM << 8);
+            if (deg) degs[o] |= (uint32_t)(find_block(pat.blkptrK, pat.nbrK, a, a) - b0) << 16;
+            if (degM) degs[o] |= (uint32_t)(find_block(pat.blkptrM, pat.nbrM, a, a) - m0) << 24;
             for (int p = 0; p < std::max(deg, 1); ++p) {
                 const int32_t b = deg ? pat.nbrK[b0 + p] : a;
                 const int ob = b == a ? -1 : owned_index(b);
@@ -400,7 +445,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                     const int va = B.nfl[k] & 3, sf = B.fslot[f];
                     const int32_t *v = fn + 3 * (size_t)f;
                     const int base = fbase + sf * FACE_STRIDE;
-                    if (b == a) { R.A.push_back((uint16_t)(base + face_diag_off(va))); Rm.A.push_back((uint16_t)(base + FACE_T8)); continue; }
+                    if (b == a) { R.A.push_back((uint16_t)(base + face_force_off(va))); Rm.A.push_back((uint16_t)(base + FACE_T8)); continue; }
                     for (int vj = 0; vj < 3; ++vj)
                         if (v[vj] == b) {
                             (va < vj ? R.A : R.B).push_back((uint16_t)(base + face_off_off(std::min(va, vj), std::max(va, vj))));
@@ -412,7 +457,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                     const int ia = B.nel[k] & 3, se = B.eslot[e];
                     const int32_t *v = ie + 4 * (size_t)e;
                     const int base = ZPAD + se * EDGE_STRIDE;
-                    if (b == a) { R.B.push_back((uint16_t)(base + edge_diag_off(ia))); continue; }   // D: loop B = stencils
+                    if (b == a) continue;                // diagonal block: phase 3
                     for (int ij = 0; ij < 4; ++ij)
                         if (v[ij] == b) (ia < ij ? R.A : R.B).push_back((uint16_t)(base + edge_off_off(std::min(ia, ij), std::max(ia, ij))));
                 }
@@ -443,7 +488,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                 Grp G{kind, 0, 0, (int)g0, 0};
                 for (size_t k = g0; k < std::min(rv.size(), g0 + GROUP); ++k) { G.nA = std::max(G.nA, pairs(rv[k].A)); G.nB = std::max(G.nB, pairs(rv[k].B)); }
                 if (G.nA > MAX_ITER || G.nB > MAX_ITER) { P.error = "tile " + std::to_string(t) + ": contribution list overflow"; return false; }
-                G.cost = kind == KIND_D ? 10 + 10L * G.nA + 6L * G.nB : kind == KIND_O ? 18 + 10L * (G.nA + G.nB) : 6 + 2L * G.nA;
+                G.cost = kind == KIND_D ? 6 + 4L * G.nA : kind == KIND_O ? 18 + 10L * (G.nA + G.nB) : 6 + 2L * G.nA;
                 groups.push_back(G);
             }
         }

@@ -4,7 +4,8 @@
 //   phase 1   thread t < nE evaluates bending stencil t, thread nEpad <= t < nEpad + nF evaluates face t - nEpad (nEpad = nE rounded up to a warp)
 //             (elements.cuh: edge_element_tile / face_element_tile) and parks the element blocks in `scr`
 //   phase 2   every output block of the tile's nodes pulls its contributions from `scr` in the plan's fixed order into staged
-//             rows (D: diagonal MDK block + f, O: off-diagonal MDK block, M: mass block)
+//             rows (D: f, O: off-diagonal MDK block, M: mass block)
+//   phase 3   diagonal MDK blocks from the row sums of the staged rows
 //   copy-out  runs of staged rows leave for their CSR slots with one bulk copy each
 // Data layouts: forces_plan.h.  Replaces Forces.cpp:333-397,498-518 (faces), :687-744,885-908 (edges), :925-929 (assembly).
 #pragma once
@@ -60,23 +61,23 @@ EOLC_HD void stg(double *p, double v) {
 #endif
 }
 
-struct ParkEdge {   // slot layout: diagonal block i at 6 i (xx xy xz yy yz zz), off-diagonal block k at 24 + 10 k (8 + 1, 1 pad)
-    double *s;
-    EOLC_HD void diag(int i, const sym3 &S) { st2(s + 6 * i, S.xx, S.xy); st2(s + 6 * i + 2, S.xz, S.yy); st2(s + 6 * i + 4, S.yz, S.zz); }
+struct ParkEdge {   // slot layout: off-diagonal block k (K_01, K_02, K_03, K_12, K_13, K_23) at 10 k (8 + 1, 1 pad).  The diagonal
+    double *s;      // blocks are not parked: phase 3 rebuilds a node's diagonal block from the row sums (forces_plan.h)
+    EOLC_HD void diag(int, const sym3 &) {}
     EOLC_HD void off(int k, const blk3 &B) {
-        double *d = s + 24 + 10 * k;
+        double *d = s + 10 * k;
         st2(d, B.m[0], B.m[1]); st2(d + 2, B.m[2], B.m[3]); st2(d + 4, B.m[4], B.m[5]); st2(d + 6, B.m[6], B.m[7]); d[8] = B.m[8];
     }
 };
-struct ParkFace {   // diagonal block v at 10 v (6) + force of vertex v at 10 v + 6 (3); off-diagonal k at 30 + 10 k; t8 at 39
+struct ParkFace {   // off-diagonal block k (K_ab, K_ac, K_bc) at 10 k; force of vertex v at 30 + 4 v; t8 at 33
     double *s;
-    EOLC_HD void diag(int i, const sym3 &S) { st2(s + 10 * i, S.xx, S.xy); st2(s + 10 * i + 2, S.xz, S.yy); st2(s + 10 * i + 4, S.yz, S.zz); }
+    EOLC_HD void diag(int, const sym3 &) {}
     EOLC_HD void off(int k, const blk3 &B) {
-        double *d = s + 30 + 10 * k;
+        double *d = s + 10 * k;
         st2(d, B.m[0], B.m[1]); st2(d + 2, B.m[2], B.m[3]); st2(d + 4, B.m[4], B.m[5]); st2(d + 6, B.m[6], B.m[7]); d[8] = B.m[8];
     }
-    EOLC_HD void force(int i, v3 v) { st2(s + 10 * i + 6, v.x, v.y); s[10 * i + 8] = v.z; }
-    EOLC_HD void mass(double m) { s[39] = m; }
+    EOLC_HD void force(int i, v3 v) { st2(s + 30 + 4 * i, v.x, v.y); s[30 + 4 * i + 2] = v.z; }
+    EOLC_HD void mass(double m) { s[FACE_T8] = m; }
 };
 
 EOLC_HD v3 ldx(const double *xs, uint32_t l) { return mk3(xs[3 * l], xs[3 * l + 1], xs[3 * l + 2]); }
@@ -133,41 +134,21 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
             const uint32_t p = (uint32_t)rec & 255u, own = (uint32_t)(rec >> 8) & 63u;
             const bool valid = (rec >> 30) & 1ull, has2 = (rec >> 28) & 1ull;
             if (kind == KIND_D) {
-                // ---- diagonal MDK block (symmetric) + f of the node: faces (f.setZero() then +=, Forces.cpp:915,500-502), then stencils
-                double xx = 0.0, xy = 0.0, xz = 0.0, yy = 0.0, yz = 0.0, zz = 0.0, f0 = 0.0, f1 = 0.0, f2 = 0.0;
+                // ---- f of the node: its faces in ascending order (f.setZero() then +=, Forces.cpp:915,500-502)
+                double f0 = 0.0, f1 = 0.0, f2 = 0.0;
                 EOLC_UNROLL_P2
                 for (int k = 0; k < nA; ++k, pl += GROUP) {
                     const double *s0, *s1;
                     pull2(*pl, scr, s0, s1);
-                    double a, b, c, d, e, g_, h, j, a1, b1, c1_, d1, e1, g1, h1, j1;
-                    ld2(s0, a, b); ld2(s0 + 2, c, d); ld2(s0 + 4, e, g_); ld2(s0 + 6, h, j);
-                    ld2(s1, a1, b1); ld2(s1 + 2, c1_, d1); ld2(s1 + 4, e1, g1); ld2(s1 + 6, h1, j1);
-                    const double q = s0[8], q1 = s1[8];
-                    xx += a; xy += b; xz += c; yy += d; yz += e; zz += g_; f0 += h; f1 += j; f2 += q;
-                    xx += a1; xy += b1; xz += c1_; yy += d1; yz += e1; zz += g1; f0 += h1; f1 += j1; f2 += q1;
-                }
-                EOLC_UNROLL_P2
-                for (int k = 0; k < nB; ++k, pl += GROUP) {
-                    const double *s0, *s1;
-                    pull2(*pl, scr, s0, s1);
-                    double a, b, c, d, e, g_, a1, b1, c1_, d1, e1, g1;
-                    ld2(s0, a, b); ld2(s0 + 2, c, d); ld2(s0 + 4, e, g_);
-                    ld2(s1, a1, b1); ld2(s1 + 2, c1_, d1); ld2(s1 + 4, e1, g1);
-                    xx += a; xy += b; xz += c; yy += d; yz += e; zz += g_;
-                    xx += a1; xy += b1; xz += c1_; yy += d1; yz += e1; zz += g1;
+                    double h, j, h1, j1;
+                    ld2(s0, h, j); ld2(s1, h1, j1);
+                    const double q = s0[2], q1 = s1[2];
+                    f0 += h; f1 += j; f2 += q;
+                    f0 += h1; f1 += j1; f2 += q1;
                 }
                 if (valid) {
                     double *fo = V.fst + offsF[own];
                     fo[0] = f0; fo[1] = f1; fo[2] = f2;
-                    const uint32_t deg = degs[own] & 255u;
-                    if (deg) {
-                        double *row = V.kst + (offsKM[own] & 0xffffu) + 3 * p;
-                        row[0] = xx; row[1] = xy; row[2] = xz;
-                        row += 3 * deg;
-                        row[0] = xy; row[1] = yy; row[2] = yz;
-                        row += 3 * deg;
-                        row[0] = xz; row[1] = yz; row[2] = zz;
-                    }
                 }
             } else if (kind == KIND_O) {
                 // ---- off-diagonal MDK block: contributions are parked as K_(lo,hi) of the element; the ones whose row vertex comes
@@ -229,7 +210,7 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                     for (int side = 0; side < 2; ++side) {
                         if (side && !has2) break;
                         const uint32_t o_ = side ? (uint32_t)(rec >> 22) & 63u : own, p_ = side ? (uint32_t)(rec >> 14) & 255u : p;
-                        const uint32_t deg = degs[o_] >> 8;
+                        const uint32_t deg = (degs[o_] >> 8) & 255u;
                         double *row = V.mst + (offsKM[o_] >> 16) + 3 * p_;
                         if (m_full) {
                             row[0] = m; row[1] = 0.0; row[2] = 0.0;
@@ -245,6 +226,36 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
             }
         }
     }
+}
+
+// Phase 3 (after a barrier: all off-diagonal blocks and mass blocks of the tile's rows are staged): the diagonal MDK block of every
+// owned node.  Each element matrix has zero row sums apart from the mass part (t8/12 + 2 t8/24 = t8/6 per row), so
+//     MDK_aa = 2 M_aa I - sum over b != a of MDK_ab           (M_aa = sum of t8/12 over the node's faces)
+// Thread t handles entry (j, k), j <= k, of node t / 6 and mirrors it: exactly symmetric like the reference's diagonal blocks.
+EOLC_HD void phase3(int tid, const TileView &V) {
+    const uint32_t h0 = V.tmplB[0];
+    const int nOwn = (int)(h0 & 255u), n4 = (nOwn + 3) & ~3;
+    if (tid >= 6 * nOwn) return;
+    const uint32_t *degs = V.tmplB + 4, *offsKM = degs + n4;
+    const int o = tid / 6, e = tid - 6 * o;
+    const int j = e < 3 ? 0 : (e < 5 ? 1 : 2), k = e < 3 ? e : (e < 5 ? e - 2 : 2);
+    const uint32_t dw = degs[o];
+    const int deg = (int)(dw & 255u), pd = (int)((dw >> 16) & 255u), pdM = (int)(dw >> 24);
+    if (!deg) return;
+    double *rows = V.kst + (offsKM[o] & 0xffffu);
+    const double *r = rows + 3 * deg * j + k;
+    // four interleaved partial sums in a fixed order (the loads of a trip are independent: no add-latency chain per block)
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int p = 0;
+    for (; p + 4 <= deg; p += 4) {
+        const double v0 = r[3 * p], v1 = r[3 * p + 3], v2 = r[3 * p + 6], v3 = r[3 * p + 9];
+        acc0 += p == pd ? 0.0 : v0; acc1 += p + 1 == pd ? 0.0 : v1; acc2 += p + 2 == pd ? 0.0 : v2; acc3 += p + 3 == pd ? 0.0 : v3;
+    }
+    for (; p < deg; ++p) acc0 += p == pd ? 0.0 : r[3 * p];
+    const double acc = (acc0 + acc1) + (acc2 + acc3);
+    const double v = (j == k ? 2.0 * V.mst[(offsKM[o] >> 16) + 3 * pdM] : 0.0) - acc;
+    rows[3 * deg * j + 3 * pd + k] = v;
+    if (j != k) rows[3 * deg * k + 3 * pd + j] = v;
 }
 
 // Copy-out: every run of staged rows (rows of owned nodes with consecutive ids) goes to its CSR slot with ONE bulk copy

@@ -146,6 +146,7 @@ int hm_plan_fill(void *p, const double *x, const double *X, const double *mat6, 
         if (m_full) for (auto &v : mbuf) v = 1e300;
         for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase1(tid, V, prm);
         for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase2(tid, tiles::NTHREADS, V, m_full);
+        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase3(tid, V);
         for (int lane = 0; lane < 32; ++lane) tiles::copy_out_runs(lane, 32, V, f, Mv, Kv, HostBulk{&ok});
     }
     return ok ? 0 : -1;
