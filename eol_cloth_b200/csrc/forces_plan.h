@@ -7,8 +7,8 @@
 // nbrK(a) = nbrM(a) + nodes sharing a bending stencil (Forces.cpp:692-697).  Column-major == row-major (symmetric pattern);
 // the values of node a's three rows are stored at 9*blkptr[a] + j*3*deg(a) + 3*p + k.
 //
-// Tiles: the nodes are partitioned into spatially compact tiles of <= MAX_OWN nodes (recursive coordinate bisection of the
-// material coordinates).  A tile evaluates every face / bending stencil that touches one of its nodes ONCE, parks the
+// Tiles: the nodes are partitioned into spatially compact tiles of <= MAX_OWN nodes (snapped strips / recursive coordinate
+// bisection of the material coordinates).  A tile evaluates every face / bending stencil that touches one of its nodes ONCE, parks the
 // element blocks in shared memory and then every output block of its nodes pulls its contributions in a fixed order
 // (faces ascending, then stencils ascending; not-transposed before transposed) — deterministic, no atomics.
 // Tiles with identical local structure (all interior tiles of a regular sheet) share one template.
@@ -119,7 +119,9 @@ namespace tiles {
 #ifndef EOLC_TILE_OWN
 #define EOLC_TILE_OWN 32
 #endif
-constexpr int NTHREADS = 256;        // compute threads per CTA = element slots per tile (phase 1: stencil warps first, then face warps)
+constexpr int NTHREADS = 256;        // compute threads per CTA: phase 1 evaluates one element per thread (stencils from thread 0 up, faces from
+                                     // the last thread down), phases 2 and 3 run on the same threads
+constexpr int P2THREADS = NTHREADS;
 constexpr int CTA_THREADS = NTHREADS + 128;   // + one service warpgroup: stages the inputs of the tiles ahead, issues the bulk copy-out
 constexpr int CTAS_PER_SM = 1;
 constexpr int MAX_OWN = EOLC_TILE_OWN;   // nodes owned by a tile (<= 63: 6-bit fields)
@@ -129,8 +131,9 @@ constexpr int MAX_LOC = 128;         // distinct nodes referenced by a tile's el
 constexpr int EDGE_STRIDE = 62;      // doubles parked per bending stencil: 6 off-diagonal blocks x 10 (9 + pad) (+2: odd number of 16-byte units)
 constexpr int FACE_STRIDE = 42;      // doubles parked per face: 3 off-diagonal blocks x 10, forces 3 x 4 (3 + pad), t8 in the first force pad
 constexpr int FACE_T8 = 33;          // offset of t8 (rho * 2A) inside a face slot
-constexpr int ZPAD = 16;             // doubles at the start of the scratch that stay zero: padded pull entries (offset 0) read the zero block
-constexpr int MAX_SCRATCH_DOUBLES = 20480;   // 160 KB of parked blocks per tile
+constexpr int ZPAD = 32;             // doubles at the start of the scratch that stay zero: padded pull entries read a zero block there (any
+                                     // even offset <= 14, chosen by bank)
+constexpr int MAX_SCRATCH_DOUBLES = 14336;   // 112 KB of parked blocks per tile
 constexpr int MAX_KSTAGE = 130 * MAX_OWN;          // doubles of MDK rows one tile stages in shared memory before the bulk copy-out
 constexpr int MAX_MSTAGE = 74 * MAX_OWN;           // doubles of M rows one tile stages (expanded blocks: m on the block diagonal, explicit zeros off it)
 constexpr int MAX_FSTAGE = 4 * MAX_OWN + 4;        // doubles of f one tile stages
@@ -158,8 +161,8 @@ enum { KIND_D = 0, KIND_O = 1, KIND_M = 2 };
 
 // Template = part A (phase 1) + part B (phase 2), u32 words, every section padded to 16 bytes:
 //   A: [nE | nF << 16, 0, 0, 0] [items: nE stencils (4 local ids, 8 bits each) then nF faces (3 local ids)]
-//      stencil slot s is evaluated by thread s, face slot s by thread roundup32(nE) + s (kinds are warp aligned)
-//   B: [nOwn | nGroups << 8, 0, 0, 0] [degs: degK | degM << 8 | position of the diagonal block in the MDK row << 16 | in the M row << 24
+//      stencil slot s is evaluated by thread s % 256, face slot s by thread 255 - s % 256
+//   B: [nOwn | nGroups << 8, word offset of the phase-3 items, number of phase-3 items, 0] [degs: degK | degM << 8 | position of the diagonal block in the MDK row << 16 | in the M row << 24
 //      per owned node] [offsKM: staging offset of the node's MDK rows | M rows << 16]
 //      [offsF: staging offset of the node's f] [groups: 4 words each: kind | nA << 8 | nB << 16, pull base, 0, 0] [records: 32 x u64 per
 //      group] [pulls]
@@ -211,8 +214,7 @@ struct Builder {
             for (int32_t k = nep[a]; k < nep[a + 1]; ++k) { int32_t e = nel[k] >> 2; if (estamp[e] != stamp) { estamp[e] = stamp; edges.push_back(e); } }
         }
         const int nE = (int)edges.size(), nF = (int)faces.size();
-        const int nEpad = (nE + 31) / 32 * 32;
-        if (n_own > MAX_OWN || nEpad + nF > NTHREADS) return false;
+        if (n_own > MAX_OWN || nE > 0xffff || nF > 0xffff) return false;
         if (ZPAD + (int64_t)nE * EDGE_STRIDE + (int64_t)nF * FACE_STRIDE > MAX_SCRATCH_DOUBLES) return false;
         int64_t kst = 0, mst = 0;
         for (int o = 0; o < n_own; ++o) { kst += 9 * (pat.blkptrK[own[o] + 1] - pat.blkptrK[own[o]]) + 2; mst += 9 * (pat.blkptrM[own[o] + 1] - pat.blkptrM[own[o]]) + 2; }
@@ -253,6 +255,173 @@ struct RecTmp {
     uint64_t rec;
     std::vector<uint16_t> A, B;    // pull offsets of loop A / loop B (single entries, paired when serialised)
 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Bank-aware layout of one template (post-pass over the unique templates; sizes do not change).
+// The block pulls of phase 2 are 128-bit loads, served a quarter warp at a time: the 8 lanes' 16-byte pieces are fetched in one
+// wavefront if they fall into 8 different bank groups, i.e. if (block offset / 2) mod 8 differs; otherwise the quarter takes as many
+// wavefronts as its fullest bank group holds distinct addresses.  Two freedoms do not change any result's meaning:
+//   (1) the slot of an element (the bank group of its blocks depends on slot mod 8): local search over slot swaps,
+//   (2) the order in which a record adds its contributions (still fixed by the plan, hence deterministic): per quarter warp and
+//       list position, every lane greedily takes the remaining contribution in the least used bank group; exhausted lanes read
+//       a zero block placed in the least used group.
+// ---------------------------------------------------------------------------------------------------------------------
+inline void optimize_template(uint32_t *T, uint32_t sizeA16, int iters) {
+    uint32_t *A = T, *B = T + (size_t)sizeA16 * 4;
+    const int nE = (int)(A[0] & 0xffffu), nF = (int)(A[0] >> 16);
+    const int nOwn = (int)(B[0] & 255u), nG = (int)((B[0] >> 8) & 255u), n4 = (nOwn + 3) & ~3;
+    uint32_t *grp = B + 4 + 3 * n4;
+    uint32_t *pulls = grp + 4 * nG + 2 * GROUP * nG;
+    const int fbase = ZPAD + nE * EDGE_STRIDE;
+    struct Ref { int elem; int boff; };                   // elem: stencil e -> e, face f -> nE + f; -1: zero pad
+    auto decode = [&](uint32_t off) {
+        Ref r{-1, 0};
+        if ((int)off >= fbase) { r.elem = nE + ((int)off - fbase) / FACE_STRIDE; r.boff = ((int)off - fbase) % FACE_STRIDE; }
+        else if ((int)off >= ZPAD) { r.elem = ((int)off - ZPAD) / EDGE_STRIDE; r.boff = ((int)off - ZPAD) % EDGE_STRIDE; }
+        return r;
+    };
+    std::vector<int> slot((size_t)nE + nF);               // element -> slot within its kind
+    for (int e = 0; e < nE; ++e) slot[e] = e;
+    for (int f = 0; f < nF; ++f) slot[nE + f] = f;
+    auto offset_of = [&](const Ref &r) { return r.elem < nE ? ZPAD + slot[r.elem] * EDGE_STRIDE + r.boff : fbase + slot[r.elem] * FACE_STRIDE + r.boff; };
+    // ---- quarter rows of the O groups: up to 8 references that one 128-bit load instruction serves together
+    struct QRow { Ref ref[8]; int n; };
+    std::vector<QRow> rows;
+    std::vector<std::vector<int>> inc((size_t)nE + nF);   // element -> rows it appears in
+    for (int g = 0; g < nG; ++g) {
+        if ((grp[4 * g] & 255u) != (uint32_t)KIND_O) continue;
+        const int nrows = (int)((grp[4 * g] >> 8) & 255u) + (int)((grp[4 * g] >> 16) & 255u);
+        const uint32_t *pl = pulls + grp[4 * g + 1];
+        for (int r = 0; r < nrows; ++r)
+            for (int half = 0; half < 2; ++half)
+                for (int q = 0; q < GROUP / 8; ++q) {
+                    QRow R; R.n = 0;
+                    for (int l = 0; l < 8; ++l) {
+                        const uint32_t e = pl[r * GROUP + 8 * q + l];
+                        const Ref rf = decode(half ? e >> 16 : e & 0xffffu);
+                        if (rf.elem < 0) continue;
+                        bool dup = false;
+                        for (int k = 0; k < R.n; ++k) dup |= R.ref[k].elem == rf.elem && R.ref[k].boff == rf.boff;
+                        if (!dup) R.ref[R.n++] = rf;
+                    }
+                    if (R.n > 1) {
+                        for (int k = 0; k < R.n; ++k) inc[R.ref[k].elem].push_back((int)rows.size());
+                        rows.push_back(R);
+                    }
+                }
+    }
+    for (auto &v : inc) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    auto row_cost = [&](const QRow &R) {                  // wavefronts of the quarter (x 16) + a tie breaker that favours even spreading
+        int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < R.n; ++k) ++cnt[(offset_of(R.ref[k]) >> 1) & 7];
+        int mx = 0, sq = 0;
+        for (int c = 0; c < 8; ++c) { mx = std::max(mx, cnt[c]); sq += cnt[c] * cnt[c]; }
+        return 16 * mx + sq;
+    };
+    if (iters > 0 && !rows.empty()) {
+        std::vector<int> cost(rows.size());
+        for (size_t r = 0; r < rows.size(); ++r) cost[r] = row_cost(rows[r]);
+        uint64_t rng = 0x9e3779b97f4a7c15ull;
+        auto next = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); };
+        std::vector<int> touched;
+        auto eval_swap = [&](int e0, int e1) {            // cost change of swapping the slots of e0 and e1 (same kind)
+            touched.clear();
+            touched.insert(touched.end(), inc[e0].begin(), inc[e0].end());
+            touched.insert(touched.end(), inc[e1].begin(), inc[e1].end());
+            std::sort(touched.begin(), touched.end());
+            touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+            std::swap(slot[e0], slot[e1]);
+            int d = 0;
+            for (int r : touched) d += row_cost(rows[r]) - cost[r];
+            std::swap(slot[e0], slot[e1]);
+            return d;
+        };
+        size_t cursor = 0;
+        for (int it = 0; it < iters; ++it) {
+            // next row with a conflict (round robin)
+            size_t r = cursor, tried = 0;
+            for (; tried < rows.size(); ++tried, r = (r + 1) % rows.size()) {
+                int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+                for (int k = 0; k < rows[r].n; ++k) mx = std::max(mx, ++cnt[(offset_of(rows[r].ref[k]) >> 1) & 7]);
+                if (mx > 1) break;
+            }
+            if (tried == rows.size()) break;              // conflict free
+            cursor = (r + 1) % rows.size();
+            const QRow &R = rows[r];
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < R.n; ++k) ++cnt[(offset_of(R.ref[k]) >> 1) & 7];
+            int pick = -1;
+            for (int k = 0, seen = 0; k < R.n; ++k)
+                if (cnt[(offset_of(R.ref[k]) >> 1) & 7] > 1 && (next() % (uint32_t)(++seen)) == 0) pick = k;
+            const int e0 = R.ref[pick].elem;
+            const int lo = e0 < nE ? 0 : nE, n = e0 < nE ? nE : nF;
+            int best = -1, bestd = 1;
+            for (int c = 0; c < 12; ++c) {
+                const int e1 = lo + (int)(next() % (uint32_t)n);
+                if (e1 == e0 || (slot[e1] & 7) == (slot[e0] & 7)) continue;
+                const int d = eval_swap(e0, e1);
+                if (d < bestd || (d == bestd && d <= 0 && (next() & 1))) { bestd = d; best = e1; }
+            }
+            if (best >= 0 && bestd <= 0) {
+                eval_swap(e0, best);                      // fills `touched`
+                std::swap(slot[e0], slot[best]);
+                for (int rr : touched) cost[rr] = row_cost(rows[rr]);
+            }
+        }
+    }
+    // ---- apply the slots: items (part A) and every pull entry (part B)
+    {
+        std::vector<uint32_t> items((size_t)nE + nF);
+        for (int e = 0; e < nE; ++e) items[slot[e]] = A[4 + e];
+        for (int f = 0; f < nF; ++f) items[nE + slot[nE + f]] = A[4 + nE + f];
+        for (int i = 0; i < nE + nF; ++i) A[4 + i] = items[i];
+    }
+    for (int g = 0; g < nG; ++g) {
+        const int kind = (int)(grp[4 * g] & 255u), nA = (int)((grp[4 * g] >> 8) & 255u), nB = (int)((grp[4 * g] >> 16) & 255u);
+        uint32_t *pl = pulls + grp[4 * g + 1];
+        for (int i = 0; i < (nA + nB) * GROUP; ++i) {
+            const Ref r0 = decode(pl[i] & 0xffffu), r1 = decode(pl[i] >> 16);
+            pl[i] = (uint32_t)(r0.elem < 0 ? 0 : offset_of(r0)) | ((uint32_t)(r1.elem < 0 ? 0 : offset_of(r1)) << 16);
+        }
+        if (kind != KIND_O) continue;
+        // ---- (2) greedy order of every lane's contributions, per quarter warp and loop
+        for (int loop = 0; loop < 2; ++loop) {
+            const int n = loop ? nB : nA;
+            uint32_t *base = pl + (loop ? nA * GROUP : 0);
+            for (int q = 0; q < GROUP / 8; ++q) {
+                std::vector<uint16_t> rem[8];
+                for (int l = 0; l < 8; ++l)
+                    for (int pos = 0; pos < 2 * n; ++pos) {
+                        const uint32_t e = base[(pos >> 1) * GROUP + 8 * q + l];
+                        const uint16_t off = (uint16_t)((pos & 1) ? e >> 16 : e & 0xffffu);
+                        if (off >= ZPAD) rem[l].push_back(off);
+                    }
+                for (int pos = 0; pos < 2 * n; ++pos) {
+                    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    uint16_t chosen[8];
+                    bool pad[8];
+                    for (int l = 0; l < 8; ++l) {
+                        pad[l] = rem[l].empty();
+                        if (pad[l]) continue;
+                        size_t best = 0;
+                        for (size_t c = 1; c < rem[l].size(); ++c)
+                            if (cnt[(rem[l][c] >> 1) & 7] < cnt[(rem[l][best] >> 1) & 7]) best = c;
+                        chosen[l] = rem[l][best];
+                        rem[l].erase(rem[l].begin() + best);
+                        ++cnt[(chosen[l] >> 1) & 7];
+                    }
+                    int zres = 0;
+                    for (int r = 1; r < 8; ++r) if (cnt[r] < cnt[zres]) zres = r;
+                    for (int l = 0; l < 8; ++l) {
+                        const uint32_t off = pad[l] ? (uint32_t)(2 * zres) : chosen[l];
+                        uint32_t &w = base[(pos >> 1) * GROUP + 8 * q + l];
+                        w = (pos & 1) ? (w & 0xffffu) | (off << 16) : (w & 0xffff0000u) | off;
+                    }
+                }
+            }
+        }
+    }
+}
 
 inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie, const Pattern &pat, const double *X_hint, bool dedup,
                   Plan &P) {
@@ -359,9 +528,10 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
     std::unordered_map<uint64_t, std::vector<uint32_t>> seen;   // hash -> template offsets (16-byte units)
     std::vector<uint32_t> T;                                   // template under construction
     std::vector<RecTmp> recs[3];
+    std::vector<std::pair<uint32_t, uint32_t>> unique_tmpl;   // (offset, size of part A) of every stored template, 16-byte units
     struct Run { uint64_t dst; uint32_t kind, src, len; };
     std::vector<Run> runs;
-    struct Grp { int kind, nA, nB, first; long cost; };
+    struct Grp { int kind, nA, nB, first, count; long cost; };
     std::vector<Grp> groups;
     for (size_t t = 0; t < leaves.size(); ++t) {
         int32_t *own = idx.data() + leaves[t].first;
@@ -482,14 +652,22 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                 std::stable_sort(rv.begin(), rv.end(), [&](const RecTmp &u, const RecTmp &v) {
                     const int cu = pairs(u.A) + pairs(u.B), cv = pairs(v.A) + pairs(v.B);
                     if (cu != cv) return cu > cv;
-                    return pairs(u.A) > pairs(v.A);
+                    if (pairs(u.A) != pairs(v.A)) return pairs(u.A) > pairs(v.A);
+                    // same position in the row = same direction on a structured mesh: neighbouring lanes then pull the same block
+                    // of neighbouring elements, whose slots fall into different bank groups
+                    if (getenv("EOLC_PLAN_SORT_OWN")) return false;
+                    return (u.rec & 255u) < (v.rec & 255u);
                 });
-            for (size_t g0 = 0; g0 < rv.size(); g0 += GROUP) {
-                Grp G{kind, 0, 0, (int)g0, 0};
-                for (size_t k = g0; k < std::min(rv.size(), g0 + GROUP); ++k) { G.nA = std::max(G.nA, pairs(rv[k].A)); G.nB = std::max(G.nB, pairs(rv[k].B)); }
+            for (size_t g0 = 0; g0 < rv.size();) {
+                // (half-width groups for the long lists were tried: a group's time is set by the latency of its trips, not by its
+                // width, so splitting only lengthened every warp's chain: 0.85 -> 0.99 ms, profiles/r01/experiments.md)
+                const size_t width = GROUP;
+                Grp G{kind, 0, 0, (int)g0, (int)std::min(rv.size() - g0, width), 0};
+                for (size_t k = g0; k < g0 + (size_t)G.count; ++k) { G.nA = std::max(G.nA, pairs(rv[k].A)); G.nB = std::max(G.nB, pairs(rv[k].B)); }
                 if (G.nA > MAX_ITER || G.nB > MAX_ITER) { P.error = "tile " + std::to_string(t) + ": contribution list overflow"; return false; }
                 G.cost = kind == KIND_D ? 6 + 4L * G.nA : kind == KIND_O ? 18 + 10L * (G.nA + G.nB) : 6 + 2L * G.nA;
                 groups.push_back(G);
+                g0 += (size_t)G.count;
             }
         }
         std::stable_sort(groups.begin(), groups.end(), [](const Grp &u, const Grp &v) { return u.cost > v.cost; });
@@ -517,7 +695,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         for (const Grp &G : groups) {
             const auto &rv = recs[G.kind];
             for (int l = 0; l < GROUP; ++l) {
-                const uint64_t r = (size_t)G.first + l < rv.size() ? rv[G.first + l].rec : 0ull;
+                const uint64_t r = l < G.count ? rv[G.first + l].rec : 0ull;
                 T.push_back((uint32_t)r); T.push_back((uint32_t)(r >> 32));
             }
         }
@@ -527,7 +705,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                 for (int r = 0; r < (loop ? G.nB : G.nA); ++r)
                     for (int l = 0; l < GROUP; ++l) {
                         uint32_t e = 0;
-                        if ((size_t)G.first + l < rv.size()) {
+                        if (l < G.count) {
                             const std::vector<uint16_t> &L = loop ? rv[G.first + l].B : rv[G.first + l].A;
                             if ((size_t)2 * r < L.size()) e = L[2 * r];
                             if ((size_t)2 * r + 1 < L.size()) e |= (uint32_t)L[2 * r + 1] << 16;
@@ -536,6 +714,28 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                     }
         }
         while (T.size() % 4) T.push_back(0);
+        {
+            // phase-3 items: one per entry (j, k), j <= k, of every owned node's diagonal MDK block, 3 words each:
+            //   start of the strided row sum (staging offset of row j, column k of the node's first block) | deg << 16 | (j == k) << 24,
+            //   destination | mirrored destination << 16,   staging offset of the node's M_aa
+            const uint32_t p3_at = (uint32_t)(T.size() - (size_t)sizeA16 * 4);
+            uint32_t n_items = 0;
+            for (int o = 0; o < n_own; ++o) {
+                const uint32_t deg = degs[o] & 255u, pd = (degs[o] >> 16) & 255u, pdM = degs[o] >> 24;
+                if (!deg) continue;
+                const uint32_t base = offsKM[o] & 0xffffu, mo = (offsKM[o] >> 16) + 3 * pdM;
+                for (uint32_t j = 0; j < 3; ++j)
+                    for (uint32_t k = j; k < 3; ++k) {
+                        T.push_back((base + 3 * deg * j + k) | (deg << 16) | ((j == k ? 1u : 0u) << 24));
+                        T.push_back((base + 3 * deg * j + 3 * pd + k) | ((base + 3 * deg * k + 3 * pd + j) << 16));
+                        T.push_back(mo);
+                        ++n_items;
+                    }
+            }
+            T[(size_t)sizeA16 * 4 + 1] = p3_at;
+            T[(size_t)sizeA16 * 4 + 2] = n_items;
+            while (T.size() % 4) T.push_back(0);
+        }
         P.n_groups += (int64_t)groups.size();
         const uint32_t sizeB16 = (uint32_t)(T.size() / 4) - sizeA16;
         if (sizeA16 > 0xffffu || sizeB16 > 0xffffu) { P.error = "tile " + std::to_string(t) + ": template too large"; return false; }
@@ -558,6 +758,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             P.tmpl.insert(P.tmpl.end(), T.begin(), T.end());
             if (dedup) seen[h].push_back(toff);
             ++P.n_templates;
+            unique_tmpl.push_back({toff, sizeA16});
         }
         // ---- geometry blob
         geo_off.push_back((uint32_t)(P.geo.size() / 4));
@@ -576,6 +777,13 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         P.n_runs += (int64_t)runs.size();
         P.max_geo16 = std::max<uint32_t>(P.max_geo16, (uint32_t)((P.geo.size() - g0) / 4));
         if (P.geo.size() / 4 >= ((size_t)1 << 32) || P.tmpl.size() / 4 >= ((size_t)1 << 32)) { P.error = "plan too large"; return false; }
+    }
+    {
+        // bank-aware post-pass over the stored templates; the slot search only where templates are shared (structured meshes)
+        const char *ob = getenv("EOLC_PLAN_BANK_ITERS");
+        const long budget = ob ? atol(ob) : 4000;
+        const int iters = (int)std::max<long>(0, std::min<long>(budget, 400000 / (long)std::max<size_t>(1, unique_tmpl.size())));
+        for (const auto &u : unique_tmpl) optimize_template(P.tmpl.data() + (size_t)u.first * 4, u.second, iters < 20 ? 0 : iters);
     }
     geo_off.push_back((uint32_t)(P.geo.size() / 4));
     {

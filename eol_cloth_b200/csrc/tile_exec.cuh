@@ -1,7 +1,7 @@
 // tile_exec.cuh — the two per-thread phases of the "tiles" assembly of Forces::fill, written once for the device
 // (forces.cu: assemble_tiles_kernel) and for the host emulation the CPU tests run (tests/hostmath/hostmath.cpp).
 //
-//   phase 1   thread t < nE evaluates bending stencil t, thread nEpad <= t < nEpad + nF evaluates face t - nEpad (nEpad = nE rounded up to a warp)
+//   phase 1   each producer thread evaluates one bending stencil and one face of the tile (more if the tile has more than 128)
 //             (elements.cuh: edge_element_tile / face_element_tile) and parks the element blocks in `scr`
 //   phase 2   every output block of the tile's nodes pulls its contributions from `scr` in the plan's fixed order into staged
 //             rows (D: f, O: off-diagonal MDK block, M: mass block)
@@ -82,23 +82,25 @@ struct ParkFace {   // off-diagonal block k (K_ab, K_ac, K_bc) at 10 k; force of
 
 EOLC_HD v3 ldx(const double *xs, uint32_t l) { return mk3(xs[3 * l], xs[3 * l + 1], xs[3 * l + 2]); }
 
-EOLC_HD void phase1(int tid, const TileView &V, const FillParams &P) {
+// Phase 1: thread tid of nthreads evaluates bending stencils tid, tid + nthreads, ... and then faces nthreads - 1 - tid, ...
+// (a regular tile has at most one of each per thread) and parks the off-diagonal element blocks in V.scr.
+EOLC_HD void phase1(int tid, int nthreads, const TileView &V, const FillParams &P) {
     const uint32_t w0 = V.tmpl[0];
-    const int nE = (int)(w0 & 0xffffu), nF = (int)(w0 >> 16), nEpad = (nE + 31) & ~31;
-    if (tid < nE) {
-        const uint32_t it = V.tmpl[4 + tid];
+    const int nE = (int)(w0 & 0xffffu), nF = (int)(w0 >> 16);
+    for (int e = tid; e < nE; e += nthreads) {
+        const uint32_t it = V.tmpl[4 + e];
         const uint32_t l0 = it & 255u, l1 = (it >> 8) & 255u, l2 = (it >> 16) & 255u, l3 = it >> 24;
         double X0x, X0y, X1x, X1y, X2x, X2y, X3x, X3y;
         ld2(V.Xs + 2 * l0, X0x, X0y); ld2(V.Xs + 2 * l1, X1x, X1y); ld2(V.Xs + 2 * l2, X2x, X2y); ld2(V.Xs + 2 * l3, X3x, X3y);
-        ParkEdge park{V.scr + ZPAD + EDGE_STRIDE * tid};
+        ParkEdge park{V.scr + ZPAD + EDGE_STRIDE * e};
         edge_element_tile(ldx(V.xs, l0), ldx(V.xs, l1), ldx(V.xs, l2), ldx(V.xs, l3), X0x, X0y, X1x, X1y, X2x, X2y, X3x, X3y, P.beta, P.dhh, park);
-    } else if (tid >= nEpad && tid < nEpad + nF) {
-        const int s = tid - nEpad;
-        const uint32_t it = V.tmpl[4 + nE + s];
+    }
+    for (int f = nthreads - 1 - tid; f < nF; f += nthreads) {   // faces from the last thread down: other warps than the stencils'
+        const uint32_t it = V.tmpl[4 + nE + f];
         const uint32_t l0 = it & 255u, l1 = (it >> 8) & 255u, l2 = (it >> 16) & 255u;
         double Xax, Xay, Xbx, Xby, Xcx, Xcy;
         ld2(V.Xs + 2 * l0, Xax, Xay); ld2(V.Xs + 2 * l1, Xbx, Xby); ld2(V.Xs + 2 * l2, Xcx, Xcy);
-        ParkFace park{V.scr + ZPAD + EDGE_STRIDE * nE + FACE_STRIDE * s};
+        ParkFace park{V.scr + ZPAD + EDGE_STRIDE * nE + FACE_STRIDE * f};
         face_element_tile(ldx(V.xs, l0), ldx(V.xs, l1), ldx(V.xs, l2), Xax, Xay, Xbx, Xby, Xcx, Xcy, P.mu, P.lam, P.rho, mk3(P.gx, P.gy, P.gz),
                           P.dhh, park);
     }
@@ -138,6 +140,7 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                 double f0 = 0.0, f1 = 0.0, f2 = 0.0;
                 EOLC_UNROLL_P2
                 for (int k = 0; k < nA; ++k, pl += GROUP) {
+                    if (!valid) continue;
                     const double *s0, *s1;
                     pull2(*pl, scr, s0, s1);
                     double h, j, h1, j1;
@@ -149,6 +152,16 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                 if (valid) {
                     double *fo = V.fst + offsF[own];
                     fo[0] = f0; fo[1] = f1; fo[2] = f2;
+                    // clear the node's diagonal block: phase 3 then sums whole rows (no stale value of an earlier tile enters the sum)
+                    const uint32_t dw = degs[own], deg = dw & 255u;
+                    if (deg) {
+                        double *row = V.kst + (offsKM[own] & 0xffffu) + 3 * ((dw >> 16) & 255u);
+                        row[0] = 0.0; row[1] = 0.0; row[2] = 0.0;
+                        row += 3 * deg;
+                        row[0] = 0.0; row[1] = 0.0; row[2] = 0.0;
+                        row += 3 * deg;
+                        row[0] = 0.0; row[1] = 0.0; row[2] = 0.0;
+                    }
                 }
             } else if (kind == KIND_O) {
                 // ---- off-diagonal MDK block: contributions are parked as K_(lo,hi) of the element; the ones whose row vertex comes
@@ -156,6 +169,7 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0, a8 = 0.0;
                 EOLC_UNROLL_P2
                 for (int k = 0; k < nA; ++k, pl += GROUP) {
+                    if (!valid) continue;
                     const double *s0, *s1;
                     pull2(*pl, scr, s0, s1);
                     double b0, b1, b2, b3, b4, b5, b6, b7, d0, d1, d2, d3, d4, d5, d6, d7;
@@ -167,6 +181,7 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                 }
                 EOLC_UNROLL_P2
                 for (int k = 0; k < nB; ++k, pl += GROUP) {
+                    if (!valid) continue;
                     const double *s0, *s1;
                     pull2(*pl, scr, s0, s1);
                     double b0, b1, b2, b3, b4, b5, b6, b7, d0, d1, d2, d3, d4, d5, d6, d7;
@@ -200,6 +215,7 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                 //      (ComputeInertial.cpp:33,44-47)
                 double m = 0.0;
                 for (int k = 0; k < nA; ++k, pl += GROUP) {
+                    if (!valid) continue;
                     const double *s0, *s1;
                     pull2(*pl, scr, s0, s1);
                     m += *s0;
@@ -231,31 +247,27 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
 // Phase 3 (after a barrier: all off-diagonal blocks and mass blocks of the tile's rows are staged): the diagonal MDK block of every
 // owned node.  Each element matrix has zero row sums apart from the mass part (t8/12 + 2 t8/24 = t8/6 per row), so
 //     MDK_aa = 2 M_aa I - sum over b != a of MDK_ab           (M_aa = sum of t8/12 over the node's faces)
-// Thread t handles entry (j, k), j <= k, of node t / 6 and mirrors it: exactly symmetric like the reference's diagonal blocks.
-EOLC_HD void phase3(int tid, const TileView &V) {
-    const uint32_t h0 = V.tmplB[0];
-    const int nOwn = (int)(h0 & 255u), n4 = (nOwn + 3) & ~3;
-    if (tid >= 6 * nOwn) return;
-    const uint32_t *degs = V.tmplB + 4, *offsKM = degs + n4;
-    const int o = tid / 6, e = tid - 6 * o;
-    const int j = e < 3 ? 0 : (e < 5 ? 1 : 2), k = e < 3 ? e : (e < 5 ? e - 2 : 2);
-    const uint32_t dw = degs[o];
-    const int deg = (int)(dw & 255u), pd = (int)((dw >> 16) & 255u), pdM = (int)(dw >> 24);
-    if (!deg) return;
-    double *rows = V.kst + (offsKM[o] & 0xffffu);
-    const double *r = rows + 3 * deg * j + k;
-    // four interleaved partial sums in a fixed order (the loads of a trip are independent: no add-latency chain per block)
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-    int p = 0;
-    for (; p + 4 <= deg; p += 4) {
-        const double v0 = r[3 * p], v1 = r[3 * p + 3], v2 = r[3 * p + 6], v3 = r[3 * p + 9];
-        acc0 += p == pd ? 0.0 : v0; acc1 += p + 1 == pd ? 0.0 : v1; acc2 += p + 2 == pd ? 0.0 : v2; acc3 += p + 3 == pd ? 0.0 : v3;
+// Work item t handles entry (j, k), j <= k, of node t / 6 and mirrors it: exactly symmetric like the reference's diagonal blocks.
+EOLC_HD void phase3(int tid, int nthreads, const TileView &V) {
+    const uint32_t *items = V.tmplB + V.tmplB[1];
+    const int n_items = (int)V.tmplB[2];
+    for (int t = tid; t < n_items; t += nthreads) {
+        const uint32_t w0 = items[3 * t], w1 = items[3 * t + 1];
+        const int deg = (int)((w0 >> 16) & 255u);
+        const double *r = V.kst + (w0 & 0xffffu);
+        // entry (j, k) of the sum of the node's blocks (the diagonal block was cleared in phase 2); four partial sums in a fixed
+        // order, so that the loads of a trip are independent of the running sums
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int p = 0;
+        for (; p + 4 <= deg; p += 4) {
+            const double v0 = r[3 * p], v1 = r[3 * p + 3], v2 = r[3 * p + 6], v3 = r[3 * p + 9];
+            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+        }
+        for (; p < deg; ++p) s0 += r[3 * p];
+        const double v = ((w0 >> 24) & 1u ? 2.0 * V.mst[items[3 * t + 2]] : 0.0) - ((s0 + s1) + (s2 + s3));
+        V.kst[w1 & 0xffffu] = v;
+        V.kst[w1 >> 16] = v;
     }
-    for (; p < deg; ++p) acc0 += p == pd ? 0.0 : r[3 * p];
-    const double acc = (acc0 + acc1) + (acc2 + acc3);
-    const double v = (j == k ? 2.0 * V.mst[(offsKM[o] >> 16) + 3 * pdM] : 0.0) - acc;
-    rows[3 * deg * j + 3 * pd + k] = v;
-    if (j != k) rows[3 * deg * k + 3 * pd + j] = v;
 }
 
 // Copy-out: every run of staged rows (rows of owned nodes with consecutive ids) goes to its CSR slot with ONE bulk copy
@@ -264,14 +276,16 @@ EOLC_HD void phase3(int tid, const TileView &V) {
 // misaligned first / last double is stored separately.  The mass rows were staged expanded, (m, 0, 0; 0, m, 0; 0, 0, m): the six
 // off-axis entries are the reference's explicit zeros (ComputeInertial.cpp:45-46, kept by setFromTriplets).
 // Lane `lane` of `nlanes` takes runs lane, lane + nlanes, ...; f, Mv, Kv: outputs of the tile's scene.
+// kinds: bit mask of the run kinds to copy now (1: MDK rows, 2: M rows, 4: f) — M rows and f are final after phase 2 already.
 template <typename Bulk>
-EOLC_HD void copy_out_runs(int lane, int nlanes, const TileView &V, double *__restrict__ f, double *__restrict__ Mv, double *__restrict__ Kv, Bulk bulk) {
+EOLC_HD void copy_out_runs(int lane, int nlanes, const TileView &V, double *__restrict__ f, double *__restrict__ Mv, double *__restrict__ Kv, uint32_t kinds, Bulk bulk) {
     const uint32_t g1 = V.geo[1];
     const uint32_t *runs = V.geo + 4 + ((((g1 >> 8) & 255u) + 3u) & ~3u);
     const int nruns = (int)V.geo[3];
     for (int r = lane; r < nruns; r += nlanes) {
         const uint32_t *c = runs + 4 * r;
         const uint32_t hi = c[1], kind = hi >> 30;
+        if (!((kinds >> kind) & 1u)) continue;
         double *dst = (kind == 0 ? Kv : kind == 1 ? Mv : f) + (((unsigned long long)(hi & 0x3fffffffu) << 32) | c[0]);
         const double *src = (kind == 0 ? V.kst : kind == 1 ? V.mst : V.fst) + c[2];
         uint32_t n = c[3];

@@ -22,7 +22,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 L = capi.lib()
 L.eolc_debug_tile_clocks.argtypes = [capi.c_vp, ctypes.c_void_p, ctypes.c_int]
-buf = np.zeros((148 * 32, 7), dtype=np.uint64)
+buf = np.zeros((148 * 64, 7), dtype=np.uint64)
 rows = L.eolc_debug_tile_clocks(plan.handle, buf.ctypes.data, buf.shape[0])
 d = buf[:rows].astype(np.float64)
 nw = rows // 148 if rows % 148 == 0 else 8

@@ -105,6 +105,51 @@ void hm_plan_pattern(void *p, int which, int32_t *outer, int32_t *inner) {
     memcpy(outer, o.data(), o.size() * 4);
     if (!in.empty()) memcpy(inner, in.data(), in.size() * 4);
 }
+// Bank-conflict model of the phase-2 block pulls (developer statistic): for every O group, list row and half (s0 / s1) the
+// number of shared-memory wavefronts one 128-bit load instruction takes = sum over quarter warps of the largest number of
+// DISTINCT 16-byte addresses falling into one of the 8 bank groups; ideal = number of quarter warps with an active lane.
+// out[0] = modelled wavefronts, out[1] = ideal, both summed over all tiles (per load instruction of a block, i.e. x4.5 in reality).
+void hm_plan_pull_conflicts(void *p, double *out) {
+    HmPlan *P = (HmPlan *)p;
+    out[0] = out[1] = 0.0;
+    for (int32_t t = 0; t < P->tp.n_tiles; ++t) {
+        const uint32_t *geo = P->tp.geo.data() + (size_t)t * P->tp.max_geo16 * 4;
+        const uint32_t *B = P->tp.tmpl.data() + (size_t)geo[0] * 4 + (size_t)(geo[2] & 0xffffu) * 4;
+        const int nOwn = B[0] & 255, nG = (B[0] >> 8) & 255, n4 = (nOwn + 3) & ~3;
+        const uint32_t *grp = B + 4 + 3 * n4;
+        const uint32_t *pulls = grp + 4 * nG + 2 * tiles::GROUP * nG;
+        for (int g = 0; g < nG; ++g) {
+            const int kind = grp[4 * g] & 255, rows = ((grp[4 * g] >> 8) & 255) + ((grp[4 * g] >> 16) & 255);
+            if (kind != tiles::KIND_O) continue;
+            const uint32_t *pl = pulls + grp[4 * g + 1];
+            for (int r = 0; r < rows; ++r)
+                for (int half = 0; half < 2; ++half)
+                    for (int q = 0; q < 4; ++q) {
+                        int addr[8], na = 0, cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        for (int l = 0; l < 8; ++l) {
+                            const uint32_t e = pl[r * 32 + 8 * q + l];
+                            const int off = half ? (int)(e >> 16) : (int)(e & 0xffffu);
+                            bool dup = false;
+                            for (int k = 0; k < na; ++k) dup |= addr[k] == off;
+                            if (!dup) { addr[na++] = off; ++cnt[(off >> 1) & 7]; }
+                        }
+                        int mx = 0;
+                        for (int k = 0; k < 8; ++k) mx = std::max(mx, cnt[k]);
+                        out[0] += mx; out[1] += 1.0;
+                    }
+        }
+    }
+}
+// developer helper: copies template part B of tile t (u32 words) into out; returns the number of words
+int hm_plan_dump(void *p, int t, uint32_t *out, int cap) {
+    HmPlan *P = (HmPlan *)p;
+    const uint32_t *geo = P->tp.geo.data() + (size_t)t * P->tp.max_geo16 * 4;
+    const uint32_t *B = P->tp.tmpl.data() + (size_t)geo[0] * 4 + (size_t)(geo[2] & 0xffffu) * 4;
+    const int n = (int)(geo[2] >> 16) * 4;
+    if (n > cap) return -1;
+    memcpy(out, B, (size_t)n * 4);
+    return n;
+}
 struct HostBulk {   // host stand-in of the device's bulk copy: same alignment contract
     bool *ok;
     void operator()(double *dst, const double *src, uint32_t bytes) const {
@@ -144,10 +189,10 @@ int hm_plan_fill(void *p, const double *x, const double *X, const double *mat6, 
         const bool m_full = geo[0] != tM_id;   // like the kernel: the M staging keeps the explicit zeros of the resident template
         tM_id = geo[0];
         if (m_full) for (auto &v : mbuf) v = 1e300;
-        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase1(tid, V, prm);
-        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase2(tid, tiles::NTHREADS, V, m_full);
-        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase3(tid, V);
-        for (int lane = 0; lane < 32; ++lane) tiles::copy_out_runs(lane, 32, V, f, Mv, Kv, HostBulk{&ok});
+        for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase1(tid, tiles::NTHREADS, V, prm);
+        for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::phase2(tid, tiles::P2THREADS, V, m_full);
+        for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::phase3(tid, tiles::P2THREADS, V);
+        for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::copy_out_runs(tid, tiles::P2THREADS, V, f, Mv, Kv, 7u, HostBulk{&ok});
     }
     return ok ? 0 : -1;
 }

@@ -104,16 +104,19 @@ def test_tiles_host_dedup_and_tiling_quality(hostmath):
     es = E.meshgen.edge_stencils(X.shape[0], fn)
     T = HostTiles(hostmath, X.shape[0], fn, es, X, True)
     i = T.info
-    assert i["n_tiles"] == 128 * 128 // 32
+    assert i["n_tiles"] == 128 * 128 // 32, i
     assert i["n_templates"] < 60, i
     assert i["elem_evals"] < 1.6 * (len(fn) + i["Ei"]), i
-    assert i["max_scratch"] * 8 <= 160 * 1024
+    assert i["max_scratch"] * 8 <= 112 * 1024
     T2 = HostTiles(hostmath, X.shape[0], fn, es, X, False)
     assert T2.info["n_templates"] == T2.info["n_tiles"]
     x = E.meshgen.drape_state(X, seed=1)
-    a, b = T.fill(x, X), T2.fill(x, X)
-    for u, v in zip(a, b):
-        assert u.tobytes() == v.tobytes()      # templates are an encoding detail: bit-identical results
+    a, b, c = T.fill(x, X), T2.fill(x, X), T.fill(x, X)
+    for u, v, w in zip(a, b, c):
+        assert u.tobytes() == w.tobytes()      # same plan, same bits
+        # shared templates get a longer bank-layout search (forces_plan.h: optimize_template), which may reorder the additions
+        # of a block: same values to rounding
+        assert np.allclose(u, v, rtol=0, atol=1e-13 * np.abs(u).max())
     T.close(); T2.close()
 
 
