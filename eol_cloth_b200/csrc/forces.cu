@@ -257,6 +257,9 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
             EOLC_SYNC();                 // [B1] elements parked, staged inputs landed, staging free
             EOLC_CLK(2)
             ta1 = (int)ctl[0];
+#ifdef EOLC_TILE_CLOCKS
+            if (__syncthreads_or(0) == 12345) clk_acc[6] += 1000000;   // the instrumented build's blocking barrier between phases 2 and 3
+#endif
             EOLC_SYNC();                 // [B2] staged rows complete
             EOLC_CLK(4)
 #ifndef EOLC_DEBUG_NO_COPYOUT
@@ -289,7 +292,13 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
             EOLC_CLK(2)
             const int ta1 = (int)ctl[0];
             tiles::phase2((int)tid, (int)NC, V, ctl[1] != 0u);
+            EOLC_CLK(0)
+#ifdef EOLC_TILE_CLOCKS
+            if (__syncthreads_or(0) == 12345) clk_acc[6] += 1000000;   // never true; see EOLC_SYNC (service warps take part in this build)
+            EOLC_CLK(5)
+#else
             asm volatile("bar.sync 1, %0;" ::"n"(tiles::NTHREADS) : "memory");   // compute warps only: off-diagonal and mass blocks staged
+#endif
             tiles::phase3((int)tid, (int)NC, V);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk-copy engine
             EOLC_CLK(3)

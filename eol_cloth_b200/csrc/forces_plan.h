@@ -139,6 +139,7 @@ constexpr int MAX_MSTAGE = 74 * MAX_OWN;           // doubles of M rows one tile
 constexpr int MAX_FSTAGE = 4 * MAX_OWN + 4;        // doubles of f one tile stages
 constexpr int MAX_ITER = 255;        // PAIRS of contributions per loop of one phase-2 group (8-bit fields)
 constexpr int GROUP = 32;            // phase-2 records per group (one warp)
+constexpr int B_HDR = 4 + P2THREADS / 32;   // words before the per-node tables of template part B: header + the warps' group ranges
 
 // smem offsets (in doubles) of the parked blocks inside an element slot
 inline int edge_off_off(int lo, int hi) { static const int k[4][4] = {{-1, 0, 1, 2}, {0, -1, 3, 4}, {1, 3, -1, 5}, {2, 4, 5, -1}}; return 10 * k[lo][hi]; }
@@ -153,20 +154,24 @@ inline int face_force_off(int v) { return 30 + 4 * v; }
 //          column node is owned by the same tile (has2) the record also writes the mirrored block (own2, p2) = transpose, and
 //          the mirrored pair has no record of its own.
 //   kind M (mass block): loop A = t8 of the faces shared by the pair; flag = diagonal block (t8/12, else t8/24); has2 as for O.
-// 64-bit record: p:8 | own:6 | p2:8 | own2:6 | has2:1 | flag:1 | valid:1
-inline uint64_t pack_rec(unsigned p, unsigned own, unsigned p2, unsigned own2, unsigned has2, unsigned flag) {
-    return (uint64_t)p | ((uint64_t)own << 8) | ((uint64_t)p2 << 14) | ((uint64_t)own2 << 22) | ((uint64_t)has2 << 28) | ((uint64_t)flag << 29) | (1ull << 30);
+// 64-bit record: off1:16 | stride1:10 | off2:16 | stride2:10 | has2:1 | flag:1 | valid:1 — staging offsets (doubles) of the first row
+// of the block and of its mirror, and the distance between the block's rows (3 x the node's row degree); kind D: off1 = staged f of
+// the node, off2 / stride2 = its diagonal MDK block (has2 = the node has a row at all).
+inline uint64_t pack_rec(unsigned off1, unsigned stride1, unsigned off2, unsigned stride2, unsigned has2, unsigned flag) {
+    return (uint64_t)off1 | ((uint64_t)stride1 << 16) | ((uint64_t)off2 << 26) | ((uint64_t)stride2 << 42) | ((uint64_t)has2 << 52) |
+           ((uint64_t)flag << 53) | (1ull << 54);
 }
 enum { KIND_D = 0, KIND_O = 1, KIND_M = 2 };
 
 // Template = part A (phase 1) + part B (phase 2), u32 words, every section padded to 16 bytes:
 //   A: [nE | nF << 16, 0, 0, 0] [items: nE stencils (4 local ids, 8 bits each) then nF faces (3 local ids)]
 //      stencil slot s is evaluated by thread s % 256, face slot s by thread 255 - s % 256
-//   B: [nOwn | nGroups << 8, word offset of the phase-3 items, number of phase-3 items, 0] [degs: degK | degM << 8 | position of the diagonal block in the MDK row << 16 | in the M row << 24
+//   B: [nOwn | nGroups << 8, word offset of the phase-3 items, number of phase-3 items, 0] [per phase-2 warp: first group | groups << 16]
+//      [degs: degK | degM << 8 | position of the diagonal block in the MDK row << 16 | in the M row << 24
 //      per owned node] [offsKM: staging offset of the node's MDK rows | M rows << 16]
-//      [offsF: staging offset of the node's f] [groups: 4 words each: kind | nA << 8 | nB << 16, pull base, 0, 0] [records: 32 x u64 per
+//      [offsF: staging offset of the node's f] [groups: 4 words each: kind | nA << 8 | nB << 16, pull base, warp, 0] [records: 32 x u64 per
 //      group] [pulls]
-//      groups are sorted by descending cost; warp w takes groups w, 15 - w, 16 + w, 31 - w, ... (snake order)
+//      every group names the phase-2 warp that runs it (longest-processing-time-first assignment by estimated cost)
 // Staging offsets follow the PARITY of the global destination (offset of a run's first double in its value array, mod 2), so that
 // staged rows and global rows are 16-byte aligned together and whole runs leave with one bulk copy (cp.async.bulk).
 // Geometry blob (per tile): [template offset (16-byte units), nOwn | nLoc << 8, size A | size B << 16 (16-byte units), nRuns]
@@ -253,6 +258,7 @@ inline void rcb(std::vector<int32_t> &idx, size_t lo, size_t hi, size_t leaves, 
 // one phase-2 record under construction
 struct RecTmp {
     uint64_t rec;
+    int p;                         // position of the block in its row (sort key: the same direction on a structured mesh)
     std::vector<uint16_t> A, B;    // pull offsets of loop A / loop B (single entries, paired when serialised)
 };
 
@@ -270,7 +276,7 @@ inline void optimize_template(uint32_t *T, uint32_t sizeA16, int iters) {
     uint32_t *A = T, *B = T + (size_t)sizeA16 * 4;
     const int nE = (int)(A[0] & 0xffffu), nF = (int)(A[0] >> 16);
     const int nOwn = (int)(B[0] & 255u), nG = (int)((B[0] >> 8) & 255u), n4 = (nOwn + 3) & ~3;
-    uint32_t *grp = B + 4 + 3 * n4;
+    uint32_t *grp = B + B_HDR + 3 * n4;
     uint32_t *pulls = grp + 4 * nG + 2 * GROUP * nG;
     const int fbase = ZPAD + nE * EDGE_STRIDE;
     struct Ref { int elem; int boff; };                   // elem: stencil e -> e, face f -> nE + f; -1: zero pad
@@ -531,7 +537,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
     std::vector<std::pair<uint32_t, uint32_t>> unique_tmpl;   // (offset, size of part A) of every stored template, 16-byte units
     struct Run { uint64_t dst; uint32_t kind, src, len; };
     std::vector<Run> runs;
-    struct Grp { int kind, nA, nB, first, count; long cost; };
+    struct Grp { int kind, nA, nB, first, count; long cost; int warp; };
     std::vector<Grp> groups;
     for (size_t t = 0; t < leaves.size(); ++t) {
         int32_t *own = idx.data() + leaves[t].first;
@@ -631,14 +637,29 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                     for (int ij = 0; ij < 4; ++ij)
                         if (v[ij] == b) (ia < ij ? R.A : R.B).push_back((uint16_t)(base + edge_off_off(std::min(ia, ij), std::max(ia, ij))));
                 }
-                unsigned p2 = 0, own2 = 0, has2 = 0;
-                if (ob >= 0) { has2 = 1; own2 = (unsigned)ob; p2 = (unsigned)(find_block(pat.blkptrK, pat.nbrK, b, a) - pat.blkptrK[b]); }
-                R.rec = pack_rec((unsigned)p, (unsigned)o, p2, own2, has2, 0);
+                const unsigned has2 = ob >= 0 ? 1u : 0u;
+                if (has2 && pat.blkptrK[b + 1] - pat.blkptrK[b] > 255) { P.error = "node " + std::to_string(b) + " has more than 255 neighbours"; return false; }
+                if (b == a) {
+                    R.rec = pack_rec(offsF[o], 0, (offsKM[o] & 0xffffu) + 3u * (unsigned)p, 3u * (unsigned)deg, deg ? 1u : 0u, 0);
+                } else {
+                    unsigned off2 = 0, s2 = 0;
+                    if (has2) {
+                        const unsigned p2 = (unsigned)(find_block(pat.blkptrK, pat.nbrK, b, a) - pat.blkptrK[b]);
+                        off2 = (offsKM[ob] & 0xffffu) + 3u * p2; s2 = 3u * (unsigned)(pat.blkptrK[b + 1] - pat.blkptrK[b]);
+                    }
+                    R.rec = pack_rec((offsKM[o] & 0xffffu) + 3u * (unsigned)p, 3u * (unsigned)deg, off2, s2, has2, 0);
+                }
+                R.p = p;
                 recs[b == a ? KIND_D : KIND_O].push_back(std::move(R));
                 if (!Rm.A.empty()) {   // the pair shares a face -> mass block
                     const unsigned pM = (unsigned)(find_block(pat.blkptrM, pat.nbrM, a, b) - m0);
-                    const unsigned pM2 = has2 ? (unsigned)(find_block(pat.blkptrM, pat.nbrM, b, a) - pat.blkptrM[b]) : 0u;
-                    Rm.rec = pack_rec(pM, (unsigned)o, pM2, own2, has2, b == a ? 1u : 0u);
+                    unsigned off2 = 0, s2 = 0;
+                    if (has2) {
+                        const unsigned pM2 = (unsigned)(find_block(pat.blkptrM, pat.nbrM, b, a) - pat.blkptrM[b]);
+                        off2 = (offsKM[ob] >> 16) + 3u * pM2; s2 = 3u * (unsigned)(pat.blkptrM[b + 1] - pat.blkptrM[b]);
+                    }
+                    Rm.rec = pack_rec((offsKM[o] >> 16) + 3u * pM, 3u * (unsigned)degM, off2, s2, has2, b == a ? 1u : 0u);
+                    Rm.p = (int)pM;
                     recs[KIND_M].push_back(std::move(Rm));
                 }
             }
@@ -656,22 +677,37 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                     // same position in the row = same direction on a structured mesh: neighbouring lanes then pull the same block
                     // of neighbouring elements, whose slots fall into different bank groups
                     if (getenv("EOLC_PLAN_SORT_OWN")) return false;
-                    return (u.rec & 255u) < (v.rec & 255u);
+                    return u.p < v.p;
                 });
             for (size_t g0 = 0; g0 < rv.size();) {
                 // (half-width groups for the long lists were tried: a group's time is set by the latency of its trips, not by its
                 // width, so splitting only lengthened every warp's chain: 0.85 -> 0.99 ms, profiles/r01/experiments.md)
                 const size_t width = GROUP;
-                Grp G{kind, 0, 0, (int)g0, (int)std::min(rv.size() - g0, width), 0};
+                Grp G{kind, 0, 0, (int)g0, (int)std::min(rv.size() - g0, width), 0, 0};
                 for (size_t k = g0; k < g0 + (size_t)G.count; ++k) { G.nA = std::max(G.nA, pairs(rv[k].A)); G.nB = std::max(G.nB, pairs(rv[k].B)); }
                 if (G.nA > MAX_ITER || G.nB > MAX_ITER) { P.error = "tile " + std::to_string(t) + ": contribution list overflow"; return false; }
-                G.cost = kind == KIND_D ? 6 + 4L * G.nA : kind == KIND_O ? 18 + 10L * (G.nA + G.nB) : 6 + 2L * G.nA;
+                // rough clocks of one group on the kernel (latency bound: a fixed part + so much per trip), for the warp assignment below
+                // (measured on the 1024^2 sheet, B200: an O group takes ~1150 + 220 per trip, an M group ~600 + 50, a D group ~700 + 50;
+                // the fixed part is the latency chain record -> row table -> staged stores; nearly empty groups take about half)
+                G.cost = kind == KIND_D ? 700 + 50L * G.nA : kind == KIND_O ? 1150 + 220L * (G.nA + G.nB) : 600 + 50L * G.nA;
+                if (G.count <= 8) G.cost /= 2;
                 groups.push_back(G);
                 g0 += (size_t)G.count;
             }
         }
         std::stable_sort(groups.begin(), groups.end(), [](const Grp &u, const Grp &v) { return u.cost > v.cost; });
         if (groups.size() > 255) { P.error = "tile " + std::to_string(t) + ": too many phase-2 groups"; return false; }
+        {
+            // longest-processing-time-first assignment of the groups to the phase-2 warps; then ordered by warp (stable), so that a
+            // warp walks its groups in descending cost
+            long load[P2THREADS / 32] = {0};
+            for (Grp &G : groups) {
+                int w = 0;
+                for (int k = 1; k < P2THREADS / 32; ++k) if (load[k] < load[w]) w = k;
+                G.warp = w; load[w] += G.cost;
+            }
+            std::stable_sort(groups.begin(), groups.end(), [](const Grp &u, const Grp &v) { return u.warp < v.warp; });
+        }
         // ---- serialise the template
         T.clear();
         T.push_back((uint32_t)nE | ((uint32_t)nF << 16));
@@ -681,13 +717,18 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         const uint32_t sizeA16 = (uint32_t)(T.size() / 4);
         T.push_back((uint32_t)n_own | ((uint32_t)groups.size() << 8));
         T.push_back(0); T.push_back(0); T.push_back(0);
+        for (int w = 0; w < P2THREADS / 32; ++w) {          // groups [first, first + count) of warp w (the groups are ordered by warp)
+            uint32_t first = 0, count = 0;
+            for (size_t g = 0; g < groups.size(); ++g) if (groups[g].warp == w) { if (!count) first = (uint32_t)g; ++count; }
+            T.push_back(first | (count << 16));
+        }
         auto push_padded = [&](const std::vector<uint32_t> &v) { T.insert(T.end(), v.begin(), v.end()); while (T.size() % 4) T.push_back(0); };
         push_padded(degs); push_padded(offsKM); push_padded(offsF);
         {
             uint32_t pbase = 0;
             for (const Grp &G : groups) {
                 T.push_back((uint32_t)G.kind | ((uint32_t)G.nA << 8) | ((uint32_t)G.nB << 16));
-                T.push_back(pbase); T.push_back(0); T.push_back(0);
+                T.push_back(pbase); T.push_back((uint32_t)G.warp); T.push_back(0);
                 pbase += (uint32_t)(G.nA + G.nB) * GROUP;
             }
             P.pull_rows += pbase / GROUP;
@@ -720,18 +761,19 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             //   destination | mirrored destination << 16,   staging offset of the node's M_aa
             const uint32_t p3_at = (uint32_t)(T.size() - (size_t)sizeA16 * 4);
             uint32_t n_items = 0;
-            for (int o = 0; o < n_own; ++o) {
-                const uint32_t deg = degs[o] & 255u, pd = (degs[o] >> 16) & 255u, pdM = degs[o] >> 24;
-                if (!deg) continue;
-                const uint32_t base = offsKM[o] & 0xffffu, mo = (offsKM[o] >> 16) + 3 * pdM;
-                for (uint32_t j = 0; j < 3; ++j)
-                    for (uint32_t k = j; k < 3; ++k) {
+            // entry-major order: neighbouring lanes work on the same entry of consecutive nodes, whose rows are 9 deg doubles apart
+            // (an odd number for the usual odd degrees: conflict-free 64-bit accesses)
+            for (uint32_t j = 0; j < 3; ++j)
+                for (uint32_t k = j; k < 3; ++k)
+                    for (int o = 0; o < n_own; ++o) {
+                        const uint32_t deg = degs[o] & 255u, pd = (degs[o] >> 16) & 255u, pdM = degs[o] >> 24;
+                        if (!deg) continue;
+                        const uint32_t base = offsKM[o] & 0xffffu, mo = (offsKM[o] >> 16) + 3 * pdM;
                         T.push_back((base + 3 * deg * j + k) | (deg << 16) | ((j == k ? 1u : 0u) << 24));
                         T.push_back((base + 3 * deg * j + 3 * pd + k) | ((base + 3 * deg * k + 3 * pd + j) << 16));
                         T.push_back(mo);
                         ++n_items;
                     }
-            }
             T[(size_t)sizeA16 * 4 + 1] = p3_at;
             T[(size_t)sizeA16 * 4 + 2] = n_items;
             while (T.size() % 4) T.push_back(0);

@@ -112,8 +112,7 @@ EOLC_HD void pull2(uint32_t e, const double *scr, const double *&s0, const doubl
     s1 = scr + (e >> 16);
 }
 
-// Phase 2: the tile's records, in groups of 32 of one kind (forces_plan.h).  Warp `warp` of `nwarps` takes groups
-// warp, 2 nwarps - 1 - warp, 2 nwarps + warp, ... (the plan sorted the groups by descending cost, so this "snake" balances the warps).
+// Phase 2: the tile's records, in groups of 32 of one kind (forces_plan.h); every group names the warp that runs it.
 // Every lane of a group runs the same trip counts; the sums land in the staging rows (shared memory), laid out like the
 // global rows.  m_full: the M staging rows do not hold this template's explicit zeros yet (first tile / template or parity
 // changed), so mass records write whole 3x3 blocks; otherwise only the three diagonal entries change.
@@ -121,20 +120,20 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const uint32_t h0 = V.tmplB[0];
     const int nOwn = (int)(h0 & 255u), nG = (int)((h0 >> 8) & 255u), n4 = (nOwn + 3) & ~3;
-    const uint32_t *degs = V.tmplB + 4, *offsKM = degs + n4, *offsF = offsKM + n4, *grp = offsF + n4;
+    const uint32_t *grp = V.tmplB + B_HDR + 3 * n4;      // after the per-node tables (host side / phase-3 item construction only)
     const unsigned long long *recs = reinterpret_cast<const unsigned long long *>(grp + 4 * nG);
     const uint32_t *pulls = reinterpret_cast<const uint32_t *>(recs + (size_t)GROUP * nG);
     const double *scr = V.scr;
-    for (int g0 = 0; g0 < nG; g0 += 2 * nwarps) {
-        for (int half = 0; half < 2; ++half) {
-            const int g = g0 + (half ? 2 * nwarps - 1 - warp : warp);
-            if (g >= nG) continue;
+    {
+        const uint32_t wr = V.tmplB[4 + warp % nwarps];           // this warp's groups (forces_plan.h balances them)
+        for (int g = (int)(wr & 0xffffu), gend = g + (int)(wr >> 16); g < gend; ++g) {
             const uint32_t gw = grp[4 * g];
             const int kind = (int)(gw & 255u), nA = (int)((gw >> 8) & 255u), nB = (int)((gw >> 16) & 255u);
             const uint32_t *pl = pulls + grp[4 * g + 1] + lane;
             const unsigned long long rec = recs[(size_t)GROUP * g + lane];
-            const uint32_t p = (uint32_t)rec & 255u, own = (uint32_t)(rec >> 8) & 63u;
-            const bool valid = (rec >> 30) & 1ull, has2 = (rec >> 28) & 1ull;
+            const uint32_t off1 = (uint32_t)rec & 0xffffu, st1 = (uint32_t)(rec >> 16) & 1023u;
+            const uint32_t off2 = (uint32_t)(rec >> 26) & 0xffffu, st2 = (uint32_t)(rec >> 42) & 1023u;
+            const bool valid = (rec >> 54) & 1ull, has2 = (rec >> 52) & 1ull;
             if (kind == KIND_D) {
                 // ---- f of the node: its faces in ascending order (f.setZero() then +=, Forces.cpp:915,500-502)
                 double f0 = 0.0, f1 = 0.0, f2 = 0.0;
@@ -150,16 +149,15 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                     f0 += h1; f1 += j1; f2 += q1;
                 }
                 if (valid) {
-                    double *fo = V.fst + offsF[own];
+                    double *fo = V.fst + off1;
                     fo[0] = f0; fo[1] = f1; fo[2] = f2;
                     // clear the node's diagonal block: phase 3 then sums whole rows (no stale value of an earlier tile enters the sum)
-                    const uint32_t dw = degs[own], deg = dw & 255u;
-                    if (deg) {
-                        double *row = V.kst + (offsKM[own] & 0xffffu) + 3 * ((dw >> 16) & 255u);
+                    if (has2) {
+                        double *row = V.kst + off2;
                         row[0] = 0.0; row[1] = 0.0; row[2] = 0.0;
-                        row += 3 * deg;
+                        row += st2;
                         row[0] = 0.0; row[1] = 0.0; row[2] = 0.0;
-                        row += 3 * deg;
+                        row += st2;
                         row[0] = 0.0; row[1] = 0.0; row[2] = 0.0;
                     }
                 }
@@ -192,21 +190,18 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                     a0 += d0; a3 += d1; a6 += d2; a1 += d3; a4 += d4; a7 += d5; a2 += d6; a5 += d7; a8 += d8;
                 }
                 if (valid) {
-                    const uint32_t deg = degs[own] & 255u;
-                    double *row = V.kst + (offsKM[own] & 0xffffu) + 3 * p;
+                    double *row = V.kst + off1;
                     row[0] = a0; row[1] = a1; row[2] = a2;
-                    row += 3 * deg;
+                    row += st1;
                     row[0] = a3; row[1] = a4; row[2] = a5;
-                    row += 3 * deg;
+                    row += st1;
                     row[0] = a6; row[1] = a7; row[2] = a8;
                     if (has2) {   // the column node is owned too: its row gets the transposed block
-                        const uint32_t own2 = (uint32_t)(rec >> 22) & 63u, p2 = (uint32_t)(rec >> 14) & 255u;
-                        const uint32_t deg2 = degs[own2] & 255u;
-                        double *r2 = V.kst + (offsKM[own2] & 0xffffu) + 3 * p2;
+                        double *r2 = V.kst + off2;
                         r2[0] = a0; r2[1] = a3; r2[2] = a6;
-                        r2 += 3 * deg2;
+                        r2 += st2;
                         r2[0] = a1; r2[1] = a4; r2[2] = a7;
-                        r2 += 3 * deg2;
+                        r2 += st2;
                         r2[0] = a2; r2[1] = a5; r2[2] = a8;
                     }
                 }
@@ -222,20 +217,19 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                     m += *s1;
                 }
                 if (valid) {
-                    m *= ((rec >> 29) & 1ull) ? (1.0 / 12.0) : (1.0 / 24.0);
+                    m *= ((rec >> 53) & 1ull) ? (1.0 / 12.0) : (1.0 / 24.0);
                     for (int side = 0; side < 2; ++side) {
                         if (side && !has2) break;
-                        const uint32_t o_ = side ? (uint32_t)(rec >> 22) & 63u : own, p_ = side ? (uint32_t)(rec >> 14) & 255u : p;
-                        const uint32_t deg = (degs[o_] >> 8) & 255u;
-                        double *row = V.mst + (offsKM[o_] >> 16) + 3 * p_;
+                        double *row = V.mst + (side ? off2 : off1);
+                        const uint32_t st = side ? st2 : st1;
                         if (m_full) {
                             row[0] = m; row[1] = 0.0; row[2] = 0.0;
-                            row += 3 * deg;
+                            row += st;
                             row[0] = 0.0; row[1] = m; row[2] = 0.0;
-                            row += 3 * deg;
+                            row += st;
                             row[0] = 0.0; row[1] = 0.0; row[2] = m;
                         } else {
-                            row[0] = m; row[3 * deg + 1] = m; row[6 * deg + 2] = m;
+                            row[0] = m; row[st + 1] = m; row[2 * st + 2] = m;
                         }
                     }
                 }
@@ -255,16 +249,15 @@ EOLC_HD void phase3(int tid, int nthreads, const TileView &V) {
         const uint32_t w0 = items[3 * t], w1 = items[3 * t + 1];
         const int deg = (int)((w0 >> 16) & 255u);
         const double *r = V.kst + (w0 & 0xffffu);
-        // entry (j, k) of the sum of the node's blocks (the diagonal block was cleared in phase 2); four partial sums in a fixed
-        // order, so that the loads of a trip are independent of the running sums
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int p = 0;
-        for (; p + 4 <= deg; p += 4) {
-            const double v0 = r[3 * p], v1 = r[3 * p + 3], v2 = r[3 * p + 6], v3 = r[3 * p + 9];
-            s0 += v0; s1 += v1; s2 += v2; s3 += v3;
-        }
-        for (; p < deg; ++p) s0 += r[3 * p];
-        const double v = ((w0 >> 24) & 1u ? 2.0 * V.mst[items[3 * t + 2]] : 0.0) - ((s0 + s1) + (s2 + s3));
+        // entry (j, k) of the sum of the node's blocks (the diagonal block was cleared in phase 2): the first 16 blocks are loaded
+        // together and summed as a fixed tree (one round trip to shared memory instead of one per block), the rest in order
+        double v16[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v16[q] = q < deg ? r[3 * q] : 0.0;
+        double s0 = ((v16[0] + v16[1]) + (v16[2] + v16[3])) + ((v16[4] + v16[5]) + (v16[6] + v16[7]));
+        double s1 = ((v16[8] + v16[9]) + (v16[10] + v16[11])) + ((v16[12] + v16[13]) + (v16[14] + v16[15]));
+        for (int p = 16; p < deg; ++p) s1 += r[3 * p];
+        const double v = ((w0 >> 24) & 1u ? 2.0 * V.mst[items[3 * t + 2]] : 0.0) - (s0 + s1);
         V.kst[w1 & 0xffffu] = v;
         V.kst[w1 >> 16] = v;
     }

@@ -4,20 +4,20 @@
 TAG=${1:-q}; NCU=${2:-1}; SAN=${3:-0}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-timeout 900 python -m pytest tests/test_forces_gpu.py -x -q > $OUT/pytest_forces.log 2>&1; echo "pytest forces rc=$?"; tail -3 $OUT/pytest_forces.log
+timeout 300 python -m pytest tests/test_forces_gpu.py -x -q > $OUT/pytest_forces.log 2>&1; echo "pytest forces rc=$?"; tail -3 $OUT/pytest_forces.log
 if [ "$SAN" = "1" ]; then
-  timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_forces_gpu.py -x -q -k "golden or shuffled or empty" > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 $OUT/memcheck.log
-  timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_forces_gpu.py -x -q -k "golden" > $OUT/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -5 $OUT/racecheck.log
+  timeout 400 compute-sanitizer --tool memcheck python -m pytest tests/test_forces_gpu.py -x -q -k "golden or shuffled or empty or phases" > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 $OUT/memcheck.log
+  timeout 400 compute-sanitizer --tool racecheck python -m pytest tests/test_forces_gpu.py -x -q -k "golden" > $OUT/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -5 $OUT/racecheck.log
 fi
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-cd > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
+timeout 240 python bench.py --steps 20 --warmup 5 --no-cpu --no-cd > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 python - <<PY
 import json
 try:
     d=json.load(open("$OUT/bench.json")); print("ms/fill", d["ms_per_step"], "frac", d["roofline"]["frac"], "e2e ms", d["e2e"]["ms_per_step"], d["clocks"])
 except Exception as e: print("bench parse failed", e); print(open("$OUT/bench.err").read()[-2000:])
 PY
-timeout 600 python bench.py --workload ensemble64 --steps 10 --warmup 3 --no-cpu --no-cd > $OUT/bench_ens.json 2> $OUT/bench_ens.err; echo "ens rc=$?"
-timeout 600 python bench.py --workload sheet256 --steps 50 --warmup 5 --no-cpu --no-cd > $OUT/bench_256.json 2> $OUT/bench_256.err; echo "256 rc=$?"
+timeout 240 python bench.py --workload ensemble64 --steps 10 --warmup 3 --no-cpu --no-cd > $OUT/bench_ens.json 2> $OUT/bench_ens.err; echo "ens rc=$?"
+timeout 240 python bench.py --workload sheet256 --steps 50 --warmup 5 --no-cpu --no-cd > $OUT/bench_256.json 2> $OUT/bench_256.err; echo "256 rc=$?"
 python - <<PY
 import json
 for n in ("bench_ens","bench_256"):

@@ -28,7 +28,7 @@ d = buf[:rows].astype(np.float64)
 nw = rows // 148 if rows % 148 == 0 else 8
 tiles = d[:, 6]
 per = d[:, :6] / tiles[:, None]
-names = ["prefetch", "phase1", "wait+bar1", "phase2", "bar2", "copyout"]
+names = ["pf|P2", "P1", "bar1", "P3", "bar2", "co|barP23"]
 print("rows", rows, "tiles/CTA", tiles.mean(), "clk/tile total", per.sum(1).mean())
 print("all warps mean :", " ".join(f"{nm}={v:.0f}" for nm, v in zip(names, per.mean(0))))
 for w in range(nw):

@@ -116,7 +116,7 @@ void hm_plan_pull_conflicts(void *p, double *out) {
         const uint32_t *geo = P->tp.geo.data() + (size_t)t * P->tp.max_geo16 * 4;
         const uint32_t *B = P->tp.tmpl.data() + (size_t)geo[0] * 4 + (size_t)(geo[2] & 0xffffu) * 4;
         const int nOwn = B[0] & 255, nG = (B[0] >> 8) & 255, n4 = (nOwn + 3) & ~3;
-        const uint32_t *grp = B + 4 + 3 * n4;
+        const uint32_t *grp = B + tiles::B_HDR + 3 * n4;
         const uint32_t *pulls = grp + 4 * nG + 2 * tiles::GROUP * nG;
         for (int g = 0; g < nG; ++g) {
             const int kind = grp[4 * g] & 255, rows = ((grp[4 * g] >> 8) & 255) + ((grp[4 * g] >> 16) & 255);

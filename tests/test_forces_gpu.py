@@ -134,6 +134,29 @@ def test_reproducible_and_dev_equals_host(ctx):
     assert Kd[2].cpu().numpy().tobytes() == K3.tobytes() and fd[2].cpu().numpy().tobytes() == f3.tobytes()
 
 
+def test_output_pointer_phases(ctx):
+    """The bulk copy-out moves 16-byte aligned runs; outputs that start 8 bytes off a 16-byte boundary (odd scene strides of a batched
+    fill, caller sub-buffers) take the head / tail path: same bits as the aligned call, nothing written outside the arrays."""
+    import torch
+    mesh = _mesh("build4", 12, seed=4)
+    N = mesh["x"].shape[0]
+    plan = E.ForcesPlan(ctx, N, mesh["face_nodes"], mesh["edge_stencil"], X_hint=mesh["X"])
+    f0, M0, K0 = plan.fill(mesh["x"], mesh["X"], MAT, GRAV, H)
+    dev = torch.device("cuda", ctx.device)
+    xd = torch.from_numpy(mesh["x"]).to(dev)
+    Xd = torch.from_numpy(mesh["X"].copy()).to(dev)
+    for pf, pm, pk in ((1, 1, 1), (0, 1, 0), (1, 0, 1)):
+        bufs = [torch.full((n + 4,), float("nan"), dtype=torch.float64, device=dev) for n in (3 * N, plan.nnz[0], plan.nnz[1])]
+        torch.cuda.synchronize()
+        ptrs = [b.data_ptr() + 8 * (1 + p) for b, p in zip(bufs, (pf, pm, pk))]      # base is 256-byte aligned: +8 odd, +16 even phase
+        plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, ptrs[0], ptrs[1], ptrs[2], n_scenes=1)
+        torch.cuda.synchronize()
+        for b, p, ref in zip(bufs, (pf, pm, pk), (f0, M0, K0)):
+            h = b.cpu().numpy()
+            assert h[1 + p:1 + p + ref.size].tobytes() == ref.tobytes()
+            assert np.isnan(h[:1 + p]).all() and np.isnan(h[1 + p + ref.size:]).all()
+
+
 def test_fullsize_1024_properties(ctx):
     """BASELINE config 4 at full size (oracle too slow): size-independent properties.
     (1) pattern sizes of SURVEY §8; (2) symmetry of M (exact) and MDK (to rounding); (3) K has translation null space, so the three
