@@ -338,12 +338,47 @@ def run_ours(args):
                                 "note": "reference Compute*.cpp object code + restated Forces.cpp glue incl. triplets + setFromTriplets; single thread like the reference"}
     if rank == 0 and not args.no_cd:
         line["cd"] = bench_cd(ctx, dev, stream)
+    if rank == 0 and not args.no_cd and S == 1:
+        line["consumer"] = bench_consumer(plan, dev, stream, f_d, M_d, K_d, N, nnzM, nnzK)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     return 0
+
+
+def bench_consumer(plan, dev, stream, f_d, M_d, K_d, N, nnzM, nnzK):
+    """Secondary: the consumer of the fill on the device: b = -(M v + h f) and one CG iteration on MDK.
+    HBM-bound kernels; bytes = matrix values + 4 B of column-block index per 3x3 block + the vectors each kernel touches."""
+    import torch
+    v = torch.zeros(3 * N, dtype=torch.float64, device=dev)
+    b = torch.empty_like(v)
+    sol = torch.empty_like(v)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        plan.rhs_dev(M_d.data_ptr(), f_d.data_ptr(), v.data_ptr(), H, b.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(10):
+        plan.rhs_dev(M_d.data_ptr(), f_d.data_ptr(), v.data_ptr(), H, b.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    rhs_ms = e0.elapsed_time(e1) / 10
+    rhs_bytes = 8 * nnzM + 4 * nnzM // 9 + 8 * 3 * N * 3
+    plan.solve_cg_dev(K_d.data_ptr(), b.data_ptr(), sol.data_ptr(), tol=1e-300, max_iter=8)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    it, _ = plan.solve_cg_dev(K_d.data_ptr(), b.data_ptr(), sol.data_ptr(), tol=1e-300, max_iter=32)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    cg_ms = e0.elapsed_time(e1) / max(it, 1)
+    cg_bytes = 8 * nnzK + 4 * nnzK // 9 + 8 * 3 * N * 12
+    peak, _ = measured_peak()
+    return {"rhs": {"what": "b = -(M v + h f), Cloth.cpp:345", "ms": rhs_ms, "GB_per_s": rhs_bytes / rhs_ms / 1e6, "frac_of_hbm_peak": rhs_bytes / rhs_ms / 1e6 / peak},
+            "cg_iteration": {"what": "Jacobi-preconditioned CG on MDK (GeneralizedSolver.cpp:120-126), 5 launches, incl. the host's convergence check every 8",
+                             "ms": cg_ms, "GB_per_s": cg_bytes / cg_ms / 1e6, "frac_of_hbm_peak": cg_bytes / cg_ms / 1e6 / peak}}
 
 
 def bench_cd(ctx, dev, stream):
@@ -358,18 +393,23 @@ def bench_cd(ctx, dev, stream):
     x_d = torch.from_numpy(x).to(dev)
     torch.cuda.synchronize()
     cap = X.shape[0] + 4096
+    # caller-owned, page-locked record buffer reused across calls (what a C++ host would do; a fresh pageable numpy array per call
+    # costs more in page faults than the whole narrow phase)
+    rec_bytes = E.CONTACT_DTYPE.itemsize
+    pinned = torch.empty(cap * rec_bytes, dtype=torch.uint8).pin_memory()
+    out = pinned.numpy().view(E.CONTACT_DTYPE)
     for _ in range(3):
-        c, _ = plan.run(x_d.data_ptr(), obs, 0, 0, capacity=cap, x_is_device_ptr=True)
-    reps = 10
+        c, _ = plan.run(x_d.data_ptr(), obs, 0, 0, x_is_device_ptr=True, out=out)
+    reps = 20
     t = time.perf_counter()
     for _ in range(reps):
-        c, _ = plan.run(x_d.data_ptr(), obs, 0, 0, capacity=cap, x_is_device_ptr=True)
+        c, _ = plan.run(x_d.data_ptr(), obs, 0, 0, x_is_device_ptr=True, out=out)
     dt = (time.perf_counter() - t) / reps
     pair_tests, launches = plan.stats()
     out = {"workload": "CD2, regular2 512x512 over the simulationSettingsBox.json box (BASELINE configs[2])",
            "contacts": int(len(c)), "ms_per_call": dt * 1e3, "contacts_per_s": len(c) / dt,
            "pair_tests_per_s": pair_tests / dt, "launches_per_call": launches,
-           "timing": "wall clock around eolc_cd_run_dev incl. D2H of the contact list and the host post-pass"}
+           "timing": "wall clock around eolc_cd_run_dev incl. D2H of the contact list (%d B records, pinned caller buffer) and the host post-pass" % rec_bytes}
     try:
         from oracle import oracle as O
         t = time.perf_counter()

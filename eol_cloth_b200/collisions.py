@@ -45,13 +45,17 @@ class CollisionPlan:
         capi.check(capi.lib().eolc_cd_edge_table(self._h, capi.iptr(out)))
         return out[:self.E].copy()
 
-    def run(self, x, obs, point_eol_flag, remap, capacity=None, x_is_device_ptr=False, n_scenes=1):
+    def run(self, x, obs, point_eol_flag, remap, capacity=None, x_is_device_ptr=False, n_scenes=1, out=None):
+        """out: optional caller-owned record buffer (CONTACT_DTYPE), reused across calls; page-locked memory is DMA'd into directly."""
+        if out is not None:
+            capacity = out.shape[0]
         if capacity is None:
             capacity = n_scenes * (self.N + 64) + 4096
         nP, nB = obs.pxyz.shape[0], obs.box_whd.shape[0]
         L = capi.lib()
+        caller_out = out
         while True:
-            out = np.empty(capacity, dtype=CONTACT_DTYPE)
+            out = caller_out if caller_out is not None else np.empty(capacity, dtype=CONTACT_DTYPE)
             if x_is_device_ptr:
                 off = np.zeros(n_scenes + 1, dtype=np.int32)
                 rc = L.eolc_cd_run_batched_dev(self._h, int(n_scenes), x, nP, capi.dptr(obs.pxyz), capi.dptr(obs.pnorms), nB,
@@ -67,7 +71,7 @@ class CollisionPlan:
                                    capi.dptr(obs.box_whd), capi.dptr(obs.box_E), int(point_eol_flag), int(remap),
                                    out.ctypes.data_as(capi.c_vp), capacity, ctypes.byref(nn))
                 n, off = nn.value, None
-            if rc == -3:       # EOLC_ERR_CAPACITY: n holds the required size
+            if rc == -3 and caller_out is None:       # EOLC_ERR_CAPACITY: n holds the required size
                 capacity = n
                 continue
             capi.check(rc)

@@ -19,7 +19,9 @@
 #include "elements.cuh"
 #include "forces_plan.h"
 #include "tile_exec.cuh"
+#include "solve.cuh"
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <numeric>
 
@@ -54,6 +56,10 @@ struct eolc_forces_plan {
     // staging for the host entry point
     DevBuf<double> d_x, d_X, d_f, d_Mv, d_Kv;
     PinnedBuf<double> p_in, p_out;
+    // block structure on the device + CG work vectors (solve.cuh), built on first use
+    DevBuf<int32_t> d_blkM, d_nbrM, d_blkK, d_nbrK;
+    DevBuf<double> d_cg;                          // r, p, Ap/z, dinv (dof each), partials, scalars
+    PinnedBuf<double> p_sc;
 #ifdef EOLC_TILE_CLOCKS
     DevBuf<unsigned long long> d_dbg;
     int dbg_grid = 0;
@@ -865,6 +871,78 @@ int eolc_debug_tile_clocks(eolc_forces_plan *plan, unsigned long long *out, int 
     return rows;
 }
 #endif
+
+// ---- consumer of the fill on the device: right-hand side and the collision-free CG branch (solve.cuh) ----
+static int ensure_block_structure(eolc_forces_plan *P) {
+    if (P->d_blkK.p || P->N == 0) return EOLC_OK;
+    cudaStream_t st = P->ctx->stream;
+    std::vector<int32_t> bm(P->pat.blkptrM.begin(), P->pat.blkptrM.end()), bk(P->pat.blkptrK.begin(), P->pat.blkptrK.end());
+    EOLC_CUDA(P->d_blkM.upload(bm, st)); EOLC_CUDA(P->d_blkK.upload(bk, st));
+    EOLC_CUDA(P->d_nbrM.upload(P->pat.nbrM, st)); EOLC_CUDA(P->d_nbrK.upload(P->pat.nbrK, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));      // bm / bk die at scope exit
+    return EOLC_OK;
+}
+
+int eolc_forces_rhs_dev(eolc_forces_plan *plan, const double *M_vals_dev, const double *f_dev, const double *v_dev, double h, double *b_dev) {
+    EOLC_REQUIRE(plan, "plan is NULL");
+    if (plan->N == 0) return EOLC_OK;
+    EOLC_REQUIRE(M_vals_dev && f_dev && v_dev && b_dev, "NULL device pointer");
+    EOLC_CUDA(cudaSetDevice(plan->ctx->device));
+    int rc = ensure_block_structure(plan);
+    if (rc) return rc;
+    const int grid = std::min((plan->N + solve::WARPS - 1) / solve::WARPS, 16 * plan->ctx->sm_count);
+    solve::k_rhs<<<grid, solve::THREADS, 0, plan->ctx->stream>>>(plan->N, plan->d_blkM.p, plan->d_nbrM.p, M_vals_dev, f_dev, v_dev, h, b_dev);
+    EOLC_CUDA(cudaGetLastError());
+    return EOLC_OK;
+}
+
+int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const double *b_dev, double *v_dev, double tol, int32_t max_iter,
+                      int32_t *iters_out, double *rel_resid_out) {
+    EOLC_REQUIRE(plan, "plan is NULL");
+    if (iters_out) *iters_out = 0;
+    if (rel_resid_out) *rel_resid_out = 0.0;
+    if (plan->N == 0) return EOLC_OK;
+    EOLC_REQUIRE(MDK_vals_dev && b_dev && v_dev, "NULL device pointer");
+    EOLC_REQUIRE(tol > 0.0 && max_iter >= 0, "tol must be positive and max_iter non-negative");
+    eolc_forces_plan *P = plan;
+    EOLC_CUDA(cudaSetDevice(P->ctx->device));
+    int rc = ensure_block_structure(P);
+    if (rc) return rc;
+    cudaStream_t st = P->ctx->stream;
+    const size_t n = (size_t)P->dof;
+    const int gridv = (int)std::min<size_t>((n + solve::THREADS - 1) / solve::THREADS, (size_t)8 * P->ctx->sm_count);
+    const int gridn = std::min((P->N + solve::WARPS - 1) / solve::WARPS, 16 * P->ctx->sm_count);
+    const size_t nparts = (size_t)2 * std::max(gridv, gridn);
+    EOLC_CUDA(P->d_cg.ensure(4 * n + nparts + 8));
+    EOLC_CUDA(P->p_sc.ensure(8));
+    double *r = P->d_cg.p, *p = r + n, *Ap = p + n, *dinv = Ap + n, *part = dinv + n, *sc = part + nparts;
+    solve::k_cg_init<<<gridv, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, b_dev, v_dev, r, p, dinv, part);
+    solve::k_cg_scalars<<<1, solve::THREADS, 0, st>>>(gridv, 2, part, sc, 0, tol);
+    int it = 0;
+    const int check_every = 8;      // the convergence flag lives on the device; the host looks at it every few iterations
+    EOLC_CUDA(cudaMemcpyAsync(P->p_sc.p, sc, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));
+    bool done = P->p_sc.p[6] != 0.0;   // zero (or already tiny) right-hand side: x = 0, like Eigen's early return
+    while (!done && it < max_iter) {
+        const int batch = std::min(check_every, max_iter - it);
+        for (int k = 0; k < batch; ++k) {
+            solve::k_cg_ap<<<gridn, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, p, Ap, part, sc);
+            solve::k_cg_scalars<<<1, solve::THREADS, 0, st>>>(gridn, 1, part, sc, 1, tol);
+            solve::k_cg_update<<<gridv, solve::THREADS, 0, st>>>(n, v_dev, r, p, Ap, dinv, part, sc);
+            solve::k_cg_scalars<<<1, solve::THREADS, 0, st>>>(gridv, 2, part, sc, 2, tol);
+            solve::k_cg_dir<<<gridv, solve::THREADS, 0, st>>>(n, p, Ap, sc);
+        }
+        it += batch;
+        EOLC_CUDA(cudaMemcpyAsync(P->p_sc.p, sc, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        EOLC_CUDA(cudaStreamSynchronize(st));
+        done = P->p_sc.p[6] != 0.0;
+    }
+    EOLC_CUDA(cudaGetLastError());
+    if (iters_out) *iters_out = it;      // upper bound to a multiple of the check interval: iterations after convergence are no-ops
+    const double rhs2 = P->p_sc.p[5] / (tol * tol);
+    if (rel_resid_out) *rel_resid_out = rhs2 > 0.0 ? std::sqrt(P->p_sc.p[2] / rhs2) : 0.0;
+    return EOLC_OK;
+}
 
 int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return plan ? 1 : 0; }
 

@@ -1,0 +1,154 @@
+// solve.cuh — the consumer of Forces::fill on the device, so that M / MDK need not cross PCIe:
+//   Cloth::solve right-hand side      b = -(M v + h f)                         /root/reference/src/Cloth.cpp:345
+//   GeneralizedSolver::velocitySolve, collision-free branch without fixed points: ConjugateGradient<SparseMatrix<double>, Lower|Upper>
+//       cg.compute(MDK); v = cg.solve(-b)                                     /root/reference/src/GeneralizedSolver.cpp:120-126
+//   (that branch is dead code in the reference, `if (!collisions && false)`, but it is the only solver a build without Mosek / Gurobi
+//   could run: BASELINE configs[0].)  The iteration restates Eigen 3.3's conjugate_gradient() (IterativeLinearSolvers/
+//   ConjugateGradient.h — external, not under /root/reference) with its default DiagonalPreconditioner, started from x = 0.
+//
+// Kernels work on the block structure of the plan's pattern (node a owns 3 rows; row j of node a is the contiguous segment
+// vals[9 blkptr[a] + 3 deg j ...] of 3 deg doubles, column block p belongs to node nbr[blkptr[a] + p]): 4 index bytes per 72 value
+// bytes, coalesced value reads.  All reductions run in a fixed order (warp tree, block tree, one-block final pass): bit-reproducible.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace eolc {
+namespace solve {
+
+constexpr int WARPS = 8, THREADS = 32 * WARPS;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// rows of node a times x: y[0..2] valid in every lane
+__device__ __forceinline__ void node_rows_times(int lane, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
+                                                const double *__restrict__ vals, const double *__restrict__ x, int a, double y[3]) {
+    const int b0 = blkptr[a], n3 = 3 * (blkptr[a + 1] - b0);
+    const double *row = vals + 9 * (size_t)b0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    // the node's three rows are one contiguous run of 3 n3 values: walk it flat (full lanes), route each product to its row's sum
+    for (int l = lane; l < 3 * n3; l += 32) {
+        const int j = l < n3 ? 0 : (l < 2 * n3 ? 1 : 2), c = l - j * n3, p = c / 3;
+        const double t = row[l] * x[3 * (size_t)nbr[b0 + p] + (c - 3 * p)];
+        if (j == 0) s0 += t; else if (j == 1) s1 += t; else s2 += t;
+    }
+    y[0] = warp_sum(s0); y[1] = warp_sum(s1); y[2] = warp_sum(s2);
+}
+
+// fixed-order block reduction of one value per warp; result valid in thread 0
+__device__ __forceinline__ double block_sum(double warp_value, double *sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sh[warp] = warp_value;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) for (int w = 0; w < WARPS; ++w) t += sh[w];
+    __syncthreads();
+    return t;
+}
+
+// b = -(M v + h f)
+__global__ void __launch_bounds__(THREADS) k_rhs(int N, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
+                                                 const double *__restrict__ Mv, const double *__restrict__ f, const double *__restrict__ v,
+                                                 double h, double *__restrict__ b) {
+    const int lane = threadIdx.x & 31;
+    for (int a = blockIdx.x * WARPS + (threadIdx.x >> 5); a < N; a += gridDim.x * WARPS) {
+        double y[3];
+        node_rows_times(lane, blkptr, nbr, Mv, v, a, y);
+        if (lane < 3) b[3 * (size_t)a + lane] = -((lane == 0 ? y[0] : lane == 1 ? y[1] : y[2]) + h * f[3 * (size_t)a + lane]);
+    }
+}
+
+// CG state scalars on the device: [0] absNew = r.z, [1] p.Ap, [2] ||r||^2, [3] alpha, [4] beta, [5] threshold, [6] converged flag (as double)
+// init: x = 0, r = rhs = -b, z = r / diag(A), p = z; partials of r.z and rhs.rhs
+__global__ void __launch_bounds__(THREADS) k_cg_init(int N, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
+                                                     const double *__restrict__ Kv, const double *__restrict__ b, double *__restrict__ x,
+                                                     double *__restrict__ r, double *__restrict__ p, double *__restrict__ dinv,
+                                                     double *__restrict__ part) {
+    __shared__ double sh[WARPS];
+    double rz = 0.0, rr = 0.0;
+    for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < 3 * (size_t)N; i += (size_t)gridDim.x * THREADS) {
+        const int a = (int)(i / 3), j = (int)(i - 3 * (size_t)a);
+        const int b0 = blkptr[a], deg = blkptr[a + 1] - b0;
+        double d = 1.0;
+        if (deg > 0) {
+            int pd = 0;
+            while (pd < deg && nbr[b0 + pd] != a) ++pd;      // position of the diagonal block in the row
+            const double akk = pd < deg ? Kv[9 * (size_t)b0 + (size_t)3 * deg * j + 3 * pd + j] : 0.0;
+            d = akk != 0.0 ? 1.0 / akk : 1.0;                // Eigen's DiagonalPreconditioner: 1 where the diagonal is zero
+        }
+        const double ri = -b[i], zi = d * ri;
+        dinv[i] = d; x[i] = 0.0; r[i] = ri; p[i] = zi;
+        rz += ri * zi; rr += ri * ri;
+    }
+    const double t0 = block_sum(warp_sum(rz), sh), t1 = block_sum(warp_sum(rr), sh);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = t0; part[2 * blockIdx.x + 1] = t1; }
+}
+
+// one block: sums `stride` interleaved partial columns in a fixed order and updates the scalars
+//   mode 0 (after init):  absNew = sum0, threshold = tol^2 * sum1, ||r||^2 = sum1
+//   mode 1 (after Ap):    p.Ap = sum0, alpha = absNew / p.Ap
+//   mode 2 (after update): absOld = absNew, absNew = sum0, ||r||^2 = sum1, beta = absNew / absOld, converged = ||r||^2 < threshold
+__global__ void __launch_bounds__(THREADS) k_cg_scalars(int nparts, int stride, const double *__restrict__ part, double *__restrict__ sc, int mode, double tol) {
+    __shared__ double sh[WARPS];
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += THREADS) { s0 += part[(size_t)stride * i]; if (stride > 1) s1 += part[(size_t)stride * i + 1]; }
+    const double t0 = block_sum(warp_sum(s0), sh), t1 = block_sum(warp_sum(s1), sh);
+    if (threadIdx.x == 0) {
+        if (mode == 0) { sc[0] = t0; sc[2] = t1; sc[5] = tol * tol * t1; sc[6] = t1 <= sc[5] || t1 == 0.0 ? 1.0 : 0.0; }
+        else if (mode == 1) { sc[1] = t0; sc[3] = sc[0] / t0; }
+        else { const double old = sc[0]; sc[0] = t0; sc[2] = t1; sc[4] = t0 / old; if (t1 < sc[5]) sc[6] = 1.0; }
+    }
+}
+
+// Ap = A p and the partials of p.Ap
+__global__ void __launch_bounds__(THREADS) k_cg_ap(int N, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
+                                                   const double *__restrict__ Kv, const double *__restrict__ p, double *__restrict__ Ap,
+                                                   double *__restrict__ part, const double *__restrict__ sc) {
+    __shared__ double sh[WARPS];
+    if (sc[6] != 0.0) return;                                  // converged: the remaining launches of the batch are no-ops
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int a = blockIdx.x * WARPS + (threadIdx.x >> 5); a < N; a += gridDim.x * WARPS) {
+        double y[3];
+        node_rows_times(lane, blkptr, nbr, Kv, p, a, y);
+        if (lane < 3) {
+            const double yi = lane == 0 ? y[0] : lane == 1 ? y[1] : y[2];
+            Ap[3 * (size_t)a + lane] = yi;
+            acc += p[3 * (size_t)a + lane] * yi;
+        }
+    }
+    const double t = block_sum(warp_sum(acc), sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+
+// x += alpha p; r -= alpha Ap; z = dinv r (kept in Ap's storage); partials of r.z and r.r
+__global__ void __launch_bounds__(THREADS) k_cg_update(size_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+                                                       double *__restrict__ Ap_z, const double *__restrict__ dinv, double *__restrict__ part,
+                                                       const double *__restrict__ sc) {
+    __shared__ double sh[WARPS];
+    if (sc[6] != 0.0) return;
+    const double alpha = sc[3];
+    double rz = 0.0, rr = 0.0;
+    for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * Ap_z[i], zi = dinv[i] * ri;
+        r[i] = ri; Ap_z[i] = zi;
+        rz += ri * zi; rr += ri * ri;
+    }
+    const double t0 = block_sum(warp_sum(rz), sh), t1 = block_sum(warp_sum(rr), sh);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = t0; part[2 * blockIdx.x + 1] = t1; }
+}
+
+// p = z + beta p
+__global__ void __launch_bounds__(THREADS) k_cg_dir(size_t n, double *__restrict__ p, const double *__restrict__ z, const double *__restrict__ sc) {
+    if (sc[6] != 0.0) return;
+    const double beta = sc[4];
+    for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) p[i] = z[i] + beta * p[i];
+}
+
+}  // namespace solve
+}  // namespace eolc

@@ -95,6 +95,18 @@ class ForcesPlan:
         capi.check(capi.lib().eolc_forces_fill_batched_dev(self._h, int(n_scenes), x_ptr, X_ptr, ctypes.byref(m),
                                                            capi.dptr(g), float(h), f_ptr, Mv_ptr, Kv_ptr))
 
+    def rhs_dev(self, Mv_ptr, f_ptr, v_ptr, h, b_ptr):
+        """b = -(M v + h f) on the device (Cloth::solve, Cloth.cpp:345); device pointers, asynchronous on ctx.stream."""
+        capi.check(capi.lib().eolc_forces_rhs_dev(self._h, Mv_ptr, f_ptr, v_ptr, float(h), b_ptr))
+
+    def solve_cg_dev(self, Kv_ptr, b_ptr, v_ptr, tol=2.220446049250313e-16, max_iter=None):
+        """v = ConjugateGradient(MDK).solve(-b) on the device (GeneralizedSolver.cpp:120-126, Eigen defaults: diagonal
+        preconditioner, x0 = 0, tol = epsilon, at most 2 dof iterations).  Returns (iterations issued, relative residual)."""
+        it, res = ctypes.c_int32(0), ctypes.c_double(0.0)
+        capi.check(capi.lib().eolc_solve_cg_dev(self._h, Kv_ptr, b_ptr, v_ptr, float(tol), int(2 * self.dof if max_iter is None else max_iter),
+                                                ctypes.byref(it), ctypes.byref(res)))
+        return it.value, res.value
+
     def close(self):
         if self._h:
             capi.lib().eolc_forces_plan_destroy(self._h)

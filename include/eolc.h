@@ -106,6 +106,18 @@ int eolc_forces_fill_dev(eolc_forces_plan *plan, const double *x_dev, const doub
 int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
                                  const eolc_material *mat, const double grav[3], double h, double *f_dev,
                                  double *M_vals_dev, double *MDK_vals_dev);
+/* ---- consumer of the fill, on the device -------------------------------- */
+/* Cloth::solve right-hand side, src/Cloth.cpp:345:  b = -(M v + h f).  M_vals_dev / f_dev: outputs of a fill with this plan;
+ * v_dev, b_dev: dof doubles.  Asynchronous on eolc_ctx_stream(). */
+int eolc_forces_rhs_dev(eolc_forces_plan *plan, const double *M_vals_dev, const double *f_dev, const double *v_dev, double h,
+                        double *b_dev);
+/* GeneralizedSolver::velocitySolve, collision-free branch without fixed points (src/GeneralizedSolver.cpp:120-126):
+ * ConjugateGradient<SparseMatrix<double>, Lower|Upper> cg; cg.compute(MDK); v = cg.solve(-b) — Eigen's CG with its default
+ * diagonal preconditioner, started from 0, stopped at ||MDK v + b|| <= tol ||b|| (Eigen's default tol is DBL_EPSILON, its default
+ * iteration cap 2 dof).  v_dev receives the solution; iters_out (may be NULL) the iterations issued (a multiple of the host's
+ * check interval), rel_resid_out (may be NULL) the final relative residual.  Synchronises the stream. */
+int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const double *b_dev, double *v_dev, double tol,
+                      int32_t max_iter, int32_t *iters_out, double *rel_resid_out);
 /* number of kernels one fill launches (for bench accounting) */
 int eolc_forces_launches_per_fill(const eolc_forces_plan *plan);
 

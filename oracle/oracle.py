@@ -224,3 +224,58 @@ def face_frame(xa, xb, xc, Xa, Xb, Xc):
     PP, QQ = np.zeros(6), np.zeros(4)
     lib().oracle_face_frame(*[_d(_f64(a)) for a in (xa, xb, xc, Xa, Xb, Xc)], _d(PP), _d(QQ))
     return PP, QQ
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Consumer of Forces::fill — numpy restatements, TEST INFRASTRUCTURE ONLY
+# ---------------------------------------------------------------------------------------------------------------------
+def _csc(mat, dof):
+    import scipy.sparse as sp
+    o, i, v = mat
+    return sp.csc_matrix((v, i, o), shape=(dof, dof))
+
+
+def cloth_rhs(M, f, v, h):
+    """b = -(M v + h f): /root/reference/src/Cloth.cpp:345.  M = (outer, inner, values) as returned by forces_fill."""
+    return -(_csc(M, f.size) @ v + h * f)
+
+
+def eigen_cg(A, b, tol=np.finfo(float).eps, max_iter=None):
+    """v = ConjugateGradient<SparseMatrix<double>, Lower|Upper>(A).solve(-b): /root/reference/src/GeneralizedSolver.cpp:122-125.
+    Restates conjugate_gradient() of Eigen 3.3 (Eigen/src/IterativeLinearSolvers/ConjugateGradient.h — EXTERNAL dependency of the
+    reference, not vendored under /root/reference; README.md:14 names Eigen 3.3, CMakeLists.txt:26 shows 3.3.4) with the default
+    DiagonalPreconditioner (1/a_ii, 1 where a_ii == 0), x0 = 0, threshold tol^2 |rhs|^2, default cap 2 n iterations.
+    Parity unpinned by the reference (the branch is dead code there); pinned here against a sparse direct solve (tests/test_oracle.py).
+    Returns (v, iterations, relative residual)."""
+    A = _csc(A, b.size) if isinstance(A, tuple) else A
+    rhs = -np.asarray(b, dtype=np.float64)
+    n = rhs.size
+    max_iter = 2 * n if max_iter is None else max_iter
+    d = A.diagonal()
+    dinv = np.where(d != 0.0, 1.0 / np.where(d != 0.0, d, 1.0), 1.0)
+    x = np.zeros(n)
+    residual = rhs.copy()
+    rhs2 = float(rhs @ rhs)
+    if rhs2 == 0.0:
+        return x, 0, 0.0
+    threshold = tol * tol * rhs2
+    r2 = float(residual @ residual)
+    if r2 < threshold:
+        return x, 0, np.sqrt(r2 / rhs2)
+    p = dinv * residual
+    abs_new = float(residual @ p)
+    it = 0
+    while it < max_iter:
+        tmp = A @ p
+        alpha = abs_new / float(p @ tmp)
+        x += alpha * p
+        residual -= alpha * tmp
+        r2 = float(residual @ residual)
+        it += 1
+        if r2 < threshold:
+            break
+        z = dinv * residual
+        abs_old = abs_new
+        abs_new = float(residual @ z)
+        p = z + (abs_new / abs_old) * p
+    return x, it, np.sqrt(r2 / rhs2)

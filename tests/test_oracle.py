@@ -151,3 +151,30 @@ def test_cd_edge_table_matches_createEdges_order(oracle):
     key = np.maximum(tab[:, 0], tab[:, 1]).astype(np.int64) * 10**6 + np.minimum(tab[:, 0], tab[:, 1])
     assert np.all(np.diff(key) > 0)
     assert tab.shape[0] == 3 * 16 + 2 * 4
+
+
+def test_eigen_cg_restatement_against_direct_solve(oracle):
+    """oracle.eigen_cg (restated Eigen 3.3 CG, the reference's collision-free solver branch) against a sparse direct solve of the
+    assembled system; cloth_rhs against dense arithmetic."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    import eol_cloth_b200 as E
+    X, fn = E.meshgen.regular2(10)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    x = E.meshgen.drape_state(X, seed=3)
+    ref = oracle.forces_fill(fn, es, x, X)
+    dof = ref["f"].size
+    rng = np.random.default_rng(0)
+    v = 0.1 * rng.standard_normal(dof)
+    h = 0.5e-2
+    b = oracle.cloth_rhs(ref["M"], ref["f"], v, h)
+    o, i, vals = ref["M"]
+    Md = sp.csc_matrix((vals, i, o), shape=(dof, dof)).toarray()
+    assert np.allclose(b, -(Md @ v + h * ref["f"]), rtol=1e-13, atol=1e-18)
+    o, i, vals = ref["MDK"]
+    K = sp.csc_matrix((vals, i, o), shape=(dof, dof))
+    sol, it, res = oracle.eigen_cg(ref["MDK"], b, tol=1e-13)
+    direct = spl.spsolve(K.tocsc(), -b)
+    assert res < 1e-13 and 0 < it <= 2 * dof
+    assert np.abs(sol - direct).max() <= 1e-9 * np.abs(direct).max()
+    assert oracle.eigen_cg(ref["MDK"], np.zeros(dof))[1] == 0
