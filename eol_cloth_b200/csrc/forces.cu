@@ -896,8 +896,20 @@ int eolc_forces_rhs_dev(eolc_forces_plan *plan, const double *M_vals_dev, const 
     return EOLC_OK;
 }
 
-int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const double *b_dev, double *v_dev, double tol, int32_t max_iter,
-                      int32_t *iters_out, double *rel_resid_out) {
+int eolc_forces_integrate_dev(eolc_forces_plan *plan, const double *v_dev, double h, double *x_dev) {
+    EOLC_REQUIRE(plan, "plan is NULL");
+    if (plan->N == 0) return EOLC_OK;
+    EOLC_REQUIRE(v_dev && x_dev, "NULL device pointer");
+    EOLC_CUDA(cudaSetDevice(plan->ctx->device));
+    const size_t n = (size_t)3 * plan->N;
+    const int grid = (int)std::min<size_t>((n + solve::THREADS - 1) / solve::THREADS, (size_t)8 * plan->ctx->sm_count);
+    solve::k_integrate<<<grid, solve::THREADS, 0, plan->ctx->stream>>>(n, x_dev, v_dev, h);
+    EOLC_CUDA(cudaGetLastError());
+    return EOLC_OK;
+}
+
+int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const double *b_dev, const unsigned char *fixed_dev, double *v_dev,
+                      double tol, int32_t max_iter, int32_t *iters_out, double *rel_resid_out) {
     EOLC_REQUIRE(plan, "plan is NULL");
     if (iters_out) *iters_out = 0;
     if (rel_resid_out) *rel_resid_out = 0.0;
@@ -916,7 +928,7 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
     EOLC_CUDA(P->d_cg.ensure(4 * n + nparts + 8));
     EOLC_CUDA(P->p_sc.ensure(8));
     double *r = P->d_cg.p, *p = r + n, *Ap = p + n, *dinv = Ap + n, *part = dinv + n, *sc = part + nparts;
-    solve::k_cg_init<<<gridv, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, b_dev, v_dev, r, p, dinv, part);
+    solve::k_cg_init<<<gridv, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, b_dev, fixed_dev, v_dev, r, p, dinv, part);
     solve::k_cg_scalars<<<1, solve::THREADS, 0, st>>>(gridv, 2, part, sc, 0, tol);
     int it = 0;
     const int check_every = 8;      // the convergence flag lives on the device; the host looks at it every few iterations
@@ -926,7 +938,7 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
     while (!done && it < max_iter) {
         const int batch = std::min(check_every, max_iter - it);
         for (int k = 0; k < batch; ++k) {
-            solve::k_cg_ap<<<gridn, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, p, Ap, part, sc);
+            solve::k_cg_ap<<<gridn, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, p, dinv, Ap, part, sc);
             solve::k_cg_scalars<<<1, solve::THREADS, 0, st>>>(gridn, 1, part, sc, 1, tol);
             solve::k_cg_update<<<gridv, solve::THREADS, 0, st>>>(n, v_dev, r, p, Ap, dinv, part, sc);
             solve::k_cg_scalars<<<1, solve::THREADS, 0, st>>>(gridv, 2, part, sc, 2, tol);

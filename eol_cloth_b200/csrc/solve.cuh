@@ -63,10 +63,11 @@ __global__ void __launch_bounds__(THREADS) k_rhs(int N, const int32_t *__restric
 }
 
 // CG state scalars on the device: [0] absNew = r.z, [1] p.Ap, [2] ||r||^2, [3] alpha, [4] beta, [5] threshold, [6] converged flag (as double)
-// init: x = 0, r = rhs = -b, z = r / diag(A), p = z; partials of r.z and rhs.rhs
+// init: x = 0, r = rhs = -b, z = r / diag(A), p = z; partials of r.z and rhs.rhs.  A dof with fixed[i] != 0 keeps x = 0: its
+// row and column drop out (dinv = 0 -> r = z = p = 0 there, and k_cg_ap zeroes its row), i.e. CG runs on the free-free block.
 __global__ void __launch_bounds__(THREADS) k_cg_init(int N, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
-                                                     const double *__restrict__ Kv, const double *__restrict__ b, double *__restrict__ x,
-                                                     double *__restrict__ r, double *__restrict__ p, double *__restrict__ dinv,
+                                                     const double *__restrict__ Kv, const double *__restrict__ b, const unsigned char *__restrict__ fixed,
+                                                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ p, double *__restrict__ dinv,
                                                      double *__restrict__ part) {
     __shared__ double sh[WARPS];
     double rz = 0.0, rr = 0.0;
@@ -80,7 +81,8 @@ __global__ void __launch_bounds__(THREADS) k_cg_init(int N, const int32_t *__res
             const double akk = pd < deg ? Kv[9 * (size_t)b0 + (size_t)3 * deg * j + 3 * pd + j] : 0.0;
             d = akk != 0.0 ? 1.0 / akk : 1.0;                // Eigen's DiagonalPreconditioner: 1 where the diagonal is zero
         }
-        const double ri = -b[i], zi = d * ri;
+        if (fixed && fixed[i]) d = 0.0;                          // prescribed (zero) velocity: the dof drops out of the system
+        const double ri = d != 0.0 ? -b[i] : 0.0, zi = d * ri;
         dinv[i] = d; x[i] = 0.0; r[i] = ri; p[i] = zi;
         rz += ri * zi; rr += ri * ri;
     }
@@ -104,10 +106,10 @@ __global__ void __launch_bounds__(THREADS) k_cg_scalars(int nparts, int stride, 
     }
 }
 
-// Ap = A p and the partials of p.Ap
+// Ap = A p (rows of fixed dofs zeroed: dinv == 0 marks them) and the partials of p.Ap
 __global__ void __launch_bounds__(THREADS) k_cg_ap(int N, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
-                                                   const double *__restrict__ Kv, const double *__restrict__ p, double *__restrict__ Ap,
-                                                   double *__restrict__ part, const double *__restrict__ sc) {
+                                                   const double *__restrict__ Kv, const double *__restrict__ p, const double *__restrict__ dinv,
+                                                   double *__restrict__ Ap, double *__restrict__ part, const double *__restrict__ sc) {
     __shared__ double sh[WARPS];
     if (sc[6] != 0.0) return;                                  // converged: the remaining launches of the batch are no-ops
     const int lane = threadIdx.x & 31;
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(THREADS) k_cg_ap(int N, const int32_t *__restr
         double y[3];
         node_rows_times(lane, blkptr, nbr, Kv, p, a, y);
         if (lane < 3) {
-            const double yi = lane == 0 ? y[0] : lane == 1 ? y[1] : y[2];
+            const double yi = dinv[3 * (size_t)a + lane] != 0.0 ? (lane == 0 ? y[0] : lane == 1 ? y[1] : y[2]) : 0.0;
             Ap[3 * (size_t)a + lane] = yi;
             acc += p[3 * (size_t)a + lane] * yi;
         }
@@ -148,6 +150,11 @@ __global__ void __launch_bounds__(THREADS) k_cg_dir(size_t n, double *__restrict
     if (sc[6] != 0.0) return;
     const double beta = sc[4];
     for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) p[i] = z[i] + beta * p[i];
+}
+
+// x += h v (Cloth::step, Cloth.cpp:394-400: node->x = node->x + h * node->v for every node)
+__global__ void __launch_bounds__(THREADS) k_integrate(size_t n, double *__restrict__ x, const double *__restrict__ v, double h) {
+    for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) x[i] = x[i] + h * v[i];
 }
 
 }  // namespace solve

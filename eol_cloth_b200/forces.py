@@ -99,11 +99,16 @@ class ForcesPlan:
         """b = -(M v + h f) on the device (Cloth::solve, Cloth.cpp:345); device pointers, asynchronous on ctx.stream."""
         capi.check(capi.lib().eolc_forces_rhs_dev(self._h, Mv_ptr, f_ptr, v_ptr, float(h), b_ptr))
 
-    def solve_cg_dev(self, Kv_ptr, b_ptr, v_ptr, tol=2.220446049250313e-16, max_iter=None):
+    def integrate_dev(self, v_ptr, h, x_ptr):
+        """x += h v on the device (Cloth::step, Cloth.cpp:394-400)."""
+        capi.check(capi.lib().eolc_forces_integrate_dev(self._h, v_ptr, float(h), x_ptr))
+
+    def solve_cg_dev(self, Kv_ptr, b_ptr, v_ptr, tol=2.220446049250313e-16, max_iter=None, fixed_ptr=None):
         """v = ConjugateGradient(MDK).solve(-b) on the device (GeneralizedSolver.cpp:120-126, Eigen defaults: diagonal
-        preconditioner, x0 = 0, tol = epsilon, at most 2 dof iterations).  Returns (iterations issued, relative residual)."""
+        preconditioner, x0 = 0, tol = epsilon, at most 2 dof iterations).  fixed_ptr: optional device pointer to dof bytes, non-zero =
+        the dof keeps velocity 0.  Returns (iterations issued, relative residual)."""
         it, res = ctypes.c_int32(0), ctypes.c_double(0.0)
-        capi.check(capi.lib().eolc_solve_cg_dev(self._h, Kv_ptr, b_ptr, v_ptr, float(tol), int(2 * self.dof if max_iter is None else max_iter),
+        capi.check(capi.lib().eolc_solve_cg_dev(self._h, Kv_ptr, b_ptr, fixed_ptr, v_ptr, float(tol), int(2 * self.dof if max_iter is None else max_iter),
                                                 ctypes.byref(it), ctypes.byref(res)))
         return it.value, res.value
 

@@ -114,10 +114,14 @@ int eolc_forces_rhs_dev(eolc_forces_plan *plan, const double *M_vals_dev, const 
 /* GeneralizedSolver::velocitySolve, collision-free branch without fixed points (src/GeneralizedSolver.cpp:120-126):
  * ConjugateGradient<SparseMatrix<double>, Lower|Upper> cg; cg.compute(MDK); v = cg.solve(-b) — Eigen's CG with its default
  * diagonal preconditioner, started from 0, stopped at ||MDK v + b|| <= tol ||b|| (Eigen's default tol is DBL_EPSILON, its default
- * iteration cap 2 dof).  v_dev receives the solution; iters_out (may be NULL) the iterations issued (a multiple of the host's
- * check interval), rel_resid_out (may be NULL) the final relative residual.  Synchronises the stream. */
-int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const double *b_dev, double *v_dev, double tol,
-                      int32_t max_iter, int32_t *iters_out, double *rel_resid_out);
+ * iteration cap 2 dof).  fixed_dev (dof bytes, may be NULL): dofs with a non-zero flag keep velocity 0 and drop out of the system
+ * (fixed points with zero prescribed velocity, the `fixedPoints` case the reference hands to a KKT / QP solve); the residual is
+ * then that of the free dofs.  v_dev receives the solution; iters_out (may be NULL) the iterations issued (a multiple of the
+ * host's check interval), rel_resid_out (may be NULL) the final relative residual.  Synchronises the stream. */
+int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const double *b_dev, const unsigned char *fixed_dev,
+                      double *v_dev, double tol, int32_t max_iter, int32_t *iters_out, double *rel_resid_out);
+/* Position update of Cloth::step (src/Cloth.cpp:394-400): x += h v for the 3N Lagrangian dofs.  Asynchronous on the stream. */
+int eolc_forces_integrate_dev(eolc_forces_plan *plan, const double *v_dev, double h, double *x_dev);
 /* number of kernels one fill launches (for bench accounting) */
 int eolc_forces_launches_per_fill(const eolc_forces_plan *plan);
 

@@ -240,14 +240,22 @@ def cloth_rhs(M, f, v, h):
     return -(_csc(M, f.size) @ v + h * f)
 
 
-def eigen_cg(A, b, tol=np.finfo(float).eps, max_iter=None):
+def eigen_cg(A, b, tol=np.finfo(float).eps, max_iter=None, fixed=None):
     """v = ConjugateGradient<SparseMatrix<double>, Lower|Upper>(A).solve(-b): /root/reference/src/GeneralizedSolver.cpp:122-125.
     Restates conjugate_gradient() of Eigen 3.3 (Eigen/src/IterativeLinearSolvers/ConjugateGradient.h — EXTERNAL dependency of the
     reference, not vendored under /root/reference; README.md:14 names Eigen 3.3, CMakeLists.txt:26 shows 3.3.4) with the default
     DiagonalPreconditioner (1/a_ii, 1 where a_ii == 0), x0 = 0, threshold tol^2 |rhs|^2, default cap 2 n iterations.
     Parity unpinned by the reference (the branch is dead code there); pinned here against a sparse direct solve (tests/test_oracle.py).
+    fixed (bool per dof, optional): those dofs keep v = 0 and drop out of the system (the solve runs on the free-free block).
     Returns (v, iterations, relative residual)."""
     A = _csc(A, b.size) if isinstance(A, tuple) else A
+    if fixed is not None and np.any(fixed):
+        free = np.flatnonzero(~np.asarray(fixed, dtype=bool))
+        sub = A.tocsr()[free][:, free].tocsc()
+        xs, it, res = eigen_cg(sub, np.asarray(b, dtype=np.float64)[free], tol, max_iter)
+        x = np.zeros(b.size)
+        x[free] = xs
+        return x, it, res
     rhs = -np.asarray(b, dtype=np.float64)
     n = rhs.size
     max_iter = 2 * n if max_iter is None else max_iter

@@ -74,3 +74,46 @@ def test_cg_zero_rhs_and_iteration_cap(ctx):
     assert it == 16 and res > 0.0
     with pytest.raises(E.EolcError):
         plan.solve_cg_dev(t["K"].data_ptr(), t["b"].data_ptr(), t["sol"].data_ptr(), tol=0.0)
+
+
+def test_drape_steps_with_fixed_corners(ctx, oracle):
+    """BASELINE configs[0]: simulationSettings.json's square cloth (Cloth::build mesh, corners 3 and 4 fixed, solver 'none', no remeshing,
+    no EOL), a few collision-free steps entirely on the device — fill -> b = -(M v + h f) -> CG on the free dofs -> x += h v
+    (Cloth.cpp:359-400) — against the same loop on the oracle.  The state after 5 steps agrees to 1e-9 of the cloth size."""
+    import torch
+    res = 5                                                  # simulationSettings.json uses 3; 5 gives interior bending stencils too
+    X, fn = E.meshgen.build4(res)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    N = X.shape[0]
+    x = np.c_[X, np.zeros(N)]
+    x[:, 2] += 1e-3 * np.sin(3.0 * X[:, 0]) * np.cos(2.0 * X[:, 1])      # not perfectly flat: exercises bending
+    # Cloth::build: grid node (i, j) -> i * res + j; corner3 = (0, 1) -> j = res - 1, corner4 = (1, 1) -> last grid node
+    fixed_nodes = [res - 1, res * res - 1]
+    fixed = np.zeros(3 * N, dtype=np.uint8)
+    for a in fixed_nodes:
+        fixed[3 * a:3 * a + 3] = 1
+    plan = E.ForcesPlan(ctx, N, fn, es, X_hint=X)
+    dev = torch.device("cuda", ctx.device)
+    xd = torch.from_numpy(x.copy()).to(dev); Xd = torch.from_numpy(X.copy()).to(dev)
+    f = torch.empty(3 * N, dtype=torch.float64, device=dev); M = torch.empty(plan.nnz[0], dtype=torch.float64, device=dev)
+    K = torch.empty(plan.nnz[1], dtype=torch.float64, device=dev)
+    v = torch.zeros(3 * N, dtype=torch.float64, device=dev); b = torch.empty_like(v); vn = torch.empty_like(v)
+    fx = torch.from_numpy(fixed).to(dev)
+    torch.cuda.synchronize()
+    x_ref, v_ref = x.copy(), np.zeros(3 * N)
+    for step in range(5):
+        plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, f.data_ptr(), M.data_ptr(), K.data_ptr())
+        plan.rhs_dev(M.data_ptr(), f.data_ptr(), v.data_ptr(), H, b.data_ptr())
+        it, rr = plan.solve_cg_dev(K.data_ptr(), b.data_ptr(), vn.data_ptr(), tol=1e-13, fixed_ptr=fx.data_ptr())
+        assert rr < 1e-13
+        plan.integrate_dev(vn.data_ptr(), H, xd.data_ptr())
+        v, vn = vn, v
+        ref = oracle.forces_fill(fn, es, x_ref, X, tuple(MAT), GRAV, H)
+        b_ref = oracle.cloth_rhs(ref["M"], ref["f"], v_ref, H)
+        v_ref, _, _ = oracle.eigen_cg(ref["MDK"], b_ref, tol=1e-13, fixed=fixed.astype(bool))
+        x_ref = x_ref + H * v_ref.reshape(-1, 3)
+    torch.cuda.synchronize()
+    got = xd.cpu().numpy()
+    assert np.abs(got - x_ref).max() <= 1e-9
+    assert np.all(got[fixed_nodes] == x[fixed_nodes])        # the fixed corners did not move
+    assert got[:, 2].min() < x[:, 2].min() - 1e-5             # the free part falls
