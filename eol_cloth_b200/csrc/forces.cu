@@ -890,7 +890,7 @@ int eolc_forces_rhs_dev(eolc_forces_plan *plan, const double *M_vals_dev, const 
     EOLC_CUDA(cudaSetDevice(plan->ctx->device));
     int rc = ensure_block_structure(plan);
     if (rc) return rc;
-    const int grid = std::min((plan->N + solve::WARPS - 1) / solve::WARPS, 16 * plan->ctx->sm_count);
+    const int grid = std::min((plan->N + 2 * solve::WARPS - 1) / (2 * solve::WARPS), 16 * plan->ctx->sm_count);
     solve::k_rhs<<<grid, solve::THREADS, 0, plan->ctx->stream>>>(plan->N, plan->d_blkM.p, plan->d_nbrM.p, M_vals_dev, f_dev, v_dev, h, b_dev);
     EOLC_CUDA(cudaGetLastError());
     return EOLC_OK;
@@ -923,7 +923,7 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
     cudaStream_t st = P->ctx->stream;
     const size_t n = (size_t)P->dof;
     const int gridv = (int)std::min<size_t>((n + solve::THREADS - 1) / solve::THREADS, (size_t)8 * P->ctx->sm_count);
-    const int gridn = std::min((P->N + solve::WARPS - 1) / solve::WARPS, 16 * P->ctx->sm_count);
+    const int gridn = std::min((P->N + 2 * solve::WARPS - 1) / (2 * solve::WARPS), 16 * P->ctx->sm_count);
     const size_t nparts = (size_t)2 * std::max(gridv, gridn);
     EOLC_CUDA(P->d_cg.ensure(4 * n + nparts + 8));
     EOLC_CUDA(P->p_sc.ensure(8));

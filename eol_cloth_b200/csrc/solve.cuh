@@ -24,19 +24,30 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// rows of node a times x: y[0..2] valid in every lane
-__device__ __forceinline__ void node_rows_times(int lane, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
+// Rows of a node times x, a HALF warp per node (a structured cloth node has 13 column blocks in MDK, 7 in M): lane hl of the half
+// takes column blocks hl, hl + 16, ... — one index load, the block's three x values, its 3 x 3 values (three runs of 3 consecutive
+// doubles, neighbouring lanes on neighbouring runs) and 9 FMAs — then a fixed 16-lane tree.  y[0..2] valid in every lane of the half.
+__device__ __forceinline__ void node_rows_times(int hl, bool active, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
                                                 const double *__restrict__ vals, const double *__restrict__ x, int a, double y[3]) {
-    const int b0 = blkptr[a], n3 = 3 * (blkptr[a + 1] - b0);
-    const double *row = vals + 9 * (size_t)b0;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    // the node's three rows are one contiguous run of 3 n3 values: walk it flat (full lanes), route each product to its row's sum
-    for (int l = lane; l < 3 * n3; l += 32) {
-        const int j = l < n3 ? 0 : (l < 2 * n3 ? 1 : 2), c = l - j * n3, p = c / 3;
-        const double t = row[l] * x[3 * (size_t)nbr[b0 + p] + (c - 3 * p)];
-        if (j == 0) s0 += t; else if (j == 1) s1 += t; else s2 += t;
+    if (active) {
+        const int b0 = blkptr[a], deg = blkptr[a + 1] - b0;
+        const unsigned n3 = 3u * (unsigned)deg;
+        const double *row = vals + 9 * (size_t)b0;
+        for (int p = hl; p < deg; p += 16) {
+            const double *xp = x + 3 * (size_t)nbr[b0 + p];
+            const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
+            const double *r = row + 3u * (unsigned)p;
+            s0 += r[0] * x0 + r[1] * x1 + r[2] * x2;
+            s1 += r[n3] * x0 + r[n3 + 1] * x1 + r[n3 + 2] * x2;
+            s2 += r[2 * n3] * x0 + r[2 * n3 + 1] * x1 + r[2 * n3 + 2] * x2;
+        }
     }
-    y[0] = warp_sum(s0); y[1] = warp_sum(s1); y[2] = warp_sum(s2);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    y[0] = s0; y[1] = s1; y[2] = s2;
 }
 
 // fixed-order block reduction of one value per warp; result valid in thread 0
@@ -54,11 +65,12 @@ __device__ __forceinline__ double block_sum(double warp_value, double *sh) {
 __global__ void __launch_bounds__(THREADS) k_rhs(int N, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
                                                  const double *__restrict__ Mv, const double *__restrict__ f, const double *__restrict__ v,
                                                  double h, double *__restrict__ b) {
-    const int lane = threadIdx.x & 31;
-    for (int a = blockIdx.x * WARPS + (threadIdx.x >> 5); a < N; a += gridDim.x * WARPS) {
+    const int hl = threadIdx.x & 15;
+    for (int a0 = 2 * (blockIdx.x * WARPS + (threadIdx.x >> 5)); a0 < N; a0 += 2 * gridDim.x * WARPS) {
+        const int a = a0 + ((threadIdx.x >> 4) & 1);
         double y[3];
-        node_rows_times(lane, blkptr, nbr, Mv, v, a, y);
-        if (lane < 3) b[3 * (size_t)a + lane] = -((lane == 0 ? y[0] : lane == 1 ? y[1] : y[2]) + h * f[3 * (size_t)a + lane]);
+        node_rows_times(hl, a < N, blkptr, nbr, Mv, v, a, y);
+        if (hl < 3 && a < N) b[3 * (size_t)a + hl] = -((hl == 0 ? y[0] : hl == 1 ? y[1] : y[2]) + h * f[3 * (size_t)a + hl]);
     }
 }
 
@@ -112,15 +124,16 @@ __global__ void __launch_bounds__(THREADS) k_cg_ap(int N, const int32_t *__restr
                                                    double *__restrict__ Ap, double *__restrict__ part, const double *__restrict__ sc) {
     __shared__ double sh[WARPS];
     if (sc[6] != 0.0) return;                                  // converged: the remaining launches of the batch are no-ops
-    const int lane = threadIdx.x & 31;
+    const int hl = threadIdx.x & 15;
     double acc = 0.0;
-    for (int a = blockIdx.x * WARPS + (threadIdx.x >> 5); a < N; a += gridDim.x * WARPS) {
+    for (int a0 = 2 * (blockIdx.x * WARPS + (threadIdx.x >> 5)); a0 < N; a0 += 2 * gridDim.x * WARPS) {
+        const int a = a0 + ((threadIdx.x >> 4) & 1);
         double y[3];
-        node_rows_times(lane, blkptr, nbr, Kv, p, a, y);
-        if (lane < 3) {
-            const double yi = dinv[3 * (size_t)a + lane] != 0.0 ? (lane == 0 ? y[0] : lane == 1 ? y[1] : y[2]) : 0.0;
-            Ap[3 * (size_t)a + lane] = yi;
-            acc += p[3 * (size_t)a + lane] * yi;
+        node_rows_times(hl, a < N, blkptr, nbr, Kv, p, a, y);
+        if (hl < 3 && a < N) {
+            const double yi = dinv[3 * (size_t)a + hl] != 0.0 ? (hl == 0 ? y[0] : hl == 1 ? y[1] : y[2]) : 0.0;
+            Ap[3 * (size_t)a + hl] = yi;
+            acc += p[3 * (size_t)a + hl] * yi;
         }
     }
     const double t = block_sum(warp_sum(acc), sh);
