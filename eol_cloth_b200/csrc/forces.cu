@@ -266,7 +266,11 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
 #ifdef EOLC_TILE_CLOCKS
             if (__syncthreads_or(0) == 12345) clk_acc[6] += 1000000;   // the instrumented build's blocking barrier between phases 2 and 3
 #endif
+#if defined(EOLC_TILE_CLOCKS) || defined(EOLC_B2_FULL)
             EOLC_SYNC();                 // [B2] staged rows complete
+#else
+            asm volatile("bar.sync 2, %0;" ::"n"(tiles::CTA_THREADS) : "memory");   // [B2] every compute thread has arrived: staged rows complete
+#endif
             EOLC_CLK(4)
 #ifndef EOLC_DEBUG_NO_COPYOUT
             if (role >= 2) {
@@ -308,7 +312,13 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
             tiles::phase3((int)tid, (int)NC, V);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk-copy engine
             EOLC_CLK(3)
-            EOLC_SYNC();                 // [B2] the scratch may be overwritten by the next phase 1
+#if defined(EOLC_TILE_CLOCKS) || defined(EOLC_B2_FULL)
+            EOLC_SYNC();                 // [B2]
+#else
+            // [B2] arrive only: the compute warps go straight to phase 1 of the next tile (the scratch is free since the named barrier
+            // above, the next tile's inputs landed before [B1]); the service warps wait here for the staged rows
+            asm volatile("bar.arrive 2, %0;" ::"n"(tiles::CTA_THREADS) : "memory");
+#endif
             EOLC_CLK(4)
 #ifdef EOLC_TILE_CLOCKS
             clk_acc[6] += 1;
