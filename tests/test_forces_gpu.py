@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import eol_cloth_b200 as E
-from util import assert_close_tol, block_row_scale
+from util import assert_close_tol, block_row_scale, fan_mesh, strip_mesh
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -85,6 +85,15 @@ def test_shuffled_node_order_and_isolated_node(ctx, oracle):
     ref = oracle.forces_fill(fnn, es, mesh["x"], Xn, tuple(MAT), GRAV, H)
     _check(forces, ref, N, "shuffled")
     assert np.all(forces.f[3 * perm[-1]:3 * perm[-1] + 3] == 0)
+
+
+@pytest.mark.parametrize("mesh", [fan_mesh(6), fan_mesh(40), fan_mesh(100), strip_mesh(50)], ids=["fan6", "fan40", "fan100", "strip50"])
+def test_high_valence_and_strips(ctx, oracle, mesh):
+    """Rows far longer than a structured sheet's 13 blocks (phase 3 beyond its 16-block tree, many contributions per record, tiles cut
+    by the capacity limits) and meshes without interior nodes."""
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    ref = oracle.forces_fill(mesh["face_nodes"], mesh["edge_stencil"], mesh["x"], mesh["X"], tuple(MAT), GRAV, H)
+    _check(forces, ref, mesh["x"].shape[0], "valence")
 
 
 def test_empty_and_single_face(ctx, oracle):

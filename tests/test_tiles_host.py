@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import eol_cloth_b200 as E
-from util import assert_close_tol, block_row_scale
+from util import assert_close_tol, block_row_scale, fan_mesh, strip_mesh
 
 MAT = E.Material.DEFAULT
 GRAV = (0.0, 0.0, -9.8)
@@ -134,6 +134,13 @@ def test_tiles_host_shuffled_isolated_material(oracle, hostmath):
     mat = E.Material(0.2, 1000.0, 0.3, 1e-3, 0.0, 0.7)
     f, _, _ = _check(T, fnn, es, x * 1.3, Xn, oracle, "shuffled", mat, (0.1, -0.2, -9.8), 1e-2)
     assert np.all(f[3 * perm[-1]:3 * perm[-1] + 3] == 0)
+    T.close()
+
+
+@pytest.mark.parametrize("mesh", [fan_mesh(6), fan_mesh(40), fan_mesh(100), strip_mesh(50)], ids=["fan6", "fan40", "fan100", "strip50"])
+def test_tiles_host_high_valence_and_strips(oracle, hostmath, mesh):
+    T = HostTiles(hostmath, mesh["x"].shape[0], mesh["face_nodes"], mesh["edge_stencil"], mesh["X"], True)
+    _check(T, mesh["face_nodes"], mesh["edge_stencil"], mesh["x"], mesh["X"], oracle, "valence")
     T.close()
 
 

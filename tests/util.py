@@ -42,3 +42,27 @@ def bit_identical_fraction(got, ref):
     for f in REAL_FIELDS:
         n += np.count_nonzero(got[f].view(np.uint64) == ref[f].view(np.uint64)); tot += got[f].size
     return n / max(tot, 1)
+
+
+def fan_mesh(k, seed=0):
+    """One centre node joined to a ring of k nodes: valence-k node (rows with k + 1 blocks, k faces and k bending stencils on one node)."""
+    import eol_cloth_b200 as E
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+    X = np.r_[[[0.0, 0.0]], np.c_[np.cos(ang), np.sin(ang)]]
+    fn = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], np.int32)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    x = np.c_[X, 0.05 * np.sin(3 * X[:, 0])] + 1e-3 * np.random.default_rng(seed + k).standard_normal((X.shape[0], 3))
+    return dict(x=x, X=X, face_nodes=fn, edge_stencil=es)
+
+
+def strip_mesh(m):
+    """A 2 x m strip: every node on the boundary, bending stencils only across the rungs and diagonals."""
+    import eol_cloth_b200 as E
+    X = np.array([[i / (m - 1), j * 0.02] for i in range(m) for j in range(2)])
+    fn = []
+    for i in range(m - 1):
+        a = 2 * i
+        fn += [[a, a + 2, a + 1], [a + 1, a + 2, a + 3]]
+    fn = np.array(fn, np.int32)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    return dict(x=np.c_[X, 0.05 * np.sin(3 * X[:, 0])], X=X, face_nodes=fn, edge_stencil=es)
