@@ -7,5 +7,5 @@ There is NO CPU fallback: importing works without a GPU, every compute call rais
 """
 from .capi import EolcError, Context, device_count, lib_path  # noqa: F401
 from .forces import Forces, ForcesPlan, Material  # noqa: F401
-from .collisions import CD, CD2, CollisionPlan, Obstacles, CONTACT_DTYPE  # noqa: F401
+from .collisions import CD, CD2, CollisionPlan, Obstacles, CONTACT_DTYPE, contact_rows  # noqa: F401
 from . import meshgen  # noqa: F401

@@ -77,6 +77,17 @@ class CollisionPlan:
             capi.check(rc)
             return (out[:n], off) if x_is_device_ptr else out[:n]
 
+    def contact_rows(self, node_eol=None):
+        """Inequality rows of the contacts of the LAST run, built on the device (Constraints.cpp:424-468): (row_nnz, cols, vals) with
+        9 slots per row in the reference's triplet order."""
+        cap = max(int(capi.lib().eolc_cd_last_count(self._h)), 1)
+        nnz, cols, vals = np.zeros(cap, np.int32), np.full(9 * cap, -1, np.int32), np.zeros(9 * cap)
+        n = ctypes.c_int32(0)
+        eol = None if node_eol is None else np.ascontiguousarray(node_eol, dtype=np.uint8)
+        capi.check(capi.lib().eolc_cd_contact_rows(self._h, None if eol is None else eol.ctypes.data_as(capi.c_vp), cap, ctypes.byref(n),
+                                                   capi.iptr(nnz), capi.iptr(cols), capi.dptr(vals)))
+        return nnz[:n.value], cols[:9 * n.value].reshape(-1, 9), vals[:9 * n.value].reshape(-1, 9)
+
     def stats(self):
         pt, ln = ctypes.c_int64(), ctypes.c_int32()
         capi.check(capi.lib().eolc_cd_last_stats(self._h, ctypes.byref(pt), ctypes.byref(ln)))
@@ -118,3 +129,15 @@ def CD(ctx, mesh, obs, cls):
 def CD2(ctx, mesh, obs, cls):
     """void CD2(...) — Collisions.cpp:55-78."""
     cls.extend(_plan_for(ctx, mesh, obs).run(mesh["x"], obs, point_eol_flag=0, remap=0))
+
+
+def contact_rows(contacts, node_eol=None):
+    """Constraints::fill, contact part (Constraints.cpp:424-468) for a host contact list: (row_nnz, cols, vals), 9 slots per row."""
+    c = np.ascontiguousarray(contacts, dtype=CONTACT_DTYPE)
+    cap = max(len(c), 1)
+    nnz, cols, vals = np.zeros(cap, np.int32), np.full(9 * cap, -1, np.int32), np.zeros(9 * cap)
+    n = ctypes.c_int32(0)
+    eol = None if node_eol is None else np.ascontiguousarray(node_eol, dtype=np.uint8)
+    capi.check(capi.lib().eolc_constraints_contact_rows(c.ctypes.data_as(capi.c_vp), len(c), None if eol is None else eol.ctypes.data_as(capi.c_vp),
+                                                        ctypes.byref(n), capi.iptr(nnz), capi.iptr(cols), capi.dptr(vals)))
+    return nnz[:n.value], cols[:9 * n.value].reshape(-1, 9), vals[:9 * n.value].reshape(-1, 9)

@@ -654,6 +654,12 @@ struct eolc_cd_plan {
     PinnedBuf<double> p_x;
     int64_t last_pair_tests = 0;
     int32_t last_launches = 0;
+    int32_t last_total = 0;             // contacts of the last run, still in d_out
+    DevBuf<int32_t> d_rows_i;           // contact rows (eolc_cd_contact_rows): row_nnz [n] + cols [9 n]
+    DevBuf<double> d_rows_v;            // vals [9 n]
+    DevBuf<unsigned char> d_eol;
+    PinnedBuf<int32_t> p_rows_i;
+    PinnedBuf<double> p_rows_v;
 };
 
 extern "C" {
@@ -770,7 +776,7 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
     const size_t total_items = scene_items * S;
     const size_t nblocks = total_items / 256;
     for (int s = 0; s <= S; ++s) scene_offset[s] = 0;
-    if (total_items == 0 || N == 0) { P->last_pair_tests = 0; P->last_launches = 0; return EOLC_OK; }
+    if (total_items == 0 || N == 0) { P->last_pair_tests = 0; P->last_launches = 0; P->last_total = 0; return EOLC_OK; }
     EOLC_REQUIRE(nblocks < ((size_t)1 << 31), "batch too large");
 
     // ---- constants to the device
@@ -853,6 +859,7 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
     }
     EOLC_CUDA(cudaGetLastError());
     P->last_launches = launches;
+    P->last_total = total;
     P->last_pair_tests = (int64_t)S * ((doPE ? (int64_t)N * nP : 0) + (int64_t)nP * F + (int64_t)nB * ((int64_t)N * 24 + 8 * (int64_t)F + (int64_t)E * 12));
 
     // ---- step (D) (:1022-1052): per box corner keep only the closest count1 == 1 record.  Only section Bc emits
@@ -901,6 +908,93 @@ int eolc_cd_run(eolc_cd_plan *plan, const double *x, int32_t n_points, const dou
     }
     return eolc_cd_run_dev(plan, plan->d_x.p, n_points, pxyz, pnorms, n_boxes, box_whd, box_E, point_eol_flag,
                            remap_box_indices, out, capacity, n_out);
+}
+
+
+// ---- Constraints::fill, contact part (src/Constraints.cpp:424-468): one shared routine for the host list and the device kernel
+}  // extern "C" (reopened below)
+namespace {
+__host__ __device__ inline int contact_row(const eolc_contact &c, const unsigned char *node_eol, int32_t *cols, double *vals) {
+    int nv;
+    if (c.count1 == 3 && c.count2 == 1) nv = 1;
+    else if (c.count1 == 2 && c.count2 == 2) nv = 2;
+    else if (c.count1 == 1 && c.count2 == 3) nv = 3;
+    else nv = 0;
+    if (node_eol) for (int j = 0; j < nv; ++j) if (node_eol[c.verts2[j]]) nv = 0;   // `continue` in the reference: no row
+    int n = 0;
+    for (int j = 0; j < nv; ++j)
+        for (int k = 0; k < 3; ++k) {
+            cols[n] = c.verts2[j] * 3 + k;
+            // (3,1): -nor1(k)   (Constraints.cpp:427-429);   (2,2), (1,3): -nor2(k) * weights2(j)   (:442-444, :458-460)
+            vals[n] = nv == 1 ? -c.nor1[k] : -c.nor2[k] * c.weights2[j];
+            ++n;
+        }
+    for (int q = n; q < 9; ++q) { cols[q] = -1; vals[q] = 0.0; }
+    return n;
+}
+__global__ void k_contact_rows(int n, const eolc_contact *__restrict__ c, const unsigned char *__restrict__ node_eol, int32_t *__restrict__ row_nnz,
+                               int32_t *__restrict__ cols, double *__restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t cc[9]; double vv[9];
+    row_nnz[i] = contact_row(c[i], node_eol, cc, vv);
+    for (int q = 0; q < 9; ++q) { cols[9 * (size_t)i + q] = cc[q]; vals[9 * (size_t)i + q] = vv[q]; }
+}
+}  // namespace
+extern "C" {
+
+int eolc_cd_last_count(const eolc_cd_plan *plan) { return plan ? plan->last_total : 0; }
+
+int eolc_constraints_contact_rows(const eolc_contact *contacts, int32_t n, const uint8_t *node_eol, int32_t *n_rows, int32_t *row_nnz,
+                                  int32_t *cols, double *vals) {
+    EOLC_REQUIRE(n_rows && n >= 0, "bad arguments");
+    EOLC_REQUIRE(n == 0 || (contacts && row_nnz && cols && vals), "NULL argument");
+    int32_t r = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        const int m = contact_row(contacts[i], node_eol, cols + 9 * (size_t)r, vals + 9 * (size_t)r);
+        if (m == 0) continue;                  // skipped contact: ineqsize does not advance
+        row_nnz[r++] = m;
+    }
+    *n_rows = r;
+    return EOLC_OK;
+}
+
+int eolc_cd_contact_rows(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t capacity_rows, int32_t *n_rows, int32_t *row_nnz, int32_t *cols,
+                         double *vals) {
+    EOLC_REQUIRE(plan && n_rows, "NULL argument");
+    eolc_cd_plan *P = plan;
+    const int n = P->last_total;
+    *n_rows = 0;
+    if (n == 0) return EOLC_OK;
+    EOLC_REQUIRE(row_nnz && cols && vals, "NULL argument");
+    if (n > capacity_rows) { *n_rows = n; set_error("row buffers too small: need %d rows, capacity %d", n, capacity_rows); return EOLC_ERR_CAPACITY; }
+    EOLC_CUDA(cudaSetDevice(P->ctx->device));
+    cudaStream_t st = P->ctx->stream;
+    EOLC_CUDA(P->d_rows_i.ensure(10 * (size_t)n)); EOLC_CUDA(P->d_rows_v.ensure(9 * (size_t)n));
+    EOLC_CUDA(P->p_rows_i.ensure(10 * (size_t)n)); EOLC_CUDA(P->p_rows_v.ensure(9 * (size_t)n));
+    const unsigned char *eol_dev = nullptr;
+    if (node_eol) {
+        EOLC_CUDA(P->d_eol.ensure((size_t)P->N));
+        EOLC_CUDA(cudaMemcpyAsync(P->d_eol.p, node_eol, (size_t)P->N, cudaMemcpyHostToDevice, st));
+        eol_dev = P->d_eol.p;
+    }
+    k_contact_rows<<<(n + 255) / 256, 256, 0, st>>>(n, P->d_out.p, eol_dev, P->d_rows_i.p, P->d_rows_i.p + n, P->d_rows_v.p);
+    EOLC_CUDA(cudaGetLastError());
+    EOLC_CUDA(cudaMemcpyAsync(P->p_rows_i.p, P->d_rows_i.p, 10 * (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaMemcpyAsync(P->p_rows_v.p, P->d_rows_v.p, 9 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));
+    // compaction of skipped contacts (EoL nodes) on the host: the common case has none and is two memcpys
+    int32_t r = 0;
+    const int32_t *hn = P->p_rows_i.p, *hc = P->p_rows_i.p + n;
+    for (int i = 0; i < n; ++i) {
+        if (hn[i] == 0) continue;
+        row_nnz[r] = hn[i];
+        memcpy(cols + 9 * (size_t)r, hc + 9 * (size_t)i, 9 * sizeof(int32_t));
+        memcpy(vals + 9 * (size_t)r, P->p_rows_v.p + 9 * (size_t)i, 9 * sizeof(double));
+        ++r;
+    }
+    *n_rows = r;
+    return EOLC_OK;
 }
 
 }  // extern "C"

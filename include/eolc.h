@@ -152,6 +152,22 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t n_scenes, const double *
                             const double *pxyz, const double *pnorms, int32_t n_boxes, const double *box_whd,
                             const double *box_E, int point_eol_flag, int remap_box_indices, eolc_contact *out,
                             int32_t capacity, int32_t *scene_offset);
+/* ---- consumer of the contact list ------------------------------------------ */
+/* Constraints::fill, contact part (src/Constraints.cpp:424-468): one inequality row per CD2 contact, in list order,
+ *   (3,1) cloth vertex / box face : 3 entries  -nor1[k]               at column 3 verts2[0] + k
+ *   (2,2) edge / edge             : 6 entries  -nor2[k] weights2[j]   at column 3 verts2[j] + k, j = 0, 1
+ *   (1,3) box corner / cloth tri  : 9 entries  -nor2[k] weights2[j]   at column 3 verts2[j] + k, j = 0, 1, 2
+ * i.e. exactly the triplets Aineq_ receives (row = running ineqsize, the reference's push order); bineq stays zero.  A contact
+ * touching an EoL node is skipped and takes no row (node_eol: N flags, may be NULL = no EoL node).  Output in a fixed-width
+ * layout: row i has row_nnz[i] entries cols[9 i ..], vals[9 i ..] (unused entries: col -1, val 0); arrays sized for n rows.
+ * eolc_constraints_contact_rows works on a host contact list; eolc_cd_contact_rows on the contacts of the plan's LAST run, which are
+ * still on the device (the rows are 112 B per contact instead of the 264 B record: for a host that only builds Aineq). */
+int eolc_constraints_contact_rows(const eolc_contact *contacts, int32_t n, const uint8_t *node_eol, int32_t *n_rows,
+                                  int32_t *row_nnz, int32_t *cols, double *vals);
+int eolc_cd_contact_rows(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t capacity_rows, int32_t *n_rows, int32_t *row_nnz,
+                         int32_t *cols, double *vals);
+/* number of contacts of the plan's last run (all scenes) */
+int eolc_cd_last_count(const eolc_cd_plan *plan);
 /* counters of the last run: candidate pair tests executed on the device (A: N*24, B: 8*F, C: E*12 after culls) */
 int eolc_cd_last_stats(const eolc_cd_plan *plan, int64_t *pair_tests, int32_t *launches);
 

@@ -287,3 +287,26 @@ def eigen_cg(A, b, tol=np.finfo(float).eps, max_iter=None, fixed=None):
         abs_new = float(residual @ z)
         p = z + (abs_new / abs_old) * p
     return x, it, np.sqrt(r2 / rhs2)
+
+
+def constraints_contact_rows(contacts, node_eol=None):
+    """Contact part of Constraints::fill, /root/reference/src/Constraints.cpp:424-468: the (row, col, value) triplets Aineq_ receives for
+    a CD2 contact list, row = running ineqsize; contacts touching an EoL node are skipped (`continue`, no row).  Returns a list of rows,
+    each a list of (col, value) in push order."""
+    rows = []
+    for c in contacts:
+        c1, c2 = int(c["count1"]), int(c["count2"])
+        v2, w2 = c["verts2"], c["weights2"]
+        if c1 == 3 and c2 == 1:                                              # :425-436
+            if node_eol is not None and node_eol[v2[0]]:
+                continue
+            rows.append([(int(v2[0]) * 3 + k, -c["nor1"][k]) for k in range(3)])
+        elif c1 == 2 and c2 == 2:                                            # :438-452
+            if node_eol is not None and (node_eol[v2[0]] or node_eol[v2[1]]):
+                continue
+            rows.append([(int(v2[j]) * 3 + k, -c["nor2"][k] * w2[j]) for j in range(2) for k in range(3)])
+        elif c1 == 1 and c2 == 3:                                            # :454-468
+            if node_eol is not None and (node_eol[v2[0]] or node_eol[v2[1]] or node_eol[v2[2]]):
+                continue
+            rows.append([(int(v2[j]) * 3 + k, -c["nor2"][k] * w2[j]) for j in range(3) for k in range(3)])
+    return rows

@@ -1,0 +1,58 @@
+"""Contact part of Constraints::fill (Constraints.cpp:424-468): the inequality rows built from a CD2 contact list.
+Integer columns and FP64 values (one negation / one multiply each) are compared bit for bit with the restatement in the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import eol_cloth_b200 as E
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _compare(rows_ref, nnz, cols, vals):
+    assert len(rows_ref) == len(nnz)
+    for r, ref in enumerate(rows_ref):
+        assert nnz[r] == len(ref)
+        assert [int(c) for c in cols[r, :nnz[r]]] == [c for c, _ in ref]
+        assert np.array(vals[r, :nnz[r]]).tobytes() == np.array([v for _, v in ref], dtype=np.float64).tobytes()
+        assert np.all(cols[r, nnz[r]:] == -1) and np.all(vals[r, nnz[r]:] == 0.0)
+
+
+@pytest.mark.parametrize("name", ["cd_build4_n16_corner", "cd_regular2_n24"])
+def test_host_rows_match_oracle_on_golden_contacts(oracle, name):
+    """Host entry point (pure host code of the library: no device needed) on the golden CD2 lists: all three contact kinds."""
+    c = np.load(os.path.join(GOLD, name + ".npz"))["cd2"]
+    c = np.ascontiguousarray(c.view(E.CONTACT_DTYPE) if c.dtype != E.CONTACT_DTYPE else c).reshape(-1)
+    kinds = {(int(a), int(b)) for a, b in zip(c["count1"], c["count2"])}
+    if name.endswith("corner"):
+        assert kinds == {(3, 1), (1, 3), (2, 2)}
+    nnz, cols, vals = E.contact_rows(c)
+    _compare(oracle.constraints_contact_rows(c), nnz, cols, vals)
+    # EoL nodes: contacts touching one take no row and the numbering closes up
+    N = int(max(c["verts2"].max(), 0)) + 1
+    eol = np.zeros(N, np.uint8)
+    eol[c["verts2"][::3, 0]] = 1
+    nnz2, cols2, vals2 = E.contact_rows(c, eol)
+    ref2 = oracle.constraints_contact_rows(c, eol.astype(bool))
+    assert 0 < len(ref2) < len(nnz)
+    _compare(ref2, nnz2, cols2, vals2)
+    assert E.contact_rows(c[:0])[0].size == 0
+
+
+@pytest.mark.gpu
+def test_device_rows_of_last_run(ctx, oracle):
+    from eol_cloth_b200.collisions import make_obstacles
+    X, fn = E.meshgen.regular2(40)
+    c0 = np.array([0.9175, -0.25, -0.549])
+    x = E.meshgen.box_scene_state(X, seed=3, centre=c0)
+    obs = make_obstacles(E.meshgen.BOX_THRESHOLD, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(c0)[None])
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, E.meshgen.BOX_THRESHOLD)
+    contacts = plan.run(x, obs, 0, 0)
+    assert len(contacts) > 50
+    ref = oracle.constraints_contact_rows(contacts)
+    _compare(ref, *plan.contact_rows())
+    _compare(ref, *E.contact_rows(contacts))
+    eol = np.zeros(X.shape[0], np.uint8)
+    eol[contacts["verts2"][::2, 0]] = 1
+    _compare(oracle.constraints_contact_rows(contacts, eol.astype(bool)), *plan.contact_rows(eol))
