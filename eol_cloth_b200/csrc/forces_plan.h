@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -187,13 +188,11 @@ struct Plan {
     std::string error;
 };
 
-struct Builder {
-    int32_t N, F, Ei;
-    const int32_t *fn, *ie;
-    const Pattern &pat;
-    std::vector<int32_t> nfp, nep;     // node -> incident faces / stencils (CSR), ascending element index, elem << 2 | pos
+// node -> incident faces / stencils (CSR), ascending element index, elem << 2 | pos; read-only once built, shared by the workers
+struct NodeCSR {
+    std::vector<int32_t> nfp, nep;
     std::vector<uint32_t> nfl, nel;
-    Builder(int32_t N_, int32_t F_, const int32_t *fn_, int32_t Ei_, const int32_t *ie_, const Pattern &p) : N(N_), F(F_), Ei(Ei_), fn(fn_), ie(ie_), pat(p) {
+    NodeCSR(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie) {
         nfp.assign(N + 1, 0); nep.assign(N + 1, 0);
         for (int64_t i = 0; i < 3 * (int64_t)F; ++i) nfp[fn[i] + 1]++;
         for (int64_t i = 0; i < 4 * (int64_t)Ei; ++i) nep[ie[i] + 1]++;
@@ -202,6 +201,17 @@ struct Builder {
         std::vector<int32_t> pf(nfp.begin(), nfp.end() - 1), pe(nep.begin(), nep.end() - 1);
         for (int32_t i = 0; i < F; ++i) for (int v = 0; v < 3; ++v) nfl[pf[fn[3 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
         for (int32_t i = 0; i < Ei; ++i) for (int v = 0; v < 4; ++v) nel[pe[ie[4 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
+    }
+};
+
+struct Builder {
+    int32_t N, F, Ei;
+    const int32_t *fn, *ie;
+    const Pattern &pat;
+    const std::vector<int32_t> &nfp, &nep;
+    const std::vector<uint32_t> &nfl, &nel;
+    Builder(int32_t N_, int32_t F_, const int32_t *fn_, int32_t Ei_, const int32_t *ie_, const Pattern &p, const NodeCSR &csr)
+        : N(N_), F(F_), Ei(Ei_), fn(fn_), ie(ie_), pat(p), nfp(csr.nfp), nep(csr.nep), nfl(csr.nfl), nel(csr.nel) {
         fstamp.assign(F, -1); estamp.assign(Ei, -1); lstamp.assign(N, -1); local.assign(N, 0);
         fslot.assign(F, 0); eslot.assign(Ei, 0);
     }
@@ -433,7 +443,8 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                   Plan &P) {
     P = Plan();
     if (N == 0) return true;
-    Builder B(N, F, fn, Ei, ie, pat);
+    const NodeCSR csr(N, F, fn, Ei, ie);
+    Builder B(N, F, fn, Ei, ie, pat, csr);
     for (int32_t e = 0; e < Ei; ++e) {
         const int32_t *s = ie + 4 * (size_t)e;
         if (s[0] == s[1] || s[0] == s[2] || s[0] == s[3] || s[1] == s[2] || s[1] == s[3] || s[2] == s[3]) {
@@ -529,296 +540,385 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         leaves.swap(ok);
     }
     P.n_tiles = (int32_t)leaves.size();
-    std::vector<uint32_t> geo_off;     // variable-size blobs first, re-laid with a fixed stride at the end
-    geo_off.reserve(leaves.size() + 1);
-    std::unordered_map<uint64_t, std::vector<uint32_t>> seen;   // hash -> template offsets (16-byte units)
-    std::vector<uint32_t> T;                                   // template under construction
-    std::vector<RecTmp> recs[3];
-    std::vector<std::pair<uint32_t, uint32_t>> unique_tmpl;   // (offset, size of part A) of every stored template, 16-byte units
     struct Run { uint64_t dst; uint32_t kind, src, len; };
-    std::vector<Run> runs;
     struct Grp { int kind, nA, nB, first, count; long cost; int warp; };
-    std::vector<Grp> groups;
-    for (size_t t = 0; t < leaves.size(); ++t) {
-        int32_t *own = idx.data() + leaves[t].first;
-        const int n_own = (int)(leaves[t].second - leaves[t].first);
-        std::sort(own, own + n_own);
-        B.fits(own, n_own, faces, edges);
-        std::sort(faces.begin(), faces.end());
-        std::sort(edges.begin(), edges.end());
-        const int nE = (int)edges.size(), nF = (int)faces.size();
-        const int fbase = ZPAD + nE * EDGE_STRIDE;
-        P.elem_evals += nE + nF;
-        P.max_scratch = std::max<uint32_t>(P.max_scratch, (uint32_t)(fbase + nF * FACE_STRIDE));
-        // local node table: owned nodes first (ascending), then halo nodes by first appearance; element -> slot maps
-        ++B.stamp;
-        std::vector<uint32_t> loc;
-        auto lid = [&](int32_t g) {
-            if (B.lstamp[g] != B.stamp) { B.lstamp[g] = B.stamp; B.local[g] = (int32_t)loc.size(); loc.push_back((uint32_t)g); }
-            return (uint32_t)B.local[g];
-        };
-        for (int o = 0; o < n_own; ++o) lid(own[o]);
-        std::vector<uint32_t> items((size_t)nE + nF, 0u);
-        for (int s = 0; s < nE; ++s) {
-            const int32_t *v = ie + 4 * (size_t)edges[s];
-            items[s] = lid(v[0]) | (lid(v[1]) << 8) | (lid(v[2]) << 16) | (lid(v[3]) << 24);
-            B.eslot[edges[s]] = s;
-        }
-        for (int s = 0; s < nF; ++s) {
-            const int32_t *v = fn + 3 * (size_t)faces[s];
-            items[nE + s] = lid(v[0]) | (lid(v[1]) << 8) | (lid(v[2]) << 16);
-            B.fslot[faces[s]] = s;
-        }
-        P.max_loc = std::max<uint32_t>(P.max_loc, (uint32_t)loc.size());
-        // ---- runs of owned nodes with consecutive ids (adjacent rows in the global arrays) and the staging offsets, which follow
-        //      the parity of the run's destination so that one bulk copy moves the run
-        std::vector<uint32_t> degs((size_t)n_own, 0u), offsKM((size_t)n_own, 0u), offsF((size_t)n_own, 0u);
-        runs.clear();
-        uint32_t stage_end[3] = {0, 0, 0};
-        for (int kind = 0; kind < 3; ++kind) {
-            uint32_t cur = 0;
-            int o = 0;
-            while (o < n_own) {
-                auto len_of = [&](int q) {
-                    return kind == 0 ? 9u * (uint32_t)(pat.blkptrK[own[q] + 1] - pat.blkptrK[own[q]])
-                         : kind == 1 ? 9u * (uint32_t)(pat.blkptrM[own[q] + 1] - pat.blkptrM[own[q]]) : 3u;
-                };
-                const uint64_t dst = kind == 0 ? (uint64_t)(9 * pat.blkptrK[own[o]]) : kind == 1 ? (uint64_t)(9 * pat.blkptrM[own[o]]) : (uint64_t)3 * (uint64_t)own[o];
-                cur = ((cur + 1u) & ~1u) + (uint32_t)(dst & 1u);      // even slot + the destination's parity
-                const uint32_t src = cur;
-                int o1 = o;
-                for (;;) {
-                    if (kind == 0) offsKM[o1] |= cur; else if (kind == 1) offsKM[o1] |= cur << 16; else offsF[o1] = cur;
-                    cur += len_of(o1);
-                    if (o1 + 1 < n_own && own[o1 + 1] == own[o1] + 1) ++o1; else break;
-                }
-                if (cur - src) runs.push_back({dst, (uint32_t)kind, src, cur - src});
-                o = o1 + 1;
+    // One worker builds the tiles [t0, t1) into its own partial plan Q (templates deduplicated within the range, geometry blobs
+    // back to back with offsets in geo_off); the ranges are merged in tile order below, so the result does not depend on the
+    // number of workers.
+    auto build_range = [&](Builder &Bw, size_t t0, size_t t1, Plan &Q, std::vector<uint32_t> &geo_off, std::vector<std::pair<uint32_t, uint32_t>> &unique_tmpl) -> bool {
+        std::vector<int32_t> faces, edges;
+        std::unordered_map<uint64_t, std::vector<uint32_t>> seen;   // hash -> template offsets (16-byte units)
+        std::vector<uint32_t> T;                                   // template under construction
+        std::vector<RecTmp> recs[3];
+        std::vector<Run> runs;
+        std::vector<Grp> groups;
+            for (size_t t = t0; t < t1; ++t) {
+            int32_t *own = idx.data() + leaves[t].first;
+            const int n_own = (int)(leaves[t].second - leaves[t].first);
+            std::sort(own, own + n_own);
+            Bw.fits(own, n_own, faces, edges);
+            std::sort(faces.begin(), faces.end());
+            std::sort(edges.begin(), edges.end());
+            const int nE = (int)edges.size(), nF = (int)faces.size();
+            const int fbase = ZPAD + nE * EDGE_STRIDE;
+            Q.elem_evals += nE + nF;
+            Q.max_scratch = std::max<uint32_t>(Q.max_scratch, (uint32_t)(fbase + nF * FACE_STRIDE));
+            // local node table: owned nodes first (ascending), then halo nodes by first appearance; element -> slot maps
+            ++Bw.stamp;
+            std::vector<uint32_t> loc;
+            auto lid = [&](int32_t g) {
+                if (Bw.lstamp[g] != Bw.stamp) { Bw.lstamp[g] = Bw.stamp; Bw.local[g] = (int32_t)loc.size(); loc.push_back((uint32_t)g); }
+                return (uint32_t)Bw.local[g];
+            };
+            for (int o = 0; o < n_own; ++o) lid(own[o]);
+            std::vector<uint32_t> items((size_t)nE + nF, 0u);
+            for (int s = 0; s < nE; ++s) {
+                const int32_t *v = ie + 4 * (size_t)edges[s];
+                items[s] = lid(v[0]) | (lid(v[1]) << 8) | (lid(v[2]) << 16) | (lid(v[3]) << 24);
+                Bw.eslot[edges[s]] = s;
             }
-            stage_end[kind] = cur;
-        }
-        if (stage_end[0] > 0xffffu || stage_end[1] > 0xffffu) { P.error = "tile " + std::to_string(t) + ": staging overflow"; return false; }
-        P.max_kstage = std::max(P.max_kstage, stage_end[0]); P.max_mstage = std::max(P.max_mstage, stage_end[1]); P.max_fstage = std::max(P.max_fstage, stage_end[2]);
-        // ---- phase-2 records
-        for (auto &r : recs) r.clear();
-        auto owned_index = [&](int32_t g) { return (B.lstamp[g] == B.stamp && B.local[g] < n_own) ? B.local[g] : -1; };
-        for (int o = 0; o < n_own; ++o) {
-            const int32_t a = own[o];
-            const int64_t b0 = pat.blkptrK[a], m0 = pat.blkptrM[a];
-            const int deg = (int)(pat.blkptrK[a + 1] - b0), degM = (int)(pat.blkptrM[a + 1] - m0);
-            if (deg > 255) { P.error = "node " + std::to_string(a) + " has more than 255 neighbours"; return false; }
-            degs[o] = (uint32_t)deg | ((uint32_t)degM << 8);
-            if (deg) degs[o] |= (uint32_t)(find_block(pat.blkptrK, pat.nbrK, a, a) - b0) << 16;
-            if (degM) degs[o] |= (uint32_t)(find_block(pat.blkptrM, pat.nbrM, a, a) - m0) << 24;
-            for (int p = 0; p < std::max(deg, 1); ++p) {
-                const int32_t b = deg ? pat.nbrK[b0 + p] : a;
-                const int ob = b == a ? -1 : owned_index(b);
-                if (ob >= 0 && b < a) continue;      // the pair is assembled by the record of (b, a), which mirrors it into this row
-                RecTmp R, Rm;
-                // faces ascending, then stencils ascending
-                for (int32_t k = B.nfp[a]; k < B.nfp[a + 1]; ++k) {
-                    const int32_t f = B.nfl[k] >> 2;
-                    const int va = B.nfl[k] & 3, sf = B.fslot[f];
-                    const int32_t *v = fn + 3 * (size_t)f;
-                    const int base = fbase + sf * FACE_STRIDE;
-                    if (b == a) { R.A.push_back((uint16_t)(base + face_force_off(va))); Rm.A.push_back((uint16_t)(base + FACE_T8)); continue; }
-                    for (int vj = 0; vj < 3; ++vj)
-                        if (v[vj] == b) {
-                            (va < vj ? R.A : R.B).push_back((uint16_t)(base + face_off_off(std::min(va, vj), std::max(va, vj))));
-                            Rm.A.push_back((uint16_t)(base + FACE_T8));
+            for (int s = 0; s < nF; ++s) {
+                const int32_t *v = fn + 3 * (size_t)faces[s];
+                items[nE + s] = lid(v[0]) | (lid(v[1]) << 8) | (lid(v[2]) << 16);
+                Bw.fslot[faces[s]] = s;
+            }
+            Q.max_loc = std::max<uint32_t>(Q.max_loc, (uint32_t)loc.size());
+            // ---- runs of owned nodes with consecutive ids (adjacent rows in the global arrays) and the staging offsets, which follow
+            //      the parity of the run's destination so that one bulk copy moves the run
+            std::vector<uint32_t> degs((size_t)n_own, 0u), offsKM((size_t)n_own, 0u), offsF((size_t)n_own, 0u);
+            runs.clear();
+            uint32_t stage_end[3] = {0, 0, 0};
+            for (int kind = 0; kind < 3; ++kind) {
+                uint32_t cur = 0;
+                int o = 0;
+                while (o < n_own) {
+                    auto len_of = [&](int q) {
+                        return kind == 0 ? 9u * (uint32_t)(pat.blkptrK[own[q] + 1] - pat.blkptrK[own[q]])
+                             : kind == 1 ? 9u * (uint32_t)(pat.blkptrM[own[q] + 1] - pat.blkptrM[own[q]]) : 3u;
+                    };
+                    const uint64_t dst = kind == 0 ? (uint64_t)(9 * pat.blkptrK[own[o]]) : kind == 1 ? (uint64_t)(9 * pat.blkptrM[own[o]]) : (uint64_t)3 * (uint64_t)own[o];
+                    cur = ((cur + 1u) & ~1u) + (uint32_t)(dst & 1u);      // even slot + the destination's parity
+                    const uint32_t src = cur;
+                    int o1 = o;
+                    for (;;) {
+                        if (kind == 0) offsKM[o1] |= cur; else if (kind == 1) offsKM[o1] |= cur << 16; else offsF[o1] = cur;
+                        cur += len_of(o1);
+                        if (o1 + 1 < n_own && own[o1 + 1] == own[o1] + 1) ++o1; else break;
+                    }
+                    if (cur - src) runs.push_back({dst, (uint32_t)kind, src, cur - src});
+                    o = o1 + 1;
+                }
+                stage_end[kind] = cur;
+            }
+            if (stage_end[0] > 0xffffu || stage_end[1] > 0xffffu) { Q.error = "tile " + std::to_string(t) + ": staging overflow"; return false; }
+            Q.max_kstage = std::max(Q.max_kstage, stage_end[0]); Q.max_mstage = std::max(Q.max_mstage, stage_end[1]); Q.max_fstage = std::max(Q.max_fstage, stage_end[2]);
+            // ---- phase-2 records
+            for (auto &r : recs) r.clear();
+            auto owned_index = [&](int32_t g) { return (Bw.lstamp[g] == Bw.stamp && Bw.local[g] < n_own) ? Bw.local[g] : -1; };
+            for (int o = 0; o < n_own; ++o) {
+                const int32_t a = own[o];
+                const int64_t b0 = pat.blkptrK[a], m0 = pat.blkptrM[a];
+                const int deg = (int)(pat.blkptrK[a + 1] - b0), degM = (int)(pat.blkptrM[a + 1] - m0);
+                if (deg > 255) { Q.error = "node " + std::to_string(a) + " has more than 255 neighbours"; return false; }
+                degs[o] = (uint32_t)deg | ((uint32_t)degM << 8);
+                if (deg) degs[o] |= (uint32_t)(find_block(pat.blkptrK, pat.nbrK, a, a) - b0) << 16;
+                if (degM) degs[o] |= (uint32_t)(find_block(pat.blkptrM, pat.nbrM, a, a) - m0) << 24;
+                for (int p = 0; p < std::max(deg, 1); ++p) {
+                    const int32_t b = deg ? pat.nbrK[b0 + p] : a;
+                    const int ob = b == a ? -1 : owned_index(b);
+                    if (ob >= 0 && b < a) continue;      // the pair is assembled by the record of (b, a), which mirrors it into this row
+                    RecTmp R, Rm;
+                    // faces ascending, then stencils ascending
+                    for (int32_t k = Bw.nfp[a]; k < Bw.nfp[a + 1]; ++k) {
+                        const int32_t f = Bw.nfl[k] >> 2;
+                        const int va = Bw.nfl[k] & 3, sf = Bw.fslot[f];
+                        const int32_t *v = fn + 3 * (size_t)f;
+                        const int base = fbase + sf * FACE_STRIDE;
+                        if (b == a) { R.A.push_back((uint16_t)(base + face_force_off(va))); Rm.A.push_back((uint16_t)(base + FACE_T8)); continue; }
+                        for (int vj = 0; vj < 3; ++vj)
+                            if (v[vj] == b) {
+                                (va < vj ? R.A : R.B).push_back((uint16_t)(base + face_off_off(std::min(va, vj), std::max(va, vj))));
+                                Rm.A.push_back((uint16_t)(base + FACE_T8));
+                            }
+                    }
+                    for (int32_t k = Bw.nep[a]; k < Bw.nep[a + 1]; ++k) {
+                        const int32_t e = Bw.nel[k] >> 2;
+                        const int ia = Bw.nel[k] & 3, se = Bw.eslot[e];
+                        const int32_t *v = ie + 4 * (size_t)e;
+                        const int base = ZPAD + se * EDGE_STRIDE;
+                        if (b == a) continue;                // diagonal block: phase 3
+                        for (int ij = 0; ij < 4; ++ij)
+                            if (v[ij] == b) (ia < ij ? R.A : R.B).push_back((uint16_t)(base + edge_off_off(std::min(ia, ij), std::max(ia, ij))));
+                    }
+                    const unsigned has2 = ob >= 0 ? 1u : 0u;
+                    if (has2 && pat.blkptrK[b + 1] - pat.blkptrK[b] > 255) { Q.error = "node " + std::to_string(b) + " has more than 255 neighbours"; return false; }
+                    if (b == a) {
+                        R.rec = pack_rec(offsF[o], 0, (offsKM[o] & 0xffffu) + 3u * (unsigned)p, 3u * (unsigned)deg, deg ? 1u : 0u, 0);
+                    } else {
+                        unsigned off2 = 0, s2 = 0;
+                        if (has2) {
+                            const unsigned p2 = (unsigned)(find_block(pat.blkptrK, pat.nbrK, b, a) - pat.blkptrK[b]);
+                            off2 = (offsKM[ob] & 0xffffu) + 3u * p2; s2 = 3u * (unsigned)(pat.blkptrK[b + 1] - pat.blkptrK[b]);
                         }
-                }
-                for (int32_t k = B.nep[a]; k < B.nep[a + 1]; ++k) {
-                    const int32_t e = B.nel[k] >> 2;
-                    const int ia = B.nel[k] & 3, se = B.eslot[e];
-                    const int32_t *v = ie + 4 * (size_t)e;
-                    const int base = ZPAD + se * EDGE_STRIDE;
-                    if (b == a) continue;                // diagonal block: phase 3
-                    for (int ij = 0; ij < 4; ++ij)
-                        if (v[ij] == b) (ia < ij ? R.A : R.B).push_back((uint16_t)(base + edge_off_off(std::min(ia, ij), std::max(ia, ij))));
-                }
-                const unsigned has2 = ob >= 0 ? 1u : 0u;
-                if (has2 && pat.blkptrK[b + 1] - pat.blkptrK[b] > 255) { P.error = "node " + std::to_string(b) + " has more than 255 neighbours"; return false; }
-                if (b == a) {
-                    R.rec = pack_rec(offsF[o], 0, (offsKM[o] & 0xffffu) + 3u * (unsigned)p, 3u * (unsigned)deg, deg ? 1u : 0u, 0);
-                } else {
-                    unsigned off2 = 0, s2 = 0;
-                    if (has2) {
-                        const unsigned p2 = (unsigned)(find_block(pat.blkptrK, pat.nbrK, b, a) - pat.blkptrK[b]);
-                        off2 = (offsKM[ob] & 0xffffu) + 3u * p2; s2 = 3u * (unsigned)(pat.blkptrK[b + 1] - pat.blkptrK[b]);
+                        R.rec = pack_rec((offsKM[o] & 0xffffu) + 3u * (unsigned)p, 3u * (unsigned)deg, off2, s2, has2, 0);
                     }
-                    R.rec = pack_rec((offsKM[o] & 0xffffu) + 3u * (unsigned)p, 3u * (unsigned)deg, off2, s2, has2, 0);
-                }
-                R.p = p;
-                recs[b == a ? KIND_D : KIND_O].push_back(std::move(R));
-                if (!Rm.A.empty()) {   // the pair shares a face -> mass block
-                    const unsigned pM = (unsigned)(find_block(pat.blkptrM, pat.nbrM, a, b) - m0);
-                    unsigned off2 = 0, s2 = 0;
-                    if (has2) {
-                        const unsigned pM2 = (unsigned)(find_block(pat.blkptrM, pat.nbrM, b, a) - pat.blkptrM[b]);
-                        off2 = (offsKM[ob] >> 16) + 3u * pM2; s2 = 3u * (unsigned)(pat.blkptrM[b + 1] - pat.blkptrM[b]);
-                    }
-                    Rm.rec = pack_rec((offsKM[o] >> 16) + 3u * pM, 3u * (unsigned)degM, off2, s2, has2, b == a ? 1u : 0u);
-                    Rm.p = (int)pM;
-                    recs[KIND_M].push_back(std::move(Rm));
-                }
-            }
-        }
-        // ---- groups: records of one kind, sorted by trip counts (stable) so that the lanes of a group run similar lists
-        auto pairs = [](const std::vector<uint16_t> &l) { return (int)(l.size() + 1) / 2; };
-        groups.clear();
-        for (int kind = 0; kind < 3; ++kind) {
-            auto &rv = recs[kind];
-            if (kind != KIND_D)
-                std::stable_sort(rv.begin(), rv.end(), [&](const RecTmp &u, const RecTmp &v) {
-                    const int cu = pairs(u.A) + pairs(u.B), cv = pairs(v.A) + pairs(v.B);
-                    if (cu != cv) return cu > cv;
-                    if (pairs(u.A) != pairs(v.A)) return pairs(u.A) > pairs(v.A);
-                    // same position in the row = same direction on a structured mesh: neighbouring lanes then pull the same block
-                    // of neighbouring elements, whose slots fall into different bank groups
-                    if (getenv("EOLC_PLAN_SORT_OWN")) return false;
-                    return u.p < v.p;
-                });
-            for (size_t g0 = 0; g0 < rv.size();) {
-                // (half-width groups for the long lists were tried: a group's time is set by the latency of its trips, not by its
-                // width, so splitting only lengthened every warp's chain: 0.85 -> 0.99 ms, profiles/r01/experiments.md)
-                const size_t width = GROUP;
-                Grp G{kind, 0, 0, (int)g0, (int)std::min(rv.size() - g0, width), 0, 0};
-                for (size_t k = g0; k < g0 + (size_t)G.count; ++k) { G.nA = std::max(G.nA, pairs(rv[k].A)); G.nB = std::max(G.nB, pairs(rv[k].B)); }
-                if (G.nA > MAX_ITER || G.nB > MAX_ITER) { P.error = "tile " + std::to_string(t) + ": contribution list overflow"; return false; }
-                // rough clocks of one group on the kernel (latency bound: a fixed part + so much per trip), for the warp assignment below
-                // (measured on the 1024^2 sheet, B200: an O group takes ~1150 + 220 per trip, an M group ~600 + 50, a D group ~700 + 50;
-                // the fixed part is the latency chain record -> row table -> staged stores; nearly empty groups take about half)
-                G.cost = kind == KIND_D ? 700 + 50L * G.nA : kind == KIND_O ? 1150 + 220L * (G.nA + G.nB) : 600 + 50L * G.nA;
-                if (G.count <= 8) G.cost /= 2;
-                groups.push_back(G);
-                g0 += (size_t)G.count;
-            }
-        }
-        std::stable_sort(groups.begin(), groups.end(), [](const Grp &u, const Grp &v) { return u.cost > v.cost; });
-        if (groups.size() > 255) { P.error = "tile " + std::to_string(t) + ": too many phase-2 groups"; return false; }
-        {
-            // longest-processing-time-first assignment of the groups to the phase-2 warps; then ordered by warp (stable), so that a
-            // warp walks its groups in descending cost
-            long load[P2THREADS / 32] = {0};
-            for (Grp &G : groups) {
-                int w = 0;
-                for (int k = 1; k < P2THREADS / 32; ++k) if (load[k] < load[w]) w = k;
-                G.warp = w; load[w] += G.cost;
-            }
-            std::stable_sort(groups.begin(), groups.end(), [](const Grp &u, const Grp &v) { return u.warp < v.warp; });
-        }
-        // ---- serialise the template
-        T.clear();
-        T.push_back((uint32_t)nE | ((uint32_t)nF << 16));
-        T.push_back(0); T.push_back(0); T.push_back(0);
-        T.insert(T.end(), items.begin(), items.end());
-        while (T.size() % 4) T.push_back(0);
-        const uint32_t sizeA16 = (uint32_t)(T.size() / 4);
-        T.push_back((uint32_t)n_own | ((uint32_t)groups.size() << 8));
-        T.push_back(0); T.push_back(0); T.push_back(0);
-        for (int w = 0; w < P2THREADS / 32; ++w) {          // groups [first, first + count) of warp w (the groups are ordered by warp)
-            uint32_t first = 0, count = 0;
-            for (size_t g = 0; g < groups.size(); ++g) if (groups[g].warp == w) { if (!count) first = (uint32_t)g; ++count; }
-            T.push_back(first | (count << 16));
-        }
-        auto push_padded = [&](const std::vector<uint32_t> &v) { T.insert(T.end(), v.begin(), v.end()); while (T.size() % 4) T.push_back(0); };
-        push_padded(degs); push_padded(offsKM); push_padded(offsF);
-        {
-            uint32_t pbase = 0;
-            for (const Grp &G : groups) {
-                T.push_back((uint32_t)G.kind | ((uint32_t)G.nA << 8) | ((uint32_t)G.nB << 16));
-                T.push_back(pbase); T.push_back((uint32_t)G.warp); T.push_back(0);
-                pbase += (uint32_t)(G.nA + G.nB) * GROUP;
-            }
-            P.pull_rows += pbase / GROUP;
-        }
-        for (const Grp &G : groups) {
-            const auto &rv = recs[G.kind];
-            for (int l = 0; l < GROUP; ++l) {
-                const uint64_t r = l < G.count ? rv[G.first + l].rec : 0ull;
-                T.push_back((uint32_t)r); T.push_back((uint32_t)(r >> 32));
-            }
-        }
-        for (const Grp &G : groups) {
-            const auto &rv = recs[G.kind];
-            for (int loop = 0; loop < 2; ++loop)
-                for (int r = 0; r < (loop ? G.nB : G.nA); ++r)
-                    for (int l = 0; l < GROUP; ++l) {
-                        uint32_t e = 0;
-                        if (l < G.count) {
-                            const std::vector<uint16_t> &L = loop ? rv[G.first + l].B : rv[G.first + l].A;
-                            if ((size_t)2 * r < L.size()) e = L[2 * r];
-                            if ((size_t)2 * r + 1 < L.size()) e |= (uint32_t)L[2 * r + 1] << 16;
+                    R.p = p;
+                    recs[b == a ? KIND_D : KIND_O].push_back(std::move(R));
+                    if (!Rm.A.empty()) {   // the pair shares a face -> mass block
+                        const unsigned pM = (unsigned)(find_block(pat.blkptrM, pat.nbrM, a, b) - m0);
+                        unsigned off2 = 0, s2 = 0;
+                        if (has2) {
+                            const unsigned pM2 = (unsigned)(find_block(pat.blkptrM, pat.nbrM, b, a) - pat.blkptrM[b]);
+                            off2 = (offsKM[ob] >> 16) + 3u * pM2; s2 = 3u * (unsigned)(pat.blkptrM[b + 1] - pat.blkptrM[b]);
                         }
-                        T.push_back(e);
+                        Rm.rec = pack_rec((offsKM[o] >> 16) + 3u * pM, 3u * (unsigned)degM, off2, s2, has2, b == a ? 1u : 0u);
+                        Rm.p = (int)pM;
+                        recs[KIND_M].push_back(std::move(Rm));
                     }
-        }
-        while (T.size() % 4) T.push_back(0);
-        {
-            // phase-3 items: one per entry (j, k), j <= k, of every owned node's diagonal MDK block, 3 words each:
-            //   start of the strided row sum (staging offset of row j, column k of the node's first block) | deg << 16 | (j == k) << 24,
-            //   destination | mirrored destination << 16,   staging offset of the node's M_aa
-            const uint32_t p3_at = (uint32_t)(T.size() - (size_t)sizeA16 * 4);
-            uint32_t n_items = 0;
-            // entry-major order: neighbouring lanes work on the same entry of consecutive nodes, whose rows are 9 deg doubles apart
-            // (an odd number for the usual odd degrees: conflict-free 64-bit accesses)
-            for (uint32_t j = 0; j < 3; ++j)
-                for (uint32_t k = j; k < 3; ++k)
-                    for (int o = 0; o < n_own; ++o) {
-                        const uint32_t deg = degs[o] & 255u, pd = (degs[o] >> 16) & 255u, pdM = degs[o] >> 24;
-                        if (!deg) continue;
-                        const uint32_t base = offsKM[o] & 0xffffu, mo = (offsKM[o] >> 16) + 3 * pdM;
-                        T.push_back((base + 3 * deg * j + k) | (deg << 16) | ((j == k ? 1u : 0u) << 24));
-                        T.push_back((base + 3 * deg * j + 3 * pd + k) | ((base + 3 * deg * k + 3 * pd + j) << 16));
-                        T.push_back(mo);
-                        ++n_items;
-                    }
-            T[(size_t)sizeA16 * 4 + 1] = p3_at;
-            T[(size_t)sizeA16 * 4 + 2] = n_items;
+                }
+            }
+            // ---- groups: records of one kind, sorted by trip counts (stable) so that the lanes of a group run similar lists
+            auto pairs = [](const std::vector<uint16_t> &l) { return (int)(l.size() + 1) / 2; };
+            groups.clear();
+            for (int kind = 0; kind < 3; ++kind) {
+                auto &rv = recs[kind];
+                if (kind != KIND_D)
+                    std::stable_sort(rv.begin(), rv.end(), [&](const RecTmp &u, const RecTmp &v) {
+                        const int cu = pairs(u.A) + pairs(u.B), cv = pairs(v.A) + pairs(v.B);
+                        if (cu != cv) return cu > cv;
+                        if (pairs(u.A) != pairs(v.A)) return pairs(u.A) > pairs(v.A);
+                        // same position in the row = same direction on a structured mesh: neighbouring lanes then pull the same block
+                        // of neighbouring elements, whose slots fall into different bank groups
+                        if (getenv("EOLC_PLAN_SORT_OWN")) return false;
+                        return u.p < v.p;
+                    });
+                for (size_t g0 = 0; g0 < rv.size();) {
+                    // (half-width groups for the long lists were tried: a group's time is set by the latency of its trips, not by its
+                    // width, so splitting only lengthened every warp's chain: 0.85 -> 0.99 ms, profiles/r01/experiments.md)
+                    const size_t width = GROUP;
+                    Grp G{kind, 0, 0, (int)g0, (int)std::min(rv.size() - g0, width), 0, 0};
+                    for (size_t k = g0; k < g0 + (size_t)G.count; ++k) { G.nA = std::max(G.nA, pairs(rv[k].A)); G.nB = std::max(G.nB, pairs(rv[k].B)); }
+                    if (G.nA > MAX_ITER || G.nB > MAX_ITER) { Q.error = "tile " + std::to_string(t) + ": contribution list overflow"; return false; }
+                    // rough clocks of one group on the kernel (latency bound: a fixed part + so much per trip), for the warp assignment below
+                    // (measured on the 1024^2 sheet, B200: an O group takes ~1150 + 220 per trip, an M group ~600 + 50, a D group ~700 + 50;
+                    // the fixed part is the latency chain record -> row table -> staged stores; nearly empty groups take about half)
+                    G.cost = kind == KIND_D ? 700 + 50L * G.nA : kind == KIND_O ? 1150 + 220L * (G.nA + G.nB) : 600 + 50L * G.nA;
+                    if (G.count <= 8) G.cost /= 2;
+                    groups.push_back(G);
+                    g0 += (size_t)G.count;
+                }
+            }
+            std::stable_sort(groups.begin(), groups.end(), [](const Grp &u, const Grp &v) { return u.cost > v.cost; });
+            if (groups.size() > 255) { Q.error = "tile " + std::to_string(t) + ": too many phase-2 groups"; return false; }
+            {
+                // longest-processing-time-first assignment of the groups to the phase-2 warps; then ordered by warp (stable), so that a
+                // warp walks its groups in descending cost
+                long load[P2THREADS / 32] = {0};
+                for (Grp &G : groups) {
+                    int w = 0;
+                    for (int k = 1; k < P2THREADS / 32; ++k) if (load[k] < load[w]) w = k;
+                    G.warp = w; load[w] += G.cost;
+                }
+                std::stable_sort(groups.begin(), groups.end(), [](const Grp &u, const Grp &v) { return u.warp < v.warp; });
+            }
+            // ---- serialise the template
+            T.clear();
+            T.push_back((uint32_t)nE | ((uint32_t)nF << 16));
+            T.push_back(0); T.push_back(0); T.push_back(0);
+            T.insert(T.end(), items.begin(), items.end());
             while (T.size() % 4) T.push_back(0);
+            const uint32_t sizeA16 = (uint32_t)(T.size() / 4);
+            T.push_back((uint32_t)n_own | ((uint32_t)groups.size() << 8));
+            T.push_back(0); T.push_back(0); T.push_back(0);
+            for (int w = 0; w < P2THREADS / 32; ++w) {          // groups [first, first + count) of warp w (the groups are ordered by warp)
+                uint32_t first = 0, count = 0;
+                for (size_t g = 0; g < groups.size(); ++g) if (groups[g].warp == w) { if (!count) first = (uint32_t)g; ++count; }
+                T.push_back(first | (count << 16));
+            }
+            auto push_padded = [&](const std::vector<uint32_t> &v) { T.insert(T.end(), v.begin(), v.end()); while (T.size() % 4) T.push_back(0); };
+            push_padded(degs); push_padded(offsKM); push_padded(offsF);
+            {
+                uint32_t pbase = 0;
+                for (const Grp &G : groups) {
+                    T.push_back((uint32_t)G.kind | ((uint32_t)G.nA << 8) | ((uint32_t)G.nB << 16));
+                    T.push_back(pbase); T.push_back((uint32_t)G.warp); T.push_back(0);
+                    pbase += (uint32_t)(G.nA + G.nB) * GROUP;
+                }
+                Q.pull_rows += pbase / GROUP;
+            }
+            for (const Grp &G : groups) {
+                const auto &rv = recs[G.kind];
+                for (int l = 0; l < GROUP; ++l) {
+                    const uint64_t r = l < G.count ? rv[G.first + l].rec : 0ull;
+                    T.push_back((uint32_t)r); T.push_back((uint32_t)(r >> 32));
+                }
+            }
+            for (const Grp &G : groups) {
+                const auto &rv = recs[G.kind];
+                for (int loop = 0; loop < 2; ++loop)
+                    for (int r = 0; r < (loop ? G.nB : G.nA); ++r)
+                        for (int l = 0; l < GROUP; ++l) {
+                            uint32_t e = 0;
+                            if (l < G.count) {
+                                const std::vector<uint16_t> &L = loop ? rv[G.first + l].B : rv[G.first + l].A;
+                                if ((size_t)2 * r < L.size()) e = L[2 * r];
+                                if ((size_t)2 * r + 1 < L.size()) e |= (uint32_t)L[2 * r + 1] << 16;
+                            }
+                            T.push_back(e);
+                        }
+            }
+            while (T.size() % 4) T.push_back(0);
+            {
+                // phase-3 items: one per entry (j, k), j <= k, of every owned node's diagonal MDK block, 3 words each:
+                //   start of the strided row sum (staging offset of row j, column k of the node's first block) | deg << 16 | (j == k) << 24,
+                //   destination | mirrored destination << 16,   staging offset of the node's M_aa
+                const uint32_t p3_at = (uint32_t)(T.size() - (size_t)sizeA16 * 4);
+                uint32_t n_items = 0;
+                // entry-major order: neighbouring lanes work on the same entry of consecutive nodes, whose rows are 9 deg doubles apart
+                // (an odd number for the usual odd degrees: conflict-free 64-bit accesses)
+                for (uint32_t j = 0; j < 3; ++j)
+                    for (uint32_t k = j; k < 3; ++k)
+                        for (int o = 0; o < n_own; ++o) {
+                            const uint32_t deg = degs[o] & 255u, pd = (degs[o] >> 16) & 255u, pdM = degs[o] >> 24;
+                            if (!deg) continue;
+                            const uint32_t base = offsKM[o] & 0xffffu, mo = (offsKM[o] >> 16) + 3 * pdM;
+                            T.push_back((base + 3 * deg * j + k) | (deg << 16) | ((j == k ? 1u : 0u) << 24));
+                            T.push_back((base + 3 * deg * j + 3 * pd + k) | ((base + 3 * deg * k + 3 * pd + j) << 16));
+                            T.push_back(mo);
+                            ++n_items;
+                        }
+                T[(size_t)sizeA16 * 4 + 1] = p3_at;
+                T[(size_t)sizeA16 * 4 + 2] = n_items;
+                while (T.size() % 4) T.push_back(0);
+            }
+            Q.n_groups += (int64_t)groups.size();
+            const uint32_t sizeB16 = (uint32_t)(T.size() / 4) - sizeA16;
+            if (sizeA16 > 0xffffu || sizeB16 > 0xffffu) { Q.error = "tile " + std::to_string(t) + ": template too large"; return false; }
+            Q.max_tmplA16 = std::max(Q.max_tmplA16, sizeA16); Q.max_tmplB16 = std::max(Q.max_tmplB16, sizeB16);
+            // ---- deduplicate
+            uint32_t toff = 0;
+            bool found = false;
+            uint64_t h = 1469598103934665603ull;
+            if (dedup) {
+                for (uint32_t w : T) { h ^= w; h *= 1099511628211ull; }
+                auto it = seen.find(h);
+                if (it != seen.end())
+                    for (uint32_t cand : it->second)
+                        if ((size_t)cand * 4 + T.size() <= Q.tmpl.size() && memcmp(Q.tmpl.data() + (size_t)cand * 4, T.data(), T.size() * 4) == 0) {
+                            toff = cand; found = true; break;
+                        }
+            }
+            if (!found) {
+                toff = (uint32_t)(Q.tmpl.size() / 4);
+                Q.tmpl.insert(Q.tmpl.end(), T.begin(), T.end());
+                if (dedup) seen[h].push_back(toff);
+                ++Q.n_templates;
+                unique_tmpl.push_back({toff, sizeA16});
+            }
+            // ---- geometry blob
+            geo_off.push_back((uint32_t)(Q.geo.size() / 4));
+            const size_t g0 = Q.geo.size();
+            Q.geo.push_back(toff);
+            Q.geo.push_back((uint32_t)n_own | ((uint32_t)loc.size() << 8));
+            Q.geo.push_back(sizeA16 | (sizeB16 << 16));
+            Q.geo.push_back((uint32_t)runs.size());
+            Q.geo.insert(Q.geo.end(), loc.begin(), loc.end());
+            while (Q.geo.size() % 4) Q.geo.push_back(0);
+            for (const Run &r : runs) {
+                const uint64_t d = r.dst | ((uint64_t)r.kind << 62);
+                Q.geo.push_back((uint32_t)d); Q.geo.push_back((uint32_t)(d >> 32));
+                Q.geo.push_back(r.src); Q.geo.push_back(r.len);
+            }
+            Q.n_runs += (int64_t)runs.size();
+            Q.max_geo16 = std::max<uint32_t>(Q.max_geo16, (uint32_t)((Q.geo.size() - g0) / 4));
+            if (Q.geo.size() / 4 >= ((size_t)1 << 32) || Q.tmpl.size() / 4 >= ((size_t)1 << 32)) { Q.error = "plan too large"; return false; }
         }
-        P.n_groups += (int64_t)groups.size();
-        const uint32_t sizeB16 = (uint32_t)(T.size() / 4) - sizeA16;
-        if (sizeA16 > 0xffffu || sizeB16 > 0xffffu) { P.error = "tile " + std::to_string(t) + ": template too large"; return false; }
-        P.max_tmplA16 = std::max(P.max_tmplA16, sizeA16); P.max_tmplB16 = std::max(P.max_tmplB16, sizeB16);
-        // ---- deduplicate
-        uint32_t toff = 0;
-        bool found = false;
-        uint64_t h = 1469598103934665603ull;
-        if (dedup) {
-            for (uint32_t w : T) { h ^= w; h *= 1099511628211ull; }
-            auto it = seen.find(h);
-            if (it != seen.end())
-                for (uint32_t cand : it->second)
-                    if ((size_t)cand * 4 + T.size() <= P.tmpl.size() && memcmp(P.tmpl.data() + (size_t)cand * 4, T.data(), T.size() * 4) == 0) {
-                        toff = cand; found = true; break;
+        geo_off.push_back((uint32_t)(Q.geo.size() / 4));
+        return true;
+    };
+    int n_workers = 1;
+    {
+        const char *ev = getenv("EOLC_PLAN_THREADS");
+        const unsigned hw = std::thread::hardware_concurrency();
+        n_workers = ev ? atoi(ev) : (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+        n_workers = std::max(1, std::min<int>(n_workers, (int)(leaves.size() / 64)));
+    }
+    std::vector<Plan> parts((size_t)n_workers);
+    std::vector<std::vector<uint32_t>> part_geo_off((size_t)n_workers);
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> part_unique((size_t)n_workers);
+    std::vector<char> part_ok((size_t)n_workers, 1);
+    auto range_of = [&](int w) { return std::make_pair(leaves.size() * (size_t)w / (size_t)n_workers, leaves.size() * (size_t)(w + 1) / (size_t)n_workers); };
+    if (n_workers == 1) {
+        part_ok[0] = build_range(B, 0, leaves.size(), parts[0], part_geo_off[0], part_unique[0]) ? 1 : 0;
+    } else {
+        std::vector<std::thread> th;
+        for (int w = 0; w < n_workers; ++w)
+            th.emplace_back([&, w]() {
+                Builder Bw(N, F, fn, Ei, ie, pat, csr);       // own scratch (stamps, slot maps); the node CSR is shared
+                const auto r = range_of(w);
+                part_ok[w] = build_range(Bw, r.first, r.second, parts[w], part_geo_off[w], part_unique[w]) ? 1 : 0;
+            });
+        for (auto &t : th) t.join();
+    }
+    for (int w = 0; w < n_workers; ++w) if (!part_ok[w]) { P.error = parts[w].error; return false; }
+    // ---- merge in tile order: templates deduplicated across the ranges, geometry blobs re-laid with a fixed stride
+    std::vector<std::pair<uint32_t, uint32_t>> unique_tmpl;   // (offset, size of part A) of every stored template, 16-byte units
+    for (int w = 0; w < n_workers; ++w) {
+        const Plan &Q = parts[w];
+        P.max_geo16 = std::max(P.max_geo16, Q.max_geo16); P.max_tmplA16 = std::max(P.max_tmplA16, Q.max_tmplA16); P.max_tmplB16 = std::max(P.max_tmplB16, Q.max_tmplB16);
+        P.max_loc = std::max(P.max_loc, Q.max_loc); P.max_scratch = std::max(P.max_scratch, Q.max_scratch);
+        P.max_kstage = std::max(P.max_kstage, Q.max_kstage); P.max_mstage = std::max(P.max_mstage, Q.max_mstage); P.max_fstage = std::max(P.max_fstage, Q.max_fstage);
+        P.elem_evals += Q.elem_evals; P.n_runs += Q.n_runs; P.n_groups += Q.n_groups; P.pull_rows += Q.pull_rows;
+    }
+    {
+        std::unordered_map<uint64_t, std::vector<uint32_t>> seen;
+        std::vector<uint32_t> fixed((size_t)P.n_tiles * P.max_geo16 * 4, 0u);
+        size_t t = 0;
+        for (int w = 0; w < n_workers; ++w) {
+            const Plan &Q = parts[w];
+            // local template offset -> global offset (first use in tile order decides the global order)
+            std::unordered_map<uint32_t, uint32_t> remap;
+            std::vector<std::pair<uint32_t, uint32_t>> local_sorted = part_unique[w];   // (local offset, sizeA16), ascending offsets
+            auto tmpl_words = [&](uint32_t loff) {     // length of the local template starting at loff: up to the next one
+                size_t end = Q.tmpl.size() / 4;
+                for (const auto &u : local_sorted) if (u.first > loff) { end = std::min<size_t>(end, u.first); }
+                return (end - loff) * 4;
+            };
+            const size_t ntw = part_geo_off[w].size() - 1;
+            for (size_t k = 0; k < ntw; ++k, ++t) {
+                const uint32_t *g = Q.geo.data() + (size_t)part_geo_off[w][k] * 4;
+                const size_t glen = (size_t)(part_geo_off[w][k + 1] - part_geo_off[w][k]) * 4;
+                uint32_t *dst = fixed.data() + t * P.max_geo16 * 4;
+                memcpy(dst, g, glen * 4);
+                const uint32_t loff = g[0];
+                auto it = remap.find(loff);
+                if (it == remap.end()) {
+                    const size_t words = tmpl_words(loff);
+                    const uint32_t *src = Q.tmpl.data() + (size_t)loff * 4;
+                    uint64_t h = 1469598103934665603ull;
+                    for (size_t q = 0; q < words; ++q) { h ^= src[q]; h *= 1099511628211ull; }
+                    uint32_t goff = 0;
+                    bool found = false;
+                    if (dedup) {
+                        auto si = seen.find(h);
+                        if (si != seen.end())
+                            for (uint32_t cand : si->second)
+                                if ((size_t)cand * 4 + words <= P.tmpl.size() && memcmp(P.tmpl.data() + (size_t)cand * 4, src, words * 4) == 0) { goff = cand; found = true; break; }
                     }
+                    if (!found) {
+                        goff = (uint32_t)(P.tmpl.size() / 4);
+                        P.tmpl.insert(P.tmpl.end(), src, src + words);
+                        if (dedup) seen[h].push_back(goff);
+                        ++P.n_templates;
+                        unique_tmpl.push_back({goff, g[2] & 0xffffu});
+                    }
+                    it = remap.emplace(loff, goff).first;
+                }
+                dst[0] = it->second;
+            }
+            if (P.tmpl.size() / 4 >= ((size_t)1 << 32)) { P.error = "plan too large"; return false; }
         }
-        if (!found) {
-            toff = (uint32_t)(P.tmpl.size() / 4);
-            P.tmpl.insert(P.tmpl.end(), T.begin(), T.end());
-            if (dedup) seen[h].push_back(toff);
-            ++P.n_templates;
-            unique_tmpl.push_back({toff, sizeA16});
-        }
-        // ---- geometry blob
-        geo_off.push_back((uint32_t)(P.geo.size() / 4));
-        const size_t g0 = P.geo.size();
-        P.geo.push_back(toff);
-        P.geo.push_back((uint32_t)n_own | ((uint32_t)loc.size() << 8));
-        P.geo.push_back(sizeA16 | (sizeB16 << 16));
-        P.geo.push_back((uint32_t)runs.size());
-        P.geo.insert(P.geo.end(), loc.begin(), loc.end());
-        while (P.geo.size() % 4) P.geo.push_back(0);
-        for (const Run &r : runs) {
-            const uint64_t d = r.dst | ((uint64_t)r.kind << 62);
-            P.geo.push_back((uint32_t)d); P.geo.push_back((uint32_t)(d >> 32));
-            P.geo.push_back(r.src); P.geo.push_back(r.len);
-        }
-        P.n_runs += (int64_t)runs.size();
-        P.max_geo16 = std::max<uint32_t>(P.max_geo16, (uint32_t)((P.geo.size() - g0) / 4));
-        if (P.geo.size() / 4 >= ((size_t)1 << 32) || P.tmpl.size() / 4 >= ((size_t)1 << 32)) { P.error = "plan too large"; return false; }
+        P.geo.swap(fixed);
     }
     {
         // bank-aware post-pass over the stored templates; the slot search only where templates are shared (structured meshes)
@@ -826,13 +926,6 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         const long budget = ob ? atol(ob) : 4000;
         const int iters = (int)std::max<long>(0, std::min<long>(budget, 400000 / (long)std::max<size_t>(1, unique_tmpl.size())));
         for (const auto &u : unique_tmpl) optimize_template(P.tmpl.data() + (size_t)u.first * 4, u.second, iters < 20 ? 0 : iters);
-    }
-    geo_off.push_back((uint32_t)(P.geo.size() / 4));
-    {
-        std::vector<uint32_t> fixed((size_t)P.n_tiles * P.max_geo16 * 4, 0u);
-        for (int32_t t = 0; t < P.n_tiles; ++t)
-            memcpy(fixed.data() + (size_t)t * P.max_geo16 * 4, P.geo.data() + (size_t)geo_off[t] * 4, (size_t)(geo_off[t + 1] - geo_off[t]) * 16);
-        P.geo.swap(fixed);
     }
     return true;
 }

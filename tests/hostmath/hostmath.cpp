@@ -140,6 +140,16 @@ void hm_plan_pull_conflicts(void *p, double *out) {
         }
     }
 }
+// FNV-1a over the plan's geometry blobs and templates: equal for equal plans (used to check that the build does not depend on the worker count)
+uint64_t hm_plan_hash(void *p) {
+    HmPlan *P = (HmPlan *)p;
+    uint64_t h = 1469598103934665603ull;
+    for (uint32_t w : P->tp.geo) { h ^= w; h *= 1099511628211ull; }
+    for (uint32_t w : P->tp.tmpl) { h ^= w; h *= 1099511628211ull; }
+    h ^= (uint64_t)P->tp.n_tiles; h *= 1099511628211ull;
+    h ^= (uint64_t)P->tp.n_templates; h *= 1099511628211ull;
+    return h;
+}
 // developer helper: copies template part B of tile t (u32 words) into out; returns the number of words
 int hm_plan_dump(void *p, int t, uint32_t *out, int cap) {
     HmPlan *P = (HmPlan *)p;

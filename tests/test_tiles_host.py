@@ -150,3 +150,26 @@ def test_tiles_host_rejects_nonmanifold(hostmath):
     es = np.array([[0, 1, 2, 2]], np.int32)
     with pytest.raises(RuntimeError):
         HostTiles(hostmath, 3, fn, es, None, True)
+
+
+def test_tiles_host_plan_independent_of_worker_count(hostmath, monkeypatch):
+    """forces_plan.h builds the tiles on several host threads and merges the ranges in tile order: the plan (geometry blobs,
+    templates, template order) must be the same bytes for 1, 3 and 8 workers, with and without template sharing."""
+    hostmath.hm_plan_hash.restype = ctypes.c_uint64
+    hostmath.hm_plan_hash.argtypes = [ctypes.c_void_p]
+    X, fn = E.meshgen.regular2(128)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(X.shape[0]).astype(np.int32)     # irregular numbering: no template sharing to speak of
+    fn_p = perm[fn]
+    es_p = np.where(es >= 0, perm[np.maximum(es, 0)], -1).astype(np.int32)
+    X_p = np.empty_like(X); X_p[perm] = X
+    for args in ((X.shape[0], fn, es, X, True), (X.shape[0], fn_p, es_p, X_p, True), (X.shape[0], fn, es, None, False)):
+        hashes, infos = [], []
+        for nt in ("1", "3", "8"):
+            monkeypatch.setenv("EOLC_PLAN_THREADS", nt)
+            T = HostTiles(hostmath, *args)
+            hashes.append(hostmath.hm_plan_hash(T.h)); infos.append(T.info)
+            T.close()
+        assert hashes[0] == hashes[1] == hashes[2], (hashes, infos)
+        assert infos[0] == infos[1] == infos[2]
