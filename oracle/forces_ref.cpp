@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
 //
-// CPU restatement of the reference's Forces::fill (non-EOL branch) over flat
+// CPU restatement of the reference's Forces::fill (Lagrangian and EOL branches) over flat
 // arrays, Eigen-free, single-threaded, linking the reference's own generated
 // arithmetic (ComputeMembrane.cpp / ComputeBending.cpp / ComputeInertial.cpp,
 // compiled UNMODIFIED from /root/reference/src into oracle/_ref/ by
@@ -19,6 +19,11 @@
 //   edgeBasedF        src/Forces.cpp:685-744 and :885-908 (non-EOL scatter)
 //   fillxB/fillxxB    src/Forces.cpp:522-539
 //   Forces::fill      src/Forces.cpp:912-930
+//   EOL branch        deform_grad src/UtilEOL.cpp:13-28; fillEOLInertia / fillEOLMembrane src/Forces.cpp:177-329;
+//                     face scatter :399-497 with fill{X,XX,Xx,xX}MI :127-175; fillEOLBending :580-683; edge scatter
+//                     :746-883 with fill{X,XX,Xx,xX}B :541-578.  The inertial and membrane expansions are the same code
+//                     with K = Mi / Km, and the bending one is the 4-vertex version of it, so one routine (expand_eol)
+//                     restates all three; its body follows fillEOLBending block by block.
 //   setFromTriplets   Eigen 3.3 SparseMatrix.h set_from_triplets (external, restated
 //                     from its published algorithm: bucket by row in insertion order,
 //                     collapse duplicates onto the first occurrence left-to-right,
@@ -128,6 +133,76 @@ void set_from_triplets(int dof, const std::vector<Trip> &T, Csc &out) {
         }
 }
 
+// ---- EOL branch -------------------------------------------------------------------------------------------------
+// deform_grad, UtilEOL.cpp:13-28: F = Dx * DX.inverse() (3x2, returned column-major F[0..2] = col 0, F[3..5] = col 1).
+// DX is a fixed-size Matrix2d there: Eigen's 2x2 inverse is adjugate * (1/det).
+void deform_grad(const double *xa, const double *xb, const double *xc, const double *Xa, const double *Xb, const double *Xc, double *F) {
+    const double Dx[6] = {xb[0] - xa[0], xb[1] - xa[1], xb[2] - xa[2], xc[0] - xa[0], xc[1] - xa[1], xc[2] - xa[2]};
+    const double D00 = Xb[0] - Xa[0], D01 = Xc[0] - Xa[0], D10 = Xb[1] - Xa[1], D11 = Xc[1] - Xa[1];
+    const double invdet = 1.0 / (D00 * D11 - D10 * D01);
+    const double i00 = D11 * invdet, i01 = -D01 * invdet, i10 = -D10 * invdet, i11 = D00 * invdet;
+    for (int r = 0; r < 3; ++r) {
+        F[r] = Dx[r] * i00 + Dx[3 + r] * i10;
+        F[3 + r] = Dx[r] * i01 + Dx[3 + r] * i11;
+    }
+}
+
+// The expanded element of fillEOLInertia / fillEOLMembrane (nv = 3, Forces.cpp:177-329) and fillEOLBending (nv = 4,
+// :580-683): local dofs [x_v (3), X_v (2)] per vertex, vertex v at jv = 5 v, its Eulerian pair at jV = 5 v + 3.
+// f: 3 nv, K(r, c): 3nv x 3nv accessor; F: the one deformation gradient every EoL vertex of the element uses (:188-191,
+// :265-268, :593-596).  fe (5 nv) and Ke (5nv x 5nv, column-major, ld = 5 nv) are filled exactly where the reference
+// fills them; everything else is NaN so that a read of an entry the reference leaves uninitialised shows up.
+template <typename KAcc>
+void expand_eol(int nv, const double *f, KAcc K, const double *F, const bool *eol, double *fe, double *Ke) {
+    const int n = 5 * nv;
+    const double nan = std::nan("");
+    for (int i = 0; i < n; ++i) fe[i] = nan;
+    for (int i = 0; i < n * n; ++i) Ke[i] = nan;
+    auto KE = [&](int r, int c) -> double & { return Ke[c * n + r]; };
+    auto Fm = [&](int r, int c) { return F[3 * c + r]; };   // 3x2
+    // x parts: segments and the upper block triangle (:199-205)
+    for (int v = 0; v < nv; ++v) {
+        for (int j = 0; j < 3; ++j) fe[5 * v + j] = f[3 * v + j];
+        for (int w = v; w < nv; ++w)
+            for (int j = 0; j < 3; ++j)
+                for (int k = 0; k < 3; ++k) KE(5 * v + j, 5 * w + k) = K(3 * v + j, 3 * w + k);
+    }
+    // Ft K_vw (2x3) and Ft K_vw F (2x2), products evaluated left to right like Fa.transpose() * Kiab * Fb
+    auto FtK = [&](int v, int w, double *T /*2x3 row-major*/) {
+        for (int a = 0; a < 2; ++a)
+            for (int k = 0; k < 3; ++k)
+                T[3 * a + k] = (Fm(0, a) * K(3 * v + 0, 3 * w + k) + Fm(1, a) * K(3 * v + 1, 3 * w + k)) + Fm(2, a) * K(3 * v + 2, 3 * w + k);
+    };
+    for (int v = 0; v < nv; ++v) {          // :207-218
+        if (!eol[v]) continue;
+        for (int a = 0; a < 2; ++a)
+            fe[5 * v + 3 + a] = ((-Fm(0, a)) * f[3 * v] + (-Fm(1, a)) * f[3 * v + 1]) + (-Fm(2, a)) * f[3 * v + 2];
+        double T[6];
+        FtK(v, v, T);
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) KE(5 * v + 3 + a, 5 * v + 3 + b) = (T[3 * a] * Fm(0, b) + T[3 * a + 1] * Fm(1, b)) + T[3 * a + 2] * Fm(2, b);
+    }
+    for (int v = 0; v < nv; ++v)            // :220-228
+        for (int w = v + 1; w < nv; ++w) {
+            if (!(eol[v] && eol[w])) continue;
+            double T[6];
+            FtK(v, w, T);
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) KE(5 * v + 3 + a, 5 * w + 3 + b) = (T[3 * a] * Fm(0, b) + T[3 * a + 1] * Fm(1, b)) + T[3 * a + 2] * Fm(2, b);
+        }
+    for (int v = 0; v < nv; ++v) {          // :230-251
+        if (!eol[v]) continue;
+        for (int w = v; w < nv; ++w)        // X_v - x_w = -Ft K_vw
+            for (int a = 0; a < 2; ++a)
+                for (int k = 0; k < 3; ++k)
+                    KE(5 * v + 3 + a, 5 * w + k) = ((-Fm(0, a)) * K(3 * v + 0, 3 * w + k) + (-Fm(1, a)) * K(3 * v + 1, 3 * w + k)) + (-Fm(2, a)) * K(3 * v + 2, 3 * w + k);
+        for (int u = 0; u < v; ++u)         // x_u - X_v = -K_uv F
+            for (int j = 0; j < 3; ++j)
+                for (int b = 0; b < 2; ++b)
+                    KE(5 * u + j, 5 * v + 3 + b) = ((-K(3 * u + j, 3 * v + 0)) * Fm(0, b) + (-K(3 * u + j, 3 * v + 1)) * Fm(1, b)) + (-K(3 * u + j, 3 * v + 2)) * Fm(2, b);
+    }
+}
+
 struct Result {
     int dof = 0;
     std::vector<double> f;
@@ -142,12 +217,36 @@ extern "C" {
 // mat = {density, e, nu, beta, dampingA, dampingB}  (src/Cloth.h:28-35)
 // edge_stencil: 4 ints per mesh edge (n0, n1, opp(adjf0), opp(adjf1)); -1 in slot 2/3 = boundary.
 // flags bit0: skip the assembly (setFromTriplets) — used only by the cpu_baseline timing split.
-void *oracle_forces_fill(int N, int F, const int32_t *face_nodes, int E, const int32_t *edge_stencil,
-                         const double *x, const double *X, const double *mat, const double *grav, double h,
-                         int flags) {
+// eol_index: N ints, -1 = Lagrangian node, k >= 0 = Node::EoL_index of an EoL node (may be NULL: no EoL node);
+// mesh.EoL_Count = 1 + the largest index.
+void *oracle_forces_fill_eol(int N, int F, const int32_t *face_nodes, int E, const int32_t *edge_stencil,
+                             const double *x, const double *X, const double *mat, const double *grav, double h,
+                             const int32_t *eol_index, int flags) {
     auto t0 = std::chrono::steady_clock::now();
     Result *R = new Result;
-    const int dof = 3 * N;  // EoL_Count == 0 (non-EOL branch only)
+    int eol_count = 0;
+    if (eol_index) for (int a = 0; a < N; ++a) eol_count = std::max(eol_count, eol_index[a] + 1);
+    const int dof = 3 * N + 2 * eol_count;       // Forces.cpp:914
+    auto is_eol = [&](int a) { return eol_index && eol_index[a] >= 0; };
+    auto Xdof = [&](int a) { return 3 * N + 2 * eol_index[a]; };   // :379-381
+    // edge->adjf[k] of the EOL bending branch (:590-591): the face holding the edge's two nodes and the stencil's opposite node
+    std::vector<std::pair<uint64_t, int>> face_key;
+    if (eol_count) {
+        face_key.reserve(F);
+        for (int i = 0; i < F; ++i) {
+            int v[3] = {face_nodes[3 * i], face_nodes[3 * i + 1], face_nodes[3 * i + 2]};
+            std::sort(v, v + 3);
+            face_key.push_back({((uint64_t)v[0] << 42) | ((uint64_t)v[1] << 21) | (uint64_t)v[2], i});
+        }
+        std::sort(face_key.begin(), face_key.end());
+    }
+    auto find_face = [&](int a, int b, int c) {
+        int v[3] = {a, b, c};
+        std::sort(v, v + 3);
+        const uint64_t key = ((uint64_t)v[0] << 42) | ((uint64_t)v[1] << 21) | (uint64_t)v[2];
+        auto it = std::lower_bound(face_key.begin(), face_key.end(), std::make_pair(key, -1));
+        return (it != face_key.end() && it->first == key) ? it->second : -1;
+    };
     R->dof = dof;
     R->f.assign(dof, 0.0);                       // Forces.cpp:914-915
     std::vector<Trip> M_, MDK_;                  // :916-917
@@ -187,6 +286,47 @@ void *oracle_forces_fill(int N, int F, const int32_t *face_nodes, int E, const i
         ComputeInertial(xa, xb, xc, Xa, Xb, Xc, grav, density, Wi, fi, Mi);   // :390
         // Kme(r,c) = Km[c*9+r] (column-major Map, :393)
         const int idx[3] = {3 * ia, 3 * ib, 3 * ic};
+        const bool eolv[3] = {is_eol(ia), is_eol(ib), is_eol(ic)};
+        if (eolv[0] || eolv[1] || eolv[2]) {                                  // :399
+            const double dhh = dampingB * h * h;
+            const int nodes[3] = {ia, ib, ic};
+            double Fg[6], fme[15], fie[15], Kme[225], Mie[225];
+            deform_grad(xa, xb, xc, Xa, Xb, Xc, Fg);                          // :188, :265
+            expand_eol(3, fi, [&](int r, int c) { return Mi[c * 9 + r]; }, Fg, eolv, fie, Mie);   // fillEOLInertia :401
+            expand_eol(3, fm, [&](int r, int c) { return Km[c * 9 + r]; }, Fg, eolv, fme, Kme);   // fillEOLMembrane :403
+            auto KE = [&](int r, int c) { return Kme[c * 15 + r]; };
+            auto ME = [&](int r, int c) { return Mie[c * 15 + r]; };
+            for (int v = 0; v < 3; ++v) {                                     // :405-412
+                for (int j = 0; j < 3; ++j) R->f[idx[v] + j] += fme[5 * v + j] + fie[5 * v + j];
+                if (eolv[v]) for (int j = 0; j < 2; ++j) R->f[Xdof(nodes[v]) + j] += fme[5 * v + 3 + j] + fie[5 * v + 3 + j];
+            }
+            // one (nr x nc) block at local (lr, lc) -> global (gr, gc); mirror = the fillxx / fillXX / fillXx / fillxX forms
+            auto put = [&](int lr, int lc, int nr, int nc, int gr, int gc, bool mirror) {
+                for (int j = 0; j < nr; ++j)
+                    for (int k = 0; k < nc; ++k) {
+                        const double m = ME(lr + j, lc + k);
+                        const double mdk = m + dhh * KE(lr + j, lc + k);
+                        M_.push_back({gr + j, gc + k, m});
+                        if (mirror) M_.push_back({gc + k, gr + j, m});
+                        MDK_.push_back({gr + j, gc + k, mdk});
+                        if (mirror) MDK_.push_back({gc + k, gr + j, mdk});
+                    }
+            };
+            for (int v = 0; v < 3; ++v) put(5 * v, 5 * v, 3, 3, idx[v], idx[v], false);                  // fillxMI :414-421
+            const int pr[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+            for (int p = 0; p < 3; ++p) put(5 * pr[p][0], 5 * pr[p][1], 3, 3, idx[pr[p][0]], idx[pr[p][1]], true);   // fillxxMI :423-429
+            for (int v = 0; v < 3; ++v)                                                                  // fillXMI :431-444
+                if (eolv[v]) put(5 * v + 3, 5 * v + 3, 2, 2, Xdof(nodes[v]), Xdof(nodes[v]), false);
+            for (int p = 0; p < 3; ++p)                                                                  // fillXXMI :446-458
+                if (eolv[pr[p][0]] && eolv[pr[p][1]])
+                    put(5 * pr[p][0] + 3, 5 * pr[p][1] + 3, 2, 2, Xdof(nodes[pr[p][0]]), Xdof(nodes[pr[p][1]]), true);
+            for (int v = 0; v < 3; ++v) {                                                                // :460-496
+                if (!eolv[v]) continue;
+                for (int w = v; w < 3; ++w) put(5 * v + 3, 5 * w, 2, 3, Xdof(nodes[v]), idx[w], true);   // fillXxMI
+                for (int u = 0; u < v; ++u) put(5 * u, 5 * v + 3, 3, 2, idx[u], Xdof(nodes[v]), true);   // fillxXMI
+            }
+            continue;
+        }
         for (int v = 0; v < 3; ++v)                                           // :500-502
             for (int j = 0; j < 3; ++j) R->f[idx[v] + j] += fm[3 * v + j] + fi[3 * v + j];
         const double dhh = dampingB * h * h;                                  // damping(1)*h*h, :105
@@ -227,6 +367,46 @@ void *oracle_forces_fill(int N, int F, const int32_t *face_nodes, int E, const i
         const double dhh = dampingB * h * h;
         auto Kbe = [&](int r, int c) { return Kb[c * 12 + r]; };              // :744
         const int idx[4] = {3 * s[0], 3 * s[1], 3 * s[2], 3 * s[3]};
+        const bool eolv[4] = {is_eol(s[0]), is_eol(s[1]), is_eol(s[2]), is_eol(s[3])};
+        if (eolv[0] || eolv[1] || eolv[2] || eolv[3]) {                       // :746
+            // F = (deform_grad(adjf[0]) + deform_grad(adjf[1])) / 2, each in its face's own vertex order (:590-596)
+            double F1[6], F2[6], Fg[6];
+            const int f0 = find_face(s[0], s[1], s[2]), f1 = find_face(s[0], s[1], s[3]);
+            if (f0 < 0 || f1 < 0) { delete R; return nullptr; }
+            const int32_t *a0 = face_nodes + 3 * f0, *a1 = face_nodes + 3 * f1;
+            deform_grad(x + 3 * a0[0], x + 3 * a0[1], x + 3 * a0[2], X + 2 * a0[0], X + 2 * a0[1], X + 2 * a0[2], F1);
+            deform_grad(x + 3 * a1[0], x + 3 * a1[1], x + 3 * a1[2], X + 2 * a1[0], X + 2 * a1[1], X + 2 * a1[2], F2);
+            for (int q = 0; q < 6; ++q) Fg[q] = (F1[q] + F2[q]) / 2;
+            double fbe[20], Kbx[400];
+            expand_eol(4, fb, Kbe, Fg, eolv, fbe, Kbx);                       // fillEOLBending :748
+            auto KX = [&](int r, int c) { return Kbx[c * 20 + r]; };
+            for (int v = 0; v < 4; ++v) {                                     // :750-760
+                for (int j = 0; j < 3; ++j) R->f[idx[v] + j] += fbe[5 * v + j];
+                if (eolv[v]) for (int j = 0; j < 2; ++j) R->f[Xdof(s[v]) + j] += fbe[5 * v + 3 + j];
+            }
+            auto put = [&](int lr, int lc, int nr, int nc, int gr, int gc, bool mirror) {   // K?? = damping(1)*h*h*Kbe.block, fill?B
+                for (int j = 0; j < nr; ++j)
+                    for (int k = 0; k < nc; ++k) {
+                        const double kv = dhh * KX(lr + j, lc + k);
+                        MDK_.push_back({gr + j, gc + k, kv});
+                        if (mirror) MDK_.push_back({gc + k, gr + j, kv});
+                    }
+            };
+            const int pr[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+            for (int v = 0; v < 4; ++v) put(5 * v, 5 * v, 3, 3, idx[v], idx[v], false);                  // :762-770
+            for (int p = 0; p < 6; ++p) put(5 * pr[p][0], 5 * pr[p][1], 3, 3, idx[pr[p][0]], idx[pr[p][1]], true);   // :772-783
+            for (int v = 0; v < 4; ++v)                                                                  // fillXB :785-801
+                if (eolv[v]) put(5 * v + 3, 5 * v + 3, 2, 2, Xdof(s[v]), Xdof(s[v]), false);
+            for (int p = 0; p < 6; ++p)                                                                  // fillXXB :803-826
+                if (eolv[pr[p][0]] && eolv[pr[p][1]])
+                    put(5 * pr[p][0] + 3, 5 * pr[p][1] + 3, 2, 2, Xdof(s[pr[p][0]]), Xdof(s[pr[p][1]]), true);
+            for (int v = 0; v < 4; ++v) {                                                                // :828-882
+                if (!eolv[v]) continue;
+                for (int w = v; w < 4; ++w) put(5 * v + 3, 5 * w, 2, 3, Xdof(s[v]), idx[w], true);       // fillXxB
+                for (int u = 0; u < v; ++u) put(5 * u, 5 * v + 3, 3, 2, idx[u], Xdof(s[v]), true);       // fillxXB
+            }
+            continue;
+        }
         for (int v = 0; v < 4; ++v)                                           // fillxB :886-893
             for (int j = 0; j < 3; ++j)
                 for (int k = 0; k < 3; ++k)
@@ -251,6 +431,12 @@ void *oracle_forces_fill(int N, int F, const int32_t *face_nodes, int E, const i
     R->seconds_elements = std::chrono::duration<double>(t1 - t0).count();
     R->seconds_assembly = std::chrono::duration<double>(t2 - t1).count();
     return R;
+}
+
+void *oracle_forces_fill(int N, int F, const int32_t *face_nodes, int E, const int32_t *edge_stencil,
+                         const double *x, const double *X, const double *mat, const double *grav, double h,
+                         int flags) {
+    return oracle_forces_fill_eol(N, F, face_nodes, E, edge_stencil, x, X, mat, grav, h, nullptr, flags);
 }
 
 int oracle_forces_dof(void *r) { return ((Result *)r)->dof; }

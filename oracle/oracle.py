@@ -59,6 +59,9 @@ def lib():
     L.oracle_forces_fill.restype = ctypes.c_void_p
     L.oracle_forces_fill.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_int, c_ip, c_dp, c_dp, c_dp, c_dp,
                                      ctypes.c_double, ctypes.c_int]
+    L.oracle_forces_fill_eol.restype = ctypes.c_void_p
+    L.oracle_forces_fill_eol.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, ctypes.c_int, c_ip, c_dp, c_dp, c_dp, c_dp,
+                                         ctypes.c_double, c_ip, ctypes.c_int]
     L.oracle_forces_dof.argtypes = [ctypes.c_void_p]
     L.oracle_forces_f.restype = c_dp
     L.oracle_forces_f.argtypes = [ctypes.c_void_p]
@@ -108,8 +111,9 @@ H_DEFAULT = 0.5e-2
 
 
 def forces_fill(face_nodes, edge_stencil, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_DEFAULT, h=H_DEFAULT,
-                skip_assembly=False):
-    """Reference Forces::fill on flat arrays.  Returns dict(f, M=(outer, inner, vals), MDK=..., seconds=(el, asm))."""
+                skip_assembly=False, eol_index=None):
+    """Reference Forces::fill on flat arrays.  Returns dict(f, M=(outer, inner, vals), MDK=..., seconds=(el, asm)).
+    eol_index (N ints, -1 = Lagrangian, k >= 0 = Node::EoL_index) switches the touched elements to the EOL branch."""
     L = lib()
     face_nodes = _i32(face_nodes).reshape(-1, 3)
     edge_stencil = _i32(edge_stencil).reshape(-1, 4)
@@ -118,8 +122,12 @@ def forces_fill(face_nodes, edge_stencil, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_
     N = x.shape[0]
     matv = _f64(mat)
     gv = _f64(grav)
-    r = L.oracle_forces_fill(N, face_nodes.shape[0], _i(face_nodes), edge_stencil.shape[0], _i(edge_stencil), _d(x),
-                             _d(X), _d(matv), _d(gv), float(h), 1 if skip_assembly else 0)
+    eol = None if eol_index is None else _i32(eol_index).reshape(N)
+    r = L.oracle_forces_fill_eol(N, face_nodes.shape[0], _i(face_nodes), edge_stencil.shape[0], _i(edge_stencil), _d(x),
+                                 _d(X), _d(matv), _d(gv), float(h), None if eol is None else _i(eol),
+                                 1 if skip_assembly else 0)
+    if not r:
+        raise RuntimeError("oracle_forces_fill_eol: a bending stencil names a face the mesh does not have")
     try:
         dof = L.oracle_forces_dof(r)
         out = {"dof": dof, "f": np.ctypeslib.as_array(L.oracle_forces_f(r), (dof,)).copy(),
