@@ -33,9 +33,10 @@ void Forces::fill(const Mesh &mesh, const Material &mat, const Eigen::Vector3d &
     // Flatten the ArcSim pointer mesh.  flatten() re-reads the topology every call; fill() hashes it and
     // rebuilds the device plan only when it changed (dynamic_remesh / preprocess, Scene.cpp:83-90).
     eolc::host::flatten(mesh, B.flat);
-    if (B.flat.EoL_Count != 0) {
-        // The Eulerian-on-Lagrangian element blocks (Forces.cpp:177-329, 399-497, 580-683, 746-883) are not on the B200 path yet.
-        std::cout << "Forces::fill (B200): mesh has EoL nodes; build with the reference Forces.cpp for EOL scenes" << std::endl;
+    // EoL nodes (flat.eol_index) switch the touched elements to the Eulerian-on-Lagrangian blocks (Forces.cpp:177-329, 399-497,
+    // 580-683, 746-883) inside the library; dof = 3N + 2 (1 + largest EoL_index) must agree with mesh.EoL_Count.
+    if ((int)mesh.EoL_Count != B.flat.EoL_Count) {
+        std::cout << "Forces::fill (B200): mesh.EoL_Count does not match the nodes flagged EoL" << std::endl;
         abort();
     }
     eolc_material m = {mat.density, mat.e, mat.nu, mat.beta, mat.dampingA, mat.dampingB};

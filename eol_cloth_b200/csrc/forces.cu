@@ -1,7 +1,8 @@
 // forces.cu — Forces::fill on the GPU (include/eolc.h, "Forces::fill" section).
 //
-// Replaces /root/reference/src/Forces.cpp:912-930 (fill), :331-520 (faceBasedF, non-EOL branch),
-// :685-910 (edgeBasedF, non-EOL branch) and Eigen's setFromTriplets.
+// Replaces /root/reference/src/Forces.cpp:912-930 (fill), :331-520 (faceBasedF), :685-910 (edgeBasedF) and Eigen's
+// setFromTriplets.  The Lagrangian 3N x 3N part of M / MDK and the face forces come from the pipelines below; meshes with EoL
+// nodes add the two small kernels at the end of this file (eol_elements_kernel, eol_gather_kernel — design in forces_eol.h).
 //
 // Default pipeline "tiles" (one persistent kernel, no HBM scratch) — assemble_tiles_kernel:
 //   the nodes are partitioned into spatially compact tiles (forces_plan.h).  One CTA per SM walks its tiles; for each tile
@@ -19,6 +20,7 @@
 #include "elements.cuh"
 #include "forces_plan.h"
 #include "tile_exec.cuh"
+#include "forces_eol.h"
 #include "solve.cuh"
 #include <algorithm>
 #include <cmath>
@@ -39,6 +41,13 @@ struct eolc_forces_plan {
     Pattern pat;                                  // block pattern of M and MDK
     std::vector<int32_t> h_outerM, h_innerM, h_outerK, h_innerK;  // lazily built Eigen-style arrays
     int pipeline = 0;                             // 0 = tiles, 1 = rows
+    // EOL branch (forces_eol.h); n_eol == 0: Lagrangian mesh, nothing of this is used
+    int32_t n_eol = 0, eol_faces = 0, eol_edges = 0, eol_targets = 0;
+    int64_t eol_scratch = 0;
+    DevBuf<int32_t> d_eol_faces, d_eol_edges;
+    DevBuf<eol::Target> d_eol_targets;
+    DevBuf<uint32_t> d_eol_sources;
+    DevBuf<double> d_eol_scratch;                 // eol_scratch doubles per scene
     bool smem_attr_set = false;
     // "tiles" pipeline
     int32_t n_tiles = 0, n_templates = 0;
@@ -337,11 +346,11 @@ size_t tiles_smem_bytes(const eolc_forces_plan *P) {
     return tiles_smem_layout(P->scr_doubles, P->kstage, P->mstage, P->tmplA16, P->tmplB16, P->geo16, P->loc_max).total;
 }
 
-int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st) {
+int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st, const tiles::RowLayout *rows) {
     tiles::Plan tp;
     const char *dd = getenv("EOLC_FORCES_DEDUP");
     const bool dedup = !(dd && strcmp(dd, "0") == 0);
-    if (!tiles::build(P->N, P->F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), P->pat, X_hint, dedup, tp)) {
+    if (!tiles::build(P->N, P->F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), P->pat, X_hint, dedup, tp, rows)) {
         set_error("tile plan: %s", tp.error.c_str());
         return EOLC_ERR_UNSUPPORTED;
     }
@@ -744,6 +753,81 @@ int build_rows_plan(eolc_forces_plan *P, cudaStream_t st) {
     return EOLC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// EOL branch (forces_eol.h): the elements that touch an EoL node, and the Eulerian rows / columns they feed
+// ------------------------------------------------------------------------------------------------
+struct EolArgs {
+    int32_t n_faces, n_edges, n_targets, n_scenes;
+    uint32_t lag_dof;
+    const int32_t *faces, *edges;
+    const eol::Target *targets;
+    const uint32_t *sources;
+    const double *x, *X;
+    double *scratch, *f, *Mv, *Kv;
+    size_t x_stride, X_stride, f_stride, M_stride, K_stride, scratch_stride;
+    eol::Params prm;
+};
+
+// one thread per (scene, EOL element): the element's Eulerian expansion into its scratch record
+__global__ void __launch_bounds__(128) eol_elements_kernel(EolArgs A) {
+    const long long per = (long long)A.n_faces + A.n_edges;
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= per * A.n_scenes) return;
+    const int s = (int)(w / per), i = (int)(w % per);
+    const double *x = A.x + (size_t)s * A.x_stride, *X = A.X + (size_t)s * A.X_stride;
+    double *scr = A.scratch + (size_t)s * A.scratch_stride;
+    if (i < A.n_faces) eol::face_record(A.faces + 4 * (size_t)i, x, X, A.prm, scr + (size_t)i * eol::FACE_REC);
+    else eol::edge_record(A.edges + 8 * (size_t)(i - A.n_faces), x, X, A.prm, scr + (size_t)A.n_faces * eol::FACE_REC + (size_t)(i - A.n_faces) * eol::EDGE_REC);
+}
+
+// one thread per (scene, Eulerian entry): fixed-order sum of its contributions, written once
+__global__ void __launch_bounds__(128) eol_gather_kernel(EolArgs A) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= (long long)A.n_targets * A.n_scenes) return;
+    const int s = (int)(w / A.n_targets), t = (int)(w % A.n_targets);
+    eol::gather_target(A.targets[t], A.sources, A.scratch + (size_t)s * A.scratch_stride, A.lag_dof, A.f + (size_t)s * A.f_stride,
+                       A.Mv + (size_t)s * A.M_stride, A.Kv + (size_t)s * A.K_stride);
+}
+
+int build_eol_plan(eolc_forces_plan *P, const int32_t *eol_index, eol::Plan &ep, cudaStream_t st) {
+    if (!eol::build(P->N, P->F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), eol_index, P->pat.blkptrM, P->pat.nbrM, P->pat.blkptrK, P->pat.nbrK, ep)) {
+        set_error("EOL plan: %s", ep.error.c_str());
+        return EOLC_ERR_UNSUPPORTED;
+    }
+    P->n_eol = ep.n_eol; P->dof = ep.dof; P->nnzM = ep.nnzM; P->nnzK = ep.nnzK;
+    P->eol_faces = ep.n_faces(); P->eol_edges = ep.n_edges(); P->eol_targets = (int32_t)ep.targets.size(); P->eol_scratch = ep.scratch_doubles;
+    EOLC_CUDA(P->d_eol_faces.alloc(ep.faces.size())); EOLC_CUDA(P->d_eol_edges.alloc(ep.edges.size()));
+    EOLC_CUDA(P->d_eol_targets.alloc(ep.targets.size())); EOLC_CUDA(P->d_eol_sources.alloc(ep.sources.size()));
+    if (!ep.faces.empty()) EOLC_CUDA(cudaMemcpyAsync(P->d_eol_faces.p, ep.faces.data(), ep.faces.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!ep.edges.empty()) EOLC_CUDA(cudaMemcpyAsync(P->d_eol_edges.p, ep.edges.data(), ep.edges.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!ep.targets.empty()) EOLC_CUDA(cudaMemcpyAsync(P->d_eol_targets.p, ep.targets.data(), ep.targets.size() * sizeof(eol::Target), cudaMemcpyHostToDevice, st));
+    if (!ep.sources.empty()) EOLC_CUDA(cudaMemcpyAsync(P->d_eol_sources.p, ep.sources.data(), ep.sources.size() * 4, cudaMemcpyHostToDevice, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));
+    P->h_outerM.swap(ep.outerM); P->h_innerM.swap(ep.innerM); P->h_outerK.swap(ep.outerK); P->h_innerK.swap(ep.innerK);
+    return EOLC_OK;
+}
+
+// after the Lagrangian kernel, same stream: records, then the gather (which also adds the bending force onto f)
+int launch_eol(eolc_forces_plan *P, int32_t S, const double *x, const double *X, const eolc_material *mat, const double *grav, double dhh,
+               double *f, double *Mv, double *Kv) {
+    cudaStream_t st = P->ctx->stream;
+    EOLC_CUDA(P->d_eol_scratch.ensure((size_t)std::max<int64_t>(P->eol_scratch, 1) * S));
+    EolArgs A;
+    A.n_faces = P->eol_faces; A.n_edges = P->eol_edges; A.n_targets = P->eol_targets; A.n_scenes = S; A.lag_dof = 3u * (uint32_t)P->N;
+    A.faces = P->d_eol_faces.p; A.edges = P->d_eol_edges.p; A.targets = P->d_eol_targets.p; A.sources = P->d_eol_sources.p;
+    A.x = x; A.X = X; A.scratch = P->d_eol_scratch.p; A.f = f; A.Mv = Mv; A.Kv = Kv;
+    A.x_stride = (size_t)3 * P->N; A.X_stride = (size_t)2 * P->N; A.f_stride = (size_t)P->dof; A.M_stride = (size_t)P->nnzM; A.K_stride = (size_t)P->nnzK;
+    A.scratch_stride = (size_t)P->eol_scratch;
+    A.prm.e = mat->e; A.prm.nu = mat->nu; A.prm.rho = mat->density; A.prm.beta = mat->beta; A.prm.gx = grav[0]; A.prm.gy = grav[1]; A.prm.gz = grav[2];
+    A.prm.dhh = dhh;
+    const long long n_el = ((long long)P->eol_faces + P->eol_edges) * S, n_t = (long long)P->eol_targets * S;
+    if (n_el > 0) eol_elements_kernel<<<(unsigned)((n_el + 127) / 128), 128, 0, st>>>(A);
+    if (n_t > 0) eol_gather_kernel<<<(unsigned)((n_t + 127) / 128), 128, 0, st>>>(A);
+    EOLC_CUDA(cudaGetLastError());
+    return EOLC_OK;
+}
+
 int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X, const eolc_material *mat,
                 const double *grav, double h, double *f, double *Mv, double *Kv) {
     cudaStream_t st = P->ctx->stream;
@@ -775,7 +859,7 @@ int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X
 #endif
         assemble_tiles_kernel<<<grid, tiles::CTA_THREADS, smem, st>>>(A);
         EOLC_CUDA(cudaGetLastError());
-        return EOLC_OK;
+        return P->n_eol ? launch_eol(P, S, x, X, mat, grav, dhh, f, Mv, Kv) : EOLC_OK;
     }
     {
         const long long n_tiles = (long long)P->n_cta * S;
@@ -807,12 +891,12 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
     EOLC_REQUIRE(F == 0 || face_nodes, "face_nodes is NULL");
     EOLC_REQUIRE(E == 0 || edge_stencil, "edge_stencil is NULL");
     EOLC_REQUIRE((int64_t)N * 3 < INT32_MAX && (int64_t)F < (1 << 25) && (int64_t)E < (1 << 25), "mesh too large for int32 indexing");
+    bool has_eol = false;
     if (eol_index)
-        for (int32_t a = 0; a < N; ++a)
-            if (eol_index[a] >= 0) {
-                set_error("node %d is an EOL node: only the Lagrangian branch of Forces::fill is implemented", a);
-                return EOLC_ERR_UNSUPPORTED;
-            }
+        for (int32_t a = 0; a < N; ++a) {
+            EOLC_REQUIRE(eol_index[a] >= -1 && eol_index[a] < N, "eol_index out of range");
+            has_eol |= eol_index[a] >= 0;
+        }
     for (int64_t i = 0; i < 3 * (int64_t)F; ++i) EOLC_REQUIRE(face_nodes[i] >= 0 && face_nodes[i] < N, "face node index out of range");
     for (int32_t i = 0; i < F; ++i) {
         const int32_t *v = face_nodes + 3 * (size_t)i;
@@ -837,7 +921,18 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
     cudaStream_t st = ctx->stream;
     const char *pe = getenv("EOLC_FORCES_PIPELINE");
     P->pipeline = (pe && strcmp(pe, "rows") == 0) ? 1 : 0;
-    int rc = P->pipeline == 0 ? build_tiles_plan(P, X_hint, st) : build_rows_plan(P, st);
+    int rc;
+    if (has_eol) {
+        if (P->pipeline != 0) { delete P; set_error("EOL nodes need the tiles pipeline"); return EOLC_ERR_UNSUPPORTED; }
+        eol::Plan ep;
+        rc = build_eol_plan(P, eol_index, ep, st);
+        if (!rc) {
+            const tiles::RowLayout rows{ep.dstM.data(), ep.dstK.data(), ep.extraM.data(), ep.extraK.data()};
+            rc = build_tiles_plan(P, X_hint, st, &rows);
+        }
+    } else {
+        rc = P->pipeline == 0 ? build_tiles_plan(P, X_hint, st, nullptr) : build_rows_plan(P, st);
+    }
     if (rc) { delete P; return rc; }
     *out = P;
     return EOLC_OK;
@@ -884,6 +979,7 @@ int eolc_debug_tile_clocks(eolc_forces_plan *plan, unsigned long long *out, int 
 
 // ---- consumer of the fill on the device: right-hand side and the collision-free CG branch (solve.cuh) ----
 static int ensure_block_structure(eolc_forces_plan *P) {
+    if (P->n_eol) { set_error("the device consumers (rhs / CG / integrate) work on the Lagrangian block structure; this plan has EoL nodes"); return EOLC_ERR_UNSUPPORTED; }
     if (P->d_blkK.p || P->N == 0) return EOLC_OK;
     cudaStream_t st = P->ctx->stream;
     std::vector<int32_t> bm(P->pat.blkptrM.begin(), P->pat.blkptrM.end()), bk(P->pat.blkptrK.begin(), P->pat.blkptrK.end());
@@ -966,7 +1062,7 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
     return EOLC_OK;
 }
 
-int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return plan ? 1 : 0; }
+int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return !plan ? 0 : plan->n_eol ? 3 : 1; }
 
 int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
                                  const eolc_material *mat, const double grav[3], double h, double *f_dev,
@@ -992,9 +1088,9 @@ int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, c
     EOLC_REQUIRE(P->nnzM == 0 || (M_vals && MDK_vals), "NULL host pointer");
     EOLC_CUDA(cudaSetDevice(P->ctx->device));
     cudaStream_t st = P->ctx->stream;
-    const size_t N = P->N;
+    const size_t N = P->N, nf = (size_t)P->dof;
     if (N == 0) return EOLC_OK;
-    EOLC_CUDA(P->d_x.ensure(3 * N)); EOLC_CUDA(P->d_X.ensure(2 * N)); EOLC_CUDA(P->d_f.ensure(3 * N));
+    EOLC_CUDA(P->d_x.ensure(3 * N)); EOLC_CUDA(P->d_X.ensure(2 * N)); EOLC_CUDA(P->d_f.ensure(nf));
     EOLC_CUDA(P->d_Mv.ensure(P->nnzM)); EOLC_CUDA(P->d_Kv.ensure(P->nnzK));
     // pinned (or registered) caller buffers are DMA'd directly; pageable ones go through the plan's pinned staging
     auto pinned = [](const void *p) {
@@ -1017,15 +1113,15 @@ int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, c
     if (rc) return rc;
     double *hf = f, *hM = M_vals, *hK = MDK_vals;
     if (!out_pinned) {
-        EOLC_CUDA(P->p_out.ensure(3 * N + P->nnzM + P->nnzK));
-        hf = P->p_out.p; hM = P->p_out.p + 3 * N; hK = P->p_out.p + 3 * N + P->nnzM;
+        EOLC_CUDA(P->p_out.ensure(nf + P->nnzM + P->nnzK));
+        hf = P->p_out.p; hM = P->p_out.p + nf; hK = P->p_out.p + nf + P->nnzM;
     }
-    EOLC_CUDA(cudaMemcpyAsync(hf, P->d_f.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaMemcpyAsync(hf, P->d_f.p, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
     EOLC_CUDA(cudaMemcpyAsync(hM, P->d_Mv.p, P->nnzM * sizeof(double), cudaMemcpyDeviceToHost, st));
     EOLC_CUDA(cudaMemcpyAsync(hK, P->d_Kv.p, P->nnzK * sizeof(double), cudaMemcpyDeviceToHost, st));
     EOLC_CUDA(cudaStreamSynchronize(st));
     if (!out_pinned) {
-        memcpy(f, hf, 3 * N * sizeof(double));
+        memcpy(f, hf, nf * sizeof(double));
         memcpy(M_vals, hM, P->nnzM * sizeof(double));
         memcpy(MDK_vals, hK, P->nnzK * sizeof(double));
     }

@@ -439,8 +439,15 @@ inline void optimize_template(uint32_t *T, uint32_t sizeA16, int iters) {
     }
 }
 
+// Where the rows of M / MDK go when they are not simply 9 * blkptr[node] apart: EOL meshes (forces_eol.h), whose Lagrangian rows
+// carry `extra` Eulerian columns behind their 3x3 blocks.  dst = value index of the node's first scalar row.
+struct RowLayout {
+    const int64_t *dstM, *dstK;
+    const int32_t *extraM, *extraK;
+};
+
 inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie, const Pattern &pat, const double *X_hint, bool dedup,
-                  Plan &P) {
+                  Plan &P, const RowLayout *rows = nullptr) {
     P = Plan();
     if (N == 0) return true;
     const NodeCSR csr(N, F, fn, Ei, ie);
@@ -596,14 +603,28 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                         return kind == 0 ? 9u * (uint32_t)(pat.blkptrK[own[q] + 1] - pat.blkptrK[own[q]])
                              : kind == 1 ? 9u * (uint32_t)(pat.blkptrM[own[q] + 1] - pat.blkptrM[own[q]]) : 3u;
                     };
-                    const uint64_t dst = kind == 0 ? (uint64_t)(9 * pat.blkptrK[own[o]]) : kind == 1 ? (uint64_t)(9 * pat.blkptrM[own[o]]) : (uint64_t)3 * (uint64_t)own[o];
+                    // destination of the node's first scalar row; with Eulerian columns (EOL meshes, forces_eol.h) a node's three
+                    // scalar rows are `extra` entries apart and leave as three runs, everything else as before
+                    const int32_t xtra = !rows ? 0 : kind == 0 ? rows->extraK[own[o]] : kind == 1 ? rows->extraM[own[o]] : 0;
+                    const uint64_t dst = kind == 2 ? (uint64_t)3 * (uint64_t)own[o]
+                                       : rows ? (uint64_t)(kind == 0 ? rows->dstK[own[o]] : rows->dstM[own[o]])
+                                              : (uint64_t)(9 * (kind == 0 ? pat.blkptrK[own[o]] : pat.blkptrM[own[o]]));
                     cur = ((cur + 1u) & ~1u) + (uint32_t)(dst & 1u);      // even slot + the destination's parity
                     const uint32_t src = cur;
                     int o1 = o;
+                    if (xtra) {        // extra is even, so the three rows keep the parity relation of the first
+                        if (kind == 0) offsKM[o] |= cur; else offsKM[o] |= cur << 16;
+                        const uint32_t row = len_of(o) / 3u;
+                        for (uint32_t j = 0; j < 3u && row; ++j) runs.push_back({dst + (uint64_t)j * (row + (uint32_t)xtra), (uint32_t)kind, src + j * row, row});
+                        cur += 3u * row;
+                        o = o + 1;
+                        continue;
+                    }
                     for (;;) {
                         if (kind == 0) offsKM[o1] |= cur; else if (kind == 1) offsKM[o1] |= cur << 16; else offsF[o1] = cur;
                         cur += len_of(o1);
-                        if (o1 + 1 < n_own && own[o1 + 1] == own[o1] + 1) ++o1; else break;
+                        if (o1 + 1 < n_own && own[o1 + 1] == own[o1] + 1 &&
+                            !(rows && kind != 2 && (kind == 0 ? rows->extraK[own[o1 + 1]] : rows->extraM[own[o1 + 1]]))) ++o1; else break;
                     }
                     if (cur - src) runs.push_back({dst, (uint32_t)kind, src, cur - src});
                     o = o1 + 1;

@@ -37,7 +37,9 @@ class ForcesPlan:
             ctx.handle, int(n_nodes), fn.shape[0], capi.iptr(fn), es.shape[0], capi.iptr(es),
             None if eol is None else capi.iptr(eol), None if xh is None else capi.dptr(xh), ctypes.byref(self._h)))
         self.N = int(n_nodes)
-        self.dof = 3 * self.N
+        dof = ctypes.c_int32()
+        capi.check(capi.lib().eolc_forces_pattern(self._h, 0, ctypes.byref(dof), None, None, None))
+        self.dof = dof.value           # 3N + 2 EoL_Count (Forces.cpp:914)
         nf, ne = ctypes.c_int32(), ctypes.c_int32()
         capi.check(capi.lib().eolc_forces_counts(self._h, ctypes.byref(nf), ctypes.byref(ne)))
         self.n_faces, self.n_interior_edges = nf.value, ne.value
@@ -137,16 +139,18 @@ class Forces:
         self._topo_key = None
 
     def fill(self, mesh, mat, grav, h):
-        """mesh: dict(x (N,3), X (N,2), face_nodes (F,3), edge_stencil (E,4)) — the flattened ArcSim mesh
-        (SURVEY Appendix B).  The topology plan is cached and rebuilt when the topology arrays change (remesh)."""
+        """mesh: dict(x (N,3), X (N,2), face_nodes (F,3), edge_stencil (E,4)[, eol_index (N,): Node::EoL_index, -1 = Lagrangian]) —
+        the flattened ArcSim mesh.  The topology plan is cached and rebuilt when the topology arrays change (remesh)."""
         fn = capi.i32(mesh["face_nodes"]).reshape(-1, 3)
         es = capi.i32(mesh["edge_stencil"]).reshape(-1, 4)
         N = np.asarray(mesh["x"]).reshape(-1, 3).shape[0]
-        key = (N, fn.shape[0], es.shape[0], hash(fn.tobytes()), hash(es.tobytes()))
+        eol = mesh.get("eol_index")
+        eol = None if eol is None else capi.i32(eol)
+        key = (N, fn.shape[0], es.shape[0], hash(fn.tobytes()), hash(es.tobytes()), None if eol is None else hash(eol.tobytes()))
         if key != self._topo_key:
             if self._plan is not None:
                 self._plan.close()
-            self._plan = ForcesPlan(self.ctx, N, fn, es, mesh.get("eol_index"), mesh.get("X"))
+            self._plan = ForcesPlan(self.ctx, N, fn, es, eol, mesh.get("X"))
             self._topo_key = key
             self._pat = [self._plan.pattern(0), self._plan.pattern(1)]
         f, Mv, Kv = self._plan.fill(mesh["x"], mesh["X"], mat, grav, h)

@@ -28,7 +28,7 @@ def hostmath():
     d = os.path.join(ROOT, "tests", "hostmath")
     so = os.path.join(d, "libhostmath.so")
     src = os.path.join(d, "hostmath.cpp")
-    deps = [src, os.path.join(ROOT, "eol_cloth_b200", "csrc", "elements.cuh"), os.path.join(ROOT, "eol_cloth_b200", "csrc", "cd_math.cuh"), os.path.join(ROOT, "eol_cloth_b200", "csrc", "forces_plan.h"), os.path.join(ROOT, "eol_cloth_b200", "csrc", "tile_exec.cuh")]
+    deps = [src, os.path.join(ROOT, "eol_cloth_b200", "csrc", "elements.cuh"), os.path.join(ROOT, "eol_cloth_b200", "csrc", "cd_math.cuh"), os.path.join(ROOT, "eol_cloth_b200", "csrc", "forces_plan.h"), os.path.join(ROOT, "eol_cloth_b200", "csrc", "tile_exec.cuh"), os.path.join(ROOT, "eol_cloth_b200", "csrc", "forces_eol.h")]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++14", "-pthread", "-o", so, src])
     return ctypes.CDLL(so)

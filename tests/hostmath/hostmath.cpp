@@ -4,6 +4,7 @@
 #include "../../eol_cloth_b200/csrc/elements.cuh"
 #include "../../eol_cloth_b200/csrc/forces_plan.h"
 #include "../../eol_cloth_b200/csrc/tile_exec.cuh"
+#include "../../eol_cloth_b200/csrc/forces_eol.h"
 using namespace eolc;
 extern "C" {
 void hostmath_face(const double *xa, const double *xb, const double *xc, const double *Xa, const double *Xb,
@@ -41,6 +42,14 @@ void hostmath_edge_row(int i, const double *x0, const double *x1, const double *
     for (int b = 0; b < 4; ++b) for (int k = 0; k < 9; ++k) K4x9[9 * b + k] = o.K[b].m[k];
 }
 
+void hostmath_edge_force(const double *x0, const double *x1, const double *x2, const double *x3, const double *X0,
+                         const double *X1, const double *X2, const double *X3, double beta, double *f12) {
+    v3 f[4];
+    eol::edge_force(mk3(x0[0], x0[1], x0[2]), mk3(x1[0], x1[1], x1[2]), mk3(x2[0], x2[1], x2[2]), mk3(x3[0], x3[1], x3[2]),
+                    X0[0], X0[1], X1[0], X1[1], X2[0], X2[1], X3[0], X3[1], beta, f);
+    for (int i = 0; i < 4; ++i) { f12[3 * i] = f[i].x; f12[3 * i + 1] = f[i].y; f12[3 * i + 2] = f[i].z; }
+}
+
 // tiles pipeline element forms
 struct CollectEdge {
     double *K;   // 10 x 9: 00,11,22,33,01,02,03,12,13,23
@@ -75,20 +84,38 @@ struct HmPlan {
     std::vector<int32_t> fn, ie;
     Pattern pat;
     tiles::Plan tp;
+    bool has_eol = false;
+    eol::Plan ep;
 };
-void *hm_plan_create(int32_t N, int32_t F, const int32_t *fn, int32_t E, const int32_t *es, const double *X_hint, int dedup, char *err, int errlen) {
+// eol_index: N ints (-1 = Lagrangian) or NULL
+void *hm_plan_create_eol(int32_t N, int32_t F, const int32_t *fn, int32_t E, const int32_t *es, const double *X_hint, int dedup, const int32_t *eol_index,
+                         char *err, int errlen) {
     HmPlan *P = new HmPlan;
     P->N = N; P->F = F;
     P->fn.assign(fn, fn + 3 * (size_t)F);
     if (!extract_interior_edges(N, E, es, P->ie)) { snprintf(err, errlen, "bad stencil"); delete P; return nullptr; }
     P->Ei = (int32_t)(P->ie.size() / 4);
     build_pattern(N, F, P->fn.data(), P->Ei, P->ie.data(), P->pat);
-    if (!tiles::build(N, F, P->fn.data(), P->Ei, P->ie.data(), P->pat, X_hint, dedup != 0, P->tp)) {
+    tiles::RowLayout rows, *prows = nullptr;
+    if (eol_index) for (int32_t a = 0; a < N; ++a) P->has_eol |= eol_index[a] >= 0;
+    if (P->has_eol) {
+        if (!eol::build(N, F, P->fn.data(), P->Ei, P->ie.data(), eol_index, P->pat.blkptrM, P->pat.nbrM, P->pat.blkptrK, P->pat.nbrK, P->ep)) {
+            snprintf(err, errlen, "%s", P->ep.error.c_str());
+            delete P;
+            return nullptr;
+        }
+        rows.dstM = P->ep.dstM.data(); rows.dstK = P->ep.dstK.data(); rows.extraM = P->ep.extraM.data(); rows.extraK = P->ep.extraK.data();
+        prows = &rows;
+    }
+    if (!tiles::build(N, F, P->fn.data(), P->Ei, P->ie.data(), P->pat, X_hint, dedup != 0, P->tp, prows)) {
         snprintf(err, errlen, "%s", P->tp.error.c_str());
         delete P;
         return nullptr;
     }
     return P;
+}
+void *hm_plan_create(int32_t N, int32_t F, const int32_t *fn, int32_t E, const int32_t *es, const double *X_hint, int dedup, char *err, int errlen) {
+    return hm_plan_create_eol(N, F, fn, E, es, X_hint, dedup, nullptr, err, errlen);
 }
 void hm_plan_destroy(void *p) { delete (HmPlan *)p; }
 // info[16]: nnzM, nnzK, n_tiles, n_templates, elem_evals, geo bytes, template bytes, max scratch doubles, max loc, Ei, runs, groups, pull rows, max staging
@@ -96,10 +123,18 @@ void hm_plan_info(void *p, int64_t *info) {
     HmPlan *P = (HmPlan *)p;
     info[0] = 9 * P->pat.nblkM; info[1] = 9 * P->pat.nblkK; info[2] = P->tp.n_tiles; info[3] = P->tp.n_templates; info[4] = P->tp.elem_evals;
     info[5] = (int64_t)P->tp.geo.size() * 4; info[6] = (int64_t)P->tp.tmpl.size() * 4; info[7] = P->tp.max_scratch; info[8] = P->tp.max_loc;
+    if (P->has_eol) { info[0] = P->ep.nnzM; info[1] = P->ep.nnzK; }
+    info[15] = P->has_eol ? P->ep.dof : 3 * P->N;
     info[9] = P->Ei; info[10] = P->tp.n_runs; info[11] = P->tp.n_groups; info[12] = P->tp.pull_rows; info[13] = P->tp.max_kstage; info[14] = P->tp.max_mstage;
 }
 void hm_plan_pattern(void *p, int which, int32_t *outer, int32_t *inner) {
     HmPlan *P = (HmPlan *)p;
+    if (P->has_eol) {
+        const std::vector<int32_t> &eo = which ? P->ep.outerK : P->ep.outerM, &ei = which ? P->ep.innerK : P->ep.innerM;
+        memcpy(outer, eo.data(), eo.size() * 4);
+        if (!ei.empty()) memcpy(inner, ei.data(), ei.size() * 4);
+        return;
+    }
     std::vector<int32_t> o, in;
     build_eigen_arrays(P->N, which ? P->pat.blkptrK : P->pat.blkptrM, which ? P->pat.nbrK : P->pat.nbrM, o, in);
     memcpy(outer, o.data(), o.size() * 4);
@@ -203,6 +238,15 @@ int hm_plan_fill(void *p, const double *x, const double *X, const double *mat6, 
         for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::phase2(tid, tiles::P2THREADS, V, m_full);
         for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::phase3(tid, tiles::P2THREADS, V);
         for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::copy_out_runs(tid, tiles::P2THREADS, V, f, Mv, Kv, 7u, HostBulk{&ok});
+    }
+    if (P->has_eol) {   // the two EOL kernels of forces.cu, one "thread" after the other
+        const eol::Plan &ep = P->ep;
+        eol::Params ep_prm{mat6[1], mat6[2], mat6[0], mat6[3], grav[0], grav[1], grav[2], mat6[5] * h * h};
+        std::vector<double> scratch((size_t)ep.scratch_doubles, 1e300);
+        for (int32_t i = 0; i < ep.n_faces(); ++i) eol::face_record(ep.faces.data() + 4 * (size_t)i, x, X, ep_prm, scratch.data() + (size_t)i * eol::FACE_REC);
+        for (int32_t i = 0; i < ep.n_edges(); ++i)
+            eol::edge_record(ep.edges.data() + 8 * (size_t)i, x, X, ep_prm, scratch.data() + (size_t)ep.n_faces() * eol::FACE_REC + (size_t)i * eol::EDGE_REC);
+        for (const eol::Target &t : ep.targets) eol::gather_target(t, ep.sources.data(), scratch.data(), 3u * (uint32_t)P->N, f, Mv, Kv);
     }
     return ok ? 0 : -1;
 }

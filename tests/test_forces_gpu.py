@@ -114,7 +114,9 @@ def test_errors(ctx):
     with pytest.raises(E.EolcError):
         E.ForcesPlan(ctx, 3, np.array([[0, 1, 1]], np.int32), np.zeros((0, 4), np.int32))     # degenerate face
     with pytest.raises(E.EolcError):
-        E.ForcesPlan(ctx, 3, np.array([[0, 1, 2]], np.int32), np.zeros((0, 4), np.int32), eol_index=np.array([-1, 0, -1], np.int32))
+        E.ForcesPlan(ctx, 3, np.array([[0, 1, 2]], np.int32), np.zeros((0, 4), np.int32), eol_index=np.array([-1, 0, 0], np.int32))   # EoL_index used twice
+    with pytest.raises(E.EolcError):
+        E.ForcesPlan(ctx, 3, np.array([[0, 1, 2]], np.int32), np.zeros((0, 4), np.int32), eol_index=np.array([-1, -2, 0], np.int32))
 
 
 def test_reproducible_and_dev_equals_host(ctx):
@@ -187,3 +189,74 @@ def test_fullsize_1024_properties(ctx):
     assert abs(M.sum() - 3 * 0.05 * 1.0) < 1e-12
     fz = forces.f.reshape(-1, 3).sum(axis=0)
     assert abs(fz[2] - (-9.8 * 0.05)) < 1e-9 and abs(fz[0]) < 1e-9 and abs(fz[1]) < 1e-9
+
+
+# ---- EOL branch: forces_eol.h ---------------------------------------------------------------------
+def _eol_mesh(gen, n, eol_nodes, seed=0):
+    mesh = _mesh(gen, n, seed)
+    N = mesh["x"].shape[0]
+    eol = np.full(N, -1, np.int32)
+    if isinstance(eol_nodes, str):            # "line": the nodes of the grid line j = n // 2, EoL indices in a shuffled order
+        line = np.arange(1, n - 1) * n + n // 2
+        eol[line] = np.random.default_rng(n).permutation(line.size)
+    else:
+        for k, a in enumerate(eol_nodes):
+            eol[a] = k
+    mesh["eol_index"] = eol
+    return mesh
+
+
+@pytest.mark.parametrize("gen,n,eol_nodes", [("regular2", 5, (12, 6, 18, 7)), ("regular2", 4, (5,)), ("build4", 3, (4, 9, 10, 1)),
+                                             ("regular2", 3, tuple(range(9))), ("regular2", 24, "line"), ("regular2", 64, "line"),
+                                             ("build4", 9, (0, 80, 40, 100))])
+def test_eol_fill_matches_oracle(ctx, oracle, gen, n, eol_nodes):
+    """Elements touching an EoL node take the EOL branch (Forces.cpp:399-497, 746-883): dof = 3N + 2 EoL_Count, Eulerian rows / columns
+    in M and MDK, the bending force in f.  Patterns bit-exact, values to 1e-10 against the oracle's restatement."""
+    mesh = _eol_mesh(gen, n, eol_nodes, seed=n)
+    N = mesh["x"].shape[0]
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    ref = oracle.forces_fill(mesh["face_nodes"], mesh["edge_stencil"], mesh["x"], mesh["X"], tuple(MAT), GRAV, H, eol_index=mesh["eol_index"])
+    assert forces.f.size == ref["dof"] == 3 * N + 2 * (int(mesh["eol_index"].max()) + 1)
+    assert forces.EoL_cutoff == 3 * N
+    _check(forces, ref, N, f"eol {gen}{n}")
+    # same plan, second state: the Eulerian entries are rewritten, not accumulated
+    mesh2 = dict(mesh, x=E.meshgen.drape_state(mesh["X"], seed=n + 100))
+    forces.fill(mesh2, MAT, GRAV, H)
+    ref2 = oracle.forces_fill(mesh["face_nodes"], mesh["edge_stencil"], mesh2["x"], mesh["X"], tuple(MAT), GRAV, H, eol_index=mesh["eol_index"])
+    _check(forces, ref2, N, f"eol {gen}{n} second state")
+
+
+def test_eol_256_line_and_batched(ctx, oracle):
+    """256x256 sheet with a line of 254 EoL nodes (the cloth crossing a box edge): full comparison, run-to-run bit reproducibility, and the
+    batched device API on two scenes (per-scene scratch records)."""
+    import torch
+    mesh = _eol_mesh("regular2", 256, "line")
+    N = mesh["x"].shape[0]
+    plan = E.ForcesPlan(ctx, N, mesh["face_nodes"], mesh["edge_stencil"], eol_index=mesh["eol_index"], X_hint=mesh["X"])
+    assert plan.dof == 3 * N + 2 * 254 and plan.launches_per_fill == 3
+    ref = oracle.forces_fill(mesh["face_nodes"], mesh["edge_stencil"], mesh["x"], mesh["X"], tuple(MAT), GRAV, H, eol_index=mesh["eol_index"])
+    f, Mv, Kv = plan.fill(mesh["x"], mesh["X"], MAT, GRAV, H)
+    f2, Mv2, Kv2 = plan.fill(mesh["x"], mesh["X"], MAT, GRAV, H)
+    assert f.tobytes() == f2.tobytes() and Mv.tobytes() == Mv2.tobytes() and Kv.tobytes() == Kv2.tobytes()
+    assert_close_tol(f, ref["f"], np.abs(ref["f"]).max(), TOL, "eol256 f")
+    for which, name, got in ((0, "M", Mv), (1, "MDK", Kv)):
+        o, i, v = ref[name]
+        po, pi = plan.pattern(which)
+        assert np.array_equal(po, o) and np.array_equal(pi, i)
+        assert_close_tol(got, v, block_row_scale(o, v, N), TOL, "eol256 " + name)
+    x2 = E.meshgen.drape_state(mesh["X"], seed=9)
+    dev = torch.device("cuda", ctx.device)
+    xs = torch.from_numpy(np.stack([mesh["x"], x2])).to(dev).contiguous()
+    Xs = torch.from_numpy(np.stack([mesh["X"], mesh["X"]])).to(dev).contiguous()
+    fo = torch.full((2, plan.dof), float("nan"), dtype=torch.float64, device=dev)
+    Mo = torch.full((2, plan.nnz[0]), float("nan"), dtype=torch.float64, device=dev)
+    Ko = torch.full((2, plan.nnz[1]), float("nan"), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    plan.fill_dev(xs.data_ptr(), Xs.data_ptr(), MAT, GRAV, H, fo.data_ptr(), Mo.data_ptr(), Ko.data_ptr(), n_scenes=2)
+    torch.cuda.synchronize()
+    assert fo[0].cpu().numpy().tobytes() == f.tobytes() and Ko[0].cpu().numpy().tobytes() == Kv.tobytes() and Mo[0].cpu().numpy().tobytes() == Mv.tobytes()
+    fb, Mb, Kb = plan.fill(x2, mesh["X"], MAT, GRAV, H)
+    assert fo[1].cpu().numpy().tobytes() == fb.tobytes() and Ko[1].cpu().numpy().tobytes() == Kb.tobytes() and Mo[1].cpu().numpy().tobytes() == Mb.tobytes()
+    with pytest.raises(E.EolcError):            # the device consumers work on the Lagrangian block structure only
+        plan.rhs_dev(Mo.data_ptr(), fo.data_ptr(), fo.data_ptr(), H, fo.data_ptr())
+    plan.close()

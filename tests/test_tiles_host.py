@@ -18,10 +18,10 @@ lp = ctypes.POINTER(ctypes.c_int64)
 
 
 class HostTiles:
-    def __init__(self, L, N, fn, es, X_hint=None, dedup=True):
+    def __init__(self, L, N, fn, es, X_hint=None, dedup=True, eol_index=None):
         self.L = L
-        L.hm_plan_create.restype = ctypes.c_void_p
-        L.hm_plan_create.argtypes = [ctypes.c_int32, ctypes.c_int32, ip, ctypes.c_int32, ip, dp, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+        L.hm_plan_create_eol.restype = ctypes.c_void_p
+        L.hm_plan_create_eol.argtypes = [ctypes.c_int32, ctypes.c_int32, ip, ctypes.c_int32, ip, dp, ctypes.c_int, ip, ctypes.c_char_p, ctypes.c_int]
         L.hm_plan_destroy.argtypes = [ctypes.c_void_p]
         L.hm_plan_info.argtypes = [ctypes.c_void_p, lp]
         L.hm_plan_pattern.argtypes = [ctypes.c_void_p, ctypes.c_int, ip, ip]
@@ -31,18 +31,20 @@ class HostTiles:
         es = np.ascontiguousarray(es, np.int32).reshape(-1, 4)
         err = ctypes.create_string_buffer(256)
         xh = None if X_hint is None else np.ascontiguousarray(X_hint, np.float64)
-        self.h = L.hm_plan_create(N, len(fn), fn.ctypes.data_as(ip), len(es), es.ctypes.data_as(ip),
-                                  None if xh is None else xh.ctypes.data_as(dp), int(dedup), err, 256)
+        eol = None if eol_index is None else np.ascontiguousarray(eol_index, np.int32)
+        self.h = L.hm_plan_create_eol(N, len(fn), fn.ctypes.data_as(ip), len(es), es.ctypes.data_as(ip),
+                                      None if xh is None else xh.ctypes.data_as(dp), int(dedup), None if eol is None else eol.ctypes.data_as(ip), err, 256)
         if not self.h:
             raise RuntimeError(err.value.decode())
         info = np.zeros(16, np.int64)
         L.hm_plan_info(self.h, info.ctypes.data_as(lp))
-        self.info = dict(zip("nnzM nnzK n_tiles n_templates elem_evals geo_bytes tmpl_bytes max_scratch max_loc Ei n_runs n_groups pull_rows max_kstage max_mstage".split(), info.tolist()))
+        self.info = dict(zip("nnzM nnzK n_tiles n_templates elem_evals geo_bytes tmpl_bytes max_scratch max_loc Ei n_runs n_groups pull_rows max_kstage max_mstage dof".split(), info.tolist()))
         self.N = N
+        self.dof = self.info["dof"]
 
     def pattern(self, which):
         nnz = self.info["nnzK" if which else "nnzM"]
-        o, i = np.zeros(3 * self.N + 1, np.int32), np.zeros(max(nnz, 1), np.int32)
+        o, i = np.zeros(self.dof + 1, np.int32), np.zeros(max(nnz, 1), np.int32)
         self.L.hm_plan_pattern(self.h, which, o.ctypes.data_as(ip), i.ctypes.data_as(ip))
         return o, i[:nnz]
 
@@ -54,7 +56,7 @@ class HostTiles:
             buf = np.full(n + 3, np.nan)
             off = ((-buf.ctypes.data // 8) % 2 + ph) % 2 if buf.ctypes.data % 16 in (0, 8) else 0
             return buf, buf[off:off + n]
-        (fb, f), (Mb, Mv), (Kb, Kv) = out(3 * self.N, phases[0]), out(self.info["nnzM"], phases[1]), out(self.info["nnzK"], phases[2])
+        (fb, f), (Mb, Mv), (Kb, Kv) = out(self.dof, phases[0]), out(self.info["nnzM"], phases[1]), out(self.info["nnzK"], phases[2])
         for a, ph in ((f, phases[0]), (Mv, phases[1]), (Kv, phases[2])):
             assert (a.ctypes.data // 8) % 2 == ph
         m = np.array(mat, np.float64); g = np.array(grav, np.float64)
@@ -69,10 +71,10 @@ class HostTiles:
         self.L.hm_plan_destroy(self.h)
 
 
-def _check(T, fn, es, x, X, oracle, what, mat=MAT, grav=GRAV, h=H, phases=(0, 0, 0)):
+def _check(T, fn, es, x, X, oracle, what, mat=MAT, grav=GRAV, h=H, phases=(0, 0, 0), eol_index=None):
     f, Mv, Kv = T.fill(x, X, mat, grav, h, phases)
     assert not np.isnan(f).any() and not np.isnan(Mv).any() and not np.isnan(Kv).any(), what + ": an output slot was never written"
-    ref = oracle.forces_fill(fn, es, x, X, tuple(mat), grav, h)
+    ref = oracle.forces_fill(fn, es, x, X, tuple(mat), grav, h, eol_index=eol_index)
     N = x.shape[0]
     assert_close_tol(f, ref["f"], max(np.abs(ref["f"]).max(), 1e-300), 1e-10, what + " f")
     for name, which, got in (("M", 0, Mv), ("MDK", 1, Kv)):
@@ -173,3 +175,51 @@ def test_tiles_host_plan_independent_of_worker_count(hostmath, monkeypatch):
             T.close()
         assert hashes[0] == hashes[1] == hashes[2], (hashes, infos)
         assert infos[0] == infos[1] == infos[2]
+
+
+def _eol_line(n, j0):
+    """EoL nodes along the grid line j = j0 of an n x n regular2 sheet (the cloth crossing a box edge), indices in a shuffled order."""
+    eol = np.full(n * n, -1, np.int32)
+    line = np.arange(1, n - 1) * n + j0
+    eol[line] = np.random.default_rng(n).permutation(line.size)
+    return eol
+
+
+@pytest.mark.parametrize("gen,n,eol_nodes,dedup", [("regular2", 5, (12, 6, 18, 7), True), ("regular2", 4, (5,), True), ("build4", 3, (4, 9, 10, 1), False),
+                                                   ("regular2", 3, tuple(range(9)), True), ("regular2", 24, "line", True), ("regular2", 33, "line", False),
+                                                   ("build4", 9, "corner+isolated", True)])
+def test_tiles_host_eol_matches_oracle(oracle, hostmath, gen, n, eol_nodes, dedup):
+    """EOL branch (forces_eol.h): the tiles plan with moved row destinations + the EOL element records + the gather, emulated on the host,
+    against the oracle's restatement of fillEOL* (f, patterns bit-exact, values to 1e-10)."""
+    X, fn = getattr(E.meshgen, gen)(n)
+    N = X.shape[0]
+    es = E.meshgen.edge_stencils(N, fn)
+    x = E.meshgen.drape_state(X, seed=n)
+    if eol_nodes == "line":
+        eol = _eol_line(n, n // 2)
+    elif eol_nodes == "corner+isolated":
+        eol = np.full(N, -1, np.int32)
+        eol[0] = 2; eol[N - 1] = 0; eol[n * n // 2] = 1          # a corner node, a cell-centre node, an interior grid node
+    else:
+        eol = np.full(N, -1, np.int32)
+        for k, a in enumerate(eol_nodes):
+            eol[a] = k
+    T = HostTiles(hostmath, N, fn, es, X, dedup, eol_index=eol)
+    assert T.dof == 3 * N + 2 * (int(eol.max()) + 1)
+    _check(T, fn, es, x, X, oracle, f"eol {gen}{n}", eol_index=eol)
+    _check(T, fn, es, x, X, oracle, f"eol {gen}{n} odd phases", phases=(1, 1, 1), eol_index=eol)
+    _check(T, fn, es, x, X, oracle, f"eol {gen}{n} mixed phases", phases=(1, 0, 1), eol_index=eol)
+    T.close()
+
+
+def test_edge_force_matches_reference(oracle, hostmath):
+    """The bending force the EOL branch needs (the Lagrangian one drops it): forces_eol.h edge_force vs the reference's ComputeBending f."""
+    hostmath.hostmath_edge_force.argtypes = [dp] * 8 + [ctypes.c_double, dp]
+    rng = np.random.default_rng(8)
+    for trial in range(50):
+        X = np.array([[0, 0], [1, 0], [0.2, 0.9], [0.7, -0.8]]) + 0.1 * rng.standard_normal((4, 2))
+        x = np.c_[X, np.zeros(4)] + 0.2 * rng.standard_normal((4, 3))
+        _, f, _ = oracle.compute_bending(*x, *X, 1e-2)
+        got = np.zeros(12)
+        hostmath.hostmath_edge_force(*[np.ascontiguousarray(v).ctypes.data_as(dp) for v in (*x, *X)], 1e-2, got.ctypes.data_as(dp))
+        assert np.abs(got - f).max() <= 1e-12 * np.abs(f).max(), trial

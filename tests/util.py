@@ -5,12 +5,13 @@ REAL_FIELDS = ("dist", "nor1", "nor2", "pos1", "pos2", "pos1_", "weights1", "wei
 
 
 def block_row_scale(outer, vals, n_nodes):
-    """s = max |entry| over the 3 rows (== columns, symmetric) of each node, broadcast to every entry."""
+    """s = max |entry| over the 3 rows (== columns, symmetric) of each node, broadcast to every entry.  With Eulerian dofs behind
+    the 3 n_nodes Lagrangian ones (EOL meshes, dof = 3N + 2 EoL_Count) the two columns of an EoL node form a group of their own."""
     outer = np.asarray(outer, dtype=np.int64)
     counts = np.diff(outer)
     col_of = np.repeat(np.arange(outer.size - 1), counts)
-    node_of = col_of // 3
-    s = np.zeros(n_nodes)
+    node_of = np.where(col_of < 3 * n_nodes, col_of // 3, n_nodes + (col_of - 3 * n_nodes) // 2)
+    s = np.zeros(n_nodes + max(outer.size - 1 - 3 * n_nodes, 0) // 2)
     np.maximum.at(s, node_of, np.abs(vals))
     return s[node_of]
 
