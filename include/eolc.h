@@ -18,8 +18,10 @@
  *
  * Simplifying assumption (true for Cloth::build, src/Cloth.cpp:73-90): one Vert per
  * Node, so the material coordinate X = node->verts[0]->u is per node.
- * Only the Lagrangian (non-EOL) branch of Forces::fill is implemented
- * (mesh.EoL_Count == 0, every BASELINE config); plan creation rejects EOL nodes.
+ * Both branches of Forces::fill are implemented: the Lagrangian one (mesh.EoL_Count == 0,
+ * every BASELINE config) and, when eol_index names EoL nodes, the Eulerian-on-Lagrangian one
+ * (src/Forces.cpp:177-329, 399-497, 580-683, 746-883): dof = 3N + 2 EoL_Count, the Eulerian
+ * dofs of node a at 3N + 2 eol_index[a] (src/Forces.cpp:379-381).
  */
 #ifndef EOLC_H_
 #define EOLC_H_
@@ -82,7 +84,9 @@ int eolc_mesh_edge_stencils(int32_t N, int32_t F, const int32_t *face_nodes, int
 /* ---- Forces::fill ------------------------------------------------------------------- */
 /* Topology plan: CSR pattern of M and MDK + element->slot maps. Rebuild only after a remesh /
  * set_indices (src/Scene.cpp:87-90).  X_hint (2N, may be NULL) is used only to group nodes into
- * spatially compact tiles; results do not depend on it. eol_index (N, may be NULL): -1 = Lagrangian. */
+ * spatially compact tiles; results do not depend on it. eol_index (N, may be NULL): Node::EoL_index of the EoL nodes, -1 =
+ * Lagrangian node; the indices must be distinct and EoL_Count = 1 + the largest (mesh.EoL_Count of the reference).  The
+ * device consumers below (rhs / CG / integrate) accept Lagrangian plans only. */
 int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face_nodes, int32_t E,
                             const int32_t *edge_stencil, const int32_t *eol_index, const double *X_hint,
                             eolc_forces_plan **out);
@@ -94,7 +98,7 @@ int eolc_forces_pattern(const eolc_forces_plan *plan, int which, int32_t *dof, i
                         const int32_t **inner);
 /* counts for the metric: faces + interior edges assembled per fill */
 int eolc_forces_counts(const eolc_forces_plan *plan, int32_t *n_faces, int32_t *n_interior_edges);
-/* One Forces::fill.  x: 3N (Node::x), X: 2N (verts[0]->u), outputs f (dof), M_vals (nnz(M)), MDK_vals (nnz(MDK)).
+/* One Forces::fill.  x: 3N (Node::x), X: 2N (verts[0]->u), outputs f (dof = 3N + 2 EoL_Count), M_vals (nnz(M)), MDK_vals (nnz(MDK)).
  * Host version copies x/X in and f/M/MDK out (pinned staging inside the plan). */
 int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
                      const double grav[3], double h, double *f, double *M_vals, double *MDK_vals);
@@ -122,7 +126,7 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
                       double *v_dev, double tol, int32_t max_iter, int32_t *iters_out, double *rel_resid_out);
 /* Position update of Cloth::step (src/Cloth.cpp:394-400): x += h v for the 3N Lagrangian dofs.  Asynchronous on the stream. */
 int eolc_forces_integrate_dev(eolc_forces_plan *plan, const double *v_dev, double h, double *x_dev);
-/* number of kernels one fill launches (for bench accounting) */
+/* number of kernels one fill launches (for bench accounting): 1, or 3 with EoL nodes */
 int eolc_forces_launches_per_fill(const eolc_forces_plan *plan);
 
 /* ---- CD / CD2 ----------------------------------------------------------------------- */
