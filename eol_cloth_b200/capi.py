@@ -53,6 +53,8 @@ def lib():
     L.eolc_forces_fill_batched_dev.argtypes = [c_vp, ctypes.c_int32, c_vp, c_vp, ctypes.POINTER(MaterialC), c_dp,
                                                ctypes.c_double, c_vp, c_vp, c_vp]
     L.eolc_forces_launches_per_fill.argtypes = [c_vp]
+    L.eolc_mesh_normals.argtypes = [c_vp, c_dp, c_dp, c_dp]
+    L.eolc_mesh_normals_dev.argtypes = [c_vp, c_vp, c_vp, c_vp]
     L.eolc_forces_rhs_dev.argtypes = [c_vp, c_vp, c_vp, c_vp, ctypes.c_double, c_vp]
     L.eolc_forces_integrate_dev.argtypes = [c_vp, c_vp, ctypes.c_double, c_vp]
     L.eolc_solve_cg_dev.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, ctypes.c_int32, c_ip, c_dp]

@@ -67,6 +67,9 @@ struct eolc_forces_plan {
     PinnedBuf<double> p_in, p_out;
     // block structure on the device + CG work vectors (solve.cuh), built on first use
     DevBuf<int32_t> d_blkM, d_nbrM, d_blkK, d_nbrK;
+    DevBuf<int32_t> d_fn, d_nfp;                  // face nodes and node -> incident faces (CSR) for the normals, built on first use
+    DevBuf<uint32_t> d_nfl;
+    DevBuf<double> d_fnorm, d_nnorm;              // staging of the host entry point
     DevBuf<double> d_cg;                          // r, p, Ap/z, dinv (dof each), partials, scalars
     PinnedBuf<double> p_sc;
 #ifdef EOLC_TILE_CLOCKS
@@ -1059,6 +1062,51 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
     if (iters_out) *iters_out = it;      // upper bound to a multiple of the check interval: iterations after convergence are no-ops
     const double rhs2 = P->p_sc.p[5] / (tol * tol);
     if (rel_resid_out) *rel_resid_out = rhs2 > 0.0 ? std::sqrt(P->p_sc.p[2] / rhs2) : 0.0;
+    return EOLC_OK;
+}
+
+// ---- per-step derived mesh data: face and node normals, kernels in solve.cuh ----
+static int ensure_face_csr(eolc_forces_plan *P) {
+    if (P->d_nfp.p || P->N == 0) return EOLC_OK;
+    cudaStream_t st = P->ctx->stream;
+    const tiles::NodeCSR csr(P->N, P->F, P->h_face_nodes.data(), 0, nullptr);
+    EOLC_CUDA(P->d_fn.upload(P->h_face_nodes, st)); EOLC_CUDA(P->d_nfp.upload(csr.nfp, st)); EOLC_CUDA(P->d_nfl.upload(csr.nfl, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));
+    return EOLC_OK;
+}
+
+int eolc_mesh_normals_dev(eolc_forces_plan *plan, const double *x_dev, double *face_n_dev, double *node_n_dev) {
+    EOLC_REQUIRE(plan, "plan is NULL");
+    if (plan->N == 0) return EOLC_OK;
+    EOLC_REQUIRE(x_dev, "NULL device pointer");
+    EOLC_CUDA(cudaSetDevice(plan->ctx->device));
+    int rc = ensure_face_csr(plan);
+    if (rc) return rc;
+    cudaStream_t st = plan->ctx->stream;
+    const size_t cap = (size_t)8 * plan->ctx->sm_count;
+    if (face_n_dev && plan->F > 0)
+        solve::k_face_normals<<<(int)std::min<size_t>(((size_t)plan->F + solve::THREADS - 1) / solve::THREADS, cap), solve::THREADS, 0, st>>>(plan->F, plan->d_fn.p, x_dev, face_n_dev);
+    if (node_n_dev)
+        solve::k_node_normals<<<(int)std::min<size_t>(((size_t)plan->N + solve::THREADS - 1) / solve::THREADS, cap), solve::THREADS, 0, st>>>(plan->N, plan->d_nfp.p, plan->d_nfl.p, plan->d_fn.p, x_dev, node_n_dev);
+    EOLC_CUDA(cudaGetLastError());
+    return EOLC_OK;
+}
+
+int eolc_mesh_normals(eolc_forces_plan *plan, const double *x, double *face_n, double *node_n) {
+    EOLC_REQUIRE(plan, "plan is NULL");
+    eolc_forces_plan *P = plan;
+    if (P->N == 0) return EOLC_OK;
+    EOLC_REQUIRE(x, "NULL host pointer");
+    EOLC_CUDA(cudaSetDevice(P->ctx->device));
+    cudaStream_t st = P->ctx->stream;
+    const size_t N = P->N, F = P->F;
+    EOLC_CUDA(P->d_x.ensure(3 * N)); EOLC_CUDA(P->d_fnorm.ensure(3 * std::max<size_t>(F, 1))); EOLC_CUDA(P->d_nnorm.ensure(3 * N));
+    EOLC_CUDA(cudaMemcpyAsync(P->d_x.p, x, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = eolc_mesh_normals_dev(P, P->d_x.p, face_n ? P->d_fnorm.p : nullptr, node_n ? P->d_nnorm.p : nullptr);
+    if (rc) return rc;
+    if (face_n && F) EOLC_CUDA(cudaMemcpyAsync(face_n, P->d_fnorm.p, 3 * F * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (node_n) EOLC_CUDA(cudaMemcpyAsync(node_n, P->d_nnorm.p, 3 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));
     return EOLC_OK;
 }
 

@@ -170,5 +170,55 @@ __global__ void __launch_bounds__(THREADS) k_integrate(size_t n, double *__restr
     for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) x[i] = x[i] + h * v[i];
 }
 
+// ---- per-step derived mesh data ------------------------------------------------------------------------------
+// face->n of compute_ws_data(Face*), /root/reference/src/external/ArcSim/mesh.cpp:135-140: normalize(cross(x1 - x0, x2 - x0)), with
+// ArcSim's normalize (vectors.hpp:111: the zero vector stays zero) and its sequential dot (vectors.hpp:108).  No FMA contraction here
+// (explicit _rn intrinsics) so that the normals match the host arithmetic to the last bit but one (sqrt and the division are IEEE).
+__device__ __forceinline__ void ws_normalize(double &a, double &b, double &c) {
+    const double m = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c)));
+    if (m == 0.0) { a = b = c = 0.0; return; }
+    a = a / m; b = b / m; c = c / m;
+}
+__device__ __forceinline__ void ws_cross(const double *u, const double *v, double *w) {
+    w[0] = __dsub_rn(__dmul_rn(u[1], v[2]), __dmul_rn(u[2], v[1]));
+    w[1] = __dsub_rn(__dmul_rn(u[2], v[0]), __dmul_rn(u[0], v[2]));
+    w[2] = __dsub_rn(__dmul_rn(u[0], v[1]), __dmul_rn(u[1], v[0]));
+}
+__global__ void __launch_bounds__(THREADS) k_face_normals(int32_t F, const int32_t *__restrict__ fn, const double *__restrict__ x, double *__restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < (size_t)F; i += (size_t)gridDim.x * THREADS) {
+        const int32_t a = fn[3 * i], b = fn[3 * i + 1], c = fn[3 * i + 2];
+        double e1[3], e2[3], n[3];
+        for (int k = 0; k < 3; ++k) { e1[k] = __dsub_rn(x[3 * (size_t)b + k], x[3 * (size_t)a + k]); e2[k] = __dsub_rn(x[3 * (size_t)c + k], x[3 * (size_t)a + k]); }
+        ws_cross(e1, e2, n);
+        ws_normalize(n[0], n[1], n[2]);
+        out[3 * i] = n[0]; out[3 * i + 1] = n[1]; out[3 * i + 2] = n[2];
+    }
+}
+// node->n = normal<WS>(node), /root/reference/src/external/ArcSim/geometry.cpp:302-316: over the node's faces (vert->adjf order = the order
+// the faces were added, mesh.cpp:372, i.e. ascending face index in the flattened mesh) n += cross(e1, e2) / (2 |e1|^2 |e2|^2) with
+// e1, e2 the edges to the next / next-but-one vertex of the face, then normalize.  nfp / nfl: node -> incident faces (CSR), face << 2 | position.
+__global__ void __launch_bounds__(THREADS) k_node_normals(int32_t N, const int32_t *__restrict__ nfp, const uint32_t *__restrict__ nfl,
+                                                          const int32_t *__restrict__ fn, const double *__restrict__ x, double *__restrict__ out) {
+    for (size_t a = blockIdx.x * (size_t)THREADS + threadIdx.x; a < (size_t)N; a += (size_t)gridDim.x * THREADS) {
+        double n[3] = {0.0, 0.0, 0.0};
+        const double p[3] = {x[3 * a], x[3 * a + 1], x[3 * a + 2]};
+        for (int32_t q = nfp[a]; q < nfp[a + 1]; ++q) {
+            const uint32_t fl = nfl[q];
+            const size_t f = fl >> 2;
+            const int j = (int)(fl & 3u), j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            const size_t b = (size_t)fn[3 * f + j1], c = (size_t)fn[3 * f + j2];
+            double e1[3], e2[3], w[3];
+            for (int k = 0; k < 3; ++k) { e1[k] = __dsub_rn(x[3 * b + k], p[k]); e2[k] = __dsub_rn(x[3 * c + k], p[k]); }
+            ws_cross(e1, e2, w);
+            const double l1 = __dadd_rn(__dadd_rn(__dmul_rn(e1[0], e1[0]), __dmul_rn(e1[1], e1[1])), __dmul_rn(e1[2], e1[2]));
+            const double l2 = __dadd_rn(__dadd_rn(__dmul_rn(e2[0], e2[0]), __dmul_rn(e2[1], e2[1])), __dmul_rn(e2[2], e2[2]));
+            const double den = __dmul_rn(__dmul_rn(2.0, l1), l2);
+            for (int k = 0; k < 3; ++k) n[k] = __dadd_rn(n[k], w[k] / den);
+        }
+        ws_normalize(n[0], n[1], n[2]);
+        out[3 * a] = n[0]; out[3 * a + 1] = n[1]; out[3 * a + 2] = n[2];
+    }
+}
+
 }  // namespace solve
 }  // namespace eolc

@@ -114,6 +114,21 @@ class ForcesPlan:
                                                 ctypes.byref(it), ctypes.byref(res)))
         return it.value, res.value
 
+    def normals(self, x):
+        """World-space face and node normals of compute_ws_data (ArcSim mesh.cpp:135-143, geometry.cpp:302-316) for the state x:
+        returns (face_n (F,3), node_n (N,3)).  Host arrays in and out."""
+        x = capi.f64(x).reshape(-1)
+        if x.size != 3 * self.N:
+            raise capi.EolcError("x must hold 3N doubles")
+        fnorm = np.empty((self.n_faces, 3))
+        nnorm = np.empty((self.N, 3))
+        capi.check(capi.lib().eolc_mesh_normals(self._h, capi.dptr(x), capi.dptr(fnorm) if self.n_faces else None, capi.dptr(nnorm)))
+        return fnorm, nnorm
+
+    def normals_dev(self, x_ptr, face_n_ptr, node_n_ptr):
+        """Same on device pointers (either output may be None); asynchronous on ctx.stream."""
+        capi.check(capi.lib().eolc_mesh_normals_dev(self._h, x_ptr, face_n_ptr, node_n_ptr))
+
     def close(self):
         if self._h:
             capi.lib().eolc_forces_plan_destroy(self._h)

@@ -126,6 +126,15 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
                       double *v_dev, double tol, int32_t max_iter, int32_t *iters_out, double *rel_resid_out);
 /* Position update of Cloth::step (src/Cloth.cpp:394-400): x += h v for the 3N Lagrangian dofs.  Asynchronous on the stream. */
 int eolc_forces_integrate_dev(eolc_forces_plan *plan, const double *v_dev, double h, double *x_dev);
+/* ---- per-step derived mesh data ---------------------------------------------- */
+/* World-space normals of compute_ws_data (src/external/ArcSim/mesh.cpp:135-140, 142-143): face_n (3F) = normalize(cross(x1 - x0,
+ * x2 - x0)); node_n (3N) = normal<WS>(node), src/external/ArcSim/geometry.cpp:302-316 (sum over the node's faces, in ascending face
+ * index = vert->adjf order of a mesh whose faces were added in index order, of cross(e1, e2) / (2 |e1|^2 |e2|^2), normalized; a
+ * node without faces gets 0).  These are what Cloth::updatePosNor (src/Cloth.cpp:150-171) and Constraints::fill
+ * (src/Constraints.cpp:181, 296-318) read as node->n / face->n.  Either output may be NULL.  The _dev form takes device pointers
+ * and is asynchronous on eolc_ctx_stream(); the node curvature of compute_ws_data(Node*) is remesher state and not produced. */
+int eolc_mesh_normals(eolc_forces_plan *plan, const double *x, double *face_n, double *node_n);
+int eolc_mesh_normals_dev(eolc_forces_plan *plan, const double *x_dev, double *face_n_dev, double *node_n_dev);
 /* number of kernels one fill launches (for bench accounting): 1, or 3 with EoL nodes */
 int eolc_forces_launches_per_fill(const eolc_forces_plan *plan);
 

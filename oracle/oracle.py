@@ -318,3 +318,43 @@ def constraints_contact_rows(contacts, node_eol=None):
                 continue
             rows.append([(int(v2[j]) * 3 + k, -c["nor2"][k] * w2[j]) for j in range(3) for k in range(3)])
     return rows
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Per-step derived mesh data — numpy restatement, TEST INFRASTRUCTURE ONLY
+# ---------------------------------------------------------------------------------------------------------------------
+def _arcsim_norm2(v):
+    """vectors.hpp:108-109: dot() sums left to right starting from 0."""
+    return (v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1]) + v[..., 2] * v[..., 2]
+
+
+def _arcsim_cross(u, v):
+    """vectors.hpp:113."""
+    return np.stack([u[..., 1] * v[..., 2] - u[..., 2] * v[..., 1], u[..., 2] * v[..., 0] - u[..., 0] * v[..., 2],
+                     u[..., 0] * v[..., 1] - u[..., 1] * v[..., 0]], axis=-1)
+
+
+def _arcsim_normalize(v):
+    """vectors.hpp:111: m == 0 ? 0 : u / m."""
+    m = np.sqrt(_arcsim_norm2(v))
+    out = np.zeros_like(v)
+    nz = m != 0
+    out[nz] = v[nz] / m[nz][:, None]
+    return out
+
+
+def mesh_normals(face_nodes, x):
+    """compute_ws_data(Face*) (ArcSim mesh.cpp:135-140): face->n = normalize(cross(x1 - x0, x2 - x0)); normal<WS>(node)
+    (geometry.cpp:302-316): n += cross(e1, e2) / (2 * norm2(e1) * norm2(e2)) over vert->adjf (faces in the order they were added
+    = ascending face index), e1 / e2 to the next / next-but-one vertex of the face; then normalize.  Returns (face_n, node_n)."""
+    fn = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    face_n = _arcsim_normalize(_arcsim_cross(x[fn[:, 1]] - x[fn[:, 0]], x[fn[:, 2]] - x[fn[:, 0]]))
+    contrib = np.empty((fn.shape[0], 3, 3))
+    for j in range(3):
+        e1 = x[fn[:, (j + 1) % 3]] - x[fn[:, j]]
+        e2 = x[fn[:, (j + 2) % 3]] - x[fn[:, j]]
+        contrib[:, j] = _arcsim_cross(e1, e2) / ((2 * _arcsim_norm2(e1)) * _arcsim_norm2(e2))[:, None]
+    n = np.zeros_like(x)
+    np.add.at(n, fn.reshape(-1), contrib.reshape(-1, 3))      # unbuffered, in index order: per node, faces ascending
+    return face_n, _arcsim_normalize(n)
