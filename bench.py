@@ -206,6 +206,30 @@ def workload_name(w):
             "ensemble64": "ensemble of 4096 regular2 64x64 scenes, Forces::fill batched (BASELINE configs[4])"}[w]
 
 
+def bind_to_gpu_numa(local):
+    """Keep this rank's host thread and its first-touch allocations (the pinned e2e buffers) on the CPUs next to its GPU: with one rank
+    per GPU and unbound processes the 8 x 1.5 GB device->host copies of the e2e leg otherwise meet on one socket's memory.
+    Returns a description for the JSON line (None when the topology cannot be read)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        devid = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, devid)
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "cpus %s" % txt
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -216,8 +240,13 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    # stdout carries the ONE JSON line and nothing else: library chatter (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -340,8 +369,13 @@ def run_ours(args):
         line["cd"] = bench_cd(ctx, dev, stream)
     if rank == 0 and not args.no_cd and S == 1:
         line["consumer"] = bench_consumer(plan, dev, stream, f_d, M_d, K_d, N, nnzM, nnzK)
+        line["consumer"]["normals"] = bench_normals(plan, dev, stream, x_d, N, F)
+        line["eol"] = bench_eol(ctx, dev, stream, n, X, fn, es, x_d, X_d, ms_local)
+    if numa:
+        line["e2e"]["host_affinity"] = numa
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -379,6 +413,59 @@ def bench_consumer(plan, dev, stream, f_d, M_d, K_d, N, nnzM, nnzK):
     return {"rhs": {"what": "b = -(M v + h f), Cloth.cpp:345", "ms": rhs_ms, "GB_per_s": rhs_bytes / rhs_ms / 1e6, "frac_of_hbm_peak": rhs_bytes / rhs_ms / 1e6 / peak},
             "cg_iteration": {"what": "Jacobi-preconditioned CG on MDK (GeneralizedSolver.cpp:120-126), 5 launches, incl. the host's convergence check every 8",
                              "ms": cg_ms, "GB_per_s": cg_bytes / cg_ms / 1e6, "frac_of_hbm_peak": cg_bytes / cg_ms / 1e6 / peak}}
+
+
+def bench_normals(plan, dev, stream, x_d, N, F):
+    """Secondary: face + node normals of compute_ws_data on the device, both kernels per call."""
+    import torch
+    fn_d = torch.empty(3 * F, dtype=torch.float64, device=dev)
+    nn_d = torch.empty(3 * N, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        plan.normals_dev(x_d.data_ptr(), fn_d.data_ptr(), nn_d.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(10):
+        plan.normals_dev(x_d.data_ptr(), fn_d.data_ptr(), nn_d.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    nbytes = 2 * (24 * N + 12 * F) + 4 * (N + 1) + 4 * 3 * F + 24 * F + 24 * N      # x + face idx (twice), node->face CSR, both outputs
+    peak, _ = measured_peak()
+    return {"what": "face->n and node->n (ArcSim mesh.cpp:135-143, geometry.cpp:302-316), 2 launches", "ms": ms,
+            "GB_per_s": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak}
+
+
+def bench_eol(ctx, dev, stream, n, X, fn, es, x_d, X_d, lagrangian_ms):
+    """Secondary: the same sheet with the n - 2 interior nodes of its middle grid line flagged EoL (the cloth crossing a box edge):
+    Forces::fill through the EOL branch (SURVEY §8a row 9), 3 launches per fill, against the Lagrangian fill of the same state."""
+    import torch
+    import eol_cloth_b200 as E
+    N = X.shape[0]
+    eol = np.full(N, -1, np.int32)
+    line = np.arange(1, n - 1) * n + n // 2
+    eol[line] = np.arange(line.size)
+    plan = E.ForcesPlan(ctx, N, fn, es, eol_index=eol, X_hint=X)
+    f_d = torch.empty(plan.dof, dtype=torch.float64, device=dev)
+    M_d = torch.empty(plan.nnz[0], dtype=torch.float64, device=dev)
+    K_d = torch.empty(plan.nnz[1], dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        plan.fill_dev(x_d.data_ptr(), X_d.data_ptr(), MAT, GRAV, H, f_d.data_ptr(), M_d.data_ptr(), K_d.data_ptr())
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(10):
+        plan.fill_dev(x_d.data_ptr(), X_d.data_ptr(), MAT, GRAV, H, f_d.data_ptr(), M_d.data_ptr(), K_d.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    out = {"workload": f"regular2 n={n} sheet, {line.size} EoL nodes on the grid line j = n/2", "dof": plan.dof, "nnz_M": plan.nnz[0],
+           "nnz_MDK": plan.nnz[1], "launches_per_fill": plan.launches_per_fill, "ms_per_fill": ms, "lagrangian_ms_per_fill": lagrangian_ms,
+           "checksum_f_eulerian": float(f_d[3 * N:].sum().item())}
+    plan.close()
+    return out
 
 
 def bench_cd(ctx, dev, stream):
