@@ -4,8 +4,10 @@
 // the way Mesh::add(Face) does, mesh.cpp:356-378), then goes through exactly what the reference-side adapters do:
 //   eolc::host::flatten(mesh) -> eolc::host::Forces::fill(...) -> eolc::host::CD2(...)
 // and dumps the results for tests/test_host_cpp.py to compare with the oracle.
-//   usage: host_driver <in.bin> <out.bin>
+//   usage: host_driver <in.bin> <out.bin> [n]     with n: the mesh is an n x n grid sheet; flag the interior nodes of its grid line
+//                                                 j = n / 2 as EoL nodes (Node::EoL, EoL_index in grid order, mesh.EoL_Count)
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <vector>
 #include "eolc_host.hpp"
@@ -41,6 +43,10 @@ int main(int argc, char **argv) {
         v->u[0] = X[2 * (size_t)i]; v->u[1] = X[2 * (size_t)i + 1]; v->u[2] = 0; v->node = n;
         n->verts.push_back(v); n->index = i; n->EoL = false; n->EoL_index = -1;
         mesh.nodes.push_back(n); mesh.verts.push_back(v);
+    }
+    if (argc > 3) {
+        const int n = std::atoi(argv[3]);
+        for (int i = 1; i + 1 < n; ++i) { Node *nd = mesh.nodes[(size_t)i * n + n / 2]; nd->EoL = true; nd->EoL_index = mesh.EoL_Count++; }
     }
     std::map<std::pair<Node *, Node *>, Edge *> edge_of;
     for (int k = 0; k < F; ++k) {

@@ -17,11 +17,19 @@ import eol_cloth_b200 as E  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def forces_case(gen, n, seed):
+def eol_line(n):
+    """EoL nodes of the EOL fixtures: the interior nodes of the grid line j = n // 2, EoL_index in grid order."""
+    eol = np.full(n * n, -1, np.int32)
+    line = np.arange(1, n - 1) * n + n // 2
+    eol[line] = np.arange(line.size)
+    return eol
+
+
+def forces_case(gen, n, seed, eol=None):
     X, fn = getattr(E.meshgen, gen)(n)
     es = E.meshgen.edge_stencils(X.shape[0], fn)
     x = E.meshgen.drape_state(X, seed=seed)
-    r = O.forces_fill(fn, es, x, X)
+    r = O.forces_fill(fn, es, x, X, eol_index=eol)
     return dict(f=r["f"], M_outer=r["M"][0], M_inner=r["M"][1], M_vals=r["M"][2], K_outer=r["MDK"][0],
                 K_inner=r["MDK"][1], K_vals=r["MDK"][2])
 
@@ -42,6 +50,9 @@ def cd_case(gen, n, centre, seed, rot=None, points=False):
 if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "forces_regular2_n12.npz"), **forces_case("regular2", 12, 0))
     np.savez_compressed(os.path.join(HERE, "forces_build4_n7.npz"), **forces_case("build4", 7, 1))
+    np.savez_compressed(os.path.join(HERE, "forces_eol_regular2_n12.npz"), **forces_case("regular2", 12, 2, eol_line(12)))
+    fn_, nn_ = O.mesh_normals(E.meshgen.build4(7)[1], E.meshgen.drape_state(E.meshgen.build4(7)[0], seed=1))
+    np.savez_compressed(os.path.join(HERE, "normals_build4_n7.npz"), face_n=fn_, node_n=nn_)
     np.savez_compressed(os.path.join(HERE, "cd_regular2_n24.npz"), **cd_case("regular2", 24, E.meshgen.BOX_CENTRE, 0))
     c3b = np.array([0.9175, -0.25, -0.549])
     np.savez_compressed(os.path.join(HERE, "cd_build4_n16_corner.npz"), **cd_case("build4", 16, c3b, 1, points=True))

@@ -70,6 +70,25 @@ def test_fill_matches_golden(ctx, name, gen, n, seed):
     _check(forces, ref, mesh["x"].shape[0], name)
 
 
+def test_eol_fill_and_normals_match_golden(ctx):
+    """Committed fixtures (tests/golden/make_golden.py): EOL fill of a 12x12 sheet with its middle grid line EoL; normals of build4 n=7."""
+    g = np.load(os.path.join(GOLD, "forces_eol_regular2_n12.npz"))
+    mesh = _mesh("regular2", 12, seed=2)
+    eol = np.full(144, -1, np.int32)
+    line = np.arange(1, 11) * 12 + 6
+    eol[line] = np.arange(line.size)
+    mesh["eol_index"] = eol
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    ref = dict(f=g["f"], M=(g["M_outer"], g["M_inner"], g["M_vals"]), MDK=(g["K_outer"], g["K_inner"], g["K_vals"]))
+    _check(forces, ref, 144, "golden eol")
+    g = np.load(os.path.join(GOLD, "normals_build4_n7.npz"))
+    mesh = _mesh("build4", 7, seed=1)
+    plan = E.ForcesPlan(ctx, mesh["x"].shape[0], mesh["face_nodes"], mesh["edge_stencil"])
+    fa, na = plan.normals(mesh["x"])
+    assert fa.tobytes() == g["face_n"].tobytes() and na.tobytes() == g["node_n"].tobytes()
+    plan.close()
+
+
 def test_shuffled_node_order_and_isolated_node(ctx, oracle):
     """Arbitrary (remeshed-like) numbering + a node no face references (its rows stay empty, f = 0)."""
     X, fn = E.meshgen.regular2(9)

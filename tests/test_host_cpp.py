@@ -49,12 +49,18 @@ def test_host_cpp_aborts_without_gpu(driver, tmp_path):
 
 
 @pytest.mark.gpu
-def test_host_cpp_matches_oracle(driver, oracle, tmp_path):
+@pytest.mark.parametrize("with_eol", [False, True], ids=["lagrangian", "eol"])
+def test_host_cpp_matches_oracle(driver, oracle, tmp_path, with_eol):
     X, fn = E.meshgen.regular2(24)
     c = np.array([0.9175, -0.25, -0.549])
     x = E.meshgen.box_scene_state(X, seed=3, centre=c)
     _write_input(tmp_path / "in.bin", X, fn, x, c)
-    r = subprocess.run([driver, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    eol = None
+    if with_eol:      # the driver flags the same nodes on its pointer mesh (Node::EoL / EoL_index), flatten() carries them over
+        eol = np.full(X.shape[0], -1, np.int32)
+        line = np.arange(1, 23) * 24 + 12
+        eol[line] = np.arange(line.size)
+    r = subprocess.run([driver, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")] + (["24"] if with_eol else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = open(tmp_path / "out.bin", "rb").read()
     dof, nE, cutoff, ncls, nnzM, nnzK = struct.unpack_from("iiiiqq", raw, 0)
@@ -70,9 +76,9 @@ def test_host_cpp_matches_oracle(driver, oracle, tmp_path):
     Ko, Ki, Kv = take(np.int32, dof + 1), take(np.int32, nnzK), take(np.float64, nnzK)
     cls = take(E.CONTACT_DTYPE, ncls)
     N = X.shape[0]
-    assert cutoff == 3 * N and dof == 3 * N
+    assert cutoff == 3 * N and dof == 3 * N + (2 * 22 if with_eol else 0)
     assert np.array_equal(es, E.meshgen.edge_stencils(N, fn))          # flatten() == the generator's ArcSim edge order
-    ref = oracle.forces_fill(fn, es, x, X, tuple(MAT), GRAV, H)
+    ref = oracle.forces_fill(fn, es, x, X, tuple(MAT), GRAV, H, eol_index=eol)
     assert_close_tol(f, ref["f"], np.abs(ref["f"]).max(), 1e-10, "f")
     for name, got in (("M", (Mo, Mi, Mv)), ("MDK", (Ko, Ki, Kv))):
         o, i, v = ref[name]

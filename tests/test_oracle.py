@@ -118,6 +118,28 @@ def test_golden_forces(oracle, name, gen, n, seed):
         assert np.array_equal(r[nm][2], g[k + "_vals"])
 
 
+def _eol_line(n):
+    eol = np.full(n * n, -1, np.int32)
+    line = np.arange(1, n - 1) * n + n // 2
+    eol[line] = np.arange(line.size)
+    return eol
+
+
+def test_golden_forces_eol_and_normals(oracle):
+    g = np.load(os.path.join(GOLD, "forces_eol_regular2_n12.npz"))
+    X, fn = E.meshgen.regular2(12)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    r = oracle.forces_fill(fn, es, E.meshgen.drape_state(X, seed=2), X, eol_index=_eol_line(12))
+    assert r["dof"] == 3 * 144 + 2 * 10 and np.array_equal(r["f"], g["f"])
+    for k, nm in (("M", "M"), ("K", "MDK")):
+        assert np.array_equal(r[nm][0], g[k + "_outer"]) and np.array_equal(r[nm][1], g[k + "_inner"])
+        assert np.array_equal(r[nm][2], g[k + "_vals"])
+    g = np.load(os.path.join(GOLD, "normals_build4_n7.npz"))
+    X, fn = E.meshgen.build4(7)
+    fa, na = oracle.mesh_normals(fn, E.meshgen.drape_state(X, seed=1))
+    assert np.array_equal(fa, g["face_n"]) and np.array_equal(na, g["node_n"])
+
+
 def _cd_inputs(gen, n, centre, seed, points):
     X, fn = getattr(E.meshgen, gen)(n)
     x = E.meshgen.box_scene_state(X, seed=seed, centre=np.asarray(centre))
