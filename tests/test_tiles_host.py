@@ -223,3 +223,26 @@ def test_edge_force_matches_reference(oracle, hostmath):
         got = np.zeros(12)
         hostmath.hostmath_edge_force(*[np.ascontiguousarray(v).ctypes.data_as(dp) for v in (*x, *X)], 1e-2, got.ctypes.data_as(dp))
         assert np.abs(got - f).max() <= 1e-12 * np.abs(f).max(), trial
+
+
+def test_tiles_host_eol_shuffled_numbering_and_faceless_eol_node(oracle, hostmath):
+    """Remeshed-like node numbering (runs of consecutive nodes are short, coupled and uncoupled nodes interleave) and an EoL node no
+    face refers to: its two Eulerian rows stay empty and its f entries are written as zeros."""
+    X, fn = E.meshgen.regular2(11)
+    rng = np.random.default_rng(3)
+    N = X.shape[0] + 1
+    perm = rng.permutation(N).astype(np.int32)
+    Xp = np.zeros((N, 2)); Xp[perm[:-1]] = X; Xp[perm[-1]] = (0.5, 0.5)
+    fnp = perm[fn]
+    es = E.meshgen.edge_stencils(N, fnp)
+    x = np.c_[Xp, 0.05 * np.sin(5 * Xp[:, 0]) * np.cos(3 * Xp[:, 1])] + 1e-3 * rng.standard_normal((N, 3))
+    eol = np.full(N, -1, np.int32)
+    chosen = perm[[5 * 11 + j for j in range(2, 9)]]          # a grid line of the original sheet
+    eol[chosen] = rng.permutation(len(chosen)) + 1
+    eol[perm[-1]] = 0                                         # the faceless node is EoL index 0
+    T = HostTiles(hostmath, N, fnp, es, Xp, True, eol_index=eol)
+    f, Mv, Kv = _check(T, fnp, es, x, Xp, oracle, "eol shuffled", eol_index=eol)
+    assert f[3 * N] == 0.0 and f[3 * N + 1] == 0.0
+    o, _ = T.pattern(1)
+    assert o[3 * N] == o[3 * N + 1] == o[3 * N + 2]
+    T.close()
