@@ -524,6 +524,58 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             for (size_t c = 0; c + 1 < ccuts.size(); ++c) leaves.push_back({ccuts[c], ccuts[c + 1]});
         }
     }
+    // ---- experiment knob, OFF by default (EOLC_PLAN_TILING=hex): hexagonal lattice tiling of structured sheets.  On the triangular
+    //      lattice of a regular sheet (neighbours (+-1, 0), (0, +-1), +-(1, 1)) the 29-node hexagon with rows of 5, 6, 7, 6, 5 nodes
+    //      touches exactly 128 stencils and 78 faces — four full stencil warps, one per scheduler, instead of the 145 stencils (a
+    //      fifth, half-empty warp next to a full one on scheduler 0) of the 8 x 4 rectangle the bisection finds; its translates by
+    //      u = (5, 2), v = (-2, 5) (det 29) tile the plane.  Measured on the 1024^2 sheet: 0.837 ms against 0.758 ms for the rectangles
+    //      (profiles/r01/experiments.md, h1): 12 % more tiles cost more in per-tile latency (barriers, the fixed latency of a phase-2
+    //      group) than the balanced phase 1 saves.  Kept for the record and for meshes with the other aspect ratios.
+    {
+        const char *tl = getenv("EOLC_PLAN_TILING");
+        std::vector<double> ux, uy;
+        if (X_hint && MAX_OWN >= 29 && tl && strcmp(tl, "hex") == 0) {
+            ux.assign(cx.begin(), cx.end()); uy.assign(cy.begin(), cy.end());
+            std::sort(ux.begin(), ux.end()); ux.erase(std::unique(ux.begin(), ux.end()), ux.end());
+            std::sort(uy.begin(), uy.end()); uy.erase(std::unique(uy.begin(), uy.end()), uy.end());
+        }
+        if (!ux.empty() && (uint64_t)ux.size() * (uint64_t)uy.size() == (uint64_t)N) {
+            const int32_t nJ = (int32_t)uy.size();
+            std::vector<int32_t> gi(N), gj(N);
+            std::vector<char> hit((size_t)N, 0);
+            bool grid = true;
+            for (int32_t a = 0; a < N && grid; ++a) {
+                gi[a] = (int32_t)(std::lower_bound(ux.begin(), ux.end(), cx[a]) - ux.begin());
+                gj[a] = (int32_t)(std::lower_bound(uy.begin(), uy.end(), cy[a]) - uy.begin());
+                char &h = hit[(size_t)gi[a] * nJ + gj[a]];
+                if (h) grid = false;
+                h = 1;
+            }
+            if (grid) {      // full tensor grid in the hint coordinates
+                static const int HROW[5][2] = {{0, 5}, {0, 6}, {0, 7}, {1, 6}, {2, 5}};   // (first column, length) of the hexagon's rows
+                const int U0 = 5, U1 = 2, V0 = -2, V1 = 5, DET = 29;
+                std::vector<uint64_t> key((size_t)N);
+                for (int32_t a = 0; a < N; ++a) {
+                    const int i = gi[a], j = gj[a];
+                    int64_t ta = 0, tb = 0;
+                    for (int r = 0; r < 5; ++r)
+                        for (int c = HROW[r][0]; c < HROW[r][0] + HROW[r][1]; ++c) {
+                            const int64_t di = i - r, dj = j - c, p = di * V1 - dj * V0, q = U0 * dj - U1 * di;
+                            if (p % DET == 0 && q % DET == 0) { ta = p / DET; tb = q / DET; r = 5; break; }
+                        }
+                    key[a] = ((uint64_t)(ta + (1 << 20)) << 32) | (uint64_t)(tb + (1 << 20));
+                }
+                std::sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
+                leaves.clear();
+                for (size_t lo = 0; lo < (size_t)N;) {
+                    size_t hi = lo + 1;
+                    while (hi < (size_t)N && key[idx[hi]] == key[idx[lo]]) ++hi;
+                    leaves.push_back({lo, hi});
+                    lo = hi;
+                }
+            }
+        }
+    }
     // ---- split leaves that exceed the kernel's capacities
     std::vector<int32_t> faces, edges;
     {
