@@ -144,8 +144,19 @@ struct BulkStore {   // one asynchronous bulk copy shared -> global; both addres
 };
 
 // Register budget: the kernel is launched with 384 threads (ptxas cap 168 registers); the two compute warpgroups then take 216
-// registers per thread and the service warpgroup drops to 64 (setmaxnreg): the pool is the CTA's own 384 x 168 allocation, and 256 x 216 + 128 x 64 = 63488 fits it.
-constexpr int COMPUTE_REGS = 216, SERVICE_REGS = 64;
+// registers per thread and the service warpgroup drops to 72 (setmaxnreg): the pool is the CTA's own 384 x 168 allocation, and
+// 256 x 216 + 128 x 72 = 64512 is all of it.  ptxas allocates each region within its setmaxnreg value (checked in the SASS: the
+// service region, which also runs phase-2 groups, stays below R72 without spills).
+#ifndef EOLC_COMPUTE_REGS
+#define EOLC_COMPUTE_REGS 216
+#endif
+#ifndef EOLC_SERVICE_REGS
+#define EOLC_SERVICE_REGS 72
+#endif
+constexpr int COMPUTE_REGS = EOLC_COMPUTE_REGS, SERVICE_REGS = EOLC_SERVICE_REGS;
+static_assert(tiles::NTHREADS * COMPUTE_REGS + 128 * SERVICE_REGS <= tiles::CTA_THREADS * 168, "register pool of the CTA");
+constexpr bool SERVICE_P2 = tiles::P2THREADS > tiles::NTHREADS;   // the service warpgroup runs phase-2 groups too
+constexpr int BAR1_THREADS = SERVICE_P2 ? tiles::CTA_THREADS : tiles::NTHREADS;
 
 __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemble_tiles_kernel(const __grid_constant__ TilesArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -275,6 +286,14 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
             EOLC_SYNC();                 // [B1] elements parked, staged inputs landed, staging free
             EOLC_CLK(2)
             ta1 = (int)ctl[0];
+            if (SERVICE_P2) {            // this warp's share of the phase-2 groups (forces_plan.h spreads them over all 12 warps)
+                set_view(fs, Ms, Ks);
+                tiles::phase2((int)tid, tiles::P2THREADS, V, ctl[1] != 0u);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this warp's staged rows -> visible to the bulk-copy engine
+#ifndef EOLC_TILE_CLOCKS
+                asm volatile("bar.sync 1, %0;" ::"n"(BAR1_THREADS) : "memory");
+#endif
+            }
 #ifdef EOLC_TILE_CLOCKS
             if (__syncthreads_or(0) == 12345) clk_acc[6] += 1000000;   // the instrumented build's blocking barrier between phases 2 and 3
 #endif
@@ -313,13 +332,13 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
             EOLC_SYNC();                 // [B1]
             EOLC_CLK(2)
             const int ta1 = (int)ctl[0];
-            tiles::phase2((int)tid, (int)NC, V, ctl[1] != 0u);
+            tiles::phase2((int)tid, tiles::P2THREADS, V, ctl[1] != 0u);
             EOLC_CLK(0)
 #ifdef EOLC_TILE_CLOCKS
             if (__syncthreads_or(0) == 12345) clk_acc[6] += 1000000;   // never true; see EOLC_SYNC (service warps take part in this build)
             EOLC_CLK(5)
 #else
-            asm volatile("bar.sync 1, %0;" ::"n"(tiles::NTHREADS) : "memory");   // compute warps only: off-diagonal and mass blocks staged
+            asm volatile("bar.sync 1, %0;" ::"n"(BAR1_THREADS) : "memory");   // every warp that ran phase-2 groups: off-diagonal and mass blocks staged
 #endif
             tiles::phase3((int)tid, (int)NC, V);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk-copy engine

@@ -122,7 +122,10 @@ namespace tiles {
 #endif
 constexpr int NTHREADS = 256;        // compute threads per CTA: phase 1 evaluates one element per thread (stencils from thread 0 up, faces from
                                      // the last thread down), phases 2 and 3 run on the same threads
-constexpr int P2THREADS = NTHREADS;
+#ifndef EOLC_P2_WARPS
+#define EOLC_P2_WARPS 12             // warps that run phase-2 groups: 12 = the 8 compute warps + the service warpgroup, which would idle
+#endif                               // between the two barriers of a tile otherwise (8: compute warps only; -3 % with 12, experiments.md p12)
+constexpr int P2THREADS = 32 * EOLC_P2_WARPS;
 constexpr int CTA_THREADS = NTHREADS + 128;   // + one service warpgroup: stages the inputs of the tiles ahead, issues the bulk copy-out
 constexpr int CTAS_PER_SM = 1;
 constexpr int MAX_OWN = EOLC_TILE_OWN;   // nodes owned by a tile (<= 63: 6-bit fields)
