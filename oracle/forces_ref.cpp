@@ -43,6 +43,8 @@
 #include <vector>
 #include <algorithm>
 #include <chrono>
+#include <thread>
+#include <utility>
 
 // reference prototypes, exactly as in src/Compute*.h (C++ linkage)
 void ComputeMembrane(const double *xa, const double *xb, const double *xc,
@@ -252,8 +254,14 @@ void *oracle_forces_fill_eol(int N, int F, const int32_t *face_nodes, int E, con
     std::vector<Trip> M_, MDK_;                  // :916-917
     const double density = mat[0], e = mat[1], nu = mat[2], beta = mat[3], dampingB = mat[5];
 
+    // The two element loops are lambdas over an index range so that the TIMING variant (flags bits 8..15 = worker threads, bench.py's
+    // CPU legs) can run ranges on several threads; with one thread they run exactly as the reference's loops do.  fl != NULL: the
+    // f contributions are logged instead of added, and replayed in element order afterwards (same sums, bit for bit).
+    typedef std::vector<std::pair<int32_t, double>> FLog;
     // ---- faceBasedF, Forces.cpp:331-520 ----
-    for (int i = 0; i < F; ++i) {
+    auto do_faces = [&](int i_begin, int i_end, std::vector<Trip> &M_, std::vector<Trip> &MDK_, FLog *fl) {
+    auto fadd = [&](int at, double v) { if (fl) fl->push_back({at, v}); else R->f[at] += v; };
+    for (int i = i_begin; i < i_end; ++i) {
         const int ia = face_nodes[3 * i], ib = face_nodes[3 * i + 1], ic = face_nodes[3 * i + 2];
         const double *xa = x + 3 * ia, *xb = x + 3 * ib, *xc = x + 3 * ic;
         const double *Xa = X + 2 * ia, *Xb = X + 2 * ib, *Xc = X + 2 * ic;
@@ -297,8 +305,8 @@ void *oracle_forces_fill_eol(int N, int F, const int32_t *face_nodes, int E, con
             auto KE = [&](int r, int c) { return Kme[c * 15 + r]; };
             auto ME = [&](int r, int c) { return Mie[c * 15 + r]; };
             for (int v = 0; v < 3; ++v) {                                     // :405-412
-                for (int j = 0; j < 3; ++j) R->f[idx[v] + j] += fme[5 * v + j] + fie[5 * v + j];
-                if (eolv[v]) for (int j = 0; j < 2; ++j) R->f[Xdof(nodes[v]) + j] += fme[5 * v + 3 + j] + fie[5 * v + 3 + j];
+                for (int j = 0; j < 3; ++j) fadd(idx[v] + j, fme[5 * v + j] + fie[5 * v + j]);
+                if (eolv[v]) for (int j = 0; j < 2; ++j) fadd(Xdof(nodes[v]) + j, fme[5 * v + 3 + j] + fie[5 * v + 3 + j]);
             }
             // one (nr x nc) block at local (lr, lc) -> global (gr, gc); mirror = the fillxx / fillXX / fillXx / fillxX forms
             auto put = [&](int lr, int lc, int nr, int nc, int gr, int gc, bool mirror) {
@@ -328,7 +336,7 @@ void *oracle_forces_fill_eol(int N, int F, const int32_t *face_nodes, int E, con
             continue;
         }
         for (int v = 0; v < 3; ++v)                                           // :500-502
-            for (int j = 0; j < 3; ++j) R->f[idx[v] + j] += fm[3 * v + j] + fi[3 * v + j];
+            for (int j = 0; j < 3; ++j) fadd(idx[v] + j, fm[3 * v + j] + fi[3 * v + j]);
         const double dhh = dampingB * h * h;                                  // damping(1)*h*h, :105
         auto Kme = [&](int r, int c) { return Km[c * 9 + r]; };
         auto Mie = [&](int r, int c) { return Mi[c * 9 + r]; };
@@ -356,9 +364,12 @@ void *oracle_forces_fill_eol(int N, int F, const int32_t *face_nodes, int E, con
                 }
         }
     }
+    };
 
     // ---- edgeBasedF, Forces.cpp:685-910 ----
-    for (int ed = 0; ed < E; ++ed) {
+    auto do_edges = [&](int e_begin, int e_end, std::vector<Trip> &MDK_, FLog *fl, bool &bad) {
+    auto fadd = [&](int at, double v) { if (fl) fl->push_back({at, v}); else R->f[at] += v; };
+    for (int ed = e_begin; ed < e_end; ++ed) {
         const int32_t *s = edge_stencil + 4 * ed;
         if (s[2] < 0 || s[3] < 0) continue;                                   // :688-690
         double Wb[1], fb[12], Kb[144];
@@ -372,7 +383,7 @@ void *oracle_forces_fill_eol(int N, int F, const int32_t *face_nodes, int E, con
             // F = (deform_grad(adjf[0]) + deform_grad(adjf[1])) / 2, each in its face's own vertex order (:590-596)
             double F1[6], F2[6], Fg[6];
             const int f0 = find_face(s[0], s[1], s[2]), f1 = find_face(s[0], s[1], s[3]);
-            if (f0 < 0 || f1 < 0) { delete R; return nullptr; }
+            if (f0 < 0 || f1 < 0) { bad = true; return; }
             const int32_t *a0 = face_nodes + 3 * f0, *a1 = face_nodes + 3 * f1;
             deform_grad(x + 3 * a0[0], x + 3 * a0[1], x + 3 * a0[2], X + 2 * a0[0], X + 2 * a0[1], X + 2 * a0[2], F1);
             deform_grad(x + 3 * a1[0], x + 3 * a1[1], x + 3 * a1[2], X + 2 * a1[0], X + 2 * a1[1], X + 2 * a1[2], F2);
@@ -381,8 +392,8 @@ void *oracle_forces_fill_eol(int N, int F, const int32_t *face_nodes, int E, con
             expand_eol(4, fb, Kbe, Fg, eolv, fbe, Kbx);                       // fillEOLBending :748
             auto KX = [&](int r, int c) { return Kbx[c * 20 + r]; };
             for (int v = 0; v < 4; ++v) {                                     // :750-760
-                for (int j = 0; j < 3; ++j) R->f[idx[v] + j] += fbe[5 * v + j];
-                if (eolv[v]) for (int j = 0; j < 2; ++j) R->f[Xdof(s[v]) + j] += fbe[5 * v + 3 + j];
+                for (int j = 0; j < 3; ++j) fadd(idx[v] + j, fbe[5 * v + j]);
+                if (eolv[v]) for (int j = 0; j < 2; ++j) fadd(Xdof(s[v]) + j, fbe[5 * v + 3 + j]);
             }
             auto put = [&](int lr, int lc, int nr, int nc, int gr, int gc, bool mirror) {   // K?? = damping(1)*h*h*Kbe.block, fill?B
                 for (int j = 0; j < nr; ++j)
@@ -422,10 +433,52 @@ void *oracle_forces_fill_eol(int N, int F, const int32_t *face_nodes, int E, con
                 }
         }
     }
+    };
+    const int nthreads = std::max(1, (flags >> 8) & 0xff);
+    if (nthreads == 1) {
+        bool bad = false;
+        do_faces(0, F, M_, MDK_, nullptr);
+        do_edges(0, E, MDK_, nullptr, bad);
+        if (bad) { delete R; return nullptr; }
+    } else {
+        struct Part { std::vector<Trip> M, K; FLog f; bool bad = false; };
+        std::vector<Part> pf(nthreads), pe(nthreads);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() {
+                // sized for the Lagrangian branch (81 + 81 triplets per face, 144 per stencil); EOL elements grow the vectors a little
+                pf[t].M.reserve((size_t)81 * (F / nthreads + 1)); pf[t].K.reserve((size_t)81 * (F / nthreads + 1));
+                pe[t].K.reserve((size_t)144 * (E / nthreads + 1));
+                do_faces((int)((int64_t)F * t / nthreads), (int)((int64_t)F * (t + 1) / nthreads), pf[t].M, pf[t].K, &pf[t].f);
+                do_edges((int)((int64_t)E * t / nthreads), (int)((int64_t)E * (t + 1) / nthreads), pe[t].K, &pe[t].f, pe[t].bad);
+            });
+        for (auto &t : th) t.join();
+        for (int t = 0; t < nthreads; ++t) if (pe[t].bad) { delete R; return nullptr; }
+        // the reference's order: every face, then every edge
+        {
+            size_t nm = 0, nk = 0;
+            for (int t = 0; t < nthreads; ++t) { nm += pf[t].M.size(); nk += pf[t].K.size() + pe[t].K.size(); }
+            M_.reserve(nm); MDK_.reserve(nk);
+        }
+        for (int pass = 0; pass < 2; ++pass)
+            for (int t = 0; t < nthreads; ++t) {
+                Part &P = pass ? pe[t] : pf[t];
+                M_.insert(M_.end(), P.M.begin(), P.M.end());
+                MDK_.insert(MDK_.end(), P.K.begin(), P.K.end());
+                for (const auto &c : P.f) R->f[c.first] += c.second;
+                Part().M.swap(P.M); Part().K.swap(P.K);
+            }
+    }
     auto t1 = std::chrono::steady_clock::now();
     if (!(flags & 1)) {
-        set_from_triplets(dof, M_, R->M);                                     // :928
-        set_from_triplets(dof, MDK_, R->MDK);                                 // :929
+        if (nthreads == 1) {
+            set_from_triplets(dof, M_, R->M);                                 // :928
+            set_from_triplets(dof, MDK_, R->MDK);                             // :929
+        } else {                                                              // timing variant: the two matrices side by side
+            std::thread tm([&]() { set_from_triplets(dof, M_, R->M); });
+            set_from_triplets(dof, MDK_, R->MDK);
+            tm.join();
+        }
     }
     auto t2 = std::chrono::steady_clock::now();
     R->seconds_elements = std::chrono::duration<double>(t1 - t0).count();

@@ -111,9 +111,11 @@ H_DEFAULT = 0.5e-2
 
 
 def forces_fill(face_nodes, edge_stencil, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_DEFAULT, h=H_DEFAULT,
-                skip_assembly=False, eol_index=None):
+                skip_assembly=False, eol_index=None, threads=1):
     """Reference Forces::fill on flat arrays.  Returns dict(f, M=(outer, inner, vals), MDK=..., seconds=(el, asm)).
-    eol_index (N ints, -1 = Lagrangian, k >= 0 = Node::EoL_index) switches the touched elements to the EOL branch."""
+    eol_index (N ints, -1 = Lagrangian, k >= 0 = Node::EoL_index) switches the touched elements to the EOL branch.
+    threads > 1: TIMING variant for bench.py's CPU legs (the reference is single-threaded): the element loops run on that many
+    threads and the two setFromTriplets side by side; the triplet order and the sums are those of one thread, bit for bit."""
     L = lib()
     face_nodes = _i32(face_nodes).reshape(-1, 3)
     edge_stencil = _i32(edge_stencil).reshape(-1, 4)
@@ -125,7 +127,7 @@ def forces_fill(face_nodes, edge_stencil, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_
     eol = None if eol_index is None else _i32(eol_index).reshape(N)
     r = L.oracle_forces_fill_eol(N, face_nodes.shape[0], _i(face_nodes), edge_stencil.shape[0], _i(edge_stencil), _d(x),
                                  _d(X), _d(matv), _d(gv), float(h), None if eol is None else _i(eol),
-                                 1 if skip_assembly else 0)
+                                 (1 if skip_assembly else 0) | (max(1, min(int(threads), 255)) << 8))
     if not r:
         raise RuntimeError("oracle_forces_fill_eol: a bending stencil names a face the mesh does not have")
     try:

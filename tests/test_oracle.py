@@ -200,3 +200,19 @@ def test_eigen_cg_restatement_against_direct_solve(oracle):
     assert res < 1e-13 and 0 < it <= 2 * dof
     assert np.abs(sol - direct).max() <= 1e-9 * np.abs(direct).max()
     assert oracle.eigen_cg(ref["MDK"], np.zeros(dof))[1] == 0
+
+
+def test_threaded_timing_variant_is_bit_identical(oracle):
+    """bench.py's CPU legs run the oracle's element loops on several threads: same triplet sequence, same sums."""
+    X, fn = E.meshgen.regular2(40)
+    es = E.meshgen.edge_stencils(X.shape[0], fn)
+    x = E.meshgen.drape_state(X, seed=4)
+    eol = np.full(X.shape[0], -1, np.int32)
+    eol[np.arange(1, 39) * 40 + 20] = np.arange(38)
+    for e in (None, eol):
+        a = oracle.forces_fill(fn, es, x, X, eol_index=e)
+        b = oracle.forces_fill(fn, es, x, X, eol_index=e, threads=5)
+        assert a["f"].tobytes() == b["f"].tobytes()
+        for k in ("M", "MDK"):
+            for u, v in zip(a[k], b[k]):
+                assert u.tobytes() == v.tobytes()
