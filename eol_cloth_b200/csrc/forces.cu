@@ -157,6 +157,16 @@ constexpr int COMPUTE_REGS = EOLC_COMPUTE_REGS, SERVICE_REGS = EOLC_SERVICE_REGS
 static_assert(tiles::NTHREADS * COMPUTE_REGS + 128 * SERVICE_REGS <= tiles::CTA_THREADS * 168, "register pool of the CTA");
 constexpr bool SERVICE_P2 = tiles::P2THREADS > tiles::NTHREADS;   // the service warpgroup runs phase-2 groups too
 constexpr int BAR1_THREADS = SERVICE_P2 ? tiles::CTA_THREADS : tiles::NTHREADS;
+// Phase 3 (the diagonal blocks from the staged rows) on the service warpgroup: the compute warps go from the end of phase 2 straight
+// to phase 1 of the next tile.  Needs the service warps in phase 2 (they then pass the same barrier 1).
+#ifndef EOLC_SERVICE_P3
+#define EOLC_SERVICE_P3 1            // -1.7 % (0.736 -> 0.724 ms, A/B in one call, profiles/r01/experiments.md p3)
+#endif
+#if defined(EOLC_TILE_CLOCKS) || defined(EOLC_B2_FULL)
+constexpr bool SERVICE_P3 = false;
+#else
+constexpr bool SERVICE_P3 = SERVICE_P2 && (EOLC_SERVICE_P3 != 0);
+#endif
 
 __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemble_tiles_kernel(const __grid_constant__ TilesArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -300,7 +310,13 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
 #if defined(EOLC_TILE_CLOCKS) || defined(EOLC_B2_FULL)
             EOLC_SYNC();                 // [B2] staged rows complete
 #else
-            asm volatile("bar.sync 2, %0;" ::"n"(tiles::CTA_THREADS) : "memory");   // [B2] every compute thread has arrived: staged rows complete
+            if (SERVICE_P3) {
+                tiles::phase3((int)(tid - NC), tiles::CTA_THREADS - (int)NC, V);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(tiles::CTA_THREADS - tiles::NTHREADS) : "memory");   // [B2] the service warps: diagonal blocks staged
+            } else {
+                asm volatile("bar.sync 2, %0;" ::"n"(tiles::CTA_THREADS) : "memory");   // [B2] every compute thread has arrived: staged rows complete
+            }
 #endif
             EOLC_CLK(4)
 #ifndef EOLC_DEBUG_NO_COPYOUT
@@ -338,14 +354,17 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
             if (__syncthreads_or(0) == 12345) clk_acc[6] += 1000000;   // never true; see EOLC_SYNC (service warps take part in this build)
             EOLC_CLK(5)
 #else
+            // with phase 3 on the service warps nothing orders this warp's staged rows before their bulk copies after this barrier
+            if (SERVICE_P3) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("bar.sync 1, %0;" ::"n"(BAR1_THREADS) : "memory");   // every warp that ran phase-2 groups: off-diagonal and mass blocks staged
 #endif
-            tiles::phase3((int)tid, (int)NC, V);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk-copy engine
+            if (!SERVICE_P3) tiles::phase3((int)tid, (int)NC, V);
+            if (!SERVICE_P3) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows -> visible to the bulk-copy engine
             EOLC_CLK(3)
 #if defined(EOLC_TILE_CLOCKS) || defined(EOLC_B2_FULL)
             EOLC_SYNC();                 // [B2]
 #else
+            if (!SERVICE_P3)
             // [B2] arrive only: the compute warps go straight to phase 1 of the next tile (the scratch is free since the named barrier
             // above, the next tile's inputs landed before [B1]); the service warps wait here for the staged rows
             asm volatile("bar.arrive 2, %0;" ::"n"(tiles::CTA_THREADS) : "memory");
