@@ -51,6 +51,7 @@ struct eolc_forces_plan {
     bool smem_attr_set = false;
     // "tiles" pipeline
     int32_t n_tiles = 0, n_templates = 0;
+    bool service_p3 = false;
     uint32_t geo16 = 0, tmplA16 = 0, tmplB16 = 0, loc_max = 0, scr_doubles = 0, kstage = 0, mstage = 0;
     int64_t elem_evals = 0, geo_bytes = 0, tmpl_bytes = 0;
     DevBuf<uint4> d_geo, d_tmpl;
@@ -159,15 +160,16 @@ constexpr bool SERVICE_P2 = tiles::P2THREADS > tiles::NTHREADS;   // the service
 constexpr int BAR1_THREADS = SERVICE_P2 ? tiles::CTA_THREADS : tiles::NTHREADS;
 // Phase 3 (the diagonal blocks from the staged rows) on the service warpgroup: the compute warps go from the end of phase 2 straight
 // to phase 1 of the next tile.  Needs the service warps in phase 2 (they then pass the same barrier 1).
-#ifndef EOLC_SERVICE_P3
-#define EOLC_SERVICE_P3 1            // -1.7 % (0.736 -> 0.724 ms, A/B in one call, profiles/r01/experiments.md p3)
-#endif
+// Decided per plan (eolc_forces_plan::service_p3 picks the instantiation): it pays when nearly every tile is a full one (1024^2 sheet: -1.7 %, 0.736 -> 0.724 ms)
+// and costs when many tiles are light boundary tiles whose phase 1 is shorter than the service warps' chain (4096 x 64^2 ensemble:
+// +2.5 %); profiles/r01/experiments.md p3.  EOLC_FORCES_P3=0|1 overrides.
 #if defined(EOLC_TILE_CLOCKS) || defined(EOLC_B2_FULL)
-constexpr bool SERVICE_P3 = false;
+constexpr bool SERVICE_P3_BUILD = false;
 #else
-constexpr bool SERVICE_P3 = SERVICE_P2 && (EOLC_SERVICE_P3 != 0);
+constexpr bool SERVICE_P3_BUILD = SERVICE_P2;
 #endif
 
+template <bool P3_ARG>
 __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemble_tiles_kernel(const __grid_constant__ TilesArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t ctl[2];          // service -> compute warps: [0] template A buffer of the NEXT tile, [1] m_full of the current tile
@@ -182,6 +184,7 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
     const uint32_t geo16 = A.geo16, tmplA16 = A.tmplA16, loc_max = A.loc_max;
     const uint32_t n_tiles = A.n_tiles, n_work = A.n_work, step = gridDim.x;
     constexpr uint32_t NC = tiles::NTHREADS, NCW = NC / 32;   // compute threads / warps; warps NCW .. NCW+3 are the service warpgroup
+    constexpr bool SERVICE_P3 = SERVICE_P3_BUILD && P3_ARG;   // two instantiations; a run-time flag cost the gain (experiments.md p3)
     constexpr int GSTAGES = 4;
 
     auto geo_hdr = [&](int stage) { return reinterpret_cast<const uint32_t *>(Gst + (uint32_t)stage * geo16); };
@@ -401,6 +404,17 @@ int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st,
     P->scr_doubles = (tp.max_scratch + 1) & ~1u;
     P->kstage = (tp.max_kstage + 1) & ~1u; P->mstage = (tp.max_mstage + 1) & ~1u;
     P->elem_evals = tp.elem_evals;
+    {
+        // phase 3 on the service warps when at least 85 % of the tiles carry at least 95 % of the heaviest tile's elements (interior
+        // tiles of a structured sheet: 233 elements, tiles on its boundary: 205)
+        uint32_t mx = 0;
+        for (uint16_t c : tp.tile_elems) mx = std::max<uint32_t>(mx, c);
+        size_t full = 0;
+        for (uint16_t c : tp.tile_elems) full += (uint32_t)c * 100u >= mx * 95u ? 1 : 0;
+        P->service_p3 = !tp.tile_elems.empty() && full * 100 >= tp.tile_elems.size() * 85;
+        const char *ev = getenv("EOLC_FORCES_P3");
+        if (ev) P->service_p3 = atoi(ev) != 0;
+    }
     P->geo_bytes = (int64_t)tp.geo.size() * 4; P->tmpl_bytes = (int64_t)tp.tmpl.size() * 4;
     if (tiles_smem_bytes(P) > (size_t)227 * 1024) { set_error("tile plan needs %zu bytes of shared memory", tiles_smem_bytes(P)); return EOLC_ERR_UNSUPPORTED; }
     static_assert(sizeof(uint4) == 16, "uint4");
@@ -882,7 +896,8 @@ int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X
         const int grid = (int)std::min<long long>(n_work, (long long)P->ctx->sm_count * tiles::CTAS_PER_SM);
         const size_t smem = tiles_smem_bytes(P);
         if (!P->smem_attr_set) {
-            EOLC_CUDA(cudaFuncSetAttribute(assemble_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            EOLC_CUDA(cudaFuncSetAttribute(assemble_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            EOLC_CUDA(cudaFuncSetAttribute(assemble_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             P->smem_attr_set = true;
         }
         TilesArgs A;
@@ -898,7 +913,8 @@ int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X
         P->dbg_grid = grid;
         A.dbg = P->d_dbg.p;
 #endif
-        assemble_tiles_kernel<<<grid, tiles::CTA_THREADS, smem, st>>>(A);
+        if (P->service_p3) assemble_tiles_kernel<true><<<grid, tiles::CTA_THREADS, smem, st>>>(A);
+        else assemble_tiles_kernel<false><<<grid, tiles::CTA_THREADS, smem, st>>>(A);
         EOLC_CUDA(cudaGetLastError());
         return P->n_eol ? launch_eol(P, S, x, X, mat, grav, dhh, f, Mv, Kv) : EOLC_OK;
     }

@@ -188,6 +188,7 @@ struct Plan {
     uint32_t max_geo16 = 0, max_tmplA16 = 0, max_tmplB16 = 0, max_loc = 0, max_scratch = 0, max_kstage = 0, max_mstage = 0, max_fstage = 0;
     int64_t elem_evals = 0;            // element evaluations per fill (>= F + Ei because of halo re-evaluation)
     int64_t n_runs = 0, n_groups = 0, pull_rows = 0;   // statistics
+    std::vector<uint16_t> tile_elems;                  // elements evaluated per tile (faces + stencils, saturated), tile order
     std::string error;
 };
 
@@ -624,6 +625,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             const int nE = (int)edges.size(), nF = (int)faces.size();
             const int fbase = ZPAD + nE * EDGE_STRIDE;
             Q.elem_evals += nE + nF;
+            Q.tile_elems.push_back((uint16_t)std::min(nE + nF, 0xffff));
             Q.max_scratch = std::max<uint32_t>(Q.max_scratch, (uint32_t)(fbase + nF * FACE_STRIDE));
             // local node table: owned nodes first (ascending), then halo nodes by first appearance; element -> slot maps
             ++Bw.stamp;
@@ -944,6 +946,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         P.max_geo16 = std::max(P.max_geo16, Q.max_geo16); P.max_tmplA16 = std::max(P.max_tmplA16, Q.max_tmplA16); P.max_tmplB16 = std::max(P.max_tmplB16, Q.max_tmplB16);
         P.max_loc = std::max(P.max_loc, Q.max_loc); P.max_scratch = std::max(P.max_scratch, Q.max_scratch);
         P.max_kstage = std::max(P.max_kstage, Q.max_kstage); P.max_mstage = std::max(P.max_mstage, Q.max_mstage); P.max_fstage = std::max(P.max_fstage, Q.max_fstage);
+        P.tile_elems.insert(P.tile_elems.end(), Q.tile_elems.begin(), Q.tile_elems.end());
         P.elem_evals += Q.elem_evals; P.n_runs += Q.n_runs; P.n_groups += Q.n_groups; P.pull_rows += Q.pull_rows;
     }
     {
