@@ -279,3 +279,41 @@ def test_eol_256_line_and_batched(ctx, oracle):
     with pytest.raises(E.EolcError):            # the device consumers work on the Lagrangian block structure only
         plan.rhs_dev(Mo.data_ptr(), fo.data_ptr(), fo.data_ptr(), H, fo.data_ptr())
     plan.close()
+
+
+def test_eol_512_properties(ctx):
+    """Size-independent properties of the EOL fill on a 512x512 sheet with 510 EoL nodes (no oracle at this size): the 3N x 3N part
+    and the face forces are the Lagrangian fill's; M exactly and MDK to rounding symmetric including the Eulerian rows; every row of
+    the stiffness part — Eulerian rows too, (X_v, x_w) = -F^T K_vw — annihilates rigid translations of the Lagrangian dofs."""
+    import scipy.sparse as sp
+    mesh = _eol_mesh("regular2", 512, "line")
+    N = mesh["x"].shape[0]
+    lag = E.Forces(ctx).fill({k: v for k, v in mesh.items() if k != "eol_index"}, MAT, GRAV, H)
+    eol = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    dof = 3 * N + 2 * 510
+    assert eol.f.size == dof and eol.M[0].size == dof + 1
+    L = 3 * N
+    Ml = sp.csc_matrix((lag.M[2], lag.M[1], lag.M[0]), shape=(L, L))
+    Kl = sp.csc_matrix((lag.MDK[2], lag.MDK[1], lag.MDK[0]), shape=(L, L))
+    Me = sp.csc_matrix((eol.M[2], eol.M[1], eol.M[0]), shape=(dof, dof))
+    Ke = sp.csc_matrix((eol.MDK[2], eol.MDK[1], eol.MDK[0]), shape=(dof, dof))
+    scale = abs(Kl).max()
+    for A, B, what in ((Me[:L, :L], Ml, "M"), (Ke[:L, :L], Kl, "MDK")):
+        A = A.tocsc(); A.sort_indices()
+        assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices), what
+        # the coupled nodes' tiles use other templates (row destinations moved): the same sums, possibly in another order
+        assert np.abs(A.data - B.data).max() <= 1e-13 * scale, what
+    assert abs(Me - Me.T).max() <= 1e-18 + 1e-15 * abs(Me).max()       # F^T (m I) F fills its 2x2 entry by entry
+    assert abs(Ke - Ke.T).max() <= 1e-13 * scale
+    T = sp.csr_matrix(np.tile(np.eye(3), (N, 1)))
+    dK = (Ke - Me)[:, :L] @ T
+    assert abs(dK).max() < 1e-9 * scale
+    # f: the Lagrangian entries differ only by the bending force of the stencils that hold an EoL node
+    touched = np.zeros(N, bool)
+    es = mesh["edge_stencil"]
+    inner = es[(es[:, 2] >= 0) & (es[:, 3] >= 0)]
+    hit = (mesh["eol_index"][inner] >= 0).any(axis=1)
+    touched[inner[hit].reshape(-1)] = True
+    diff = (eol.f[:L] != lag.f).reshape(N, 3).any(axis=1)
+    assert diff.any() and not (diff & ~touched).any()
+    assert np.isfinite(eol.f).all() and np.abs(eol.f[L:]).max() > 0
