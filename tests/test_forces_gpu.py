@@ -317,3 +317,26 @@ def test_eol_512_properties(ctx):
     diff = (eol.f[:L] != lag.f).reshape(N, 3).any(axis=1)
     assert diff.any() and not (diff & ~touched).any()
     assert np.isfinite(eol.f).all() and np.abs(eol.f[L:]).max() > 0
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_eol_random_triangulation_matches_oracle(ctx, oracle, seed):
+    """Irregular Delaunay mesh, a random third of the nodes EoL (faces / stencils with 1..4 EoL vertices), against the oracle."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(100 + seed)
+    n = 60 + 25 * seed
+    X = rng.uniform(0, 1, (n, 2))
+    tri = Delaunay(X).simplices.astype(np.int32)
+    a, b, c = X[tri[:, 0]], X[tri[:, 1]], X[tri[:, 2]]
+    cr = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0])
+    tri[cr < 0] = tri[cr < 0][:, [0, 2, 1]]
+    tri = tri[np.abs(cr) > 1e-4]
+    es = E.meshgen.edge_stencils(n, tri)
+    x = np.c_[X, 0.1 * np.sin(4 * X[:, 0]) * np.cos(3 * X[:, 1])] + 2e-3 * rng.standard_normal((n, 3))
+    eol = np.full(n, -1, np.int32)
+    chosen = rng.choice(n, n // 3, replace=False)
+    eol[chosen] = rng.permutation(len(chosen))
+    mesh = dict(x=x, X=X, face_nodes=tri, edge_stencil=es, eol_index=eol)
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    ref = oracle.forces_fill(tri, es, x, X, tuple(MAT), GRAV, H, eol_index=eol)
+    _check(forces, ref, n, f"eol delaunay {seed}")

@@ -246,3 +246,29 @@ def test_tiles_host_eol_shuffled_numbering_and_faceless_eol_node(oracle, hostmat
     o, _ = T.pattern(1)
     assert o[3 * N] == o[3 * N + 1] == o[3 * N + 2]
     T.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_tiles_host_eol_random_triangulations(oracle, hostmath, seed):
+    """Irregular meshes (Delaunay triangulations of random points: valences 3..10, no structure for the templates to share) with a random
+    third of the nodes EoL, so that faces and stencils with 1, 2, 3 and 4 EoL vertices all occur."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(100 + seed)
+    n = 60 + 25 * seed
+    X = rng.uniform(0, 1, (n, 2))
+    tri = Delaunay(X).simplices.astype(np.int32)
+    # counter-clockwise faces
+    a, b, c = X[tri[:, 0]], X[tri[:, 1]], X[tri[:, 2]]
+    flip = ((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0])) < 0
+    tri[flip] = tri[flip][:, [0, 2, 1]]
+    area = np.abs((b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (c[:, 0] - a[:, 0]))
+    tri = tri[area > 1e-4]                       # slivers on the hull would only test the conditioning of DX^-1
+    es = E.meshgen.edge_stencils(n, tri)
+    x = np.c_[X, 0.1 * np.sin(4 * X[:, 0]) * np.cos(3 * X[:, 1])] + 2e-3 * rng.standard_normal((n, 3))
+    eol = np.full(n, -1, np.int32)
+    chosen = rng.choice(n, n // 3, replace=False)
+    eol[chosen] = rng.permutation(len(chosen))
+    T = HostTiles(hostmath, n, tri, es, X, True, eol_index=eol)
+    _check(T, tri, es, x, X, oracle, f"eol delaunay {seed}", eol_index=eol)
+    _check(T, tri, es, x, X, oracle, f"eol delaunay {seed} odd phases", phases=(1, 1, 1), eol_index=eol)
+    T.close()
