@@ -57,6 +57,7 @@ def lib():
     L.eolc_mesh_normals_dev.argtypes = [c_vp, c_vp, c_vp, c_vp]
     L.eolc_forces_rhs_dev.argtypes = [c_vp, c_vp, c_vp, c_vp, ctypes.c_double, c_vp]
     L.eolc_forces_integrate_dev.argtypes = [c_vp, c_vp, ctypes.c_double, c_vp]
+    L.eolc_forces_integrate_X_dev.argtypes = [c_vp, c_vp, ctypes.c_double, c_vp]
     L.eolc_solve_cg_dev.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_double, ctypes.c_int32, c_ip, c_dp]
     L.eolc_cd_plan_create.argtypes = [c_vp, ctypes.c_int32, ctypes.c_int32, c_ip, ctypes.c_double, ctypes.POINTER(c_vp)]
     L.eolc_cd_plan_destroy.argtypes = [c_vp]

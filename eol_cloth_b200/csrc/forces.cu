@@ -68,6 +68,8 @@ struct eolc_forces_plan {
     PinnedBuf<double> p_in, p_out;
     // block structure on the device + CG work vectors (solve.cuh), built on first use
     DevBuf<int32_t> d_blkM, d_nbrM, d_blkK, d_nbrK;
+    std::vector<int32_t> h_eol_index;             // N, EOL plans only
+    DevBuf<int32_t> d_outerM, d_innerM, d_outerK, d_innerK, d_eol_index;   // scalar structure of an EOL plan for the device consumers, built on first use
     DevBuf<int32_t> d_fn, d_nfp;                  // face nodes and node -> incident faces (CSR) for the normals, built on first use
     DevBuf<uint32_t> d_nfl;
     DevBuf<double> d_fnorm, d_nnorm;              // staging of the host entry point
@@ -851,6 +853,7 @@ int build_eol_plan(eolc_forces_plan *P, const int32_t *eol_index, eol::Plan &ep,
         return EOLC_ERR_UNSUPPORTED;
     }
     P->n_eol = ep.n_eol; P->dof = ep.dof; P->nnzM = ep.nnzM; P->nnzK = ep.nnzK;
+    P->h_eol_index.assign(eol_index, eol_index + P->N);
     P->eol_faces = ep.n_faces(); P->eol_edges = ep.n_edges(); P->eol_targets = (int32_t)ep.targets.size(); P->eol_scratch = ep.scratch_doubles;
     EOLC_CUDA(P->d_eol_faces.alloc(ep.faces.size())); EOLC_CUDA(P->d_eol_edges.alloc(ep.edges.size()));
     EOLC_CUDA(P->d_eol_targets.alloc(ep.targets.size())); EOLC_CUDA(P->d_eol_sources.alloc(ep.sources.size()));
@@ -1036,7 +1039,15 @@ int eolc_debug_tile_clocks(eolc_forces_plan *plan, unsigned long long *out, int 
 
 // ---- consumer of the fill on the device: right-hand side and the collision-free CG branch (solve.cuh) ----
 static int ensure_block_structure(eolc_forces_plan *P) {
-    if (P->n_eol) { set_error("the device consumers (rhs / CG / integrate) work on the Lagrangian block structure; this plan has EoL nodes"); return EOLC_ERR_UNSUPPORTED; }
+    if (P->n_eol) {      // EOL plan: the consumers walk the scalar arrays (solve.cuh, *_csr kernels)
+        if (P->d_outerK.p) return EOLC_OK;
+        cudaStream_t st = P->ctx->stream;
+        EOLC_CUDA(P->d_outerM.upload(P->h_outerM, st)); EOLC_CUDA(P->d_innerM.upload(P->h_innerM, st));
+        EOLC_CUDA(P->d_outerK.upload(P->h_outerK, st)); EOLC_CUDA(P->d_innerK.upload(P->h_innerK, st));
+        EOLC_CUDA(P->d_eol_index.upload(P->h_eol_index, st));
+        EOLC_CUDA(cudaStreamSynchronize(st));
+        return EOLC_OK;
+    }
     if (P->d_blkK.p || P->N == 0) return EOLC_OK;
     cudaStream_t st = P->ctx->stream;
     std::vector<int32_t> bm(P->pat.blkptrM.begin(), P->pat.blkptrM.end()), bk(P->pat.blkptrK.begin(), P->pat.blkptrK.end());
@@ -1053,6 +1064,12 @@ int eolc_forces_rhs_dev(eolc_forces_plan *plan, const double *M_vals_dev, const 
     EOLC_CUDA(cudaSetDevice(plan->ctx->device));
     int rc = ensure_block_structure(plan);
     if (rc) return rc;
+    if (plan->n_eol) {
+        const int gridr = std::min((plan->dof + solve::WARPS - 1) / solve::WARPS, 16 * plan->ctx->sm_count);
+        solve::k_rhs_csr<<<gridr, solve::THREADS, 0, plan->ctx->stream>>>(plan->dof, plan->d_outerM.p, plan->d_innerM.p, M_vals_dev, f_dev, v_dev, h, b_dev);
+        EOLC_CUDA(cudaGetLastError());
+        return EOLC_OK;
+    }
     const int grid = std::min((plan->N + 2 * solve::WARPS - 1) / (2 * solve::WARPS), 16 * plan->ctx->sm_count);
     solve::k_rhs<<<grid, solve::THREADS, 0, plan->ctx->stream>>>(plan->N, plan->d_blkM.p, plan->d_nbrM.p, M_vals_dev, f_dev, v_dev, h, b_dev);
     EOLC_CUDA(cudaGetLastError());
@@ -1067,6 +1084,19 @@ int eolc_forces_integrate_dev(eolc_forces_plan *plan, const double *v_dev, doubl
     const size_t n = (size_t)3 * plan->N;
     const int grid = (int)std::min<size_t>((n + solve::THREADS - 1) / solve::THREADS, (size_t)8 * plan->ctx->sm_count);
     solve::k_integrate<<<grid, solve::THREADS, 0, plan->ctx->stream>>>(n, x_dev, v_dev, h);
+    EOLC_CUDA(cudaGetLastError());
+    return EOLC_OK;
+}
+
+int eolc_forces_integrate_X_dev(eolc_forces_plan *plan, const double *v_dev, double h, double *X_dev) {
+    EOLC_REQUIRE(plan, "plan is NULL");
+    if (plan->N == 0 || plan->n_eol == 0) return EOLC_OK;
+    EOLC_REQUIRE(v_dev && X_dev, "NULL device pointer");
+    EOLC_CUDA(cudaSetDevice(plan->ctx->device));
+    int rc = ensure_block_structure(plan);
+    if (rc) return rc;
+    const int grid = (int)std::min<size_t>(((size_t)plan->N + solve::THREADS - 1) / solve::THREADS, (size_t)8 * plan->ctx->sm_count);
+    solve::k_integrate_X<<<grid, solve::THREADS, 0, plan->ctx->stream>>>(plan->N, plan->d_eol_index.p, X_dev, v_dev, h);
     EOLC_CUDA(cudaGetLastError());
     return EOLC_OK;
 }
@@ -1086,12 +1116,15 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
     cudaStream_t st = P->ctx->stream;
     const size_t n = (size_t)P->dof;
     const int gridv = (int)std::min<size_t>((n + solve::THREADS - 1) / solve::THREADS, (size_t)8 * P->ctx->sm_count);
-    const int gridn = std::min((P->N + 2 * solve::WARPS - 1) / (2 * solve::WARPS), 16 * P->ctx->sm_count);
+    const bool csr = P->n_eol != 0;
+    const int gridn = csr ? std::min((P->dof + solve::WARPS - 1) / solve::WARPS, 16 * P->ctx->sm_count)
+                          : std::min((P->N + 2 * solve::WARPS - 1) / (2 * solve::WARPS), 16 * P->ctx->sm_count);
     const size_t nparts = (size_t)2 * std::max(gridv, gridn);
     EOLC_CUDA(P->d_cg.ensure(4 * n + nparts + 8));
     EOLC_CUDA(P->p_sc.ensure(8));
     double *r = P->d_cg.p, *p = r + n, *Ap = p + n, *dinv = Ap + n, *part = dinv + n, *sc = part + nparts;
-    solve::k_cg_init<<<gridv, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, b_dev, fixed_dev, v_dev, r, p, dinv, part);
+    if (csr) solve::k_cg_init_csr<<<gridv, solve::THREADS, 0, st>>>(P->dof, P->d_outerK.p, P->d_innerK.p, MDK_vals_dev, b_dev, fixed_dev, v_dev, r, p, dinv, part);
+    else solve::k_cg_init<<<gridv, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, b_dev, fixed_dev, v_dev, r, p, dinv, part);
     solve::k_cg_scalars<<<1, solve::THREADS, 0, st>>>(gridv, 2, part, sc, 0, tol);
     int it = 0;
     const int check_every = 8;      // the convergence flag lives on the device; the host looks at it every few iterations
@@ -1101,7 +1134,8 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
     while (!done && it < max_iter) {
         const int batch = std::min(check_every, max_iter - it);
         for (int k = 0; k < batch; ++k) {
-            solve::k_cg_ap<<<gridn, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, p, dinv, Ap, part, sc);
+            if (csr) solve::k_cg_ap_csr<<<gridn, solve::THREADS, 0, st>>>(P->dof, P->d_outerK.p, P->d_innerK.p, MDK_vals_dev, p, dinv, Ap, part, sc);
+            else solve::k_cg_ap<<<gridn, solve::THREADS, 0, st>>>(P->N, P->d_blkK.p, P->d_nbrK.p, MDK_vals_dev, p, dinv, Ap, part, sc);
             solve::k_cg_scalars<<<1, solve::THREADS, 0, st>>>(gridn, 1, part, sc, 1, tol);
             solve::k_cg_update<<<gridv, solve::THREADS, 0, st>>>(n, v_dev, r, p, Ap, dinv, part, sc);
             solve::k_cg_scalars<<<1, solve::THREADS, 0, st>>>(gridv, 2, part, sc, 2, tol);

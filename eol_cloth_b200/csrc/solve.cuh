@@ -170,6 +170,69 @@ __global__ void __launch_bounds__(THREADS) k_integrate(size_t n, double *__restr
     for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) x[i] = x[i] + h * v[i];
 }
 
+// ---- scalar-CSR forms of the same three kernels for plans with Eulerian dofs (EOL meshes, forces_eol.h): the rows of a node coupled to
+// EoL nodes carry extra columns and the Eulerian rows have no block structure, so these walk Eigen's outer / inner arrays, a warp per
+// scalar row (4 index bytes per value instead of 4 per 72: EOL plans only).  Same fixed-order reductions.
+__global__ void __launch_bounds__(THREADS) k_rhs_csr(int dof, const int32_t *__restrict__ outer, const int32_t *__restrict__ inner,
+                                                     const double *__restrict__ Mv, const double *__restrict__ f, const double *__restrict__ v,
+                                                     double h, double *__restrict__ b) {
+    const int lane = threadIdx.x & 31;
+    for (int row = blockIdx.x * WARPS + (threadIdx.x >> 5); row < dof; row += gridDim.x * WARPS) {
+        double s = 0.0;
+        for (int k = outer[row] + lane; k < outer[row + 1]; k += 32) s += Mv[k] * v[inner[k]];
+        s = warp_sum(s);
+        if (lane == 0) b[row] = -(s + h * f[row]);
+    }
+}
+__global__ void __launch_bounds__(THREADS) k_cg_init_csr(int dof, const int32_t *__restrict__ outer, const int32_t *__restrict__ inner,
+                                                         const double *__restrict__ Kv, const double *__restrict__ b, const unsigned char *__restrict__ fixed,
+                                                         double *__restrict__ x, double *__restrict__ r, double *__restrict__ p, double *__restrict__ dinv,
+                                                         double *__restrict__ part) {
+    __shared__ double sh[WARPS];
+    double rz = 0.0, rr = 0.0;
+    for (size_t i = blockIdx.x * (size_t)THREADS + threadIdx.x; i < (size_t)dof; i += (size_t)gridDim.x * THREADS) {
+        int lo = outer[i], hi = outer[i + 1];
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (inner[mid] < (int)i) lo = mid + 1; else hi = mid; }   // the diagonal entry, if stored
+        const double akk = (lo < outer[i + 1] && inner[lo] == (int)i) ? Kv[lo] : 0.0;
+        double d = akk != 0.0 ? 1.0 / akk : 1.0;                 // Eigen's DiagonalPreconditioner: 1 where the diagonal is zero
+        if (fixed && fixed[i]) d = 0.0;
+        const double ri = d != 0.0 ? -b[i] : 0.0, zi = d * ri;
+        dinv[i] = d; x[i] = 0.0; r[i] = ri; p[i] = zi;
+        rz += ri * zi; rr += ri * ri;
+    }
+    const double t0 = block_sum(warp_sum(rz), sh), t1 = block_sum(warp_sum(rr), sh);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = t0; part[2 * blockIdx.x + 1] = t1; }
+}
+__global__ void __launch_bounds__(THREADS) k_cg_ap_csr(int dof, const int32_t *__restrict__ outer, const int32_t *__restrict__ inner,
+                                                       const double *__restrict__ Kv, const double *__restrict__ p, const double *__restrict__ dinv,
+                                                       double *__restrict__ Ap, double *__restrict__ part, const double *__restrict__ sc) {
+    __shared__ double sh[WARPS];
+    if (sc[6] != 0.0) return;
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int row = blockIdx.x * WARPS + (threadIdx.x >> 5); row < dof; row += gridDim.x * WARPS) {
+        double s = 0.0;
+        for (int k = outer[row] + lane; k < outer[row + 1]; k += 32) s += Kv[k] * p[inner[k]];
+        s = warp_sum(s);
+        if (lane == 0) {
+            const double yi = dinv[row] != 0.0 ? s : 0.0;
+            Ap[row] = yi;
+            acc += p[row] * yi;
+        }
+    }
+    const double t = block_sum(warp_sum(acc), sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+// Eulerian part of the position update (Cloth.cpp:401-407): vert->u += h * vert->v for the EoL nodes, v taken at 3N + 2 EoL_index
+__global__ void __launch_bounds__(THREADS) k_integrate_X(int N, const int32_t *__restrict__ eol_index, double *__restrict__ X, const double *__restrict__ v, double h) {
+    for (size_t a = blockIdx.x * (size_t)THREADS + threadIdx.x; a < (size_t)N; a += (size_t)gridDim.x * THREADS) {
+        const int k = eol_index[a];
+        if (k < 0) continue;
+        X[2 * a] = X[2 * a] + h * v[3 * (size_t)N + 2 * (size_t)k];
+        X[2 * a + 1] = X[2 * a + 1] + h * v[3 * (size_t)N + 2 * (size_t)k + 1];
+    }
+}
+
 // ---- per-step derived mesh data ------------------------------------------------------------------------------
 // face->n of compute_ws_data(Face*), /root/reference/src/external/ArcSim/mesh.cpp:135-140: normalize(cross(x1 - x0, x2 - x0)), with
 // ArcSim's normalize (vectors.hpp:111: the zero vector stays zero) and its sequential dot (vectors.hpp:108).  No FMA contraction here

@@ -105,6 +105,10 @@ class ForcesPlan:
         """x += h v on the device (Cloth::step, Cloth.cpp:394-400)."""
         capi.check(capi.lib().eolc_forces_integrate_dev(self._h, v_ptr, float(h), x_ptr))
 
+    def integrate_X_dev(self, v_ptr, h, X_ptr):
+        """X += h v_X for the EoL nodes on the device (Cloth::step, Cloth.cpp:401-407); no-op without EoL nodes."""
+        capi.check(capi.lib().eolc_forces_integrate_X_dev(self._h, v_ptr, float(h), X_ptr))
+
     def solve_cg_dev(self, Kv_ptr, b_ptr, v_ptr, tol=2.220446049250313e-16, max_iter=None, fixed_ptr=None):
         """v = ConjugateGradient(MDK).solve(-b) on the device (GeneralizedSolver.cpp:120-126, Eigen defaults: diagonal
         preconditioner, x0 = 0, tol = epsilon, at most 2 dof iterations).  fixed_ptr: optional device pointer to dof bytes, non-zero =

@@ -86,7 +86,7 @@ int eolc_mesh_edge_stencils(int32_t N, int32_t F, const int32_t *face_nodes, int
  * set_indices (src/Scene.cpp:87-90).  X_hint (2N, may be NULL) is used only to group nodes into
  * spatially compact tiles; results do not depend on it. eol_index (N, may be NULL): Node::EoL_index of the EoL nodes, -1 =
  * Lagrangian node; the indices must be distinct and EoL_Count = 1 + the largest (mesh.EoL_Count of the reference).  The
- * device consumers below (rhs / CG / integrate) accept Lagrangian plans only. */
+ * device consumers below work on both kinds of plan (block structure for Lagrangian plans, Eigen's scalar arrays for EOL plans). */
 int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face_nodes, int32_t E,
                             const int32_t *edge_stencil, const int32_t *eol_index, const double *X_hint,
                             eolc_forces_plan **out);
@@ -126,6 +126,9 @@ int eolc_solve_cg_dev(eolc_forces_plan *plan, const double *MDK_vals_dev, const 
                       double *v_dev, double tol, int32_t max_iter, int32_t *iters_out, double *rel_resid_out);
 /* Position update of Cloth::step (src/Cloth.cpp:394-400): x += h v for the 3N Lagrangian dofs.  Asynchronous on the stream. */
 int eolc_forces_integrate_dev(eolc_forces_plan *plan, const double *v_dev, double h, double *x_dev);
+/* Its Eulerian part (src/Cloth.cpp:401-407): vert->u += h vert->v for the EoL nodes, X_dev (2N) updated in place from the Eulerian
+ * entries of v_dev (dof).  No-op for a plan without EoL nodes. */
+int eolc_forces_integrate_X_dev(eolc_forces_plan *plan, const double *v_dev, double h, double *X_dev);
 /* ---- per-step derived mesh data ---------------------------------------------- */
 /* World-space normals of compute_ws_data (src/external/ArcSim/mesh.cpp:135-140, 142-143): face_n (3F) = normalize(cross(x1 - x0,
  * x2 - x0)); node_n (3N) = normal<WS>(node), src/external/ArcSim/geometry.cpp:302-316 (sum over the node's faces, in ascending face

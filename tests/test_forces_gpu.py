@@ -276,8 +276,6 @@ def test_eol_256_line_and_batched(ctx, oracle):
     assert fo[0].cpu().numpy().tobytes() == f.tobytes() and Ko[0].cpu().numpy().tobytes() == Kv.tobytes() and Mo[0].cpu().numpy().tobytes() == Mv.tobytes()
     fb, Mb, Kb = plan.fill(x2, mesh["X"], MAT, GRAV, H)
     assert fo[1].cpu().numpy().tobytes() == fb.tobytes() and Ko[1].cpu().numpy().tobytes() == Kb.tobytes() and Mo[1].cpu().numpy().tobytes() == Mb.tobytes()
-    with pytest.raises(E.EolcError):            # the device consumers work on the Lagrangian block structure only
-        plan.rhs_dev(Mo.data_ptr(), fo.data_ptr(), fo.data_ptr(), H, fo.data_ptr())
     plan.close()
 
 

@@ -117,3 +117,64 @@ def test_drape_steps_with_fixed_corners(ctx, oracle):
     assert np.abs(got - x_ref).max() <= 1e-9
     assert np.all(got[fixed_nodes] == x[fixed_nodes])        # the fixed corners did not move
     assert got[:, 2].min() < x[:, 2].min() - 1e-5             # the free part falls
+
+
+def test_eol_plan_rhs_cg_and_integrate(ctx, oracle):
+    """The consumers on a plan with EoL nodes (scalar-CSR kernels over Eigen's arrays): b = -(M v + h f) over all 3N + 2 EoL_Count dofs;
+    CG on MDK with the EoL nodes' Lagrangian dofs held (an EoL node slides along its box edge: x prescribed, X free — the unconstrained
+    EOL system is singular, [I, -F] has a null space per EoL node); X += h v_X for the EoL nodes."""
+    import torch
+    import scipy.sparse as sp
+    n = 24
+    X, fn = E.meshgen.regular2(n)
+    N = X.shape[0]
+    es = E.meshgen.edge_stencils(N, fn)
+    x = E.meshgen.drape_state(X, seed=n)
+    eol = np.full(N, -1, np.int32)
+    line = np.arange(1, n - 1) * n + n // 2
+    eol[line] = np.random.default_rng(1).permutation(line.size)
+    plan = E.ForcesPlan(ctx, N, fn, es, eol_index=eol, X_hint=X)
+    dof = plan.dof
+    assert dof == 3 * N + 2 * line.size
+    dev = torch.device("cuda", ctx.device)
+    xd, Xd = torch.from_numpy(x).to(dev), torch.from_numpy(X.copy()).to(dev)
+    fd = torch.empty(dof, dtype=torch.float64, device=dev)
+    Md = torch.empty(plan.nnz[0], dtype=torch.float64, device=dev)
+    Kd = torch.empty(plan.nnz[1], dtype=torch.float64, device=dev)
+    bd = torch.empty(dof, dtype=torch.float64, device=dev)
+    sold = torch.empty(dof, dtype=torch.float64, device=dev)
+    v = 0.1 * np.random.default_rng(n).standard_normal(dof)
+    vd = torch.from_numpy(v).to(dev)
+    torch.cuda.synchronize()
+    plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, fd.data_ptr(), Md.data_ptr(), Kd.data_ptr())
+    plan.rhs_dev(Md.data_ptr(), fd.data_ptr(), vd.data_ptr(), H, bd.data_ptr())
+    torch.cuda.synchronize()
+    ref = oracle.forces_fill(fn, es, x, X, tuple(MAT), GRAV, H, eol_index=eol)
+    b_ref = oracle.cloth_rhs(ref["M"], ref["f"], v, H)
+    b = bd.cpu().numpy()
+    assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    fixed = np.zeros(dof, np.uint8)
+    for a in line:
+        fixed[3 * a:3 * a + 3] = 1
+    fixd = torch.from_numpy(fixed).to(dev)
+    torch.cuda.synchronize()
+    it, res = plan.solve_cg_dev(Kd.data_ptr(), bd.data_ptr(), sold.data_ptr(), tol=1e-12, max_iter=4 * dof, fixed_ptr=fixd.data_ptr())
+    sol = sold.cpu().numpy()
+    sol_ref, it_ref, _ = oracle.eigen_cg(ref["MDK"], b_ref, tol=1e-12, max_iter=4 * dof, fixed=fixed.astype(bool))
+    assert res < 1e-12 and it_ref <= it <= it_ref + 8 + max(4, it_ref // 10), (it, it_ref, res)
+    assert np.all(sol[fixed != 0] == 0.0)
+    assert np.abs(sol - sol_ref).max() <= 1e-6 * np.abs(sol_ref).max()
+    o, i, vals = ref["MDK"]
+    K = sp.csc_matrix((vals, i, o), shape=(dof, dof)).tocsr()
+    free = np.flatnonzero(fixed == 0)
+    assert np.linalg.norm((K @ sol + b_ref)[free]) <= 1e-9 * np.linalg.norm(b_ref[free])
+    # x += h v (Lagrangian dofs), X += h v_X (EoL nodes): Cloth.cpp:394-407
+    plan.integrate_dev(sold.data_ptr(), H, xd.data_ptr())
+    plan.integrate_X_dev(sold.data_ptr(), H, Xd.data_ptr())
+    torch.cuda.synchronize()
+    X_new = X.copy()
+    for a in line:
+        X_new[a] += H * sol[3 * N + 2 * eol[a]:3 * N + 2 * eol[a] + 2]
+    assert np.allclose(Xd.cpu().numpy(), X_new, rtol=0, atol=1e-16)
+    assert np.allclose(xd.cpu().numpy().reshape(-1), x.reshape(-1) + H * sol[:3 * N], rtol=0, atol=1e-15)
+    plan.close()
