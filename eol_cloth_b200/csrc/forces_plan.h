@@ -443,6 +443,13 @@ inline void optimize_template(uint32_t *T, uint32_t sizeA16, int iters) {
     }
 }
 
+// host threads the plan build may use: EOLC_PLAN_THREADS, else the hardware concurrency capped at 16
+inline int n_workers_hw() {
+    const char *ev = getenv("EOLC_PLAN_THREADS");
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1, ev ? atoi(ev) : (int)std::min<unsigned>(hw ? hw : 1u, 16u));
+}
+
 // Where the rows of M / MDK go when they are not simply 9 * blkptr[node] apart: EOL meshes (forces_eol.h), whose Lagrangian rows
 // carry `extra` Eulerian columns behind their 3x3 blocks.  dst = value index of the node's first scalar row.
 struct RowLayout {
@@ -914,13 +921,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         geo_off.push_back((uint32_t)(Q.geo.size() / 4));
         return true;
     };
-    int n_workers = 1;
-    {
-        const char *ev = getenv("EOLC_PLAN_THREADS");
-        const unsigned hw = std::thread::hardware_concurrency();
-        n_workers = ev ? atoi(ev) : (int)std::min<unsigned>(hw ? hw : 1u, 16u);
-        n_workers = std::max(1, std::min<int>(n_workers, (int)(leaves.size() / 64)));
-    }
+    int n_workers = std::max(1, std::min<int>(n_workers_hw(), (int)(leaves.size() / 64)));
     std::vector<Plan> parts((size_t)n_workers);
     std::vector<std::vector<uint32_t>> part_geo_off((size_t)n_workers);
     std::vector<std::vector<std::pair<uint32_t, uint32_t>>> part_unique((size_t)n_workers);
@@ -1004,7 +1005,18 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         const char *ob = getenv("EOLC_PLAN_BANK_ITERS");
         const long budget = ob ? atol(ob) : 4000;
         const int iters = (int)std::max<long>(0, std::min<long>(budget, 400000 / (long)std::max<size_t>(1, unique_tmpl.size())));
-        for (const auto &u : unique_tmpl) optimize_template(P.tmpl.data() + (size_t)u.first * 4, u.second, iters < 20 ? 0 : iters);
+        // templates are disjoint ranges of P.tmpl: one worker per slice of the list, same result for any worker count
+        const int nw = std::max(1, std::min<int>(n_workers_hw(), (int)unique_tmpl.size()));
+        auto slice = [&](int w) {
+            for (size_t k = (size_t)w; k < unique_tmpl.size(); k += (size_t)nw)
+                optimize_template(P.tmpl.data() + (size_t)unique_tmpl[k].first * 4, unique_tmpl[k].second, iters < 20 ? 0 : iters);
+        };
+        if (nw == 1) slice(0);
+        else {
+            std::vector<std::thread> th;
+            for (int w = 0; w < nw; ++w) th.emplace_back(slice, w);
+            for (auto &t : th) t.join();
+        }
     }
     return true;
 }
