@@ -407,13 +407,7 @@ int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st,
     P->kstage = (tp.max_kstage + 1) & ~1u; P->mstage = (tp.max_mstage + 1) & ~1u;
     P->elem_evals = tp.elem_evals;
     {
-        // phase 3 on the service warps when at least 85 % of the tiles carry at least 95 % of the heaviest tile's elements (interior
-        // tiles of a structured sheet: 233 elements, tiles on its boundary: 205)
-        uint32_t mx = 0;
-        for (uint16_t c : tp.tile_elems) mx = std::max<uint32_t>(mx, c);
-        size_t full = 0;
-        for (uint16_t c : tp.tile_elems) full += (uint32_t)c * 100u >= mx * 95u ? 1 : 0;
-        P->service_p3 = !tp.tile_elems.empty() && full * 100 >= tp.tile_elems.size() * 85;
+        P->service_p3 = tiles::mostly_full_tiles(tp);
         const char *ev = getenv("EOLC_FORCES_P3");
         if (ev) P->service_p3 = atoi(ev) != 0;
     }

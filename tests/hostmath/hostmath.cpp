@@ -118,13 +118,14 @@ void *hm_plan_create(int32_t N, int32_t F, const int32_t *fn, int32_t E, const i
     return hm_plan_create_eol(N, F, fn, E, es, X_hint, dedup, nullptr, err, errlen);
 }
 void hm_plan_destroy(void *p) { delete (HmPlan *)p; }
-// info[16]: nnzM, nnzK, n_tiles, n_templates, elem_evals, geo bytes, template bytes, max scratch doubles, max loc, Ei, runs, groups, pull rows, max staging
+// info[17]: nnzM, nnzK, n_tiles, n_templates, elem_evals, geo bytes, template bytes, max scratch doubles, max loc, Ei, runs, groups, pull rows, max staging
 void hm_plan_info(void *p, int64_t *info) {
     HmPlan *P = (HmPlan *)p;
     info[0] = 9 * P->pat.nblkM; info[1] = 9 * P->pat.nblkK; info[2] = P->tp.n_tiles; info[3] = P->tp.n_templates; info[4] = P->tp.elem_evals;
     info[5] = (int64_t)P->tp.geo.size() * 4; info[6] = (int64_t)P->tp.tmpl.size() * 4; info[7] = P->tp.max_scratch; info[8] = P->tp.max_loc;
     if (P->has_eol) { info[0] = P->ep.nnzM; info[1] = P->ep.nnzK; }
     info[15] = P->has_eol ? P->ep.dof : 3 * P->N;
+    info[16] = tiles::mostly_full_tiles(P->tp) ? 1 : 0;
     info[9] = P->Ei; info[10] = P->tp.n_runs; info[11] = P->tp.n_groups; info[12] = P->tp.pull_rows; info[13] = P->tp.max_kstage; info[14] = P->tp.max_mstage;
 }
 void hm_plan_pattern(void *p, int which, int32_t *outer, int32_t *inner) {
