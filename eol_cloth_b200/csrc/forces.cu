@@ -11,7 +11,9 @@
 //   pull its contributions from shared memory in a fixed order and writes it ONCE to its fixed CSR slot (tile_exec.cuh).
 //   M and f come out of the same kernel.  No atomics, no scratch traffic: HBM sees x, X, the plan's index streams and each
 //   output value exactly once.  The inputs of the NEXT tile (node table, x / X gathers, template) are staged with cp.async
-//   while the current tile computes.
+//   while the current tile computes.  Warp roles: 8 compute warps (216 registers, setmaxnreg) run phases 1 and 2; the service
+//   warpgroup (4 warps, 72 registers) stages the next tiles, takes its share of the phase-2 groups, sums the diagonal blocks
+//   (phase 3, for plans of mostly full tiles: assemble_tiles_kernel<true>) and issues the bulk copy-out (cp.async.bulk).
 // Alternative pipeline "rows" (EOLC_FORCES_PIPELINE=rows, the previous design, kept for A/B measurements): a CTA owns a run
 //   of consecutive nodes, one thread per (node, incident element) evaluates that element's block ROW — every element is
 //   re-evaluated once per node it touches (3x / 4x), which made the kernel FP64-issue bound (profiles/r01).
