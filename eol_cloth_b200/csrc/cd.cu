@@ -24,6 +24,8 @@
 #include "common.h"
 #include "cd_math.cuh"
 #include <algorithm>
+#include <cmath>
+#include <cstring>
 #include <random>
 
 using namespace eolc;
@@ -59,12 +61,56 @@ struct BoxData {
     double edgeAngle[12];    // e1->angle
     double angleCD[12];      // acos(n1c.n1d)  (:906)
     double dx1[12][3], len1[12], tan1[12][3], nor1e[12][3];   // x1b-x1a, |dx1|, dx1/len1, normalized(n1c+n1d)
+    // The three acos() of section C (:879-887, :907-915) only feed threshold comparisons.  Their outcome is decided on the
+    // device in cosine space against critical doubles found on the host WITH THE HOST'S libm acos (the one a reference
+    // build on this machine calls), see angle_cuts(): identical decisions by construction, and no FP64 acos on the device.
+    double cosParHi, cosParLo;   // |acos c| < 2 deg  <=>  cosParHi <= c <= 1 ;  |pi - acos c| < 2 deg  <=>  -1 <= c <= cosParLo
+    double cosWedge[12];         // acos c - angleCD[k] > 2 deg  <=>  -1 <= c < cosWedge[k]  (c <= 1)
 };
+
+// ---- libm-exact angle decisions in cosine space ----------------------------------------------------
+// order-preserving map between doubles and integers (-0.0 and +0.0 share key 0)
+inline int64_t dkey(double d) { int64_t i; std::memcpy(&i, &d, 8); return i >= 0 ? i : INT64_MIN - i; }
+inline double dunkey(int64_t k) { int64_t i = k >= 0 ? k : INT64_MIN - k; double d; std::memcpy(&d, &i, 8); return d; }
+
+// pred is false ... false true ... true over the doubles of [-1, 1] (acos is monotone; libm's rounding cannot break that
+// further away from the switch than its error bound, and the WINDOW doubles on either side of it are checked one by one).
+// Returns the smallest c with pred(c); 2.0 when there is none.  ok = false if the window check fails.
+template <class P> double first_true(P pred, bool &ok) {
+    const int64_t WINDOW = 512;
+    int64_t lo = dkey(-1.0), hi = dkey(1.0);
+    if (pred(-1.0)) return -1.0;
+    if (!pred(1.0)) return 2.0;
+    while (hi - lo > 1) {
+        int64_t mid = lo + (hi - lo) / 2;
+        if (pred(dunkey(mid))) hi = mid; else lo = mid;
+    }
+    for (int64_t k = std::max(dkey(-1.0), hi - WINDOW); k <= std::min(dkey(1.0), hi + WINDOW); ++k)
+        if (pred(dunkey(k)) != (k >= hi)) ok = false;
+    return dunkey(hi);
+}
+
+const double kThreshAng = 2.0 * M_PI / 180.0;   // :877
+
+// global cuts (depend on libm only): computed once per process
+bool parallel_cuts(double &hi, double &lo) {
+    static bool done = false, good = true;
+    static double s_hi, s_lo;
+    if (!done) {
+        volatile double T = kThreshAng;   // keep the calls run-time libm calls (no compile-time folding)
+        s_hi = first_true([&](double c) { double angle = acos(c); return fabs(angle) < T; }, good);
+        double nf = first_true([&](double c) { double angle = acos(c); return !(fabs(M_PI - angle) < T); }, good);
+        s_lo = nf > 1.5 ? 1.0 : dunkey(dkey(nf) - 1);   // last c that still satisfies |pi - acos c| < T
+        done = true;
+    }
+    hi = s_hi; lo = s_lo;
+    return good;
+}
 
 V3 hcol(const double (*M)[3], int i) { return mk(M[i][0], M[i][1], M[i][2]); }
 
 // createBox + createFaceNormals + createVertNormals on the host (libm acos, as the reference)
-void make_box(BoxData &B, const double *whd, const double *E1) {
+bool make_box(BoxData &B, const double *whd, const double *E1) {
     double S[4] = {0.5 * whd[0], 0.5 * whd[1], 0.5 * whd[2], 1.0};
     double E[16];
     for (int c = 0; c < 4; ++c)
@@ -126,6 +172,13 @@ void make_box(BoxData &B, const double *whd, const double *E1) {
         B.tan1[k][0] = tan1.x; B.tan1[k][1] = tan1.y; B.tan1[k][2] = tan1.z;
         B.nor1e[k][0] = nor1.x; B.nor1e[k][1] = nor1.y; B.nor1e[k][2] = nor1.z;
     }
+    bool ok = parallel_cuts(B.cosParHi, B.cosParLo);
+    for (int k = 0; k < 12; ++k) {
+        // :906-915 with angleCD >= 0 (an acos; the `angleCD < 0` branch cannot be taken): reject iff angleCN - angleCD > threshAng
+        volatile double angleCD = B.angleCD[k], T = kThreshAng;
+        B.cosWedge[k] = first_true([&](double c) { double angleCN = acos(c); return !(angleCN - angleCD > T); }, ok);
+    }
+    return ok;
 }
 
 // ---- device helpers ------------------------------------------------------------------------------
@@ -510,20 +563,19 @@ __device__ bool test_edge_edge(int k1, const BoxData &B, V3 x2a, V3 x2b, V3 dx2,
     V3 dx1 = bcol(B.dx1, k1);
     double len1 = B.len1[k1];
     V3 tan1 = bcol(B.tan1, k1);
-    const double threshAng = 2.0 * M_PI / 180.0;
-    double angle = acos(dot(tan1, nor2));
-    if (fabs(angle) < threshAng || fabs(sub(M_PI, angle)) < threshAng) return false;
-    angle = acos(dv(dot(tan1, dx2), len2));
-    if (fabs(angle) < threshAng || fabs(sub(M_PI, angle)) < threshAng) return false;
+    // :877-887: acos(c) within 2 deg of 0 or pi, decided in cosine space against the host libm's critical doubles (BoxData);
+    // c outside [-1, 1] or NaN gives a NaN angle in the reference, which fails both comparisons
+    double c = dot(tan1, nor2);
+    if ((c >= B.cosParHi && c <= 1.0) || (c <= B.cosParLo && c >= -1.0)) return false;
+    c = dv(dot(tan1, dx2), len2);
+    if ((c >= B.cosParHi && c <= 1.0) || (c <= B.cosParLo && c >= -1.0)) return false;
     V3 nor = normalized(cross(dx1, dx2));
     V3 x1c = bcol(B.verts1, c_edgeVerts1[k1][2]), x1d = bcol(B.verts1, c_edgeVerts1[k1][3]);
     V3 n1c = bcol(B.faceNors1, c_edgeFaces1[k1][0]), n1d = bcol(B.faceNors1, c_edgeFaces1[k1][1]);
     V3 nor1 = bcol(B.nor1e, k1);
     if (dot(nor, nor1) < 0.0) nor = neg(nor);
-    double angleCD = B.angleCD[k1];
-    double angleCN = acos(dot(n1c, nor));
-    if (angleCD < 0.0) { angleCD = -angleCD; angleCN = -angleCN; }
-    if (angleCN < -threshAng || sub(angleCN, angleCD) > threshAng) return false;
+    c = dot(n1c, nor);   // :906-915: angleCN - angleCD > 2 deg (angleCN < -2 deg cannot happen: an acos)
+    if (c >= -1.0 && c <= 1.0 && c < B.cosWedge[k1]) return false;
     double u2c, u2d;
     int i2c = intersect_square(x2a, dx2, x1a, x1b, x1c, u2c);
     int i2d = intersect_square(x2a, dx2, x1b, x1a, x1d, u2d);
@@ -747,6 +799,16 @@ int eolc_cd_last_stats(const eolc_cd_plan *plan, int64_t *pair_tests, int32_t *l
     return EOLC_OK;
 }
 
+int eolc_cd_angle_cuts(const double *box_whd, const double *box_E, double *cuts14) {
+    EOLC_REQUIRE(box_whd && box_E && cuts14, "NULL argument");
+    BoxData B;
+    bool ok = make_box(B, box_whd, box_E);
+    cuts14[0] = B.cosParHi; cuts14[1] = B.cosParLo;
+    for (int k = 0; k < 12; ++k) cuts14[2 + k] = B.cosWedge[k];
+    if (!ok) { set_error("eolc_cd_angle_cuts: this libm's acos is not monotone next to a decision threshold"); return EOLC_ERR_UNSUPPORTED; }
+    return EOLC_OK;
+}
+
 int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32_t n_points, const double *pxyz,
                             const double *pnorms, int32_t n_boxes, const double *box_whd, const double *box_E,
                             int point_eol_flag, int remap_box_indices, eolc_contact *out, int32_t capacity,
@@ -781,7 +843,9 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
 
     // ---- constants to the device
     std::vector<BoxData> hb((size_t)nB);
-    for (int b = 0; b < nB; ++b) make_box(hb[b], box_whd + 3 * b, box_E + 16 * b);
+    for (int b = 0; b < nB; ++b)
+        if (!make_box(hb[b], box_whd + 3 * b, box_E + 16 * b))
+        { set_error("eolc_cd_run: this libm's acos is not monotone next to a decision threshold"); return EOLC_ERR_UNSUPPORTED; }
     EOLC_CUDA(P->d_boxes.ensure(std::max(nB, 1)));
     if (nB) EOLC_CUDA(cudaMemcpyAsync(P->d_boxes.p, hb.data(), sizeof(BoxData) * nB, cudaMemcpyHostToDevice, st));
     EOLC_CUDA(P->d_pxyz.ensure(3 * (size_t)std::max(nP, 1))); EOLC_CUDA(P->d_pnorms.ensure(3 * (size_t)std::max(nP, 1)));

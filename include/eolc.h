@@ -168,6 +168,16 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t n_scenes, const double *
                             const double *pxyz, const double *pnorms, int32_t n_boxes, const double *box_whd,
                             const double *box_E, int point_eol_flag, int remap_box_indices, eolc_contact *out,
                             int32_t capacity, int32_t *scene_offset);
+/* Host-only diagnostic (no GPU needed).  Section C's three acos() (src/boxTriCollision.cpp:879-887, :907-915) only feed
+ * threshold comparisons; the device decides them in cosine space against critical doubles that the host finds by bisection
+ * WITH ITS OWN libm acos (the function a reference build on the same machine calls), checking every double in a window on
+ * either side of each switch — so the contact set cannot differ from a libm-linked reference through acos rounding.
+ * cuts14 = [cosParHi, cosParLo, cosWedge[0..11]]:
+ *   |acos c| < 2 deg        <=>  cosParHi <= c <= 1
+ *   |pi - acos c| < 2 deg   <=>  -1 <= c <= cosParLo
+ *   acos c - acos(n1c.n1d of box edge k) > 2 deg  <=>  -1 <= c < cosWedge[k]   (and c <= 1)
+ * Returns EOLC_ERR_UNSUPPORTED if libm's acos is not monotone inside a window (eolc_cd_run then refuses to run). */
+int eolc_cd_angle_cuts(const double *box_whd, const double *box_E, double *cuts14);
 /* ---- consumer of the contact list ------------------------------------------ */
 /* Constraints::fill, contact part (src/Constraints.cpp:424-468): one inequality row per CD2 contact, in list order,
  *   (3,1) cloth vertex / box face : 3 entries  -nor1[k]               at column 3 verts2[0] + k

@@ -4,10 +4,14 @@
 // single-threaded, linking the reference's own raytri.cpp (intersect_triangle3_inc, compiled
 // UNMODIFIED from /root/reference/src into oracle/_ref/ by oracle/Makefile).
 //
-// PARITY UNPINNED by the reference's own tests (it ships none) and Eigen is absent, so
-// boxTriCollision.cpp / Collisions.cpp cannot be compiled here.  Pinned pieces: raytri.cpp is the reference's
-// object code; the libstdc++ mt19937 / uniform_real_distribution stream is checked against the known-answer
-// vector of SURVEY.md §8a; border cases of intersect_triangle3_inc are checked in tests/test_oracle.py.
+// PARITY PINNED TO THE REFERENCE'S OWN CODE: oracle/_ref/libbtc_ref.so is boxTriCollision.cpp + Collisions.cpp + raytri.cpp
+// compiled UNMODIFIED from /root/reference/src against oracle/mini_eigen (oracle/Makefile, oracle/ref_cd_driver.cpp), and
+// tests/test_cd_ref_pin.py requires this restatement to equal it in every field of every contact, bit for bit, on every case
+// where the reference is defined (its `int` edge hash overflows above ~19 k nodes).  The reference ships no tests or golden
+// vectors of its own.  What remains restated rather than run: the arithmetic inside Eigen's small-vector
+// operators (mini_eigen header; the contact set is shown not to depend on the one ambiguous detail, the reduction order).
+// This file exists because the GPU is also checked above the reference's size limit (256^2 ... 1024^2 sheets), where the
+// 64-bit key below continues the order the reference intends.
 //
 // Follows, line by line:
 //   createEdges        src/boxTriCollision.cpp:141-231   (DEVIATION: the sort key is int64; the reference's

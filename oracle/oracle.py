@@ -170,6 +170,118 @@ def cd(face_nodes, x, threshold, pxyz=None, pnorms=None, box_whd=None, box_E=Non
         capacity = n.value
 
 
+# ---- the reference's own collision code (oracle/_ref/libbtc_ref*.so: boxTriCollision.cpp, Collisions.cpp, raytri.cpp compiled
+# UNMODIFIED against oracle/mini_eigen by oracle/Makefile; prebuilt files travel to the GPU box) ---------------------------------
+_REFLIBS = {}
+
+
+def ref_lib(scalar_redux=False):
+    """libbtc_ref.so (Eigen 3.3 SSE2 reduction order) or libbtc_ref_scalar.so (non-vectorised order)."""
+    name = "libbtc_ref_scalar.so" if scalar_redux else "libbtc_ref.so"
+    if name in _REFLIBS:
+        return _REFLIBS[name]
+    path = os.path.join(_HERE, "_ref", name)
+    if not os.path.exists(path):
+        build()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing and /root/reference is not here to build it from")
+    L = ctypes.CDLL(path)
+    L.ref_cd.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_ip, ctypes.c_double, ctypes.c_int, c_dp, c_dp, ctypes.c_int,
+                         c_dp, c_dp, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.ref_btc_box.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, ctypes.c_double, c_dp, c_dp, ctypes.c_int,
+                              ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.ref_btc_points.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, ctypes.c_double, ctypes.c_int, c_dp, c_dp, ctypes.c_int,
+                                 ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    L.ref_btc_edges.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_ip, c_dp, c_ip, c_dp]
+    L.ref_btc_boxtables.argtypes = [c_dp] * 6
+    L.ref_btc_hash_defined.argtypes = [ctypes.c_int, ctypes.c_int]
+    assert L.ref_redux_order() == (1 if scalar_redux else 0)
+    _REFLIBS[name] = L
+    return L
+
+
+def ref_hash_defined(N, F):
+    """True while the reference's `int` edge hash (boxTriCollision.cpp:167-169) does not overflow: (3F+1)(N) + N < 2^31."""
+    return (3 * F + 1) * N + N < 2 ** 31 - 1
+
+
+def _ref_call(fn, N, *args):
+    capacity = N + 4096
+    while True:
+        out = np.zeros(capacity, dtype=CONTACT_DTYPE)
+        n = ctypes.c_int(0)
+        rc = fn(*args, out.ctypes.data_as(ctypes.c_void_p), capacity, ctypes.byref(n))
+        if rc == 0:
+            return out[:n.value].copy()
+        capacity = n.value
+
+
+def ref_cd(face_nodes, x, threshold, pxyz=None, pnorms=None, box_whd=None, box_E=None, which=0, eol=None, scalar_redux=False):
+    """The reference's CD (which=1, Collisions.cpp:11-53) / CD2 (which=0, :55-78), run as compiled from its own sources."""
+    L = ref_lib(scalar_redux)
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    N, F = x.shape[0], face_nodes.shape[0]
+    if box_whd is not None and len(box_whd) and not ref_hash_defined(N, F):
+        raise ValueError("the reference's int edge hash overflows (undefined behaviour) for this mesh size")
+    pxyz = _f64(np.zeros((0, 3)) if pxyz is None else pxyz).reshape(-1, 3)
+    pnorms = _f64(np.zeros((0, 3)) if pnorms is None else pnorms).reshape(-1, 3)
+    box_whd = _f64(np.zeros((0, 3)) if box_whd is None else box_whd).reshape(-1, 3)
+    box_E = _f64(np.zeros((0, 16)) if box_E is None else box_E).reshape(-1, 16)
+    eolv = None if eol is None else _i32(eol).reshape(N)
+    return _ref_call(L.ref_cd, N + 8 * box_whd.shape[0] + pxyz.shape[0], N, F, _i(face_nodes), _d(x),
+                     None if eolv is None else _i(eolv), float(threshold), pxyz.shape[0], _d(pxyz), _d(pnorms),
+                     box_whd.shape[0], _d(box_whd), _d(box_E), int(which))
+
+
+def ref_btc_box(face_nodes, x, threshold, whd, E1, EOL=False, scalar_redux=False):
+    """btc::boxTriCollision (boxTriCollision.cpp:603-1063) for one box; EOL=True skips section (A) (:674)."""
+    L = ref_lib(scalar_redux)
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    whd = _f64(whd).reshape(3)
+    E1 = _f64(E1).reshape(16)
+    return _ref_call(L.ref_btc_box, x.shape[0], x.shape[0], face_nodes.shape[0], _i(face_nodes), _d(x), float(threshold),
+                     _d(whd), _d(E1), int(bool(EOL)))
+
+
+def ref_btc_points(face_nodes, x, threshold, pxyz, pnorms, EOL=False, scalar_redux=False):
+    """btc::pointTriCollision (boxTriCollision.cpp:1067-1224)."""
+    L = ref_lib(scalar_redux)
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    pxyz = _f64(pxyz).reshape(-1, 3)
+    pnorms = _f64(pnorms).reshape(-1, 3)
+    return _ref_call(L.ref_btc_points, x.shape[0] + pxyz.shape[0], x.shape[0], face_nodes.shape[0], _i(face_nodes), _d(x),
+                     float(threshold), pxyz.shape[0], _d(pxyz), _d(pnorms), int(bool(EOL)))
+
+
+def ref_btc_edges(face_nodes, x, scalar_redux=False):
+    """btc::createEdges (boxTriCollision.cpp:141-231) -> (table [E,6] = verts(4)+faces(2), normals [E,6], internal [E], angle [E])."""
+    L = ref_lib(scalar_redux)
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    F = face_nodes.shape[0]
+    if not ref_hash_defined(x.shape[0], F):
+        raise ValueError("the reference's int edge hash overflows (undefined behaviour) for this mesh size")
+    tab = np.zeros((3 * F, 6), dtype=np.int32)
+    nrm = np.zeros((3 * F, 6), dtype=np.float64)
+    internal = np.zeros(3 * F, dtype=np.int32)
+    angle = np.zeros(3 * F, dtype=np.float64)
+    E = L.ref_btc_edges(x.shape[0], F, _i(face_nodes), _d(x), _i(tab), _d(nrm), _i(internal), _d(angle))
+    return tab[:E].copy(), nrm[:E].copy(), internal[:E].copy(), angle[:E].copy()
+
+
+def ref_btc_boxtables(whd, E1, scalar_redux=False):
+    """btc::createBox (boxTriCollision.cpp:400-420): verts1 (14,3), faceNors1 (24,3), vertNors1 (14,3), box edge angles (12)."""
+    L = ref_lib(scalar_redux)
+    whd = _f64(whd).reshape(3)
+    E1 = _f64(E1).reshape(16)
+    v, fnr, vn, ang = np.zeros((14, 3)), np.zeros((24, 3)), np.zeros((14, 3)), np.zeros(12)
+    L.ref_btc_boxtables(_d(whd), _d(E1), _d(v), _d(fnr), _d(vn), _d(ang))
+    return v, fnr, vn, ang
+
+
 def cd_edges(face_nodes, x):
     L = lib()
     face_nodes = _i32(face_nodes).reshape(-1, 3)

@@ -1,4 +1,6 @@
-"""Generates tests/golden/*.npz from the CPU oracle (reference Compute*.cpp / raytri.cpp object code + restated glue).
+"""Generates tests/golden/*.npz.  forces_* / normals_*: from the CPU oracle (reference Compute*.cpp / raytri.cpp object code +
+restated glue).  cd_*: from THE REFERENCE'S OWN collision code, oracle/_ref/libbtc_ref.so = boxTriCollision.cpp + Collisions.cpp +
+raytri.cpp compiled unmodified against oracle/mini_eigen (oracle/Makefile); `source` in the file says so.
 
 Run in the build container (where /root/reference exists):  python tests/golden/make_golden.py
 The fixtures pin (a) the oracle against silent drift and (b) the CUDA path on the GPU box, where the reference
@@ -41,9 +43,9 @@ def cd_case(gen, n, centre, seed, rot=None, points=False):
     if points:
         pxyz = np.array([[0.25, 0.25, x[:, 2].max() - 4e-3], [0.1, 0.8, -0.2], x[5] + 1e-3])
         pn = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0]])
-    out = {}
-    for name, flag, remap in (("cd", 1, 1), ("cd2", 0, 0)):
-        out[name] = O.cd(fn, x, E.meshgen.BOX_THRESHOLD, pxyz, pn, E.meshgen.BOX_WHD[None], E.meshgen.box_frame(centre, rot)[None], flag, remap)
+    out = {"source": np.array("libbtc_ref")}
+    for name, which in (("cd", 1), ("cd2", 0)):
+        out[name] = O.ref_cd(fn, x, E.meshgen.BOX_THRESHOLD, pxyz, pn, E.meshgen.BOX_WHD[None], E.meshgen.box_frame(centre, rot)[None], which)
     return out
 
 
