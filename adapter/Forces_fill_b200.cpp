@@ -21,6 +21,7 @@ struct Backend {
     eolc::host::FlatMesh flat;
 };
 Backend &backend_of(const Forces *self) {
+    eolc::host::Context::instance();   // constructed before the table below, hence destroyed after the plans it holds
     static thread_local std::vector<std::pair<const Forces *, std::unique_ptr<Backend> > > table;
     for (auto &e : table) if (e.first == self) return *e.second;
     table.emplace_back(self, std::unique_ptr<Backend>(new Backend));
@@ -30,8 +31,9 @@ Backend &backend_of(const Forces *self) {
 
 void Forces::fill(const Mesh &mesh, const Material &mat, const Eigen::Vector3d &grav, double h) {
     Backend &B = backend_of(this);
-    // Flatten the ArcSim pointer mesh.  flatten() re-reads the topology every call; fill() hashes it and
-    // rebuilds the device plan only when it changed (dynamic_remesh / preprocess, Scene.cpp:83-90).
+    // Flatten the ArcSim pointer mesh into page-locked arrays.  flatten() compares while it copies and renews
+    // B.flat's version counters only when an index / a material coordinate really changed; fill() rebuilds the device plan when
+    // the topology version moved (dynamic_remesh / preprocess, Scene.cpp:83-90) and skips M when X and the density did not.
     eolc::host::flatten(mesh, B.flat);
     // EoL nodes (flat.eol_index) switch the touched elements to the Eulerian-on-Lagrangian blocks (Forces.cpp:177-329, 399-497,
     // 580-683, 746-883) inside the library; dof = 3N + 2 (1 + largest EoL_index) must agree with mesh.EoL_Count.
@@ -49,6 +51,8 @@ void Forces::fill(const Mesh &mesh, const Material &mat, const Eigen::Vector3d &
     // The plan's pattern IS Eigen's compressed column-major layout (outerIndexPtr / innerIndexPtr / valuePtr), so the
     // matrices are assigned from a Map without any triplet pass.
     typedef Eigen::Map<const Eigen::SparseMatrix<double> > SpMap;
-    M = SpMap(dof, dof, (Eigen::Index)B.forces.M.nnz, B.forces.M.outer, B.forces.M.inner, B.forces.M.values.data());
+    // M depends on X and the density only (ComputeInertial.cpp:33,44-47): when neither changed the member still holds it
+    if (B.forces.M_updated || M.rows() != dof || M.nonZeros() != (Eigen::Index)B.forces.M.nnz)
+        M = SpMap(dof, dof, (Eigen::Index)B.forces.M.nnz, B.forces.M.outer, B.forces.M.inner, B.forces.M.values.data());
     MDK = SpMap(dof, dof, (Eigen::Index)B.forces.MDK.nnz, B.forces.MDK.outer, B.forces.MDK.inner, B.forces.MDK.values.data());
 }

@@ -52,6 +52,12 @@ def lib():
     L.eolc_forces_fill_dev.argtypes = [c_vp, c_vp, c_vp, ctypes.POINTER(MaterialC), c_dp, ctypes.c_double, c_vp, c_vp, c_vp]
     L.eolc_forces_fill_batched_dev.argtypes = [c_vp, ctypes.c_int32, c_vp, c_vp, ctypes.POINTER(MaterialC), c_dp,
                                                ctypes.c_double, c_vp, c_vp, c_vp]
+    L.eolc_forces_fill_ex.argtypes = [c_vp, c_dp, c_dp, ctypes.POINTER(MaterialC), c_dp, ctypes.c_double, c_dp, c_dp, c_dp, ctypes.c_uint32]
+    L.eolc_forces_fill_batched_dev_ex.argtypes = [c_vp, ctypes.c_int32, c_vp, c_vp, ctypes.POINTER(MaterialC), c_dp,
+                                                  ctypes.c_double, c_vp, c_vp, c_vp, ctypes.c_uint32]
+    L.eolc_host_alloc.restype = c_vp
+    L.eolc_host_alloc.argtypes = [ctypes.c_size_t]
+    L.eolc_host_free.argtypes = [c_vp]
     L.eolc_forces_launches_per_fill.argtypes = [c_vp]
     L.eolc_mesh_normals.argtypes = [c_vp, c_dp, c_dp, c_dp]
     L.eolc_mesh_normals_dev.argtypes = [c_vp, c_vp, c_vp, c_vp]
@@ -76,6 +82,35 @@ def lib():
     L.eolc_cd_last_stats.argtypes = [c_vp, ctypes.POINTER(ctypes.c_int64), c_ip]
     _LIB = L
     return L
+
+
+FILL_M_UNCHANGED = 1   # EOLC_FILL_M_UNCHANGED
+
+
+class HostBuffer:
+    """Page-locked host array from eolc_host_alloc (the DMA target itself; pageable arrays cost a staging copy)."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.array = None
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        self._p = lib().eolc_host_alloc(max(n, 1))
+        if not self._p:
+            raise EolcError("eolc_host_alloc: " + lib().eolc_last_error().decode())
+        buf = (ctypes.c_char * max(n, 1)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            lib().eolc_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def check(rc):

@@ -689,6 +689,7 @@ inline size_t pad256(size_t n) { return (n + 255) / 256 * 256; }
 
 struct eolc_cd_plan {
     eolc_ctx *ctx = nullptr;
+    int device = 0;                               // own copy: the plan may be destroyed after its ctx (thread_local order)
     int32_t N = 0, F = 0, E = 0;
     double threshold = 0;
     std::vector<EdgeRec> h_edges;
@@ -723,7 +724,7 @@ int eolc_cd_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face
     for (int64_t i = 0; i < 3 * (int64_t)F; ++i) EOLC_REQUIRE(face_nodes[i] >= 0 && face_nodes[i] < N, "face node index out of range");
     EOLC_CUDA(cudaSetDevice(ctx->device));
     eolc_cd_plan *P = new eolc_cd_plan;
-    P->ctx = ctx; P->N = N; P->F = F; P->threshold = threshold;
+    P->ctx = ctx; P->device = ctx->device; P->N = N; P->F = F; P->threshold = threshold;
     // createEdges (:141-231) with an int64 key: stable sort of the 3F half-edges by (max+1)*(3F+1) + (min+1)
     {
         struct HE { int64_t key; int32_t face; int8_t i; };
@@ -777,7 +778,7 @@ int eolc_cd_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face
 
 void eolc_cd_plan_destroy(eolc_cd_plan *plan) {
     if (!plan) return;
-    cudaSetDevice(plan->ctx->device);
+    cudaSetDevice(plan->device);
     delete plan;
 }
 

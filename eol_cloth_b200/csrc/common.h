@@ -42,9 +42,10 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
     cudaError_t alloc(size_t count) {
         release();
-        n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc((void **)&p, count * sizeof(T));
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;   // a failed allocation leaves an empty buffer: a retry allocates again
+        return e;
     }
     cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
     cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {

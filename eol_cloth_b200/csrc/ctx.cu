@@ -46,10 +46,34 @@ int eolc_ctx_create(int device, eolc_ctx **out) {
     eolc_ctx *c = new eolc_ctx;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    EOLC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaError_t es = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (es != cudaSuccess) {
+        delete c;
+        eolc::set_error("cudaStreamCreateWithFlags failed: %s", cudaGetErrorString(es));
+        return EOLC_ERR_CUDA;
+    }
     *out = c;
     return EOLC_OK;
 }
+
+void *eolc_host_alloc(size_t bytes) {
+    if (bytes == 0) return nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        eolc::set_error("no CUDA device available (%s); this library has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return nullptr;
+    }
+    void *p = nullptr;
+    // portable: page-locked for every CUDA context of the process (one ctx per GPU in an ensemble host)
+    e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); eolc::set_error("eolc_host_alloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+void eolc_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 void eolc_ctx_destroy(eolc_ctx *ctx) {
     if (!ctx) return;

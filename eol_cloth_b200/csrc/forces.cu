@@ -36,6 +36,7 @@ using namespace eolc;
 // ------------------------------------------------------------------------------------------------
 struct eolc_forces_plan {
     eolc_ctx *ctx = nullptr;
+    int device = 0;                               // own copy: the plan may be destroyed after its ctx (thread_local order)
     int32_t N = 0, F = 0, E = 0, Ei = 0, dof = 0;
     int64_t nnzM = 0, nnzK = 0;
     // host topology
@@ -51,6 +52,7 @@ struct eolc_forces_plan {
     DevBuf<uint32_t> d_eol_sources;
     DevBuf<double> d_eol_scratch;                 // eol_scratch doubles per scene
     bool smem_attr_set = false;
+    bool host_M_valid = false;                    // eolc_forces_fill has produced M on this plan (EOLC_FILL_M_UNCHANGED may skip it)
     // "tiles" pipeline
     int32_t n_tiles = 0, n_templates = 0;
     bool service_p3 = false;
@@ -128,6 +130,7 @@ struct TilesArgs {
     double *f, *Mv, *Kv;
     size_t x_stride, X_stride, f_stride, M_stride, K_stride;
     tiles::FillParams prm;
+    uint32_t skip_m;   // EOLC_FILL_M_UNCHANGED: M rows are neither recomputed (apart from M_aa, which MDK_aa needs) nor written
 #ifdef EOLC_TILE_CLOCKS
     unsigned long long *dbg;   // per (CTA, warp): clocks spent in [prefetch issue, phase 1, wait+barrier, phase 2, barrier, copy-out], tiles
 #endif
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
             ta1 = (int)ctl[0];
             if (SERVICE_P2) {            // this warp's share of the phase-2 groups (forces_plan.h spreads them over all 12 warps)
                 set_view(fs, Ms, Ks);
-                tiles::phase2((int)tid, tiles::P2THREADS, V, ctl[1] != 0u);
+                tiles::phase2((int)tid, tiles::P2THREADS, V, ctl[1] != 0u, A.skip_m != 0u);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this warp's staged rows -> visible to the bulk-copy engine
 #ifndef EOLC_TILE_CLOCKS
                 asm volatile("bar.sync 1, %0;" ::"n"(BAR1_THREADS) : "memory");
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
 #ifndef EOLC_DEBUG_NO_COPYOUT
             if (role >= 2) {
                 set_view(fs, Ms, Ks);
-                tiles::copy_out_runs((int)(2 * lane + (role - 2)), 64, V, fs, Ms, Ks, 7u, BulkStore());
+                tiles::copy_out_runs((int)(2 * lane + (role - 2)), 64, V, fs, Ms, Ks, A.skip_m ? 5u : 7u, BulkStore());
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
 #endif
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(tiles::CTA_THREADS, tiles::CTAS_PER_SM) assemb
             EOLC_SYNC();                 // [B1]
             EOLC_CLK(2)
             const int ta1 = (int)ctl[0];
-            tiles::phase2((int)tid, tiles::P2THREADS, V, ctl[1] != 0u);
+            tiles::phase2((int)tid, tiles::P2THREADS, V, ctl[1] != 0u, A.skip_m != 0u);
             EOLC_CLK(0)
 #ifdef EOLC_TILE_CLOCKS
             if (__syncthreads_or(0) == 12345) clk_acc[6] += 1000000;   // never true; see EOLC_SYNC (service warps take part in this build)
@@ -883,7 +886,7 @@ int launch_eol(eolc_forces_plan *P, int32_t S, const double *x, const double *X,
 }
 
 int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X, const eolc_material *mat,
-                const double *grav, double h, double *f, double *Mv, double *Kv) {
+                const double *grav, double h, double *f, double *Mv, double *Kv, bool skip_m = false) {
     cudaStream_t st = P->ctx->stream;
     const double dhh = mat->dampingB * h * h;   // damping(1)*h*h, Forces.cpp:105
     if (P->N == 0) return EOLC_OK;
@@ -907,6 +910,7 @@ int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X
         A.M_stride = (size_t)P->nnzM; A.K_stride = (size_t)P->nnzK;
         A.prm.mu = membrane_mu(mat->e, mat->nu); A.prm.lam = membrane_lambda(mat->e, mat->nu); A.prm.rho = mat->density; A.prm.beta = mat->beta;
         A.prm.gx = grav[0]; A.prm.gy = grav[1]; A.prm.gz = grav[2]; A.prm.dhh = dhh;
+        A.skip_m = skip_m ? 1u : 0u;
 #ifdef EOLC_TILE_CLOCKS
         EOLC_CUDA(P->d_dbg.ensure((size_t)grid * (tiles::CTA_THREADS / 32) * 7));
         P->dbg_grid = grid;
@@ -960,7 +964,7 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
     }
     EOLC_CUDA(cudaSetDevice(ctx->device));
     eolc_forces_plan *P = new eolc_forces_plan;
-    P->ctx = ctx; P->N = N; P->F = F; P->E = E; P->dof = 3 * N;
+    P->ctx = ctx; P->device = ctx->device; P->N = N; P->F = F; P->E = E; P->dof = 3 * N;
     P->h_face_nodes.assign(face_nodes, face_nodes + 3 * (size_t)F);
     for (int32_t e = 0; e < E; ++e) {
         const int32_t *s = edge_stencil + 4 * (size_t)e;
@@ -996,7 +1000,7 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
 
 void eolc_forces_plan_destroy(eolc_forces_plan *plan) {
     if (!plan) return;
-    cudaSetDevice(plan->ctx->device);
+    cudaSetDevice(plan->device);
     delete plan;
 }
 
@@ -1196,15 +1200,27 @@ int eolc_mesh_normals(eolc_forces_plan *plan, const double *x, double *face_n, d
 
 int eolc_forces_launches_per_fill(const eolc_forces_plan *plan) { return !plan ? 0 : plan->n_eol ? 3 : 1; }
 
-int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
-                                 const eolc_material *mat, const double grav[3], double h, double *f_dev,
-                                 double *M_vals_dev, double *MDK_vals_dev) {
+// M depends only on X and the density (ComputeInertial.cpp:33,44-47): for a Lagrangian mesh it is constant between remeshes.
+static bool honours_m_unchanged(const eolc_forces_plan *P, uint32_t flags) {
+    return (flags & EOLC_FILL_M_UNCHANGED) && P->pipeline == 0 && P->n_eol == 0;
+}
+
+int eolc_forces_fill_batched_dev_ex(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
+                                    const eolc_material *mat, const double grav[3], double h, double *f_dev,
+                                    double *M_vals_dev, double *MDK_vals_dev, uint32_t flags) {
     EOLC_REQUIRE(plan && mat && grav, "NULL argument");
     EOLC_REQUIRE(n_scenes >= 1, "n_scenes must be >= 1");
+    EOLC_REQUIRE((flags & ~EOLC_FILL_M_UNCHANGED) == 0, "unknown flag");
     EOLC_REQUIRE(plan->N == 0 || (x_dev && X_dev && f_dev), "NULL device pointer");
     EOLC_REQUIRE(plan->nnzM == 0 || (M_vals_dev && MDK_vals_dev), "NULL device pointer");
     EOLC_CUDA(cudaSetDevice(plan->ctx->device));
-    return launch_fill(plan, n_scenes, x_dev, X_dev, mat, grav, h, f_dev, M_vals_dev, MDK_vals_dev);
+    return launch_fill(plan, n_scenes, x_dev, X_dev, mat, grav, h, f_dev, M_vals_dev, MDK_vals_dev, honours_m_unchanged(plan, flags));
+}
+
+int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
+                                 const eolc_material *mat, const double grav[3], double h, double *f_dev,
+                                 double *M_vals_dev, double *MDK_vals_dev) {
+    return eolc_forces_fill_batched_dev_ex(plan, n_scenes, x_dev, X_dev, mat, grav, h, f_dev, M_vals_dev, MDK_vals_dev, 0u);
 }
 
 int eolc_forces_fill_dev(eolc_forces_plan *plan, const double *x_dev, const double *X_dev, const eolc_material *mat,
@@ -1214,8 +1230,16 @@ int eolc_forces_fill_dev(eolc_forces_plan *plan, const double *x_dev, const doub
 
 int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
                      const double grav[3], double h, double *f, double *M_vals, double *MDK_vals) {
+    return eolc_forces_fill_ex(plan, x, X, mat, grav, h, f, M_vals, MDK_vals, 0u);
+}
+
+int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
+                        const double grav[3], double h, double *f, double *M_vals, double *MDK_vals, uint32_t flags) {
     EOLC_REQUIRE(plan && mat && grav, "NULL argument");
+    EOLC_REQUIRE((flags & ~EOLC_FILL_M_UNCHANGED) == 0, "unknown flag");
     eolc_forces_plan *P = plan;
+    // M unchanged: valid only if this plan's device copy of M was produced by an earlier full fill
+    const bool skip_m = honours_m_unchanged(P, flags) && P->host_M_valid;
     EOLC_REQUIRE(P->N == 0 || (x && X && f), "NULL host pointer");
     EOLC_REQUIRE(P->nnzM == 0 || (M_vals && MDK_vals), "NULL host pointer");
     EOLC_CUDA(cudaSetDevice(P->ctx->device));
@@ -1231,7 +1255,7 @@ int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, c
         return a.type == cudaMemoryTypeHost;
     };
     const bool in_pinned = pinned(x) && pinned(X);
-    const bool out_pinned = pinned(f) && pinned(M_vals) && pinned(MDK_vals);
+    const bool out_pinned = pinned(f) && (skip_m || pinned(M_vals)) && pinned(MDK_vals);
     const double *hx = x, *hX = X;
     if (!in_pinned) {
         EOLC_CUDA(P->p_in.ensure(5 * N));
@@ -1241,7 +1265,7 @@ int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, c
     }
     EOLC_CUDA(cudaMemcpyAsync(P->d_x.p, hx, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
     EOLC_CUDA(cudaMemcpyAsync(P->d_X.p, hX, 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
-    int rc = launch_fill(P, 1, P->d_x.p, P->d_X.p, mat, grav, h, P->d_f.p, P->d_Mv.p, P->d_Kv.p);
+    int rc = launch_fill(P, 1, P->d_x.p, P->d_X.p, mat, grav, h, P->d_f.p, P->d_Mv.p, P->d_Kv.p, skip_m);
     if (rc) return rc;
     double *hf = f, *hM = M_vals, *hK = MDK_vals;
     if (!out_pinned) {
@@ -1249,14 +1273,15 @@ int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, c
         hf = P->p_out.p; hM = P->p_out.p + nf; hK = P->p_out.p + nf + P->nnzM;
     }
     EOLC_CUDA(cudaMemcpyAsync(hf, P->d_f.p, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EOLC_CUDA(cudaMemcpyAsync(hM, P->d_Mv.p, P->nnzM * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (!skip_m) EOLC_CUDA(cudaMemcpyAsync(hM, P->d_Mv.p, P->nnzM * sizeof(double), cudaMemcpyDeviceToHost, st));
     EOLC_CUDA(cudaMemcpyAsync(hK, P->d_Kv.p, P->nnzK * sizeof(double), cudaMemcpyDeviceToHost, st));
     EOLC_CUDA(cudaStreamSynchronize(st));
     if (!out_pinned) {
         memcpy(f, hf, nf * sizeof(double));
-        memcpy(M_vals, hM, P->nnzM * sizeof(double));
+        if (!skip_m) memcpy(M_vals, hM, P->nnzM * sizeof(double));
         memcpy(MDK_vals, hK, P->nnzK * sizeof(double));
     }
+    P->host_M_valid = true;
     return EOLC_OK;
 }
 

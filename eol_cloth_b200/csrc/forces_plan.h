@@ -836,7 +836,11 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             {
                 uint32_t pbase = 0;
                 for (const Grp &G : groups) {
-                    T.push_back((uint32_t)G.kind | ((uint32_t)G.nA << 8) | ((uint32_t)G.nB << 16));
+                    // bit 24: a mass group without a diagonal record — skipped as a whole when the caller says M is unchanged
+                    uint32_t offdiag_only = G.kind == KIND_M ? 1u : 0u;
+                    if (G.kind == KIND_M)
+                        for (int l = 0; l < G.count; ++l) if ((recs[KIND_M][G.first + l].rec >> 53) & 1ull) offdiag_only = 0u;
+                    T.push_back((uint32_t)G.kind | ((uint32_t)G.nA << 8) | ((uint32_t)G.nB << 16) | (offdiag_only << 24));
                     T.push_back(pbase); T.push_back((uint32_t)G.warp); T.push_back(0);
                     pbase += (uint32_t)(G.nA + G.nB) * GROUP;
                 }

@@ -116,7 +116,9 @@ EOLC_HD void pull2(uint32_t e, const double *scr, const double *&s0, const doubl
 // Every lane of a group runs the same trip counts; the sums land in the staging rows (shared memory), laid out like the
 // global rows.  m_full: the M staging rows do not hold this template's explicit zeros yet (first tile / template or parity
 // changed), so mass records write whole 3x3 blocks; otherwise only the three diagonal entries change.
-EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
+// skip_m: the caller declared M unchanged since the last fill (EOLC_FILL_M_UNCHANGED): only the diagonal mass records run (phase 3
+// needs M_aa for the diagonal MDK block); off-diagonal mass groups are skipped and the M rows are not copied out.
+EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full, bool skip_m = false) {
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const uint32_t h0 = V.tmplB[0];
     const int nOwn = (int)(h0 & 255u), nG = (int)((h0 >> 8) & 255u), n4 = (nOwn + 3) & ~3;
@@ -129,6 +131,7 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
         for (int g = (int)(wr & 0xffffu), gend = g + (int)(wr >> 16); g < gend; ++g) {
             const uint32_t gw = grp[4 * g];
             const int kind = (int)(gw & 255u), nA = (int)((gw >> 8) & 255u), nB = (int)((gw >> 16) & 255u);
+            if (skip_m && ((gw >> 24) & 1u)) continue;
             const uint32_t *pl = pulls + grp[4 * g + 1] + lane;
             const unsigned long long rec = recs[(size_t)GROUP * g + lane];
             const uint32_t off1 = (uint32_t)rec & 0xffffu, st1 = (uint32_t)(rec >> 16) & 1023u;
@@ -216,7 +219,7 @@ EOLC_HD void phase2(int tid, int nthreads, const TileView &V, bool m_full) {
                     m += *s0;
                     m += *s1;
                 }
-                if (valid) {
+                if (valid && !(skip_m && !((rec >> 53) & 1ull))) {
                     m *= ((rec >> 53) & 1ull) ? (1.0 / 12.0) : (1.0 / 24.0);
                     for (int side = 0; side < 2; ++side) {
                         if (side && !has2) break;

@@ -83,19 +83,22 @@ class ForcesPlan:
                                                float(h), capi.dptr(f), capi.dptr(Mv), capi.dptr(Kv)))
         return f, Mv, Kv
 
-    def fill_into(self, x, X, mat, grav, h, f, Mv, Kv):
-        """Same as fill() but into caller-provided contiguous float64 arrays (no allocation in the timed region)."""
+    def fill_into(self, x, X, mat, grav, h, f, Mv, Kv, m_unchanged=False):
+        """Same as fill() but into caller-provided contiguous float64 arrays (no allocation in the timed region).
+        m_unchanged: EOLC_FILL_M_UNCHANGED — X and the density are those of the previous fill, Mv is left as it is."""
         g = capi.f64(grav)
         m = _matc(mat)
-        capi.check(capi.lib().eolc_forces_fill(self._h, capi.dptr(x), capi.dptr(X), ctypes.byref(m), capi.dptr(g),
-                                               float(h), capi.dptr(f), capi.dptr(Mv), capi.dptr(Kv)))
+        capi.check(capi.lib().eolc_forces_fill_ex(self._h, capi.dptr(x), capi.dptr(X), ctypes.byref(m), capi.dptr(g),
+                                                  float(h), capi.dptr(f), capi.dptr(Mv), capi.dptr(Kv),
+                                                  capi.FILL_M_UNCHANGED if m_unchanged else 0))
 
-    def fill_dev(self, x_ptr, X_ptr, mat, grav, h, f_ptr, Mv_ptr, Kv_ptr, n_scenes=1):
+    def fill_dev(self, x_ptr, X_ptr, mat, grav, h, f_ptr, Mv_ptr, Kv_ptr, n_scenes=1, m_unchanged=False):
         """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on ctx.stream."""
         g = capi.f64(grav)
         m = _matc(mat)
-        capi.check(capi.lib().eolc_forces_fill_batched_dev(self._h, int(n_scenes), x_ptr, X_ptr, ctypes.byref(m),
-                                                           capi.dptr(g), float(h), f_ptr, Mv_ptr, Kv_ptr))
+        capi.check(capi.lib().eolc_forces_fill_batched_dev_ex(self._h, int(n_scenes), x_ptr, X_ptr, ctypes.byref(m),
+                                                              capi.dptr(g), float(h), f_ptr, Mv_ptr, Kv_ptr,
+                                                              capi.FILL_M_UNCHANGED if m_unchanged else 0))
 
     def rhs_dev(self, Mv_ptr, f_ptr, v_ptr, h, b_ptr):
         """b = -(M v + h f) on the device (Cloth::solve, Cloth.cpp:345); device pointers, asynchronous on ctx.stream."""

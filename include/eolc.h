@@ -26,6 +26,7 @@
 #ifndef EOLC_H_
 #define EOLC_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -102,6 +103,20 @@ int eolc_forces_counts(const eolc_forces_plan *plan, int32_t *n_faces, int32_t *
  * Host version copies x/X in and f/M/MDK out (pinned staging inside the plan). */
 int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
                      const double grav[3], double h, double *f, double *M_vals, double *MDK_vals);
+/* Flags of the *_ex entry points.
+ * EOLC_FILL_M_UNCHANGED: the caller states that X and the density are the ones of the previous fill on this plan, so M, which
+ *   depends on nothing else (src/ComputeInertial.cpp:33,44-47; SURVEY §8a row 5: "constant between remeshes when EOL is off"),
+ *   is the same matrix: M_vals is left untouched (host entry: no device-to-host copy of M; device entries: the M rows are
+ *   neither recomputed nor written).  f and MDK are produced as always and are bit-identical to a full fill.  Honoured for
+ *   Lagrangian plans only (with EoL nodes M depends on x through F = deform_grad); otherwise M is recomputed.  M_vals must be
+ *   the buffer of the previous fill or at least a valid one. */
+#define EOLC_FILL_M_UNCHANGED 1u
+int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
+                        const double grav[3], double h, double *f, double *M_vals, double *MDK_vals, uint32_t flags);
+/* Page-locked host memory for the buffers handed to the host entry points (x, X, f, M_vals, MDK_vals, contact lists): such
+ * buffers are the target of the DMA itself, pageable ones cost a staging copy (1.5 GB per fill at 1024^2).  NULL on failure. */
+void *eolc_host_alloc(size_t bytes);
+void eolc_host_free(void *p);
 /* Same, every pointer is a DEVICE pointer on the plan's device; asynchronous on eolc_ctx_stream(). */
 int eolc_forces_fill_dev(eolc_forces_plan *plan, const double *x_dev, const double *X_dev, const eolc_material *mat,
                          const double grav[3], double h, double *f_dev, double *M_vals_dev, double *MDK_vals_dev);
@@ -110,6 +125,9 @@ int eolc_forces_fill_dev(eolc_forces_plan *plan, const double *x_dev, const doub
 int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
                                  const eolc_material *mat, const double grav[3], double h, double *f_dev,
                                  double *M_vals_dev, double *MDK_vals_dev);
+int eolc_forces_fill_batched_dev_ex(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
+                                    const eolc_material *mat, const double grav[3], double h, double *f_dev,
+                                    double *M_vals_dev, double *MDK_vals_dev, uint32_t flags);
 /* ---- consumer of the fill, on the device -------------------------------- */
 /* Cloth::solve right-hand side, src/Cloth.cpp:345:  b = -(M v + h f).  M_vals_dev / f_dev: outputs of a fill with this plan;
  * v_dev, b_dev: dof doubles.  Asynchronous on eolc_ctx_stream(). */

@@ -16,6 +16,7 @@
 #ifndef EOLC_HOST_HPP_
 #define EOLC_HOST_HPP_
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -61,48 +62,104 @@ private:
     eolc_ctx *h_ = nullptr;
 };
 
+// Page-locked host array (eolc_host_alloc): what the host entry points DMA from / into directly.  A pageable std::vector
+// costs an extra pass through the library's staging buffer (1.5 GB per fill at 1024^2).  The small vector-like surface the
+// host layer and the adapters need; contents are NOT preserved by a growing resize().
+template <class T>
+class PinnedArray {
+public:
+    PinnedArray() {}
+    ~PinnedArray() { eolc_host_free(p_); }
+    PinnedArray(const PinnedArray &) = delete;
+    PinnedArray &operator=(const PinnedArray &) = delete;
+    void resize(size_t n) {
+        if (n > cap_) {
+            eolc_host_free(p_);
+            p_ = nullptr; cap_ = 0;
+            p_ = static_cast<T *>(eolc_host_alloc(n * sizeof(T)));
+            if (!p_) fail("eolc_host_alloc", EOLC_ERR_CUDA);
+            cap_ = n;
+        }
+        n_ = n;
+    }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    T &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+    T *begin() { return p_; }
+    T *end() { return p_ + n_; }
+    const T *begin() const { return p_; }
+    const T *end() const { return p_ + n_; }
+private:
+    T *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+};
+
+// Process-wide source of version numbers: two FlatMesh objects never carry the same one, so a cache keyed on a version cannot
+// mistake one mesh for another.
+inline uint64_t next_version() { static std::atomic<uint64_t> v(0); return ++v; }
+
 // The part of the ArcSim mesh the hot path reads, flattened.
 struct FlatMesh {
     int32_t N = 0, F = 0, E = 0;
-    std::vector<double> x;             // 3N  Node::x
-    std::vector<double> X;             // 2N  node->verts[0]->u[0..1]
+    PinnedArray<double> x;             // 3N  Node::x
+    PinnedArray<double> X;             // 2N  node->verts[0]->u[0..1]
     std::vector<int32_t> face_nodes;   // 3F  faces[k]->v[0..2]->node->index
     std::vector<int32_t> edge_stencil; // 4E  (n[0], n[1], opp(adjf[0]), opp(adjf[1])), -1 = no face
     std::vector<int32_t> eol_index;    // N   Node::EoL_index, -1 = Lagrangian
     int32_t EoL_Count = 0;
+    // Change counters maintained by flatten(): the consumers key their caches on them instead of re-hashing the arrays.
+    uint64_t topology_version = 0;     // renewed when N, face_nodes, edge_stencil or eol_index changed (remesh / set_indices)
+    uint64_t X_version = 0;            // renewed when any material coordinate changed (remesh, or EoL nodes moving in X)
+    // for callers that fill the arrays themselves instead of through flatten(): declare what changed
+    void touch_topology() { topology_version = next_version(); X_version = next_version(); }
+    void touch_X() { X_version = next_version(); }
 };
 
 // Works on any mesh type with ArcSim's field names (mesh.hpp:57-190): nodes[i]->{x, verts, index, EoL, EoL_index},
 // verts->{u, node}, faces[k]->v[3], edges[e]->{n[2], adjf[2]}.  `positions_only` refreshes x (and X) of an existing
 // FlatMesh without touching the topology arrays — what a step without remeshing needs.
+// Changes are detected while the values are copied (a compare per value written, no second pass, no hash): the version counters
+// of `out` move only when something really changed, whatever the caller believes.
 template <class MeshT>
 void flatten(const MeshT &mesh, FlatMesh &out, bool positions_only = false) {
     const size_t N = mesh.nodes.size();
+    bool topo_changed = out.N != (int32_t)N || out.x.size() != 3 * N, X_changed = topo_changed;
     out.N = (int32_t)N;
     out.x.resize(3 * N);
     out.X.resize(2 * N);
     for (size_t i = 0; i < N; ++i) {
         const auto *n = mesh.nodes[i];
         out.x[3 * i] = n->x[0]; out.x[3 * i + 1] = n->x[1]; out.x[3 * i + 2] = n->x[2];      // Forces.cpp:343-348
-        out.X[2 * i] = n->verts[0]->u[0]; out.X[2 * i + 1] = n->verts[0]->u[1];              // Forces.cpp:349-355
+        const double u0 = n->verts[0]->u[0], u1 = n->verts[0]->u[1];                         // Forces.cpp:349-355
+        if (!X_changed && (out.X[2 * i] != u0 || out.X[2 * i + 1] != u1)) X_changed = true;
+        out.X[2 * i] = u0; out.X[2 * i + 1] = u1;
     }
-    if (positions_only) return;
-    out.eol_index.assign(N, -1);
+    if (X_changed) out.X_version = next_version();
+    if (positions_only) { if (topo_changed) out.topology_version = next_version(); return; }
+    if (out.eol_index.size() != N) { out.eol_index.assign(N, -1); topo_changed = true; }
     out.EoL_Count = 0;
-    for (size_t i = 0; i < N; ++i)
-        if (mesh.nodes[i]->EoL) { out.eol_index[i] = mesh.nodes[i]->EoL_index; ++out.EoL_Count; }
+    for (size_t i = 0; i < N; ++i) {
+        const int32_t v = mesh.nodes[i]->EoL ? (int32_t)mesh.nodes[i]->EoL_index : -1;
+        if (mesh.nodes[i]->EoL) ++out.EoL_Count;
+        if (out.eol_index[i] != v) { out.eol_index[i] = v; topo_changed = true; }
+    }
     const size_t F = mesh.faces.size();
+    if (out.face_nodes.size() != 3 * F) { out.face_nodes.assign(3 * F, -1); topo_changed = true; }
     out.F = (int32_t)F;
-    out.face_nodes.resize(3 * F);
     for (size_t k = 0; k < F; ++k)
-        for (int j = 0; j < 3; ++j) out.face_nodes[3 * k + j] = mesh.faces[k]->v[j]->node->index;   // Forces.cpp:376-378
+        for (int j = 0; j < 3; ++j) {                                                              // Forces.cpp:376-378
+            const int32_t v = mesh.faces[k]->v[j]->node->index;
+            if (out.face_nodes[3 * k + j] != v) { out.face_nodes[3 * k + j] = v; topo_changed = true; }
+        }
     const size_t E = mesh.edges.size();
+    if (out.edge_stencil.size() != 4 * E) { out.edge_stencil.assign(4 * E, -2); topo_changed = true; }
     out.E = (int32_t)E;
-    out.edge_stencil.resize(4 * E);
     for (size_t e = 0; e < E; ++e) {
         const auto *ed = mesh.edges[e];
-        int32_t *s = &out.edge_stencil[4 * e];
-        s[0] = ed->n[0]->index; s[1] = ed->n[1]->index; s[2] = -1; s[3] = -1;
+        int32_t s[4] = {(int32_t)ed->n[0]->index, (int32_t)ed->n[1]->index, -1, -1};
         for (int side = 0; side < 2; ++side) {
             const auto *f = ed->adjf[side];
             if (!f) continue;                                                                      // Forces.cpp:688-690
@@ -111,7 +168,10 @@ void flatten(const MeshT &mesh, FlatMesh &out, bool positions_only = false) {
                 if (nd != ed->n[0] && nd != ed->n[1]) { s[2 + side] = nd->index; break; }
             }
         }
+        int32_t *d = &out.edge_stencil[4 * e];
+        for (int q = 0; q < 4; ++q) if (d[q] != s[q]) { d[q] = s[q]; topo_changed = true; }
     }
+    if (topo_changed) out.topology_version = next_version();
 }
 
 // Column-major compressed sparse matrix laid out exactly like Eigen::SparseMatrix<double> (outer/inner/values).
@@ -121,55 +181,51 @@ struct SparseCSC {
     int64_t nnz = 0;
     const int32_t *outer = nullptr;   // cols + 1
     const int32_t *inner = nullptr;   // nnz, ascending within a column
-    std::vector<double> values;       // nnz
+    PinnedArray<double> values;       // nnz, page-locked: eolc_forces_fill copies device -> here without staging
 };
-
-namespace detail {
-inline uint64_t fnv1a(const void *p, size_t n, uint64_t h = 1469598103934665603ull) {
-    const unsigned char *b = (const unsigned char *)p;
-    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
-    return h;
-}
-inline uint64_t topo_key(const FlatMesh &m) {
-    uint64_t h = fnv1a(&m.N, sizeof m.N);
-    h = fnv1a(m.face_nodes.data(), m.face_nodes.size() * sizeof(int32_t), h);
-    h = fnv1a(m.edge_stencil.data(), m.edge_stencil.size() * sizeof(int32_t), h);
-    return fnv1a(m.eol_index.data(), m.eol_index.size() * sizeof(int32_t), h);
-}
-}  // namespace detail
 
 // class Forces (Forces.h:26-45).  The topology plan (CSR pattern + element->slot maps) is cached and rebuilt only when
 // the flattened topology changes, i.e. after dynamic_remesh / set_indices (Scene.cpp:87-90) or the preprocessor.
 class Forces {
 public:
-    explicit Forces(Context *ctx = nullptr) : EoL_cutoff(0), ctx_(ctx) {}
+    // The Context outlives the plan: it is looked up BEFORE the plan can exist, so a thread_local Forces constructed by an adapter is
+    // destroyed before the thread's Context (reverse order of construction).
+    explicit Forces(Context *ctx = nullptr) : EoL_cutoff(0), ctx_(ctx ? ctx : &Context::instance()) {}
     ~Forces() { eolc_forces_plan_destroy(plan_); }
     Forces(const Forces &) = delete;
     Forces &operator=(const Forces &) = delete;
 
-    std::vector<double> f;   // Eigen::VectorXd f
+    PinnedArray<double> f;   // Eigen::VectorXd f
     SparseCSC M;             // Eigen::SparseMatrix<double> M
     SparseCSC MDK;           // Eigen::SparseMatrix<double> MDK
     int EoL_cutoff;
 
     // void Forces::fill(const Mesh&, const Material&, const Vector3d& grav, double h)   Forces.cpp:912-930
+    // M_updated tells the caller whether M.values was rewritten by the last fill (false: M is the matrix of the previous step;
+    // it depends on X and the density only, ComputeInertial.cpp:33,44-47, so a step without remeshing leaves it alone).
+    bool M_updated = true;
     void fill(const FlatMesh &mesh, const eolc_material &mat, const double grav[3], double h) {
-        Context &c = ctx_ ? *ctx_ : Context::instance();
-        const uint64_t key = detail::topo_key(mesh);
-        if (!plan_ || key != key_) {
+        Context &c = *ctx_;
+        // the plan follows the mesh's topology counter (flatten() moves it only when an index really changed)
+        if (!plan_ || mesh.topology_version != topo_version_) {
             eolc_forces_plan_destroy(plan_);
             plan_ = nullptr;
             check(eolc_forces_plan_create(c.handle(), mesh.N, mesh.F, mesh.face_nodes.data(), mesh.E, mesh.edge_stencil.data(),
                                           mesh.eol_index.empty() ? nullptr : mesh.eol_index.data(), mesh.X.data(), &plan_),
                   "eolc_forces_plan_create");
-            key_ = key;
+            topo_version_ = mesh.topology_version;
             bind(0, M);
             bind(1, MDK);
+            have_M_ = false;
         }
         f.resize((size_t)M.rows);                       // f.resize(3N + 2 EoL_Count), Forces.cpp:914
         EoL_cutoff = 3 * mesh.N;                        // Forces.cpp:919
-        check(eolc_forces_fill(plan_, mesh.x.data(), mesh.X.data(), &mat, grav, h, f.data(), M.values.data(), MDK.values.data()),
+        const bool same_M = have_M_ && mesh.EoL_Count == 0 && mesh.X_version == X_version_ && mat.density == density_;
+        check(eolc_forces_fill_ex(plan_, mesh.x.data(), mesh.X.data(), &mat, grav, h, f.data(), M.values.data(), MDK.values.data(),
+                                  same_M ? EOLC_FILL_M_UNCHANGED : 0u),
               "eolc_forces_fill");
+        M_updated = !same_M;
+        have_M_ = true; X_version_ = mesh.X_version; density_ = mat.density;
     }
     const eolc_forces_plan *plan() const { return plan_; }
 
@@ -182,7 +238,9 @@ private:
     }
     Context *ctx_;
     eolc_forces_plan *plan_ = nullptr;
-    uint64_t key_ = 0;
+    uint64_t topo_version_ = 0, X_version_ = 0;
+    double density_ = 0.0;
+    bool have_M_ = false;
 };
 
 // What CD / CD2 read from `Obstacles` (Obstacles.h:31-35, Points.h:22-24, Box.h:43-47).
@@ -200,21 +258,20 @@ typedef eolc_contact Collision;           // POD mirror of btc::Collision (boxTr
 namespace detail {
 struct CdCache {
     eolc_cd_plan *plan = nullptr;
-    uint64_t key = 0;
-    std::vector<eolc_contact> buf;
+    uint64_t topo_version = 0;
+    double threshold = 0.0;
+    PinnedArray<eolc_contact> buf;       // page-locked: the contact list is DMA'd straight into it
     ~CdCache() { eolc_cd_plan_destroy(plan); }
 };
 inline void run_cd(const FlatMesh &mesh, const ObstaclesFlat &obs, std::vector<std::shared_ptr<Collision> > &cls, int cd1, Context *ctx) {
+    Context &c = ctx ? *ctx : Context::instance();   // before the cache: the thread's Context must outlive the cached plan
     static thread_local CdCache cache;
-    Context &c = ctx ? *ctx : Context::instance();
-    uint64_t key = fnv1a(&mesh.N, sizeof mesh.N);
-    key = fnv1a(mesh.face_nodes.data(), mesh.face_nodes.size() * sizeof(int32_t), key);
-    key = fnv1a(&obs.cdthreshold, sizeof obs.cdthreshold, key);
-    if (!cache.plan || cache.key != key) {
+    // the plan (btc edge table + perturbation stream) follows the mesh's topology counter and the threshold
+    if (!cache.plan || cache.topo_version != mesh.topology_version || cache.threshold != obs.cdthreshold) {
         eolc_cd_plan_destroy(cache.plan);
         cache.plan = nullptr;
         check(eolc_cd_plan_create(c.handle(), mesh.N, mesh.F, mesh.face_nodes.data(), obs.cdthreshold, &cache.plan), "eolc_cd_plan_create");
-        cache.key = key;
+        cache.topo_version = mesh.topology_version; cache.threshold = obs.cdthreshold;
     }
     if (cache.buf.size() < 1024) cache.buf.resize(1024);
     int32_t n = 0;

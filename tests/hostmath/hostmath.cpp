@@ -204,7 +204,12 @@ struct HostBulk {   // host stand-in of the device's bulk copy: same alignment c
     }
 };
 // returns 0, or -1 if a bulk copy was issued with a misaligned address / size
+int hm_plan_fill_ex(void *p, const double *x, const double *X, const double *mat6, const double *grav, double h, double *f, double *Mv, double *Kv, int skip_m);
 int hm_plan_fill(void *p, const double *x, const double *X, const double *mat6, const double *grav, double h, double *f, double *Mv, double *Kv) {
+    return hm_plan_fill_ex(p, x, X, mat6, grav, h, f, Mv, Kv, 0);
+}
+// skip_m: EOLC_FILL_M_UNCHANGED as the kernel runs it (off-diagonal mass groups skipped, M rows not copied out)
+int hm_plan_fill_ex(void *p, const double *x, const double *X, const double *mat6, const double *grav, double h, double *f, double *Mv, double *Kv, int skip_m) {
     HmPlan *P = (HmPlan *)p;
     tiles::FillParams prm;
     prm.mu = membrane_mu(mat6[1], mat6[2]); prm.lam = membrane_lambda(mat6[1], mat6[2]); prm.rho = mat6[0]; prm.beta = mat6[3];
@@ -236,9 +241,9 @@ int hm_plan_fill(void *p, const double *x, const double *X, const double *mat6, 
         tM_id = geo[0];
         if (m_full) for (auto &v : mbuf) v = 1e300;
         for (int tid = 0; tid < tiles::NTHREADS; ++tid) tiles::phase1(tid, tiles::NTHREADS, V, prm);
-        for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::phase2(tid, tiles::P2THREADS, V, m_full);
+        for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::phase2(tid, tiles::P2THREADS, V, m_full, skip_m != 0);
         for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::phase3(tid, tiles::P2THREADS, V);
-        for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::copy_out_runs(tid, tiles::P2THREADS, V, f, Mv, Kv, 7u, HostBulk{&ok});
+        for (int tid = 0; tid < tiles::P2THREADS; ++tid) tiles::copy_out_runs(tid, tiles::P2THREADS, V, f, Mv, Kv, skip_m ? 5u : 7u, HostBulk{&ok});
     }
     if (P->has_eol) {   // the two EOL kernels of forces.cu, one "thread" after the other
         const eol::Plan &ep = P->ep;

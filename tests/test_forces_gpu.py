@@ -338,3 +338,51 @@ def test_eol_random_triangulation_matches_oracle(ctx, oracle, seed):
     forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
     ref = oracle.forces_fill(tri, es, x, X, tuple(MAT), GRAV, H, eol_index=eol)
     _check(forces, ref, n, f"eol delaunay {seed}")
+
+
+def test_m_unchanged_flag_and_pinned_host_buffers(ctx):
+    """EOLC_FILL_M_UNCHANGED (include/eolc.h): f and MDK bit-identical to the full fill, M left untouched — on the device entry,
+    on the host entry with page-locked buffers from eolc_host_alloc, and ignored (M recomputed) for a plan with EoL nodes."""
+    import torch
+    from eol_cloth_b200 import capi
+    X, fn = E.meshgen.regular2(70)
+    N = X.shape[0]
+    es = E.meshgen.edge_stencils(N, fn)
+    x0, x1 = E.meshgen.drape_state(X, seed=1), E.meshgen.drape_state(X, seed=2)
+    plan = E.ForcesPlan(ctx, N, fn, es, X_hint=X)
+    f_ref, M_ref, K_ref = plan.fill(x1, X, MAT, GRAV, H)
+    # host entry, pinned buffers: full fill of state 0, then state 1 with the flag
+    bufs = [capi.HostBuffer(s) for s in ((N, 3), (N, 2), (plan.dof,), (plan.nnz[0],), (plan.nnz[1],))]
+    xh, Xh, fh, Mh, Kh = (b.array for b in bufs)
+    xh[:] = x0; Xh[:] = X
+    plan.fill_into(xh, Xh, MAT, GRAV, H, fh, Mh, Kh)
+    M0 = Mh.copy()
+    assert np.array_equal(M0, M_ref)                      # M does not depend on x
+    xh[:] = x1
+    Mh[:] = 123.0                                          # sentinel: must survive
+    plan.fill_into(xh, Xh, MAT, GRAV, H, fh, Mh, Kh, m_unchanged=True)
+    assert fh.tobytes() == f_ref.tobytes() and Kh.tobytes() == K_ref.tobytes()
+    assert (Mh == 123.0).all()
+    # device entry
+    dev = torch.device("cuda", ctx.device)
+    xd, Xd = torch.from_numpy(x1).to(dev), torch.from_numpy(X).to(dev)
+    fd = torch.full((plan.dof,), float("nan"), dtype=torch.float64, device=dev)
+    Md = torch.full((plan.nnz[0],), 7.0, dtype=torch.float64, device=dev)
+    Kd = torch.full((plan.nnz[1],), float("nan"), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, fd.data_ptr(), Md.data_ptr(), Kd.data_ptr(), m_unchanged=True)
+    torch.cuda.synchronize()
+    assert fd.cpu().numpy().tobytes() == f_ref.tobytes() and Kd.cpu().numpy().tobytes() == K_ref.tobytes()
+    assert bool((Md == 7.0).all())
+    plan.close()
+    # EoL plan: the flag is not honoured, M is recomputed
+    eol = np.full(N, -1, np.int32)
+    eol[np.arange(1, 69) * 70 + 35] = np.arange(68)
+    plan_e = E.ForcesPlan(ctx, N, fn, es, eol_index=eol, X_hint=X)
+    fe, Me, Ke = plan_e.fill(x1, X, MAT, GRAV, H)
+    f2, M2, K2 = np.empty_like(fe), np.full_like(Me, 5.0), np.empty_like(Ke)
+    plan_e.fill_into(np.ascontiguousarray(x1), np.ascontiguousarray(X), MAT, GRAV, H, f2, M2, K2, m_unchanged=True)
+    assert M2.tobytes() == Me.tobytes() and K2.tobytes() == Ke.tobytes() and f2.tobytes() == fe.tobytes()
+    plan_e.close()
+    for b in bufs:
+        b.free()

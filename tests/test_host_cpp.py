@@ -63,8 +63,10 @@ def test_host_cpp_matches_oracle(driver, oracle, tmp_path, with_eol):
     r = subprocess.run([driver, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")] + (["24"] if with_eol else []), capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = open(tmp_path / "out.bin", "rb").read()
-    dof, nE, cutoff, ncls, nnzM, nnzK = struct.unpack_from("iiiiqq", raw, 0)
-    off = struct.calcsize("iiiiqq")
+    dof, nE, cutoff, ncls, nnzM, nnzK, m_updated_second, _ = struct.unpack_from("iiiiqqii", raw, 0)
+    off = struct.calcsize("iiiiqqii")
+    # second fill on unchanged X: M skipped on the Lagrangian mesh (EOLC_FILL_M_UNCHANGED), recomputed with EoL nodes
+    assert m_updated_second == (1 if with_eol else 0)
 
     def take(dtype, n):
         nonlocal off

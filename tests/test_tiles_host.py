@@ -27,6 +27,8 @@ class HostTiles:
         L.hm_plan_pattern.argtypes = [ctypes.c_void_p, ctypes.c_int, ip, ip]
         L.hm_plan_fill.restype = ctypes.c_int
         L.hm_plan_fill.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, ctypes.c_double, dp, dp, dp]
+        L.hm_plan_fill_ex.restype = ctypes.c_int
+        L.hm_plan_fill_ex.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, ctypes.c_double, dp, dp, dp, ctypes.c_int]
         fn = np.ascontiguousarray(fn, np.int32).reshape(-1, 3)
         es = np.ascontiguousarray(es, np.int32).reshape(-1, 4)
         err = ctypes.create_string_buffer(256)
@@ -69,6 +71,26 @@ class HostTiles:
 
     def close(self):
         self.L.hm_plan_destroy(self.h)
+
+
+def test_tiles_host_m_unchanged_mode(hostmath):
+    """EOLC_FILL_M_UNCHANGED: f and MDK bit-identical to the full fill, not one M value written."""
+    for gen, n in (("regular2", 19), ("build4", 8)):
+        X, fn = getattr(E.meshgen, gen)(n)
+        es = E.meshgen.edge_stencils(X.shape[0], fn)
+        x = E.meshgen.drape_state(X, seed=n)
+        T = HostTiles(hostmath, X.shape[0], fn, es, X, True)
+        f, Mv, Kv = T.fill(x, X)
+        f2, M2, K2 = np.full_like(f, np.nan), np.full(Mv.size + 1, np.nan)[:Mv.size], np.full_like(Kv, np.nan)
+        m = np.array(MAT, np.float64); g = np.array(GRAV, np.float64)
+        x = np.ascontiguousarray(x); Xc = np.ascontiguousarray(X)
+        rc = hostmath.hm_plan_fill_ex(T.h, x.ctypes.data_as(dp), Xc.ctypes.data_as(dp), m.ctypes.data_as(dp), g.ctypes.data_as(dp), H,
+                                      f2.ctypes.data_as(dp), M2.ctypes.data_as(dp), K2.ctypes.data_as(dp), 1)
+        if (f2.ctypes.data // 8) % 2 == 0 and (K2.ctypes.data // 8) % 2 == 0:
+            assert rc == 0
+        assert f2.tobytes() == f.tobytes() and K2.tobytes() == Kv.tobytes()
+        assert np.isnan(M2).all()
+        T.close()
 
 
 def _check(T, fn, es, x, X, oracle, what, mat=MAT, grav=GRAV, h=H, phases=(0, 0, 0), eol_index=None):
