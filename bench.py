@@ -10,9 +10,13 @@ does not shard: weak scaling, no collective on the data path; NCCL
 max-over-ranks of the device time.
 
   value        element assemblies / s with x, X resident in HBM (device-pointer C-ABI entry, CUDA events on the ctx stream)
-  e2e          the same through the host-buffer C-ABI entry (eolc_forces_fill): pinned x/X H2D + f/M/MDK D2H every step
+  e2e          the same through the host-buffer C-ABI entry (eolc_forces_fill_ex) with page-locked buffers from eolc_host_alloc:
+               x/X H2D + f/MDK D2H every step; M is copied only when it changed (it depends on X and the density only) —
+               the steady step of a simulation without remeshing; the full fill (M recomputed and copied) is reported beside it
   roofline     algorithmic bytes of one fill (24N+16N+12F+16Ei+24N+8nnz(M)+8nnz(MDK)) / device time of one fill
   cpu_baseline the oracle (reference Compute*.cpp object code + restated Forces.cpp glue), 1 thread, bounded sample
+  ensemble     BASELINE configs[4] at every N: 4096 independent 64x64 scenes sharded contiguously over the ranks (strong
+               scaling, no collective), batched Forces::fill + batched CD2 narrow phase per step
   cd           secondary metric contacts/s: CD2 on the 512x512 box scene (BASELINE configs[2]), device + D2H of the list
 """
 import argparse
@@ -148,6 +152,30 @@ class ClockSampler:
         return out
 
 
+def sheet_counts(n):
+    """regular2 n x n sheet: N, F, E, Ei, nnz(M), nnz(MDK) in closed form (pattern(M) = node pairs sharing a face,
+    pattern(MDK) adds the opposite-vertex pairs of interior edges; 3x3 blocks)."""
+    N, F = n * n, 2 * (n - 1) ** 2
+    Ed = 3 * (n - 1) ** 2 + 2 * (n - 1)
+    Ei = Ed - 4 * (n - 1)
+    return N, F, Ed, Ei, 9 * (N + 2 * Ed), 9 * (N + 2 * Ed + 2 * Ei)
+
+
+def workload_config(workload, world):
+    """The `config` object of the JSON line — the same for both arms (the driver compares them)."""
+    n = {"sheet1024": 1024, "sheet256": 256, "ensemble64": 64}[workload]
+    N, F, _, Ei, nnzM, nnzK = sheet_counts(n)
+    if workload == "ensemble64":
+        per = "4096 scenes sharded over %d rank(s)" % world
+        par = "ensemble x%d" % world
+        ws = algorithmic_bytes(N, F, Ei, nnzM, nnzK) * (4096 // world)
+    else:
+        per, par, ws = 1, "replicas x%d" % world, algorithmic_bytes(N, F, Ei, nnzM, nnzK)
+    return {"workload": workload_name(workload), "mesh": f"regular2 n={n}", "scenes_per_gpu": per, "nodes": N, "faces": F,
+            "interior_edges": Ei, "nnz_M": nnzM, "nnz_MDK": nnzK, "parallelism": par,
+            "l2_policy": "working set per step (%.0f MB) exceeds the 126 MB L2" % (ws / 1e6)}
+
+
 def make_sheet(n, seed):
     import eol_cloth_b200 as E
     X, fn = E.meshgen.regular2(n)
@@ -171,39 +199,76 @@ def cpu_forces_sample(n=256, repeats=3):
     return elements / best, elements, best
 
 
+def mem_available_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return None
+
+
 def run_reference(args):
-    """--impl reference: the reference CPU path (oracle) on the same metric, bounded sample per step, on all the host threads the path
-    can use: the reference program is single-threaded; the oracle's timing variant runs its element loops on every core and the two
-    setFromTriplets side by side (same triplets, same sums — tests/test_oracle.py), which is the most the path offers."""
+    """--impl reference: the reference's CPU path on the same metric and config, on the box's host cores.  Only oracle/ is loaded
+    (reference Compute*.cpp object code + the Forces.cpp glue restated, pinned in tests/test_oracle.py) — no product code.
+    The reference program is single-threaded; the oracle's timing variant runs the element loops on every core and the two
+    setFromTriplets side by side (same triplets, same sums, bit for bit), which is the most the path offers: `value` is that
+    threaded number, `single_thread_value` the reference as it is.
+    Step = one Forces::fill of a BOUNDED SAMPLE of the workload: the first `rows` grid rows of the same 1024 x 1024 sheet (same
+    coordinates, numbering, state), so that the K + W steps the driver asks for end within minutes; then ONE fill of the full
+    configuration (when the host has the memory: ~23 GB of triplets) is timed beside it as `full_config`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle as O
-    n = 256
-    X, fn, es, x = make_sheet(n, 0)
+    n = {"sheet1024": 1024, "sheet256": 256, "ensemble64": 64}[args.workload]
+    rows = n if n <= 256 else min(n, max(2, args.ref_rows))
+    X, fn = O.sheet_regular2(n, rows=rows)
+    es = O.arcsim_edge_stencils(X.shape[0], fn)
+    x = O.drape_state(X, seed=0, n_total=n * n)
     elements = fn.shape[0] + int((es[:, 3] >= 0).sum())
     cores = max(1, min(len(os.sched_getaffinity(0)), 64))
     t = time.perf_counter()
-    O.forces_fill(fn, es, x, X, MAT, GRAV, H)                      # the reference as it is: one thread (also the warm-up)
+    O.forces_fill(fn, es, x, X, MAT, GRAV, H)                      # the reference as it is: one thread (untimed warm-up of the caches too)
     dt1 = time.perf_counter() - t
-    for _ in range(max(0, min(args.warmup, 2) - 1)):
+    for _ in range(args.warmup):
         O.forces_fill(fn, es, x, X, MAT, GRAV, H, threads=cores)
-    steps = max(1, min(args.steps, 10))
     t = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(args.steps):
         O.forces_fill(fn, es, x, X, MAT, GRAV, H, threads=cores)
-    dt = (time.perf_counter() - t) / steps
+    dt = (time.perf_counter() - t) / args.steps
     value = elements / dt
-    sample = f"regular2 n={n} sheet ({elements} elements) per step; the 1024x1024 workload needs >25 GB of triplets on the reference path"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    N_full, F_full, _, Ei_full, _, _ = sheet_counts(n)
+    sample = (f"Forces::fill of the first {rows} grid rows of the regular2 n={n} sheet ({elements} of its {F_full + Ei_full} elements) per step"
+              if rows < n else f"Forces::fill of the whole regular2 n={n} sheet ({elements} elements) per step")
+    full = None
+    avail = mem_available_gb()
+    if rows < n and not args.no_full:
+        if avail is not None and avail < 40.0:
+            full = {"skipped": "MemAvailable %.1f GB < 40 GB (the reference path materialises ~23 GB of triplets at 1024^2)" % avail}
+        else:
+            Xf, fnf = O.sheet_regular2(n)
+            esf = O.arcsim_edge_stencils(Xf.shape[0], fnf)
+            xf = O.drape_state(Xf, seed=0)
+            t = time.perf_counter()
+            r = O.forces_fill(fnf, esf, xf, Xf, MAT, GRAV, H, threads=cores)
+            dtf = time.perf_counter() - t
+            full = {"value": (F_full + Ei_full) / dtf, "unit": UNIT, "seconds": dtf, "elements": F_full + Ei_full, "steps": 1,
+                    "nnz_MDK": int(r["MDK"][2].size), "seconds_elements_assembly": list(r["seconds"]),
+                    "note": "one fill of the whole configuration, same threads; the sample's per-element rate is the HIGHER of the two "
+                            "(less memory traffic), so `value` is the conservative denominator"}
+            del r
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "ensemble64" else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "sample": sample},
+            "config": workload_config(args.workload, max(1, args.gpus)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "single_thread_value": elements / dt1,
-                             "note": "reference Compute*.cpp object code (oracle/_ref) + Eigen-free restatement of Forces.cpp glue; element loops on all cores, "
-                                     "M and MDK assembled side by side; the reference itself is single-threaded (single_thread_value); triplet growth and "
-                                     "setFromTriplets dominate and do not parallelise further"},
+                             "value_is": "threaded timing variant on %d cores (the reference program itself is single-threaded: single_thread_value)" % cores,
+                             "single_thread_value": elements / dt1, "full_config": full, "mem_available_gb": avail,
+                             "note": "reference Compute*.cpp object code (oracle/_ref) + Eigen-free restatement of Forces.cpp glue incl. triplets and "
+                                     "setFromTriplets; no product code is loaded by this arm"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
@@ -213,6 +278,13 @@ def workload_name(w):
     return {"sheet1024": "regular2 1024x1024 sheet, Forces::fill (f+M+MDK) into fixed CSR pattern (BASELINE configs[3])",
             "sheet256": "regular2 256x256 sheet, Forces::fill (BASELINE configs[1])",
             "ensemble64": "ensemble of 4096 regular2 64x64 scenes, Forces::fill batched (BASELINE configs[4])"}[w]
+
+
+def numa_nodes():
+    try:
+        return len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except Exception:
+        return None
 
 
 def bind_to_gpu_numa(local):
@@ -280,6 +352,7 @@ def run_ours(args):
     elements = F + Ei
     nnzM, nnzK = plan.nnz
     abytes = algorithmic_bytes(N, F, Ei, nnzM, nnzK)
+    assert (N, F, Ei, nnzM, nnzK) == tuple(sheet_counts(n)[i] for i in (0, 1, 3, 4, 5)), "closed-form counts disagree with the plan"
 
     xs = np.stack([E.meshgen.drape_state(X, seed=lo + s) for s in range(S)]) if S <= 64 else None
     if xs is None:   # big ensembles: perturb per scene on the device-side copy (seeded, cheap)
@@ -319,31 +392,58 @@ def run_ours(args):
     total_elements = sum_over_ranks(float(elements * S), dev)
     value = total_elements / (ms * 1e-3)
     checksum = float(K_d[0].sum().item()) + float(f_d[0].sum().item())
+    # the timed region above is short (K fills of < 1 ms): five more blocks of K fills each, for the spread (not the headline)
+    repeat_ms = []
+    for _ in range(5):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_dev()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        repeat_ms.append(ev0.elapsed_time(ev1) / args.steps)
 
-    # ---- e2e: host-buffer C-ABI entry, pinned host arrays, one scene per step per rank
-    x_h = torch.from_numpy(xs[0].copy()).pin_memory()
-    X_h = torch.from_numpy(X.copy()).pin_memory()
-    f_h = torch.empty(3 * N, dtype=torch.float64).pin_memory()
-    M_h = torch.empty(nnzM, dtype=torch.float64).pin_memory()
-    K_h = torch.empty(nnzK, dtype=torch.float64).pin_memory()
-    xa, Xa, fa, Ma, Ka = (t.numpy() for t in (x_h, X_h, f_h, M_h, K_h))
+    # ---- e2e: host-buffer C-ABI entry (what eolc::host::Forces::fill calls), one scene per step per rank.  Buffers are page-locked
+    # memory from eolc_host_alloc (the host layer's PinnedArray).  Steady step: EOLC_FILL_M_UNCHANGED (X and density as in the
+    # previous fill => M is the same matrix and is neither recomputed nor copied); full step: everything.
+    from eol_cloth_b200 import capi
+    hb = [capi.HostBuffer(shape) for shape in ((N, 3), (N, 2), (3 * N,), (nnzM,), (nnzK,))]
+    xa, Xa, fa, Ma, Ka = (b.array for b in hb)
+    xa[:] = xs[0]; Xa[:] = X
     e2e_steps = max(3, min(args.steps, 10))
 
-    def step_host():
-        plan.fill_into(xa, Xa, MAT, GRAV, H, fa, Ma, Ka)
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3, dev)
+    def timed_host(fn_step, reps):
+        for _ in range(2):
+            fn_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn_step()
+        barrier()
+        return max_over_ranks((time.perf_counter() - t0) / reps * 1e3, dev)
+
+    e2e_full_ms = timed_host(lambda: plan.fill_into(xa, Xa, MAT, GRAV, H, fa, Ma, Ka), e2e_steps)
+    e2e_ms = timed_host(lambda: plan.fill_into(xa, Xa, MAT, GRAV, H, fa, Ma, Ka, m_unchanged=True), e2e_steps)
+    e2e_checksum = float(Ka[::4099].sum() + fa[::257].sum() + Ma[::4099].sum())
+    # the same call with pageable caller buffers (plain numpy arrays): staged through the library's pinned buffer + one more copy
+    pg = [np.empty_like(a) for a in (fa, Ma, Ka)]
+    e2e_pageable_ms = None
+    if rank == 0:      # no collective in here: the other ranks have moved on
+        xp_, Xp_ = np.ascontiguousarray(xs[0]), np.ascontiguousarray(X)
+        for it in range(4):
+            if it == 1:
+                t0 = time.perf_counter()
+            plan.fill_into(xp_, Xp_, MAT, GRAV, H, pg[0], pg[1], pg[2], m_unchanged=True)
+        e2e_pageable_ms = (time.perf_counter() - t0) / 3 * 1e3
+    del pg
     clk.__exit__(None, None, None)
     clocks = clk.summary()
-    e2e_value = sum_over_ranks(float(elements), dev) / (e2e_ms * 1e-3)
+    total_el_1 = sum_over_ranks(float(elements), dev)
+    e2e_value = total_el_1 / (e2e_ms * 1e-3)
     h2d = 8 * (3 * N + 2 * N)
-    d2h = 8 * (3 * N + nnzM + nnzK)
+    d2h = 8 * (3 * N + nnzK)
+    d2h_full = 8 * (3 * N + nnzM + nnzK)
+    for b_ in hb:
+        b_.free()
 
     peak, peak_src = measured_peak()
     traffic, traffic_src = measured_traffic(args.workload)
@@ -353,37 +453,45 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.workload), "mesh": f"regular2 n={n}", "scenes_per_gpu": S, "nodes": N,
-                   "faces": F, "interior_edges": Ei, "nnz_M": nnzM, "nnz_MDK": nnzK, "parallelism": f"replicas x{world}",
-                   "l2_policy": "working set per step (%.0f MB) exceeds the 126 MB L2" % (abytes * S / 1e6)},
+        "config": workload_config(args.workload, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "steps": e2e_steps, "api": "eolc_forces_fill (host buffers, pinned)"},
+                "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "api": "eolc_forces_fill_ex(EOLC_FILL_M_UNCHANGED), page-locked host buffers from eolc_host_alloc: x, X in; f, MDK out; "
+                       "M is the previous step's matrix (depends on X and the density only) and is not copied again",
+                "full_fill": {"value": total_el_1 / (e2e_full_ms * 1e-3), "ms_per_step": e2e_full_ms, "d2h_bytes_per_step": d2h_full,
+                              "what": "every step recomputes and copies M too (a step after remeshing)"},
+                "pageable_ms_per_step": e2e_pageable_ms, "checksum": e2e_checksum, "numa_nodes": numa_nodes()},
         "gpu_launches": args.steps * plan.launches_per_fill * (1 if S == 1 else 1),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic if pipeline == "tiles" else None, "traffic_source": traffic_src if pipeline == "tiles" else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_fill": abytes, "launches_per_fill": plan.launches_per_fill,
                      "kernel": "assemble_%s_kernel: one launch = one fill of all scenes of the rank (%d elements)" % (pipeline, elements * S),
-                     "ms": ms_local,
+                     "ms": ms_local, "repeat_ms": sorted(repeat_ms),
                      "note": "not HBM-bound: FP64 issue + shared-memory traffic bound, see DESIGN.md 3.4"},
         "checksum": checksum,
     }
 
-    # the other roof of this kernel (the honest bound is max(HBM time, FP64 time)): FP64 instructions executed per
-    # launch (a property of the plan, from the committed ncu capture) against the issue rate of the FP64 pipe — 2 warp instructions
-    # per clock and SM (64 FP64 lanes per SM), at the SM clock sampled during the run
+    # the other roof of this kernel (the honest bound is max(HBM time, FP64 time)): FP64 warp instructions executed per
+    # launch (a property of the plan, from the committed ncu capture) against the MEASURED issue rate of the FP64 pipe
+    # (profiles/fp64_peak.json: scripts/micro/fp64_peak.cu, dependent-DFMA chains, 1.986 warp instructions per clock and SM)
     try:
         fp = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]["fp64_warp_instructions"]
+        pk = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["peak"]
         n_instr = fp["DFMA"] + fp["DMUL"] + fp["DADD"]
-        sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz")
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        if pipeline == "tiles" and S == 1 and sm_mhz:
-            peak_instr = 2.0 * sms * sm_mhz * 1e6 * (ms_local * 1e-3)
-            line["roofline"]["fp64"] = {"warp_instructions_per_fill": n_instr, "tflops_executed": (2 * fp["DFMA"] + fp["DMUL"] + fp["DADD"]) * 32 / (ms_local * 1e-3) / 1e12,
-                                        "frac_of_fp64_issue_peak": n_instr / peak_instr, "source": fp["source"],
-                                        "note": "phase 1 alone keeps the pipe ~1.1-1.2 instr/clk/SM busy (peak 2); phases 2-3 issue no FP64 multiplies"}
+        if pipeline == "tiles" and S == 1:
+            line["roofline"]["fp64"] = {"warp_instructions_per_fill": n_instr,
+                                        "tflops_executed": (2 * fp["DFMA"] + fp["DMUL"] + fp["DADD"]) * 32 / (ms_local * 1e-3) / 1e12,
+                                        "peak_tflops_measured": pk["tflops"], "peak_warp_instr_per_s_measured": pk["warp_instr_per_s"],
+                                        "frac_of_fp64_issue_peak": n_instr / (pk["warp_instr_per_s"] * ms_local * 1e-3),
+                                        "floor_ms_at_measured_peak": n_instr / pk["warp_instr_per_s"] * 1e3,
+                                        "source": fp["source"], "peak_source": "profiles/fp64_peak.json (DFMA microbenchmark on B200, this round)"}
     except Exception:
         pass
+    if not args.no_ensemble and args.workload != "ensemble64":
+        ens = bench_ensemble(ctx, dev, stream, rank, world, barrier)     # every rank takes part
+        if rank == 0:
+            line["ensemble"] = ens
     if rank == 0 and not args.no_cpu:
         v, el, dt = cpu_forces_sample(256, 3)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
@@ -395,6 +503,10 @@ def run_ours(args):
         line["consumer"] = bench_consumer(plan, dev, stream, f_d, M_d, K_d, N, nnzM, nnzK)
         line["consumer"]["normals"] = bench_normals(plan, dev, stream, x_d, N, F)
         line["eol"] = bench_eol(ctx, dev, stream, n, X, fn, es, x_d, X_d, ms_local)
+    if rank == 0 and S == 1 and not args.no_cpu:
+        hl = bench_host_layer(n)
+        if hl is not None:
+            line["e2e"]["host_layer"] = hl
     if numa:
         line["e2e"]["host_affinity"] = numa
     if rank == 0:
@@ -404,6 +516,103 @@ def run_ours(args):
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     return 0
+
+
+def gather_ranks(v, device, world):
+    import torch
+    if world == 1:
+        return [float(v)]
+    t = torch.tensor([float(v)], dtype=torch.float64, device=device)
+    out = [torch.zeros_like(t) for _ in range(world)]
+    torch.distributed.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
+def bench_ensemble(ctx, dev, stream, rank, world, barrier, total_scenes=4096, n=64, steps=10, warmup=3):
+    """BASELINE configs[4] / SURVEY §8e: 4096 independent regular2 64x64 scenes (state seed = scene id) over the box of the box
+    scene, sharded contiguously over the ranks (strong scaling, no collective on the data path).  A step = one batched Forces::fill
+    of the rank's scenes (1 launch) + one batched CD2 narrow phase (records stay on the device, the per-scene offsets come
+    back).  Timed with CUDA events on the library's stream, max over ranks."""
+    import torch
+    import eol_cloth_b200 as E
+    from eol_cloth_b200.collisions import make_obstacles
+    lo, hi = shard_range(total_scenes, rank, world)
+    S = hi - lo
+    X, fn = E.meshgen.regular2(n)
+    N, F = X.shape[0], fn.shape[0]
+    es = E.meshgen.edge_stencils(N, fn)
+    centre = np.array([0.9175, -0.25, -0.549])           # SURVEY §8d variant 3b: all three contact types fire
+    obs = make_obstacles(E.meshgen.BOX_THRESHOLD, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(centre)[None])
+    plan = E.ForcesPlan(ctx, N, fn, es, X_hint=X)
+    cdp = E.CollisionPlan(ctx, N, fn, E.meshgen.BOX_THRESHOLD)
+    nnzM, nnzK = plan.nnz
+    elements = F + plan.n_interior_edges
+    xs = np.stack([E.meshgen.box_scene_state(X, seed=lo + s, centre=centre) for s in range(S)])
+    x_d = torch.from_numpy(xs).to(dev)
+    X_d = torch.from_numpy(np.broadcast_to(X, (S,) + X.shape).copy()).to(dev)
+    f_d = torch.empty((S, 3 * N), dtype=torch.float64, device=dev)
+    M_d = torch.empty((S, nnzM), dtype=torch.float64, device=dev)
+    K_d = torch.empty((S, nnzK), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    fill_ms = cd_ms = 0.0
+    contacts = 0
+    for it in range(warmup + steps):
+        if it == warmup:
+            barrier()
+        ev[0].record(stream)
+        plan.fill_dev(x_d.data_ptr(), X_d.data_ptr(), MAT, GRAV, H, f_d.data_ptr(), M_d.data_ptr(), K_d.data_ptr(), n_scenes=S)
+        ev[1].record(stream)
+        off = cdp.run_resident(x_d.data_ptr(), obs, 0, 0, n_scenes=S)
+        ev[2].record(stream)
+        torch.cuda.synchronize()
+        if it >= warmup:
+            fill_ms += ev[0].elapsed_time(ev[1]); cd_ms += ev[1].elapsed_time(ev[2])
+        contacts = int(off[-1])
+    barrier()
+    fill_ms /= steps; cd_ms /= steps
+    pair_tests, cd_launches = cdp.stats()
+    per_rank = gather_ranks(fill_ms + cd_ms, dev, world)
+    step_ms = max(per_rank)
+    fill_max, cd_max = max_over_ranks(fill_ms, dev), max_over_ranks(cd_ms, dev)
+    tot_contacts = sum_over_ranks(float(contacts), dev)
+    tot_tests = sum_over_ranks(float(pair_tests), dev)
+    N_, F_, _, Ei_, nM_, nK_ = sheet_counts(n)
+    abytes = algorithmic_bytes(N_, F_, Ei_, nM_, nK_) * S
+    peak, _ = measured_peak()
+    checksum = float(K_d[0].sum().item()) + float(off[1])
+    out = {"workload": "ensemble of %d independent regular2 %dx%d scenes (BASELINE configs[4]): batched Forces::fill + batched CD2 over the box" % (total_scenes, n, n),
+           "scaling": "strong", "scenes_total": total_scenes, "scenes_this_rank": S, "shard": "contiguous, rank r owns [r S/G, (r+1) S/G)",
+           "steps": steps, "warmup": warmup,
+           "elements_per_s": total_scenes * elements / (fill_max * 1e-3), "contacts_per_s": tot_contacts / (cd_max * 1e-3),
+           "pair_tests_per_s": tot_tests / (cd_max * 1e-3), "scenes_per_s": total_scenes / (step_ms * 1e-3),
+           "ms_per_step": step_ms, "fill_ms": fill_max, "cd_ms": cd_max, "per_rank_ms": per_rank,
+           "load_balance": (sum(per_rank) / len(per_rank)) / step_ms,
+           "contacts_total": int(tot_contacts), "launches_per_step": plan.launches_per_fill + cd_launches,
+           "fill_roofline": {"achieved_GBps": abytes / (fill_ms * 1e-3) / 1e9, "frac_of_hbm_peak": abytes / (fill_ms * 1e-3) / 1e9 / peak},
+           "timing": "CUDA events on the library stream, max over ranks; contacts stay on the device (eolc_cd_run_batched_resident_dev)",
+           "parity": "tests/test_cd_gpu.py::test_ensemble_4096_scenes_sampled_against_reference, tests/test_forces_gpu.py (batched fill)",
+           "checksum": checksum}
+    plan.close(); cdp.close()
+    del x_d, X_d, f_d, M_d, K_d
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_host_layer(n):
+    """Adapter-level step time: the C++ host layer (include/eolc_host.hpp) driven from a C++ program with an ArcSim-shaped pointer
+    mesh — flatten() + Forces::fill, as adapter/Forces_fill_b200.cpp does each step (minus the copy into Eigen objects)."""
+    exe = os.path.join(ROOT, "tests", "cpp", "host_driver")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, "bench", str(n), "3"], capture_output=True, text=True, timeout=300)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        d["what"] = "flatten of the pointer mesh + eolc::host::Forces::fill per step (tests/cpp/host_driver bench)"
+        d["elements_per_s_steady"] = d["elements"] / (d["step_M_unchanged_ms"] * 1e-3)
+        return d
+    except Exception as e:
+        return {"error": str(e)[:200]}
 
 
 def bench_consumer(plan, dev, stream, f_d, M_d, K_d, N, nnzM, nnzK):
@@ -517,7 +726,27 @@ def bench_cd(ctx, dev, stream):
         c, _ = plan.run(x_d.data_ptr(), obs, 0, 0, x_is_device_ptr=True, out=out)
     dt = (time.perf_counter() - t) / reps
     pair_tests, launches = plan.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        plan.run_resident(x_d.data_ptr(), obs, 0, 0)
+    t = time.perf_counter()
+    e0.record(stream)
+    for _ in range(reps):
+        plan.run_resident(x_d.data_ptr(), obs, 0, 0)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dt_res = (time.perf_counter() - t) / reps
+    dev_ms = e0.elapsed_time(e1) / reps
+    t = time.perf_counter()
+    for _ in range(reps):
+        plan.run_resident(x_d.data_ptr(), obs, 0, 0)
+        rows = plan.contact_rows()
+    dt_rows = (time.perf_counter() - t) / reps
     out = {"workload": "CD2, regular2 512x512 over the simulationSettingsBox.json box (BASELINE configs[2])",
+           "resident": {"ms_per_call": dt_res * 1e3, "stream_ms_per_call": dev_ms, "contacts_per_s": len(c) / dt_res,
+                        "what": "eolc_cd_run_batched_resident_dev: records stay on the device, offsets come back (one stream sync)"},
+           "resident_plus_rows": {"ms_per_call": dt_rows * 1e3, "rows": int(len(rows[0])),
+                                  "what": "resident run + eolc_cd_contact_rows: the 112 B/contact inequality rows of Constraints::fill to the host instead of the 264 B records"},
            "contacts": int(len(c)), "ms_per_call": dt * 1e3, "contacts_per_s": len(c) / dt,
            "pair_tests_per_s": pair_tests / dt, "launches_per_call": launches,
            "timing": "wall clock around eolc_cd_run_dev incl. D2H of the contact list (%d B records, pinned caller buffer) and the host post-pass" % rec_bytes}
@@ -539,6 +768,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sheet1024", choices=["sheet1024", "sheet256", "ensemble64"])
+    ap.add_argument("--ref-rows", type=int, default=128, help="--impl reference: grid rows of the sheet in the per-step sample")
+    ap.add_argument("--no-full", action="store_true", help="--impl reference: skip the single fill of the full configuration")
+    ap.add_argument("--no-ensemble", action="store_true", help="skip the configs[4] ensemble object")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cd", action="store_true", help="skip the secondary CD measurement")
     args = ap.parse_args()

@@ -75,6 +75,9 @@ def lib():
                                   ctypes.c_int, c_vp, ctypes.c_int32, c_ip]
     L.eolc_cd_run_batched_dev.argtypes = [c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_dp, c_dp, ctypes.c_int32, c_dp,
                                           c_dp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int32, c_ip]
+    L.eolc_cd_run_batched_resident_dev.argtypes = [c_vp, ctypes.c_int32, c_vp, ctypes.c_int32, c_dp, c_dp, ctypes.c_int32, c_dp,
+                                                   c_dp, ctypes.c_int, ctypes.c_int, c_ip]
+    L.eolc_cd_contacts_dev.argtypes = [c_vp, ctypes.POINTER(c_vp), c_ip]
     L.eolc_cd_angle_cuts.argtypes = [c_dp, c_dp, c_dp]
     L.eolc_constraints_contact_rows.argtypes = [c_vp, ctypes.c_int32, c_vp, c_ip, c_ip, c_ip, c_dp]
     L.eolc_cd_contact_rows.argtypes = [c_vp, c_vp, ctypes.c_int32, c_ip, c_ip, c_ip, c_dp]

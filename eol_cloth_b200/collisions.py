@@ -77,6 +77,22 @@ class CollisionPlan:
             capi.check(rc)
             return (out[:n], off) if x_is_device_ptr else out[:n]
 
+    def run_resident(self, x_ptr, obs, point_eol_flag, remap, n_scenes=1):
+        """Device-resident run: x_ptr is a device pointer to n_scenes states; the records stay on the device (contacts_dev()),
+        only the per-scene offsets (n_scenes + 1) come back."""
+        off = np.zeros(n_scenes + 1, dtype=np.int32)
+        nP, nB = obs.pxyz.shape[0], obs.box_whd.shape[0]
+        capi.check(capi.lib().eolc_cd_run_batched_resident_dev(self._h, int(n_scenes), x_ptr, nP, capi.dptr(obs.pxyz), capi.dptr(obs.pnorms),
+                                                               nB, capi.dptr(obs.box_whd), capi.dptr(obs.box_E), int(point_eol_flag),
+                                                               int(remap), capi.iptr(off)))
+        return off
+
+    def contacts_dev(self):
+        """(device pointer, count) of the records of the last run."""
+        p, n = capi.c_vp(), ctypes.c_int32(0)
+        capi.check(capi.lib().eolc_cd_contacts_dev(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
     def contact_rows(self, node_eol=None):
         """Inequality rows of the contacts of the LAST run, built on the device (Constraints.cpp:424-468): (row_nnz, cols, vals) with
         9 slots per row in the reference's triplet order."""

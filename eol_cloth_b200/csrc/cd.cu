@@ -810,10 +810,14 @@ int eolc_cd_angle_cuts(const double *box_whd, const double *box_E, double *cuts1
     return EOLC_OK;
 }
 
-int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32_t n_points, const double *pxyz,
-                            const double *pnorms, int32_t n_boxes, const double *box_whd, const double *box_E,
-                            int point_eol_flag, int remap_box_indices, eolc_contact *out, int32_t capacity,
-                            int32_t *scene_offset) {
+}  // extern "C" (reopened below)
+
+// One run.  resident: the records stay in the plan's device buffer (eolc_cd_contacts_dev / eolc_cd_contact_rows read them there);
+// only the per-scene offsets come back to the host.
+static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32_t n_points, const double *pxyz,
+                       const double *pnorms, int32_t n_boxes, const double *box_whd, const double *box_E,
+                       int point_eol_flag, int remap_box_indices, eolc_contact *out, int32_t capacity,
+                       int32_t *scene_offset, bool resident) {
     EOLC_REQUIRE(plan && scene_offset, "NULL argument");
     eolc_cd_plan *P = plan;
     EOLC_REQUIRE(S >= 1 && n_points >= 0 && n_boxes >= 0 && capacity >= 0, "bad sizes");
@@ -896,7 +900,7 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
     // ---- capacity check before anything is written to the caller
     const int *bo = P->p_blockoff.p;
     for (int s = 0; s <= S; ++s) scene_offset[s] = bo[(size_t)s * scene_items / 256];
-    if (total > capacity) {
+    if (!resident && total > capacity) {
         set_error("contact buffer too small: need %d, capacity %d", total, capacity);
         return EOLC_ERR_CAPACITY;
     }
@@ -912,6 +916,7 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
             k_C_write<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox + nA + nBc, remap_box_indices, nP);
             launches += 3;
         }
+        if (!resident) {
         // pinned caller buffer: DMA straight into it; pageable: via the plan's pinned staging
         cudaPointerAttributes pa;
         bool out_pinned = cudaPointerGetAttributes(&pa, out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
@@ -921,6 +926,7 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
         EOLC_CUDA(cudaMemcpyAsync(dst, P->d_out.p, sizeof(eolc_contact) * total, cudaMemcpyDeviceToHost, st));
         EOLC_CUDA(cudaStreamSynchronize(st));
         if (!out_pinned) memcpy(out, dst, sizeof(eolc_contact) * total);
+        }
     }
     EOLC_CUDA(cudaGetLastError());
     P->last_launches = launches;
@@ -929,7 +935,8 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
 
     // ---- step (D) (:1022-1052): per box corner keep only the closest count1 == 1 record.  Only section Bc emits
     // count1 == 1 records and it emits at most one per corner, so the reference's delete list is always empty and the
-    // pass is the identity; this is verified per box from the (<= 8 record) corner section, O(1) per box.
+    // pass is the identity; this is verified per box from the (<= 8 record) corner section, O(1) per box (host copy only).
+    if (!resident)
     for (int s = 0; s < S; ++s)
         for (int b = 0; b < nB; ++b) {
             const size_t bb = ((size_t)s * scene_items + secBox + (size_t)b * box_items + nA) / 256;
@@ -944,6 +951,30 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, 
                 seen |= 1 << corner;
             }
         }
+    return EOLC_OK;
+}
+
+extern "C" {
+
+int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32_t n_points, const double *pxyz,
+                            const double *pnorms, int32_t n_boxes, const double *box_whd, const double *box_E,
+                            int point_eol_flag, int remap_box_indices, eolc_contact *out, int32_t capacity,
+                            int32_t *scene_offset) {
+    return cd_run_impl(plan, S, x_dev, n_points, pxyz, pnorms, n_boxes, box_whd, box_E, point_eol_flag, remap_box_indices, out, capacity,
+                       scene_offset, false);
+}
+
+int eolc_cd_run_batched_resident_dev(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32_t n_points, const double *pxyz,
+                                     const double *pnorms, int32_t n_boxes, const double *box_whd, const double *box_E,
+                                     int point_eol_flag, int remap_box_indices, int32_t *scene_offset) {
+    return cd_run_impl(plan, S, x_dev, n_points, pxyz, pnorms, n_boxes, box_whd, box_E, point_eol_flag, remap_box_indices, nullptr, 0,
+                       scene_offset, true);
+}
+
+int eolc_cd_contacts_dev(const eolc_cd_plan *plan, const eolc_contact **contacts_dev, int32_t *count) {
+    EOLC_REQUIRE(plan && contacts_dev && count, "NULL argument");
+    *contacts_dev = plan->last_total > 0 ? plan->d_out.p : nullptr;
+    *count = plan->last_total;
     return EOLC_OK;
 }
 

@@ -186,6 +186,16 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t n_scenes, const double *
                             const double *pxyz, const double *pnorms, int32_t n_boxes, const double *box_whd,
                             const double *box_E, int point_eol_flag, int remap_box_indices, eolc_contact *out,
                             int32_t capacity, int32_t *scene_offset);
+/* Same run, but the records stay on the device (no device-to-host copy of the list; only the per-scene offsets come back):
+ * for a consumer that lives on the device too — eolc_cd_contact_rows below (112 B of rows per contact instead of the 264 B
+ * record), or any kernel reading eolc_cd_contacts_dev.  Step (D) needs no pass: section Bc emits at most one record per
+ * corner by construction (a lexicographic argmin).  The device buffer is owned by the plan and valid until its next run. */
+int eolc_cd_run_batched_resident_dev(eolc_cd_plan *plan, int32_t n_scenes, const double *x_dev, int32_t n_points,
+                                     const double *pxyz, const double *pnorms, int32_t n_boxes, const double *box_whd,
+                                     const double *box_E, int point_eol_flag, int remap_box_indices, int32_t *scene_offset);
+int eolc_cd_contacts_dev(const eolc_cd_plan *plan, const eolc_contact **contacts_dev, int32_t *count);
+/* Limits of one run: n_scenes * max(8 * n_boxes, n_points, 1) <= 65535 (a grid dimension); larger batches / point clouds must be
+ * split by the caller (EOLC_ERR_ARG otherwise). */
 /* Host-only diagnostic (no GPU needed).  Section C's three acos() (src/boxTriCollision.cpp:879-887, :907-915) only feed
  * threshold comparisons; the device decides them in cosine space against critical doubles that the host finds by bisection
  * WITH ITS OWN libm acos (the function a reference build on the same machine calls), checking every double in a window on

@@ -105,6 +105,62 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+# ---- synthetic inputs without the product package (bench.py --impl reference must not load libeolc_b200.so) -------------------
+def arcsim_edge_stencils(n_nodes, face_nodes):
+    """(E,4) int32 stencils (n0, n1, opp(adjf[0]), opp(adjf[1])), -1 = no face, in the order ArcSim creates mesh.edges while faces
+    are added (Mesh::add(Face), src/external/ArcSim/mesh.cpp:356-378): for face k, i = 0,1,2, edge (v[i] -> v[i+1]) is appended iff
+    no edge joins those nodes yet; adjf[side] with side = 0 iff the face runs n[0] -> n[1].  Vectorised numpy restatement;
+    tests/test_oracle.py holds it equal to the loop restatement and to eolc_mesh_edge_stencils."""
+    fn = _i32(face_nodes).reshape(-1, 3)
+    a = fn[:, [0, 1, 2]].ravel()
+    b = fn[:, [1, 2, 0]].ravel()
+    c = fn[:, [2, 0, 1]].ravel()
+    key = np.minimum(a, b).astype(np.int64) * int(n_nodes) + np.maximum(a, b)
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    first = np.ones(ks.size, bool)
+    first[1:] = ks[1:] != ks[:-1]
+    gid = np.cumsum(first) - 1
+    creators = order[first]                  # the half-edge that creates each edge = its first occurrence
+    eorder = np.argsort(creators, kind="stable")
+    rank = np.empty(eorder.size, np.int64)
+    rank[eorder] = np.arange(eorder.size)
+    ce = creators[eorder]
+    es = np.full((ce.size, 4), -1, np.int32)
+    es[:, 0], es[:, 1], es[:, 2] = a[ce], b[ce], c[ce]
+    later = order[~first]
+    e2 = rank[gid[~first]]
+    side = np.where(a[later] == es[e2, 0], 0, 1)
+    es[e2, 2 + side] = c[later]
+    return es
+
+
+def sheet_regular2(n, m=None, rows=None):
+    """regular2 sheet of the benchmarks: node (i, j) -> i m + j at X = (i/(n-1), j/(m-1)), two counter-clockwise
+    triangles per cell.  rows: only the first `rows` grid rows (a strip of the same sheet: same coordinates, same numbering)."""
+    m = n if m is None else m
+    r = n if rows is None else rows
+    i, j = np.meshgrid(np.arange(r), np.arange(m), indexing="ij")
+    X = np.stack([i.ravel() / (n - 1), j.ravel() / (m - 1)], axis=1).astype(np.float64)
+    ci, cj = np.meshgrid(np.arange(r - 1), np.arange(m - 1), indexing="ij")
+    k0 = (ci * m + cj).ravel()
+    faces = np.empty((2 * k0.size, 3), dtype=np.int32)
+    faces[0::2] = np.stack([k0, k0 + m, k0 + m + 1], axis=1)
+    faces[1::2] = np.stack([k0, k0 + m + 1, k0 + 1], axis=1)
+    return X, faces
+
+
+def drape_state(X, seed=0, amp=0.05, noise=1e-3, n_total=None):
+    """x = (X, 0.05 sin(2 pi X0) cos(2 pi X1)) + U(-1e-3, 1e-3) on all coords; n_total: the random stream
+    is drawn for that many nodes and the first len(X) are used (a strip gets the states of the full sheet's nodes)."""
+    rng = np.random.default_rng(seed)
+    r = rng.uniform(-noise, noise, size=((X.shape[0] if n_total is None else n_total), 3))[:X.shape[0]]
+    x = np.zeros((X.shape[0], 3))
+    x[:, :2] = X
+    x[:, 2] = amp * np.sin(2 * np.pi * X[:, 0]) * np.cos(2 * np.pi * X[:, 1])
+    return x + r
+
+
 MATERIAL_DEFAULT = (0.05, 50.0, 0.01, 1.0e-5, 0.0, 1.0)  # simulationSettings.json:27-33
 GRAV_DEFAULT = (0.0, 0.0, -9.8)
 H_DEFAULT = 0.5e-2

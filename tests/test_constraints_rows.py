@@ -56,3 +56,24 @@ def test_device_rows_of_last_run(ctx, oracle):
     eol = np.zeros(X.shape[0], np.uint8)
     eol[contacts["verts2"][::2, 0]] = 1
     _compare(oracle.constraints_contact_rows(contacts, eol.astype(bool)), *plan.contact_rows(eol))
+
+
+@pytest.mark.gpu
+def test_resident_run_feeds_device_rows(ctx, oracle):
+    """eolc_cd_run_batched_resident_dev: the records never leave the device; offsets and the rows built from them on the device equal
+    those of the host-copied list (3 scenes)."""
+    import torch
+    from eol_cloth_b200.collisions import make_obstacles
+    X, fn = E.meshgen.regular2(36)
+    c0 = np.array([0.9175, -0.25, -0.549])
+    obs = make_obstacles(E.meshgen.BOX_THRESHOLD, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(c0)[None])
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, E.meshgen.BOX_THRESHOLD)
+    xs = np.stack([E.meshgen.box_scene_state(X, seed=s, centre=c0) for s in range(3)])
+    xd = torch.from_numpy(xs).to(torch.device("cuda", ctx.device))
+    torch.cuda.synchronize()
+    host_list, off_h = plan.run(xd.data_ptr(), obs, 0, 0, x_is_device_ptr=True, n_scenes=3)
+    off_r = plan.run_resident(xd.data_ptr(), obs, 0, 0, n_scenes=3)
+    assert np.array_equal(off_r, off_h)
+    ptr, n = plan.contacts_dev()
+    assert n == len(host_list) and ptr
+    _compare(oracle.constraints_contact_rows(host_list), *plan.contact_rows())
