@@ -47,6 +47,48 @@ EOLC_HD double rsq(double x) {
 #endif
 }
 
+// ---- the reference's rest-area expressions, with the reference's roundings ------------------------------------------------------
+// ComputeMembrane.cpp:43 / ComputeInertial.cpp:33 (t7, twice the signed rest area of a face) and ComputeBending.cpp:53 (A0 + A1 of
+// a stencil) are generated as sums of products of ABSOLUTE material coordinates: a small difference of O(|X|^2) terms.  On a fine
+// mesh the rounding of every single product shows in the result at eps |X|^2 / (2A) — 3e-10 relative on the 1024^2 sheet — and
+// from there in every entry of M, of the membrane K and f, and of the bending K.  Agreement with the reference to 1e-10 therefore
+// needs the SAME roundings: each product rounded on its own (no FMA contraction) and the terms added left to right, exactly as the
+// generated code does (g++ without -mfma contracts nothing).  All other arithmetic is well conditioned and may contract.
+EOLC_HD double ref_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+EOLC_HD double ref_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+// Xax * Xby - Xax * Xcy - Xbx * Xay + Xcx * Xay + Xbx * Xcy - Xcx * Xby
+EOLC_HD double rest_area2(double Xax, double Xay, double Xbx, double Xby, double Xcx, double Xcy) {
+    double s = ref_add(ref_mul(Xax, Xby), -ref_mul(Xax, Xcy));
+    s = ref_add(s, -ref_mul(Xbx, Xay));
+    s = ref_add(s, ref_mul(Xcx, Xay));
+    s = ref_add(s, ref_mul(Xbx, Xcy));
+    return ref_add(s, -ref_mul(Xcx, Xby));
+}
+// -X0x * X2y / 2 + X2x * X0y / 2 + X1x * X2y / 2 - X2x * X1y / 2 + X0x * X3y / 2 - X3x * X0y / 2 - X1x * X3y / 2 + X3x * X1y / 2
+// (the halvings are exact, so this is half the left-to-right sum of the signed products)
+EOLC_HD double stencil_area(double X0x, double X0y, double X1x, double X1y, double X2x, double X2y, double X3x, double X3y) {
+    double s = ref_add(-ref_mul(X0x, X2y), ref_mul(X2x, X0y));
+    s = ref_add(s, ref_mul(X1x, X2y));
+    s = ref_add(s, -ref_mul(X2x, X1y));
+    s = ref_add(s, ref_mul(X0x, X3y));
+    s = ref_add(s, -ref_mul(X3x, X0y));
+    s = ref_add(s, -ref_mul(X1x, X3y));
+    s = ref_add(s, ref_mul(X3x, X1y));
+    return 0.5 * s;
+}
+
 struct v3 { double x, y, z; };
 EOLC_HD v3 mk3(double x, double y, double z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
 EOLC_HD v3 operator+(v3 a, v3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -95,7 +137,7 @@ EOLC_HD void face_element(v3 xa, v3 xb, v3 xc, double Xax, double Xay, double Xb
     double il2 = 1.0 / sqrt(dot(Py, Py));
     Py = il2 * Py;
     // rest-shape gradients (ComputeMembrane.cpp:43,52-70,101-110): rows of DX^-1
-    double t7 = Xax * Xby - Xax * Xcy - Xbx * Xay + Xcx * Xay + Xbx * Xcy - Xcx * Xby;
+    double t7 = rest_area2(Xax, Xay, Xbx, Xby, Xcx, Xcy);
     double t17 = 1.0 / t7;
     double gb0 = t17 * (Xcy - Xay), gb1 = t17 * (Xax - Xcx);
     double gc0 = t17 * (Xay - Xby), gc1 = t17 * (Xbx - Xax);
@@ -153,7 +195,7 @@ EOLC_HD void face_element(v3 xa, v3 xb, v3 xc, double Xax, double Xay, double Xb
 
 // rho * 2A(signed) of one face, for the mass matrix (ComputeInertial.cpp:33)
 EOLC_HD double face_t8(double Xax, double Xay, double Xbx, double Xby, double Xcx, double Xcy, double rho) {
-    return rho * (Xax * Xby - Xax * Xcy - Xbx * Xay + Xcx * Xay + Xbx * Xcy - Xcx * Xby);
+    return rho * rest_area2(Xax, Xay, Xbx, Xby, Xcx, Xcy);
 }
 
 // One interior edge: the 10 upper 3x3 blocks of dhh * Kb, order 00,11,22,33,01,02,03,12,13,23
@@ -165,7 +207,7 @@ EOLC_HD void edge_element(v3 x0, v3 x1, v3 x2, v3 x3, double X0x, double X0y, do
     // c = 3/2 * t6 * t17 (ComputeBending.cpp:50-53,102)
     double ex = X1x - X0x, ey = X1y - X0y;
     double t6 = beta * (ex * ex + ey * ey);
-    double den = 0.5 * (-X0x * X2y + X2x * X0y + X1x * X2y - X2x * X1y + X0x * X3y - X3x * X0y - X1x * X3y + X3x * X1y);
+    double den = stencil_area(X0x, X0y, X1x, X1y, X2x, X2y, X3x, X3y);
     double c = 1.5 * t6 / den;
     v3 e = x1 - x0, a = x2 - x0, b = x3 - x0;
     v3 n0 = cross(e, a), n1 = cross(b, e);
@@ -331,7 +373,7 @@ EOLC_HD void edge_element_tile(v3 x0, v3 x1, v3 x2, v3 x3, double X0x, double X0
     // c = 3/2 t6 t17 (ComputeBending.cpp:50-53,102);  K dhh = kk Hess(D), kk = -c dhh
     const double ex = X1x - X0x, ey = X1y - X0y;
     const double t6 = beta * (ex * ex + ey * ey);
-    const double den = 0.5 * (-X0x * X2y + X2x * X0y + X1x * X2y - X2x * X1y + X0x * X3y - X3x * X0y - X1x * X3y + X3x * X1y);
+    const double den = stencil_area(X0x, X0y, X1x, X1y, X2x, X2y, X3x, X3y);
     const double kk = -(1.5 * t6 / den) * dhh;
     const v3 e = x1 - x0, a = x2 - x0, b = x3 - x0;
     const v3 n0 = cross(e, a), n1 = cross(b, e);
@@ -437,7 +479,7 @@ EOLC_HD void face_element_tile(v3 xa, v3 xb, v3 xc, double Xax, double Xay, doub
     const v3 Px = rsq(dot(d1, d1)) * d1;
     v3 Py = cross(nrm, Px);
     Py = rsq(dot(Py, Py)) * Py;
-    const double t7 = Xax * Xby - Xax * Xcy - Xbx * Xay + Xcx * Xay + Xbx * Xcy - Xcx * Xby;
+    const double t7 = rest_area2(Xax, Xay, Xbx, Xby, Xcx, Xcy);
     const double t17 = 1.0 / t7;
     const double gb0 = t17 * (Xcy - Xay), gb1 = t17 * (Xax - Xcx);
     const double gc0 = t17 * (Xay - Xby), gc1 = t17 * (Xbx - Xax);
@@ -523,7 +565,7 @@ EOLC_HD void face_row(int v, v3 xa, v3 xb, v3 xc, double Xax, double Xay, double
     v3 Px = rsq(dot(d1, d1)) * d1;
     v3 Py = cross(nrm, Px);
     Py = rsq(dot(Py, Py)) * Py;
-    double t7 = Xax * Xby - Xax * Xcy - Xbx * Xay + Xcx * Xay + Xbx * Xcy - Xcx * Xby;
+    double t7 = rest_area2(Xax, Xay, Xbx, Xby, Xcx, Xcy);
     double t17 = 1.0 / t7;
     double gb0 = t17 * (Xcy - Xay), gb1 = t17 * (Xax - Xcx);
     double gc0 = t17 * (Xay - Xby), gc1 = t17 * (Xbx - Xax);
@@ -576,7 +618,7 @@ EOLC_HD void edge_row_emit(int i, v3 x0, v3 x1, v3 x2, v3 x3, double X0x, double
                            double X2y, double X3x, double X3y, double beta, double dhh, Emit emit) {
     double ex = X1x - X0x, ey = X1y - X0y;
     double t6 = beta * (ex * ex + ey * ey);
-    double den = 0.5 * (-X0x * X2y + X2x * X0y + X1x * X2y - X2x * X1y + X0x * X3y - X3x * X0y - X1x * X3y + X3x * X1y);
+    double den = stencil_area(X0x, X0y, X1x, X1y, X2x, X2y, X3x, X3y);
     double c = 1.5 * t6 / den;
     v3 u, v;
     double D, k0, k1, k01, kg0, kg1;

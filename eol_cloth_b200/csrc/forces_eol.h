@@ -118,7 +118,7 @@ EOLC_HD void edge_force(v3 x0, v3 x1, v3 x2, v3 x3, double X0x, double X0y, doub
                         double X3y, double beta, v3 *f) {
     const double ex = X1x - X0x, ey = X1y - X0y;
     const double t6 = beta * (ex * ex + ey * ey);
-    const double den = 0.5 * (-X0x * X2y + X2x * X0y + X1x * X2y - X2x * X1y + X0x * X3y - X3x * X0y - X1x * X3y + X3x * X1y);
+    const double den = stencil_area(X0x, X0y, X1x, X1y, X2x, X2y, X3x, X3y);
     const double c = 1.5 * t6 / den;
     const v3 e = x1 - x0, a = x2 - x0, b = x3 - x0;
     const v3 n0 = cross(e, a), n1 = cross(b, e);
