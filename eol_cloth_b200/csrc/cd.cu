@@ -25,6 +25,7 @@
 #include "cd_math.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 
@@ -66,6 +67,7 @@ struct BoxData {
     // build on this machine calls), see angle_cuts(): identical decisions by construction, and no FP64 acos on the device.
     double cosParHi, cosParLo;   // |acos c| < 2 deg  <=>  cosParHi <= c <= 1 ;  |pi - acos c| < 2 deg  <=>  -1 <= c <= cosParLo
     double cosWedge[12];         // acos c - angleCD[k] > 2 deg  <=>  -1 <= c < cosWedge[k]  (c <= 1)
+    double aabbEdge[12][6];      // AABB of box edge k (its two corners), for the conservative pair cull of section C
 };
 
 // ---- libm-exact angle decisions in cosine space ----------------------------------------------------
@@ -172,6 +174,11 @@ bool make_box(BoxData &B, const double *whd, const double *E1) {
         B.tan1[k][0] = tan1.x; B.tan1[k][1] = tan1.y; B.tan1[k][2] = tan1.z;
         B.nor1e[k][0] = nor1.x; B.nor1e[k][1] = nor1.y; B.nor1e[k][2] = nor1.z;
     }
+    for (int k = 0; k < 12; ++k)
+        for (int r = 0; r < 3; ++r) {
+            const double a = B.verts1[h_edgeVerts1[k][0]][r], b = B.verts1[h_edgeVerts1[k][1]][r];
+            B.aabbEdge[k][r] = std::min(a, b); B.aabbEdge[k][3 + r] = std::max(a, b);
+        }
     bool ok = parallel_cuts(B.cosParHi, B.cosParLo);
     for (int k = 0; k < 12; ++k) {
         // :906-915 with angleCD >= 0 (an acos; the `angleCD < 0` branch cannot be taken): reject iff angleCN - angleCD > threshAng
@@ -287,15 +294,19 @@ __device__ __forceinline__ int block_excl_prefix(int cnt) {
 
 // single-block exclusive scan of blocksum[0..n) -> blockoff[0..n], blockoff[n] = total
 __global__ void __launch_bounds__(1024) k_scan(size_t n, const int *__restrict__ in, int *__restrict__ out) {
+    // one block, 8 consecutive entries per thread and round: 8192 entries per round (a batched ensemble has ~10^5 block counts)
+    constexpr int PER = 8;
     __shared__ int s[32];
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     int l = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (size_t base = 0; base < n; base += 1024) {
-        size_t i = base + threadIdx.x;
-        int v = i < n ? in[i] : 0;
-        int inc = v;
+    for (size_t base = 0; base < n; base += 1024 * PER) {
+        const size_t i0 = base + (size_t)threadIdx.x * PER;
+        int v[PER], tot = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { v[q] = i0 + q < n ? in[i0 + q] : 0; tot += v[q]; }
+        int inc = tot;
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
         if (l == 31) s[w] = inc;
         __syncthreads();
@@ -305,9 +316,11 @@ __global__ void __launch_bounds__(1024) k_scan(size_t n, const int *__restrict__
             s[l] = t;
         }
         __syncthreads();
-        int wbase = w > 0 ? s[w - 1] : 0;
-        int c = carry;
-        if (i < n) out[i] = c + wbase + inc - v;
+        const int wbase = w > 0 ? s[w - 1] : 0;
+        const int c = carry;
+        int run = c + wbase + inc - tot;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { if (i0 + q < n) out[i0 + q] = run; run += v[q]; }
         __syncthreads();
         if (threadIdx.x == 1023) carry = c + wbase + inc;
         __syncthreads();
@@ -359,6 +372,30 @@ __device__ int test_vertex_box(int i2, int F, V3 x2, const double *__restrict__ 
     return best;
 }
 
+// The record of cloth vertex i2 against its winning box triangle j1 (what the loop above leaves in *rec for the winner): the same
+// expressions on the same inputs, so the same bits, without the other 23 triangles.
+__device__ __forceinline__ void vertex_box_record(int i2, int j1, int F, V3 x2, const double *__restrict__ fnp, const BoxData &B, eolc_contact *rec) {
+    V3 x1a = bcol(B.verts1, c_faces1[j1][0]), x1b = bcol(B.verts1, c_faces1[j1][1]), x1c = bcol(B.verts1, c_faces1[j1][2]);
+    V3 nor1 = bcol(B.faceNors1, j1);
+    double proj = dot(nor1, x2 - x1a);
+    V3 x1 = x2 - scale(proj, nor1);
+    double dist = norm(x2 - x1);
+    double u, v;
+    barycentric(u, v, x1a, x1b, x1c, x1);
+    double w = sub(sub(1.0, u), v);
+    V3 nor2 = i2 < F ? dcol(fnp, i2) : mk(0, 0, 0);
+    if (dot(nor2, nor1) < 0.0) nor2 = neg(nor2);
+    zero_contact(*rec);
+    rec->dist = dist;
+    st(rec->nor1, nor1); st(rec->nor2, nor2); st(rec->pos1, x1); st(rec->pos2, x2);
+    rec->count1 = 3; rec->count2 = 1;
+    rec->verts1[0] = c_faces1[j1][0]; rec->verts1[1] = c_faces1[j1][1]; rec->verts1[2] = c_faces1[j1][2];
+    rec->verts2[0] = i2; rec->verts2[1] = -1; rec->verts2[2] = -1;
+    rec->weights1[0] = u; rec->weights1[1] = v; rec->weights1[2] = w;
+    rec->weights2[0] = 1.0; rec->weights2[1] = 0.0; rec->weights2[2] = 0.0;
+    rec->tri1 = j1; rec->tri2 = -1;
+}
+
 // grid: (ceil(N/256), S*B)
 __global__ void __launch_bounds__(256) k_A_count(int N, int F, int nB, const double *__restrict__ xp, const double *__restrict__ fnp,
                                                  const BoxData *__restrict__ boxes, double threshold, int *__restrict__ info,
@@ -372,20 +409,41 @@ __global__ void __launch_bounds__(256) k_A_count(int N, int F, int nB, const dou
     info[item0 + blockIdx.x * 256 + threadIdx.x] = j1;
     block_count_store(j1 >= 0 ? 1 : 0, blocksum, item0 / 256 + blockIdx.x);
 }
-__global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, const double *__restrict__ xp, const double *__restrict__ fnp,
+// The hits of a block occupy consecutive output slots (prefix order), so the block's records form ONE contiguous range: they are
+// staged in shared memory and leave with coalesced 8-byte stores (a record is 33 doubles; writing it from one thread puts 32 lanes on
+// 32 different 264-byte-strided lines per store).  Persistent over the (scene, box, item block) triples; empty blocks are skipped.
+__global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, int S, const double *__restrict__ xp, const double *__restrict__ fnp,
                                                  const BoxData *__restrict__ boxes, double threshold, const int *__restrict__ info,
                                                  const int *__restrict__ blockoff, eolc_contact *__restrict__ out, size_t xstride,
                                                  size_t fstride, size_t scene_items, size_t box_items, size_t secA_off) {
-    int s = blockIdx.y / nB, b = blockIdx.y % nB;
-    size_t item0 = s * scene_items + secA_off + b * box_items;
-    int i2 = blockIdx.x * 256 + threadIdx.x;
-    int j1 = info[item0 + i2];
-    int pre = block_excl_prefix(j1 >= 0 ? 1 : 0);
-    if (j1 < 0) return;
-    eolc_contact rec;
-    test_vertex_box(i2, F, dcol(xp + s * xstride, i2), fnp + s * fstride, boxes[b], threshold, &rec);
-    finish_contact(rec, threshold);
-    out[blockoff[item0 / 256 + blockIdx.x] + pre] = rec;
+    extern __shared__ __align__(16) unsigned char stage_raw[];
+    eolc_contact *stage = reinterpret_cast<eolc_contact *>(stage_raw);
+    static_assert(sizeof(eolc_contact) % 8 == 0, "records are copied as 8-byte words");
+    const int nbx = (N + 255) / 256;
+    const long long nvb = (long long)nbx * nB * S;
+    for (long long vb = blockIdx.x; vb < nvb; vb += gridDim.x) {
+        const int bx = (int)(vb % nbx);
+        const int sb = (int)(vb / nbx), s = sb / nB, b = sb % nB;
+        const size_t item0 = s * scene_items + secA_off + b * box_items;
+        const size_t blk = item0 / 256 + bx;
+        const int base = blockoff[blk], cnt = blockoff[blk + 1] - base;
+        if (cnt == 0) continue;                       // block-uniform
+        const int i2 = bx * 256 + threadIdx.x;
+        const int j1 = info[item0 + i2];
+        const int pre = block_excl_prefix(j1 >= 0 ? 1 : 0);
+        if (j1 >= 0) {
+            eolc_contact rec;
+            vertex_box_record(i2, j1, F, dcol(xp + s * xstride, i2), fnp + s * fstride, boxes[b], &rec);
+            finish_contact(rec, threshold);
+            stage[pre] = rec;
+        }
+        __syncthreads();
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(stage);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(out + base);
+        const int nw = cnt * (int)(sizeof(eolc_contact) / 8);
+        for (int w = threadIdx.x; w < nw; w += 256) dst[w] = src[w];
+        __syncthreads();                              // the stage and the prefix scratch are reused by the next round
+    }
 }
 
 // ---- sections Bc / PT: point (box corner or obstacle point) vs all cloth triangles -------------------
@@ -555,10 +613,41 @@ __global__ void __launch_bounds__(256) k_PE_write(int N, int P, const double *__
 // ---- section C: cloth edge vs box edge (boxTriCollision.cpp:849-1017) ----------------------------------
 struct EdgeRec { int32_t v[4]; int32_t f[2]; };
 
-__device__ bool test_edge_edge(int k1, const BoxData &B, V3 x2a, V3 x2b, V3 dx2, double len2, V3 nor2, const double *aabbE2k,
+// The rejections of one (cloth edge, box edge) pair that need nothing but the two AABBs: the reference's soft-edge and face-AABB
+// tests (:858-871), then a conservative cull that is not in the reference and cannot change a result: a record needs u1 within
+// thr/len1 of [0, 1] and u2 within thr/len2 of [0, 1] (:933, :981), i.e. x1 within thr of the box edge's AABB and x2 within thr of
+// the cloth edge's, and |x2 - x1| <= 2 thr (:988-999): the two AABBs are then at most 4 thr apart in every coordinate.  Pairs
+// further apart than 6 thr are rejected before any arithmetic.
+struct CullBox {            // what pair_culled reads of one box, staged in shared memory by the block
+    double edgeAngle[12];
+    double aabbFc[12][6], aabbFd[12][6];   // AABBs of the two box triangles next to box edge k (aabbF1[edgeFaces1[k][0 / 1]])
+    double aabbEdge[12][6];
+};
+__device__ __forceinline__ void stage_cull_box(CullBox &C, const BoxData &B) {
+    for (int i = threadIdx.x; i < 12 * 6; i += blockDim.x) {
+        const int k = i / 6, r = i % 6;
+        C.aabbFc[k][r] = B.aabbF1[c_edgeFaces1[k][0]][r];
+        C.aabbFd[k][r] = B.aabbF1[c_edgeFaces1[k][1]][r];
+        C.aabbEdge[k][r] = B.aabbEdge[k][r];
+        if (r == 0) C.edgeAngle[k] = B.edgeAngle[k];
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ bool pair_culled(int k1, const CullBox &C, const double *aabbE2k, double threshold) {
+    // the conservative test first: it removes nearly every pair with six subtractions; the reference's own (exact) tests then run
+    // on the few survivors — the order of rejections does not matter, a pair is dropped if any of them fires
+    const double m = 6.0 * threshold;
+    const double *a = C.aabbEdge[k1];
+    if (a[0] - aabbE2k[3] > m || aabbE2k[0] - a[3] > m || a[1] - aabbE2k[4] > m || aabbE2k[1] - a[4] > m || a[2] - aabbE2k[5] > m ||
+        aabbE2k[2] - a[5] > m)
+        return true;
+    if (C.edgeAngle[k1] < M_PI / 6.0) return true;   // soft edge
+    return !check_aabb(C.aabbFc[k1], aabbE2k) && !check_aabb(C.aabbFd[k1], aabbE2k);
+}
+
+// the rest of :873-1017 for a pair that survived pair_culled(); out of line: the survivors are few and the callers stay light
+__device__ __noinline__ bool test_edge_edge(int k1, const BoxData &B, V3 x2a, V3 x2b, V3 dx2, double len2, V3 nor2,
                                double threshold, eolc_contact *rec, const EdgeRec &e2, int k2) {
-    if (B.edgeAngle[k1] < M_PI / 6.0) return false;   // soft edge
-    if (!check_aabb(B.aabbF1[c_edgeFaces1[k1][0]], aabbE2k) && !check_aabb(B.aabbF1[c_edgeFaces1[k1][1]], aabbE2k)) return false;
     V3 x1a = bcol(B.verts1, c_edgeVerts1[k1][0]), x1b = bcol(B.verts1, c_edgeVerts1[k1][1]);
     V3 dx1 = bcol(B.dx1, k1);
     double len1 = B.len1[k1];
@@ -576,15 +665,17 @@ __device__ bool test_edge_edge(int k1, const BoxData &B, V3 x2a, V3 x2b, V3 dx2,
     if (dot(nor, nor1) < 0.0) nor = neg(nor);
     c = dot(n1c, nor);   // :906-915: angleCN - angleCD > 2 deg (angleCN < -2 deg cannot happen: an acos)
     if (c >= -1.0 && c <= 1.0 && c < B.cosWedge[k1]) return false;
+    // the reference intersects first (:920-924) and then rejects on the line-line parameters (:927-936); both are pure functions of
+    // the same inputs, so the cheap rejection runs first and the eight ray / triangle tests only for its survivors
+    double u1, u2;
+    lineline(u1, u2, x1a, x1b, x2a, x2b);
+    double thresh1 = dv(mul(1.0, threshold), len1), thresh2 = dv(mul(1.0, threshold), len2);
+    if (u1 < -thresh1 || u1 > add(1.0, thresh1) || u2 < -thresh2 || u2 > add(1.0, thresh2)) return false;
     double u2c, u2d;
     int i2c = intersect_square(x2a, dx2, x1a, x1b, x1c, u2c);
     int i2d = intersect_square(x2a, dx2, x1b, x1a, x1d, u2d);
     i2c = i2c && (0.0 <= u2c && u2c <= 1.0);
     i2d = i2d && (0.0 <= u2d && u2d <= 1.0);
-    double u1, u2;
-    lineline(u1, u2, x1a, x1b, x2a, x2b);
-    double thresh1 = dv(mul(1.0, threshold), len1), thresh2 = dv(mul(1.0, threshold), len2);
-    if (u1 < -thresh1 || u1 > add(1.0, thresh1) || u2 < -thresh2 || u2 > add(1.0, thresh2)) return false;
     V3 x1, x2;
     if (i2c && i2d) {
         x1 = scale(sub(1.0, u1), x1a) + scale(u1, x1b);
@@ -624,63 +715,141 @@ __device__ bool test_edge_edge(int k1, const BoxData &B, V3 x2a, V3 x2b, V3 dx2,
     return true;
 }
 
-// shared per-edge setup (:851-856, build_AABB_E :455-468)
-__device__ __forceinline__ void edge_setup(const EdgeRec &e2, const double *__restrict__ xp, const double *__restrict__ fn0,
-                                           V3 &x2a, V3 &x2b, V3 &dx2, double &len2, V3 &nor2, double *aabbE) {
+// per-edge setup: the end points and the AABB (build_AABB_E :455-468) for the culls; length and edge normal (:851-856) only for
+// edges with a surviving pair
+__device__ __forceinline__ void edge_ends(const EdgeRec &e2, const double *__restrict__ xp, V3 &x2a, V3 &x2b, double *aabbE) {
     x2a = dcol(xp, e2.v[0]); x2b = dcol(xp, e2.v[1]);
+    aabbE[0] = fmin(x2b.x, x2a.x); aabbE[1] = fmin(x2b.y, x2a.y); aabbE[2] = fmin(x2b.z, x2a.z);
+    aabbE[3] = fmax(x2b.x, x2a.x); aabbE[4] = fmax(x2b.y, x2a.y); aabbE[5] = fmax(x2b.z, x2a.z);
+}
+__device__ __forceinline__ void edge_frame(const EdgeRec &e2, const double *__restrict__ fn0, V3 x2a, V3 x2b, V3 &dx2, double &len2, V3 &nor2) {
     dx2 = x2b - x2a;
     len2 = norm(dx2);
     V3 n0 = dcol(fn0, e2.f[0]);
     V3 n1 = e2.f[1] >= 0 ? dcol(fn0, e2.f[1]) : mk(0, 0, 0);   // boundary: normals[1] stays zero (:94-95)
     nor2 = normalized(n0 + n1);
-    aabbE[0] = fmin(x2b.x, x2a.x); aabbE[1] = fmin(x2b.y, x2a.y); aabbE[2] = fmin(x2b.z, x2a.z);
-    aabbE[3] = fmax(x2b.x, x2a.x); aabbE[4] = fmax(x2b.y, x2a.y); aabbE[5] = fmax(x2b.z, x2a.z);
 }
 
-__global__ void __launch_bounds__(256) k_C_count(int E, int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
-                                                 const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
-                                                 int *__restrict__ info, int *__restrict__ blocksum, size_t xstride, size_t fstride,
-                                                 size_t scene_items, size_t box_items, size_t secC_off) {
-    int s = blockIdx.y / nB, b = blockIdx.y % nB;
-    int k2 = blockIdx.x * 256 + threadIdx.x;
-    int mask = 0;
+// Pass 1 of section C, in three light / dense kernels instead of one divergent one:
+//   k_C_cull   one thread per cloth edge: the AABB rejections of its 12 pairs; survivors are appended to a work list
+//   k_C_test   one thread per surviving pair (all lanes busy): the rest of :873-1017; a hit sets its bit in the edge's mask
+//   k_C_sum    hits per 256-item block, for the scan
+// The work list's order does not matter (integer atomics): a pair's outcome lands in its own bit.  If the list overflows, the
+// pairs that did not fit are tested in place by k_C_cull.
+__global__ void __launch_bounds__(256) k_C_cull(int E, int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
+                                                const BoxData *__restrict__ boxes, double threshold,
+                                                int *__restrict__ info, unsigned long long *__restrict__ cand_list, int *__restrict__ counter,
+                                                int capacity, size_t xstride, size_t scene_items, size_t box_items, size_t secC_off) {
+    __shared__ CullBox C;
+    const int s = blockIdx.y / nB, b = blockIdx.y % nB;
+    const int k2 = blockIdx.x * 256 + threadIdx.x;
+    const BoxData &B = boxes[b];
+    stage_cull_box(C, B);
+    const size_t item = s * scene_items + secC_off + b * box_items + k2;
+    int cand = 0;
+    const int mask = 0;
     if (k2 < E) {
-        EdgeRec e2 = edges[k2];
-        V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
-        edge_setup(e2, xp + s * xstride, fn0 + s * fstride, x2a, x2b, dx2, len2, nor2, aabbE);
-        const BoxData &B = boxes[b];
+        const EdgeRec e2 = edges[k2];
+        V3 x2a, x2b;
+        double aabbE[6];
+        edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
         // whole-box cull first: an edge outside the padded box AABB fails all 24 face-AABB tests
-        if (check_aabb(B.aabbB1, aabbE))
+        if (check_aabb(B.aabbB1, aabbE)) {
+#pragma unroll
             for (int k1 = 0; k1 < 12; ++k1)
-                if (test_edge_edge(k1, B, x2a, x2b, dx2, len2, nor2, aabbE, threshold, nullptr, e2, k2)) mask |= 1 << k1;
+                if (!pair_culled(k1, C, aabbE, threshold)) cand |= 1 << k1;
+        }
     }
-    size_t item0 = s * scene_items + secC_off + b * box_items;
-    info[item0 + k2] = mask;
-    block_count_store(__popc(mask), blocksum, item0 / 256 + blockIdx.x);
+    if (cand) {
+        const int n = __popc(cand);
+        const int at = atomicAdd(counter, n);       // keeps counting past the capacity: the host then grows the list and repeats the pass
+        int q = 0;
+        for (int k1 = 0; k1 < 12; ++k1)
+            if ((cand >> k1) & 1) {
+                if (at + q < capacity) cand_list[at + q] = (unsigned long long)item | ((unsigned long long)k1 << 60);
+                ++q;
+            }
+    }
+    info[item] = mask;
 }
-__global__ void __launch_bounds__(256) k_C_write(int E, int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
-                                                 const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
-                                                 const int *__restrict__ info, const int *__restrict__ blockoff,
-                                                 eolc_contact *__restrict__ out, size_t xstride, size_t fstride, size_t scene_items,
-                                                 size_t box_items, size_t secC_off, int remap, int nP) {
-    int s = blockIdx.y / nB, b = blockIdx.y % nB;
-    size_t item0 = s * scene_items + secC_off + b * box_items;
-    int k2 = blockIdx.x * 256 + threadIdx.x;
-    int mask = info[item0 + k2];
-    int pre = block_excl_prefix(__popc(mask));
+__global__ void __launch_bounds__(256) k_C_test(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
+                                                const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
+                                                int *__restrict__ info, const unsigned long long *__restrict__ cand_list,
+                                                const int *__restrict__ counter, int capacity, size_t xstride, size_t fstride,
+                                                size_t scene_items, size_t box_items, size_t secC_off) {
+    const int n = min(*counter, capacity);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const unsigned long long c = cand_list[i];
+        const size_t item = (size_t)(c & ((1ull << 60) - 1));
+        const int k1 = (int)(c >> 60);
+        const size_t s = item / scene_items, rem = item - s * scene_items - secC_off;
+        const int b = (int)(rem / box_items), k2 = (int)(rem - (size_t)b * box_items);
+        const EdgeRec e2 = edges[k2];
+        V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
+        edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
+        edge_frame(e2, fn0 + s * fstride, x2a, x2b, dx2, len2, nor2);
+        if (test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, threshold, nullptr, e2, k2)) atomicOr(info + item, 1 << k1);
+    }
+}
+// one warp per 256-item block of section C
+__global__ void __launch_bounds__(256) k_C_sum(int nbx, long long nblk, const int *__restrict__ info, int *__restrict__ blocksum,
+                                               size_t scene_items, size_t box_items, size_t secC_off, int nB) {
+    const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= nblk) return;
+    const int bx = (int)(w % nbx);
+    const long long sb = w / nbx;
+    const size_t item0 = (size_t)(sb / nB) * scene_items + secC_off + (size_t)(sb % nB) * box_items;
+    const int *p = info + item0 + (size_t)bx * 256;
+    int t = 0;
+    for (int q = threadIdx.x & 31; q < 256; q += 32) t += __popc(p[q]);
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) blocksum[item0 / 256 + bx] = t;
+}
+
+// Pass 2 of section C.  Hits are few (a band of cloth edges along the box edges) and scattered over the item blocks; re-deriving a
+// record is ~2 k FP64 instructions.  k_C_expand (light, full occupancy) turns every hit bit into a work item carrying its final
+// output slot; k_C_write then runs one thread per hit, all lanes busy.  The order of the work list is irrelevant (appended with an
+// integer atomic): every item writes its own, predetermined slot, so the output is the same bits every run.
+struct CHit { int32_t k2; int32_t sb_k1; int32_t slot; int32_t pad; };   // sb_k1 = (scene * nB + box) | k1 << 16
+__global__ void __launch_bounds__(256) k_C_expand(int E, int nB, const int *__restrict__ info, const int *__restrict__ blockoff,
+                                                  CHit *__restrict__ work, int *__restrict__ counter, int capacity, size_t scene_items,
+                                                  size_t box_items, size_t secC_off) {
+    const int s = blockIdx.y / nB, b = blockIdx.y % nB;
+    const size_t item0 = s * scene_items + secC_off + b * box_items;
+    const size_t blk = item0 / 256 + blockIdx.x;
+    const int base = blockoff[blk];
+    if (blockoff[blk + 1] == base) return;            // block-uniform
+    const int k2 = blockIdx.x * 256 + threadIdx.x;
+    const int mask = info[item0 + k2];
+    const int pre = block_excl_prefix(__popc(mask));
     if (!mask) return;
-    EdgeRec e2 = edges[k2];
-    V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
-    edge_setup(e2, xp + s * xstride, fn0 + s * fstride, x2a, x2b, dx2, len2, nor2, aabbE);
-    eolc_contact *dst = out + blockoff[item0 / 256 + blockIdx.x] + pre;
+    const int n = __popc(mask);
+    const int at = atomicAdd(counter, n);
+    int q = 0;
     for (int k1 = 0; k1 < 12; ++k1)
         if (mask & (1 << k1)) {
-            eolc_contact rec;
-            test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, aabbE, threshold, &rec, e2, k2);
-            finish_contact(rec, threshold);
-            if (remap) remap_contact(rec, nP + b * 8 + b * 12);
-            *dst++ = rec;
+            if (at + q < capacity) work[at + q] = CHit{k2, (int)blockIdx.y | (k1 << 16), base + pre + q, 0};
+            ++q;
         }
+}
+__global__ void __launch_bounds__(256) k_C_write(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
+                                                 const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
+                                                 const CHit *__restrict__ work, const int *__restrict__ counter, int capacity,
+                                                 eolc_contact *__restrict__ out, size_t xstride, size_t fstride, int remap, int nP) {
+    const int n = min(*counter, capacity);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const CHit h = work[i];
+        const int sb = h.sb_k1 & 0xffff, k1 = h.sb_k1 >> 16, s = sb / nB, b = sb % nB;
+        const EdgeRec e2 = edges[h.k2];
+        V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
+        edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
+        edge_frame(e2, fn0 + s * fstride, x2a, x2b, dx2, len2, nor2);
+        eolc_contact rec;
+        test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, threshold, &rec, e2, h.k2);
+        finish_contact(rec, threshold);
+        if (remap) remap_contact(rec, nP + b * 8 + b * 12);
+        out[h.slot] = rec;
+    }
 }
 
 inline size_t pad256(size_t n) { return (n + 255) / 256 * 256; }
@@ -703,11 +872,15 @@ struct eolc_cd_plan {
     DevBuf<Cand> d_partial;
     DevBuf<eolc_contact> d_out;
     PinnedBuf<eolc_contact> p_out;
-    PinnedBuf<int> p_blockoff;
+    PinnedBuf<int> p_blockoff, p_counter;
     PinnedBuf<double> p_x;
     int64_t last_pair_tests = 0;
     int32_t last_launches = 0;
     int32_t last_total = 0;             // contacts of the last run, still in d_out
+    bool smem_attr_set = false;
+    DevBuf<CHit> d_chits;               // work list of section C's write pass
+    DevBuf<int> d_counter;              // [0]: pairs in d_cands, [1]: hits in d_chits
+    DevBuf<unsigned long long> d_cands; // work list of section C's test pass: item | k1 << 60
     DevBuf<int32_t> d_rows_i;           // contact rows (eolc_cd_contact_rows): row_nnz [n] + cols [9 n]
     DevBuf<double> d_rows_v;            // vals [9 n]
     DevBuf<unsigned char> d_eol;
@@ -888,13 +1061,31 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
         k_A_count<<<dim3((unsigned)(nA / 256), S * nB), 256, 0, st>>>(N, F, nB, P->d_xp.p, P->d_fnp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, xs, fs, scene_items, box_items, secBox);
         k_PT_partial<<<dim3(nchunk, S * nB * 8), 256, 0, st>>>(F, nB * 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, P->d_fnp.p, P->d_aabb.p, thr, P->d_partial.p, xs, fs);
         k_PT_final<<<S * nB, 256, 0, st>>>(nchunk, 8, nB, P->d_partial.p, P->d_info.p, P->d_blocksum.p, scene_items, secBox + nA, box_items);
-        k_C_count<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, xs, fs, scene_items, box_items, secBox + nA + nBc);
-        launches += 4;
+        launches += 3;
     }
-    k_scan<<<1, 1024, 0, st>>>(nblocks, P->d_blocksum.p, P->d_blockoff.p); ++launches;
     EOLC_CUDA(P->p_blockoff.ensure(nblocks + 1));
-    EOLC_CUDA(cudaMemcpyAsync(P->p_blockoff.p, P->d_blockoff.p, sizeof(int) * (nblocks + 1), cudaMemcpyDeviceToHost, st));
-    EOLC_CUDA(cudaStreamSynchronize(st));
+    EOLC_CUDA(P->d_counter.ensure(2)); EOLC_CUDA(P->p_counter.ensure(2));
+    const long long nblkC = (long long)(nC / 256) * S * nB;
+    long long cap = std::min<long long>(std::max<long long>((long long)P->d_cands.n, nblkC * 128 + 65536), (long long)1 << 30);   // half a pair per edge, and then some
+    if (const char *ev = getenv("EOLC_CD_PAIR_CAP")) cap = std::max<long long>(1, atoll(ev));   // test knob: forces the overflow path
+    for (int attempt = 0;; ++attempt) {
+        if (nB) {
+            EOLC_CUDA(P->d_cands.ensure((size_t)cap));
+            EOLC_CUDA(cudaMemsetAsync(P->d_counter.p, 0, 2 * sizeof(int), st));
+            k_C_cull<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_edges.p, P->d_xp.p, P->d_boxes.p, thr, P->d_info.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
+            const int gridT = (int)std::max<long long>(1, std::min<long long>(nblkC, (long long)P->ctx->sm_count * 2));
+            k_C_test<<<gridT, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_info.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, fs, scene_items, box_items, secBox + nA + nBc);
+            k_C_sum<<<(unsigned)((nblkC + 7) / 8), 256, 0, st>>>((int)(nC / 256), nblkC, P->d_info.p, P->d_blocksum.p, scene_items, box_items, secBox + nA + nBc, nB);
+            launches += 3;
+        }
+        k_scan<<<1, 1024, 0, st>>>(nblocks, P->d_blocksum.p, P->d_blockoff.p); ++launches;
+        EOLC_CUDA(cudaMemcpyAsync(P->p_blockoff.p, P->d_blockoff.p, sizeof(int) * (nblocks + 1), cudaMemcpyDeviceToHost, st));
+        EOLC_CUDA(cudaMemcpyAsync(P->p_counter.p, P->d_counter.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        EOLC_CUDA(cudaStreamSynchronize(st));
+        if (!nB || P->p_counter.p[0] <= cap) break;
+        if (attempt >= 1) { set_error("internal: the pair list of section C overflowed twice"); return EOLC_ERR_UNSUPPORTED; }
+        cap = P->p_counter.p[0];        // the pass counted every surviving pair: this is the exact size
+    }
     const int total = P->p_blockoff.p[nblocks];
 
     // ---- capacity check before anything is written to the caller
@@ -911,9 +1102,25 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
         if (doPE) { k_PE_write<<<dim3((unsigned)(nPE / 256), S), 256, 0, st>>>(N, nP, P->d_pxyz.p, P->d_pnorms.p, P->d_xp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, scene_items, secPE); ++launches; }
         if (nP) { k_PT_write<<<dim3((unsigned)(nPT / 256), S), 256, 0, st>>>(F, nP, 1, nullptr, P->d_pxyz.p, P->d_pnorms.p, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secPT, 0, 0, nP); ++launches; }
         if (nB) {
-            k_A_write<<<dim3((unsigned)(nA / 256), S * nB), 256, 0, st>>>(N, F, nB, P->d_xp.p, P->d_fnp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox);
+            {
+                const long long nvb = (long long)(nA / 256) * S * nB;
+                const int gridA = (int)std::min<long long>(nvb, (long long)P->ctx->sm_count * 3);
+                const size_t smemA = 256 * sizeof(eolc_contact);
+                if (!P->smem_attr_set) {
+                    EOLC_CUDA(cudaFuncSetAttribute(k_A_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+                    P->smem_attr_set = true;
+                }
+                k_A_write<<<gridA, 256, smemA, st>>>(N, F, nB, S, P->d_xp.p, P->d_fnp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox);
+            }
             k_PT_write<<<dim3(1, S * nB), 256, 0, st>>>(F, 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secBox + nA, box_items, remap_box_indices, nP);
-            k_C_write<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox + nA + nBc, remap_box_indices, nP);
+            {
+                // every record has its slot: the work list of section C can hold at most `total` items
+                EOLC_CUDA(P->d_chits.ensure((size_t)total + 1));
+                k_C_expand<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_info.p, P->d_blockoff.p, P->d_chits.p, P->d_counter.p + 1, total, scene_items, box_items, secBox + nA + nBc);
+                const int gridC = std::max(1, std::min((total + 255) / 256, P->ctx->sm_count * 2));
+                k_C_write<<<gridC, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_chits.p, P->d_counter.p + 1, total, P->d_out.p, xs, fs, remap_box_indices, nP);
+                ++launches;
+            }
             launches += 3;
         }
         if (!resident) {

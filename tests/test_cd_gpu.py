@@ -163,3 +163,20 @@ def test_ensemble_4096_scenes_sampled_against_reference(ctx, oracle):
                 assert got.tobytes() == own.tobytes(), f"scene {s}: not bit-identical to the reference's own code"
                 assert got.tobytes() == oracle.cd(fn, xs[s - s0], THR, None, None, obs.box_whd, obs.box_E, 0, 0).tobytes()
     assert total > 1000 * S
+
+
+def test_pair_list_overflow_repeats_the_pass(ctx, oracle, monkeypatch):
+    """Section C's pair work list is sized by a heuristic; when it overflows the device has counted the pairs and the host repeats
+    the pass with the exact size.  Forced here with a 3-entry list: same contacts, bit for bit."""
+    X, fn = E.meshgen.regular2(40)
+    c = np.array([0.9175, -0.25, -0.549])
+    x = E.meshgen.box_scene_state(X, seed=2, centre=c)
+    obs = make_obstacles(THR, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(c)[None])
+    ref = oracle.cd(fn, x, THR, None, None, obs.box_whd, obs.box_E, 0, 0)
+    assert int((ref["count1"] == 2).sum()) > 3
+    monkeypatch.setenv("EOLC_CD_PAIR_CAP", "3")
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, THR)
+    got = plan.run(x, obs, 0, 0)
+    assert got.tobytes() == ref.tobytes()
+    monkeypatch.delenv("EOLC_CD_PAIR_CAP")
+    assert plan.run(x, obs, 0, 0).tobytes() == ref.tobytes()
