@@ -88,6 +88,7 @@ def lib():
 
 
 FILL_M_UNCHANGED = 1   # EOLC_FILL_M_UNCHANGED
+FILL_EXACT_SYMMETRY = 2   # EOLC_FILL_EXACT_SYMMETRY
 
 
 class HostBuffer:

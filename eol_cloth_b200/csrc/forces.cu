@@ -52,7 +52,11 @@ struct eolc_forces_plan {
     DevBuf<uint32_t> d_eol_sources;
     DevBuf<double> d_eol_scratch;                 // eol_scratch doubles per scene
     bool smem_attr_set = false;
-    bool host_M_valid = false;                    // eolc_forces_fill has produced M on this plan (EOLC_FILL_M_UNCHANGED may skip it)
+    bool host_M_valid = false;
+    // exact symmetry of MDK (EOLC_FILL_EXACT_SYMMETRY): the pairs (a, b), a < b, whose two nodes are owned by different tiles
+    std::vector<int32_t> h_tile_of;               // owner tile per node ("tiles" pipeline)
+    DevBuf<uint4> d_sym_pairs;                    // per pair: offset of block (a,b), offset of block (b,a), row strides (a | b << 16), 0
+    int64_t n_sym_pairs = -1;                     // -1: not built yet                    // eolc_forces_fill has produced M on this plan (EOLC_FILL_M_UNCHANGED may skip it)
     // "tiles" pipeline
     int32_t n_tiles = 0, n_templates = 0;
     bool service_p3 = false;
@@ -417,6 +421,11 @@ int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st,
         if (ev) P->service_p3 = atoi(ev) != 0;
     }
     P->geo_bytes = (int64_t)tp.geo.size() * 4; P->tmpl_bytes = (int64_t)tp.tmpl.size() * 4;
+    P->h_tile_of.assign((size_t)P->N, -1);
+    for (int32_t t = 0; t < tp.n_tiles; ++t) {
+        const uint32_t *g = tp.geo.data() + (size_t)t * 4 * tp.max_geo16;
+        for (uint32_t l = 0, n_own = g[1] & 255u; l < n_own; ++l) P->h_tile_of[g[4 + l]] = t;
+    }
     if (tiles_smem_bytes(P) > (size_t)227 * 1024) { set_error("tile plan needs %zu bytes of shared memory", tiles_smem_bytes(P)); return EOLC_ERR_UNSUPPORTED; }
     static_assert(sizeof(uint4) == 16, "uint4");
     EOLC_CUDA(P->d_geo.alloc(tp.geo.size() / 4));
@@ -885,6 +894,66 @@ int launch_eol(eolc_forces_plan *P, int32_t S, const double *x, const double *X,
     return EOLC_OK;
 }
 
+// ---- exact symmetry of MDK ------------------------------------------------------------------------------------------------------
+// The reference pushes every off-diagonal element block twice, (i, j) and mirrored (j, i) (fillxxMI / fillxxB, Forces.cpp:114-125,
+// :531-539), so its MDK is symmetric bit for bit.  Here a pair of nodes owned by ONE tile is summed once and mirrored (exact), but the
+// two blocks of a pair that straddles two tiles are summed by two CTAs in two orders and agree to rounding only.  This pass copies
+// the block of the lower node onto the transposed block of the higher one for those pairs (~30 % of the pairs, 0.1 ms at 1024^2).
+__global__ void __launch_bounds__(256) symmetrize_kernel(long long n_pairs, const uint4 *__restrict__ pairs, double *__restrict__ Kv, size_t K_stride) {
+    double *K = Kv + (size_t)blockIdx.y * K_stride;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * 256) {
+        const uint4 p = pairs[i];
+        const double *src = K + p.x;
+        double *dst = K + p.y;
+        const uint32_t ss = p.z & 0xffffu, ds = p.z >> 16;
+        double b[9];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) b[3 * j + k] = src[j * ss + k];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dst[j * ds + k] = b[3 * k + j];
+    }
+}
+
+static int ensure_sym_pairs(eolc_forces_plan *P) {
+    if (P->n_sym_pairs >= 0) return EOLC_OK;
+    if (P->n_eol) { set_error("EOLC_FILL_EXACT_SYMMETRY is implemented for Lagrangian plans (no EoL nodes)"); return EOLC_ERR_UNSUPPORTED; }
+    if (9 * P->pat.nblkK >= ((int64_t)1 << 32)) { set_error("EOLC_FILL_EXACT_SYMMETRY: matrix too large for 32-bit block offsets"); return EOLC_ERR_UNSUPPORTED; }
+    const Pattern &pat = P->pat;
+    std::vector<uint4> pairs;
+    for (int32_t a = 0; a < P->N; ++a) {
+        const int64_t a0 = pat.blkptrK[a], a1 = pat.blkptrK[a + 1];
+        const uint32_t dega = (uint32_t)(a1 - a0);
+        for (int64_t q = a0; q < a1; ++q) {
+            const int32_t b = pat.nbrK[q];
+            if (b <= a) continue;
+            // "rows" pipeline: every row is summed on its own; "tiles": only pairs across two tiles differ
+            if (P->pipeline == 0 && P->h_tile_of[a] == P->h_tile_of[b]) continue;
+            const uint32_t degb = (uint32_t)(pat.blkptrK[b + 1] - pat.blkptrK[b]);
+            const int64_t qb = find_block(pat.blkptrK, pat.nbrK, b, a);
+            pairs.push_back(make_uint4((uint32_t)(9 * a0 + 3 * (q - a0)), (uint32_t)(9 * pat.blkptrK[b] + 3 * (qb - pat.blkptrK[b])),
+                                       (3u * dega) | ((3u * degb) << 16), 0u));
+        }
+    }
+    EOLC_CUDA(P->d_sym_pairs.upload(pairs, P->ctx->stream));
+    EOLC_CUDA(cudaStreamSynchronize(P->ctx->stream));
+    P->n_sym_pairs = (int64_t)pairs.size();
+    return EOLC_OK;
+}
+
+static int launch_symmetrize(eolc_forces_plan *P, int32_t S, double *Kv) {
+    int rc = ensure_sym_pairs(P);
+    if (rc) return rc;
+    if (P->n_sym_pairs == 0) return EOLC_OK;
+    const int grid = (int)std::min<int64_t>((P->n_sym_pairs + 255) / 256, (int64_t)P->ctx->sm_count * 8);
+    symmetrize_kernel<<<dim3(grid, S), 256, 0, P->ctx->stream>>>(P->n_sym_pairs, P->d_sym_pairs.p, Kv, (size_t)P->nnzK);
+    EOLC_CUDA(cudaGetLastError());
+    return EOLC_OK;
+}
+
 int launch_fill(eolc_forces_plan *P, int32_t S, const double *x, const double *X, const eolc_material *mat,
                 const double *grav, double h, double *f, double *Mv, double *Kv, bool skip_m = false) {
     cudaStream_t st = P->ctx->stream;
@@ -1210,11 +1279,13 @@ int eolc_forces_fill_batched_dev_ex(eolc_forces_plan *plan, int32_t n_scenes, co
                                     double *M_vals_dev, double *MDK_vals_dev, uint32_t flags) {
     EOLC_REQUIRE(plan && mat && grav, "NULL argument");
     EOLC_REQUIRE(n_scenes >= 1, "n_scenes must be >= 1");
-    EOLC_REQUIRE((flags & ~EOLC_FILL_M_UNCHANGED) == 0, "unknown flag");
+    EOLC_REQUIRE((flags & ~(EOLC_FILL_M_UNCHANGED | EOLC_FILL_EXACT_SYMMETRY)) == 0, "unknown flag");
     EOLC_REQUIRE(plan->N == 0 || (x_dev && X_dev && f_dev), "NULL device pointer");
     EOLC_REQUIRE(plan->nnzM == 0 || (M_vals_dev && MDK_vals_dev), "NULL device pointer");
     EOLC_CUDA(cudaSetDevice(plan->ctx->device));
-    return launch_fill(plan, n_scenes, x_dev, X_dev, mat, grav, h, f_dev, M_vals_dev, MDK_vals_dev, honours_m_unchanged(plan, flags));
+    int rc = launch_fill(plan, n_scenes, x_dev, X_dev, mat, grav, h, f_dev, M_vals_dev, MDK_vals_dev, honours_m_unchanged(plan, flags));
+    if (rc == EOLC_OK && (flags & EOLC_FILL_EXACT_SYMMETRY) && plan->N) rc = launch_symmetrize(plan, n_scenes, MDK_vals_dev);
+    return rc;
 }
 
 int eolc_forces_fill_batched_dev(eolc_forces_plan *plan, int32_t n_scenes, const double *x_dev, const double *X_dev,
@@ -1236,7 +1307,7 @@ int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, c
 int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
                         const double grav[3], double h, double *f, double *M_vals, double *MDK_vals, uint32_t flags) {
     EOLC_REQUIRE(plan && mat && grav, "NULL argument");
-    EOLC_REQUIRE((flags & ~EOLC_FILL_M_UNCHANGED) == 0, "unknown flag");
+    EOLC_REQUIRE((flags & ~(EOLC_FILL_M_UNCHANGED | EOLC_FILL_EXACT_SYMMETRY)) == 0, "unknown flag");
     eolc_forces_plan *P = plan;
     // M unchanged: valid only if this plan's device copy of M was produced by an earlier full fill
     const bool skip_m = honours_m_unchanged(P, flags) && P->host_M_valid;
@@ -1267,6 +1338,9 @@ int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X
     EOLC_CUDA(cudaMemcpyAsync(P->d_X.p, hX, 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
     int rc = launch_fill(P, 1, P->d_x.p, P->d_X.p, mat, grav, h, P->d_f.p, P->d_Mv.p, P->d_Kv.p, skip_m);
     if (rc) return rc;
+    // the host entry always hands out an exactly symmetric MDK, like the reference's (0.1 ms next to the copies); plans with EoL nodes
+    // keep their rounding-level asymmetry across tiles
+    if (P->n_eol == 0) { rc = launch_symmetrize(P, 1, P->d_Kv.p); if (rc) return rc; }
     double *hf = f, *hM = M_vals, *hK = MDK_vals;
     if (!out_pinned) {
         EOLC_CUDA(P->p_out.ensure(nf + P->nnzM + P->nnzK));

@@ -92,13 +92,15 @@ class ForcesPlan:
                                                   float(h), capi.dptr(f), capi.dptr(Mv), capi.dptr(Kv),
                                                   capi.FILL_M_UNCHANGED if m_unchanged else 0))
 
-    def fill_dev(self, x_ptr, X_ptr, mat, grav, h, f_ptr, Mv_ptr, Kv_ptr, n_scenes=1, m_unchanged=False):
-        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on ctx.stream."""
+    def fill_dev(self, x_ptr, X_ptr, mat, grav, h, f_ptr, Mv_ptr, Kv_ptr, n_scenes=1, m_unchanged=False, exact_symmetry=False):
+        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on ctx.stream.
+        exact_symmetry: EOLC_FILL_EXACT_SYMMETRY — MDK symmetric bit for bit, as the host entries always deliver it."""
         g = capi.f64(grav)
         m = _matc(mat)
         capi.check(capi.lib().eolc_forces_fill_batched_dev_ex(self._h, int(n_scenes), x_ptr, X_ptr, ctypes.byref(m),
                                                               capi.dptr(g), float(h), f_ptr, Mv_ptr, Kv_ptr,
-                                                              capi.FILL_M_UNCHANGED if m_unchanged else 0))
+                                                              (capi.FILL_M_UNCHANGED if m_unchanged else 0) |
+                                                              (capi.FILL_EXACT_SYMMETRY if exact_symmetry else 0)))
 
     def rhs_dev(self, Mv_ptr, f_ptr, v_ptr, h, b_ptr):
         """b = -(M v + h f) on the device (Cloth::solve, Cloth.cpp:345); device pointers, asynchronous on ctx.stream."""

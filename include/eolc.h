@@ -109,8 +109,13 @@ int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, c
  *   is the same matrix: M_vals is left untouched (host entry: no device-to-host copy of M; device entries: the M rows are
  *   neither recomputed nor written).  f and MDK are produced as always and are bit-identical to a full fill.  Honoured for
  *   Lagrangian plans only (with EoL nodes M depends on x through F = deform_grad); otherwise M is recomputed.  M_vals must be
- *   the buffer of the previous fill or at least a valid one. */
+ *   the buffer of the previous fill or at least a valid one.
+ * EOLC_FILL_EXACT_SYMMETRY (device entries; the host entries always do it): MDK symmetric bit for bit, like the reference's mirrored
+ *   triplets (src/Forces.cpp:114-125, :531-539).  Pairs of nodes owned by one tile are summed once and mirrored anyway; the blocks of
+ *   pairs across two tiles agree to rounding only, and this flag adds a pass that copies the lower node's block onto the higher
+ *   node's transposed block.  Lagrangian plans only (EOLC_ERR_UNSUPPORTED with EoL nodes). */
 #define EOLC_FILL_M_UNCHANGED 1u
+#define EOLC_FILL_EXACT_SYMMETRY 2u
 int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
                         const double grav[3], double h, double *f, double *M_vals, double *MDK_vals, uint32_t flags);
 /* Page-locked host memory for the buffers handed to the host entry points (x, X, f, M_vals, MDK_vals, contact lists): such

@@ -156,7 +156,8 @@ def test_reproducible_and_dev_equals_host(ctx):
     Md = torch.empty((S, plan.nnz[0]), dtype=torch.float64, device=dev)
     Kd = torch.empty((S, plan.nnz[1]), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
-    plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, fd.data_ptr(), Md.data_ptr(), Kd.data_ptr(), n_scenes=S)
+    # (the host entry always symmetrises MDK exactly; the device entry on request)
+    plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, fd.data_ptr(), Md.data_ptr(), Kd.data_ptr(), n_scenes=S, exact_symmetry=True)
     torch.cuda.synchronize()
     assert fd[0].cpu().numpy().tobytes() == f1.tobytes() and Kd[0].cpu().numpy().tobytes() == K1.tobytes()
     assert Md[0].cpu().numpy().tobytes() == M1.tobytes()
@@ -179,7 +180,7 @@ def test_output_pointer_phases(ctx):
         bufs = [torch.full((n + 4,), float("nan"), dtype=torch.float64, device=dev) for n in (3 * N, plan.nnz[0], plan.nnz[1])]
         torch.cuda.synchronize()
         ptrs = [b.data_ptr() + 8 * (1 + p) for b, p in zip(bufs, (pf, pm, pk))]      # base is 256-byte aligned: +8 odd, +16 even phase
-        plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, ptrs[0], ptrs[1], ptrs[2], n_scenes=1)
+        plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, ptrs[0], ptrs[1], ptrs[2], n_scenes=1, exact_symmetry=True)
         torch.cuda.synchronize()
         for b, p, ref in zip(bufs, (pf, pm, pk), (f0, M0, K0)):
             h = b.cpu().numpy()
@@ -200,8 +201,9 @@ def test_fullsize_1024_properties(ctx):
     K = sp.csc_matrix((forces.MDK[2], forces.MDK[1], forces.MDK[0]), shape=(3 * N, 3 * N))
     assert abs(M - M.T).max() == 0.0
     scale = abs(K).max()
-    # MDK: rows are assembled independently (owner-computes), so (r,c) and (c,r) agree to rounding, not bitwise
-    assert abs(K - K.T).max() <= 1e-13 * scale
+    # MDK: exactly symmetric like the reference's mirrored triplets (Forces.cpp:114-125): pairs inside a tile are summed once and
+    # mirrored, pairs across two tiles are made equal by the symmetrisation pass of the host entry (EOLC_FILL_EXACT_SYMMETRY)
+    assert abs(K - K.T).max() == 0.0
     T = sp.csr_matrix(np.tile(np.eye(3), (N, 1)))       # translations
     dK = (K - M) @ T
     assert abs(dK).max() < 1e-9 * scale
@@ -393,7 +395,7 @@ def test_m_unchanged_flag_and_pinned_host_buffers(ctx):
     Md = torch.full((plan.nnz[0],), 7.0, dtype=torch.float64, device=dev)
     Kd = torch.full((plan.nnz[1],), float("nan"), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
-    plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, fd.data_ptr(), Md.data_ptr(), Kd.data_ptr(), m_unchanged=True)
+    plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, fd.data_ptr(), Md.data_ptr(), Kd.data_ptr(), m_unchanged=True, exact_symmetry=True)
     torch.cuda.synchronize()
     assert fd.cpu().numpy().tobytes() == f_ref.tobytes() and Kd.cpu().numpy().tobytes() == K_ref.tobytes()
     assert bool((Md == 7.0).all())
@@ -409,3 +411,35 @@ def test_m_unchanged_flag_and_pinned_host_buffers(ctx):
     plan_e.close()
     for b in bufs:
         b.free()
+
+
+@pytest.mark.parametrize("gen,n", [("regular2", 50), ("build4", 23)])
+def test_exact_symmetry_flag(ctx, gen, n):
+    """Device entry: without the flag the blocks of pairs across two tiles agree to rounding; with EOLC_FILL_EXACT_SYMMETRY the matrix
+    is symmetric bit for bit and differs from the plain fill only in those mirrored blocks (by rounding)."""
+    import scipy.sparse as sp
+    import torch
+    mesh = _mesh(gen, n, seed=4)
+    N = mesh["x"].shape[0]
+    plan = E.ForcesPlan(ctx, N, mesh["face_nodes"], mesh["edge_stencil"], X_hint=mesh["X"])
+    o, i = plan.pattern(1)
+    dev = torch.device("cuda", ctx.device)
+    xd, Xd = torch.from_numpy(mesh["x"]).to(dev), torch.from_numpy(mesh["X"]).to(dev)
+    out = {}
+    for sym in (False, True):
+        fd = torch.empty(plan.dof, dtype=torch.float64, device=dev)
+        Md = torch.empty(plan.nnz[0], dtype=torch.float64, device=dev)
+        Kd = torch.empty(plan.nnz[1], dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        plan.fill_dev(xd.data_ptr(), Xd.data_ptr(), MAT, GRAV, H, fd.data_ptr(), Md.data_ptr(), Kd.data_ptr(), exact_symmetry=sym)
+        torch.cuda.synchronize()
+        out[sym] = Kd.cpu().numpy()
+    K0 = sp.csc_matrix((out[False], i, o), shape=(3 * N, 3 * N))
+    K1 = sp.csc_matrix((out[True], i, o), shape=(3 * N, 3 * N))
+    assert abs(K1 - K1.T).max() == 0.0
+    scale = abs(K0).max()
+    assert 0.0 < abs(K0 - K0.T).max() <= 1e-13 * scale        # the plain fill really is asymmetric at rounding level
+    assert abs(K1 - K0).max() <= 1e-13 * scale
+    # one triangle is kept as it was (the lower node's blocks; the value array is row storage, read here as columns), the other mirrored
+    assert min(abs(sp.triu(K1) - sp.triu(K0)).max(), abs(sp.tril(K1) - sp.tril(K0)).max()) == 0.0
+    plan.close()
