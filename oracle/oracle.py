@@ -231,9 +231,11 @@ def cd(face_nodes, x, threshold, pxyz=None, pnorms=None, box_whd=None, box_E=Non
 _REFLIBS = {}
 
 
-def ref_lib(scalar_redux=False):
-    """libbtc_ref.so (Eigen 3.3 SSE2 reduction order) or libbtc_ref_scalar.so (non-vectorised order)."""
-    name = "libbtc_ref_scalar.so" if scalar_redux else "libbtc_ref.so"
+def ref_lib(scalar_redux=False, adapter=False):
+    """libbtc_ref.so (Eigen 3.3 SSE2 reduction order), libbtc_ref_scalar.so (non-vectorised order), or — adapter=True —
+    libadapter_cd.so: the same driver and reference types, but CD / CD2 are this repository's adapter/Collisions_b200.cpp, i.e. the
+    call lands on the GPU through include/eolc_host.hpp and the C ABI (needs a CUDA device; aborts like the reference otherwise)."""
+    name = "libadapter_cd.so" if adapter else "libbtc_ref_scalar.so" if scalar_redux else "libbtc_ref.so"
     if name in _REFLIBS:
         return _REFLIBS[name]
     path = os.path.join(_HERE, "_ref", name)
@@ -251,7 +253,7 @@ def ref_lib(scalar_redux=False):
     L.ref_btc_edges.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_ip, c_dp, c_ip, c_dp]
     L.ref_btc_boxtables.argtypes = [c_dp] * 6
     L.ref_btc_hash_defined.argtypes = [ctypes.c_int, ctypes.c_int]
-    assert L.ref_redux_order() == (1 if scalar_redux else 0)
+    assert adapter or L.ref_redux_order() == (1 if scalar_redux else 0)
     _REFLIBS[name] = L
     return L
 
@@ -272,13 +274,15 @@ def _ref_call(fn, N, *args):
         capacity = n.value
 
 
-def ref_cd(face_nodes, x, threshold, pxyz=None, pnorms=None, box_whd=None, box_E=None, which=0, eol=None, scalar_redux=False):
-    """The reference's CD (which=1, Collisions.cpp:11-53) / CD2 (which=0, :55-78), run as compiled from its own sources."""
-    L = ref_lib(scalar_redux)
+def ref_cd(face_nodes, x, threshold, pxyz=None, pnorms=None, box_whd=None, box_E=None, which=0, eol=None, scalar_redux=False,
+           adapter=False):
+    """The reference's CD (which=1, Collisions.cpp:11-53) / CD2 (which=0, :55-78), run as compiled from its own sources; with
+    adapter=True the same call sites reach adapter/Collisions_b200.cpp instead (the drop-in, executed)."""
+    L = ref_lib(scalar_redux, adapter)
     face_nodes = _i32(face_nodes).reshape(-1, 3)
     x = _f64(x).reshape(-1, 3)
     N, F = x.shape[0], face_nodes.shape[0]
-    if box_whd is not None and len(box_whd) and not ref_hash_defined(N, F):
+    if not adapter and box_whd is not None and len(box_whd) and not ref_hash_defined(N, F):
         raise ValueError("the reference's int edge hash overflows (undefined behaviour) for this mesh size")
     pxyz = _f64(np.zeros((0, 3)) if pxyz is None else pxyz).reshape(-1, 3)
     pnorms = _f64(np.zeros((0, 3)) if pnorms is None else pnorms).reshape(-1, 3)

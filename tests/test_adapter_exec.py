@@ -1,0 +1,57 @@
+"""The reference-side adapter, EXECUTED: adapter/Collisions_b200.cpp — the file a maintainer drops in place of src/Collisions.cpp —
+compiled against the reference's own headers (Collisions.h, external/ArcSim/mesh.hpp, Obstacles.h, Box.h, Points.h, boxTriCollision.h) with
+oracle/mini_eigen standing in for Eigen, linked with the reference's boxTriCollision.cpp, include/eolc_host.hpp and libeolc_b200.so
+(oracle/_ref/libadapter_cd.so, built by oracle/Makefile; travels prebuilt to the GPU box).  The call goes
+    ArcSim Mesh + shared_ptr<Obstacles>  ->  CD / CD2 (adapter)  ->  eolc::host::flatten / CD  ->  C ABI  ->  GPU
+and comes back as vector<shared_ptr<btc::Collision>>.  It must equal the reference's own CD / CD2 (libbtc_ref.so) in every field."""
+import numpy as np
+import pytest
+
+import eol_cloth_b200 as E
+
+pytestmark = pytest.mark.gpu
+THR = E.meshgen.BOX_THRESHOLD
+C3B = np.array([0.9175, -0.25, -0.549])
+
+
+def _rot(axis, ang):
+    axis = np.asarray(axis, float) / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+
+def _same(a, b, what):
+    assert len(a) == len(b), f"{what}: {len(a)} vs {len(b)} contacts"
+    for f in a.dtype.names:
+        assert a[f].tobytes() == b[f].tobytes(), f"{what}: field {f} differs"
+
+
+@pytest.mark.parametrize("gen,n,centre,rot,seed", [("regular2", 40, C3B, None, 2), ("build4", 21, (0.5, 0.5, -0.549), ((1, 2, 0.5), 0.05), 4),
+                                                   ("regular2", 64, C3B, None, 7), ("regular2", 33, (0.7, 0.3, -0.549), ((0, 0, 1), 0.3), 3)])
+def test_adapter_cd_equals_reference(oracle, gen, n, centre, rot, seed):
+    X, fn = getattr(E.meshgen, gen)(n)
+    x = E.meshgen.box_scene_state(X, seed=seed, centre=np.asarray(centre))
+    whd = E.meshgen.BOX_WHD[None]
+    Em = E.meshgen.box_frame(np.asarray(centre), None if rot is None else _rot(*rot))[None]
+    for which in (1, 0):
+        ref = oracle.ref_cd(fn, x, THR, None, None, whd, Em, which)
+        got = oracle.ref_cd(fn, x, THR, None, None, whd, Em, which, adapter=True)
+        _same(ref, got, f"{gen}{n} {'CD' if which else 'CD2'}")
+        assert len(ref) > 0
+
+
+def test_adapter_points_two_boxes_and_repeated_calls(oracle):
+    """Points + two boxes (CD's index remap), then the same mesh again with moved positions (the adapter's cached plan and page-locked
+    buffers are reused), then another mesh (the plan is rebuilt)."""
+    X, fn = E.meshgen.regular2(30)
+    x = E.meshgen.box_scene_state(X, seed=5, centre=C3B)
+    pxyz = np.array([[0.25, 0.25, x[:, 2].max() - 4e-3], [0.1, 0.8, -0.2], x[5] + 1e-3, x[100] - 2e-3])
+    pn = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0], [0, 0.6, 0.8]])
+    whd = np.stack([E.meshgen.BOX_WHD, [0.3, 0.3, 0.3]])
+    Em = np.stack([E.meshgen.box_frame(C3B), E.meshgen.box_frame(np.array([0.15, 0.8, -0.36]), _rot((0.3, 1, 0.2), 0.4))])
+    for xs in (x, x + [0.0, 0.0, 3e-4]):
+        for which in (1, 0):
+            _same(oracle.ref_cd(fn, xs, THR, pxyz, pn, whd, Em, which), oracle.ref_cd(fn, xs, THR, pxyz, pn, whd, Em, which, adapter=True), "points+2boxes")
+    X2, fn2 = E.meshgen.build4(14)
+    x2 = E.meshgen.box_scene_state(X2, seed=1, centre=C3B)
+    _same(oracle.ref_cd(fn2, x2, THR, None, None, whd[:1], Em[:1], 0), oracle.ref_cd(fn2, x2, THR, None, None, whd[:1], Em[:1], 0, adapter=True), "second mesh")

@@ -216,3 +216,22 @@ def test_threaded_timing_variant_is_bit_identical(oracle):
         for k in ("M", "MDK"):
             for u, v in zip(a[k], b[k]):
                 assert u.tobytes() == v.tobytes()
+
+
+def test_product_free_generators_equal_the_products(oracle):
+    """bench.py --impl reference builds its inputs without loading the product: oracle.sheet_regular2 / arcsim_edge_stencils /
+    drape_state must be the product's meshgen.regular2 / edge_stencils (eolc_mesh_edge_stencils) / drape_state, and a strip sample must
+    be a prefix of the full sheet (coordinates, numbering, faces, state)."""
+    import eol_cloth_b200 as E
+    for gen, n in (("regular2", 3), ("regular2", 17), ("build4", 9), ("regular2", 64)):
+        X, fn = getattr(E.meshgen, gen)(n)
+        assert np.array_equal(oracle.arcsim_edge_stencils(len(X), fn), E.meshgen.edge_stencils(len(X), fn)), (gen, n)
+    X, fn = E.meshgen.regular2(33)
+    X2, fn2 = oracle.sheet_regular2(33)
+    assert np.array_equal(X, X2) and np.array_equal(fn, fn2)
+    assert np.array_equal(E.meshgen.drape_state(X, seed=4), oracle.drape_state(X2, seed=4))
+    Xs, fs = oracle.sheet_regular2(33, rows=9)
+    assert np.array_equal(Xs, X[:9 * 33]) and np.array_equal(fs, fn[:2 * 8 * 32])
+    assert np.array_equal(oracle.drape_state(Xs, seed=4, n_total=33 * 33), E.meshgen.drape_state(X, seed=4)[:9 * 33])
+    perm = np.random.default_rng(0).permutation(len(fn))          # any face order: edges appear in first-use order
+    assert np.array_equal(oracle.arcsim_edge_stencils(len(X), fn[perm]), E.meshgen.edge_stencils(len(X), fn[perm]))
