@@ -516,6 +516,7 @@ def run_ours(args):
         line["consumer"]["normals"] = bench_normals(plan, dev, stream, x_d, N, F)
         line["eol"] = bench_eol(ctx, dev, stream, n, X, fn, es, x_d, X_d, ms_local)
     if rank == 0 and S == 1 and not args.no_cpu:
+        line["plan_build_ms"] = bench_plan_build(ctx)
         hl = bench_host_layer(n)
         if hl is not None:
             line["e2e"]["host_layer"] = hl
@@ -608,6 +609,31 @@ def bench_ensemble(ctx, dev, stream, rank, world, barrier, total_scenes=4096, n=
     plan.close(); cdp.close()
     del x_d, X_d, f_d, M_d, K_d
     torch.cuda.empty_cache()
+    return out
+
+
+def bench_plan_build(ctx):
+    """Host cost of a topology change: eolc_forces_plan_create (pattern, tiles, templates, upload) for the 512^2
+    sheet in its structured numbering, with a random node / face numbering (every tile its own template), and for the 1024^2 sheet."""
+    import eol_cloth_b200 as E
+    out = {}
+    for label, n, shuffle in (("sheet512", 512, False), ("sheet512_shuffled", 512, True), ("sheet1024", 1024, False)):
+        X, fn = E.meshgen.regular2(n)
+        if shuffle:
+            rng = np.random.default_rng(5)
+            perm = rng.permutation(X.shape[0])
+            Xn = np.empty_like(X); Xn[perm] = X
+            X, fn = Xn, perm[fn].astype(np.int32)[rng.permutation(len(fn))]
+        es = E.meshgen.edge_stencils(X.shape[0], fn)
+        best = None
+        for _ in range(2):
+            t = time.perf_counter()
+            plan = E.ForcesPlan(ctx, X.shape[0], fn, es, X_hint=X)
+            dt = time.perf_counter() - t
+            plan.close()
+            best = dt if best is None else min(best, dt)
+        out[label] = best * 1e3
+    out["what"] = "ms of host time for eolc_forces_plan_create (best of 2), threads = min(cores, 16)"
     return out
 
 

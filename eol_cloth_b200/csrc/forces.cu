@@ -401,11 +401,11 @@ size_t tiles_smem_bytes(const eolc_forces_plan *P) {
     return tiles_smem_layout(P->scr_doubles, P->kstage, P->mstage, P->tmplA16, P->tmplB16, P->geo16, P->loc_max).total;
 }
 
-int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st, const tiles::RowLayout *rows) {
+int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st, const tiles::RowLayout *rows, const NodeCSR *csr) {
     tiles::Plan tp;
     const char *dd = getenv("EOLC_FORCES_DEDUP");
     const bool dedup = !(dd && strcmp(dd, "0") == 0);
-    if (!tiles::build(P->N, P->F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), P->pat, X_hint, dedup, tp, rows)) {
+    if (!tiles::build(P->N, P->F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), P->pat, X_hint, dedup, tp, rows, csr)) {
         set_error("tile plan: %s", tp.error.c_str());
         return EOLC_ERR_UNSUPPORTED;
     }
@@ -1044,7 +1044,9 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
         P->h_iedge.insert(P->h_iedge.end(), s, s + 4);
     }
     P->Ei = (int32_t)(P->h_iedge.size() / 4);
-    build_pattern(N, F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), P->pat);
+    // node -> incident elements, built once: the pattern, the tiles and (later, on demand) the normals read it
+    const NodeCSR csr(N, F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data());
+    build_pattern(N, F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), P->pat, &csr);
     P->nnzM = 9 * P->pat.nblkM; P->nnzK = 9 * P->pat.nblkK;
     if (P->nnzK > (int64_t)INT32_MAX) { delete P; set_error("nnz(MDK) exceeds int32 (Eigen StorageIndex is int)"); return EOLC_ERR_UNSUPPORTED; }
     cudaStream_t st = ctx->stream;
@@ -1057,10 +1059,10 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
         rc = build_eol_plan(P, eol_index, ep, st);
         if (!rc) {
             const tiles::RowLayout rows{ep.dstM.data(), ep.dstK.data(), ep.extraM.data(), ep.extraK.data()};
-            rc = build_tiles_plan(P, X_hint, st, &rows);
+            rc = build_tiles_plan(P, X_hint, st, &rows, &csr);
         }
     } else {
-        rc = P->pipeline == 0 ? build_tiles_plan(P, X_hint, st, nullptr) : build_rows_plan(P, st);
+        rc = P->pipeline == 0 ? build_tiles_plan(P, X_hint, st, nullptr, &csr) : build_rows_plan(P, st);
     }
     if (rc) { delete P; return rc; }
     *out = P;

@@ -19,12 +19,31 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <new>
 #include <string>
+#include <chrono>
+#include <cstdio>
 #include <thread>
 #include <unordered_map>
 #include <vector>
 
 namespace eolc {
+
+// host threads the plan build may use: EOLC_PLAN_THREADS, else the hardware concurrency capped at 16
+inline int n_workers_hw() {
+    const char *ev = getenv("EOLC_PLAN_THREADS");
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1, ev ? atoi(ev) : (int)std::min<unsigned>(hw ? hw : 1u, 16u));
+}
+// body(lo, hi) over contiguous slices of [0, n) on the plan-build threads; results must not depend on the slicing
+template <class Body> inline void par_for(size_t n, Body body) {
+    const int nw = (int)std::min<size_t>((size_t)n_workers_hw(), std::max<size_t>(1, n / 4096));
+    if (nw <= 1) { body((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int w = 0; w < nw; ++w) th.emplace_back([&, w]() { body(n * (size_t)w / (size_t)nw, n * (size_t)(w + 1) / (size_t)nw); });
+    for (auto &t : th) t.join();
+}
 
 struct Pattern {
     int32_t N = 0;
@@ -38,46 +57,82 @@ inline int64_t find_block(const std::vector<int64_t> &blkptr, const std::vector<
     return std::lower_bound(beg, end, b) - nbr.begin();
 }
 
-// fn: 3F face nodes; ie: 4Ei interior-edge stencils
-inline void build_pattern(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie, Pattern &P) {
-    P.N = N;
-    std::vector<int64_t> cntM(N + 1, 0), cntK(N + 1, 0);
-    std::vector<char> used(N, 0);
-    for (int64_t i = 0; i < 3 * (int64_t)F; ++i) { used[fn[i]] = 1; cntM[fn[i] + 1] += 2; cntK[fn[i] + 1] += 2; }
-    for (int64_t i = 0; i < 4 * (int64_t)Ei; ++i) cntK[ie[i] + 1] += 3;
-    for (int32_t a = 0; a < N; ++a) {
-        if (used[a]) { cntM[a + 1] += 1; cntK[a + 1] += 1; } else { cntM[a + 1] = 0; cntK[a + 1] = 0; }   // isolated nodes own no block
+// node -> incident faces / stencils (CSR), ascending element index, elem << 2 | pos; read-only once built, shared by the workers
+struct NodeCSR {
+    std::vector<int32_t> nfp, nep;
+    std::vector<uint32_t> nfl, nel;
+    NodeCSR(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie) {
+        nfp.assign(N + 1, 0); nep.assign(N + 1, 0);
+        for (int64_t i = 0; i < 3 * (int64_t)F; ++i) nfp[fn[i] + 1]++;
+        for (int64_t i = 0; i < 4 * (int64_t)Ei; ++i) nep[ie[i] + 1]++;
+        for (int32_t a = 0; a < N; ++a) { nfp[a + 1] += nfp[a]; nep[a + 1] += nep[a]; }
+        nfl.resize(nfp[N]); nel.resize(nep[N]);
+        std::vector<int32_t> pf(nfp.begin(), nfp.end() - 1), pe(nep.begin(), nep.end() - 1);
+        for (int32_t i = 0; i < F; ++i) for (int v = 0; v < 3; ++v) nfl[pf[fn[3 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
+        for (int32_t i = 0; i < Ei; ++i) for (int v = 0; v < 4; ++v) nel[pe[ie[4 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
     }
-    for (int32_t a = 0; a < N; ++a) { cntM[a + 1] += cntM[a]; cntK[a + 1] += cntK[a]; }
-    std::vector<int32_t> rawM(cntM[N]), rawK(cntK[N]);
-    std::vector<int64_t> pM(cntM.begin(), cntM.end() - 1), pK(cntK.begin(), cntK.end() - 1);
-    for (int32_t a = 0; a < N; ++a) if (used[a]) { rawM[pM[a]++] = a; rawK[pK[a]++] = a; }
-    for (int32_t i = 0; i < F; ++i)
-        for (int v = 0; v < 3; ++v) {
-            int32_t a = fn[3 * (size_t)i + v];
-            for (int w = 0; w < 3; ++w) if (w != v) { rawM[pM[a]++] = fn[3 * (size_t)i + w]; rawK[pK[a]++] = fn[3 * (size_t)i + w]; }
-        }
-    for (int32_t i = 0; i < Ei; ++i)
-        for (int v = 0; v < 4; ++v) {
-            int32_t a = ie[4 * (size_t)i + v];
-            if (!used[a]) continue;   // cannot happen for a stencil built from faces; keeps the arrays consistent
-            for (int w = 0; w < 4; ++w) if (w != v) rawK[pK[a]++] = ie[4 * (size_t)i + w];
-        }
-    auto compress = [&](std::vector<int64_t> &cnt, std::vector<int64_t> &fill, std::vector<int32_t> &raw, std::vector<int64_t> &blkptr,
-                        std::vector<int32_t> &nbr) {
-        blkptr.assign(N + 1, 0);
-        nbr.clear();
-        nbr.reserve(raw.size() / 2);
-        for (int32_t a = 0; a < N; ++a) {
-            auto b = raw.begin() + cnt[a], e = raw.begin() + fill[a];
-            std::sort(b, e);
-            auto u = std::unique(b, e);
-            nbr.insert(nbr.end(), b, u);
-            blkptr[a + 1] = (int64_t)nbr.size();
+};
+
+// fn: 3F face nodes; ie: 4Ei interior-edge stencils.  Per node: itself + the other vertices of its faces (M), + the other vertices
+// of its bending stencils (MDK); sorted, unique.  Isolated nodes (no face) own no block.  Parallel over contiguous node ranges on the
+// plan-build threads (each range gathers from the node -> element lists into its own buffer; the buffers are concatenated in
+// range order, so the result does not depend on the thread count).
+inline void build_pattern(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie, Pattern &P, const NodeCSR *csr_in = nullptr) {
+    std::unique_ptr<NodeCSR> own_csr;
+    if (!csr_in) { own_csr.reset(new NodeCSR(N, F, fn, Ei, ie)); csr_in = own_csr.get(); }
+    const NodeCSR &c = *csr_in;
+    P.N = N;
+    P.blkptrM.assign((size_t)N + 1, 0); P.blkptrK.assign((size_t)N + 1, 0);
+    const int nw = (int)std::min<size_t>((size_t)n_workers_hw(), std::max<size_t>(1, (size_t)N / 4096));
+    std::vector<std::vector<int32_t>> partM((size_t)nw), partK((size_t)nw);
+    auto work = [&](int w) {
+        const size_t lo = (size_t)N * (size_t)w / (size_t)nw, hi = (size_t)N * (size_t)(w + 1) / (size_t)nw;
+        std::vector<int32_t> &oM = partM[(size_t)w], &oK = partK[(size_t)w];
+        oM.reserve((hi - lo) * 8); oK.reserve((hi - lo) * 14);
+        std::vector<int32_t> bm, bk;
+        for (size_t a = lo; a < hi; ++a) {
+            if (c.nfp[a + 1] == c.nfp[a]) continue;          // isolated: no block
+            bm.clear(); bk.clear();
+            bm.push_back((int32_t)a);
+            for (int32_t k = c.nfp[a]; k < c.nfp[a + 1]; ++k) {
+                const int32_t *v = fn + 3 * (size_t)(c.nfl[k] >> 2);
+                for (int j = 0; j < 3; ++j) if (v[j] != (int32_t)a) bm.push_back(v[j]);
+            }
+            std::sort(bm.begin(), bm.end());
+            bm.erase(std::unique(bm.begin(), bm.end()), bm.end());
+            bk = bm;
+            for (int32_t k = c.nep[a]; k < c.nep[a + 1]; ++k) {
+                const int32_t *v = ie + 4 * (size_t)(c.nel[k] >> 2);
+                for (int j = 0; j < 4; ++j) if (v[j] != (int32_t)a) bk.push_back(v[j]);
+            }
+            std::sort(bk.begin(), bk.end());
+            bk.erase(std::unique(bk.begin(), bk.end()), bk.end());
+            P.blkptrM[a + 1] = (int64_t)bm.size(); P.blkptrK[a + 1] = (int64_t)bk.size();
+            oM.insert(oM.end(), bm.begin(), bm.end()); oK.insert(oK.end(), bk.begin(), bk.end());
         }
     };
-    compress(cntM, pM, rawM, P.blkptrM, P.nbrM);
-    compress(cntK, pK, rawK, P.blkptrK, P.nbrK);
+    if (nw == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int w = 0; w < nw; ++w) th.emplace_back(work, w);
+        for (auto &t : th) t.join();
+    }
+    for (int32_t a = 0; a < N; ++a) { P.blkptrM[a + 1] += P.blkptrM[a]; P.blkptrK[a + 1] += P.blkptrK[a]; }
+    P.nbrM.resize((size_t)P.blkptrM[N]); P.nbrK.resize((size_t)P.blkptrK[N]);
+    {
+        std::vector<size_t> offM((size_t)nw + 1, 0), offK((size_t)nw + 1, 0);
+        for (int w = 0; w < nw; ++w) { offM[(size_t)w + 1] = offM[(size_t)w] + partM[(size_t)w].size(); offK[(size_t)w + 1] = offK[(size_t)w] + partK[(size_t)w].size(); }
+        auto copy = [&](int w) {
+            std::copy(partM[(size_t)w].begin(), partM[(size_t)w].end(), P.nbrM.begin() + (std::ptrdiff_t)offM[(size_t)w]);
+            std::copy(partK[(size_t)w].begin(), partK[(size_t)w].end(), P.nbrK.begin() + (std::ptrdiff_t)offK[(size_t)w]);
+        };
+        if (nw == 1) copy(0);
+        else {
+            std::vector<std::thread> th;
+            for (int w = 0; w < nw; ++w) th.emplace_back(copy, w);
+            for (auto &t : th) t.join();
+        }
+    }
     P.nblkM = P.blkptrM[N];
     P.nblkK = P.blkptrK[N];
 }
@@ -116,6 +171,7 @@ inline void build_eigen_arrays(int32_t N, const std::vector<int64_t> &blkptr, co
 // tiles
 // ---------------------------------------------------------------------------------------------------------------------
 namespace tiles {
+using eolc::NodeCSR;   // defined above: the pattern build reads it too
 
 #ifndef EOLC_TILE_OWN
 #define EOLC_TILE_OWN 32
@@ -192,22 +248,6 @@ struct Plan {
     std::string error;
 };
 
-// node -> incident faces / stencils (CSR), ascending element index, elem << 2 | pos; read-only once built, shared by the workers
-struct NodeCSR {
-    std::vector<int32_t> nfp, nep;
-    std::vector<uint32_t> nfl, nel;
-    NodeCSR(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie) {
-        nfp.assign(N + 1, 0); nep.assign(N + 1, 0);
-        for (int64_t i = 0; i < 3 * (int64_t)F; ++i) nfp[fn[i] + 1]++;
-        for (int64_t i = 0; i < 4 * (int64_t)Ei; ++i) nep[ie[i] + 1]++;
-        for (int32_t a = 0; a < N; ++a) { nfp[a + 1] += nfp[a]; nep[a + 1] += nep[a]; }
-        nfl.resize(nfp[N]); nel.resize(nep[N]);
-        std::vector<int32_t> pf(nfp.begin(), nfp.end() - 1), pe(nep.begin(), nep.end() - 1);
-        for (int32_t i = 0; i < F; ++i) for (int v = 0; v < 3; ++v) nfl[pf[fn[3 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
-        for (int32_t i = 0; i < Ei; ++i) for (int v = 0; v < 4; ++v) nel[pe[ie[4 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
-    }
-};
-
 struct Builder {
     int32_t N, F, Ei;
     const int32_t *fn, *ie;
@@ -216,11 +256,23 @@ struct Builder {
     const std::vector<uint32_t> &nfl, &nel;
     Builder(int32_t N_, int32_t F_, const int32_t *fn_, int32_t Ei_, const int32_t *ie_, const Pattern &p, const NodeCSR &csr)
         : N(N_), F(F_), Ei(Ei_), fn(fn_), ie(ie_), pat(p), nfp(csr.nfp), nep(csr.nep), nfl(csr.nfl), nel(csr.nel) {
-        fstamp.assign(F, -1); estamp.assign(Ei, -1); lstamp.assign(N, -1); local.assign(N, 0);
-        fslot.assign(F, 0); eslot.assign(Ei, 0);
+        // zero pages from calloc are mapped on first touch: a worker pays for the part of the mesh its tiles touch, not for 6 arrays of
+        // mesh size (stamps start at 1, so 0 means "never seen")
+        fstamp.alloc((size_t)F); estamp.alloc((size_t)Ei); lstamp.alloc((size_t)N); local.alloc((size_t)N);
+        fslot.alloc((size_t)F); eslot.alloc((size_t)Ei);
     }
+    struct Zeroed {
+        int32_t *p = nullptr;
+        Zeroed() {}
+        Zeroed(const Zeroed &) = delete;
+        Zeroed &operator=(const Zeroed &) = delete;
+        ~Zeroed() { free(p); }
+        void alloc(size_t n) { free(p); p = static_cast<int32_t *>(calloc(n ? n : 1, sizeof(int32_t))); if (!p) throw std::bad_alloc(); }
+        int32_t &operator[](size_t i) { return p[i]; }
+        int32_t operator[](size_t i) const { return p[i]; }
+    };
     // scratch for tile construction
-    std::vector<int32_t> fstamp, estamp, lstamp, local, fslot, eslot;   // *slot: element -> slot of the tile being built
+    Zeroed fstamp, estamp, lstamp, local, fslot, eslot;   // *slot: element -> slot of the tile being built
     int32_t stamp = 0;
 
     // element sets of a candidate tile; returns false if the tile exceeds the kernel's capacities
@@ -267,6 +319,30 @@ inline void rcb(std::vector<int32_t> &idx, size_t lo, size_t hi, size_t leaves, 
     });
     rcb(idx, lo, mid, lleaves, cx, cy, out);
     rcb(idx, mid, hi, leaves - lleaves, cx, cy, out);
+}
+// the same bisection with the two halves of the top `depth` levels on two threads (disjoint ranges of idx; leaves in the same order)
+inline void rcb_par(std::vector<int32_t> &idx, size_t lo, size_t hi, size_t leaves, const double *cx, const double *cy,
+                    std::vector<std::pair<size_t, size_t>> &out, int depth) {
+    if (depth <= 0 || leaves < 256) { rcb(idx, lo, hi, leaves, cx, cy, out); return; }
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    for (size_t i = lo; i < hi; ++i) {
+        x0 = std::min(x0, cx[idx[i]]); x1 = std::max(x1, cx[idx[i]]);
+        y0 = std::min(y0, cy[idx[i]]); y1 = std::max(y1, cy[idx[i]]);
+    }
+    const bool ax = (x1 - x0) >= (y1 - y0);
+    const double *c0 = ax ? cx : cy, *c1 = ax ? cy : cx;
+    const size_t lleaves = leaves / 2;
+    const size_t mid = lo + (size_t)(((hi - lo) * (uint64_t)lleaves + leaves / 2) / leaves);
+    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int32_t a, int32_t b) {
+        if (c0[a] != c0[b]) return c0[a] < c0[b];
+        if (c1[a] != c1[b]) return c1[a] < c1[b];
+        return a < b;
+    });
+    std::vector<std::pair<size_t, size_t>> right;
+    std::thread th([&]() { rcb_par(idx, mid, hi, leaves - lleaves, cx, cy, right, depth - 1); });
+    rcb_par(idx, lo, mid, lleaves, cx, cy, out, depth - 1);
+    th.join();
+    out.insert(out.end(), right.begin(), right.end());
 }
 
 // one phase-2 record under construction
@@ -454,12 +530,6 @@ inline bool mostly_full_tiles(const Plan &P) {
     return !P.tile_elems.empty() && full * 100 >= P.tile_elems.size() * 85;
 }
 
-// host threads the plan build may use: EOLC_PLAN_THREADS, else the hardware concurrency capped at 16
-inline int n_workers_hw() {
-    const char *ev = getenv("EOLC_PLAN_THREADS");
-    const unsigned hw = std::thread::hardware_concurrency();
-    return std::max(1, ev ? atoi(ev) : (int)std::min<unsigned>(hw ? hw : 1u, 16u));
-}
 
 // Where the rows of M / MDK go when they are not simply 9 * blkptr[node] apart: EOL meshes (forces_eol.h), whose Lagrangian rows
 // carry `extra` Eulerian columns behind their 3x3 blocks.  dst = value index of the node's first scalar row.
@@ -469,10 +539,22 @@ struct RowLayout {
 };
 
 inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie, const Pattern &pat, const double *X_hint, bool dedup,
-                  Plan &P, const RowLayout *rows = nullptr) {
+                  Plan &P, const RowLayout *rows = nullptr, const NodeCSR *csr_in = nullptr) {
     P = Plan();
     if (N == 0) return true;
-    const NodeCSR csr(N, F, fn, Ei, ie);
+    const bool timing = getenv("EOLC_PLAN_TIMING") != nullptr;
+    auto tnow = []() { return std::chrono::steady_clock::now(); };
+    auto tlast = tnow();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto t = tnow();
+        fprintf(stderr, "[plan] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tlast).count());
+        tlast = t;
+    };
+    std::unique_ptr<NodeCSR> own_csr;
+    if (!csr_in) { own_csr.reset(new NodeCSR(N, F, fn, Ei, ie)); csr_in = own_csr.get(); }
+    const NodeCSR &csr = *csr_in;
+    lap("node csr");
     Builder B(N, F, fn, Ei, ie, pat, csr);
     for (int32_t e = 0; e < Ei; ++e) {
         const int32_t *s = ie + 4 * (size_t)e;
@@ -502,11 +584,14 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         }
         for (int32_t a = 0; a < N; ++a) cx[a] = order[a];
     }
+    lap("builder + coordinates");
     std::vector<int32_t> idx(N);
     for (int32_t a = 0; a < N; ++a) idx[a] = a;
     std::vector<std::pair<size_t, size_t>> leaves;
     if ((MAX_OWN & (MAX_OWN - 1)) == 0 || !X_hint) {
-        rcb(idx, 0, (size_t)N, ((size_t)N + MAX_OWN - 1) / MAX_OWN, cx.data(), cy.data(), leaves);
+        int depth = 0;
+        while ((1 << depth) < n_workers_hw()) ++depth;
+        rcb_par(idx, 0, (size_t)N, ((size_t)N + MAX_OWN - 1) / MAX_OWN, cx.data(), cy.data(), leaves, depth);
     } else {
         // Tile sizes that are not a power of two: bisection leaves ragged tiles on structured meshes.  Snapped strip tiling instead:
         // strips of ~sqrt(MAX_OWN) node columns along x, cut into chunks of <= MAX_OWN nodes along y; every cut moves to the nearest
@@ -598,37 +683,71 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             }
         }
     }
-    // ---- split leaves that exceed the kernel's capacities
+    lap("bisection");
+    // ---- split leaves that exceed the kernel's capacities.  The capacity check of every leaf (the same element gathering the tile
+    //      builders do) runs on the plan-build threads, each with its own scratch; only leaves that fail it are bisected further,
+    //      one after the other.  Per-worker scratch (Builder) is created once and reused by the tile builders below.
     std::vector<int32_t> faces, edges;
+    const int n_workers = (int)std::min<size_t>((size_t)n_workers_hw(), std::max<size_t>(1, leaves.size() / 64));
+    std::vector<std::unique_ptr<Builder>> wb((size_t)n_workers);
     {
+        std::vector<char> pre_ok(leaves.size(), 0);
+        auto check_range = [&](int w) {
+            if (n_workers > 1 || !wb[0]) wb[(size_t)w].reset(new Builder(N, F, fn, Ei, ie, pat, csr));
+            std::vector<int32_t> fcs, eds;
+            for (size_t k = leaves.size() * (size_t)w / (size_t)n_workers; k < leaves.size() * (size_t)(w + 1) / (size_t)n_workers; ++k) {
+                const auto r = leaves[k];
+                pre_ok[k] = r.second > r.first && r.second - r.first <= (size_t)MAX_OWN &&
+                            wb[(size_t)w]->fits(idx.data() + r.first, (int)(r.second - r.first), fcs, eds);
+            }
+        };
+        if (n_workers == 1) check_range(0);
+        else {
+            std::vector<std::thread> th;
+            for (int w = 0; w < n_workers; ++w) th.emplace_back(check_range, w);
+            for (auto &t : th) t.join();
+        }
         std::vector<std::pair<size_t, size_t>> ok;
-        std::vector<std::pair<size_t, size_t>> work(leaves.rbegin(), leaves.rend());
-        while (!work.empty()) {
-            auto r = work.back(); work.pop_back();
-            if (r.second == r.first) continue;
-            if (B.fits(idx.data() + r.first, (int)std::min<size_t>(r.second - r.first, MAX_OWN + 1), faces, edges) && r.second - r.first <= (size_t)MAX_OWN) {
-                ok.push_back(r);
-                continue;
+        for (size_t k = 0; k < leaves.size(); ++k) {
+            if (pre_ok[k]) { ok.push_back(leaves[k]); continue; }
+            std::vector<std::pair<size_t, size_t>> work(1, leaves[k]);
+            while (!work.empty()) {
+                auto r = work.back(); work.pop_back();
+                if (r.second == r.first) continue;
+                if (B.fits(idx.data() + r.first, (int)std::min<size_t>(r.second - r.first, MAX_OWN + 1), faces, edges) && r.second - r.first <= (size_t)MAX_OWN) {
+                    ok.push_back(r);
+                    continue;
+                }
+                if (r.second - r.first == 1) {
+                    P.error = "node " + std::to_string(idx[r.first]) + " has too many incident faces / bending stencils for one tile";
+                    return false;
+                }
+                std::vector<std::pair<size_t, size_t>> two;
+                rcb(idx, r.first, r.second, 2, cx.data(), cy.data(), two);
+                work.push_back(two[1]); work.push_back(two[0]);
             }
-            if (r.second - r.first == 1) {
-                P.error = "node " + std::to_string(idx[r.first]) + " has too many incident faces / bending stencils for one tile";
-                return false;
-            }
-            std::vector<std::pair<size_t, size_t>> two;
-            rcb(idx, r.first, r.second, 2, cx.data(), cy.data(), two);
-            work.push_back(two[1]); work.push_back(two[0]);
         }
         leaves.swap(ok);
     }
     P.n_tiles = (int32_t)leaves.size();
     struct Run { uint64_t dst; uint32_t kind, src, len; };
     struct Grp { int kind, nA, nB, first, count; long cost; int warp; };
+    const bool verify_dedup = getenv("EOLC_PLAN_VERIFY_DEDUP") != nullptr;
+    const bool sort_own = getenv("EOLC_PLAN_SORT_OWN") != nullptr;   // developer knob (read once: getenv in a sort comparator costs a third of the build)
     // One worker builds the tiles [t0, t1) into its own partial plan Q (templates deduplicated within the range, geometry blobs
     // back to back with offsets in geo_off); the ranges are merged in tile order below, so the result does not depend on the
     // number of workers.
     auto build_range = [&](Builder &Bw, size_t t0, size_t t1, Plan &Q, std::vector<uint32_t> &geo_off, std::vector<std::pair<uint32_t, uint32_t>> &unique_tmpl) -> bool {
         std::vector<int32_t> faces, edges;
         std::unordered_map<uint64_t, std::vector<uint32_t>> seen;   // hash -> template offsets (16-byte units)
+        // Structural shortcut: the template of a tile is a function of its LOCAL structure only — the element -> local node lists, the
+        // degrees and staging offsets of the owned nodes, and the neighbour rows of the owned nodes written in local ids (that fixes
+        // every block position p, every mirrored position and which neighbours are owned).  On a structured mesh thousands of tiles
+        // share one signature; only the first of them builds (sorts, groups, serialises) the template.  EOLC_PLAN_VERIFY_DEDUP=1
+        // builds every template anyway and checks it against the one the shortcut would have reused.
+        struct SigEntry { std::vector<uint32_t> words; uint32_t toff, sizeA16, sizeB16; int64_t n_groups, pull_rows; };
+        std::unordered_map<uint64_t, std::vector<SigEntry>> sig_seen;
+        std::vector<uint32_t> sigw;
         std::vector<uint32_t> T;                                   // template under construction
         std::vector<RecTmp> recs[3];
         std::vector<Run> runs;
@@ -708,6 +827,33 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             }
             if (stage_end[0] > 0xffffu || stage_end[1] > 0xffffu) { Q.error = "tile " + std::to_string(t) + ": staging overflow"; return false; }
             Q.max_kstage = std::max(Q.max_kstage, stage_end[0]); Q.max_mstage = std::max(Q.max_mstage, stage_end[1]); Q.max_fstage = std::max(Q.max_fstage, stage_end[2]);
+            // ---- structural signature (see above)
+            const SigEntry *reuse = nullptr;
+            uint64_t sigh = 1469598103934665603ull;
+            if (dedup) {
+                sigw.clear();
+                sigw.push_back((uint32_t)n_own); sigw.push_back((uint32_t)nE); sigw.push_back((uint32_t)nF);
+                sigw.insert(sigw.end(), items.begin(), items.end());
+                for (int o = 0; o < n_own; ++o) {
+                    const int32_t a = own[o];
+                    sigw.push_back((uint32_t)(pat.blkptrK[a + 1] - pat.blkptrK[a]) | ((uint32_t)(pat.blkptrM[a + 1] - pat.blkptrM[a]) << 16));
+                    sigw.push_back(offsKM[o]); sigw.push_back(offsF[o]);
+                    // every neighbour of an owned node shares an element with it, hence has a local id already
+                    for (int64_t q = pat.blkptrK[a]; q < pat.blkptrK[a + 1]; ++q) sigw.push_back(lid(pat.nbrK[q]));
+                    for (int64_t q = pat.blkptrM[a]; q < pat.blkptrM[a + 1]; ++q) sigw.push_back(lid(pat.nbrM[q]) | 0x80000000u);
+                }
+                for (uint32_t w : sigw) { sigh ^= w; sigh *= 1099511628211ull; }
+                auto it = sig_seen.find(sigh);
+                if (it != sig_seen.end())
+                    for (const SigEntry &e : it->second)
+                        if (e.words == sigw) { reuse = &e; break; }
+            }
+            uint32_t toff = 0, sizeA16 = 0, sizeB16 = 0;
+            if (reuse && !verify_dedup) {
+                toff = reuse->toff; sizeA16 = reuse->sizeA16; sizeB16 = reuse->sizeB16;
+                Q.n_groups += reuse->n_groups; Q.pull_rows += reuse->pull_rows;
+            } else {
+            const int64_t groups_before = Q.n_groups, pulls_before = Q.pull_rows;
             // ---- phase-2 records
             for (auto &r : recs) r.clear();
             auto owned_index = [&](int32_t g) { return (Bw.lstamp[g] == Bw.stamp && Bw.local[g] < n_own) ? Bw.local[g] : -1; };
@@ -785,7 +931,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                         if (pairs(u.A) != pairs(v.A)) return pairs(u.A) > pairs(v.A);
                         // same position in the row = same direction on a structured mesh: neighbouring lanes then pull the same block
                         // of neighbouring elements, whose slots fall into different bank groups
-                        if (getenv("EOLC_PLAN_SORT_OWN")) return false;
+                        if (sort_own) return false;
                         return u.p < v.p;
                     });
                 for (size_t g0 = 0; g0 < rv.size();) {
@@ -823,7 +969,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             T.push_back(0); T.push_back(0); T.push_back(0);
             T.insert(T.end(), items.begin(), items.end());
             while (T.size() % 4) T.push_back(0);
-            const uint32_t sizeA16 = (uint32_t)(T.size() / 4);
+            sizeA16 = (uint32_t)(T.size() / 4);
             T.push_back((uint32_t)n_own | ((uint32_t)groups.size() << 8));
             T.push_back(0); T.push_back(0); T.push_back(0);
             for (int w = 0; w < P2THREADS / 32; ++w) {          // groups [first, first + count) of warp w (the groups are ordered by warp)
@@ -892,11 +1038,10 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                 while (T.size() % 4) T.push_back(0);
             }
             Q.n_groups += (int64_t)groups.size();
-            const uint32_t sizeB16 = (uint32_t)(T.size() / 4) - sizeA16;
+            sizeB16 = (uint32_t)(T.size() / 4) - sizeA16;
             if (sizeA16 > 0xffffu || sizeB16 > 0xffffu) { Q.error = "tile " + std::to_string(t) + ": template too large"; return false; }
             Q.max_tmplA16 = std::max(Q.max_tmplA16, sizeA16); Q.max_tmplB16 = std::max(Q.max_tmplB16, sizeB16);
             // ---- deduplicate
-            uint32_t toff = 0;
             bool found = false;
             uint64_t h = 1469598103934665603ull;
             if (dedup) {
@@ -914,6 +1059,14 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                 if (dedup) seen[h].push_back(toff);
                 ++Q.n_templates;
                 unique_tmpl.push_back({toff, sizeA16});
+            }
+            if (reuse) {   // EOLC_PLAN_VERIFY_DEDUP: the shortcut would have reused this template — it must be the one just built
+                if (reuse->toff != toff || reuse->sizeA16 != sizeA16 || reuse->sizeB16 != sizeB16) {
+                    Q.error = "tile " + std::to_string(t) + ": structural signature matched a different template"; return false;
+                }
+            } else if (dedup) {
+                sig_seen[sigh].push_back(SigEntry{sigw, toff, sizeA16, sizeB16, Q.n_groups - groups_before, Q.pull_rows - pulls_before});
+            }
             }
             // ---- geometry blob
             geo_off.push_back((uint32_t)(Q.geo.size() / 4));
@@ -936,7 +1089,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         geo_off.push_back((uint32_t)(Q.geo.size() / 4));
         return true;
     };
-    int n_workers = std::max(1, std::min<int>(n_workers_hw(), (int)(leaves.size() / 64)));
+    lap("capacity check");
     std::vector<Plan> parts((size_t)n_workers);
     std::vector<std::vector<uint32_t>> part_geo_off((size_t)n_workers);
     std::vector<std::vector<std::pair<uint32_t, uint32_t>>> part_unique((size_t)n_workers);
@@ -948,13 +1101,14 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         std::vector<std::thread> th;
         for (int w = 0; w < n_workers; ++w)
             th.emplace_back([&, w]() {
-                Builder Bw(N, F, fn, Ei, ie, pat, csr);       // own scratch (stamps, slot maps); the node CSR is shared
+                // own scratch (stamps, slot maps), created for the capacity check above; the node CSR is shared
                 const auto r = range_of(w);
-                part_ok[w] = build_range(Bw, r.first, r.second, parts[w], part_geo_off[w], part_unique[w]) ? 1 : 0;
+                part_ok[w] = build_range(*wb[(size_t)w], r.first, r.second, parts[w], part_geo_off[w], part_unique[w]) ? 1 : 0;
             });
         for (auto &t : th) t.join();
     }
     for (int w = 0; w < n_workers; ++w) if (!part_ok[w]) { P.error = parts[w].error; return false; }
+    lap("tiles (workers)");
     // ---- merge in tile order: templates deduplicated across the ranges, geometry blobs re-laid with a fixed stride
     std::vector<std::pair<uint32_t, uint32_t>> unique_tmpl;   // (offset, size of part A) of every stored template, 16-byte units
     for (int w = 0; w < n_workers; ++w) {
@@ -1015,6 +1169,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         }
         P.geo.swap(fixed);
     }
+    lap("merge");
     {
         // bank-aware post-pass over the stored templates; the slot search only where templates are shared (structured meshes)
         const char *ob = getenv("EOLC_PLAN_BANK_ITERS");
@@ -1033,6 +1188,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
             for (auto &t : th) t.join();
         }
     }
+    lap("bank post-pass");
     return true;
 }
 
