@@ -23,7 +23,9 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "eolc.h"
@@ -122,7 +124,31 @@ struct FlatMesh {
 // verts->{u, node}, faces[k]->v[3], edges[e]->{n[2], adjf[2]}.  `positions_only` refreshes x (and X) of an existing
 // FlatMesh without touching the topology arrays — what a step without remeshing needs.
 // Changes are detected while the values are copied (a compare per value written, no second pass, no hash): the version counters
-// of `out` move only when something really changed, whatever the caller believes.
+// of `out` move only when something really changed, whatever the caller believes.  The loops run on up to 16 host threads
+// (EOLC_HOST_THREADS overrides): the walk over a million-node pointer mesh is latency-bound pointer chasing (100 ms on one core),
+// every node / face / edge is independent, and the result does not depend on the thread count.
+namespace detail {
+inline int host_threads() {
+    const char *ev = std::getenv("EOLC_HOST_THREADS");
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int n = ev ? std::atoi(ev) : (int)(hw ? (hw < 16u ? hw : 16u) : 1u);
+    return n < 1 ? 1 : n;
+}
+// body(lo, hi) -> bool "something changed", over contiguous slices of [0, n); returns the OR
+template <class Body> inline bool par_any(size_t n, Body body) {
+    const int nw = (int)std::min<size_t>((size_t)host_threads(), n / 16384 + 1);
+    if (nw <= 1) return body((size_t)0, n);
+    std::vector<char> changed((size_t)nw, 0);
+    std::vector<std::thread> th;
+    for (int w = 0; w < nw; ++w)
+        th.emplace_back([&, w]() { changed[(size_t)w] = body(n * (size_t)w / (size_t)nw, n * (size_t)(w + 1) / (size_t)nw) ? 1 : 0; });
+    for (auto &t : th) t.join();
+    bool any = false;
+    for (char c : changed) any = any || c;
+    return any;
+}
+}  // namespace detail
+
 template <class MeshT>
 void flatten(const MeshT &mesh, FlatMesh &out, bool positions_only = false) {
     const size_t N = mesh.nodes.size();
@@ -130,47 +156,60 @@ void flatten(const MeshT &mesh, FlatMesh &out, bool positions_only = false) {
     out.N = (int32_t)N;
     out.x.resize(3 * N);
     out.X.resize(2 * N);
-    for (size_t i = 0; i < N; ++i) {
-        const auto *n = mesh.nodes[i];
-        out.x[3 * i] = n->x[0]; out.x[3 * i + 1] = n->x[1]; out.x[3 * i + 2] = n->x[2];      // Forces.cpp:343-348
-        const double u0 = n->verts[0]->u[0], u1 = n->verts[0]->u[1];                         // Forces.cpp:349-355
-        if (!X_changed && (out.X[2 * i] != u0 || out.X[2 * i + 1] != u1)) X_changed = true;
-        out.X[2 * i] = u0; out.X[2 * i + 1] = u1;
-    }
+    X_changed |= detail::par_any(N, [&](size_t lo, size_t hi) {
+        bool ch = false;
+        for (size_t i = lo; i < hi; ++i) {
+            const auto *n = mesh.nodes[i];
+            out.x[3 * i] = n->x[0]; out.x[3 * i + 1] = n->x[1]; out.x[3 * i + 2] = n->x[2];      // Forces.cpp:343-348
+            const double u0 = n->verts[0]->u[0], u1 = n->verts[0]->u[1];                         // Forces.cpp:349-355
+            if (out.X[2 * i] != u0 || out.X[2 * i + 1] != u1) ch = true;
+            out.X[2 * i] = u0; out.X[2 * i + 1] = u1;
+        }
+        return ch;
+    });
     if (X_changed) out.X_version = next_version();
     if (positions_only) { if (topo_changed) out.topology_version = next_version(); return; }
     if (out.eol_index.size() != N) { out.eol_index.assign(N, -1); topo_changed = true; }
-    out.EoL_Count = 0;
+    int32_t eol_count = 0;
     for (size_t i = 0; i < N; ++i) {
         const int32_t v = mesh.nodes[i]->EoL ? (int32_t)mesh.nodes[i]->EoL_index : -1;
-        if (mesh.nodes[i]->EoL) ++out.EoL_Count;
+        if (mesh.nodes[i]->EoL) ++eol_count;
         if (out.eol_index[i] != v) { out.eol_index[i] = v; topo_changed = true; }
     }
+    out.EoL_Count = eol_count;
     const size_t F = mesh.faces.size();
     if (out.face_nodes.size() != 3 * F) { out.face_nodes.assign(3 * F, -1); topo_changed = true; }
     out.F = (int32_t)F;
-    for (size_t k = 0; k < F; ++k)
-        for (int j = 0; j < 3; ++j) {                                                              // Forces.cpp:376-378
-            const int32_t v = mesh.faces[k]->v[j]->node->index;
-            if (out.face_nodes[3 * k + j] != v) { out.face_nodes[3 * k + j] = v; topo_changed = true; }
-        }
+    topo_changed |= detail::par_any(F, [&](size_t lo, size_t hi) {
+        bool ch = false;
+        for (size_t k = lo; k < hi; ++k)
+            for (int j = 0; j < 3; ++j) {                                                          // Forces.cpp:376-378
+                const int32_t v = mesh.faces[k]->v[j]->node->index;
+                if (out.face_nodes[3 * k + j] != v) { out.face_nodes[3 * k + j] = v; ch = true; }
+            }
+        return ch;
+    });
     const size_t E = mesh.edges.size();
     if (out.edge_stencil.size() != 4 * E) { out.edge_stencil.assign(4 * E, -2); topo_changed = true; }
     out.E = (int32_t)E;
-    for (size_t e = 0; e < E; ++e) {
-        const auto *ed = mesh.edges[e];
-        int32_t s[4] = {(int32_t)ed->n[0]->index, (int32_t)ed->n[1]->index, -1, -1};
-        for (int side = 0; side < 2; ++side) {
-            const auto *f = ed->adjf[side];
-            if (!f) continue;                                                                      // Forces.cpp:688-690
-            for (int j = 0; j < 3; ++j) {                                                          // get_other_vert, mesh.hpp:276-280
-                const auto *nd = f->v[j]->node;
-                if (nd != ed->n[0] && nd != ed->n[1]) { s[2 + side] = nd->index; break; }
+    topo_changed |= detail::par_any(E, [&](size_t lo, size_t hi) {
+        bool ch = false;
+        for (size_t e = lo; e < hi; ++e) {
+            const auto *ed = mesh.edges[e];
+            int32_t s[4] = {(int32_t)ed->n[0]->index, (int32_t)ed->n[1]->index, -1, -1};
+            for (int side = 0; side < 2; ++side) {
+                const auto *f = ed->adjf[side];
+                if (!f) continue;                                                                  // Forces.cpp:688-690
+                for (int j = 0; j < 3; ++j) {                                                      // get_other_vert, mesh.hpp:276-280
+                    const auto *nd = f->v[j]->node;
+                    if (nd != ed->n[0] && nd != ed->n[1]) { s[2 + side] = nd->index; break; }
+                }
             }
+            int32_t *d = &out.edge_stencil[4 * e];
+            for (int q = 0; q < 4; ++q) if (d[q] != s[q]) { d[q] = s[q]; ch = true; }
         }
-        int32_t *d = &out.edge_stencil[4 * e];
-        for (int q = 0; q < 4; ++q) if (d[q] != s[q]) { d[q] = s[q]; topo_changed = true; }
-    }
+        return ch;
+    });
     if (topo_changed) out.topology_version = next_version();
 }
 

@@ -24,7 +24,7 @@ def driver():
     libdir = os.path.join(ROOT, "eol_cloth_b200")
     deps = [SRC, os.path.join(ROOT, "include", "eolc_host.hpp"), os.path.join(ROOT, "include", "eolc.h")]
     if not os.path.exists(EXE) or any(os.path.getmtime(p) > os.path.getmtime(EXE) for p in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++11", "-Wall", "-I", os.path.join(ROOT, "include"), SRC, "-o", EXE,
+        subprocess.check_call(["g++", "-O2", "-std=c++11", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), SRC, "-o", EXE,
                                "-L", libdir, "-leolc_b200", "-Wl,-rpath," + libdir])
     return EXE
 
