@@ -50,10 +50,11 @@ void run(const Mesh &mesh, const shared_ptr<Obstacles> &obs, vector<shared_ptr<b
     static thread_local eolc::host::ObstaclesFlat of;
     eolc::host::flatten(mesh, flat);                       // verts2 / faces2 of Collisions.cpp:13-27 (+ the stencils, unused here)
     flatten_obstacles(obs, of);
-    vector<shared_ptr<eolc::host::Collision> > raw;
-    if (cd1) eolc::host::CD(flat, of, raw); else eolc::host::CD2(flat, of, raw);   // eolc_cd_plan_create (on change) + eolc_cd_run
-    cls.reserve(cls.size() + raw.size());
-    for (const auto &c : raw) cls.push_back(to_btc(*c));    // appended: the caller clears (Scene.cpp:93)
+    // eolc_cd_plan_create (on a topology / threshold change) + eolc_cd_run; the records arrive in the thread's page-locked buffer and
+    // are turned into btc::Collision objects straight from there (one allocation per contact, as the interface demands)
+    const eolc::host::ContactView raw = cd1 ? eolc::host::CD_view(flat, of) : eolc::host::CD2_view(flat, of);
+    cls.reserve(cls.size() + (size_t)raw.size);
+    for (int32_t i = 0; i < raw.size; ++i) cls.push_back(to_btc(raw.data[i]));    // appended: the caller clears (Scene.cpp:93)
 }
 }  // namespace
 

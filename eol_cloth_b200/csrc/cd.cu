@@ -1066,6 +1066,7 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
     EOLC_CUDA(P->p_blockoff.ensure(nblocks + 1));
     EOLC_CUDA(P->d_counter.ensure(2)); EOLC_CUDA(P->p_counter.ensure(2));
     const long long nblkC = (long long)(nC / 256) * S * nB;
+    EOLC_REQUIRE(nblkC * 256 * 12 < (long long)INT32_MAX, "too many (cloth edge, box edge) pairs for one run; split the batch");   // the pair counter is an int
     long long cap = std::min<long long>(std::max<long long>((long long)P->d_cands.n, nblkC * 128 + 65536), (long long)1 << 30);   // half a pair per edge, and then some
     if (const char *ev = getenv("EOLC_CD_PAIR_CAP")) cap = std::max<long long>(1, atoll(ev));   // test knob: forces the overflow path
     for (int attempt = 0;; ++attempt) {

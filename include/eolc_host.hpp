@@ -302,7 +302,9 @@ struct CdCache {
     PinnedArray<eolc_contact> buf;       // page-locked: the contact list is DMA'd straight into it
     ~CdCache() { eolc_cd_plan_destroy(plan); }
 };
-inline void run_cd(const FlatMesh &mesh, const ObstaclesFlat &obs, std::vector<std::shared_ptr<Collision> > &cls, int cd1, Context *ctx) {
+// The contacts of one call as a view into the thread's page-locked record buffer (valid until the next call of the thread)
+struct ContactView { const eolc_contact *data; int32_t size; };
+inline ContactView run_cd_view(const FlatMesh &mesh, const ObstaclesFlat &obs, int cd1, Context *ctx) {
     Context &c = ctx ? *ctx : Context::instance();   // before the cache: the thread's Context must outlive the cached plan
     static thread_local CdCache cache;
     // the plan (btc edge table + perturbation stream) follows the mesh's topology counter and the threshold
@@ -321,8 +323,13 @@ inline void run_cd(const FlatMesh &mesh, const ObstaclesFlat &obs, std::vector<s
         check(rc, "eolc_cd_run");
         break;
     }
-    cls.reserve(cls.size() + (size_t)n);
-    for (int32_t i = 0; i < n; ++i) cls.push_back(std::make_shared<Collision>(cache.buf[(size_t)i]));   // appended, caller clears (Scene.cpp:93)
+    ContactView v = {cache.buf.data(), n};
+    return v;
+}
+inline void run_cd(const FlatMesh &mesh, const ObstaclesFlat &obs, std::vector<std::shared_ptr<Collision> > &cls, int cd1, Context *ctx) {
+    const ContactView v = run_cd_view(mesh, obs, cd1, ctx);
+    cls.reserve(cls.size() + (size_t)v.size);
+    for (int32_t i = 0; i < v.size; ++i) cls.push_back(std::make_shared<Collision>(v.data[i]));   // appended, caller clears (Scene.cpp:93)
 }
 }  // namespace detail
 
@@ -330,6 +337,11 @@ inline void run_cd(const FlatMesh &mesh, const ObstaclesFlat &obs, std::vector<s
 inline void CD(const FlatMesh &mesh, const ObstaclesFlat &obs, std::vector<std::shared_ptr<Collision> > &cls, Context *ctx = nullptr) {
     detail::run_cd(mesh, obs, cls, 1, ctx);
 }
+// The same calls for a caller that builds its own record objects (the reference-side adapter makes btc::Collision objects): the
+// contacts as a view into the calling thread's page-locked buffer, valid until the thread's next CD / CD2 call.
+typedef detail::ContactView ContactView;
+inline ContactView CD_view(const FlatMesh &mesh, const ObstaclesFlat &obs, Context *ctx = nullptr) { return detail::run_cd_view(mesh, obs, 1, ctx); }
+inline ContactView CD2_view(const FlatMesh &mesh, const ObstaclesFlat &obs, Context *ctx = nullptr) { return detail::run_cd_view(mesh, obs, 0, ctx); }
 // void CD2(...)                                                                                  Collisions.cpp:55-78
 inline void CD2(const FlatMesh &mesh, const ObstaclesFlat &obs, std::vector<std::shared_ptr<Collision> > &cls, Context *ctx = nullptr) {
     detail::run_cd(mesh, obs, cls, 0, ctx);
