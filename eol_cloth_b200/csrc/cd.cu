@@ -1263,6 +1263,27 @@ int eolc_constraints_contact_rows(const eolc_contact *contacts, int32_t n, const
     return EOLC_OK;
 }
 
+int eolc_constraints_fixed_rows(const double *c, const int32_t *ci, const double *v, int32_t n_nodes, int32_t eq_row0, int32_t *n_rows,
+                                int32_t *rows, int32_t *cols, double *vals, double *beq) {
+    EOLC_REQUIRE(c && ci && n_rows && rows && cols && vals && beq && n_nodes >= 0, "bad arguments");
+    int32_t n = 0;
+    for (int k = 0; k < 4; ++k) {
+        const double *ck = c + 6 * k;
+        if (ck[0] == -1.0) continue;                                   // `if (fs->c1(0) != -1)`, Constraints.cpp:470
+        EOLC_REQUIRE(ci[k] >= 0 && ci[k] < n_nodes && v, "fixed corner names a node the mesh does not have");
+        for (int j = 0; j < 3; ++j) {
+            if (ck[j] != 1.0) continue;                                // `if (fs->c1(j) == 1.0) addFixed(...)`
+            rows[n] = eq_row0 + n;
+            cols[n] = ci[k] * 3 + j;
+            vals[n] = ck[j];                                           // Aeq_.push_back(T(eqsize, ci, c(i)))          :116
+            beq[n] = (1 - 0.01) * v[3 * (size_t)ci[k] + j] + ck[j + 3]; // (1 - 0.01) * v + c(i + 3)                    :117
+            ++n;
+        }
+    }
+    *n_rows = n;
+    return EOLC_OK;
+}
+
 int eolc_cd_contact_rows(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t capacity_rows, int32_t *n_rows, int32_t *row_nnz, int32_t *cols,
                          double *vals) {
     EOLC_REQUIRE(plan && n_rows, "NULL argument");

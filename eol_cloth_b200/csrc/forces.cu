@@ -56,7 +56,9 @@ struct eolc_forces_plan {
     // exact symmetry of MDK (EOLC_FILL_EXACT_SYMMETRY): the pairs (a, b), a < b, whose two nodes are owned by different tiles
     std::vector<int32_t> h_tile_of;               // owner tile per node ("tiles" pipeline)
     DevBuf<uint4> d_sym_pairs;                    // per pair: offset of block (a,b), offset of block (b,a), row strides (a | b << 16), 0
-    int64_t n_sym_pairs = -1;                     // -1: not built yet                    // eolc_forces_fill has produced M on this plan (EOLC_FILL_M_UNCHANGED may skip it)
+    int64_t n_sym_pairs = -1;                     // -1: not built yet
+    std::vector<int64_t> h_dstK;                  // EOL plans: value index of scalar row 3a of every node (rows carry Eulerian columns)
+    std::vector<int32_t> h_extraK;                // EOL plans: Eulerian columns per scalar row of the node                    // eolc_forces_fill has produced M on this plan (EOLC_FILL_M_UNCHANGED may skip it)
     // "tiles" pipeline
     int32_t n_tiles = 0, n_templates = 0;
     bool service_p3 = false;
@@ -920,8 +922,10 @@ __global__ void __launch_bounds__(256) symmetrize_kernel(long long n_pairs, cons
 
 static int ensure_sym_pairs(eolc_forces_plan *P) {
     if (P->n_sym_pairs >= 0) return EOLC_OK;
-    if (P->n_eol) { set_error("EOLC_FILL_EXACT_SYMMETRY is implemented for Lagrangian plans (no EoL nodes)"); return EOLC_ERR_UNSUPPORTED; }
-    if (9 * P->pat.nblkK >= ((int64_t)1 << 32)) { set_error("EOLC_FILL_EXACT_SYMMETRY: matrix too large for 32-bit block offsets"); return EOLC_ERR_UNSUPPORTED; }
+    // EOL plans: the Lagrangian blocks sit in rows that also carry Eulerian columns (forces_eol.h): first scalar row of node a at
+    // h_dstK[a], rows 3 deg + extra apart.  The Eulerian rows / columns come from one source per mirrored pair and are symmetric already.
+    const bool eol = P->n_eol != 0;
+    if (P->nnzK >= ((int64_t)1 << 32)) { set_error("EOLC_FILL_EXACT_SYMMETRY: matrix too large for 32-bit block offsets"); return EOLC_ERR_UNSUPPORTED; }
     const Pattern &pat = P->pat;
     std::vector<uint4> pairs;
     for (int32_t a = 0; a < P->N; ++a) {
@@ -934,8 +938,9 @@ static int ensure_sym_pairs(eolc_forces_plan *P) {
             if (P->pipeline == 0 && P->h_tile_of[a] == P->h_tile_of[b]) continue;
             const uint32_t degb = (uint32_t)(pat.blkptrK[b + 1] - pat.blkptrK[b]);
             const int64_t qb = find_block(pat.blkptrK, pat.nbrK, b, a);
-            pairs.push_back(make_uint4((uint32_t)(9 * a0 + 3 * (q - a0)), (uint32_t)(9 * pat.blkptrK[b] + 3 * (qb - pat.blkptrK[b])),
-                                       (3u * dega) | ((3u * degb) << 16), 0u));
+            const int64_t rowa = eol ? P->h_dstK[a] : 9 * a0, rowb = eol ? P->h_dstK[b] : 9 * pat.blkptrK[b];
+            const uint32_t stra = 3u * dega + (eol ? (uint32_t)P->h_extraK[a] : 0u), strb = 3u * degb + (eol ? (uint32_t)P->h_extraK[b] : 0u);
+            pairs.push_back(make_uint4((uint32_t)(rowa + 3 * (q - a0)), (uint32_t)(rowb + 3 * (qb - pat.blkptrK[b])), stra | (strb << 16), 0u));
         }
     }
     EOLC_CUDA(P->d_sym_pairs.upload(pairs, P->ctx->stream));
@@ -1059,6 +1064,7 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
         rc = build_eol_plan(P, eol_index, ep, st);
         if (!rc) {
             const tiles::RowLayout rows{ep.dstM.data(), ep.dstK.data(), ep.extraM.data(), ep.extraK.data()};
+            P->h_dstK = ep.dstK; P->h_extraK = ep.extraK;
             rc = build_tiles_plan(P, X_hint, st, &rows, &csr);
         }
     } else {
@@ -1340,9 +1346,9 @@ int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X
     EOLC_CUDA(cudaMemcpyAsync(P->d_X.p, hX, 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
     int rc = launch_fill(P, 1, P->d_x.p, P->d_X.p, mat, grav, h, P->d_f.p, P->d_Mv.p, P->d_Kv.p, skip_m);
     if (rc) return rc;
-    // the host entry always hands out an exactly symmetric MDK, like the reference's (0.1 ms next to the copies); plans with EoL nodes
-    // keep their rounding-level asymmetry across tiles
-    if (P->n_eol == 0) { rc = launch_symmetrize(P, 1, P->d_Kv.p); if (rc) return rc; }
+    // the host entry always hands out an exactly symmetric MDK, like the reference's (0.3 ms next to the copies)
+    rc = launch_symmetrize(P, 1, P->d_Kv.p);
+    if (rc) return rc;
     double *hf = f, *hM = M_vals, *hK = MDK_vals;
     if (!out_pinned) {
         EOLC_CUDA(P->p_out.ensure(nf + P->nnzM + P->nnzK));

@@ -113,7 +113,7 @@ int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, c
  * EOLC_FILL_EXACT_SYMMETRY (device entries; the host entries always do it): MDK symmetric bit for bit, like the reference's mirrored
  *   triplets (src/Forces.cpp:114-125, :531-539).  Pairs of nodes owned by one tile are summed once and mirrored anyway; the blocks of
  *   pairs across two tiles agree to rounding only, and this flag adds a pass that copies the lower node's block onto the higher
- *   node's transposed block.  Lagrangian plans only (EOLC_ERR_UNSUPPORTED with EoL nodes). */
+ *   node's transposed block (for plans with EoL nodes too: their Eulerian rows / columns are mirrored from one source already). */
 #define EOLC_FILL_M_UNCHANGED 1u
 #define EOLC_FILL_EXACT_SYMMETRY 2u
 int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X, const eolc_material *mat,
@@ -225,6 +225,14 @@ int eolc_constraints_contact_rows(const eolc_contact *contacts, int32_t n, const
                                   int32_t *row_nnz, int32_t *cols, double *vals);
 int eolc_cd_contact_rows(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t capacity_rows, int32_t *n_rows, int32_t *row_nnz,
                          int32_t *cols, double *vals);
+/* Constraints::fill, fixed-corner part (src/Constraints.cpp:114-119, :470-497): the equality rows of the four corner records of a
+ * FixedList (src/FixedList.h:32-37).  corner k: c[6 k .. 6 k + 5] = (mask x, y, z, prescribed velocity x, y, z), node index ci[k];
+ * a corner with c[6 k] == -1 is absent, a component with mask == 1.0 gets one row
+ *     Aeq(row, 3 ci[k] + j) = mask_j ,   beq(row) = (1 - 0.01) v[3 ci[k] + j] + c[6 k + 3 + j]        (v: 3N node velocities)
+ * in the reference's push order (corners 1..4, components x, y, z), rows numbered from eq_row0 (the reference's running eqsize).
+ * Host-only (at most 12 rows).  Outputs hold 12 entries; *n_rows rows are written. */
+int eolc_constraints_fixed_rows(const double *c /*24*/, const int32_t *ci /*4*/, const double *v, int32_t n_nodes, int32_t eq_row0,
+                                int32_t *n_rows, int32_t *rows, int32_t *cols, double *vals, double *beq);
 /* number of contacts of the plan's last run (all scenes) */
 int eolc_cd_last_count(const eolc_cd_plan *plan);
 /* counters of the last run: candidate pair tests executed on the device (A: N*24, B: 8*F, C: E*12 after culls) */

@@ -497,6 +497,23 @@ def constraints_contact_rows(contacts, node_eol=None):
 # ---------------------------------------------------------------------------------------------------------------------
 # Per-step derived mesh data — numpy restatement, TEST INFRASTRUCTURE ONLY
 # ---------------------------------------------------------------------------------------------------------------------
+def constraints_fixed_rows(c, ci, v, eq_row0=0):
+    """Restatement of the fixed-corner rows of Constraints::fill (Constraints.cpp:114-119, :470-497): c (4, 6) = mask + prescribed
+    velocity of FixedList::c1..c4, ci (4,) node indices, v (N, 3) node velocities.  Returns (rows, cols, vals, beq) in push order."""
+    c = np.asarray(c, float).reshape(4, 6)
+    v = np.asarray(v, float).reshape(-1, 3)
+    rows, cols, vals, beq = [], [], [], []
+    eqsize = int(eq_row0)
+    for k in range(4):
+        if c[k, 0] != -1:
+            for j in range(3):
+                if c[k, j] == 1.0:
+                    rows.append(eqsize); cols.append(int(ci[k]) * 3 + j); vals.append(c[k, j])
+                    beq.append((1 - 0.01) * v[int(ci[k]), j] + c[k, j + 3])
+                    eqsize += 1
+    return np.array(rows, np.int32), np.array(cols, np.int32), np.array(vals), np.array(beq)
+
+
 def _arcsim_norm2(v):
     """vectors.hpp:108-109: dot() sums left to right starting from 0."""
     return (v[..., 0] * v[..., 0] + v[..., 1] * v[..., 1]) + v[..., 2] * v[..., 2]

@@ -40,6 +40,32 @@ def test_host_rows_match_oracle_on_golden_contacts(oracle, name):
     assert E.contact_rows(c[:0])[0].size == 0
 
 
+def test_fixed_corner_rows(oracle):
+    """eolc_constraints_fixed_rows == the fixed-corner part of Constraints::fill (Constraints.cpp:470-497), host only."""
+    import ctypes
+    from eol_cloth_b200 import capi
+    L = capi.lib()
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((50, 3))
+    cases = [
+        (np.array([[1, 1, 1, 0, 0, 0], [1, 1, 1, 0, 0, 0], [-1, 0, 0, 0, 0, 0], [-1, 0, 0, 0, 0, 0]], float), [3, 4, 0, 0], 0),   # simulationSettings.json: corners 3, 4 pinned
+        (np.array([[1, 0, 1, 0.1, 0.2, 0.3], [0, 0, 0, 1, 1, 1], [-1, 1, 1, 9, 9, 9], [0, 1, 0, -0.5, 0.25, 2]], float), [0, 7, 49, 21], 5),
+        (np.full((4, 6), -1.0), [0, 0, 0, 0], 2),
+    ]
+    for c, ci, row0 in cases:
+        ci = np.array(ci, np.int32)
+        n = ctypes.c_int32(0)
+        rows, cols, vals, beq = np.zeros(12, np.int32), np.zeros(12, np.int32), np.zeros(12), np.zeros(12)
+        capi.check(L.eolc_constraints_fixed_rows(capi.dptr(np.ascontiguousarray(c)), capi.iptr(ci), capi.dptr(np.ascontiguousarray(v)), 50, row0,
+                                                 ctypes.byref(n), capi.iptr(rows), capi.iptr(cols), capi.dptr(vals), capi.dptr(beq)))
+        r, cc, vv, bb = oracle.constraints_fixed_rows(c, ci, v, row0)
+        assert n.value == len(r)
+        assert np.array_equal(rows[:n.value], r) and np.array_equal(cols[:n.value], cc)
+        assert vals[:n.value].tobytes() == vv.tobytes() and beq[:n.value].tobytes() == bb.tobytes()
+    assert L.eolc_constraints_fixed_rows(capi.dptr(np.ascontiguousarray(cases[0][0])), capi.iptr(np.array([3, 99, 0, 0], np.int32)),
+                                         capi.dptr(np.ascontiguousarray(v)), 50, 0, ctypes.byref(n), capi.iptr(rows), capi.iptr(cols), capi.dptr(vals), capi.dptr(beq)) == -1
+
+
 @pytest.mark.gpu
 def test_device_rows_of_last_run(ctx, oracle):
     from eol_cloth_b200.collisions import make_obstacles

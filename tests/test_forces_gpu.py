@@ -296,7 +296,7 @@ def test_eol_256_line_and_batched(ctx, oracle):
     Mo = torch.full((2, plan.nnz[0]), float("nan"), dtype=torch.float64, device=dev)
     Ko = torch.full((2, plan.nnz[1]), float("nan"), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
-    plan.fill_dev(xs.data_ptr(), Xs.data_ptr(), MAT, GRAV, H, fo.data_ptr(), Mo.data_ptr(), Ko.data_ptr(), n_scenes=2)
+    plan.fill_dev(xs.data_ptr(), Xs.data_ptr(), MAT, GRAV, H, fo.data_ptr(), Mo.data_ptr(), Ko.data_ptr(), n_scenes=2, exact_symmetry=True)
     torch.cuda.synchronize()
     assert fo[0].cpu().numpy().tobytes() == f.tobytes() and Ko[0].cpu().numpy().tobytes() == Kv.tobytes() and Mo[0].cpu().numpy().tobytes() == Mv.tobytes()
     fb, Mb, Kb = plan.fill(x2, mesh["X"], MAT, GRAV, H)
@@ -443,3 +443,25 @@ def test_exact_symmetry_flag(ctx, gen, n):
     # one triangle is kept as it was (the lower node's blocks; the value array is row storage, read here as columns), the other mirrored
     assert min(abs(sp.triu(K1) - sp.triu(K0)).max(), abs(sp.tril(K1) - sp.tril(K0)).max()) == 0.0
     plan.close()
+
+
+def test_eol_host_fill_is_exactly_symmetric(ctx):
+    """With EoL nodes too the host entry hands out M and MDK as symmetric as the reference's: bit for bit everywhere the reference
+    mirrors its triplets — the Lagrangian blocks (pairs across two tiles through the symmetrisation pass; their rows carry Eulerian
+    columns, forces_eol.h) and the Eulerian / Lagrangian and Eulerian / Eulerian off-diagonal blocks (one source per mirrored pair).
+    The 2x2 DIAGONAL Eulerian blocks F^T K_vv F are pushed entry by entry by the reference (fillXMI / fillXB, Forces.cpp:127-136,
+    541-548), unsymmetrised, and are symmetric to rounding only there too (the oracle shows the same)."""
+    import scipy.sparse as sp
+    mesh = _eol_mesh("regular2", 64, "line")
+    N = 64 * 64
+    forces = E.Forces(ctx).fill(mesh, MAT, GRAV, H)
+    dof = forces.f.size
+    assert dof == 3 * N + 2 * 62
+    for name, A in (("M", forces.M), ("MDK", forces.MDK)):
+        S = sp.csc_matrix((A[2], A[1], A[0]), shape=(dof, dof))
+        D = (S - S.T).tocoo()
+        nz = D.data != 0
+        r, c = D.row[nz], D.col[nz]
+        in_diag_eulerian_block = (r >= 3 * N) & (c >= 3 * N) & ((r - 3 * N) // 2 == (c - 3 * N) // 2)
+        assert in_diag_eulerian_block.all(), name
+        assert abs(D.data).max(initial=0.0) <= 1e-13 * abs(S).max()
