@@ -504,18 +504,19 @@ def run_ours(args):
         ens = bench_ensemble(ctx, dev, stream, rank, world, barrier)     # every rank takes part
         if rank == 0:
             line["ensemble"] = ens
-    if rank == 0 and not args.no_cpu:
+    solo = world == 1      # the CPU baseline and the secondary objects are measured on the N = 1 line only
+    if rank == 0 and solo and not args.no_cpu:
         v, el, dt = cpu_forces_sample(256, 3)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"regular2 n=256 sheet ({el} elements), best of 3, {dt:.2f} s per fill",
                                 "note": "reference Compute*.cpp object code + restated Forces.cpp glue incl. triplets + setFromTriplets; single thread like the reference"}
-    if rank == 0 and not args.no_cd:
+    if rank == 0 and solo and not args.no_cd:
         line["cd"] = bench_cd(ctx, dev, stream)
-    if rank == 0 and not args.no_cd and S == 1:
+    if rank == 0 and solo and not args.no_cd and S == 1:
         line["consumer"] = bench_consumer(plan, dev, stream, f_d, M_d, K_d, N, nnzM, nnzK)
         line["consumer"]["normals"] = bench_normals(plan, dev, stream, x_d, N, F)
         line["eol"] = bench_eol(ctx, dev, stream, n, X, fn, es, x_d, X_d, ms_local)
-    if rank == 0 and S == 1 and not args.no_cpu:
+    if rank == 0 and solo and S == 1 and not args.no_cpu:
         line["plan_build_ms"] = bench_plan_build(ctx)
         hl = bench_host_layer(n)
         if hl is not None:
