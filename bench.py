@@ -634,7 +634,8 @@ def bench_plan_build(ctx):
             plan.close()
             best = dt if best is None else min(best, dt)
         out[label] = best * 1e3
-    out["what"] = "ms of host time for eolc_forces_plan_create (best of 2), threads = min(cores, 16)"
+    out["what"] = ("ms of host time for eolc_forces_plan_create (best of 2: the second build finds the bank-optimised templates in the "
+                   "process-wide cache, as a re-plan in a running simulation does), threads = min(cores, 16)")
     return out
 
 

@@ -25,6 +25,7 @@
 #include "forces_eol.h"
 #include "solve.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <numeric>
@@ -1037,6 +1038,14 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
         EOLC_REQUIRE(v[0] != v[1] && v[1] != v[2] && v[0] != v[2], "degenerate face (repeated node)");
     }
     EOLC_CUDA(cudaSetDevice(ctx->device));
+    const bool timing = getenv("EOLC_PLAN_TIMING") != nullptr;
+    auto tlast = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[plan_create] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tlast).count());
+        tlast = t;
+    };
     eolc_forces_plan *P = new eolc_forces_plan;
     P->ctx = ctx; P->device = ctx->device; P->N = N; P->F = F; P->E = E; P->dof = 3 * N;
     P->h_face_nodes.assign(face_nodes, face_nodes + 3 * (size_t)F);
@@ -1049,9 +1058,12 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
         P->h_iedge.insert(P->h_iedge.end(), s, s + 4);
     }
     P->Ei = (int32_t)(P->h_iedge.size() / 4);
+    lap("copy + validate");
     // node -> incident elements, built once: the pattern, the tiles and (later, on demand) the normals read it
     const NodeCSR csr(N, F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data());
+    lap("node csr");
     build_pattern(N, F, P->h_face_nodes.data(), P->Ei, P->h_iedge.data(), P->pat, &csr);
+    lap("pattern");
     P->nnzM = 9 * P->pat.nblkM; P->nnzK = 9 * P->pat.nblkK;
     if (P->nnzK > (int64_t)INT32_MAX) { delete P; set_error("nnz(MDK) exceeds int32 (Eigen StorageIndex is int)"); return EOLC_ERR_UNSUPPORTED; }
     cudaStream_t st = ctx->stream;
@@ -1070,6 +1082,7 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
     } else {
         rc = P->pipeline == 0 ? build_tiles_plan(P, X_hint, st, nullptr, &csr) : build_rows_plan(P, st);
     }
+    lap("tiles + upload");
     if (rc) { delete P; return rc; }
     *out = P;
     return EOLC_OK;

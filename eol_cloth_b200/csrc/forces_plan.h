@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <chrono>
@@ -1177,9 +1178,42 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
         const int iters = (int)std::max<long>(0, std::min<long>(budget, 400000 / (long)std::max<size_t>(1, unique_tmpl.size())));
         // templates are disjoint ranges of P.tmpl: one worker per slice of the list, same result for any worker count
         const int nw = std::max(1, std::min<int>(n_workers_hw(), (int)unique_tmpl.size()));
+        // The search is a deterministic function of the template's words and the iteration budget, and a remeshed or re-planned mesh
+        // brings mostly the same templates again: results are remembered process-wide (keyed by the words before the search).
+        struct BankCache { std::mutex mu; std::unordered_map<uint64_t, std::vector<std::pair<std::vector<uint32_t>, std::vector<uint32_t>>>> map; size_t words = 0; };
+        static BankCache cache;
+        auto tmpl_len = [&](size_t k) {     // words of stored template k: up to the next stored template (they are appended in order)
+            size_t end = P.tmpl.size();
+            for (const auto &u : unique_tmpl) if ((size_t)u.first * 4 > (size_t)unique_tmpl[k].first * 4) end = std::min(end, (size_t)u.first * 4);
+            return end - (size_t)unique_tmpl[k].first * 4;
+        };
+        const int eff_iters = iters < 20 ? 0 : iters;
         auto slice = [&](int w) {
-            for (size_t k = (size_t)w; k < unique_tmpl.size(); k += (size_t)nw)
-                optimize_template(P.tmpl.data() + (size_t)unique_tmpl[k].first * 4, unique_tmpl[k].second, iters < 20 ? 0 : iters);
+            for (size_t k = (size_t)w; k < unique_tmpl.size(); k += (size_t)nw) {
+                uint32_t *T = P.tmpl.data() + (size_t)unique_tmpl[k].first * 4;
+                const size_t len = unique_tmpl.size() <= 64 ? tmpl_len(k) : 0;   // cache only where templates are shared (structured meshes)
+                uint64_t h = 1469598103934665603ull ^ (uint64_t)eff_iters;
+                std::vector<uint32_t> before;
+                if (len) {
+                    before.assign(T, T + len);
+                    for (uint32_t x : before) { h ^= x; h *= 1099511628211ull; }
+                    std::lock_guard<std::mutex> g(cache.mu);
+                    auto it = cache.map.find(h);
+                    if (it != cache.map.end()) {
+                        bool hit = false;
+                        for (const auto &e : it->second) if (e.first == before) { memcpy(T, e.second.data(), len * 4); hit = true; break; }
+                        if (hit) continue;
+                    }
+                }
+                optimize_template(T, unique_tmpl[k].second, eff_iters);
+                if (len) {
+                    std::lock_guard<std::mutex> g(cache.mu);
+                    if (cache.words + 2 * len < ((size_t)64 << 20)) {      // at most 256 MB of remembered templates
+                        cache.map[h].push_back({std::move(before), std::vector<uint32_t>(T, T + len)});
+                        cache.words += 2 * len;
+                    }
+                }
+            }
         };
         if (nw == 1) slice(0);
         else {
