@@ -86,7 +86,9 @@ int eolc_mesh_edge_stencils(int32_t N, int32_t F, const int32_t *face_nodes, int
 /* Topology plan: CSR pattern of M and MDK + element->slot maps. Rebuild only after a remesh /
  * set_indices (src/Scene.cpp:87-90).  X_hint (2N, may be NULL) is used only to group nodes into
  * spatially compact tiles; results do not depend on it. eol_index (N, may be NULL): Node::EoL_index of the EoL nodes, -1 =
- * Lagrangian node; the indices must be distinct and EoL_Count = 1 + the largest (mesh.EoL_Count of the reference).  The
+ * Lagrangian node; the indices must be distinct and EoL_Count = 1 + the largest (mesh.EoL_Count of the reference).
+ * Limits (EOLC_ERR_UNSUPPORTED otherwise): at most 255 neighbours per node; the faces and bending stencils touching one node must fit
+ * one tile (about 150 faces + 150 stencils, e.g. a fan of valence 150); bending stencils may not repeat a node.  The
  * device consumers below work on both kinds of plan (block structure for Lagrangian plans, Eigen's scalar arrays for EOL plans). */
 int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *face_nodes, int32_t E,
                             const int32_t *edge_stencil, const int32_t *eol_index, const double *X_hint,

@@ -465,3 +465,4 @@ def test_eol_host_fill_is_exactly_symmetric(ctx):
         in_diag_eulerian_block = (r >= 3 * N) & (c >= 3 * N) & ((r - 3 * N) // 2 == (c - 3 * N) // 2)
         assert in_diag_eulerian_block.all(), name
         assert abs(D.data).max(initial=0.0) <= 1e-13 * abs(S).max()
+
