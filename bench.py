@@ -468,7 +468,9 @@ def run_ours(args):
                        "M is the previous step's matrix (depends on X and the density only) and is not copied again",
                 "full_fill": {"value": total_el_1 / (e2e_full_ms * 1e-3), "ms_per_step": e2e_full_ms, "d2h_bytes_per_step": d2h_full,
                               "what": "every step recomputes and copies M too (a step after remeshing)"},
-                "pageable_ms_per_step": e2e_pageable_ms, "checksum": e2e_checksum, "numa_nodes": numa_nodes()},
+                "pageable_ms_per_step": e2e_pageable_ms, "checksum": e2e_checksum, "numa_nodes": numa_nodes(),
+                "limiter": "PCIe: %.0f MB device-to-host per rank-step (%.1f GB/s here); at N > 1 the ranks' copies meet in the host's "
+                           "memory system (the box exposes %s NUMA node(s)), so per-rank time grows with N" % (d2h / 1e6, d2h / e2e_ms / 1e6, numa_nodes())},
         "gpu_launches": args.steps * plan.launches_per_fill * (1 if S == 1 else 1),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
