@@ -779,16 +779,26 @@ def bench_cd(ctx, dev, stream):
     torch.cuda.synchronize()
     dt_res = (time.perf_counter() - t) / reps
     dev_ms = e0.elapsed_time(e1) / reps
+    for _ in range(2):
+        plan.run_resident(x_d.data_ptr(), obs, 0, 0); rows = plan.contact_rows(); csr = plan.contact_rows_csr()
     t = time.perf_counter()
     for _ in range(reps):
         plan.run_resident(x_d.data_ptr(), obs, 0, 0)
         rows = plan.contact_rows()
     dt_rows = (time.perf_counter() - t) / reps
+    t = time.perf_counter()
+    for _ in range(reps):
+        plan.run_resident(x_d.data_ptr(), obs, 0, 0)
+        csr = plan.contact_rows_csr()
+    dt_csr = (time.perf_counter() - t) / reps
     out = {"workload": "CD2, regular2 512x512 over the simulationSettingsBox.json box (BASELINE configs[2])",
            "resident": {"ms_per_call": dt_res * 1e3, "stream_ms_per_call": dev_ms, "contacts_per_s": len(c) / dt_res,
                         "what": "eolc_cd_run_batched_resident_dev: records stay on the device, offsets come back (one stream sync)"},
-           "resident_plus_rows": {"ms_per_call": dt_rows * 1e3, "rows": int(len(rows[0])),
-                                  "what": "resident run + eolc_cd_contact_rows: the 112 B/contact inequality rows of Constraints::fill to the host instead of the 264 B records"},
+           "resident_plus_rows": {"ms_per_call": dt_rows * 1e3, "rows": int(len(rows[0])), "d2h_bytes": int(112 * len(rows[0])),
+                                  "what": "resident run + eolc_cd_contact_rows: the fixed-width 112 B/contact inequality rows of Constraints::fill to page-locked host arrays instead of the 264 B records"},
+           "resident_plus_rows_csr": {"ms_per_call": dt_csr * 1e3, "rows": int(len(csr[0]) - 1), "nnz": int(len(csr[1])),
+                                      "d2h_bytes": int(4 * len(csr[0]) + 12 * len(csr[1])), "contacts_per_s": len(c) / dt_csr,
+                                      "what": "resident run + eolc_cd_contact_rows_csr: the same rows compacted on the device (row_ptr / cols / vals = Aineq's triplet sequence)"},
            "contacts": int(len(c)), "ms_per_call": dt * 1e3, "contacts_per_s": len(c) / dt,
            "pair_tests_per_s": pair_tests / dt, "launches_per_call": launches,
            "timing": "wall clock around eolc_cd_run_dev incl. D2H of the contact list (%d B records, pinned caller buffer) and the host post-pass" % rec_bytes}

@@ -82,6 +82,7 @@ def lib():
     L.eolc_constraints_contact_rows.argtypes = [c_vp, ctypes.c_int32, c_vp, c_ip, c_ip, c_ip, c_dp]
     L.eolc_constraints_fixed_rows.argtypes = [c_dp, c_ip, c_dp, ctypes.c_int32, ctypes.c_int32, c_ip, c_ip, c_ip, c_dp, c_dp]
     L.eolc_cd_contact_rows.argtypes = [c_vp, c_vp, ctypes.c_int32, c_ip, c_ip, c_ip, c_dp]
+    L.eolc_cd_contact_rows_csr.argtypes = [c_vp, c_vp, ctypes.c_int32, ctypes.c_int32, c_ip, c_ip, c_ip, c_ip, c_dp]
     L.eolc_cd_last_count.argtypes = [c_vp]
     L.eolc_cd_last_stats.argtypes = [c_vp, ctypes.POINTER(ctypes.c_int64), c_ip]
     _LIB = L

@@ -93,16 +93,38 @@ class CollisionPlan:
         capi.check(capi.lib().eolc_cd_contacts_dev(self._h, ctypes.byref(p), ctypes.byref(n)))
         return p.value, n.value
 
+    def _row_buffers(self, cap):
+        """Page-locked result arrays kept across calls (allocating and first-touching 20 MB of fresh pageable memory per call cost
+        more than the device work and the copy together)."""
+        b = getattr(self, "_rowbuf", None)
+        if b is None or b[0] < cap:
+            for hb in (b[1:] if b else ()):
+                hb.free()
+            c = max(cap, 1) + max(cap, 1) // 4
+            b = self._rowbuf = (c, capi.HostBuffer(c + 1, np.int32), capi.HostBuffer(9 * c, np.int32), capi.HostBuffer(9 * c, np.float64))
+        return b
+
     def contact_rows(self, node_eol=None):
         """Inequality rows of the contacts of the LAST run, built on the device (Constraints.cpp:424-468): (row_nnz, cols, vals) with
-        9 slots per row in the reference's triplet order."""
-        cap = max(int(capi.lib().eolc_cd_last_count(self._h)), 1)
-        nnz, cols, vals = np.zeros(cap, np.int32), np.full(9 * cap, -1, np.int32), np.zeros(9 * cap)
+        9 slots per row in the reference's triplet order.  The arrays are views of buffers owned by the plan, valid until its
+        next contact_rows call."""
+        cap, nnz, cols, vals = self._row_buffers(int(capi.lib().eolc_cd_last_count(self._h)))
         n = ctypes.c_int32(0)
         eol = None if node_eol is None else np.ascontiguousarray(node_eol, dtype=np.uint8)
         capi.check(capi.lib().eolc_cd_contact_rows(self._h, None if eol is None else eol.ctypes.data_as(capi.c_vp), cap, ctypes.byref(n),
-                                                   capi.iptr(nnz), capi.iptr(cols), capi.dptr(vals)))
-        return nnz[:n.value], cols[:9 * n.value].reshape(-1, 9), vals[:9 * n.value].reshape(-1, 9)
+                                                   capi.iptr(nnz.array), capi.iptr(cols.array), capi.dptr(vals.array)))
+        return nnz.array[:n.value], cols.array[:9 * n.value].reshape(-1, 9), vals.array[:9 * n.value].reshape(-1, 9)
+
+    def contact_rows_csr(self, node_eol=None):
+        """The same rows compacted on the device: (row_ptr, cols, vals) — Aineq's triplets are (r, cols[q], vals[q]) for
+        row_ptr[r] <= q < row_ptr[r + 1], in the reference's push order.  Views of buffers owned by the plan."""
+        cap, rp, cols, vals = self._row_buffers(int(capi.lib().eolc_cd_last_count(self._h)))
+        n, nz = ctypes.c_int32(0), ctypes.c_int32(0)
+        eol = None if node_eol is None else np.ascontiguousarray(node_eol, dtype=np.uint8)
+        capi.check(capi.lib().eolc_cd_contact_rows_csr(self._h, None if eol is None else eol.ctypes.data_as(capi.c_vp), cap, 9 * cap,
+                                                       ctypes.byref(n), ctypes.byref(nz), capi.iptr(rp.array), capi.iptr(cols.array),
+                                                       capi.dptr(vals.array)))
+        return rp.array[:n.value + 1], cols.array[:nz.value], vals.array[:nz.value]
 
     def stats(self):
         pt, ln = ctypes.c_int64(), ctypes.c_int32()
@@ -111,6 +133,9 @@ class CollisionPlan:
 
     def close(self):
         if self._h:
+            for hb in (getattr(self, "_rowbuf", None) or ())[1:]:
+                hb.free()
+            self._rowbuf = None
             capi.lib().eolc_cd_plan_destroy(self._h)
             self._h = capi.c_vp()
 

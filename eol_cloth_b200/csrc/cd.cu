@@ -1244,6 +1244,44 @@ __global__ void k_contact_rows(int n, const eolc_contact *__restrict__ c, const 
     row_nnz[i] = contact_row(c[i], node_eol, cc, vv);
     for (int q = 0; q < 9; ++q) { cols[9 * (size_t)i + q] = cc[q]; vals[9 * (size_t)i + q] = vv[q]; }
 }
+// compact (CSR) form of the same rows.  Per contact: 3 nv entries and (nv > 0) rows, packed as entries | rows << 16 inside a block
+// (at most 2304 / 256 per 256 contacts); pass 1 stores the two sums of every block (bs[blk], bs[nblk + blk]), ONE scan of the 2 nblk
+// sums gives the block offsets (rows relative to off[nblk] = the entry total), pass 2 adds the in-block prefix and writes.
+__device__ __forceinline__ int rows_nv(const eolc_contact &c, const unsigned char *__restrict__ node_eol) {
+    const int c1 = c.count1, c2 = c.count2;
+    int nv = (c1 == 3 && c2 == 1) ? 1 : (c1 == 2 && c2 == 2) ? 2 : (c1 == 1 && c2 == 3) ? 3 : 0;
+    if (node_eol) for (int j = 0; j < nv; ++j) if (node_eol[c.verts2[j]]) nv = 0;
+    return nv;
+}
+__global__ void __launch_bounds__(256) k_rows_count(int n, int nblk, const eolc_contact *__restrict__ c, const unsigned char *__restrict__ node_eol,
+                                                    int32_t *__restrict__ bs) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int nv = i < n ? rows_nv(c[i], node_eol) : 0;
+    int cnt = 3 * nv | (nv > 0 ? 1 << 16 : 0);
+    __shared__ int s[8];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < 8; ++k) t += s[k];
+        bs[blockIdx.x] = t & 0xffff; bs[nblk + blockIdx.x] = t >> 16;
+    }
+}
+__global__ void __launch_bounds__(256) k_rows_write(int n, int nblk, const eolc_contact *__restrict__ c, const unsigned char *__restrict__ node_eol,
+                                                    const int32_t *__restrict__ off, int32_t *__restrict__ row_ptr, int32_t *__restrict__ cols,
+                                                    double *__restrict__ vals) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    int32_t cc[9]; double vv[9];
+    const int m = i < n ? contact_row(c[i], node_eol, cc, vv) : 0;
+    const int pre = block_excl_prefix(m | (m > 0 ? 1 << 16 : 0));
+    const int32_t at = off[blockIdx.x] + (pre & 0xffff), row = off[nblk + blockIdx.x] - off[nblk] + (pre >> 16);
+    if (m) {
+        row_ptr[row] = at;
+        for (int q = 0; q < m; ++q) { cols[at + q] = cc[q]; vals[at + q] = vv[q]; }
+    }
+    if (i == n - 1) row_ptr[off[2 * nblk] - off[nblk]] = off[nblk];
+}
 }  // namespace
 extern "C" {
 
@@ -1284,6 +1322,30 @@ int eolc_constraints_fixed_rows(const double *c, const int32_t *ci, const double
     return EOLC_OK;
 }
 
+}  // extern "C" (reopened below)
+// device -> caller array: straight DMA when the caller's array is page-locked, else through the plan's pinned staging (one memcpy
+// after the stream has been synchronised: `Pending` remembers it)
+namespace {
+struct Pending { void *dst; const void *src; size_t bytes; };
+template <typename T>
+int fetch(T *dst, const T *src_dev, size_t count, PinnedBuf<T> &stage, size_t stage_off, size_t stage_total, cudaStream_t st,
+          std::vector<Pending> &later) {
+    if (!count) return EOLC_OK;
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, dst) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    T *to = dst;
+    if (!pinned) {
+        EOLC_CUDA(stage.ensure(stage_total));   // sized for every array that shares it, so an earlier slice is never moved
+        to = stage.p + stage_off;
+        later.push_back({dst, to, count * sizeof(T)});
+    }
+    EOLC_CUDA(cudaMemcpyAsync(to, src_dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+    return EOLC_OK;
+}
+}  // namespace
+extern "C" {
+
 int eolc_cd_contact_rows(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t capacity_rows, int32_t *n_rows, int32_t *row_nnz, int32_t *cols,
                          double *vals) {
     EOLC_REQUIRE(plan && n_rows, "NULL argument");
@@ -1296,7 +1358,6 @@ int eolc_cd_contact_rows(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t ca
     EOLC_CUDA(cudaSetDevice(P->ctx->device));
     cudaStream_t st = P->ctx->stream;
     EOLC_CUDA(P->d_rows_i.ensure(10 * (size_t)n)); EOLC_CUDA(P->d_rows_v.ensure(9 * (size_t)n));
-    EOLC_CUDA(P->p_rows_i.ensure(10 * (size_t)n)); EOLC_CUDA(P->p_rows_v.ensure(9 * (size_t)n));
     const unsigned char *eol_dev = nullptr;
     if (node_eol) {
         EOLC_CUDA(P->d_eol.ensure((size_t)P->N));
@@ -1305,10 +1366,23 @@ int eolc_cd_contact_rows(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t ca
     }
     k_contact_rows<<<(n + 255) / 256, 256, 0, st>>>(n, P->d_out.p, eol_dev, P->d_rows_i.p, P->d_rows_i.p + n, P->d_rows_v.p);
     EOLC_CUDA(cudaGetLastError());
+    if (!node_eol) {
+        // no contact can be skipped: the device arrays ARE the result; they go straight into the caller's arrays
+        std::vector<Pending> later;
+        int rc = fetch(row_nnz, P->d_rows_i.p, (size_t)n, P->p_rows_i, 0, 10 * (size_t)n, st, later);
+        if (!rc) rc = fetch(cols, P->d_rows_i.p + n, 9 * (size_t)n, P->p_rows_i, (size_t)n, 10 * (size_t)n, st, later);
+        if (!rc) rc = fetch(vals, P->d_rows_v.p, 9 * (size_t)n, P->p_rows_v, 0, 9 * (size_t)n, st, later);
+        if (rc) return rc;
+        EOLC_CUDA(cudaStreamSynchronize(st));
+        for (const Pending &c : later) memcpy(c.dst, c.src, c.bytes);
+        *n_rows = n;
+        return EOLC_OK;
+    }
+    EOLC_CUDA(P->p_rows_i.ensure(10 * (size_t)n)); EOLC_CUDA(P->p_rows_v.ensure(9 * (size_t)n));
     EOLC_CUDA(cudaMemcpyAsync(P->p_rows_i.p, P->d_rows_i.p, 10 * (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     EOLC_CUDA(cudaMemcpyAsync(P->p_rows_v.p, P->d_rows_v.p, 9 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
     EOLC_CUDA(cudaStreamSynchronize(st));
-    // compaction of skipped contacts (EoL nodes) on the host: the common case has none and is two memcpys
+    // compaction of the skipped contacts (EoL nodes) on the host
     int32_t r = 0;
     const int32_t *hn = P->p_rows_i.p, *hc = P->p_rows_i.p + n;
     for (int i = 0; i < n; ++i) {
@@ -1319,6 +1393,53 @@ int eolc_cd_contact_rows(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t ca
         ++r;
     }
     *n_rows = r;
+    return EOLC_OK;
+}
+
+int eolc_cd_contact_rows_csr(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t capacity_rows, int32_t capacity_nnz, int32_t *n_rows,
+                             int32_t *nnz, int32_t *row_ptr, int32_t *cols, double *vals) {
+    EOLC_REQUIRE(plan && n_rows && nnz, "NULL argument");
+    eolc_cd_plan *P = plan;
+    const int n = P->last_total;
+    *n_rows = 0; *nnz = 0;
+    if (capacity_rows >= 0 && row_ptr) row_ptr[0] = 0;
+    if (n == 0) return EOLC_OK;
+    EOLC_REQUIRE((int64_t)n * 9 < INT32_MAX, "too many contacts for int32 row pointers");
+    EOLC_CUDA(cudaSetDevice(P->ctx->device));
+    cudaStream_t st = P->ctx->stream;
+    // device: per-block sums -> one exclusive scan -> compact write (3 launches)
+    const int nblk = (n + 255) / 256;
+    EOLC_CUDA(P->d_rows_i.ensure(4 * (size_t)nblk + 2 + (size_t)n + 1 + 9 * (size_t)n)); EOLC_CUDA(P->d_rows_v.ensure(9 * (size_t)n));
+    int32_t *bs = P->d_rows_i.p, *off = bs + 2 * nblk, *rp = off + (2 * nblk + 1), *cl = rp + (n + 1);   // cl: 9 n
+    const unsigned char *eol_dev = nullptr;
+    if (node_eol) {
+        EOLC_CUDA(P->d_eol.ensure((size_t)P->N));
+        EOLC_CUDA(cudaMemcpyAsync(P->d_eol.p, node_eol, (size_t)P->N, cudaMemcpyHostToDevice, st));
+        eol_dev = P->d_eol.p;
+    }
+    k_rows_count<<<nblk, 256, 0, st>>>(n, nblk, P->d_out.p, eol_dev, bs);
+    k_scan<<<1, 1024, 0, st>>>((size_t)2 * nblk, bs, off);
+    k_rows_write<<<nblk, 256, 0, st>>>(n, nblk, P->d_out.p, eol_dev, off, rp, cl, P->d_rows_v.p);
+    EOLC_CUDA(cudaGetLastError());
+    EOLC_CUDA(P->p_counter.ensure(2));
+    EOLC_CUDA(cudaMemcpyAsync(P->p_counter.p, off + nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaMemcpyAsync(P->p_counter.p + 1, off + 2 * nblk, sizeof(int), cudaMemcpyDeviceToHost, st));
+    EOLC_CUDA(cudaStreamSynchronize(st));
+    const int32_t total = P->p_counter.p[0], rows = P->p_counter.p[1] - total;
+    *n_rows = rows; *nnz = total;
+    if (rows > capacity_rows || total > capacity_nnz) {
+        set_error("row buffers too small: need %d rows / %d entries, capacity %d / %d", rows, total, capacity_rows, capacity_nnz);
+        return EOLC_ERR_CAPACITY;
+    }
+    EOLC_REQUIRE(row_ptr && (total == 0 || (cols && vals)), "NULL argument");
+    std::vector<Pending> later;
+    const size_t stage_i = (size_t)rows + 1 + (size_t)total;
+    int rc = fetch(row_ptr, rp, (size_t)rows + 1, P->p_rows_i, 0, stage_i, st, later);
+    if (!rc) rc = fetch(cols, cl, (size_t)total, P->p_rows_i, (size_t)rows + 1, stage_i, st, later);
+    if (!rc) rc = fetch(vals, P->d_rows_v.p, (size_t)total, P->p_rows_v, 0, (size_t)total, st, later);
+    if (rc) return rc;
+    EOLC_CUDA(cudaStreamSynchronize(st));
+    for (const Pending &c : later) memcpy(c.dst, c.src, c.bytes);
     return EOLC_OK;
 }
 

@@ -227,6 +227,13 @@ int eolc_constraints_contact_rows(const eolc_contact *contacts, int32_t n, const
                                   int32_t *row_nnz, int32_t *cols, double *vals);
 int eolc_cd_contact_rows(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t capacity_rows, int32_t *n_rows, int32_t *row_nnz,
                          int32_t *cols, double *vals);
+/* The same rows in compressed (CSR) form, compacted on the device: row r holds entries row_ptr[r] .. row_ptr[r + 1) of cols / vals —
+ * the reference's exact Aineq_ triplet sequence (row = running ineqsize), 40 B per (3,1) contact instead of 112 B fixed-width or
+ * the 264 B record.  *n_rows and *nnz are always set; EOLC_ERR_CAPACITY (nothing copied) if they exceed capacity_rows /
+ * capacity_nnz (row_ptr holds capacity_rows + 1 entries; nnz <= 9 * eolc_cd_last_count).  Page-locked arrays (eolc_host_alloc) are
+ * the DMA targets themselves; pageable ones cost a staging copy. */
+int eolc_cd_contact_rows_csr(eolc_cd_plan *plan, const uint8_t *node_eol, int32_t capacity_rows, int32_t capacity_nnz,
+                             int32_t *n_rows, int32_t *nnz, int32_t *row_ptr, int32_t *cols, double *vals);
 /* Constraints::fill, fixed-corner part (src/Constraints.cpp:114-119, :470-497): the equality rows of the four corner records of a
  * FixedList (src/FixedList.h:32-37).  corner k: c[6 k .. 6 k + 5] = (mask x, y, z, prescribed velocity x, y, z), node index ci[k];
  * a corner with c[6 k] == -1 is absent, a component with mask == 1.0 gets one row

@@ -1,11 +1,13 @@
 """Contact part of Constraints::fill (Constraints.cpp:424-468): the inequality rows built from a CD2 contact list.
 Integer columns and FP64 values (one negation / one multiply each) are compared bit for bit with the restatement in the oracle."""
+import ctypes
 import os
 
 import numpy as np
 import pytest
 
 import eol_cloth_b200 as E
+from eol_cloth_b200 import capi
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -66,6 +68,14 @@ def test_fixed_corner_rows(oracle):
                                          capi.dptr(np.ascontiguousarray(v)), 50, 0, ctypes.byref(n), capi.iptr(rows), capi.iptr(cols), capi.dptr(vals), capi.dptr(beq)) == -1
 
 
+def _compare_csr(rows_ref, row_ptr, cols, vals):
+    """CSR rows == the oracle's rows, entry for entry (the reference's triplet sequence), bit for bit."""
+    assert len(row_ptr) == len(rows_ref) + 1 and row_ptr[0] == 0
+    assert np.array_equal(np.diff(row_ptr), [len(r) for r in rows_ref])
+    assert [int(c) for c in cols] == [c for r in rows_ref for c, _ in r]
+    assert np.asarray(vals).tobytes() == np.array([v for r in rows_ref for _, v in r], dtype=np.float64).tobytes()
+
+
 @pytest.mark.gpu
 def test_device_rows_of_last_run(ctx, oracle):
     from eol_cloth_b200.collisions import make_obstacles
@@ -79,9 +89,21 @@ def test_device_rows_of_last_run(ctx, oracle):
     ref = oracle.constraints_contact_rows(contacts)
     _compare(ref, *plan.contact_rows())
     _compare(ref, *E.contact_rows(contacts))
+    _compare_csr(ref, *plan.contact_rows_csr())
     eol = np.zeros(X.shape[0], np.uint8)
     eol[contacts["verts2"][::2, 0]] = 1
-    _compare(oracle.constraints_contact_rows(contacts, eol.astype(bool)), *plan.contact_rows(eol))
+    ref_eol = oracle.constraints_contact_rows(contacts, eol.astype(bool))
+    assert len(ref_eol) < len(ref)
+    _compare(ref_eol, *plan.contact_rows(eol))
+    _compare_csr(ref_eol, *plan.contact_rows_csr(eol))
+    # pageable result arrays and the capacity error of the C entry
+    L, n, nz = capi.lib(), ctypes.c_int32(0), ctypes.c_int32(0)
+    rp, cc, vv = np.zeros(len(contacts) + 1, np.int32), np.zeros(9 * len(contacts), np.int32), np.zeros(9 * len(contacts))
+    assert L.eolc_cd_contact_rows_csr(plan._h, None, len(contacts), 9 * len(contacts), ctypes.byref(n), ctypes.byref(nz), capi.iptr(rp),
+                                      capi.iptr(cc), capi.dptr(vv)) == 0
+    _compare_csr(ref, rp[:n.value + 1], cc[:nz.value], vv[:nz.value])
+    assert L.eolc_cd_contact_rows_csr(plan._h, None, 3, 9, ctypes.byref(n), ctypes.byref(nz), capi.iptr(rp), capi.iptr(cc), capi.dptr(vv)) == -3
+    assert n.value == len(contacts) and nz.value == sum(len(r) for r in ref)
 
 
 @pytest.mark.gpu
@@ -103,3 +125,4 @@ def test_resident_run_feeds_device_rows(ctx, oracle):
     ptr, n = plan.contacts_dev()
     assert n == len(host_list) and ptr
     _compare(oracle.constraints_contact_rows(host_list), *plan.contact_rows())
+    _compare_csr(oracle.constraints_contact_rows(host_list), *plan.contact_rows_csr())
