@@ -236,11 +236,15 @@ __global__ void __launch_bounds__(THREADS) k_integrate_X(int N, const int32_t *_
 // ---- per-step derived mesh data ------------------------------------------------------------------------------
 // face->n of compute_ws_data(Face*), /root/reference/src/external/ArcSim/mesh.cpp:135-140: normalize(cross(x1 - x0, x2 - x0)), with
 // ArcSim's normalize (vectors.hpp:111: the zero vector stays zero) and its sequential dot (vectors.hpp:108).  No FMA contraction here
-// (explicit _rn intrinsics) so that the normals match the host arithmetic to the last bit but one (sqrt and the division are IEEE).
+// (explicit _rn intrinsics; sqrt and the division are IEEE) so that the normals match the host arithmetic bit for bit.
+// A vector divided by a scalar is u * (1 / a) in ArcSim (vectors.hpp:104; the _mm256_div_pd specialisation at :130 sits behind
+// `#if defined(_AVX)`, which no compiler and no line of the reference's CMakeLists.txt defines): one reciprocal, three products —
+// NOT three divisions, which differ in the last bit (found by tests/test_forces_ref_pin.py against the reference's own code).
 __device__ __forceinline__ void ws_normalize(double &a, double &b, double &c) {
     const double m = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c)));
     if (m == 0.0) { a = b = c = 0.0; return; }
-    a = a / m; b = b / m; c = c / m;
+    const double inv = __ddiv_rn(1.0, m);
+    a = __dmul_rn(inv, a); b = __dmul_rn(inv, b); c = __dmul_rn(inv, c);
 }
 __device__ __forceinline__ void ws_cross(const double *u, const double *v, double *w) {
     w[0] = __dsub_rn(__dmul_rn(u[1], v[2]), __dmul_rn(u[2], v[1]));
@@ -276,7 +280,8 @@ __global__ void __launch_bounds__(THREADS) k_node_normals(int32_t N, const int32
             const double l1 = __dadd_rn(__dadd_rn(__dmul_rn(e1[0], e1[0]), __dmul_rn(e1[1], e1[1])), __dmul_rn(e1[2], e1[2]));
             const double l2 = __dadd_rn(__dadd_rn(__dmul_rn(e2[0], e2[0]), __dmul_rn(e2[1], e2[1])), __dmul_rn(e2[2], e2[2]));
             const double den = __dmul_rn(__dmul_rn(2.0, l1), l2);
-            for (int k = 0; k < 3; ++k) n[k] = __dadd_rn(n[k], w[k] / den);
+            const double inv = __ddiv_rn(1.0, den);                       // cross(e1, e2) / den = cross * (1 / den), vectors.hpp:104
+            for (int k = 0; k < 3; ++k) n[k] = __dadd_rn(n[k], __dmul_rn(inv, w[k]));
         }
         ws_normalize(n[0], n[1], n[2]);
         out[3 * a] = n[0]; out[3 * a + 1] = n[1]; out[3 * a + 2] = n[2];

@@ -526,11 +526,13 @@ def _arcsim_cross(u, v):
 
 
 def _arcsim_normalize(v):
-    """vectors.hpp:111: m == 0 ? 0 : u / m."""
+    """vectors.hpp:111: m == 0 ? 0 : u / m, and u / m is u * (1 / m) (vectors.hpp:104: one reciprocal, then products; the true-division
+    specialisation at :130 is behind `#if defined(_AVX)`, which nothing defines).  Pinned by tests/test_forces_ref_pin.py against
+    ArcSim's own compiled code."""
     m = np.sqrt(_arcsim_norm2(v))
     out = np.zeros_like(v)
     nz = m != 0
-    out[nz] = v[nz] / m[nz][:, None]
+    out[nz] = (1.0 / m[nz])[:, None] * v[nz]
     return out
 
 
@@ -545,7 +547,106 @@ def mesh_normals(face_nodes, x):
     for j in range(3):
         e1 = x[fn[:, (j + 1) % 3]] - x[fn[:, j]]
         e2 = x[fn[:, (j + 2) % 3]] - x[fn[:, j]]
-        contrib[:, j] = _arcsim_cross(e1, e2) / ((2 * _arcsim_norm2(e1)) * _arcsim_norm2(e2))[:, None]
+        contrib[:, j] = (1.0 / ((2 * _arcsim_norm2(e1)) * _arcsim_norm2(e2)))[:, None] * _arcsim_cross(e1, e2)   # u / a = u * (1 / a)
     n = np.zeros_like(x)
     np.add.at(n, fn.reshape(-1), contrib.reshape(-1, 3))      # unbuffered, in index order: per node, faces ascending
     return face_n, _arcsim_normalize(n)
+
+
+# ---- the reference's own Forces::fill (oracle/_ref/libforces_ref.so: Forces.cpp, UtilEOL.cpp, conversions.cpp, Compute*.cpp and ArcSim's
+# mesh / geometry / util / vectors / transformation .cpp compiled UNMODIFIED against oracle/mini_eigen by oracle/Makefile; the prebuilt
+# file travels to the GPU box).  adapter=True: libadapter_forces.so, the same driver with adapter/Forces_fill_b200.cpp in place of
+# Forces.cpp — the drop-in body, executed on the GPU ------------------------------------------------------------------------------
+def ref_forces_lib(adapter=False):
+    name = "libadapter_forces.so" if adapter else "libforces_ref.so"
+    if name in _REFLIBS:
+        return _REFLIBS[name]
+    path = os.path.join(_HERE, "_ref", name)
+    if not os.path.exists(path):
+        build()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing and /root/reference is not here to build it from")
+    L = ctypes.CDLL(path)
+    L.ref_forces_fill.restype = ctypes.c_void_p
+    L.ref_forces_fill.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_dp, c_ip, c_dp, c_dp, ctypes.c_double]
+    L.ref_forces_mesh.restype = ctypes.c_void_p
+    L.ref_forces_mesh.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_dp]
+    L.ref_forces_free.argtypes = [ctypes.c_void_p]
+    L.ref_forces_refill.argtypes = [ctypes.c_void_p, c_dp, c_dp]
+    L.ref_forces_dof.argtypes = [ctypes.c_void_p]
+    L.ref_forces_eol_cutoff.argtypes = [ctypes.c_void_p]
+    L.ref_forces_f.restype = c_dp
+    L.ref_forces_f.argtypes = [ctypes.c_void_p]
+    L.ref_forces_nnz.restype = ctypes.c_int64
+    L.ref_forces_nnz.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    for nm, rt in (("outer", c_ip), ("inner", c_ip), ("vals", c_dp)):
+        fn = getattr(L, "ref_forces_" + nm)
+        fn.restype = rt
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.ref_forces_n_edges.argtypes = [ctypes.c_void_p]
+    L.ref_forces_edge_stencils.argtypes = [ctypes.c_void_p, c_ip]
+    L.ref_forces_normals.argtypes = [ctypes.c_void_p, c_dp, c_dp, c_dp]
+    _REFLIBS[name] = L
+    return L
+
+
+def _ref_forces_result(L, r):
+    dof = L.ref_forces_dof(r)
+    out = {"dof": dof, "EoL_cutoff": L.ref_forces_eol_cutoff(r), "f": np.ctypeslib.as_array(L.ref_forces_f(r), (dof,)).copy()}
+    for which, name in ((0, "M"), (1, "MDK")):
+        nnz = L.ref_forces_nnz(r, which)
+        outer = np.ctypeslib.as_array(L.ref_forces_outer(r, which), (dof + 1,)).copy()
+        inner = np.ctypeslib.as_array(L.ref_forces_inner(r, which), (max(nnz, 1),))[:nnz].copy()
+        vals = np.ctypeslib.as_array(L.ref_forces_vals(r, which), (max(nnz, 1),))[:nnz].copy()
+        out[name] = (outer, inner, vals)
+    es = np.zeros((max(L.ref_forces_n_edges(r), 1), 4), np.int32)
+    L.ref_forces_edge_stencils(r, _i(es))
+    out["edge_stencil"] = es[:L.ref_forces_n_edges(r)]
+    return out
+
+
+def ref_forces_fill(face_nodes, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_DEFAULT, h=H_DEFAULT, eol_index=None, adapter=False, more_steps=()):
+    """The reference's Forces::fill (Forces.cpp:912-930), run as compiled from its own sources on a mesh built the way Cloth::build
+    builds it (the edges come from ArcSim's Mesh::add(Face*)).  Returns dict(dof, EoL_cutoff, f, M=(outer, inner, vals), MDK=...,
+    edge_stencil).  adapter=True: the same call reaches adapter/Forces_fill_b200.cpp instead (needs a CUDA device).
+    more_steps: sequence of (x, X or None): Forces::fill is called again on the SAME Mesh / Forces objects after each update; the
+    result is then a list of dicts (one per fill)."""
+    L = ref_forces_lib(adapter)
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    X = _f64(X).reshape(-1, 2)
+    N = x.shape[0]
+    eol = None if eol_index is None else _i32(eol_index).reshape(N)
+    r = L.ref_forces_fill(N, face_nodes.shape[0], _i(face_nodes), _d(x), _d(X), None if eol is None else _i(eol), _d(_f64(mat)),
+                          _d(_f64(grav)), float(h))
+    try:
+        outs = [_ref_forces_result(L, r)]
+        for xs, Xs in more_steps:
+            xs = _f64(xs).reshape(N, 3)
+            Xs = None if Xs is None else _f64(Xs).reshape(N, 2)
+            L.ref_forces_refill(r, _d(xs), None if Xs is None else _d(Xs))
+            outs.append(_ref_forces_result(L, r))
+    finally:
+        L.ref_forces_free(r)
+    return outs if more_steps else outs[0]
+
+
+def ref_mesh_data(face_nodes, x, X, x_new=None):
+    """ArcSim's own mesh code on flat arrays: (edge_stencil in mesh.edges order, face normals, node normals) after compute_ws_data
+    (mesh.cpp:135-151, geometry.cpp:302-316), optionally with new positions written to Node::x first."""
+    L = ref_forces_lib()
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    X = _f64(X).reshape(-1, 2)
+    N, F = x.shape[0], face_nodes.shape[0]
+    r = L.ref_forces_mesh(N, F, _i(face_nodes), _d(x), _d(X))
+    try:
+        E = L.ref_forces_n_edges(r)
+        es = np.zeros((max(E, 1), 4), np.int32)
+        L.ref_forces_edge_stencils(r, _i(es))
+        fn, nn = np.zeros((max(F, 1), 3)), np.zeros((max(N, 1), 3))
+        xn = None if x_new is None else _f64(x_new).reshape(N, 3)
+        L.ref_forces_normals(r, None if xn is None else _d(xn), _d(fn), _d(nn))
+    finally:
+        L.ref_forces_free(r)
+    return es[:E], fn[:F], nn[:N]

@@ -1,6 +1,8 @@
-"""Generates tests/golden/*.npz.  forces_* / normals_*: from the CPU oracle (reference Compute*.cpp / raytri.cpp object code +
-restated glue).  cd_*: from THE REFERENCE'S OWN collision code, oracle/_ref/libbtc_ref.so = boxTriCollision.cpp + Collisions.cpp +
-raytri.cpp compiled unmodified against oracle/mini_eigen (oracle/Makefile); `source` in the file says so.
+"""Generates tests/golden/*.npz — all of them from THE REFERENCE'S OWN CODE, compiled unmodified against oracle/mini_eigen by
+oracle/Makefile; `source` in each file names the library:
+  forces_* / normals_*: oracle/_ref/libforces_ref.so = Forces.cpp + UtilEOL.cpp + conversions.cpp + Compute*.cpp + ArcSim's mesh /
+                        geometry / util / vectors / transformation .cpp  (Forces::fill on a mesh built like Cloth::build; compute_ws_data);
+  cd_*:                 oracle/_ref/libbtc_ref.so = boxTriCollision.cpp + Collisions.cpp + raytri.cpp.
 
 Run in the build container (where /root/reference exists):  python tests/golden/make_golden.py
 The fixtures pin (a) the oracle against silent drift and (b) the CUDA path on the GPU box, where the reference
@@ -31,8 +33,9 @@ def forces_case(gen, n, seed, eol=None):
     X, fn = getattr(E.meshgen, gen)(n)
     es = E.meshgen.edge_stencils(X.shape[0], fn)
     x = E.meshgen.drape_state(X, seed=seed)
-    r = O.forces_fill(fn, es, x, X, eol_index=eol)
-    return dict(f=r["f"], M_outer=r["M"][0], M_inner=r["M"][1], M_vals=r["M"][2], K_outer=r["MDK"][0],
+    r = O.ref_forces_fill(fn, x, X, eol_index=eol)
+    assert np.array_equal(r["edge_stencil"], es)
+    return dict(source=np.array("libforces_ref"), f=r["f"], M_outer=r["M"][0], M_inner=r["M"][1], M_vals=r["M"][2], K_outer=r["MDK"][0],
                 K_inner=r["MDK"][1], K_vals=r["MDK"][2])
 
 
@@ -53,8 +56,8 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "forces_regular2_n12.npz"), **forces_case("regular2", 12, 0))
     np.savez_compressed(os.path.join(HERE, "forces_build4_n7.npz"), **forces_case("build4", 7, 1))
     np.savez_compressed(os.path.join(HERE, "forces_eol_regular2_n12.npz"), **forces_case("regular2", 12, 2, eol_line(12)))
-    fn_, nn_ = O.mesh_normals(E.meshgen.build4(7)[1], E.meshgen.drape_state(E.meshgen.build4(7)[0], seed=1))
-    np.savez_compressed(os.path.join(HERE, "normals_build4_n7.npz"), face_n=fn_, node_n=nn_)
+    _, fn_, nn_ = O.ref_mesh_data(E.meshgen.build4(7)[1], E.meshgen.drape_state(E.meshgen.build4(7)[0], seed=1), E.meshgen.build4(7)[0])
+    np.savez_compressed(os.path.join(HERE, "normals_build4_n7.npz"), source=np.array("libforces_ref"), face_n=fn_, node_n=nn_)
     np.savez_compressed(os.path.join(HERE, "cd_regular2_n24.npz"), **cd_case("regular2", 24, E.meshgen.BOX_CENTRE, 0))
     c3b = np.array([0.9175, -0.25, -0.549])
     np.savez_compressed(os.path.join(HERE, "cd_build4_n16_corner.npz"), **cd_case("build4", 16, c3b, 1, points=True))

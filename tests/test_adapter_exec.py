@@ -55,3 +55,65 @@ def test_adapter_points_two_boxes_and_repeated_calls(oracle):
     X2, fn2 = E.meshgen.build4(14)
     x2 = E.meshgen.box_scene_state(X2, seed=1, centre=C3B)
     _same(oracle.ref_cd(fn2, x2, THR, None, None, whd[:1], Em[:1], 0), oracle.ref_cd(fn2, x2, THR, None, None, whd[:1], Em[:1], 0, adapter=True), "second mesh")
+
+
+# ---- Forces::fill -------------------------------------------------------------------------------------------------------------------
+# adapter/Forces_fill_b200.cpp — the body a maintainer puts in place of Forces.cpp:912-930 — compiled against the reference's own Forces.h
+# (mesh.hpp, <Eigen/Dense>, <Eigen/Sparse> = oracle/mini_eigen) and linked with the reference's ArcSim mesh code and the same driver as
+# libforces_ref.so (oracle/_ref/libadapter_forces.so).  The call goes
+#     Mesh (built by ArcSim's own Mesh::add) + Material + Vector3d  ->  Forces::fill (adapter)  ->  eolc::host::flatten / Forces  ->  C ABI  ->  GPU
+# and comes back in the members Eigen::VectorXd f, Eigen::SparseMatrix<double> M, MDK, int EoL_cutoff of the reference's class Forces.
+# It must equal the reference's own Forces::fill (libforces_ref.so): identical compressed index arrays, values within 1e-10.
+from util import assert_close_tol, block_row_scale  # noqa: E402
+
+
+def _same_fill(ref, got, n_nodes, what):
+    assert ref["dof"] == got["dof"] and ref["EoL_cutoff"] == got["EoL_cutoff"], what
+    for k in ("M", "MDK"):
+        assert np.array_equal(ref[k][0], got[k][0]) and np.array_equal(ref[k][1], got[k][1]), f"{what}: {k} index arrays differ"
+        assert_close_tol(got[k][2], ref[k][2], block_row_scale(ref[k][0], ref[k][2], n_nodes), 1e-10, f"{what} {k}")
+    assert_close_tol(got["f"], ref["f"], np.abs(ref["f"]).max(), 1e-10, f"{what} f")
+
+
+@pytest.mark.parametrize("gen,n", [("regular2", 24), ("build4", 13), ("regular2", 3)])
+def test_adapter_forces_fill_equals_reference(oracle, gen, n):
+    X, fn = getattr(E.meshgen, gen)(n)
+    x = E.meshgen.drape_state(X, seed=n)
+    ref = oracle.ref_forces_fill(fn, x, X)
+    got = oracle.ref_forces_fill(fn, x, X, adapter=True)
+    _same_fill(ref, got, X.shape[0], f"{gen}{n}")
+    K = got["MDK"]
+    import scipy.sparse as sp
+    A = sp.csc_matrix((K[2], K[1], K[0]), shape=(got["dof"], got["dof"]))
+    assert abs(A - A.T).max() == 0.0          # exactly symmetric, like the reference's mirrored triplets
+
+
+def test_adapter_forces_fill_steps_on_the_same_objects(oracle):
+    """Three fills on the same Mesh / Forces objects: the adapter keeps its plan and page-locked buffers; the second step moves x only
+    (M is not recomputed nor copied: the member must still hold it), the third also moves the material coordinates (M changes)."""
+    X, fn = E.meshgen.regular2(20)
+    rng = np.random.default_rng(9)
+    x = E.meshgen.drape_state(X, seed=1)
+    x2 = x + 1e-3 * rng.standard_normal(x.shape)
+    X3 = X + 2e-4 * rng.standard_normal(X.shape)
+    steps = [(x2, None), (x2, X3)]
+    refs = oracle.ref_forces_fill(fn, x, X, more_steps=steps)
+    gots = oracle.ref_forces_fill(fn, x, X, adapter=True, more_steps=steps)
+    for i, (r, g) in enumerate(zip(refs, gots)):
+        _same_fill(r, g, X.shape[0], f"step {i}")
+    assert refs[0]["M"][2].tobytes() == refs[1]["M"][2].tobytes() != refs[2]["M"][2].tobytes()
+    assert gots[0]["M"][2].tobytes() == gots[1]["M"][2].tobytes() != gots[2]["M"][2].tobytes()
+
+
+def test_adapter_forces_fill_with_eol_nodes(oracle):
+    """EoL nodes: dof = 3N + 2 EoL_Count, Eulerian blocks, EoL_cutoff — through the adapter."""
+    X, fn = E.meshgen.regular2(16)
+    N = X.shape[0]
+    eol = np.full(N, -1, np.int32)
+    line = np.arange(1, 15) * 16 + 8
+    eol[line] = np.arange(line.size)
+    x = E.meshgen.drape_state(X, seed=2)
+    ref = oracle.ref_forces_fill(fn, x, X, eol_index=eol)
+    got = oracle.ref_forces_fill(fn, x, X, eol_index=eol, adapter=True)
+    assert ref["dof"] == 3 * N + 2 * line.size
+    _same_fill(ref, got, N, "EOL line")

@@ -18,9 +18,12 @@ def _literal(fn, x):
             d += a[i] * b[i]
         return d
     def cross(u, v): return [u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]]
+    def div(u, a):          # vectors.hpp:104: u / a is u * (1 / a) — one reciprocal, then products (pinned to the reference's own
+        r = 1 / a           # compiled code by tests/test_forces_ref_pin.py::test_normals_of_compute_ws_data)
+        return [r * u[0], r * u[1], r * u[2]]
     def normalize(u):
         m = math.sqrt(dot(u, u))
-        return [0.0, 0.0, 0.0] if m == 0 else [u[0] / m, u[1] / m, u[2] / m]
+        return [0.0, 0.0, 0.0] if m == 0 else div(u, m)
     x = x.tolist()
     face_n = [normalize(cross(sub(x[f[1]], x[f[0]]), sub(x[f[2]], x[f[0]]))) for f in fn.tolist()]
     adjf = [[] for _ in x]
@@ -34,8 +37,8 @@ def _literal(fn, x):
             f = fn[i].tolist()
             j = f.index(a); j1 = (j + 1) % 3; j2 = (j + 2) % 3
             e1 = sub(x[f[j1]], x[a]); e2 = sub(x[f[j2]], x[a])
-            c = cross(e1, e2); den = 2 * dot(e1, e1) * dot(e2, e2)
-            n = [n[0] + c[0] / den, n[1] + c[1] / den, n[2] + c[2] / den]
+            c = div(cross(e1, e2), 2 * dot(e1, e1) * dot(e2, e2))
+            n = [n[0] + c[0], n[1] + c[1], n[2] + c[2]]
         node_n.append(normalize(n))
     return np.array(face_n).reshape(-1, 3), np.array(node_n).reshape(-1, 3)
 
@@ -60,9 +63,16 @@ def test_oracle_normals_match_the_literal_loops(oracle, gen, n, isolated):
 
 
 def test_oracle_normals_flat_sheet(oracle):
-    X, fn = E.meshgen.regular2(6)
-    fa, na = oracle.mesh_normals(fn, np.c_[X, np.zeros(len(X))])
-    assert np.array_equal(fa, np.tile([0.0, 0.0, 1.0], (len(fn), 1))) and np.array_equal(na, np.tile([0.0, 0.0, 1.0], (len(X), 1)))
+    """A flat sheet: normals (0, 0, 1) up to ONE rounding — ArcSim normalises with u * (1 / m) (vectors.hpp:104), and (1 / m) * m need
+    not be exactly 1 (n = 6: m = 0.04, z = 1 + 2^-52); the reference's own compiled code gives the same bits."""
+    for n in (6, 9):
+        X, fn = E.meshgen.regular2(n)
+        x = np.c_[X, np.zeros(len(X))]
+        fa, na = oracle.mesh_normals(fn, x)
+        assert np.all(fa[:, :2] == 0) and np.all(na[:, :2] == 0)
+        assert np.abs(fa[:, 2] - 1).max() <= 2.3e-16 and np.abs(na[:, 2] - 1).max() <= 2.3e-16
+        _, fr, nr = oracle.ref_mesh_data(fn, x, X)
+        assert fa.tobytes() == fr.tobytes() and na.tobytes() == nr.tobytes()
 
 
 @pytest.mark.gpu
