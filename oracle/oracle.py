@@ -650,3 +650,61 @@ def ref_mesh_data(face_nodes, x, X, x_new=None):
     finally:
         L.ref_forces_free(r)
     return es[:E], fn[:F], nn[:N]
+
+
+# ---- the reference's own Constraints::fill (oracle/_ref/libconstraints_ref.so: Constraints.cpp + Collisions.cpp + boxTriCollision.cpp +
+# Box.cpp + Obstacles.cpp + ... compiled UNMODIFIED, oracle/Makefile) ------------------------------------------------------------
+def ref_constraints_fill(face_nodes, x, X, v, threshold, pxyz=None, pnorms=None, box_whd=None, box_E=None, fixed_c=None, fixed_ci=None,
+                         corner_id=None, h=H_DEFAULT):
+    """Constraints::fill (Constraints.cpp:122-513) as compiled from the reference's own sources: CD2 inside (:423), the contact rows
+    (:424-468), the fixed-corner rows (:470-497).  Returns dict(Aineq=(n_rows, outer, inner, vals) [column-major compressed, as
+    Eigen stores it], bineq, Aeq=..., beq, hasFixed, hasCollisions).  corner_id: see oracle/ref_constraints_driver.cpp."""
+    name = "libconstraints_ref.so"
+    if name not in _REFLIBS:
+        path = os.path.join(_HERE, "_ref", name)
+        if not os.path.exists(path):
+            build()
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing and /root/reference is not here to build it from")
+        L = ctypes.CDLL(path)
+        L.ref_constraints_fill.restype = ctypes.c_void_p
+        L.ref_constraints_fill.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_dp, c_dp, c_ip, ctypes.c_double, ctypes.c_int, c_dp, c_dp,
+                                           ctypes.c_int, c_dp, c_dp, c_dp, c_ip, ctypes.c_double]
+        L.ref_constraints_free.argtypes = [ctypes.c_void_p]
+        for nm, rt in (("rows", ctypes.c_int), ("cols", ctypes.c_int), ("nnz", ctypes.c_int64), ("outer", c_ip), ("inner", c_ip), ("vals", c_dp), ("b", c_dp)):
+            fn = getattr(L, "ref_constraints_" + nm)
+            fn.restype = rt
+            fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.ref_constraints_flags.argtypes = [ctypes.c_void_p]
+        _REFLIBS[name] = L
+    L = _REFLIBS[name]
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    X = _f64(X).reshape(-1, 2)
+    v = _f64(v).reshape(-1, 3)
+    N = x.shape[0]
+    pxyz = _f64(np.zeros((0, 3)) if pxyz is None else pxyz).reshape(-1, 3)
+    pnorms = _f64(np.zeros((0, 3)) if pnorms is None else pnorms).reshape(-1, 3)
+    box_whd = _f64(np.zeros((0, 3)) if box_whd is None else box_whd).reshape(-1, 3)
+    box_E = _f64(np.zeros((0, 16)) if box_E is None else box_E).reshape(-1, 16)
+    if box_whd.shape[0] and not ref_hash_defined(N, face_nodes.shape[0]):
+        raise ValueError("the reference's int edge hash overflows (undefined behaviour) for this mesh size")
+    fc = _f64(-np.ones((4, 6)) if fixed_c is None else fixed_c).reshape(4, 6)
+    fi = _i32(np.zeros(4) if fixed_ci is None else fixed_ci).reshape(4)
+    cid = None if corner_id is None else _i32(corner_id).reshape(N)
+    r = L.ref_constraints_fill(N, face_nodes.shape[0], _i(face_nodes), _d(x), _d(X), _d(v), None if cid is None else _i(cid), float(threshold),
+                               pxyz.shape[0], _d(pxyz), _d(pnorms), box_whd.shape[0], _d(box_whd), _d(box_E), _d(fc), _i(fi), float(h))
+    try:
+        out = {}
+        for which, nm, bn in ((0, "Aineq", "bineq"), (1, "Aeq", "beq")):
+            rows, cols, nnz = L.ref_constraints_rows(r, which), L.ref_constraints_cols(r, which), L.ref_constraints_nnz(r, which)
+            outer = np.ctypeslib.as_array(L.ref_constraints_outer(r, which), (cols + 1,)).copy()
+            inner = np.ctypeslib.as_array(L.ref_constraints_inner(r, which), (nnz,)).copy() if nnz else np.zeros(0, np.int32)
+            vals = np.ctypeslib.as_array(L.ref_constraints_vals(r, which), (nnz,)).copy() if nnz else np.zeros(0)
+            out[nm] = (rows, outer, inner, vals)
+            out[bn] = np.ctypeslib.as_array(L.ref_constraints_b(r, which), (rows,)).copy() if rows else np.zeros(0)
+        fl = L.ref_constraints_flags(r)
+        out["hasFixed"], out["hasCollisions"] = bool(fl & 1), bool(fl & 2)
+    finally:
+        L.ref_constraints_free(r)
+    return out

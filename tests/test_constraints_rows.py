@@ -126,3 +126,86 @@ def test_resident_run_feeds_device_rows(ctx, oracle):
     assert n == len(host_list) and ptr
     _compare(oracle.constraints_contact_rows(host_list), *plan.contact_rows())
     _compare_csr(oracle.constraints_contact_rows(host_list), *plan.contact_rows_csr())
+
+
+# ---- against THE REFERENCE'S OWN Constraints::fill (oracle/_ref/libconstraints_ref.so: Constraints.cpp, Collisions.cpp, boxTriCollision.cpp,
+# Box.cpp, Obstacles.cpp, ... compiled unmodified; it calls CD2 itself and assembles Aineq / Aeq with setFromTriplets) ---------------
+def _csc_of_rows(n_rows, n_cols, nnz, cols, vals, row0=0):
+    """The library's rows as the compressed column-major matrix Eigen builds from the same triplets."""
+    import scipy.sparse as sp
+    r = np.repeat(np.arange(len(nnz)), nnz) + row0
+    keep = np.arange(9)[None, :] < np.asarray(nnz)[:, None]
+    A = sp.csc_matrix((np.asarray(vals).reshape(-1, 9)[keep], (r, np.asarray(cols).reshape(-1, 9)[keep])), shape=(n_rows, n_cols))
+    A.sort_indices()
+    return A
+
+
+def _assert_same_csc(A, ref, what):
+    rows, outer, inner, vals = ref
+    assert A.shape[0] == rows, what
+    assert np.array_equal(A.indptr, outer) and np.array_equal(A.indices, inner), what + ": index arrays"
+    assert A.data.tobytes() == vals.tobytes(), what + ": values differ from the reference's"
+
+
+@pytest.mark.parametrize("gen,n,centre,points", [("regular2", 24, None, False), ("build4", 16, (0.9175, -0.25, -0.549), True), ("regular2", 40, (0.9175, -0.25, -0.549), False)])
+def test_rows_equal_the_reference_constraints_fill(oracle, gen, n, centre, points):
+    X, fn = getattr(E.meshgen, gen)(n)
+    N = X.shape[0]
+    centre = E.meshgen.BOX_CENTRE if centre is None else np.asarray(centre)
+    x = E.meshgen.box_scene_state(X, seed=n, centre=centre)
+    v = 0.1 * np.random.default_rng(n).standard_normal((N, 3))
+    pxyz = pn = None
+    if points:
+        pxyz = np.array([[0.25, 0.25, x[:, 2].max() - 4e-3], [0.1, 0.8, -0.2], x[5] + 1e-3])
+        pn = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0]])
+    whd, Em = E.meshgen.BOX_WHD[None], E.meshgen.box_frame(centre)[None]
+    fixed_c = np.array([[1, 1, 1, 0.0, 0.0, 0.1], [1, 0, 1, 0.2, 0.0, 0.0], [-1, 0, 0, 0, 0, 0], [0, 1, 0, 0, -0.3, 0]], float)
+    fixed_ci = np.array([0, n - 1, 3, N - 1], np.int32)
+    ref = oracle.ref_constraints_fill(fn, x, X, v, E.meshgen.BOX_THRESHOLD, pxyz, pn, whd, Em, fixed_c, fixed_ci)
+    contacts = oracle.ref_cd(fn, x, E.meshgen.BOX_THRESHOLD, pxyz, pn, whd, Em, which=0)     # the CD2 list the reference built inside
+    assert ref["hasCollisions"] and ref["hasFixed"] and len(contacts) > 20
+    nnz, cols, vals = E.contact_rows(contacts)
+    assert len(nnz) == ref["Aineq"][0] == len(contacts)
+    _assert_same_csc(_csc_of_rows(len(nnz), 3 * N, nnz, cols, vals), ref["Aineq"], "Aineq")
+    assert not ref["bineq"].any()
+    # the oracle's restatement too
+    rr = oracle.constraints_contact_rows(contacts)
+    assert [len(r) for r in rr] == list(nnz)
+    # fixed corners -> Aeq / beq
+    L, m = capi.lib(), ctypes.c_int32(0)
+    rows, cc, vv, bb = np.zeros(12, np.int32), np.zeros(12, np.int32), np.zeros(12), np.zeros(12)
+    capi.check(L.eolc_constraints_fixed_rows(capi.dptr(np.ascontiguousarray(fixed_c)), capi.iptr(fixed_ci), capi.dptr(np.ascontiguousarray(v)), N, 0,
+                                             ctypes.byref(m), capi.iptr(rows), capi.iptr(cc), capi.dptr(vv), capi.dptr(bb)))
+    import scipy.sparse as sp
+    A = sp.csc_matrix((vv[:m.value], (rows[:m.value], cc[:m.value])), shape=(m.value, 3 * N))
+    A.sort_indices()
+    _assert_same_csc(A, ref["Aeq"], "Aeq")
+    assert bb[:m.value].tobytes() == ref["beq"].tobytes()
+
+
+def test_rows_with_eol_nodes_equal_the_reference(oracle):
+    """Contacts touching an EoL node take no row (`continue`, :426,:440,:454).  The EoL nodes are given Node::cornerID = an obstacle
+    point, for which the reference first adds its own rows (one inequality, two equalities per node, :144-211): the contact rows
+    then start at row #EoL and the fixed rows at 2 #EoL."""
+    X, fn = E.meshgen.regular2(30)
+    N = X.shape[0]
+    c0 = np.array([0.9175, -0.25, -0.549])
+    x = E.meshgen.box_scene_state(X, seed=5, centre=c0)
+    v = np.zeros((N, 3))
+    pxyz, pn = np.array([[0.1, 0.8, -0.2]]), np.array([[0.0, 0.6, 0.8]])
+    whd, Em = E.meshgen.BOX_WHD[None], E.meshgen.box_frame(c0)[None]
+    contacts = oracle.ref_cd(fn, x, E.meshgen.BOX_THRESHOLD, pxyz, pn, whd, Em, which=0)
+    eol_nodes = np.unique(contacts["verts2"][::3, 0])[:25]
+    corner_id = np.full(N, -1, np.int32); corner_id[eol_nodes] = 0
+    fixed_c = np.array([[1, 1, 1, 0, 0, 0], [-1, 0, 0, 0, 0, 0], [-1, 0, 0, 0, 0, 0], [-1, 0, 0, 0, 0, 0.0]])
+    ref = oracle.ref_constraints_fill(fn, x, X, v, E.meshgen.BOX_THRESHOLD, pxyz, pn, whd, Em, fixed_c, np.array([1, 0, 0, 0], np.int32), corner_id=corner_id)
+    flags = np.zeros(N, np.uint8); flags[eol_nodes] = 1
+    nnz, cols, vals = E.contact_rows(contacts, flags)
+    ne = len(eol_nodes)
+    assert 0 < len(nnz) < len(contacts) and ref["Aineq"][0] == ne + len(nnz) and ref["Aeq"][0] == 2 * ne + 3
+    import scipy.sparse as sp
+    rows, outer, inner, valsr = ref["Aineq"]
+    R = sp.csc_matrix((valsr, inner, outer), shape=(rows, 3 * N + 2 * ne)).tocsr()[ne:, :3 * N].tocsc()
+    R.sort_indices()
+    A = _csc_of_rows(len(nnz), 3 * N, nnz, cols, vals)
+    assert np.array_equal(A.indptr, R.indptr) and np.array_equal(A.indices, R.indices) and A.data.tobytes() == R.data.tobytes()
