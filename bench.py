@@ -14,7 +14,8 @@ max-over-ranks of the device time.
                x/X H2D + f/MDK D2H every step; M is copied only when it changed (it depends on X and the density only) —
                the steady step of a simulation without remeshing; the full fill (M recomputed and copied) is reported beside it
   roofline     algorithmic bytes of one fill (24N+16N+12F+16Ei+24N+8nnz(M)+8nnz(MDK)) / device time of one fill
-  cpu_baseline the oracle (reference Compute*.cpp object code + restated Forces.cpp glue), 1 thread, bounded sample
+  cpu_baseline the reference's OWN compiled Forces::fill (oracle/_ref/libforces_ref.so, kind "reference"), 1 thread, 256^2 sample;
+               --impl reference runs that code as one instance per host core on strips of the same 1024^2 sheet
   ensemble     BASELINE configs[4] at every N: 4096 independent 64x64 scenes sharded contiguously over the ranks (strong
                scaling, no collective), batched Forces::fill + batched CD2 narrow phase per step
   cd           secondary metric contacts/s: CD2 on the 512x512 box scene (BASELINE configs[2]), device + D2H of the list
@@ -199,6 +200,26 @@ def cpu_forces_sample(n=256, repeats=3):
     return elements / best, elements, best
 
 
+def cpu_baseline_leg():
+    """The reference CPU path beside the GPU number, on rank 0 at N = 1: the reference's OWN compiled Forces::fill
+    (oracle/_ref/libforces_ref.so, kind "reference"), one thread like the reference program, regular2 256 x 256 sample; the oracle
+    port (kind "port") on the same sample next to it, and alone when the reference library is missing."""
+    from oracle import oracle as O
+    vp, el, dtp = cpu_forces_sample(256, 2)
+    port = {"value": vp, "unit": UNIT, "cores": 1, "kind": "port", "seconds_per_fill": dtp,
+            "note": "reference Compute*.cpp object code + restated Forces.cpp glue incl. triplets + setFromTriplets"}
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libforces_ref.so")):
+        return dict(port, sample=f"regular2 n=256 sheet ({el} elements), best of 2, {dtp:.2f} s per fill")
+    X, fn = O.sheet_regular2(256)
+    x = O.drape_state(X, seed=0)
+    dt = O.ref_forces_seconds(fn, x, X, MAT, GRAV, H, instances=1, repeats=2)
+    return {"value": el / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"regular2 n=256 sheet ({el} elements), Forces::fill alone (mesh built before), best of 2, {dt:.2f} s per fill",
+            "note": "the reference's own Forces.cpp + UtilEOL.cpp + Compute*.cpp + ArcSim mesh code compiled unmodified against oracle/mini_eigen "
+                    "(oracle/_ref/libforces_ref.so); single thread, as the reference program runs",
+            "port": port}
+
+
 def mem_available_gb():
     try:
         for ln in open("/proc/meminfo"):
@@ -210,14 +231,16 @@ def mem_available_gb():
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path on the same metric and config, on the box's host cores.  Only oracle/ is loaded
-    (reference Compute*.cpp object code + the Forces.cpp glue restated, pinned in tests/test_oracle.py) — no product code.
-    The reference program is single-threaded; the oracle's timing variant runs the element loops on every core and the two
-    setFromTriplets side by side (same triplets, same sums, bit for bit), which is the most the path offers: `value` is that
-    threaded number, `single_thread_value` the reference as it is.
-    Step = one Forces::fill of a BOUNDED SAMPLE of the workload: the first `rows` grid rows of the same 1024 x 1024 sheet (same
-    coordinates, numbering, state), so that the K + W steps the driver asks for end within minutes; then ONE fill of the full
-    configuration (when the host has the memory: ~23 GB of triplets) is timed beside it as `full_config`."""
+    """--impl reference: THE REFERENCE'S OWN CODE on the same metric and config, on the box's host cores.  Only oracle/ is loaded — no
+    product code.  oracle/_ref/libforces_ref.so is /root/reference/src/Forces.cpp + UtilEOL.cpp + conversions.cpp + Compute*.cpp +
+    ArcSim's mesh code compiled unmodified (oracle/Makefile; the prebuilt file travels to the GPU box); its Forces::fill is what a
+    step times.  The reference program is single-threaded (`single_thread_value`); to use every host core the arm runs one
+    independent instance per core side by side — each its own Mesh / Forces objects on its own strip of the workload's sheet — and
+    `value` is their combined rate: the most this host gets out of the reference's code, which makes it the conservative denominator.
+    Step = one Forces::fill per instance on a BOUNDED SAMPLE: `--ref-rows` grid rows of the same 1024 x 1024 sheet (same coordinates,
+    numbering, state) per instance, so that the K + W steps the driver asks for end within minutes.  Beside it: the threaded timing
+    variant of the oracle port on 128 rows (`port_threaded`, round 1-2's denominator) and ONE fill of the full configuration with it
+    (`full_config`; the reference's own code would need ~60 s and ~40 GB for that)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -229,19 +252,43 @@ def run_reference(args):
     x = O.drape_state(X, seed=0, n_total=n * n)
     elements = fn.shape[0] + int((es[:, 3] >= 0).sum())
     cores = max(1, min(len(os.sched_getaffinity(0)), 64))
-    t = time.perf_counter()
-    O.forces_fill(fn, es, x, X, MAT, GRAV, H)                      # the reference as it is: one thread (untimed warm-up of the caches too)
-    dt1 = time.perf_counter() - t
-    for _ in range(args.warmup):
-        O.forces_fill(fn, es, x, X, MAT, GRAV, H, threads=cores)
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        O.forces_fill(fn, es, x, X, MAT, GRAV, H, threads=cores)
-    dt = (time.perf_counter() - t) / args.steps
-    value = elements / dt
     N_full, F_full, _, Ei_full, _, _ = sheet_counts(n)
-    sample = (f"Forces::fill of the first {rows} grid rows of the regular2 n={n} sheet ({elements} of its {F_full + Ei_full} elements) per step"
-              if rows < n else f"Forces::fill of the whole regular2 n={n} sheet ({elements} elements) per step")
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libforces_ref.so"))
+    port = None
+    if have_ref:
+        dt1 = O.ref_forces_seconds(fn, x, X, MAT, GRAV, H, instances=1, repeats=2)          # the reference as it is: one thread
+        times = O.ref_forces_seconds(fn, x, X, MAT, GRAV, H, instances=cores, repeats=args.warmup + args.steps, all_times=True)
+        dt = sum(times[args.warmup:]) / args.steps
+        value = cores * elements / dt
+        kind = "reference"
+        what = ("oracle/_ref/libforces_ref.so: the reference's own Forces.cpp + UtilEOL.cpp + conversions.cpp + Compute*.cpp + ArcSim mesh code, compiled "
+                "unmodified against oracle/mini_eigen (Eigen is not in this image: its operators are restated there, bounds-checked); no product code is loaded by this arm")
+        value_is = ("%d independent instances of the reference's single-threaded Forces::fill side by side, one per core, each on its own %d-row strip; "
+                    "the reference program itself runs ONE (single_thread_value)" % (cores, rows))
+        sample = (f"per instance: Forces::fill of {rows} grid rows of the regular2 n={n} sheet ({elements} of its {F_full + Ei_full} elements) per step; {cores} instances per step"
+                  if rows < n else f"per instance: Forces::fill of the whole regular2 n={n} sheet ({elements} elements) per step; {cores} instances per step")
+    prow = n if n <= 256 else min(n, 128)
+    Xp, fnp = O.sheet_regular2(n, rows=prow)
+    esp = O.arcsim_edge_stencils(Xp.shape[0], fnp)
+    xp = O.drape_state(Xp, seed=0, n_total=n * n)
+    elp = fnp.shape[0] + int((esp[:, 3] >= 0).sum())
+    t = time.perf_counter()
+    O.forces_fill(fnp, esp, xp, Xp, MAT, GRAV, H)
+    dtp1 = time.perf_counter() - t
+    psteps = args.steps if not have_ref else min(args.steps, 3)
+    for _ in range(args.warmup if not have_ref else 1):
+        O.forces_fill(fnp, esp, xp, Xp, MAT, GRAV, H, threads=cores)
+    t = time.perf_counter()
+    for _ in range(psteps):
+        O.forces_fill(fnp, esp, xp, Xp, MAT, GRAV, H, threads=cores)
+    dtp = (time.perf_counter() - t) / psteps
+    port = {"value": elp / dtp, "single_thread_value": elp / dtp1, "unit": UNIT, "cores": cores, "steps": psteps,
+            "sample": f"first {prow} grid rows of the sheet ({elp} elements) per step",
+            "what": "oracle port (reference Compute*.cpp object code + Eigen-free restatement of the Forces.cpp glue, pinned to libforces_ref.so in "
+                    "tests/test_forces_ref_pin.py), element loops on all cores, the two setFromTriplets side by side"}
+    if not have_ref:
+        dt1, dt, value, kind, elements = dtp1, dtp, elp / dtp, "port", elp
+        what, value_is, sample = port["what"], "threaded timing variant of the port (oracle/_ref/libforces_ref.so is missing)", port["sample"]
     full = None
     avail = mem_available_gb()
     if rows < n and not args.no_full:
@@ -254,21 +301,18 @@ def run_reference(args):
             t = time.perf_counter()
             r = O.forces_fill(fnf, esf, xf, Xf, MAT, GRAV, H, threads=cores)
             dtf = time.perf_counter() - t
-            full = {"value": (F_full + Ei_full) / dtf, "unit": UNIT, "seconds": dtf, "elements": F_full + Ei_full, "steps": 1,
+            full = {"value": (F_full + Ei_full) / dtf, "unit": UNIT, "seconds": dtf, "elements": F_full + Ei_full, "steps": 1, "kind": "port",
                     "nnz_MDK": int(r["MDK"][2].size), "seconds_elements_assembly": list(r["seconds"]),
-                    "note": "one fill of the whole configuration, same threads; the sample's per-element rate is the HIGHER of the two "
-                            "(less memory traffic), so `value` is the conservative denominator"}
+                    "note": "one fill of the whole configuration by the threaded port, same cores"}
             del r
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong" if args.workload == "ensemble64" else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, max(1, args.gpus)),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "value_is": "threaded timing variant on %d cores (the reference program itself is single-threaded: single_thread_value)" % cores,
-                             "single_thread_value": elements / dt1, "full_config": full, "mem_available_gb": avail,
-                             "note": "reference Compute*.cpp object code (oracle/_ref) + Eigen-free restatement of Forces.cpp glue incl. triplets and "
-                                     "setFromTriplets; no product code is loaded by this arm"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "value_is": value_is,
+                             "single_thread_value": (elements if have_ref else elp) / dt1, "port_threaded": port, "full_config": full,
+                             "mem_available_gb": avail, "note": what},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
@@ -508,10 +552,7 @@ def run_ours(args):
             line["ensemble"] = ens
     solo = world == 1      # the CPU baseline and the secondary objects are measured on the N = 1 line only
     if rank == 0 and solo and not args.no_cpu:
-        v, el, dt = cpu_forces_sample(256, 3)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"regular2 n=256 sheet ({el} elements), best of 3, {dt:.2f} s per fill",
-                                "note": "reference Compute*.cpp object code + restated Forces.cpp glue incl. triplets + setFromTriplets; single thread like the reference"}
+        line["cpu_baseline"] = cpu_baseline_leg()
     if rank == 0 and solo and not args.no_cd:
         line["cd"] = bench_cd(ctx, dev, stream)
     if rank == 0 and solo and not args.no_cd and S == 1:
@@ -820,7 +861,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sheet1024", choices=["sheet1024", "sheet256", "ensemble64"])
-    ap.add_argument("--ref-rows", type=int, default=128, help="--impl reference: grid rows of the sheet in the per-step sample")
+    ap.add_argument("--ref-rows", type=int, default=16, help="--impl reference: grid rows of the sheet per instance and step (one instance per core)")
     ap.add_argument("--no-full", action="store_true", help="--impl reference: skip the single fill of the full configuration")
     ap.add_argument("--no-ensemble", action="store_true", help="skip the configs[4] ensemble object")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -5,6 +5,7 @@ this module.  The product package (eol_cloth_b200) never does.
 """
 import ctypes
 import os
+import time
 import subprocess
 
 import numpy as np
@@ -569,6 +570,9 @@ def ref_forces_lib(adapter=False):
     L = ctypes.CDLL(path)
     L.ref_forces_fill.restype = ctypes.c_void_p
     L.ref_forces_fill.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_dp, c_ip, c_dp, c_dp, ctypes.c_double]
+    L.ref_forces_new.restype = ctypes.c_void_p
+    L.ref_forces_new.argtypes = L.ref_forces_fill.argtypes
+    L.ref_forces_run.argtypes = [ctypes.c_void_p]
     L.ref_forces_mesh.restype = ctypes.c_void_p
     L.ref_forces_mesh.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_dp]
     L.ref_forces_free.argtypes = [ctypes.c_void_p]
@@ -629,6 +633,34 @@ def ref_forces_fill(face_nodes, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_DEFAULT, h
     finally:
         L.ref_forces_free(r)
     return outs if more_steps else outs[0]
+
+
+def ref_forces_seconds(face_nodes, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_DEFAULT, h=H_DEFAULT, instances=1, repeats=1, all_times=False):
+    """Wall-clock seconds of Forces::fill ALONE (the meshes are built before the clock starts) as compiled from the reference's own
+    sources: `instances` independent Mesh / Forces objects built from the same arrays, filled side by side on one thread each (the
+    reference program is single-threaded; this is what a host with that many cores can get out of its code).  Forces::fill is
+    called `repeats` times on the same objects (as Cloth::step does); returns the best time, or every time with all_times."""
+    import threading
+    L = ref_forces_lib()
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    X = _f64(X).reshape(-1, 2)
+    m, g = _f64(mat), _f64(grav)
+    hs = [L.ref_forces_new(x.shape[0], face_nodes.shape[0], _i(face_nodes), _d(x), _d(X), None, _d(m), _d(g), float(h)) for _ in range(instances)]
+    times = []
+    try:
+        for _ in range(repeats):
+            th = [threading.Thread(target=L.ref_forces_run, args=(hh,)) for hh in hs]     # ctypes releases the GIL for the call
+            t = time.perf_counter()
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+            times.append(time.perf_counter() - t)
+    finally:
+        for hh in hs:
+            L.ref_forces_free(hh)
+    return times if all_times else min(times)
 
 
 def ref_mesh_data(face_nodes, x, X, x_new=None):

@@ -67,16 +67,28 @@ void build_mesh(Run &R, int N, int F, const int32_t *face_nodes, const double *x
 
 extern "C" {
 
-// Reference Forces::fill on a mesh rebuilt from flat arrays.  mat6 = density, e, nu, beta, dampingA, dampingB.
-void *ref_forces_fill(int N, int F, const int32_t *face_nodes, const double *x, const double *X, const int32_t *eol_index,
-                      const double *mat6, const double *grav3, double h) {
+// The mesh, material, gravity and step of one run; no fill yet (so that bench.py can time Forces::fill alone, and several
+// instances side by side).  mat6 = density, e, nu, beta, dampingA, dampingB.
+void *ref_forces_new(int N, int F, const int32_t *face_nodes, const double *x, const double *X, const int32_t *eol_index,
+                     const double *mat6, const double *grav3, double h) {
     Run *R = new Run;
     R->material.density = mat6[0]; R->material.e = mat6[1]; R->material.nu = mat6[2]; R->material.beta = mat6[3];
     R->material.dampingA = mat6[4]; R->material.dampingB = mat6[5];
     build_mesh(*R, N, F, face_nodes, x, X, eol_index);
     for (int j = 0; j < 3; ++j) R->grav[j] = grav3[j];
     R->h = h;
-    R->forces.fill(R->mesh, R->material, Eigen::Vector3d(grav3[0], grav3[1], grav3[2]), h);   // the call of Cloth.cpp:365
+    return R;
+}
+// Forces::fill(mesh, mat, grav, h): the call of Cloth.cpp:365
+void ref_forces_run(void *p) {
+    Run *R = static_cast<Run *>(p);
+    R->forces.fill(R->mesh, R->material, Eigen::Vector3d(R->grav[0], R->grav[1], R->grav[2]), R->h);
+}
+// Reference Forces::fill on a mesh rebuilt from flat arrays.
+void *ref_forces_fill(int N, int F, const int32_t *face_nodes, const double *x, const double *X, const int32_t *eol_index,
+                      const double *mat6, const double *grav3, double h) {
+    void *R = ref_forces_new(N, F, face_nodes, x, X, eol_index, mat6, grav3, h);
+    ref_forces_run(R);
     return R;
 }
 // The next step on the SAME Mesh and Forces objects: new world positions (and, if X is given, new material coordinates — what an
