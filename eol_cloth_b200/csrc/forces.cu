@@ -169,7 +169,8 @@ struct BulkStore {   // one asynchronous bulk copy shared -> global; both addres
 #define EOLC_SERVICE_REGS 72
 #endif
 constexpr int COMPUTE_REGS = EOLC_COMPUTE_REGS, SERVICE_REGS = EOLC_SERVICE_REGS;
-static_assert(tiles::NTHREADS * COMPUTE_REGS + 128 * SERVICE_REGS <= tiles::CTA_THREADS * 168, "register pool of the CTA");
+constexpr int LAUNCH_REGS = (65536 / (tiles::CTA_THREADS * tiles::CTAS_PER_SM)) / 8 * 8;   // what ptxas may use under the launch bounds: 168 for one 384-thread CTA per SM
+static_assert(tiles::NTHREADS * COMPUTE_REGS + 128 * SERVICE_REGS <= tiles::CTA_THREADS * LAUNCH_REGS, "register pool of the CTA");
 constexpr bool SERVICE_P2 = tiles::P2THREADS > tiles::NTHREADS;   // the service warpgroup runs phase-2 groups too
 constexpr int BAR1_THREADS = SERVICE_P2 ? tiles::CTA_THREADS : tiles::NTHREADS;
 // Phase 3 (the diagonal blocks from the staged rows) on the service warpgroup: the compute warps go from the end of phase 2 straight
@@ -429,7 +430,7 @@ int build_tiles_plan(eolc_forces_plan *P, const double *X_hint, cudaStream_t st,
         const uint32_t *g = tp.geo.data() + (size_t)t * 4 * tp.max_geo16;
         for (uint32_t l = 0, n_own = g[1] & 255u; l < n_own; ++l) P->h_tile_of[g[4 + l]] = t;
     }
-    if (tiles_smem_bytes(P) > (size_t)227 * 1024) { set_error("tile plan needs %zu bytes of shared memory", tiles_smem_bytes(P)); return EOLC_ERR_UNSUPPORTED; }
+    if (tiles_smem_bytes(P) > (size_t)(227 / tiles::CTAS_PER_SM - (tiles::CTAS_PER_SM > 1 ? 1 : 0)) * 1024) { set_error("tile plan needs %zu bytes of shared memory", tiles_smem_bytes(P)); return EOLC_ERR_UNSUPPORTED; }
     static_assert(sizeof(uint4) == 16, "uint4");
     EOLC_CUDA(P->d_geo.alloc(tp.geo.size() / 4));
     EOLC_CUDA(P->d_tmpl.alloc(tp.tmpl.size() / 4));

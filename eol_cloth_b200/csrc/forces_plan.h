@@ -177,14 +177,20 @@ using eolc::NodeCSR;   // defined above: the pattern build reads it too
 #ifndef EOLC_TILE_OWN
 #define EOLC_TILE_OWN 32
 #endif
-constexpr int NTHREADS = 256;        // compute threads per CTA: phase 1 evaluates one element per thread (stencils from thread 0 up, faces from
+#ifndef EOLC_NTHREADS
+#define EOLC_NTHREADS 256
+#endif
+#ifndef EOLC_CTAS_PER_SM
+#define EOLC_CTAS_PER_SM 1
+#endif
+constexpr int NTHREADS = EOLC_NTHREADS;   // compute threads per CTA: phase 1 evaluates one element per thread (stencils from thread 0 up, faces from
                                      // the last thread down), phases 2 and 3 run on the same threads
 #ifndef EOLC_P2_WARPS
 #define EOLC_P2_WARPS 12             // warps that run phase-2 groups: 12 = the 8 compute warps + the service warpgroup, which would idle
 #endif                               // between the two barriers of a tile otherwise (8: compute warps only; -3 % with 12, experiments.md p12)
 constexpr int P2THREADS = 32 * EOLC_P2_WARPS;
 constexpr int CTA_THREADS = NTHREADS + 128;   // + one service warpgroup: stages the inputs of the tiles ahead, issues the bulk copy-out
-constexpr int CTAS_PER_SM = 1;
+constexpr int CTAS_PER_SM = EOLC_CTAS_PER_SM;   // 2: experiment (half-size CTAs, smaller tiles, phases of two CTAs interleave; experiments.md)
 constexpr int MAX_OWN = EOLC_TILE_OWN;   // nodes owned by a tile (<= 63: 6-bit fields)
 constexpr int MAX_LOC = 128;         // distinct nodes referenced by a tile's elements (8-bit local ids)
 // Only OFF-DIAGONAL element blocks are parked: every element matrix has zero row sums (translation invariance; the mass part sums
@@ -194,7 +200,10 @@ constexpr int FACE_STRIDE = 42;      // doubles parked per face: 3 off-diagonal 
 constexpr int FACE_T8 = 33;          // offset of t8 (rho * 2A) inside a face slot
 constexpr int ZPAD = 32;             // doubles at the start of the scratch that stay zero: padded pull entries read a zero block there (any
                                      // even offset <= 14, chosen by bank)
-constexpr int MAX_SCRATCH_DOUBLES = 14336;   // 112 KB of parked blocks per tile
+#ifndef EOLC_MAX_SCRATCH_DOUBLES
+#define EOLC_MAX_SCRATCH_DOUBLES 14336
+#endif
+constexpr int MAX_SCRATCH_DOUBLES = EOLC_MAX_SCRATCH_DOUBLES;   // 112 KB of parked blocks per tile
 constexpr int MAX_KSTAGE = 130 * MAX_OWN;          // doubles of MDK rows one tile stages in shared memory before the bulk copy-out
 constexpr int MAX_MSTAGE = 74 * MAX_OWN;           // doubles of M rows one tile stages (expanded blocks: m on the block diagonal, explicit zeros off it)
 constexpr int MAX_FSTAGE = 4 * MAX_OWN + 4;        // doubles of f one tile stages
