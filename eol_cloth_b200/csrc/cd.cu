@@ -332,17 +332,28 @@ __global__ void __launch_bounds__(1024) k_scan(size_t n, const int *__restrict__
 // returns winning j1 (or -1) and, if rec != NULL, fills the record
 __device__ int test_vertex_box(int i2, int F, V3 x2, const double *__restrict__ fnp, const BoxData &B, double threshold, eolc_contact *rec) {
     if (!check_aabb_point(x2, B.aabbB1)) return -1;
+    // :689-697 — inside all 24 half-spaces; the projections are kept: the second loop (:699-) forms the same expression again
+    double pj[24];
+#pragma unroll
     for (int j1 = 0; j1 < 24; ++j1) {
         V3 x1a = bcol(B.verts1, c_faces1[j1][0]);
-        if (dot(bcol(B.faceNors1, j1), x2 - x1a) > 0.0) return -1;
+        pj[j1] = dot(bcol(B.faceNors1, j1), x2 - x1a);
+        if (pj[j1] > 0.0) return -1;
     }
     int best = -1;
     double bestd = 0.0;
     const double lim = mul(5.0, threshold);
+    // A conservative screen the reference does not have and that cannot change a result: dist = |x2 - (x2 - proj nor1)| equals |proj|
+    // up to a few roundings of the coordinates (nor1 is a unit vector), so a triangle whose plane is farther than lim plus a margin a
+    // million times those roundings fails `dist > lim` (:712) for certain; only the near planes (the face the vertex rests on) run the
+    // reference's expressions, which decide exactly as before.  Removes ~20 of the 24 sqrt / barycentric evaluations per vertex.
+    const double guard = lim + (1e-6 * lim + 1e-9 + 1e-10 * (fabs(x2.x) + fabs(x2.y) + fabs(x2.z)));
+#pragma unroll 1
     for (int j1 = 0; j1 < 24; ++j1) {
+        const double proj = pj[j1];
+        if (-proj > guard) continue;
         V3 x1a = bcol(B.verts1, c_faces1[j1][0]), x1b = bcol(B.verts1, c_faces1[j1][1]), x1c = bcol(B.verts1, c_faces1[j1][2]);
         V3 nor1 = bcol(B.faceNors1, j1);
-        double proj = dot(nor1, x2 - x1a);
         if (proj > 0.0) continue;
         V3 x1 = x2 - scale(proj, nor1);
         double dist = norm(x2 - x1);
