@@ -55,3 +55,13 @@ def test_gpu_eol_fill_equals_the_reference_fill(ctx, oracle, n, kind):
     ref = oracle.ref_forces_fill(fn, x, X, tuple(MAT), GRAV, H, eol_index=eol)
     assert ref["dof"] == 3 * N + 2 * int((eol >= 0).sum())
     _compare(ref, _gpu_fill(ctx, X, fn, x, eol), N, f"EOL {kind}")
+
+
+def test_gpu_fill_512_equals_the_reference_fill(ctx, oracle):
+    """The largest size at which the reference's own code is run in the suite (1.3 M elements, 0.2 G triplets, ~20 s on one thread;
+    the whole 1024^2 sheet goes through the pinned restatement, tests/test_forces_gpu.py::test_fullsize_1024_values_match_oracle)."""
+    X, fn = E.meshgen.regular2(512)
+    x = E.meshgen.drape_state(X, seed=0)
+    ref = oracle.ref_forces_fill(fn, x, X, tuple(MAT), GRAV, H)
+    assert len(ref["MDK"][2]) == 30560364 and len(ref["M"][2]) == 16478226          # SURVEY §8 table
+    _compare(ref, _gpu_fill(ctx, X, fn, x), X.shape[0], "regular2 512")
