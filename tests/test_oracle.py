@@ -106,16 +106,26 @@ def test_survey_counts_64(oracle):
     assert r["M"][2].size == 253458 and r["MDK"][2].size == 465516
 
 
+def _close_to_golden(r, g, n_nodes):
+    """The fixtures are written by THE REFERENCE'S OWN compiled Forces::fill (oracle/_ref/libforces_ref.so, tests/golden/make_golden.py);
+    the Eigen-free restatement reproduces them: identical index arrays, M bit for bit, f / MDK to 1e-13 of the block-row scale (they
+    differ in last bits only where Eigen's operators order a sum differently; tests/test_forces_ref_pin.py has the full comparison)."""
+    from util import assert_close_tol, block_row_scale
+    assert str(g["source"]) == "libforces_ref"
+    assert_close_tol(r["f"], g["f"], np.abs(g["f"]).max(), 1e-13, "f")
+    for k, nm in (("M", "M"), ("K", "MDK")):
+        assert np.array_equal(r[nm][0], g[k + "_outer"]) and np.array_equal(r[nm][1], g[k + "_inner"])
+        assert_close_tol(r[nm][2], g[k + "_vals"], block_row_scale(g[k + "_outer"], g[k + "_vals"], n_nodes), 1e-13, nm)
+    assert np.array_equal(r["M"][2], g["M_vals"])
+
+
 @pytest.mark.parametrize("name,gen,n,seed", [("forces_regular2_n12", "regular2", 12, 0), ("forces_build4_n7", "build4", 7, 1)])
 def test_golden_forces(oracle, name, gen, n, seed):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     X, fn = getattr(E.meshgen, gen)(n)
     es = E.meshgen.edge_stencils(X.shape[0], fn)
     r = oracle.forces_fill(fn, es, E.meshgen.drape_state(X, seed=seed), X)
-    assert np.array_equal(r["f"], g["f"])
-    for k, nm in (("M", "M"), ("K", "MDK")):
-        assert np.array_equal(r[nm][0], g[k + "_outer"]) and np.array_equal(r[nm][1], g[k + "_inner"])
-        assert np.array_equal(r[nm][2], g[k + "_vals"])
+    _close_to_golden(r, g, X.shape[0])
 
 
 def _eol_line(n):
@@ -130,10 +140,8 @@ def test_golden_forces_eol_and_normals(oracle):
     X, fn = E.meshgen.regular2(12)
     es = E.meshgen.edge_stencils(X.shape[0], fn)
     r = oracle.forces_fill(fn, es, E.meshgen.drape_state(X, seed=2), X, eol_index=_eol_line(12))
-    assert r["dof"] == 3 * 144 + 2 * 10 and np.array_equal(r["f"], g["f"])
-    for k, nm in (("M", "M"), ("K", "MDK")):
-        assert np.array_equal(r[nm][0], g[k + "_outer"]) and np.array_equal(r[nm][1], g[k + "_inner"])
-        assert np.array_equal(r[nm][2], g[k + "_vals"])
+    assert r["dof"] == 3 * 144 + 2 * 10
+    _close_to_golden(r, g, X.shape[0])
     g = np.load(os.path.join(GOLD, "normals_build4_n7.npz"))
     X, fn = E.meshgen.build4(7)
     fa, na = oracle.mesh_normals(fn, E.meshgen.drape_state(X, seed=1))
