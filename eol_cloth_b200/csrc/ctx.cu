@@ -75,6 +75,22 @@ void *eolc_host_alloc(size_t bytes) {
 
 void eolc_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+// A caller's OWN array (e.g. the value array of an Eigen::SparseMatrix) becomes page-locked in place, so that the host entry points
+// DMA straight into it; undone by eolc_host_unregister before the array is freed or reallocated.
+int eolc_host_register(void *p, size_t bytes) {
+    EOLC_REQUIRE(p && bytes, "eolc_host_register: NULL / empty range");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return EOLC_OK; }
+    if (e != cudaSuccess) { cudaGetLastError(); eolc::set_error("eolc_host_register(%zu bytes) failed: %s", bytes, cudaGetErrorString(e)); return EOLC_ERR_CUDA; }
+    return EOLC_OK;
+}
+int eolc_host_unregister(void *p) {
+    if (!p) return EOLC_OK;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); if (e != cudaErrorHostMemoryNotRegistered) { eolc::set_error("eolc_host_unregister failed: %s", cudaGetErrorString(e)); return EOLC_ERR_CUDA; } }
+    return EOLC_OK;
+}
+
 void eolc_ctx_destroy(eolc_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);

@@ -124,6 +124,12 @@ int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X
  * buffers are the target of the DMA itself, pageable ones cost a staging copy (1.5 GB per fill at 1024^2).  NULL on failure. */
 void *eolc_host_alloc(size_t bytes);
 void eolc_host_free(void *p);
+/* The same for an array the CALLER owns and cannot allocate through eolc_host_alloc — e.g. valuePtr() of the Eigen::SparseMatrix
+ * members of the reference's class Forces (src/Forces.h:35-36): eolc_host_register page-locks it in place (cudaHostRegister), after
+ * which eolc_forces_fill[_ex] copies device -> that array directly; eolc_host_unregister before the array is freed or reallocated.
+ * Registering is slow (about 0.1 s per GB): once per topology change, not per step. */
+int eolc_host_register(void *p, size_t bytes);
+int eolc_host_unregister(void *p);
 /* Same, every pointer is a DEVICE pointer on the plan's device; asynchronous on eolc_ctx_stream(). */
 int eolc_forces_fill_dev(eolc_forces_plan *plan, const double *x_dev, const double *X_dev, const eolc_material *mat,
                          const double grav[3], double h, double *f_dev, double *M_vals_dev, double *MDK_vals_dev);

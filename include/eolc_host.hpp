@@ -149,6 +149,11 @@ template <class Body> inline bool par_any(size_t n, Body body) {
 }
 }  // namespace detail
 
+// memcpy of a large array on the host threads (a single thread moves ~10 GB/s: 0.1 s for the 1 GB of MDK values at 1024^2)
+template <class T> inline void par_copy(T *dst, const T *src, size_t n) {
+    detail::par_any(n, [&](size_t lo, size_t hi) { std::memcpy(dst + lo, src + lo, (hi - lo) * sizeof(T)); return false; });
+}
+
 template <class MeshT>
 void flatten(const MeshT &mesh, FlatMesh &out, bool positions_only = false) {
     const size_t N = mesh.nodes.size();
@@ -243,28 +248,42 @@ public:
     // M_updated tells the caller whether M.values was rewritten by the last fill (false: M is the matrix of the previous step;
     // it depends on X and the density only, ComputeInertial.cpp:33,44-47, so a step without remeshing leaves it alone).
     bool M_updated = true;
-    void fill(const FlatMesh &mesh, const eolc_material &mat, const double grav[3], double h) {
+    // Caller-owned result arrays (dof, nnz(M), nnz(MDK) doubles) instead of this object's own f / M.values / MDK.values: what an
+    // adapter passes to have the results written straight into the Eigen members of the reference's class Forces (their value
+    // arrays page-locked in place with eolc_host_register) — no second 1 GB copy on the host.
+    struct External { double *f, *M_vals, *MDK_vals; };
+    // The plan for this topology (rebuilt only when mesh.topology_version moved) and the patterns M / MDK (rows, nnz, outer, inner)
+    // that go with it; true if it was rebuilt, i.e. if arrays sized from an earlier pattern are stale.
+    bool prepare(const FlatMesh &mesh) {
         Context &c = *ctx_;
-        // the plan follows the mesh's topology counter (flatten() moves it only when an index really changed)
-        if (!plan_ || mesh.topology_version != topo_version_) {
-            eolc_forces_plan_destroy(plan_);
-            plan_ = nullptr;
-            check(eolc_forces_plan_create(c.handle(), mesh.N, mesh.F, mesh.face_nodes.data(), mesh.E, mesh.edge_stencil.data(),
-                                          mesh.eol_index.empty() ? nullptr : mesh.eol_index.data(), mesh.X.data(), &plan_),
-                  "eolc_forces_plan_create");
-            topo_version_ = mesh.topology_version;
-            bind(0, M);
-            bind(1, MDK);
-            have_M_ = false;
+        if (plan_ && mesh.topology_version == topo_version_) return false;
+        eolc_forces_plan_destroy(plan_);
+        plan_ = nullptr;
+        check(eolc_forces_plan_create(c.handle(), mesh.N, mesh.F, mesh.face_nodes.data(), mesh.E, mesh.edge_stencil.data(),
+                                      mesh.eol_index.empty() ? nullptr : mesh.eol_index.data(), mesh.X.data(), &plan_),
+              "eolc_forces_plan_create");
+        topo_version_ = mesh.topology_version;
+        bind(0, M);
+        bind(1, MDK);
+        have_M_ = false;
+        return true;
+    }
+    void fill(const FlatMesh &mesh, const eolc_material &mat, const double grav[3], double h, const External *ext = nullptr) {
+        prepare(mesh);
+        double *fo, *Mo, *Ko;
+        if (ext) { fo = ext->f; Mo = ext->M_vals; Ko = ext->MDK_vals; }
+        else {
+            f.resize((size_t)M.rows);                   // f.resize(3N + 2 EoL_Count), Forces.cpp:914
+            M.values.resize((size_t)M.nnz); MDK.values.resize((size_t)MDK.nnz);
+            fo = f.data(); Mo = M.values.data(); Ko = MDK.values.data();
         }
-        f.resize((size_t)M.rows);                       // f.resize(3N + 2 EoL_Count), Forces.cpp:914
+        if (Mo != last_M_out_) have_M_ = false;         // another destination: it does not hold the previous step's M
         EoL_cutoff = 3 * mesh.N;                        // Forces.cpp:919
         const bool same_M = have_M_ && mesh.EoL_Count == 0 && mesh.X_version == X_version_ && mat.density == density_;
-        check(eolc_forces_fill_ex(plan_, mesh.x.data(), mesh.X.data(), &mat, grav, h, f.data(), M.values.data(), MDK.values.data(),
-                                  same_M ? EOLC_FILL_M_UNCHANGED : 0u),
+        check(eolc_forces_fill_ex(plan_, mesh.x.data(), mesh.X.data(), &mat, grav, h, fo, Mo, Ko, same_M ? EOLC_FILL_M_UNCHANGED : 0u),
               "eolc_forces_fill");
         M_updated = !same_M;
-        have_M_ = true; X_version_ = mesh.X_version; density_ = mat.density;
+        have_M_ = true; X_version_ = mesh.X_version; density_ = mat.density; last_M_out_ = Mo;
     }
     const eolc_forces_plan *plan() const { return plan_; }
 
@@ -272,14 +291,14 @@ private:
     void bind(int which, SparseCSC &A) {
         int32_t dof = 0;
         check(eolc_forces_pattern(plan_, which, &dof, &A.nnz, &A.outer, &A.inner), "eolc_forces_pattern");
-        A.rows = A.cols = dof;
-        A.values.resize((size_t)A.nnz);
+        A.rows = A.cols = dof;       // A.values is sized by fill() when the results go to this object's own arrays
     }
     Context *ctx_;
     eolc_forces_plan *plan_ = nullptr;
     uint64_t topo_version_ = 0, X_version_ = 0;
     double density_ = 0.0;
     bool have_M_ = false;
+    const double *last_M_out_ = nullptr;
 };
 
 // What CD / CD2 read from `Obstacles` (Obstacles.h:31-35, Points.h:22-24, Box.h:43-47).

@@ -559,7 +559,9 @@ def mesh_normals(face_nodes, x):
 # file travels to the GPU box).  adapter=True: libadapter_forces.so, the same driver with adapter/Forces_fill_b200.cpp in place of
 # Forces.cpp — the drop-in body, executed on the GPU ------------------------------------------------------------------------------
 def ref_forces_lib(adapter=False):
-    name = "libadapter_forces.so" if adapter else "libforces_ref.so"
+    """adapter: False = the reference's own Forces.cpp; True = adapter/Forces_fill_b200.cpp (results copied into the Eigen members);
+    "zero_copy" = the same built with -DEOLC_ADAPTER_ZERO_COPY (the members' value arrays are the DMA targets)."""
+    name = "libadapter_forces_zc.so" if adapter == "zero_copy" else "libadapter_forces.so" if adapter else "libforces_ref.so"
     if name in _REFLIBS:
         return _REFLIBS[name]
     path = os.path.join(_HERE, "_ref", name)
@@ -573,6 +575,8 @@ def ref_forces_lib(adapter=False):
     L.ref_forces_new.restype = ctypes.c_void_p
     L.ref_forces_new.argtypes = L.ref_forces_fill.argtypes
     L.ref_forces_run.argtypes = [ctypes.c_void_p]
+    L.ref_forces_time_steps.restype = ctypes.c_double
+    L.ref_forces_time_steps.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
     L.ref_forces_mesh.restype = ctypes.c_void_p
     L.ref_forces_mesh.argtypes = [ctypes.c_int, ctypes.c_int, c_ip, c_dp, c_dp]
     L.ref_forces_free.argtypes = [ctypes.c_void_p]
@@ -661,6 +665,24 @@ def ref_forces_seconds(face_nodes, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_DEFAULT
         for hh in hs:
             L.ref_forces_free(hh)
     return times if all_times else min(times)
+
+
+def ref_forces_step_seconds(face_nodes, x, X, mat=MATERIAL_DEFAULT, grav=GRAV_DEFAULT, h=H_DEFAULT, steps=5, adapter=False):
+    """(seconds of the first Forces::fill, mean seconds of `steps` further fills on the same Mesh / Forces objects with every node
+    moved a little in between) — the reference's own code, or with adapter=True the drop-in body on the GPU: flatten of the ArcSim
+    pointer mesh + host -> device + kernels + device -> the members f / M / MDK of the reference's class Forces."""
+    L = ref_forces_lib(adapter)
+    face_nodes = _i32(face_nodes).reshape(-1, 3)
+    x = _f64(x).reshape(-1, 3)
+    X = _f64(X).reshape(-1, 2)
+    h_ = L.ref_forces_new(x.shape[0], face_nodes.shape[0], _i(face_nodes), _d(x), _d(X), None, _d(_f64(mat)), _d(_f64(grav)), float(h))
+    try:
+        t = time.perf_counter()
+        L.ref_forces_run(h_)
+        first = time.perf_counter() - t
+        return first, L.ref_forces_time_steps(h_, int(steps), 1e-7)
+    finally:
+        L.ref_forces_free(h_)
 
 
 def ref_mesh_data(face_nodes, x, X, x_new=None):

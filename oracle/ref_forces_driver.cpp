@@ -17,6 +17,7 @@
 //   * vectors.cpp needs -fpermissive (an explicit instantiation without a definition).
 // The same driver linked with adapter/Forces_fill_b200.cpp INSTEAD of Forces.cpp gives oracle/_ref/libadapter_forces.so: the
 // reference-side drop-in body of Forces::fill, executed (reference Mesh / Forces types -> include/eolc_host.hpp -> C ABI -> GPU).
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -25,6 +26,9 @@
 #include "external/ArcSim/geometry.hpp"  // compute_ms_data / compute_ws_data
 #include "external/ArcSim/util.hpp"
 
+// adapter builds only (adapter/Forces_fill_b200.cpp): drops what the adapter holds for a Forces object before the object dies
+extern "C" void eolc_adapter_forces_release(const void *forces_this) __attribute__((weak));
+
 namespace {
 
 struct Run {
@@ -32,7 +36,10 @@ struct Run {
     Material material;
     Forces forces;
     double grav[3], h;
-    ~Run() { delete_mesh(mesh); }
+    ~Run() {
+        if (eolc_adapter_forces_release) eolc_adapter_forces_release(&forces);
+        delete_mesh(mesh);
+    }
 };
 
 // The mesh the way Cloth::build makes it (Cloth.cpp:63-129): one Vert + one Node per grid point, connect(), faces through
@@ -66,6 +73,7 @@ void build_mesh(Run &R, int N, int F, const int32_t *face_nodes, const double *x
 }  // namespace
 
 extern "C" {
+void ref_forces_run(void *p);
 
 // The mesh, material, gravity and step of one run; no fill yet (so that bench.py can time Forces::fill alone, and several
 // instances side by side).  mat6 = density, e, nu, beta, dampingA, dampingB.
@@ -109,6 +117,21 @@ void *ref_forces_mesh(int N, int F, const int32_t *face_nodes, const double *x, 
     return R;
 }
 void ref_forces_free(void *p) { delete static_cast<Run *>(p); }
+
+// Seconds per Forces::fill over `steps` further fills on the same objects, every node moved a little before each one (what a time
+// step does between two fills); the clock covers the moves' successor only: Forces::fill — for the adapter build that is flatten +
+// host -> device + kernels + device -> the Eigen members.
+double ref_forces_time_steps(void *p, int steps, double eps) {
+    Run *R = static_cast<Run *>(p);
+    double total = 0.0;
+    for (int s = 0; s < steps; ++s) {
+        for (size_t i = 0; i < R->mesh.nodes.size(); ++i) R->mesh.nodes[i]->x[2] += eps * (double)((i + (size_t)s) % 3 == 0 ? 1 : -1);
+        const auto t0 = std::chrono::steady_clock::now();
+        ref_forces_run(p);
+        total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return steps > 0 ? total / steps : 0.0;
+}
 
 int ref_forces_dof(void *p) { return (int)static_cast<Run *>(p)->forces.f.size(); }
 int ref_forces_eol_cutoff(void *p) { return static_cast<Run *>(p)->forces.EoL_cutoff; }

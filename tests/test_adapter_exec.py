@@ -75,12 +75,16 @@ def _same_fill(ref, got, n_nodes, what):
     assert_close_tol(got["f"], ref["f"], np.abs(ref["f"]).max(), 1e-10, f"{what} f")
 
 
+MODES = [True, "zero_copy"]    # results copied into the Eigen members / the members' value arrays are the DMA targets (-DEOLC_ADAPTER_ZERO_COPY)
+
+
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("gen,n", [("regular2", 24), ("build4", 13), ("regular2", 3)])
-def test_adapter_forces_fill_equals_reference(oracle, gen, n):
+def test_adapter_forces_fill_equals_reference(oracle, gen, n, mode):
     X, fn = getattr(E.meshgen, gen)(n)
     x = E.meshgen.drape_state(X, seed=n)
     ref = oracle.ref_forces_fill(fn, x, X)
-    got = oracle.ref_forces_fill(fn, x, X, adapter=True)
+    got = oracle.ref_forces_fill(fn, x, X, adapter=mode)
     _same_fill(ref, got, X.shape[0], f"{gen}{n}")
     K = got["MDK"]
     import scipy.sparse as sp
@@ -88,7 +92,8 @@ def test_adapter_forces_fill_equals_reference(oracle, gen, n):
     assert abs(A - A.T).max() == 0.0          # exactly symmetric, like the reference's mirrored triplets
 
 
-def test_adapter_forces_fill_steps_on_the_same_objects(oracle):
+@pytest.mark.parametrize("mode", MODES)
+def test_adapter_forces_fill_steps_on_the_same_objects(oracle, mode):
     """Three fills on the same Mesh / Forces objects: the adapter keeps its plan and page-locked buffers; the second step moves x only
     (M is not recomputed nor copied: the member must still hold it), the third also moves the material coordinates (M changes)."""
     X, fn = E.meshgen.regular2(20)
@@ -98,14 +103,15 @@ def test_adapter_forces_fill_steps_on_the_same_objects(oracle):
     X3 = X + 2e-4 * rng.standard_normal(X.shape)
     steps = [(x2, None), (x2, X3)]
     refs = oracle.ref_forces_fill(fn, x, X, more_steps=steps)
-    gots = oracle.ref_forces_fill(fn, x, X, adapter=True, more_steps=steps)
+    gots = oracle.ref_forces_fill(fn, x, X, adapter=mode, more_steps=steps)
     for i, (r, g) in enumerate(zip(refs, gots)):
         _same_fill(r, g, X.shape[0], f"step {i}")
     assert refs[0]["M"][2].tobytes() == refs[1]["M"][2].tobytes() != refs[2]["M"][2].tobytes()
     assert gots[0]["M"][2].tobytes() == gots[1]["M"][2].tobytes() != gots[2]["M"][2].tobytes()
 
 
-def test_adapter_forces_fill_with_eol_nodes(oracle):
+@pytest.mark.parametrize("mode", MODES)
+def test_adapter_forces_fill_with_eol_nodes(oracle, mode):
     """EoL nodes: dof = 3N + 2 EoL_Count, Eulerian blocks, EoL_cutoff — through the adapter."""
     X, fn = E.meshgen.regular2(16)
     N = X.shape[0]
@@ -114,6 +120,27 @@ def test_adapter_forces_fill_with_eol_nodes(oracle):
     eol[line] = np.arange(line.size)
     x = E.meshgen.drape_state(X, seed=2)
     ref = oracle.ref_forces_fill(fn, x, X, eol_index=eol)
-    got = oracle.ref_forces_fill(fn, x, X, eol_index=eol, adapter=True)
+    got = oracle.ref_forces_fill(fn, x, X, eol_index=eol, adapter=mode)
     assert ref["dof"] == 3 * N + 2 * line.size
     _same_fill(ref, got, N, "EOL line")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_adapter_forces_fill_step_time(oracle, capsys, mode):
+    """Several steady steps through the adapter on the same objects (the driver moves every node a little before each): values equal
+    the reference's own fill of the same states; then the step time on a 512^2 sheet, ArcSim pointer mesh in, Eigen members out.
+    Default mode: the values pass through the host layer's page-locked arrays and are copied into the members on the host threads;
+    zero-copy mode: the members' value arrays are page-locked in place once and the device -> host copy lands in them."""
+    X, fn = E.meshgen.regular2(96)
+    x = E.meshgen.drape_state(X, seed=3)
+    rng = np.random.default_rng(1)
+    steps = [(x + 1e-4 * rng.standard_normal(x.shape), None) for _ in range(4)]
+    refs = oracle.ref_forces_fill(fn, x, X, more_steps=steps)
+    gots = oracle.ref_forces_fill(fn, x, X, adapter=mode, more_steps=steps)
+    for i, (r, g) in enumerate(zip(refs, gots)):
+        _same_fill(r, g, X.shape[0], f"step {i}")
+    X, fn = E.meshgen.regular2(512)
+    first, steady = oracle.ref_forces_step_seconds(fn, E.meshgen.drape_state(X, seed=0), X, steps=5, adapter=mode)
+    with capsys.disabled():
+        print(f"\n[adapter Forces::fill ({'zero copy' if mode == 'zero_copy' else 'copy'}), regular2 512^2, ArcSim mesh -> Eigen members] first call {first * 1e3:.1f} ms, steady step {steady * 1e3:.2f} ms")
+    assert steady < 0.1           # 412 MB per step; 13-20 ms on a B200 box
