@@ -48,7 +48,7 @@ shared_ptr<btc::Collision> to_btc(const eolc_contact &c) {
 void run(const Mesh &mesh, const shared_ptr<Obstacles> &obs, vector<shared_ptr<btc::Collision> > &cls, bool cd1) {
     static thread_local eolc::host::FlatMesh flat;
     static thread_local eolc::host::ObstaclesFlat of;
-    eolc::host::flatten(mesh, flat);                       // verts2 / faces2 of Collisions.cpp:13-27 (+ the stencils, unused here)
+    eolc::host::flatten_step(mesh, flat);                   // verts2 / faces2 of Collisions.cpp:13-27 (+ the stencils, unused here)
     flatten_obstacles(obs, of);
     // eolc_cd_plan_create (on a topology / threshold change) + eolc_cd_run; the records arrive in the thread's page-locked buffer and
     // are turned into btc::Collision objects straight from there (one allocation per contact, as the interface demands)

@@ -68,7 +68,7 @@ void Forces::fill(const Mesh &mesh, const Material &mat, const Eigen::Vector3d &
     // Flatten the ArcSim pointer mesh into page-locked arrays.  flatten() compares while it copies and renews
     // B.flat's version counters only when an index / a material coordinate really changed; fill() rebuilds the device plan when
     // the topology version moved (dynamic_remesh / preprocess, Scene.cpp:83-90) and skips M when X and the density did not.
-    eolc::host::flatten(mesh, B.flat);
+    eolc::host::flatten_step(mesh, B.flat);   // full walk, or positions only under EOLC_STATIC_TOPOLOGY=1
     // EoL nodes (flat.eol_index) switch the touched elements to the Eulerian-on-Lagrangian blocks (Forces.cpp:177-329, 399-497,
     // 580-683, 746-883) inside the library; dof = 3N + 2 (1 + largest EoL_index) must agree with mesh.EoL_Count.
     if ((int)mesh.EoL_Count != B.flat.EoL_Count) {
