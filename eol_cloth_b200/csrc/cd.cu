@@ -328,6 +328,40 @@ __global__ void __launch_bounds__(1024) k_scan(size_t n, const int *__restrict__
     if (threadIdx.x == 0) out[n] = carry;
 }
 
+// The same scan on many blocks for long inputs (a batched ensemble has ~3 x 10^5 block counts: 0.2 ms on one block): chunks of 8192
+// entries are scanned locally, their totals by the single-block kernel above, and the chunk offsets are added.
+constexpr int SCAN_CHUNK = 1024 * 8;
+__global__ void __launch_bounds__(1024) k_scan_local(size_t n, const int *__restrict__ in, int *__restrict__ out, int *__restrict__ chunk_total) {
+    constexpr int PER = 8;
+    __shared__ int s[32];
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t i0 = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * PER;
+    int v[PER], tot = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { v[q] = i0 + q < n ? in[i0 + q] : 0; tot += v[q]; }
+    int inc = tot;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
+    if (l == 31) s[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int t = s[l];
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, t, o); if (l >= o) t += u; }
+        s[l] = t;
+    }
+    __syncthreads();
+    int run = (w > 0 ? s[w - 1] : 0) + inc - tot;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { if (i0 + q < n) out[i0 + q] = run; run += v[q]; }
+    if (threadIdx.x == 1023) chunk_total[blockIdx.x] = run;
+}
+__global__ void __launch_bounds__(1024) k_scan_add(size_t n, int *__restrict__ out, const int *__restrict__ chunk_off, int n_chunks) {
+    const size_t i0 = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * 8;
+    const int add = chunk_off[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (i0 + q < n) out[i0 + q] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = chunk_off[n_chunks];
+}
+
 // ---- section A: cloth vertex vs box (boxTriCollision.cpp:675-764) -----------------------------------
 // returns winning j1 (or -1) and, if rec != NULL, fills the record
 __device__ int test_vertex_box(int i2, int F, V3 x2, const double *__restrict__ fnp, const BoxData &B, double threshold, eolc_contact *rec) {
@@ -822,26 +856,40 @@ __global__ void __launch_bounds__(256) k_C_sum(int nbx, long long nblk, const in
 // output slot; k_C_write then runs one thread per hit, all lanes busy.  The order of the work list is irrelevant (appended with an
 // integer atomic): every item writes its own, predetermined slot, so the output is the same bits every run.
 struct CHit { int32_t k2; int32_t sb_k1; int32_t slot; int32_t pad; };   // sb_k1 = (scene * nB + box) | k1 << 16
-__global__ void __launch_bounds__(256) k_C_expand(int E, int nB, const int *__restrict__ info, const int *__restrict__ blockoff,
+// One WARP per 256-item block (8 per CTA; a CTA per item block spent its time being scheduled: 196 k CTAs that mostly read two offsets
+// and return): lane l takes the items 8 l .. 8 l + 7, so the hits keep their item order.
+__global__ void __launch_bounds__(256) k_C_expand(int nbx, long long nblk, int nB, const int *__restrict__ info, const int *__restrict__ blockoff,
                                                   CHit *__restrict__ work, int *__restrict__ counter, int capacity, size_t scene_items,
                                                   size_t box_items, size_t secC_off) {
-    const int s = blockIdx.y / nB, b = blockIdx.y % nB;
-    const size_t item0 = s * scene_items + secC_off + b * box_items;
-    const size_t blk = item0 / 256 + blockIdx.x;
+    const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= nblk) return;
+    const int lane = threadIdx.x & 31;
+    const int bx = (int)(w % nbx);
+    const long long sb = w / nbx;
+    const size_t item0 = (size_t)(sb / nB) * scene_items + secC_off + (size_t)(sb % nB) * box_items;
+    const size_t blk = item0 / 256 + bx;
     const int base = blockoff[blk];
-    if (blockoff[blk + 1] == base) return;            // block-uniform
-    const int k2 = blockIdx.x * 256 + threadIdx.x;
-    const int mask = info[item0 + k2];
-    const int pre = block_excl_prefix(__popc(mask));
-    if (!mask) return;
-    const int n = __popc(mask);
-    const int at = atomicAdd(counter, n);
-    int q = 0;
-    for (int k1 = 0; k1 < 12; ++k1)
-        if (mask & (1 << k1)) {
-            if (at + q < capacity) work[at + q] = CHit{k2, (int)blockIdx.y | (k1 << 16), base + pre + q, 0};
-            ++q;
-        }
+    if (blockoff[blk + 1] == base) return;            // warp-uniform
+    const int4 *p = reinterpret_cast<const int4 *>(info + item0 + (size_t)bx * 256 + 8 * lane);
+    const int4 m0 = p[0], m1 = p[1];
+    const int m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cnt += __popc(m[q]);
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (!cnt) return;
+    int slot = base + inc - cnt;
+    int at = atomicAdd(counter, cnt);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int k2 = bx * 256 + 8 * lane + q;
+        for (int k1 = 0; k1 < 12; ++k1)
+            if (m[q] & (1 << k1)) {
+                if (at < capacity) work[at] = CHit{k2, (int)sb | (k1 << 16), slot, 0};
+                ++at; ++slot;
+            }
+    }
 }
 __global__ void __launch_bounds__(256) k_C_write(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
                                                  const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
@@ -892,6 +940,7 @@ struct eolc_cd_plan {
     DevBuf<CHit> d_chits;               // work list of section C's write pass
     DevBuf<int> d_counter;              // [0]: pairs in d_cands, [1]: hits in d_chits
     DevBuf<unsigned long long> d_cands; // work list of section C's test pass: item | k1 << 60
+    DevBuf<int> d_scan_tmp;             // multi-block scan: chunk totals and their offsets
     DevBuf<int32_t> d_rows_i;           // contact rows (eolc_cd_contact_rows): row_nnz [n] + cols [9 n]
     DevBuf<double> d_rows_v;            // vals [9 n]
     DevBuf<unsigned char> d_eol;
@@ -1090,7 +1139,15 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
             k_C_sum<<<(unsigned)((nblkC + 7) / 8), 256, 0, st>>>((int)(nC / 256), nblkC, P->d_info.p, P->d_blocksum.p, scene_items, box_items, secBox + nA + nBc, nB);
             launches += 3;
         }
-        k_scan<<<1, 1024, 0, st>>>(nblocks, P->d_blocksum.p, P->d_blockoff.p); ++launches;
+        if (nblocks <= (size_t)4 * SCAN_CHUNK) { k_scan<<<1, 1024, 0, st>>>(nblocks, P->d_blocksum.p, P->d_blockoff.p); ++launches; }
+        else {
+            const int nch = (int)((nblocks + SCAN_CHUNK - 1) / SCAN_CHUNK);
+            EOLC_CUDA(P->d_scan_tmp.ensure(2 * (size_t)nch + 1));
+            k_scan_local<<<nch, 1024, 0, st>>>(nblocks, P->d_blocksum.p, P->d_blockoff.p, P->d_scan_tmp.p);
+            k_scan<<<1, 1024, 0, st>>>((size_t)nch, P->d_scan_tmp.p, P->d_scan_tmp.p + nch);
+            k_scan_add<<<nch, 1024, 0, st>>>(nblocks, P->d_blockoff.p, P->d_scan_tmp.p + nch, nch);
+            launches += 3;
+        }
         EOLC_CUDA(cudaMemcpyAsync(P->p_blockoff.p, P->d_blockoff.p, sizeof(int) * (nblocks + 1), cudaMemcpyDeviceToHost, st));
         EOLC_CUDA(cudaMemcpyAsync(P->p_counter.p, P->d_counter.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
         EOLC_CUDA(cudaStreamSynchronize(st));
@@ -1128,7 +1185,7 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
             {
                 // every record has its slot: the work list of section C can hold at most `total` items
                 EOLC_CUDA(P->d_chits.ensure((size_t)total + 1));
-                k_C_expand<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_info.p, P->d_blockoff.p, P->d_chits.p, P->d_counter.p + 1, total, scene_items, box_items, secBox + nA + nBc);
+                k_C_expand<<<(unsigned)((nblkC + 7) / 8), 256, 0, st>>>((int)(nC / 256), nblkC, nB, P->d_info.p, P->d_blockoff.p, P->d_chits.p, P->d_counter.p + 1, total, scene_items, box_items, secBox + nA + nBc);
                 const int gridC = std::max(1, std::min((total + 255) / 256, P->ctx->sm_count * 2));
                 k_C_write<<<gridC, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_chits.p, P->d_counter.p + 1, total, P->d_out.p, xs, fs, remap_box_indices, nP);
                 ++launches;
