@@ -452,7 +452,23 @@ __global__ void __launch_bounds__(256) k_A_count(int N, int F, int nB, const dou
     if (i2 < N) j1 = test_vertex_box(i2, F, dcol(xp + s * xstride, i2), fnp + s * fstride, boxes[b], threshold, nullptr);
     size_t item0 = s * scene_items + secA_off + b * box_items;
     info[item0 + blockIdx.x * 256 + threadIdx.x] = j1;
-    block_count_store(j1 >= 0 ? 1 : 0, blocksum, item0 / 256 + blockIdx.x);
+    // no block-wide count here: the warps of a block finish far apart (a vertex outside the box returns after one AABB test, one on a
+    // face runs the barycentric path), and a barrier kept the early ones — and the CTA's slot — waiting (46 % of the kernel's stall
+    // samples, ncu r02k).  k_A_sum counts the hits of every 256-item block afterwards, one warp per block.
+    (void)blocksum;
+}
+__global__ void __launch_bounds__(256) k_A_sum(int nbx, long long nblk, const int *__restrict__ info, int *__restrict__ blocksum,
+                                               size_t scene_items, size_t box_items, size_t secA_off, int nB) {
+    const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (w >= nblk) return;
+    const int bx = (int)(w % nbx);
+    const long long sb = w / nbx;
+    const size_t item0 = (size_t)(sb / nB) * scene_items + secA_off + (size_t)(sb % nB) * box_items;
+    const int4 *p = reinterpret_cast<const int4 *>(info + item0 + (size_t)bx * 256 + 8 * (threadIdx.x & 31));
+    const int4 m0 = p[0], m1 = p[1];
+    int t = (m0.x >= 0) + (m0.y >= 0) + (m0.z >= 0) + (m0.w >= 0) + (m1.x >= 0) + (m1.y >= 0) + (m1.z >= 0) + (m1.w >= 0);
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) blocksum[item0 / 256 + bx] = t;
 }
 // The hits of 32 consecutive items occupy consecutive output slots (prefix order), so a WARP's records form one contiguous range: they
 // are staged in the warp's slice of shared memory and leave with coalesced 8-byte stores (a record is 33 doubles; writing it from one
@@ -1148,6 +1164,11 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
     }
     if (nB) {
         k_A_count<<<dim3((unsigned)(nA / 256), S * nB), 256, 0, st>>>(N, F, nB, P->d_xp.p, P->d_fnp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, xs, fs, scene_items, box_items, secBox);
+        {
+            const long long nblkA = (long long)(nA / 256) * S * nB;
+            k_A_sum<<<(unsigned)((nblkA + 7) / 8), 256, 0, st>>>((int)(nA / 256), nblkA, P->d_info.p, P->d_blocksum.p, scene_items, box_items, secBox, nB);
+            ++launches;
+        }
         k_PT_partial<<<dim3(nchunk, S * nB * 8), 256, 0, st>>>(F, nB * 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, P->d_fnp.p, P->d_aabb.p, thr, P->d_partial.p, xs, fs);
         k_PT_final<<<S * nB, 256, 0, st>>>(nchunk, 8, nB, P->d_partial.p, P->d_info.p, P->d_blocksum.p, scene_items, secBox + nA, box_items);
         launches += 3;
