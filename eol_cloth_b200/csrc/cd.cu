@@ -579,6 +579,75 @@ __global__ void __launch_bounds__(256) k_PT_partial(int F, int npts_per_scene, i
         partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = b0;
     }
 }
+// Box mode, all 8 corners of a box against a chunk of the cloth's faces in ONE pass: a face's indices, its three vertices and its
+// normal are loaded once and tested against the eight corners (the per-corner kernel above read every face eight times: 1.2 GB of DRAM
+// and eight times the gather instructions on the 4096-scene batch).  Same expressions on the same inputs as test_point_tri, so the
+// same bits; partial[] has the layout of the per-corner kernel.  grid: (nchunk, S * nB)
+__global__ void __launch_bounds__(256, 4) k_PT_partial8(int F, int nB, const BoxData *__restrict__ boxes, const int32_t *__restrict__ fn,
+                                                     const double *__restrict__ xp, const double *__restrict__ fnp,
+                                                     const double *__restrict__ aabbB2, double threshold, Cand *__restrict__ partial,
+                                                     size_t xstride, size_t fstride) {
+    const int s = blockIdx.y / nB, b = blockIdx.y % nB;
+    const BoxData &B = boxes[b];
+    // the corners and their normals live in shared memory (uniform reads): 48 doubles in registers would leave one CTA per SM
+    __shared__ double cx[8][3], cn[8][3];
+    __shared__ unsigned live_s;
+    if (threadIdx.x < 24) { cx[threadIdx.x / 3][threadIdx.x % 3] = B.verts1[threadIdx.x / 3][threadIdx.x % 3]; cn[threadIdx.x / 3][threadIdx.x % 3] = B.vertNors1[threadIdx.x / 3][threadIdx.x % 3]; }
+    if (threadIdx.x == 0) {
+        unsigned l = 0;
+        for (int c = 0; c < 8; ++c) if (check_aabb_point(bcol(B.verts1, c), aabbB2 + 6 * s)) l |= 1u << c;
+        live_s = l;
+    }
+    __syncthreads();
+    const unsigned live = live_s;
+    // a thread's best candidate per corner: shared memory, [corner][thread] (rarely written: only a hit closer than the best so far)
+    __shared__ double bd[8][256];
+    __shared__ int bj[8][256];
+    for (int c = 0; c < 8; ++c) { bd[c][threadIdx.x] = 0.0; bj[c][threadIdx.x] = -1; }
+    if (live) {
+        const double lim = mul(5.0, threshold);
+        const double *xs = xp + s * xstride, *fs = fnp + s * fstride;
+        for (int j2 = blockIdx.x * 256 + threadIdx.x; j2 < F; j2 += gridDim.x * 256) {
+            const V3 x2a = dcol(xs, fn[3 * (size_t)j2]), x2b = dcol(xs, fn[3 * (size_t)j2 + 1]), x2c = dcol(xs, fn[3 * (size_t)j2 + 2]);
+            const V3 n2 = dcol(fs, j2);
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                if (!((live >> c) & 1u)) continue;
+                const V3 x1c = mk(cx[c][0], cx[c][1], cx[c][2]), nor1c = mk(cn[c][0], cn[c][1], cn[c][2]);
+                V3 nor2 = n2;                                     // test_point_tri, line by line
+                if (dot(nor1c, nor2) < 0.0) nor2 = neg(nor2);
+                const double proj = dot(x1c - x2a, nor2);
+                if (proj < 0.0) continue;
+                const V3 x2 = x1c - scale(proj, nor2);
+                const double dist = norm(x2 - x1c);
+                if (dist > lim) continue;
+                double u, v;
+                barycentric(u, v, x2a, x2b, x2c, x1c);
+                const double w = sub(sub(1.0, u), v);
+                if (u < 0.0 || 1.0 < u || v < 0.0 || 1.0 < v || w < 0.0 || 1.0 < w) continue;
+                Cand cur; cur.dist = bd[c][threadIdx.x]; cur.j2 = bj[c][threadIdx.x];
+                if (better(dist, j2, cur)) { bd[c][threadIdx.x] = dist; bj[c][threadIdx.x] = j2; }
+            }
+        }
+    }
+    __shared__ Cand sm[8][8];
+    for (int c = 0; c < 8; ++c) {
+        Cand bc; bc.dist = bd[c][threadIdx.x]; bc.j2 = bj[c][threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double d = __shfl_xor_sync(0xffffffffu, bc.dist, o);
+            const int j = __shfl_xor_sync(0xffffffffu, bc.j2, o);
+            if (j >= 0 && better(d, j, bc)) { bc.dist = d; bc.j2 = j; }
+        }
+        if ((threadIdx.x & 31) == 0) sm[c][threadIdx.x >> 5] = bc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int c = threadIdx.x;
+        Cand b0 = sm[c][0];
+        for (int i = 1; i < 8; ++i) if (sm[c][i].j2 >= 0 && better(sm[c][i].dist, sm[c][i].j2, b0)) b0 = sm[c][i];
+        partial[((size_t)blockIdx.y * 8 + c) * gridDim.x + blockIdx.x] = b0;
+    }
+}
 // one warp per (scene, point): reduce the partials, store winner j2 in info[], count in blocksum (section <= 256 items)
 // grid: S * nsec blocks of 256 threads; section sec of scene s holds pts_per_sec points (8 per box, or P)
 __global__ void __launch_bounds__(256) k_PT_final(int nchunk, int pts_per_sec, int nsec, const Cand *__restrict__ partial,
@@ -1169,7 +1238,7 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
             k_A_sum<<<(unsigned)((nblkA + 7) / 8), 256, 0, st>>>((int)(nA / 256), nblkA, P->d_info.p, P->d_blocksum.p, scene_items, box_items, secBox, nB);
             ++launches;
         }
-        k_PT_partial<<<dim3(nchunk, S * nB * 8), 256, 0, st>>>(F, nB * 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, P->d_fnp.p, P->d_aabb.p, thr, P->d_partial.p, xs, fs);
+        k_PT_partial8<<<dim3(nchunk, S * nB), 256, 0, st>>>(F, nB, P->d_boxes.p, P->d_fn.p, P->d_xp.p, P->d_fnp.p, P->d_aabb.p, thr, P->d_partial.p, xs, fs);
         k_PT_final<<<S * nB, 256, 0, st>>>(nchunk, 8, nB, P->d_partial.p, P->d_info.p, P->d_blocksum.p, scene_items, secBox + nA, box_items);
         launches += 3;
     }
