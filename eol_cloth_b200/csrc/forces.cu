@@ -45,6 +45,7 @@ struct eolc_forces_plan {
     Pattern pat;                                  // block pattern of M and MDK
     std::vector<int32_t> h_outerM, h_innerM, h_outerK, h_innerK;  // lazily built Eigen-style arrays
     int pipeline = 0;                             // 0 = tiles, 1 = rows
+    int max_degM = -1;                            // largest number of column blocks in a row of M (computed on first use by the rhs kernel)
     // EOL branch (forces_eol.h); n_eol == 0: Lagrangian mesh, nothing of this is used
     int32_t n_eol = 0, eol_faces = 0, eol_edges = 0, eol_targets = 0;
     int64_t eol_scratch = 0;
@@ -1161,8 +1162,18 @@ int eolc_forces_rhs_dev(eolc_forces_plan *plan, const double *M_vals_dev, const 
         EOLC_CUDA(cudaGetLastError());
         return EOLC_OK;
     }
-    const int grid = std::min((plan->N + 2 * solve::WARPS - 1) / (2 * solve::WARPS), 16 * plan->ctx->sm_count);
-    solve::k_rhs<<<grid, solve::THREADS, 0, plan->ctx->stream>>>(plan->N, plan->d_blkM.p, plan->d_nbrM.p, M_vals_dev, f_dev, v_dev, h, b_dev);
+    if (plan->max_degM < 0) {
+        int m = 0;
+        for (int32_t a = 0; a < plan->N; ++a) m = std::max(m, (int)(plan->pat.blkptrM[a + 1] - plan->pat.blkptrM[a]));
+        plan->max_degM = m;
+    }
+    if (plan->max_degM <= 8) {     // 8 lanes per node: four nodes per warp instead of two, the same bits
+        const int grid = std::min((plan->N + 4 * solve::WARPS - 1) / (4 * solve::WARPS), 16 * plan->ctx->sm_count);
+        solve::k_rhs<8><<<grid, solve::THREADS, 0, plan->ctx->stream>>>(plan->N, plan->d_blkM.p, plan->d_nbrM.p, M_vals_dev, f_dev, v_dev, h, b_dev);
+    } else {
+        const int grid = std::min((plan->N + 2 * solve::WARPS - 1) / (2 * solve::WARPS), 16 * plan->ctx->sm_count);
+        solve::k_rhs<16><<<grid, solve::THREADS, 0, plan->ctx->stream>>>(plan->N, plan->d_blkM.p, plan->d_nbrM.p, M_vals_dev, f_dev, v_dev, h, b_dev);
+    }
     EOLC_CUDA(cudaGetLastError());
     return EOLC_OK;
 }

@@ -27,6 +27,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Rows of a node times x, a HALF warp per node (a structured cloth node has 13 column blocks in MDK, 7 in M): lane hl of the half
 // takes column blocks hl, hl + 16, ... — one index load, the block's three x values, its 3 x 3 values (three runs of 3 consecutive
 // doubles, neighbouring lanes on neighbouring runs) and 9 FMAs — then a fixed 16-lane tree.  y[0..2] valid in every lane of the half.
+// LPN lanes per node: 16 in general; 8 when no row has more than 8 column blocks (the mass matrix of a triangle mesh of valence <= 7):
+// twice the nodes per warp, and bit for bit the same sums (with at most one block per lane the 16-lane tree only adds zeros on top).
+template <int LPN = 16>
 __device__ __forceinline__ void node_rows_times(int hl, bool active, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
                                                 const double *__restrict__ vals, const double *__restrict__ x, int a, double y[3]) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -34,7 +37,7 @@ __device__ __forceinline__ void node_rows_times(int hl, bool active, const int32
         const int b0 = blkptr[a], deg = blkptr[a + 1] - b0;
         const unsigned n3 = 3u * (unsigned)deg;
         const double *row = vals + 9 * (size_t)b0;
-        for (int p = hl; p < deg; p += 16) {
+        for (int p = hl; p < deg; p += LPN) {
             const double *xp = x + 3 * (size_t)nbr[b0 + p];
             const double x0 = xp[0], x1 = xp[1], x2 = xp[2];
             const double *r = row + 3u * (unsigned)p;
@@ -44,7 +47,7 @@ __device__ __forceinline__ void node_rows_times(int hl, bool active, const int32
         }
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
+    for (int o = LPN / 2; o > 0; o >>= 1) {
         s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
     y[0] = s0; y[1] = s1; y[2] = s2;
@@ -62,14 +65,16 @@ __device__ __forceinline__ double block_sum(double warp_value, double *sh) {
 }
 
 // b = -(M v + h f)
+template <int LPN>
 __global__ void __launch_bounds__(THREADS) k_rhs(int N, const int32_t *__restrict__ blkptr, const int32_t *__restrict__ nbr,
                                                  const double *__restrict__ Mv, const double *__restrict__ f, const double *__restrict__ v,
                                                  double h, double *__restrict__ b) {
-    const int hl = threadIdx.x & 15;
-    for (int a0 = 2 * (blockIdx.x * WARPS + (threadIdx.x >> 5)); a0 < N; a0 += 2 * gridDim.x * WARPS) {
-        const int a = a0 + ((threadIdx.x >> 4) & 1);
+    constexpr int NPW = 32 / LPN;                       // nodes per warp
+    const int hl = threadIdx.x & (LPN - 1);
+    for (int a0 = NPW * (blockIdx.x * WARPS + (threadIdx.x >> 5)); a0 < N; a0 += NPW * gridDim.x * WARPS) {
+        const int a = a0 + ((threadIdx.x & 31) / LPN);
         double y[3];
-        node_rows_times(hl, a < N, blkptr, nbr, Mv, v, a, y);
+        node_rows_times<LPN>(hl, a < N, blkptr, nbr, Mv, v, a, y);
         if (hl < 3 && a < N) b[3 * (size_t)a + hl] = -((hl == 0 ? y[0] : hl == 1 ? y[1] : y[2]) + h * f[3 * (size_t)a + hl]);
     }
 }
