@@ -221,22 +221,25 @@ __global__ void k_perturb(int N, const double *__restrict__ x, const double *__r
     xp[o + i] = add(x[o + i], r[i]);   // verts2.block<3,1>(0,i2) += r
 }
 
-// face normals of the perturbed verts (createFaceNormals :233-247: dba.cross(-dac)) and of the unperturbed verts
-// (createEdges :193-214: (xb-xa).cross(xc-xa)); -(xa-xc) == xc-xa exactly, so both use the same expression.
-__global__ void k_face_normals(int F, const int32_t *__restrict__ fn, const double *__restrict__ x, const double *__restrict__ xp,
-                               double *__restrict__ fn0, double *__restrict__ fnp, size_t xstride, size_t fstride) {
+// Face normals.  createFaceNormals (:233-247) forms dba.cross(-dac) on the perturbed verts, createEdges (:193-214)
+// (xb-xa).cross(xc-xa) on the unperturbed ones; both are kept as written (they differ at most in the sign of a zero).
+// Box scenes evaluate them where they are needed (section A's and C's records, every face once in section Bc) instead of storing
+// two normals per face first: on the 4096 x 64^2 batch that pass wrote 1.56 GB and took 0.51 ms of the 4.1 ms narrow phase.
+__device__ __forceinline__ V3 face_cross_p(V3 xa, V3 xb, V3 xc) { return cross(xb - xa, neg(xa - xc)); }
+__device__ __forceinline__ V3 face_normal_p(const int32_t *__restrict__ fn, const double *__restrict__ xp, int k) {
+    return normalized(face_cross_p(dcol(xp, fn[3 * (size_t)k]), dcol(xp, fn[3 * (size_t)k + 1]), dcol(xp, fn[3 * (size_t)k + 2])));
+}
+__device__ __forceinline__ V3 face_normal_0(const int32_t *__restrict__ fn, const double *__restrict__ x, int k) {
+    V3 xa = dcol(x, fn[3 * (size_t)k]), xb = dcol(x, fn[3 * (size_t)k + 1]), xc = dcol(x, fn[3 * (size_t)k + 2]);
+    return normalized(cross(xb - xa, xc - xa));
+}
+// Stored normals of the perturbed verts: only for obstacle POINTS (section PT tests every point against every face, so a face's
+// normal would otherwise be formed once per point).
+__global__ void k_face_normals(int F, const int32_t *__restrict__ fn, const double *__restrict__ xp, double *__restrict__ fnp,
+                               size_t xstride, size_t fstride) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= F) return;
-    size_t xo = blockIdx.y * xstride, fo = blockIdx.y * fstride;
-    int a = fn[3 * k], b = fn[3 * k + 1], c = fn[3 * k + 2];
-    {
-        V3 xa = dcol(x + xo, a), xb = dcol(x + xo, b), xc = dcol(x + xo, c);
-        st(fn0 + fo + 3 * (size_t)k, normalized(cross(xb - xa, xc - xa)));
-    }
-    {
-        V3 xa = dcol(xp + xo, a), xb = dcol(xp + xo, b), xc = dcol(xp + xo, c);
-        st(fnp + fo + 3 * (size_t)k, normalized(cross(xb - xa, neg(xa - xc))));
-    }
+    st(fnp + blockIdx.y * fstride + 3 * (size_t)k, face_normal_p(fn, xp + blockIdx.y * xstride, k));
 }
 
 // per-scene AABB of the perturbed verts (build_AABB_B :425-433); min/max are order independent.
@@ -362,9 +365,21 @@ __global__ void __launch_bounds__(1024) k_scan_add(size_t n, int *__restrict__ o
     if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = chunk_off[n_chunks];
 }
 
+// Division-free screen of barycentric()'s verdict.  nb, ng, denom are the SAME floats barycentric() divides (beta = nb / denom,
+// gamma = ng / denom; same operations in the same order), and IEEE division is monotone with a relative error of 2^-53: a quotient
+// beyond [-1e-6, 1 + 1e-6] stays beyond [0, 1] when rounded, and u = (1 - beta) - gamma, w = (1 - u) - beta follow beta and gamma
+// to a few 1e-16 while both are O(1).  So `true` means the reference's `u < 0 || 1 < u || v < 0 || ...` rejects for certain,
+// whatever the triangle's shape; zero or NaN denominators are left to the reference's own expressions.
+__device__ __forceinline__ bool barycentric_rejects(double nb, double ng, double denom) {
+    const double e = 1e-6;
+    if (denom > 0.0) { const double lo = -e * denom, hi = denom + e * denom; return nb < lo || nb > hi || ng < lo || ng > hi || nb + ng > hi; }
+    if (denom < 0.0) { const double lo = -e * denom, hi = denom + e * denom; return nb > lo || nb < hi || ng > lo || ng < hi || nb + ng < hi; }
+    return false;
+}
+
 // ---- section A: cloth vertex vs box (boxTriCollision.cpp:675-764) -----------------------------------
 // returns winning j1 (or -1) and, if rec != NULL, fills the record
-__device__ int test_vertex_box(int i2, int F, V3 x2, const double *__restrict__ fnp, const BoxData &B, double threshold, eolc_contact *rec) {
+__device__ int test_vertex_box(int i2, int F, V3 x2, const int32_t *__restrict__ fn, const double *__restrict__ xs, const BoxData &B, double threshold, eolc_contact *rec) {
     if (!check_aabb_point(x2, B.aabbB1)) return -1;
     // :689-697 — inside all 24 half-spaces; the projections are kept: the second loop (:699-) forms the same expression again
     double pj[24];
@@ -390,6 +405,12 @@ __device__ int test_vertex_box(int i2, int F, V3 x2, const double *__restrict__ 
         V3 nor1 = bcol(B.faceNors1, j1);
         if (proj > 0.0) continue;
         V3 x1 = x2 - scale(proj, nor1);
+        {   // a vertex resting on a box face is near the planes of that face's four triangles and inside one of them: the other three
+            // are turned away here without the square root and the two divisions (barycentric_rejects: same floats, same verdict)
+            const V3 v0 = x1b - x1a, v1 = x1c - x1a, v2 = x1 - x1a;
+            const double d00 = dot(v0, v0), d01 = dot(v0, v1), d11 = dot(v1, v1), d20 = dot(v2, v0), d21 = dot(v2, v1);
+            if (barycentric_rejects(sub(mul(d11, d20), mul(d01, d21)), sub(mul(d00, d21), mul(d01, d20)), sub(mul(d00, d11), mul(d01, d01)))) continue;
+        }
         double dist = norm(x2 - x1);
         if (dist > lim) continue;
         double u, v;
@@ -400,7 +421,7 @@ __device__ int test_vertex_box(int i2, int F, V3 x2, const double *__restrict__ 
             best = j1; bestd = dist;
             if (rec) {
                 // faceNors2.col(i2): indexed with the VERTEX id (reference quirk, :731); out of range -> zero
-                V3 nor2 = i2 < F ? dcol(fnp, i2) : mk(0, 0, 0);
+                V3 nor2 = i2 < F ? face_normal_p(fn, xs, i2) : mk(0, 0, 0);
                 if (dot(nor2, nor1) < 0.0) nor2 = neg(nor2);
                 zero_contact(*rec);
                 rec->dist = dist;
@@ -419,7 +440,7 @@ __device__ int test_vertex_box(int i2, int F, V3 x2, const double *__restrict__ 
 
 // The record of cloth vertex i2 against its winning box triangle j1 (what the loop above leaves in *rec for the winner): the same
 // expressions on the same inputs, so the same bits, without the other 23 triangles.
-__device__ __forceinline__ void vertex_box_record(int i2, int j1, int F, V3 x2, const double *__restrict__ fnp, const BoxData &B, eolc_contact *rec) {
+__device__ __forceinline__ void vertex_box_record(int i2, int j1, int F, V3 x2, const int32_t *__restrict__ fn, const double *__restrict__ xs, const BoxData &B, eolc_contact *rec) {
     V3 x1a = bcol(B.verts1, c_faces1[j1][0]), x1b = bcol(B.verts1, c_faces1[j1][1]), x1c = bcol(B.verts1, c_faces1[j1][2]);
     V3 nor1 = bcol(B.faceNors1, j1);
     double proj = dot(nor1, x2 - x1a);
@@ -428,7 +449,7 @@ __device__ __forceinline__ void vertex_box_record(int i2, int j1, int F, V3 x2, 
     double u, v;
     barycentric(u, v, x1a, x1b, x1c, x1);
     double w = sub(sub(1.0, u), v);
-    V3 nor2 = i2 < F ? dcol(fnp, i2) : mk(0, 0, 0);
+    V3 nor2 = i2 < F ? face_normal_p(fn, xs, i2) : mk(0, 0, 0);
     if (dot(nor2, nor1) < 0.0) nor2 = neg(nor2);
     zero_contact(*rec);
     rec->dist = dist;
@@ -442,14 +463,14 @@ __device__ __forceinline__ void vertex_box_record(int i2, int j1, int F, V3 x2, 
 }
 
 // grid: (ceil(N/256), S*B)
-__global__ void __launch_bounds__(256) k_A_count(int N, int F, int nB, const double *__restrict__ xp, const double *__restrict__ fnp,
+__global__ void __launch_bounds__(256) k_A_count(int N, int F, int nB, const double *__restrict__ xp,
                                                  const BoxData *__restrict__ boxes, double threshold, int *__restrict__ info,
-                                                 int *__restrict__ blocksum, size_t xstride, size_t fstride,
+                                                 int *__restrict__ blocksum, size_t xstride,
                                                  size_t scene_items, size_t box_items, size_t secA_off) {
     int s = blockIdx.y / nB, b = blockIdx.y % nB;
     int i2 = blockIdx.x * 256 + threadIdx.x;
     int j1 = -1;
-    if (i2 < N) j1 = test_vertex_box(i2, F, dcol(xp + s * xstride, i2), fnp + s * fstride, boxes[b], threshold, nullptr);
+    if (i2 < N) j1 = test_vertex_box(i2, F, dcol(xp + s * xstride, i2), nullptr, nullptr, boxes[b], threshold, nullptr);
     size_t item0 = s * scene_items + secA_off + b * box_items;
     info[item0 + blockIdx.x * 256 + threadIdx.x] = j1;
     // no block-wide count here: the warps of a block finish far apart (a vertex outside the box returns after one AABB test, one on a
@@ -476,10 +497,10 @@ __global__ void __launch_bounds__(256) k_A_sum(int nbx, long long nblk, const in
 // 256-item block, warp of it), no block barrier: the slot of a warp's first hit is the block's offset plus the hits of the block's
 // earlier items, which the warp counts itself from the block's 256 info words (one coalesced kilobyte).  (The first version staged per
 // CTA with three barriers per item block and ran at a third of the warp slots: 0.55 ms on the 4096 x 64^2 batch.)
-__global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, int S, const double *__restrict__ xp, const double *__restrict__ fnp,
+__global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, int S, const double *__restrict__ xp, const int32_t *__restrict__ fn,
                                                  const BoxData *__restrict__ boxes, double threshold, const int *__restrict__ info,
                                                  const int *__restrict__ blockoff, eolc_contact *__restrict__ out, size_t xstride,
-                                                 size_t fstride, size_t scene_items, size_t box_items, size_t secA_off) {
+                                                 size_t scene_items, size_t box_items, size_t secA_off) {
     extern __shared__ __align__(16) unsigned char stage_raw[];
     static_assert(sizeof(eolc_contact) % 8 == 0, "records are copied as 8-byte words");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -510,7 +531,7 @@ __global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, int S, co
         if (cnt == 0) continue;                        // warp-uniform
         const int pre = __popc(hits & ((1u << lane) - 1u));
         if (j1 >= 0) {                                 // the record is built in place in the warp's stage
-            vertex_box_record(i2, j1, F, dcol(xp + s * xstride, i2), fnp + s * fstride, boxes[b], &stage[pre]);
+            vertex_box_record(i2, j1, F, dcol(xp + s * xstride, i2), fn, xp + s * xstride, boxes[b], &stage[pre]);
             finish_contact(stage[pre], threshold);
         }
         __syncwarp();
@@ -531,7 +552,7 @@ __device__ __forceinline__ bool test_point_tri(V3 x1, V3 nor1, int j2, const int
                                                const double *__restrict__ fnp, double lim, double &dist, V3 &nor2, V3 &x2,
                                                double &u, double &v, double &w) {
     V3 x2a = dcol(xp, fn[3 * (size_t)j2]), x2b = dcol(xp, fn[3 * (size_t)j2 + 1]), x2c = dcol(xp, fn[3 * (size_t)j2 + 2]);
-    nor2 = dcol(fnp, j2);
+    nor2 = fnp ? dcol(fnp, j2) : normalized(face_cross_p(x2a, x2b, x2c));   // NULL: box scenes, no stored normals
     if (dot(nor1, nor2) < 0.0) nor2 = neg(nor2);
     double proj = dot(x1 - x2a, nor2);
     if (proj < 0.0) return false;
@@ -558,7 +579,7 @@ __global__ void __launch_bounds__(256) k_PT_partial(int F, int npts_per_scene, i
     Cand best; best.dist = 0.0; best.j2 = -1;
     if (check_aabb_point(x1, aabbB2 + 6 * s)) {
         const double lim = mul(5.0, threshold);
-        const double *xs = xp + s * xstride, *fs = fnp + s * fstride;
+        const double *xs = xp + s * xstride, *fs = fnp ? fnp + s * fstride : nullptr;
         for (int j2 = blockIdx.x * 256 + threadIdx.x; j2 < F; j2 += gridDim.x * 256) {
             double dist, u, v, w; V3 nor2, x2;
             if (test_point_tri(x1, nor1, j2, fn, xs, fs, lim, dist, nor2, x2, u, v, w) && better(dist, j2, best)) { best.dist = dist; best.j2 = j2; }
@@ -579,59 +600,108 @@ __global__ void __launch_bounds__(256) k_PT_partial(int F, int npts_per_scene, i
         partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = b0;
     }
 }
+#ifndef EOLC_PT8_CTAS
+#define EOLC_PT8_CTAS 4      // resident CTAs per SM the register allocation of k_PT_partial8 aims at
+#endif
 // Box mode, all 8 corners of a box against a chunk of the cloth's faces in ONE pass: a face's indices, its three vertices and its
 // normal are loaded once and tested against the eight corners (the per-corner kernel above read every face eight times: 1.2 GB of DRAM
 // and eight times the gather instructions on the 4096-scene batch).  Same expressions on the same inputs as test_point_tri, so the
 // same bits; partial[] has the layout of the per-corner kernel.  grid: (nchunk, S * nB)
-__global__ void __launch_bounds__(256, 4) k_PT_partial8(int F, int nB, const BoxData *__restrict__ boxes, const int32_t *__restrict__ fn,
-                                                     const double *__restrict__ xp, const double *__restrict__ fnp,
+// The reference's test of one point against one triangle (test_point_tri above, line by line) for the few pairs that pass the screens
+// of k_PT_partial8; out of line so that the screening loop stays small.
+__device__ __noinline__ bool point_tri_exact(V3 x1c, V3 nor1c, V3 x2a, V3 x2b, V3 x2c, double lim, double &dist) {
+    V3 nor2 = normalized(face_cross_p(x2a, x2b, x2c));
+    if (dot(nor1c, nor2) < 0.0) nor2 = neg(nor2);
+    const double proj = dot(x1c - x2a, nor2);
+    if (proj < 0.0) return false;
+    const V3 x2 = x1c - scale(proj, nor2);
+    dist = norm(x2 - x1c);
+    if (dist > lim) return false;
+    double u, v;
+    barycentric(u, v, x2a, x2b, x2c, x1c);
+    const double w = sub(sub(1.0, u), v);
+    return !(u < 0.0 || 1.0 < u || v < 0.0 || 1.0 < v || w < 0.0 || 1.0 < w);
+}
+__global__ void __launch_bounds__(256, EOLC_PT8_CTAS) k_PT_partial8(int F, int nB, const BoxData *__restrict__ boxes, const int32_t *__restrict__ fn,
+                                                     const double *__restrict__ xp,
                                                      const double *__restrict__ aabbB2, double threshold, Cand *__restrict__ partial,
-                                                     size_t xstride, size_t fstride) {
+                                                     size_t xstride) {
     const int s = blockIdx.y / nB, b = blockIdx.y % nB;
     const BoxData &B = boxes[b];
     // the corners and their normals live in shared memory (uniform reads): 48 doubles in registers would leave one CTA per SM
-    __shared__ double cx[8][3], cn[8][3];
-    __shared__ unsigned live_s;
+    __shared__ double cx[8][3], cn[8][3], cl1[8];
+    __shared__ int lc[8], nlive_s;                       // the corners inside the cloth's AABB (:774), ascending
     if (threadIdx.x < 24) { cx[threadIdx.x / 3][threadIdx.x % 3] = B.verts1[threadIdx.x / 3][threadIdx.x % 3]; cn[threadIdx.x / 3][threadIdx.x % 3] = B.vertNors1[threadIdx.x / 3][threadIdx.x % 3]; }
     if (threadIdx.x == 0) {
-        unsigned l = 0;
-        for (int c = 0; c < 8; ++c) if (check_aabb_point(bcol(B.verts1, c), aabbB2 + 6 * s)) l |= 1u << c;
-        live_s = l;
+        int n = 0;
+        for (int c = 0; c < 8; ++c) {
+            const V3 p = bcol(B.verts1, c);
+            cl1[c] = fabs(p.x) + fabs(p.y) + fabs(p.z);
+            if (check_aabb_point(p, aabbB2 + 6 * s)) lc[n++] = c;
+        }
+        nlive_s = n;
     }
     __syncthreads();
-    const unsigned live = live_s;
+    const int nlive = nlive_s;
     // a thread's best candidate per corner: shared memory, [corner][thread] (rarely written: only a hit closer than the best so far)
     __shared__ double bd[8][256];
     __shared__ int bj[8][256];
-    for (int c = 0; c < 8; ++c) { bd[c][threadIdx.x] = 0.0; bj[c][threadIdx.x] = -1; }
-    if (live) {
+    for (int q = 0; q < nlive; ++q) { bd[lc[q]][threadIdx.x] = 0.0; bj[lc[q]][threadIdx.x] = -1; }
+    if (nlive) {
         const double lim = mul(5.0, threshold);
-        const double *xs = xp + s * xstride, *fs = fnp + s * fstride;
+        const double *xs = xp + s * xstride;
+        // Two conservative screens the reference does not have and that cannot change a result; only pairs that pass both run the
+        // reference's expressions (point_tri_exact), which decide exactly as before.
+        // (1) Plane distance.  With m = dba x (-dac) (the vector the reference normalises into faceNors2) a record needs 0 <= proj and
+        //     |x2 - x1| <= lim, where proj = (x1 - x2a) . m / |m| and |x2 - x1| = |proj| up to a few roundings of the coordinates.  A
+        //     corner whose distance to the face's plane, formed WITHOUT the normalisation, exceeds lim by a margin a million times
+        //     those roundings fails one of the two tests for certain, whichever way nor2 is flipped.
+        // (2) barycentric_rejects: the cloth lying flat on the box's top is in the plane of four corners with all its faces.
+        // The unit normal (a square root and three divisions) is formed for the faces that come that close to a corner only — the
+        // kernel used to read it from a 24 B-per-face array that a separate pass over all faces had written (0.51 ms on the batch).
+        const double guard0 = lim + 1e-3 * lim + 1e-9;
         for (int j2 = blockIdx.x * 256 + threadIdx.x; j2 < F; j2 += gridDim.x * 256) {
             const V3 x2a = dcol(xs, fn[3 * (size_t)j2]), x2b = dcol(xs, fn[3 * (size_t)j2 + 1]), x2c = dcol(xs, fn[3 * (size_t)j2 + 2]);
-            const V3 n2 = dcol(fs, j2);
+            const V3 v0 = x2b - x2a, v1 = x2c - x2a;               // barycentric()'s v0, v1; v1 == -(x2a - x2c) exactly
+            const V3 m = cross(v0, v1);                            // == face_cross_p up to the sign of a zero
+            const double mm = m.x * m.x + m.y * m.y + m.z * m.z;
+            const double t = x2a.x * m.x + x2a.y * m.y + x2a.z * m.z;
+            const double gbase = guard0 + 1e-9 * (fabs(x2a.x) + fabs(x2a.y) + fabs(x2a.z));
+            const bool screen = mm > 1e-200 && mm < 1e200;         // degenerate faces take the reference's path unscreened
+            bool have_lat = false;
+            double d00 = 0.0, d01 = 0.0, d11 = 0.0, denom = 0.0;
+            unsigned pass = 0;                                     // corners (positions in lc[]) that the screens let through
 #pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
-                if (!((live >> c) & 1u)) continue;
-                const V3 x1c = mk(cx[c][0], cx[c][1], cx[c][2]), nor1c = mk(cn[c][0], cn[c][1], cn[c][2]);
-                V3 nor2 = n2;                                     // test_point_tri, line by line
-                if (dot(nor1c, nor2) < 0.0) nor2 = neg(nor2);
-                const double proj = dot(x1c - x2a, nor2);
-                if (proj < 0.0) continue;
-                const V3 x2 = x1c - scale(proj, nor2);
-                const double dist = norm(x2 - x1c);
-                if (dist > lim) continue;
-                double u, v;
-                barycentric(u, v, x2a, x2b, x2c, x1c);
-                const double w = sub(sub(1.0, u), v);
-                if (u < 0.0 || 1.0 < u || v < 0.0 || 1.0 < v || w < 0.0 || 1.0 < w) continue;
+            for (int q = 0; q < nlive; ++q) {
+                if (screen) {
+                    const int c = lc[q];
+                    const V3 x1c = mk(cx[c][0], cx[c][1], cx[c][2]);
+                    const double pm = (x1c.x * m.x + x1c.y * m.y + x1c.z * m.z) - t;
+                    const double g = gbase + 1e-9 * cl1[c];
+                    if (pm * pm > g * g * mm) continue;
+                    if (!have_lat) { d00 = dot(v0, v0); d01 = dot(v0, v1); d11 = dot(v1, v1); denom = sub(mul(d00, d11), mul(d01, d01)); have_lat = true; }
+                    const V3 v2 = x1c - x2a;
+                    const double d20 = dot(v2, v0), d21 = dot(v2, v1);
+                    if (barycentric_rejects(sub(mul(d11, d20), mul(d01, d21)), sub(mul(d00, d21), mul(d01, d20)), denom)) continue;
+                }
+                pass |= 1u << q;
+            }
+            while (pass) {                                         // rare: a handful of faces per corner
+                const int q = __ffs(pass) - 1;
+                pass &= pass - 1;
+                const int c = lc[q];
+                double dist;
+                if (!point_tri_exact(mk(cx[c][0], cx[c][1], cx[c][2]), mk(cn[c][0], cn[c][1], cn[c][2]), x2a, x2b, x2c, lim, dist)) continue;
                 Cand cur; cur.dist = bd[c][threadIdx.x]; cur.j2 = bj[c][threadIdx.x];
                 if (better(dist, j2, cur)) { bd[c][threadIdx.x] = dist; bj[c][threadIdx.x] = j2; }
             }
         }
     }
     __shared__ Cand sm[8][8];
-    for (int c = 0; c < 8; ++c) {
+    if (threadIdx.x < 64) { sm[threadIdx.x >> 3][threadIdx.x & 7].dist = 0.0; sm[threadIdx.x >> 3][threadIdx.x & 7].j2 = -1; }   // corners that are not live: no candidate
+    __syncthreads();
+    for (int q = 0; q < nlive; ++q) {
+        const int c = lc[q];
         Cand bc; bc.dist = bd[c][threadIdx.x]; bc.j2 = bj[c][threadIdx.x];
         for (int o = 16; o > 0; o >>= 1) {
             const double d = __shfl_xor_sync(0xffffffffu, bc.dist, o);
@@ -692,7 +762,7 @@ __global__ void __launch_bounds__(256) k_PT_write(int F, int pts_per_sec, int ns
     if (boxes) { const BoxData &B = boxes[sec]; x1 = bcol(B.verts1, pt); nor1 = bcol(B.vertNors1, pt); }
     else { x1 = dcol(pxyz, pt); nor1 = dcol(pnorms, pt); }
     double dist, u, v, w; V3 nor2, x2;
-    test_point_tri(x1, nor1, j2, fn, xp + s * xstride, fnp + s * fstride, mul(5.0, threshold), dist, nor2, x2, u, v, w);
+    test_point_tri(x1, nor1, j2, fn, xp + s * xstride, fnp ? fnp + s * fstride : nullptr, mul(5.0, threshold), dist, nor2, x2, u, v, w);
     eolc_contact rec;
     zero_contact(rec);
     rec.dist = dist;
@@ -763,20 +833,18 @@ struct EdgeRec { int32_t v[4]; int32_t f[2]; };
 // thr/len1 of [0, 1] and u2 within thr/len2 of [0, 1] (:933, :981), i.e. x1 within thr of the box edge's AABB and x2 within thr of
 // the cloth edge's, and |x2 - x1| <= 2 thr (:988-999): the two AABBs are then at most 4 thr apart in every coordinate.  Pairs
 // further apart than 6 thr are rejected before any arithmetic.
-struct CullBox {            // what pair_culled reads of one box, staged in shared memory by the block
+struct CullBox {            // what k_C_cull reads of one box: a kernel PARAMETER (constant bank: the operands of the culls need no loads)
+    double aabbB1[6];
     double edgeAngle[12];
     double aabbFc[12][6], aabbFd[12][6];   // AABBs of the two box triangles next to box edge k (aabbF1[edgeFaces1[k][0 / 1]])
     double aabbEdge[12][6];
 };
-__device__ __forceinline__ void stage_cull_box(CullBox &C, const BoxData &B) {
-    for (int i = threadIdx.x; i < 12 * 6; i += blockDim.x) {
-        const int k = i / 6, r = i % 6;
-        C.aabbFc[k][r] = B.aabbF1[c_edgeFaces1[k][0]][r];
-        C.aabbFd[k][r] = B.aabbF1[c_edgeFaces1[k][1]][r];
-        C.aabbEdge[k][r] = B.aabbEdge[k][r];
-        if (r == 0) C.edgeAngle[k] = B.edgeAngle[k];
+inline void make_cull_box(CullBox &C, const BoxData &B) {
+    for (int r = 0; r < 6; ++r) C.aabbB1[r] = B.aabbB1[r];
+    for (int k = 0; k < 12; ++k) {
+        C.edgeAngle[k] = B.edgeAngle[k];
+        for (int r = 0; r < 6; ++r) { C.aabbFc[k][r] = B.aabbF1[h_edgeFaces1[k][0]][r]; C.aabbFd[k][r] = B.aabbF1[h_edgeFaces1[k][1]][r]; C.aabbEdge[k][r] = B.aabbEdge[k][r]; }
     }
-    __syncthreads();
 }
 __device__ __forceinline__ bool pair_culled(int k1, const CullBox &C, const double *aabbE2k, double threshold) {
     // the conservative test first: it removes nearly every pair with six subtractions; the reference's own (exact) tests then run
@@ -867,11 +935,12 @@ __device__ __forceinline__ void edge_ends(const EdgeRec &e2, const double *__res
     aabbE[0] = fmin(x2b.x, x2a.x); aabbE[1] = fmin(x2b.y, x2a.y); aabbE[2] = fmin(x2b.z, x2a.z);
     aabbE[3] = fmax(x2b.x, x2a.x); aabbE[4] = fmax(x2b.y, x2a.y); aabbE[5] = fmax(x2b.z, x2a.z);
 }
-__device__ __forceinline__ void edge_frame(const EdgeRec &e2, const double *__restrict__ fn0, V3 x2a, V3 x2b, V3 &dx2, double &len2, V3 &nor2) {
+// normals of the edge's faces on the UNPERTURBED verts (createEdges :193-214), formed here for the few edges with a surviving pair
+__device__ __forceinline__ void edge_frame(const EdgeRec &e2, const int32_t *__restrict__ fn, const double *__restrict__ x0, V3 x2a, V3 x2b, V3 &dx2, double &len2, V3 &nor2) {
     dx2 = x2b - x2a;
     len2 = norm(dx2);
-    V3 n0 = dcol(fn0, e2.f[0]);
-    V3 n1 = e2.f[1] >= 0 ? dcol(fn0, e2.f[1]) : mk(0, 0, 0);   // boundary: normals[1] stays zero (:94-95)
+    V3 n0 = face_normal_0(fn, x0, e2.f[0]);
+    V3 n1 = e2.f[1] >= 0 ? face_normal_0(fn, x0, e2.f[1]) : mk(0, 0, 0);   // boundary: normals[1] stays zero (:94-95)
     nor2 = normalized(n0 + n1);
 }
 
@@ -881,56 +950,55 @@ __device__ __forceinline__ void edge_frame(const EdgeRec &e2, const double *__re
 //   k_C_sum    hits per 256-item block, for the scan
 // The work list's order does not matter (integer atomics): a pair's outcome lands in its own bit.  If the list overflows, the
 // pairs that did not fit are tested in place by k_C_cull.
-__global__ void __launch_bounds__(256) k_C_cull(int E, int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
-                                                const BoxData *__restrict__ boxes, double threshold,
+// One launch per box, the box's cull data a __grid_constant__ parameter: the first version staged it in shared memory per 256-edge
+// CTA (a global load, a barrier and ~200 shared-memory loads per thread in front of a kernel that is a chain of dependent latencies:
+// record -> end points -> list slot).  grid: (nC / 256, S)
+#ifndef EOLC_CULL_CTAS
+#define EOLC_CULL_CTAS 4
+#endif
+__global__ void __launch_bounds__(256, EOLC_CULL_CTAS) k_C_cull(int E, int b, const __grid_constant__ CullBox C, const EdgeRec *__restrict__ edges,
+                                                const double *__restrict__ xp, double threshold,
                                                 int *__restrict__ info, unsigned long long *__restrict__ cand_list, int *__restrict__ counter,
                                                 int capacity, size_t xstride, size_t scene_items, size_t box_items, size_t secC_off) {
-    __shared__ CullBox C;
-    const int s = blockIdx.y / nB, b = blockIdx.y % nB;
+    const int s = blockIdx.y;
     const int k2 = blockIdx.x * 256 + threadIdx.x;
-    const BoxData &B = boxes[b];
-    stage_cull_box(C, B);
     const size_t item = s * scene_items + secC_off + b * box_items + k2;
     int cand = 0;
-    const int mask = 0;
     if (k2 < E) {
         const EdgeRec e2 = edges[k2];
         V3 x2a, x2b;
         double aabbE[6];
         edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
         // whole-box cull first: an edge outside the padded box AABB fails all 24 face-AABB tests
-        if (check_aabb(B.aabbB1, aabbE)) {
+        if (check_aabb(C.aabbB1, aabbE)) {
 #pragma unroll
             for (int k1 = 0; k1 < 12; ++k1)
                 if (!pair_culled(k1, C, aabbE, threshold)) cand |= 1 << k1;
         }
     }
-    {
-        // one atomic per WARP (the per-lane atomics on the single counter were 11 % of the kernel's stall samples, ncu r02k): the lanes'
-        // counts are scanned in the warp, lane 31 reserves the warp's range.  The counter keeps counting past the capacity: the host
-        // then grows the list and repeats the pass.
-        const int n = __popc(cand), lane = threadIdx.x & 31;
-        int inc = n;
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        const int total = __shfl_sync(0xffffffffu, inc, 31);
-        int base = 0;
-        if (total) {
-            if (lane == 31) base = atomicAdd(counter, total);
-            base = __shfl_sync(0xffffffffu, base, 31);
+    info[item] = 0;
+    // one atomic per WARP (the per-lane atomics on the single counter were 11 % of the kernel's stall samples, ncu r02k): the lanes'
+    // counts are scanned in the warp, lane 31 reserves the warp's range.  The counter keeps counting past the capacity: the host
+    // then grows the list and repeats the pass.
+    const int n = __popc(cand), lane = threadIdx.x & 31;
+    if (!__any_sync(0xffffffffu, n)) return;
+    int inc = n;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    int base = 0;
+    if (lane == 31) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int at = base + inc - n;
+    for (int k1 = 0; k1 < 12; ++k1)
+        if ((cand >> k1) & 1) {
+            if (at < capacity) cand_list[at] = (unsigned long long)item | ((unsigned long long)k1 << 60);
+            ++at;
         }
-        int at = base + inc - n;
-        for (int k1 = 0; k1 < 12; ++k1)
-            if ((cand >> k1) & 1) {
-                if (at < capacity) cand_list[at] = (unsigned long long)item | ((unsigned long long)k1 << 60);
-                ++at;
-            }
-    }
-    info[item] = mask;
 }
 __global__ void __launch_bounds__(256) k_C_test(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
-                                                const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
+                                                const int32_t *__restrict__ fn, const double *__restrict__ x0, const BoxData *__restrict__ boxes, double threshold,
                                                 int *__restrict__ info, const unsigned long long *__restrict__ cand_list,
-                                                const int *__restrict__ counter, int capacity, size_t xstride, size_t fstride,
+                                                const int *__restrict__ counter, int capacity, size_t xstride,
                                                 size_t scene_items, size_t box_items, size_t secC_off) {
     const int n = min(*counter, capacity);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
@@ -942,7 +1010,7 @@ __global__ void __launch_bounds__(256) k_C_test(int nB, const EdgeRec *__restric
         const EdgeRec e2 = edges[k2];
         V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
         edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
-        edge_frame(e2, fn0 + s * fstride, x2a, x2b, dx2, len2, nor2);
+        edge_frame(e2, fn, x0 + s * xstride, x2a, x2b, dx2, len2, nor2);
         if (test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, threshold, nullptr, e2, k2)) atomicOr(info + item, 1 << k1);
     }
 }
@@ -1006,9 +1074,9 @@ __global__ void __launch_bounds__(256) k_C_expand(int nbx, long long nblk, int n
     }
 }
 __global__ void __launch_bounds__(256) k_C_write(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
-                                                 const double *__restrict__ fn0, const BoxData *__restrict__ boxes, double threshold,
+                                                 const int32_t *__restrict__ fn, const double *__restrict__ x0, const BoxData *__restrict__ boxes, double threshold,
                                                  const CHit *__restrict__ work, const int *__restrict__ counter, int capacity,
-                                                 eolc_contact *__restrict__ out, size_t xstride, size_t fstride, int remap, int nP) {
+                                                 eolc_contact *__restrict__ out, size_t xstride, int remap, int nP) {
     const int n = min(*counter, capacity);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const CHit h = work[i];
@@ -1016,7 +1084,7 @@ __global__ void __launch_bounds__(256) k_C_write(int nB, const EdgeRec *__restri
         const EdgeRec e2 = edges[h.k2];
         V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
         edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
-        edge_frame(e2, fn0 + s * fstride, x2a, x2b, dx2, len2, nor2);
+        edge_frame(e2, fn, x0 + s * xstride, x2a, x2b, dx2, len2, nor2);
         eolc_contact rec;
         test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, threshold, &rec, e2, h.k2);
         finish_contact(rec, threshold);
@@ -1039,7 +1107,7 @@ struct eolc_cd_plan {
     DevBuf<EdgeRec> d_edges;
     DevBuf<double> d_r;                 // perturbation table, 3N
     // per-run buffers
-    DevBuf<double> d_x, d_xp, d_fn0, d_fnp, d_aabb, d_aabb_part, d_pxyz, d_pnorms;
+    DevBuf<double> d_x, d_xp, d_fnp, d_aabb, d_aabb_part, d_pxyz, d_pnorms;
     DevBuf<BoxData> d_boxes;
     DevBuf<int> d_info, d_blocksum, d_blockoff;
     DevBuf<Cand> d_partial;
@@ -1206,13 +1274,14 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
         EOLC_CUDA(cudaMemcpyAsync(P->d_pnorms.p, pnorms, sizeof(double) * 3 * nP, cudaMemcpyHostToDevice, st));
     }
     const size_t xs = 3 * (size_t)N, fs = 3 * (size_t)F;
-    EOLC_CUDA(P->d_xp.ensure(xs * S)); EOLC_CUDA(P->d_fn0.ensure(std::max<size_t>(fs * S, 1))); EOLC_CUDA(P->d_fnp.ensure(std::max<size_t>(fs * S, 1)));
+    EOLC_CUDA(P->d_xp.ensure(xs * S));
+    if (nP) EOLC_CUDA(P->d_fnp.ensure(std::max<size_t>(fs * S, 1)));   // stored face normals: obstacle points only
     EOLC_CUDA(P->d_aabb.ensure(6 * (size_t)S));
     EOLC_CUDA(P->d_info.ensure(total_items)); EOLC_CUDA(P->d_blocksum.ensure(nblocks)); EOLC_CUDA(P->d_blockoff.ensure(nblocks + 1));
 
     // ---- prepare
     k_perturb<<<dim3((unsigned)((xs + 255) / 256), S), 256, 0, st>>>(N, x_dev, P->d_r.p, P->d_xp.p, xs); ++launches;
-    if (F) { k_face_normals<<<dim3((F + 255) / 256, S), 256, 0, st>>>(F, P->d_fn.p, x_dev, P->d_xp.p, P->d_fn0.p, P->d_fnp.p, xs, fs); ++launches; }
+    if (F && nP) { k_face_normals<<<dim3((F + 255) / 256, S), 256, 0, st>>>(F, P->d_fn.p, P->d_xp.p, P->d_fnp.p, xs, fs); ++launches; }
     {
         const int nb = std::max(1, std::min((N + 2047) / 2048, 64));
         EOLC_CUDA(P->d_aabb_part.ensure(6 * (size_t)S * nb));
@@ -1232,14 +1301,17 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
         launches += 2;
     }
     if (nB) {
-        k_A_count<<<dim3((unsigned)(nA / 256), S * nB), 256, 0, st>>>(N, F, nB, P->d_xp.p, P->d_fnp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, xs, fs, scene_items, box_items, secBox);
+        k_A_count<<<dim3((unsigned)(nA / 256), S * nB), 256, 0, st>>>(N, F, nB, P->d_xp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, xs, scene_items, box_items, secBox);
         {
             const long long nblkA = (long long)(nA / 256) * S * nB;
             k_A_sum<<<(unsigned)((nblkA + 7) / 8), 256, 0, st>>>((int)(nA / 256), nblkA, P->d_info.p, P->d_blocksum.p, scene_items, box_items, secBox, nB);
             ++launches;
         }
-        k_PT_partial8<<<dim3(nchunk, S * nB), 256, 0, st>>>(F, nB, P->d_boxes.p, P->d_fn.p, P->d_xp.p, P->d_fnp.p, P->d_aabb.p, thr, P->d_partial.p, xs, fs);
-        k_PT_final<<<S * nB, 256, 0, st>>>(nchunk, 8, nB, P->d_partial.p, P->d_info.p, P->d_blocksum.p, scene_items, secBox + nA, box_items);
+        // chunks of a scene's faces per (scene, box): enough CTAs to fill the GPU and no more — every CTA pays the staging of the corners
+        // and an eight-corner reduction, which a batch of thousands of small scenes would otherwise pay four times per scene
+        const int nchunk8 = (int)std::max<long long>(1, std::min<long long>(nchunk, (4LL * P->ctx->sm_count + (long long)S * nB - 1) / ((long long)S * nB)));
+        k_PT_partial8<<<dim3(nchunk8, S * nB), 256, 0, st>>>(F, nB, P->d_boxes.p, P->d_fn.p, P->d_xp.p, P->d_aabb.p, thr, P->d_partial.p, xs);
+        k_PT_final<<<S * nB, 256, 0, st>>>(nchunk8, 8, nB, P->d_partial.p, P->d_info.p, P->d_blocksum.p, scene_items, secBox + nA, box_items);
         launches += 3;
     }
     EOLC_CUDA(P->p_blockoff.ensure(nblocks + 1));
@@ -1252,11 +1324,15 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
         if (nB) {
             EOLC_CUDA(P->d_cands.ensure((size_t)cap));
             EOLC_CUDA(cudaMemsetAsync(P->d_counter.p, 0, 2 * sizeof(int), st));
-            k_C_cull<<<dim3((unsigned)(nC / 256), S * nB), 256, 0, st>>>(E, nB, P->d_edges.p, P->d_xp.p, P->d_boxes.p, thr, P->d_info.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
+            for (int b = 0; b < nB; ++b) {
+                CullBox cb;
+                make_cull_box(cb, hb[b]);
+                k_C_cull<<<dim3((unsigned)(nC / 256), S), 256, 0, st>>>(E, b, cb, P->d_edges.p, P->d_xp.p, thr, P->d_info.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
+            }
             const int gridT = (int)std::max<long long>(1, std::min<long long>(nblkC, (long long)P->ctx->sm_count * 2));
-            k_C_test<<<gridT, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_info.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, fs, scene_items, box_items, secBox + nA + nBc);
+            k_C_test<<<gridT, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn.p, x_dev, P->d_boxes.p, thr, P->d_info.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
             k_C_sum<<<(unsigned)((nblkC + 7) / 8), 256, 0, st>>>((int)(nC / 256), nblkC, P->d_info.p, P->d_blocksum.p, scene_items, box_items, secBox + nA + nBc, nB);
-            launches += 3;
+            launches += 2 + nB;
         }
         if (nblocks <= (size_t)4 * SCAN_CHUNK) { k_scan<<<1, 1024, 0, st>>>(nblocks, P->d_blocksum.p, P->d_blockoff.p); ++launches; }
         else {
@@ -1298,15 +1374,15 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
                     EOLC_CUDA(cudaFuncSetAttribute(k_A_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
                     P->smem_attr_set = true;
                 }
-                k_A_write<<<gridA, 256, smemA, st>>>(N, F, nB, S, P->d_xp.p, P->d_fnp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, box_items, secBox);
+                k_A_write<<<gridA, 256, smemA, st>>>(N, F, nB, S, P->d_xp.p, P->d_fn.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, scene_items, box_items, secBox);
             }
-            k_PT_write<<<dim3(1, S * nB), 256, 0, st>>>(F, 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secBox + nA, box_items, remap_box_indices, nP);
+            k_PT_write<<<dim3(1, S * nB), 256, 0, st>>>(F, 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, nullptr, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secBox + nA, box_items, remap_box_indices, nP);
             {
                 // every record has its slot: the work list of section C can hold at most `total` items
                 EOLC_CUDA(P->d_chits.ensure((size_t)total + 1));
                 k_C_expand<<<(unsigned)((nblkC + 7) / 8), 256, 0, st>>>((int)(nC / 256), nblkC, nB, P->d_info.p, P->d_blockoff.p, P->d_chits.p, P->d_counter.p + 1, total, scene_items, box_items, secBox + nA + nBc);
                 const int gridC = std::max(1, std::min((total + 255) / 256, P->ctx->sm_count * 2));
-                k_C_write<<<gridC, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn0.p, P->d_boxes.p, thr, P->d_chits.p, P->d_counter.p + 1, total, P->d_out.p, xs, fs, remap_box_indices, nP);
+                k_C_write<<<gridC, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn.p, x_dev, P->d_boxes.p, thr, P->d_chits.p, P->d_counter.p + 1, total, P->d_out.p, xs, remap_box_indices, nP);
                 ++launches;
             }
             launches += 3;
