@@ -377,16 +377,23 @@ __device__ __forceinline__ bool barycentric_rejects(double nb, double ng, double
     return false;
 }
 
+// What pass 1 of section A reads of one box, as a kernel PARAMETER (constant bank: the 24 plane tests take their operands from it
+// without a load; the pass used to read the box from global memory).  faceA[j] = verts1[faces1[j][0]].
+struct ABox { double aabbB1[6]; double faceA[24][3]; double faceNors1[24][3]; double verts1[14][3]; };
+inline void make_a_box(ABox &A, const BoxData &B) {
+    for (int r = 0; r < 6; ++r) A.aabbB1[r] = B.aabbB1[r];
+    for (int j = 0; j < 24; ++j) for (int r = 0; r < 3; ++r) { A.faceA[j][r] = B.verts1[h_faces1[j][0]][r]; A.faceNors1[j][r] = B.faceNors1[j][r]; }
+    for (int v = 0; v < 14; ++v) for (int r = 0; r < 3; ++r) A.verts1[v][r] = B.verts1[v][r];
+}
 // ---- section A: cloth vertex vs box (boxTriCollision.cpp:675-764) -----------------------------------
-// returns winning j1 (or -1) and, if rec != NULL, fills the record
-__device__ int test_vertex_box(int i2, int F, V3 x2, const int32_t *__restrict__ fn, const double *__restrict__ xs, const BoxData &B, double threshold, eolc_contact *rec) {
+// returns the winning j1 (or -1); the record of the winner is formed in pass 2 (vertex_box_record)
+__device__ __forceinline__ int test_vertex_box(V3 x2, const ABox &B, double threshold) {
     if (!check_aabb_point(x2, B.aabbB1)) return -1;
     // :689-697 — inside all 24 half-spaces; the projections are kept: the second loop (:699-) forms the same expression again
     double pj[24];
 #pragma unroll
     for (int j1 = 0; j1 < 24; ++j1) {
-        V3 x1a = bcol(B.verts1, c_faces1[j1][0]);
-        pj[j1] = dot(bcol(B.faceNors1, j1), x2 - x1a);
+        pj[j1] = dot(bcol(B.faceNors1, j1), x2 - bcol(B.faceA, j1));
         if (pj[j1] > 0.0) return -1;
     }
     int best = -1;
@@ -417,23 +424,7 @@ __device__ int test_vertex_box(int i2, int F, V3 x2, const int32_t *__restrict__
         barycentric(u, v, x1a, x1b, x1c, x1);
         double w = sub(sub(1.0, u), v);
         if (u < 0.0 || 1.0 < u || v < 0.0 || 1.0 < v || w < 0.0 || 1.0 < w) continue;
-        if (best < 0 || dist < bestd) {
-            best = j1; bestd = dist;
-            if (rec) {
-                // faceNors2.col(i2): indexed with the VERTEX id (reference quirk, :731); out of range -> zero
-                V3 nor2 = i2 < F ? face_normal_p(fn, xs, i2) : mk(0, 0, 0);
-                if (dot(nor2, nor1) < 0.0) nor2 = neg(nor2);
-                zero_contact(*rec);
-                rec->dist = dist;
-                st(rec->nor1, nor1); st(rec->nor2, nor2); st(rec->pos1, x1); st(rec->pos2, x2);
-                rec->count1 = 3; rec->count2 = 1;
-                rec->verts1[0] = c_faces1[j1][0]; rec->verts1[1] = c_faces1[j1][1]; rec->verts1[2] = c_faces1[j1][2];
-                rec->verts2[0] = i2; rec->verts2[1] = -1; rec->verts2[2] = -1;
-                rec->weights1[0] = u; rec->weights1[1] = v; rec->weights1[2] = w;
-                rec->weights2[0] = 1.0; rec->weights2[1] = 0.0; rec->weights2[2] = 0.0;
-                rec->tri1 = j1; rec->tri2 = -1;
-            }
-        }
+        if (best < 0 || dist < bestd) { best = j1; bestd = dist; }
     }
     return best;
 }
@@ -462,21 +453,17 @@ __device__ __forceinline__ void vertex_box_record(int i2, int j1, int F, V3 x2, 
     rec->tri1 = j1; rec->tri2 = -1;
 }
 
-// grid: (ceil(N/256), S*B)
-__global__ void __launch_bounds__(256) k_A_count(int N, int F, int nB, const double *__restrict__ xp,
-                                                 const BoxData *__restrict__ boxes, double threshold, int *__restrict__ info,
-                                                 int *__restrict__ blocksum, size_t xstride,
-                                                 size_t scene_items, size_t box_items, size_t secA_off) {
-    int s = blockIdx.y / nB, b = blockIdx.y % nB;
-    int i2 = blockIdx.x * 256 + threadIdx.x;
+// grid: (ceil(N/256), S), one launch per box
+__global__ void __launch_bounds__(256) k_A_count(int N, int b, const __grid_constant__ ABox B, const double *__restrict__ xp, double threshold,
+                                                 int *__restrict__ info, size_t xstride, size_t scene_items, size_t box_items, size_t secA_off) {
+    const int s = blockIdx.y;
+    const int i2 = blockIdx.x * 256 + threadIdx.x;
     int j1 = -1;
-    if (i2 < N) j1 = test_vertex_box(i2, F, dcol(xp + s * xstride, i2), nullptr, nullptr, boxes[b], threshold, nullptr);
-    size_t item0 = s * scene_items + secA_off + b * box_items;
-    info[item0 + blockIdx.x * 256 + threadIdx.x] = j1;
+    if (i2 < N) j1 = test_vertex_box(dcol(xp + s * xstride, i2), B, threshold);
+    info[s * scene_items + secA_off + b * box_items + i2] = j1;
     // no block-wide count here: the warps of a block finish far apart (a vertex outside the box returns after one AABB test, one on a
     // face runs the barycentric path), and a barrier kept the early ones — and the CTA's slot — waiting (46 % of the kernel's stall
     // samples, ncu r02k).  k_A_sum counts the hits of every 256-item block afterwards, one warp per block.
-    (void)blocksum;
 }
 __global__ void __launch_bounds__(256) k_A_sum(int nbx, long long nblk, const int *__restrict__ info, int *__restrict__ blocksum,
                                                size_t scene_items, size_t box_items, size_t secA_off, int nB) {
@@ -507,7 +494,30 @@ __global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, int S, co
     eolc_contact *stage = reinterpret_cast<eolc_contact *>(stage_raw) + 32 * wib;
     const int nbx = (N + 255) / 256;
     const long long nwork = (long long)nbx * nB * S * 8;
-    for (long long wk = (long long)blockIdx.x * 8 + wib; wk < nwork; wk += (long long)gridDim.x * 8) {
+    // 32 of a warp's work items at a time: lane l reads the two block offsets of its l-th next item, and the warp then works through the items whose
+    // block has hits (most have none).  One item after the other, each empty item cost a full memory round trip of the whole warp:
+    // the kernel was a chain of ~150 dependent latencies per warp (0.57 ms on the 4096 x 64^2 batch at 25 % of the warp slots).
+    // A big batch hands every warp runs of 32 consecutive items (neighbouring items share their block's info words and offsets);
+    // with little work per warp the items go round the warps one by one, so that no warp is left with a run of 32 busy ones.
+    const long long W = (long long)gridDim.x * 8, w0 = (long long)blockIdx.x * 8 + wib;
+    const bool runs = nwork >= 64 * W;
+    const long long lstride = runs ? 1 : W;
+    for (long long wk0 = runs ? 32 * w0 : w0; wk0 < nwork; wk0 += 32 * W) {
+      unsigned todo;
+      {
+        const long long wkl = wk0 + lane * lstride;
+        bool has = false;
+        if (wkl < nwork) {
+            const long long vbl = wkl >> 3;
+            const int bxl = (int)(vbl % nbx), sbl = (int)(vbl / nbx);
+            const size_t blkl = ((size_t)(sbl / nB) * scene_items + secA_off + (size_t)(sbl % nB) * box_items) / 256 + bxl;
+            has = blockoff[blkl + 1] != blockoff[blkl];
+        }
+        todo = __ballot_sync(0xffffffffu, has);
+      }
+      while (todo) {
+        const long long wk = wk0 + (__ffs(todo) - 1) * lstride;
+        todo &= todo - 1;
         const int sub = (int)(wk & 7);                 // which 32 items of the 256-item block
         const long long vb = wk >> 3;
         const int bx = (int)(vb % nbx);
@@ -515,7 +525,6 @@ __global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, int S, co
         const size_t item0 = s * scene_items + secA_off + b * box_items;
         const size_t blk = item0 / 256 + bx;
         const int base = blockoff[blk];
-        if (blockoff[blk + 1] == base) continue;       // warp-uniform
         // hits of the block's earlier items: lane l counts the items 8 l .. 8 l + 7 of the block, a warp scan gives every prefix
         const int4 *ip = reinterpret_cast<const int4 *>(info + item0 + (size_t)bx * 256 + 8 * lane);
         const int4 m0 = ip[0], m1 = ip[1];
@@ -540,6 +549,7 @@ __global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, int S, co
         const int nw = cnt * (int)(sizeof(eolc_contact) / 8);
         for (int w = lane; w < nw; w += 32) dst[w] = src[w];
         __syncwarp();                                  // the warp's stage is reused by its next work item
+      }
     }
 }
 
@@ -837,23 +847,21 @@ struct CullBox {            // what k_C_cull reads of one box: a kernel PARAMETE
     double aabbB1[6];
     double edgeAngle[12];
     double aabbFc[12][6], aabbFd[12][6];   // AABBs of the two box triangles next to box edge k (aabbF1[edgeFaces1[k][0 / 1]])
-    double aabbEdge[12][6];
+    double cullLo[12][3], cullHi[12][3];   // AABB of box edge k widened by 6 thr: the conservative pair cull is six comparisons
 };
-inline void make_cull_box(CullBox &C, const BoxData &B) {
+inline void make_cull_box(CullBox &C, const BoxData &B, double threshold) {
     for (int r = 0; r < 6; ++r) C.aabbB1[r] = B.aabbB1[r];
     for (int k = 0; k < 12; ++k) {
         C.edgeAngle[k] = B.edgeAngle[k];
-        for (int r = 0; r < 6; ++r) { C.aabbFc[k][r] = B.aabbF1[h_edgeFaces1[k][0]][r]; C.aabbFd[k][r] = B.aabbF1[h_edgeFaces1[k][1]][r]; C.aabbEdge[k][r] = B.aabbEdge[k][r]; }
+        for (int r = 0; r < 6; ++r) { C.aabbFc[k][r] = B.aabbF1[h_edgeFaces1[k][0]][r]; C.aabbFd[k][r] = B.aabbF1[h_edgeFaces1[k][1]][r]; }
+        for (int r = 0; r < 3; ++r) { C.cullLo[k][r] = B.aabbEdge[k][r] - 6.0 * threshold; C.cullHi[k][r] = B.aabbEdge[k][3 + r] + 6.0 * threshold; }
     }
 }
 __device__ __forceinline__ bool pair_culled(int k1, const CullBox &C, const double *aabbE2k, double threshold) {
-    // the conservative test first: it removes nearly every pair with six subtractions; the reference's own (exact) tests then run
+    // the conservative test first: it removes nearly every pair with six comparisons; the reference's own (exact) tests then run
     // on the few survivors — the order of rejections does not matter, a pair is dropped if any of them fires
-    const double m = 6.0 * threshold;
-    const double *a = C.aabbEdge[k1];
-    if (a[0] - aabbE2k[3] > m || aabbE2k[0] - a[3] > m || a[1] - aabbE2k[4] > m || aabbE2k[1] - a[4] > m || a[2] - aabbE2k[5] > m ||
-        aabbE2k[2] - a[5] > m)
-        return true;
+    const double *lo = C.cullLo[k1], *hi = C.cullHi[k1];
+    if (aabbE2k[3] < lo[0] || aabbE2k[0] > hi[0] || aabbE2k[4] < lo[1] || aabbE2k[1] > hi[1] || aabbE2k[5] < lo[2] || aabbE2k[2] > hi[2]) return true;
     if (C.edgeAngle[k1] < M_PI / 6.0) return true;   // soft edge
     return !check_aabb(C.aabbFc[k1], aabbE2k) && !check_aabb(C.aabbFd[k1], aabbE2k);
 }
@@ -947,7 +955,7 @@ __device__ __forceinline__ void edge_frame(const EdgeRec &e2, const int32_t *__r
 // Pass 1 of section C, in three light / dense kernels instead of one divergent one:
 //   k_C_cull   one thread per cloth edge: the AABB rejections of its 12 pairs; survivors are appended to a work list
 //   k_C_test   one thread per surviving pair (all lanes busy): the rest of :873-1017; a hit sets its bit in the edge's mask
-//   k_C_sum    hits per 256-item block, for the scan
+//   (the hits per 256-item block, for the scan, are counted by k_C_test with an integer atomic per hit)
 // The work list's order does not matter (integer atomics): a pair's outcome lands in its own bit.  If the list overflows, the
 // pairs that did not fit are tested in place by k_C_cull.
 // One launch per box, the box's cull data a __grid_constant__ parameter: the first version staged it in shared memory per 256-edge
@@ -958,11 +966,13 @@ __device__ __forceinline__ void edge_frame(const EdgeRec &e2, const int32_t *__r
 #endif
 __global__ void __launch_bounds__(256, EOLC_CULL_CTAS) k_C_cull(int E, int b, const __grid_constant__ CullBox C, const EdgeRec *__restrict__ edges,
                                                 const double *__restrict__ xp, double threshold,
-                                                int *__restrict__ info, unsigned long long *__restrict__ cand_list, int *__restrict__ counter,
-                                                int capacity, size_t xstride, size_t scene_items, size_t box_items, size_t secC_off) {
+                                                int *__restrict__ info, int *__restrict__ blocksum, unsigned long long *__restrict__ cand_list,
+                                                int *__restrict__ counter, int capacity, size_t xstride, size_t scene_items, size_t box_items,
+                                                size_t secC_off) {
     const int s = blockIdx.y;
     const int k2 = blockIdx.x * 256 + threadIdx.x;
     const size_t item = s * scene_items + secC_off + b * box_items + k2;
+    if (threadIdx.x == 0) blocksum[item / 256] = 0;          // k_C_test counts the block's hits
     int cand = 0;
     if (k2 < E) {
         const EdgeRec e2 = edges[k2];
@@ -997,7 +1007,7 @@ __global__ void __launch_bounds__(256, EOLC_CULL_CTAS) k_C_cull(int E, int b, co
 }
 __global__ void __launch_bounds__(256) k_C_test(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
                                                 const int32_t *__restrict__ fn, const double *__restrict__ x0, const BoxData *__restrict__ boxes, double threshold,
-                                                int *__restrict__ info, const unsigned long long *__restrict__ cand_list,
+                                                int *__restrict__ info, int *__restrict__ blocksum, const unsigned long long *__restrict__ cand_list,
                                                 const int *__restrict__ counter, int capacity, size_t xstride,
                                                 size_t scene_items, size_t box_items, size_t secC_off) {
     const int n = min(*counter, capacity);
@@ -1011,24 +1021,12 @@ __global__ void __launch_bounds__(256) k_C_test(int nB, const EdgeRec *__restric
         V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
         edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
         edge_frame(e2, fn, x0 + s * xstride, x2a, x2b, dx2, len2, nor2);
-        if (test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, threshold, nullptr, e2, k2)) atomicOr(info + item, 1 << k1);
+        if (test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, threshold, nullptr, e2, k2)) {
+            atomicOr(info + item, 1 << k1);
+            atomicAdd(blocksum + item / 256, 1);      // hits per 256-item block, for the scan (integer atomics: the same counts every run)
+        }
     }
 }
-// one warp per 256-item block of section C
-__global__ void __launch_bounds__(256) k_C_sum(int nbx, long long nblk, const int *__restrict__ info, int *__restrict__ blocksum,
-                                               size_t scene_items, size_t box_items, size_t secC_off, int nB) {
-    const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (w >= nblk) return;
-    const int bx = (int)(w % nbx);
-    const long long sb = w / nbx;
-    const size_t item0 = (size_t)(sb / nB) * scene_items + secC_off + (size_t)(sb % nB) * box_items;
-    const int *p = info + item0 + (size_t)bx * 256;
-    int t = 0;
-    for (int q = threadIdx.x & 31; q < 256; q += 32) t += __popc(p[q]);
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if ((threadIdx.x & 31) == 0) blocksum[item0 / 256 + bx] = t;
-}
-
 // Pass 2 of section C.  Hits are few (a band of cloth edges along the box edges) and scattered over the item blocks; re-deriving a
 // record is ~2 k FP64 instructions.  k_C_expand (light, full occupancy) turns every hit bit into a work item carrying its final
 // output slot; k_C_write then runs one thread per hit, all lanes busy.  The order of the work list is irrelevant (appended with an
@@ -1301,7 +1299,11 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
         launches += 2;
     }
     if (nB) {
-        k_A_count<<<dim3((unsigned)(nA / 256), S * nB), 256, 0, st>>>(N, F, nB, P->d_xp.p, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, xs, scene_items, box_items, secBox);
+        for (int b = 0; b < nB; ++b) {
+            ABox ab;
+            make_a_box(ab, hb[b]);
+            k_A_count<<<dim3((unsigned)(nA / 256), S), 256, 0, st>>>(N, b, ab, P->d_xp.p, thr, P->d_info.p, xs, scene_items, box_items, secBox);
+        }
         {
             const long long nblkA = (long long)(nA / 256) * S * nB;
             k_A_sum<<<(unsigned)((nblkA + 7) / 8), 256, 0, st>>>((int)(nA / 256), nblkA, P->d_info.p, P->d_blocksum.p, scene_items, box_items, secBox, nB);
@@ -1312,7 +1314,7 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
         const int nchunk8 = (int)std::max<long long>(1, std::min<long long>(nchunk, (4LL * P->ctx->sm_count + (long long)S * nB - 1) / ((long long)S * nB)));
         k_PT_partial8<<<dim3(nchunk8, S * nB), 256, 0, st>>>(F, nB, P->d_boxes.p, P->d_fn.p, P->d_xp.p, P->d_aabb.p, thr, P->d_partial.p, xs);
         k_PT_final<<<S * nB, 256, 0, st>>>(nchunk8, 8, nB, P->d_partial.p, P->d_info.p, P->d_blocksum.p, scene_items, secBox + nA, box_items);
-        launches += 3;
+        launches += 2 + nB;
     }
     EOLC_CUDA(P->p_blockoff.ensure(nblocks + 1));
     EOLC_CUDA(P->d_counter.ensure(2)); EOLC_CUDA(P->p_counter.ensure(2));
@@ -1326,13 +1328,12 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
             EOLC_CUDA(cudaMemsetAsync(P->d_counter.p, 0, 2 * sizeof(int), st));
             for (int b = 0; b < nB; ++b) {
                 CullBox cb;
-                make_cull_box(cb, hb[b]);
-                k_C_cull<<<dim3((unsigned)(nC / 256), S), 256, 0, st>>>(E, b, cb, P->d_edges.p, P->d_xp.p, thr, P->d_info.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
+                make_cull_box(cb, hb[b], thr);
+                k_C_cull<<<dim3((unsigned)(nC / 256), S), 256, 0, st>>>(E, b, cb, P->d_edges.p, P->d_xp.p, thr, P->d_info.p, P->d_blocksum.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
             }
             const int gridT = (int)std::max<long long>(1, std::min<long long>(nblkC, (long long)P->ctx->sm_count * 2));
-            k_C_test<<<gridT, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn.p, x_dev, P->d_boxes.p, thr, P->d_info.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
-            k_C_sum<<<(unsigned)((nblkC + 7) / 8), 256, 0, st>>>((int)(nC / 256), nblkC, P->d_info.p, P->d_blocksum.p, scene_items, box_items, secBox + nA + nBc, nB);
-            launches += 2 + nB;
+            k_C_test<<<gridT, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn.p, x_dev, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
+            launches += 1 + nB;
         }
         if (nblocks <= (size_t)4 * SCAN_CHUNK) { k_scan<<<1, 1024, 0, st>>>(nblocks, P->d_blocksum.p, P->d_blockoff.p); ++launches; }
         else {
