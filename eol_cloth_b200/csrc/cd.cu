@@ -866,19 +866,35 @@ __device__ __forceinline__ bool pair_culled(int k1, const CullBox &C, const doub
     return !check_aabb(C.aabbFc[k1], aabbE2k) && !check_aabb(C.aabbFd[k1], aabbE2k);
 }
 
+// e2->normal (:851-856 reads what createEdges :193-214 stored): the normalised sum of the normals of the edge's faces on the
+// UNPERTURBED verts.  Only the first rejection of :877-881 reads it: pass 1 forms it for the pairs that reach that test, pass 2 never.
+__device__ __forceinline__ V3 edge_normal(const EdgeRec &e2, const int32_t *__restrict__ fn, const double *__restrict__ x0) {
+    V3 n0 = face_normal_0(fn, x0, e2.f[0]);
+    V3 n1 = e2.f[1] >= 0 ? face_normal_0(fn, x0, e2.f[1]) : mk(0, 0, 0);   // boundary: normals[1] stays zero (:94-95)
+    return normalized(n0 + n1);
+}
+
 // the rest of :873-1017 for a pair that survived pair_culled(); out of line: the survivors are few and the callers stay light
-__device__ __noinline__ bool test_edge_edge(int k1, const BoxData &B, V3 x2a, V3 x2b, V3 dx2, double len2, V3 nor2,
+// rec == NULL (pass 1): the verdict.  rec != NULL (pass 2, a pair that passed): the record; fn / x0 are not read.
+__device__ __noinline__ bool test_edge_edge(int k1, const BoxData &B, V3 x2a, V3 x2b, const int32_t *__restrict__ fn, const double *__restrict__ x0,
                                double threshold, eolc_contact *rec, const EdgeRec &e2, int k2) {
+    const V3 dx2 = x2b - x2a;
+    const double len2 = norm(dx2);
     V3 x1a = bcol(B.verts1, c_edgeVerts1[k1][0]), x1b = bcol(B.verts1, c_edgeVerts1[k1][1]);
     V3 dx1 = bcol(B.dx1, k1);
     double len1 = B.len1[k1];
     V3 tan1 = bcol(B.tan1, k1);
     // :877-887: acos(c) within 2 deg of 0 or pi, decided in cosine space against the host libm's critical doubles (BoxData);
     // c outside [-1, 1] or NaN gives a NaN angle in the reference, which fails both comparisons
-    double c = dot(tan1, nor2);
+    // The first of the two (tan1 against the cloth edge's normal, :877-881) is the only use of that normal — two face normals and
+    // three normalisations behind two more dependent gathers.  Every rejection here is a pure function of the inputs, so the order is
+    // free: the cheap one runs first, and pass 2 (whose pairs have passed) does not form the normal at all.
+    double c = dv(dot(tan1, dx2), len2);
     if ((c >= B.cosParHi && c <= 1.0) || (c <= B.cosParLo && c >= -1.0)) return false;
-    c = dv(dot(tan1, dx2), len2);
-    if ((c >= B.cosParHi && c <= 1.0) || (c <= B.cosParLo && c >= -1.0)) return false;
+    if (!rec) {
+        c = dot(tan1, edge_normal(e2, fn, x0));
+        if ((c >= B.cosParHi && c <= 1.0) || (c <= B.cosParLo && c >= -1.0)) return false;
+    }
     V3 nor = normalized(cross(dx1, dx2));
     V3 x1c = bcol(B.verts1, c_edgeVerts1[k1][2]), x1d = bcol(B.verts1, c_edgeVerts1[k1][3]);
     V3 n1c = bcol(B.faceNors1, c_edgeFaces1[k1][0]), n1d = bcol(B.faceNors1, c_edgeFaces1[k1][1]);
@@ -943,15 +959,6 @@ __device__ __forceinline__ void edge_ends(const EdgeRec &e2, const double *__res
     aabbE[0] = fmin(x2b.x, x2a.x); aabbE[1] = fmin(x2b.y, x2a.y); aabbE[2] = fmin(x2b.z, x2a.z);
     aabbE[3] = fmax(x2b.x, x2a.x); aabbE[4] = fmax(x2b.y, x2a.y); aabbE[5] = fmax(x2b.z, x2a.z);
 }
-// normals of the edge's faces on the UNPERTURBED verts (createEdges :193-214), formed here for the few edges with a surviving pair
-__device__ __forceinline__ void edge_frame(const EdgeRec &e2, const int32_t *__restrict__ fn, const double *__restrict__ x0, V3 x2a, V3 x2b, V3 &dx2, double &len2, V3 &nor2) {
-    dx2 = x2b - x2a;
-    len2 = norm(dx2);
-    V3 n0 = face_normal_0(fn, x0, e2.f[0]);
-    V3 n1 = e2.f[1] >= 0 ? face_normal_0(fn, x0, e2.f[1]) : mk(0, 0, 0);   // boundary: normals[1] stays zero (:94-95)
-    nor2 = normalized(n0 + n1);
-}
-
 // Pass 1 of section C, in three light / dense kernels instead of one divergent one:
 //   k_C_cull   one thread per cloth edge: the AABB rejections of its 12 pairs; survivors are appended to a work list
 //   k_C_test   one thread per surviving pair (all lanes busy): the rest of :873-1017; a hit sets its bit in the edge's mask
@@ -1005,7 +1012,7 @@ __global__ void __launch_bounds__(256, EOLC_CULL_CTAS) k_C_cull(int E, int b, co
             ++at;
         }
 }
-__global__ void __launch_bounds__(256) k_C_test(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
+__global__ void __launch_bounds__(256, 2) k_C_test(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
                                                 const int32_t *__restrict__ fn, const double *__restrict__ x0, const BoxData *__restrict__ boxes, double threshold,
                                                 int *__restrict__ info, int *__restrict__ blocksum, const unsigned long long *__restrict__ cand_list,
                                                 const int *__restrict__ counter, int capacity, size_t xstride,
@@ -1018,10 +1025,8 @@ __global__ void __launch_bounds__(256) k_C_test(int nB, const EdgeRec *__restric
         const size_t s = item / scene_items, rem = item - s * scene_items - secC_off;
         const int b = (int)(rem / box_items), k2 = (int)(rem - (size_t)b * box_items);
         const EdgeRec e2 = edges[k2];
-        V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
-        edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
-        edge_frame(e2, fn, x0 + s * xstride, x2a, x2b, dx2, len2, nor2);
-        if (test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, threshold, nullptr, e2, k2)) {
+        const V3 x2a = dcol(xp + s * xstride, e2.v[0]), x2b = dcol(xp + s * xstride, e2.v[1]);
+        if (test_edge_edge(k1, boxes[b], x2a, x2b, fn, x0 + s * xstride, threshold, nullptr, e2, k2)) {
             atomicOr(info + item, 1 << k1);
             atomicAdd(blocksum + item / 256, 1);      // hits per 256-item block, for the scan (integer atomics: the same counts every run)
         }
@@ -1071,7 +1076,7 @@ __global__ void __launch_bounds__(256) k_C_expand(int nbx, long long nblk, int n
             }
     }
 }
-__global__ void __launch_bounds__(256) k_C_write(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
+__global__ void __launch_bounds__(256, 2) k_C_write(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
                                                  const int32_t *__restrict__ fn, const double *__restrict__ x0, const BoxData *__restrict__ boxes, double threshold,
                                                  const CHit *__restrict__ work, const int *__restrict__ counter, int capacity,
                                                  eolc_contact *__restrict__ out, size_t xstride, int remap, int nP) {
@@ -1080,11 +1085,9 @@ __global__ void __launch_bounds__(256) k_C_write(int nB, const EdgeRec *__restri
         const CHit h = work[i];
         const int sb = h.sb_k1 & 0xffff, k1 = h.sb_k1 >> 16, s = sb / nB, b = sb % nB;
         const EdgeRec e2 = edges[h.k2];
-        V3 x2a, x2b, dx2, nor2; double len2, aabbE[6];
-        edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
-        edge_frame(e2, fn, x0 + s * xstride, x2a, x2b, dx2, len2, nor2);
+        const V3 x2a = dcol(xp + s * xstride, e2.v[0]), x2b = dcol(xp + s * xstride, e2.v[1]);
         eolc_contact rec;
-        test_edge_edge(k1, boxes[b], x2a, x2b, dx2, len2, nor2, threshold, &rec, e2, h.k2);
+        test_edge_edge(k1, boxes[b], x2a, x2b, nullptr, nullptr, threshold, &rec, e2, h.k2);
         finish_contact(rec, threshold);
         if (remap) remap_contact(rec, nP + b * 8 + b * 12);
         out[h.slot] = rec;
