@@ -670,8 +670,17 @@ __global__ void __launch_bounds__(256, EOLC_PT8_CTAS) k_PT_partial8(int F, int n
         // The unit normal (a square root and three divisions) is formed for the faces that come that close to a corner only — the
         // kernel used to read it from a 24 B-per-face array that a separate pass over all faces had written (0.51 ms on the batch).
         const double guard0 = lim + 1e-3 * lim + 1e-9;
-        for (int j2 = blockIdx.x * 256 + threadIdx.x; j2 < F; j2 += gridDim.x * 256) {
-            const V3 x2a = dcol(xs, fn[3 * (size_t)j2]), x2b = dcol(xs, fn[3 * (size_t)j2 + 1]), x2c = dcol(xs, fn[3 * (size_t)j2 + 2]);
+        // the indices of the thread's next face are fetched while it works on this one: with one CTA per scene a thread walks ~30
+        // faces, and index -> vertices -> arithmetic was two dependent round trips per face
+        int j2 = blockIdx.x * 256 + threadIdx.x;
+        int ia = 0, ib = 0, ic = 0;
+        if (j2 < F) { ia = fn[3 * (size_t)j2]; ib = fn[3 * (size_t)j2 + 1]; ic = fn[3 * (size_t)j2 + 2]; }
+        for (; j2 < F; j2 += gridDim.x * 256) {
+            const V3 x2a = dcol(xs, ia), x2b = dcol(xs, ib), x2c = dcol(xs, ic);
+            {
+                const int jn = j2 + gridDim.x * 256;
+                if (jn < F) { ia = fn[3 * (size_t)jn]; ib = fn[3 * (size_t)jn + 1]; ic = fn[3 * (size_t)jn + 2]; }
+            }
             const V3 v0 = x2b - x2a, v1 = x2c - x2a;               // barycentric()'s v0, v1; v1 == -(x2a - x2c) exactly
             const V3 m = cross(v0, v1);                            // == face_cross_p up to the sign of a zero
             const double mm = m.x * m.x + m.y * m.y + m.z * m.z;
