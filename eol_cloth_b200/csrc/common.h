@@ -76,4 +76,6 @@ struct eolc_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // second copy engine for the big device-to-host copies of the host entry points
+    cudaEvent_t copy_event = nullptr;
 };

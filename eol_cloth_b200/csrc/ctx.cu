@@ -52,6 +52,9 @@ int eolc_ctx_create(int device, eolc_ctx **out) {
         eolc::set_error("cudaStreamCreateWithFlags failed: %s", cudaGetErrorString(es));
         return EOLC_ERR_CUDA;
     }
+    // optional: without them the host entries copy on the one stream
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); c->copy_stream = nullptr; }
+    if (cudaEventCreateWithFlags(&c->copy_event, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); c->copy_event = nullptr; }
     *out = c;
     return EOLC_OK;
 }
@@ -95,6 +98,8 @@ void eolc_ctx_destroy(eolc_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
     delete ctx;
 }
 

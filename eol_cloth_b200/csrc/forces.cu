@@ -1364,11 +1364,12 @@ int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X
     if (!in_pinned) {
         EOLC_CUDA(P->p_in.ensure(5 * N));
         memcpy(P->p_in.p, x, 3 * N * sizeof(double));
-        memcpy(P->p_in.p + 3 * N, X, 2 * N * sizeof(double));
+        if (!skip_m) memcpy(P->p_in.p + 3 * N, X, 2 * N * sizeof(double));
         hx = P->p_in.p; hX = P->p_in.p + 3 * N;
     }
     EOLC_CUDA(cudaMemcpyAsync(P->d_x.p, hx, 3 * N * sizeof(double), cudaMemcpyHostToDevice, st));
-    EOLC_CUDA(cudaMemcpyAsync(P->d_X.p, hX, 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    // M unchanged == X unchanged (the flag's contract): the plan's device copy of X is the previous host fill's, no second upload
+    if (!skip_m) EOLC_CUDA(cudaMemcpyAsync(P->d_X.p, hX, 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
     int rc = launch_fill(P, 1, P->d_x.p, P->d_X.p, mat, grav, h, P->d_f.p, P->d_Mv.p, P->d_Kv.p, skip_m);
     if (rc) return rc;
     // the host entry always hands out an exactly symmetric MDK, like the reference's (0.3 ms next to the copies)
@@ -1381,8 +1382,18 @@ int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X
     }
     EOLC_CUDA(cudaMemcpyAsync(hf, P->d_f.p, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (!skip_m) EOLC_CUDA(cudaMemcpyAsync(hM, P->d_Mv.p, P->nnzM * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EOLC_CUDA(cudaMemcpyAsync(hK, P->d_Kv.p, P->nnzK * sizeof(double), cudaMemcpyDeviceToHost, st));
+    // the big copy goes out in two halves on two streams: two copy engines keep the link a few per cent busier than one (54.7 ->
+    // 57.1 GB/s on the 980 MB of the 1024^2 sheet, scratch/d2h_bw.py)
+    cudaStream_t st2 = P->ctx->copy_stream;
+    const size_t half = (P->nnzK > ((size_t)1 << 22) && st2 && P->ctx->copy_event) ? (P->nnzK / 2) & ~(size_t)511 : 0;
+    if (half) {
+        EOLC_CUDA(cudaEventRecord(P->ctx->copy_event, st));
+        EOLC_CUDA(cudaStreamWaitEvent(st2, P->ctx->copy_event, 0));
+        EOLC_CUDA(cudaMemcpyAsync(hK + half, P->d_Kv.p + half, (P->nnzK - half) * sizeof(double), cudaMemcpyDeviceToHost, st2));
+    }
+    EOLC_CUDA(cudaMemcpyAsync(hK, P->d_Kv.p, (half ? half : P->nnzK) * sizeof(double), cudaMemcpyDeviceToHost, st));
     EOLC_CUDA(cudaStreamSynchronize(st));
+    if (half) EOLC_CUDA(cudaStreamSynchronize(st2));
     if (!out_pinned) {
         memcpy(f, hf, nf * sizeof(double));
         if (!skip_m) memcpy(M_vals, hM, P->nnzM * sizeof(double));

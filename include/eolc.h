@@ -108,8 +108,8 @@ int eolc_forces_fill(eolc_forces_plan *plan, const double *x, const double *X, c
 /* Flags of the *_ex entry points.
  * EOLC_FILL_M_UNCHANGED: the caller states that X and the density are the ones of the previous fill on this plan, so M, which
  *   depends on nothing else (src/ComputeInertial.cpp:33,44-47; SURVEY §8a row 5: "constant between remeshes when EOL is off"),
- *   is the same matrix: M_vals is left untouched (host entry: no device-to-host copy of M; device entries: the M rows are
- *   neither recomputed nor written).  f and MDK are produced as always and are bit-identical to a full fill.  Honoured for
+ *   is the same matrix: M_vals is left untouched (host entry: no device-to-host copy of M and no second upload of X, the plan
+ *   keeps the previous host fill's copy on the device; device entries: the M rows are neither recomputed nor written).  f and MDK are produced as always and are bit-identical to a full fill.  Honoured for
  *   Lagrangian plans only (with EoL nodes M depends on x through F = deform_grad); otherwise M is recomputed.  M_vals must be
  *   the buffer of the previous fill or at least a valid one.
  * EOLC_FILL_EXACT_SYMMETRY (device entries; the host entries always do it): MDK symmetric bit for bit, like the reference's mirrored

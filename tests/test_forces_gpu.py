@@ -385,6 +385,7 @@ def test_m_unchanged_flag_and_pinned_host_buffers(ctx):
     assert np.array_equal(M0, M_ref)                      # M does not depend on x
     xh[:] = x1
     Mh[:] = 123.0                                          # sentinel: must survive
+    Xh[:] = np.nan                                         # the flag says "X as in the previous fill": the host copy is not read again
     plan.fill_into(xh, Xh, MAT, GRAV, H, fh, Mh, Kh, m_unchanged=True)
     assert fh.tobytes() == f_ref.tobytes() and Kh.tobytes() == K_ref.tobytes()
     assert (Mh == 123.0).all()
