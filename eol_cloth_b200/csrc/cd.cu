@@ -1250,8 +1250,8 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
     EOLC_REQUIRE(n_points == 0 || (pxyz && pnorms), "pxyz/pnorms is NULL");
     EOLC_REQUIRE(n_boxes == 0 || (box_whd && box_E), "box_whd/box_E is NULL");
     EOLC_REQUIRE(capacity == 0 || out, "out is NULL");
-    EOLC_REQUIRE((int64_t)S * std::max(n_boxes, 1) <= 65535 && (int64_t)S * std::max(8 * n_boxes, n_points) <= 65535,
-                 "too many scenes*boxes for one launch; split the batch");
+    EOLC_REQUIRE((int64_t)S * std::max(std::max(n_boxes, n_points), 1) <= 65535,      // a grid dimension, and 16 bits of CHit::sb_k1
+                 "too many scenes * max(boxes, points) for one run; split the batch");
     EOLC_CUDA(cudaSetDevice(P->ctx->device));
     cudaStream_t st = P->ctx->stream;
     const int N = P->N, F = P->F, E = P->E, nB = n_boxes, nP = n_points;

@@ -207,7 +207,7 @@ int eolc_cd_run_batched_resident_dev(eolc_cd_plan *plan, int32_t n_scenes, const
                                      const double *pxyz, const double *pnorms, int32_t n_boxes, const double *box_whd,
                                      const double *box_E, int point_eol_flag, int remap_box_indices, int32_t *scene_offset);
 int eolc_cd_contacts_dev(const eolc_cd_plan *plan, const eolc_contact **contacts_dev, int32_t *count);
-/* Limits of one run: n_scenes * max(8 * n_boxes, n_points, 1) <= 65535 (a grid dimension); larger batches / point clouds must be
+/* Limits of one run: n_scenes * max(n_boxes, n_points, 1) <= 65535 (a grid dimension); larger batches / point clouds must be
  * split by the caller (EOLC_ERR_ARG otherwise). */
 /* Host-only diagnostic (no GPU needed).  Section C's three acos() (src/boxTriCollision.cpp:879-887, :907-915) only feed
  * threshold comparisons; the device decides them in cosine space against critical doubles that the host finds by bisection

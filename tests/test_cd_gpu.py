@@ -138,6 +138,30 @@ def test_batched_scenes_equal_single(ctx):
         assert allc[off[s]:off[s + 1]].tobytes() == single.tobytes()
 
 
+def test_batch_of_20000_small_scenes(ctx):
+    """One run takes n_scenes * max(n_boxes, n_points, 1) <= 65535: 20,000 scenes of a 12x12 sheet over the box in one call, sampled
+    scenes equal to single-scene runs bit for bit; one scene more than the limit is refused with EOLC_ERR_ARG."""
+    import torch
+    X, fn = E.meshgen.regular2(12)
+    c = np.array([0.9175, -0.25, -0.549])
+    obs = make_obstacles(THR, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(c)[None])
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, THR)
+    S = 20000
+    base = np.stack([E.meshgen.box_scene_state(X, seed=s, centre=c) for s in range(50)])
+    xs = base[np.arange(S) % 50].copy()
+    xs[:, :, 2] += 1e-6 * (np.arange(S) // 50)[:, None]          # 20,000 different states
+    xd = torch.from_numpy(xs).to(torch.device("cuda", ctx.device))
+    torch.cuda.synchronize()
+    allc, off = plan.run(xd.data_ptr(), obs, 0, 0, capacity=1_000_000, x_is_device_ptr=True, n_scenes=S)
+    assert off[0] == 0 and off[-1] == len(allc) and len(allc) > S
+    for s in (0, 1, 49, 50, 8191, 8192, 12345, S - 1):
+        single = plan.run(xs[s], obs, 0, 0)
+        assert allc[off[s]:off[s + 1]].tobytes() == single.tobytes(), f"scene {s}"
+    with pytest.raises(Exception):
+        plan.run_resident(xd.data_ptr(), obs, 0, 0, n_scenes=65536)
+    plan.close()
+
+
 def test_ensemble_4096_scenes_sampled_against_reference(ctx, oracle):
     """BASELINE configs[4]: the full batch of 4096 independent 64x64 scenes (state seed = scene id) against the box, one batched
     call per chunk; 40 sampled scenes are compared bit for bit with the reference's own code (libbtc_ref.so) and the oracle."""
