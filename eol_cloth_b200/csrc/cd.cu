@@ -1021,7 +1021,10 @@ __global__ void __launch_bounds__(256, EOLC_CULL_CTAS) k_C_cull(int E, int b, co
             ++at;
         }
 }
-__global__ void __launch_bounds__(256, 2) k_C_test(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
+#ifndef EOLC_CTEST_CTAS
+#define EOLC_CTEST_CTAS 2
+#endif
+__global__ void __launch_bounds__(256, EOLC_CTEST_CTAS) k_C_test(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
                                                 const int32_t *__restrict__ fn, const double *__restrict__ x0, const BoxData *__restrict__ boxes, double threshold,
                                                 int *__restrict__ info, int *__restrict__ blocksum, const unsigned long long *__restrict__ cand_list,
                                                 const int *__restrict__ counter, int capacity, size_t xstride,
@@ -1343,7 +1346,7 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
                 make_cull_box(cb, hb[b], thr);
                 k_C_cull<<<dim3((unsigned)(nC / 256), S), 256, 0, st>>>(E, b, cb, P->d_edges.p, P->d_xp.p, thr, P->d_info.p, P->d_blocksum.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
             }
-            const int gridT = (int)std::max<long long>(1, std::min<long long>(nblkC, (long long)P->ctx->sm_count * 2));
+            const int gridT = (int)std::max<long long>(1, std::min<long long>(nblkC, (long long)P->ctx->sm_count * EOLC_CTEST_CTAS));
             k_C_test<<<gridT, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn.p, x_dev, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
             launches += 1 + nB;
         }

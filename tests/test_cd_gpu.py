@@ -58,6 +58,45 @@ def test_box_scene_matches_oracle(ctx, oracle, gen, n, centre, rot, seed):
     assert len(ref) > 0
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_pathological_faces_and_borderline_vertices(ctx, oracle, seed):
+    """The conservative screens in front of the reference's expressions (plane distance without the normalisation, the division-free
+    barycentric verdict, the pair culls) must not change a decision where the geometry is bad: sliver faces (two vertices 1e-9 /
+    1e-13 apart, three vertices on a line), vertices and faces exactly in the planes of the box's top and sides, vertices at the
+    box's corners and on its edges, faces a hair inside / outside the 5 thr band.  Bit for bit against the reference's own code."""
+    rng = np.random.default_rng(100 + seed)
+    n = 28
+    X, fn = E.meshgen.regular2(n)
+    centre = np.array([0.9175, -0.25, -0.549])
+    x = E.meshgen.box_scene_state(X, seed=seed, centre=centre)
+    obs = make_obstacles(THR, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(centre)[None])
+    lo, hi = centre - 0.5 * E.meshgen.BOX_WHD, centre + 0.5 * E.meshgen.BOX_WHD
+    top = hi[2]
+    over = np.where((x[:, 0] > lo[0]) & (x[:, 0] < hi[0]) & (x[:, 1] > lo[1]) & (x[:, 1] < hi[1]))[0]
+    assert len(over) > 30
+    pick = rng.permutation(over)
+    # slivers: a vertex almost on its right-hand neighbour, and three vertices of a row on one line
+    for k, eps in ((0, 1e-9), (1, 1e-13), (2, 0.0)):
+        a = pick[k]
+        if (a + 1) % n:
+            x[a + 1] = x[a] + eps
+    a = pick[3]
+    if a + n + 1 < len(x):
+        x[a + n + 1] = 2.0 * x[a + n] - x[a + n - 1] if (a + n) % n else x[a + n + 1]
+    # exactly in the top plane, a hair above / below it, and at the edge of the 5 thr band
+    for k, dz in zip(range(4, 12), (0.0, 1e-16, -1e-16, 5.0 * THR, 5.0 * THR * (1 + 1e-15), 5.0 * THR * (1 - 1e-15), -5.0 * THR, THR)):
+        x[pick[k], 2] = top + dz
+    # at the box's corners and on its edges (top face), and exactly in a side plane
+    cs = [np.array([sx, sy, top]) for sx in (lo[0], hi[0]) for sy in (lo[1], hi[1])]
+    near = [int(np.argmin(np.linalg.norm(x[:, :2] - c[:2], axis=1))) for c in cs]
+    for a, c in zip(near, cs):
+        x[a] = c
+    x[pick[12], 0] = hi[0]; x[pick[13], 1] = lo[1]
+    x[pick[14]] = np.array([hi[0], x[pick[14], 1], top])
+    got, ref = _both(ctx, oracle, fn, x, obs, f"pathological {seed}")
+    assert len(ref) > 50
+
+
 def test_points_and_two_boxes(ctx, oracle):
     X, fn = E.meshgen.regular2(30)
     x = E.meshgen.box_scene_state(X, seed=5, centre=np.array([0.9175, -0.25, -0.549]))
