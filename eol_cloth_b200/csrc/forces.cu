@@ -1383,7 +1383,7 @@ int eolc_forces_fill_ex(eolc_forces_plan *plan, const double *x, const double *X
     EOLC_CUDA(cudaMemcpyAsync(hf, P->d_f.p, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (!skip_m) EOLC_CUDA(cudaMemcpyAsync(hM, P->d_Mv.p, P->nnzM * sizeof(double), cudaMemcpyDeviceToHost, st));
     // the big copy goes out in two halves on two streams: two copy engines keep the link a few per cent busier than one (54.7 ->
-    // 57.1 GB/s on the 980 MB of the 1024^2 sheet, scratch/d2h_bw.py)
+    // 57.1 GB/s on the 980 MB of the 1024^2 sheet, scripts/micro/d2h_bw.py)
     cudaStream_t st2 = P->ctx->copy_stream;
     const size_t half = (P->nnzK > ((size_t)1 << 22) && st2 && P->ctx->copy_event) ? (P->nnzK / 2) & ~(size_t)511 : 0;
     if (half) {
