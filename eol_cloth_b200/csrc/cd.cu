@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(256) k_PT_partial(int F, int npts_per_scene, i
     }
 }
 #ifndef EOLC_PT8_CTAS
-#define EOLC_PT8_CTAS 4      // resident CTAs per SM the register allocation of k_PT_partial8 aims at
+#define EOLC_PT8_CTAS 3      // resident CTAs per SM the register allocation of k_PT_partial8 aims at (80 registers, no spills: 352 us on the batch; 4 CTAs with 64 registers and 64 bytes of spills: 378 us)
 #endif
 // Box mode, all 8 corners of a box against a chunk of the cloth's faces in ONE pass: a face's indices, its three vertices and its
 // normal are loaded once and tested against the eight corners (the per-corner kernel above read every face eight times: 1.2 GB of DRAM
@@ -676,12 +676,17 @@ __global__ void __launch_bounds__(256, EOLC_PT8_CTAS) k_PT_partial8(int F, int n
         int ia = 0, ib = 0, ic = 0;
         if (j2 < F) { ia = fn[3 * (size_t)j2]; ib = fn[3 * (size_t)j2 + 1]; ic = fn[3 * (size_t)j2 + 2]; }
         for (; j2 < F; j2 += gridDim.x * 256) {
-            const V3 x2a = dcol(xs, ia), x2b = dcol(xs, ib), x2c = dcol(xs, ic);
+            const int ja = ia, jb = ib, jc = ic;
+            const V3 x2a = dcol(xs, ja);
+            V3 v0, v1;                                             // barycentric()'s v0, v1; v1 == -(x2a - x2c) exactly
+            {   // the other two vertices are not kept: the few pairs that reach the reference's expressions load the face again
+                const V3 x2b = dcol(xs, jb), x2c = dcol(xs, jc);
+                v0 = x2b - x2a; v1 = x2c - x2a;
+            }
             {
                 const int jn = j2 + gridDim.x * 256;
                 if (jn < F) { ia = fn[3 * (size_t)jn]; ib = fn[3 * (size_t)jn + 1]; ic = fn[3 * (size_t)jn + 2]; }
             }
-            const V3 v0 = x2b - x2a, v1 = x2c - x2a;               // barycentric()'s v0, v1; v1 == -(x2a - x2c) exactly
             const V3 m = cross(v0, v1);                            // == face_cross_p up to the sign of a zero
             const double mm = m.x * m.x + m.y * m.y + m.z * m.z;
             const double t = x2a.x * m.x + x2a.y * m.y + x2a.z * m.z;
@@ -710,7 +715,7 @@ __global__ void __launch_bounds__(256, EOLC_PT8_CTAS) k_PT_partial8(int F, int n
                 pass &= pass - 1;
                 const int c = lc[q];
                 double dist;
-                if (!point_tri_exact(mk(cx[c][0], cx[c][1], cx[c][2]), mk(cn[c][0], cn[c][1], cn[c][2]), x2a, x2b, x2c, lim, dist)) continue;
+                if (!point_tri_exact(mk(cx[c][0], cx[c][1], cx[c][2]), mk(cn[c][0], cn[c][1], cn[c][2]), dcol(xs, ja), dcol(xs, jb), dcol(xs, jc), lim, dist)) continue;
                 Cand cur; cur.dist = bd[c][threadIdx.x]; cur.j2 = bj[c][threadIdx.x];
                 if (better(dist, j2, cur)) { bd[c][threadIdx.x] = dist; bj[c][threadIdx.x] = j2; }
             }
