@@ -985,33 +985,51 @@ __device__ __forceinline__ void edge_ends(const EdgeRec &e2, const double *__res
 #ifndef EOLC_CULL_CTAS
 #define EOLC_CULL_CTAS 4
 #endif
-__global__ void __launch_bounds__(256, EOLC_CULL_CTAS) k_C_cull(int E, int b, const __grid_constant__ CullBox C, const EdgeRec *__restrict__ edges,
+#ifndef EOLC_CULL_EPT
+#define EOLC_CULL_EPT 1      // edges per thread (items 256 apart)
+#endif
+__global__ void __launch_bounds__(256, EOLC_CULL_CTAS) k_C_cull(int E, int nC, int b, const __grid_constant__ CullBox C, const EdgeRec *__restrict__ edges,
                                                 const double *__restrict__ xp, double threshold,
                                                 int *__restrict__ info, int *__restrict__ blocksum, unsigned long long *__restrict__ cand_list,
                                                 int *__restrict__ counter, int capacity, size_t xstride, size_t scene_items, size_t box_items,
                                                 size_t secC_off) {
     const int s = blockIdx.y;
-    const int k2 = blockIdx.x * 256 + threadIdx.x;
-    const size_t item = s * scene_items + secC_off + b * box_items + k2;
-    if (threadIdx.x == 0) blocksum[item / 256] = 0;          // k_C_test counts the block's hits
-    int cand = 0;
-    if (k2 < E) {
-        const EdgeRec e2 = edges[k2];
-        V3 x2a, x2b;
-        double aabbE[6];
-        edge_ends(e2, xp + s * xstride, x2a, x2b, aabbE);
-        // whole-box cull first: an edge outside the padded box AABB fails all 24 face-AABB tests
-        if (check_aabb(C.aabbB1, aabbE)) {
+    const size_t item0 = s * scene_items + secC_off + b * box_items;
+    const double *xs = xp + s * xstride;
+    int k2[EOLC_CULL_EPT], cand[EOLC_CULL_EPT];
+    EdgeRec e2[EOLC_CULL_EPT];
 #pragma unroll
-            for (int k1 = 0; k1 < 12; ++k1)
-                if (!pair_culled(k1, C, aabbE, threshold)) cand |= 1 << k1;
-        }
+    for (int i = 0; i < EOLC_CULL_EPT; ++i) {
+        k2[i] = (blockIdx.x * EOLC_CULL_EPT + i) * 256 + threadIdx.x;
+        if (k2[i] < E) e2[i] = edges[k2[i]];
+        else { e2[i].v[0] = e2[i].v[1] = 0; }
+        if (threadIdx.x == 0 && k2[i] < nC) blocksum[(item0 + k2[i]) / 256] = 0;          // k_C_test counts the block's hits
     }
-    info[item] = 0;
+    V3 xa[EOLC_CULL_EPT], xb[EOLC_CULL_EPT];
+#pragma unroll
+    for (int i = 0; i < EOLC_CULL_EPT; ++i) { xa[i] = dcol(xs, e2[i].v[0]); xb[i] = dcol(xs, e2[i].v[1]); }
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < EOLC_CULL_EPT; ++i) {
+        cand[i] = 0;
+        if (k2[i] < E) {
+            double aabbE[6];                                                      // build_AABB_E :455-468
+            aabbE[0] = fmin(xb[i].x, xa[i].x); aabbE[1] = fmin(xb[i].y, xa[i].y); aabbE[2] = fmin(xb[i].z, xa[i].z);
+            aabbE[3] = fmax(xb[i].x, xa[i].x); aabbE[4] = fmax(xb[i].y, xa[i].y); aabbE[5] = fmax(xb[i].z, xa[i].z);
+            // whole-box cull first: an edge outside the padded box AABB fails all 24 face-AABB tests
+            if (check_aabb(C.aabbB1, aabbE)) {
+#pragma unroll
+                for (int k1 = 0; k1 < 12; ++k1)
+                    if (!pair_culled(k1, C, aabbE, threshold)) cand[i] |= 1 << k1;
+            }
+        }
+        n += __popc(cand[i]);
+        if (k2[i] < nC) info[item0 + k2[i]] = 0;
+    }
     // one atomic per WARP (the per-lane atomics on the single counter were 11 % of the kernel's stall samples, ncu r02k): the lanes'
     // counts are scanned in the warp, lane 31 reserves the warp's range.  The counter keeps counting past the capacity: the host
     // then grows the list and repeats the pass.
-    const int n = __popc(cand), lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     if (!__any_sync(0xffffffffu, n)) return;
     int inc = n;
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -1020,11 +1038,13 @@ __global__ void __launch_bounds__(256, EOLC_CULL_CTAS) k_C_cull(int E, int b, co
     if (lane == 31) base = atomicAdd(counter, total);
     base = __shfl_sync(0xffffffffu, base, 31);
     int at = base + inc - n;
-    for (int k1 = 0; k1 < 12; ++k1)
-        if ((cand >> k1) & 1) {
-            if (at < capacity) cand_list[at] = (unsigned long long)item | ((unsigned long long)k1 << 60);
-            ++at;
-        }
+#pragma unroll
+    for (int i = 0; i < EOLC_CULL_EPT; ++i)
+        for (int k1 = 0; k1 < 12; ++k1)
+            if ((cand[i] >> k1) & 1) {
+                if (at < capacity) cand_list[at] = (unsigned long long)(item0 + k2[i]) | ((unsigned long long)k1 << 60);
+                ++at;
+            }
 }
 #ifndef EOLC_CTEST_CTAS
 #define EOLC_CTEST_CTAS 2
@@ -1349,7 +1369,7 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
             for (int b = 0; b < nB; ++b) {
                 CullBox cb;
                 make_cull_box(cb, hb[b], thr);
-                k_C_cull<<<dim3((unsigned)(nC / 256), S), 256, 0, st>>>(E, b, cb, P->d_edges.p, P->d_xp.p, thr, P->d_info.p, P->d_blocksum.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
+                k_C_cull<<<dim3((unsigned)((nC / 256 + EOLC_CULL_EPT - 1) / EOLC_CULL_EPT), S), 256, 0, st>>>(E, (int)nC, b, cb, P->d_edges.p, P->d_xp.p, thr, P->d_info.p, P->d_blocksum.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
             }
             const int gridT = (int)std::max<long long>(1, std::min<long long>(nblkC, (long long)P->ctx->sm_count * EOLC_CTEST_CTAS));
             k_C_test<<<gridT, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn.p, x_dev, P->d_boxes.p, thr, P->d_info.p, P->d_blocksum.p, P->d_cands.p, P->d_counter.p, (int)cap, xs, scene_items, box_items, secBox + nA + nBc);
