@@ -1,5 +1,5 @@
 """CD narrow phase, device-resident runs, for ncu: (a) CD2 on the 512x512 box scene, (b) the 4096 x 64x64 ensemble batch.
-usage: python scripts/bench_cd.py [reps]"""
+usage: python scripts/bench_cd.py [reps] [scenes]"""
 import os
 import sys
 import time
@@ -43,7 +43,7 @@ torch.cuda.synchronize()
 timed(plan, xd, obs, 1, "sheet512")
 plan.close()
 
-S = 4096
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 X, fn = E.meshgen.regular2(64)
 c = np.array([0.9175, -0.25, -0.549])
 obs = make_obstacles(THR, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(c)[None])
@@ -51,6 +51,6 @@ plan = E.CollisionPlan(ctx, X.shape[0], fn, THR)
 xs = np.stack([E.meshgen.box_scene_state(X, seed=s, centre=c) for s in range(S)])
 xd = torch.from_numpy(xs).to(dev)
 torch.cuda.synchronize()
-timed(plan, xd, obs, S, "ensemble4096x64")
+timed(plan, xd, obs, S, "ensemble%dx64" % S)
 plan.close()
 ctx.close()
