@@ -610,6 +610,9 @@ __global__ void __launch_bounds__(256) k_PT_partial(int F, int npts_per_scene, i
         partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = b0;
     }
 }
+#ifndef EOLC_PT8_WAVES
+#define EOLC_PT8_WAVES 4LL     // CTAs of k_PT_partial8 per SM a run aims at (chunks of a scene's faces are added until there are that many)
+#endif
 #ifndef EOLC_PT8_CTAS
 #define EOLC_PT8_CTAS 3      // resident CTAs per SM the register allocation of k_PT_partial8 aims at (80 registers, no spills: 352 us on the batch; 4 CTAs with 64 registers and 64 bytes of spills: 378 us)
 #endif
@@ -966,13 +969,6 @@ __device__ __noinline__ bool test_edge_edge(int k1, const BoxData &B, V3 x2a, V3
     return true;
 }
 
-// per-edge setup: the end points and the AABB (build_AABB_E :455-468) for the culls; length and edge normal (:851-856) only for
-// edges with a surviving pair
-__device__ __forceinline__ void edge_ends(const EdgeRec &e2, const double *__restrict__ xp, V3 &x2a, V3 &x2b, double *aabbE) {
-    x2a = dcol(xp, e2.v[0]); x2b = dcol(xp, e2.v[1]);
-    aabbE[0] = fmin(x2b.x, x2a.x); aabbE[1] = fmin(x2b.y, x2a.y); aabbE[2] = fmin(x2b.z, x2a.z);
-    aabbE[3] = fmax(x2b.x, x2a.x); aabbE[4] = fmax(x2b.y, x2a.y); aabbE[5] = fmax(x2b.z, x2a.z);
-}
 // Pass 1 of section C, in three light / dense kernels instead of one divergent one:
 //   k_C_cull   one thread per cloth edge: the AABB rejections of its 12 pairs; survivors are appended to a work list
 //   k_C_test   one thread per surviving pair (all lanes busy): the rest of :873-1017; a hit sets its bit in the edge's mask
@@ -1351,7 +1347,7 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
         }
         // chunks of a scene's faces per (scene, box): enough CTAs to fill the GPU and no more — every CTA pays the staging of the corners
         // and an eight-corner reduction, which a batch of thousands of small scenes would otherwise pay four times per scene
-        const int nchunk8 = (int)std::max<long long>(1, std::min<long long>(nchunk, (4LL * P->ctx->sm_count + (long long)S * nB - 1) / ((long long)S * nB)));
+        const int nchunk8 = (int)std::max<long long>(1, std::min<long long>(nchunk, (EOLC_PT8_WAVES * P->ctx->sm_count + (long long)S * nB - 1) / ((long long)S * nB)));
         k_PT_partial8<<<dim3(nchunk8, S * nB), 256, 0, st>>>(F, nB, P->d_boxes.p, P->d_fn.p, P->d_xp.p, P->d_aabb.p, thr, P->d_partial.p, xs);
         k_PT_final<<<S * nB, 256, 0, st>>>(nchunk8, 8, nB, P->d_partial.p, P->d_info.p, P->d_blocksum.p, scene_items, secBox + nA, box_items);
         launches += 2 + nB;
