@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(256) k_A_sum(int nbx, long long nblk, const in
 __global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, int S, const double *__restrict__ xp, const int32_t *__restrict__ fn,
                                                  const BoxData *__restrict__ boxes, double threshold, const int *__restrict__ info,
                                                  const int *__restrict__ blockoff, eolc_contact *__restrict__ out, size_t xstride,
-                                                 size_t scene_items, size_t box_items, size_t secA_off) {
+                                                 size_t scene_items, size_t box_items, size_t secA_off, int out_cap) {
     extern __shared__ __align__(16) unsigned char stage_raw[];
     static_assert(sizeof(eolc_contact) % 8 == 0, "records are copied as 8-byte words");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(256) k_A_write(int N, int F, int nB, int S, co
         __syncwarp();
         const unsigned long long *src = reinterpret_cast<const unsigned long long *>(stage);
         unsigned long long *dst = reinterpret_cast<unsigned long long *>(out + base + before);
-        const int nw = cnt * (int)(sizeof(eolc_contact) / 8);
+        const int nw = max(0, min(cnt, out_cap - (base + before))) * (int)(sizeof(eolc_contact) / 8);     // out_cap: see k_PT_write
         for (int w = lane; w < nw; w += 32) dst[w] = src[w];
         __syncwarp();                                  // the warp's stage is reused by its next work item
       }
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(256) k_PT_write(int F, int pts_per_sec, int ns
                                                   const double *__restrict__ fnp, double threshold, const int *__restrict__ info,
                                                   const int *__restrict__ blockoff, eolc_contact *__restrict__ out, size_t xstride,
                                                   size_t fstride, size_t scene_items, size_t sec0_off, size_t sec_stride,
-                                                  int remap, int nP) {
+                                                  int remap, int nP, int out_cap) {
     int s = blockIdx.y / nsec, sec = blockIdx.y % nsec;
     size_t item0 = s * scene_items + sec0_off + sec * sec_stride;
     int pt = blockIdx.x * 256 + threadIdx.x;
@@ -803,7 +803,8 @@ __global__ void __launch_bounds__(256) k_PT_write(int F, int pts_per_sec, int ns
     rec.tri1 = -1; rec.tri2 = j2;
     finish_contact(rec, threshold);
     if (boxes && remap) remap_contact(rec, nP + sec * 8 + sec * 12);
-    out[blockoff[item0 / 256 + blockIdx.x] + pre] = rec;
+    const int slot = blockoff[item0 / 256 + blockIdx.x] + pre;
+    if (slot < out_cap) out[slot] = rec;          // out_cap: a speculative pass 2 runs before the host knows the total (eolc_cd_run)
 }
 
 // ---- section PE: cloth vertex vs obstacle points (pointTriCollision :1099-1139, EOL == true) ----------
@@ -831,7 +832,7 @@ __global__ void __launch_bounds__(256) k_PE_count(int N, int P, const double *__
 __global__ void __launch_bounds__(256) k_PE_write(int N, int P, const double *__restrict__ pxyz, const double *__restrict__ pnorms,
                                                   const double *__restrict__ xp, double threshold, const int *__restrict__ info,
                                                   const int *__restrict__ blockoff, eolc_contact *__restrict__ out, size_t xstride,
-                                                  size_t scene_items, size_t sec_off) {
+                                                  size_t scene_items, size_t sec_off, int out_cap) {
     int s = blockIdx.y;
     size_t item0 = s * scene_items + sec_off;
     int i2 = blockIdx.x * 256 + threadIdx.x;
@@ -849,7 +850,8 @@ __global__ void __launch_bounds__(256) k_PE_write(int N, int P, const double *__
     rec.weights1[0] = 1.0; rec.weights2[0] = 1.0;
     rec.tri1 = -1; rec.tri2 = -1;
     finish_contact(rec, threshold);
-    out[blockoff[item0 / 256 + blockIdx.x] + pre] = rec;
+    const int slot = blockoff[item0 / 256 + blockIdx.x] + pre;
+    if (slot < out_cap) out[slot] = rec;          // out_cap: a speculative pass 2 runs before the host knows the total (eolc_cd_run)
 }
 
 // ---- section C: cloth edge vs box edge (boxTriCollision.cpp:849-1017) ----------------------------------
@@ -1112,7 +1114,7 @@ __global__ void __launch_bounds__(256) k_C_expand(int nbx, long long nblk, int n
 __global__ void __launch_bounds__(256, 2) k_C_write(int nB, const EdgeRec *__restrict__ edges, const double *__restrict__ xp,
                                                  const int32_t *__restrict__ fn, const double *__restrict__ x0, const BoxData *__restrict__ boxes, double threshold,
                                                  const CHit *__restrict__ work, const int *__restrict__ counter, int capacity,
-                                                 eolc_contact *__restrict__ out, size_t xstride, int remap, int nP) {
+                                                 eolc_contact *__restrict__ out, size_t xstride, int remap, int nP, int out_cap) {
     const int n = min(*counter, capacity);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const CHit h = work[i];
@@ -1123,7 +1125,7 @@ __global__ void __launch_bounds__(256, 2) k_C_write(int nB, const EdgeRec *__res
         test_edge_edge(k1, boxes[b], x2a, x2b, nullptr, nullptr, threshold, &rec, e2, h.k2);
         finish_contact(rec, threshold);
         if (remap) remap_contact(rec, nP + b * 8 + b * 12);
-        out[h.slot] = rec;
+        if (h.slot < out_cap) out[h.slot] = rec;
     }
 }
 
@@ -1358,6 +1360,40 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
     EOLC_REQUIRE(nblkC * 256 * 12 < (long long)INT32_MAX, "too many (cloth edge, box edge) pairs for one run; split the batch");   // the pair counter is an int
     long long cap = std::min<long long>(std::max<long long>((long long)P->d_cands.n, nblkC * 128 + 65536), (long long)1 << 30);   // half a pair per edge, and then some
     if (const char *ev = getenv("EOLC_CD_PAIR_CAP")) cap = std::max<long long>(1, atoll(ev));   // test knob: forces the overflow path
+    // ---- pass 2 (records incl. step (E) pos1_ and the CD index remap, written on the device in final order) as a callable: the
+    // device-resident entry launches it SPECULATIVELY, right behind the scan and before the host has seen any size, whenever the
+    // plan's record / hit buffers exist from an earlier run — every write is guarded by the buffers' capacities — and the host then
+    // only confirms that the totals fitted.  A simulation's contact count changes slowly from step to step, so the usual run has no
+    // point at which the GPU waits for the host (the round trip in the middle cost ~35 us: a quarter of a 512-scene batch's call).
+    auto pass2 = [&](int out_cap, int chit_cap) -> int {
+        if (doPE) { k_PE_write<<<dim3((unsigned)(nPE / 256), S), 256, 0, st>>>(N, nP, P->d_pxyz.p, P->d_pnorms.p, P->d_xp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, scene_items, secPE, out_cap); ++launches; }
+        if (nP) { k_PT_write<<<dim3((unsigned)(nPT / 256), S), 256, 0, st>>>(F, nP, 1, nullptr, P->d_pxyz.p, P->d_pnorms.p, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secPT, 0, 0, nP, out_cap); ++launches; }
+        if (nB) {
+            {
+                const long long nvb = (long long)(nA / 256) * S * nB;
+                const int gridA = (int)std::min<long long>(nvb, (long long)P->ctx->sm_count * 3);
+                const size_t smemA = 256 * sizeof(eolc_contact);
+                if (!P->smem_attr_set) {
+                    EOLC_CUDA(cudaFuncSetAttribute(k_A_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+                    P->smem_attr_set = true;
+                }
+                k_A_write<<<gridA, 256, smemA, st>>>(N, F, nB, S, P->d_xp.p, P->d_fn.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, scene_items, box_items, secBox, out_cap);
+            }
+            k_PT_write<<<dim3(1, S * nB), 256, 0, st>>>(F, 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, nullptr, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secBox + nA, box_items, remap_box_indices, nP, out_cap);
+            {
+                // every record has its slot: the work list of section C holds at most as many items as there are records
+                EOLC_CUDA(cudaMemsetAsync(P->d_counter.p + 1, 0, sizeof(int), st));
+                k_C_expand<<<(unsigned)((nblkC + 7) / 8), 256, 0, st>>>((int)(nC / 256), nblkC, nB, P->d_info.p, P->d_blockoff.p, P->d_chits.p, P->d_counter.p + 1, chit_cap, scene_items, box_items, secBox + nA + nBc);
+                const int gridC = std::max(1, std::min((chit_cap + 255) / 256, P->ctx->sm_count * 2));
+                k_C_write<<<gridC, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn.p, x_dev, P->d_boxes.p, thr, P->d_chits.p, P->d_counter.p + 1, chit_cap, P->d_out.p, xs, remap_box_indices, nP, out_cap);
+                ++launches;
+            }
+            launches += 3;
+        }
+        return EOLC_OK;
+    };
+    bool speculated = false;
+    int spec_cap = 0;
     for (int attempt = 0;; ++attempt) {
         if (nB) {
             EOLC_CUDA(P->d_cands.ensure((size_t)cap));
@@ -1380,12 +1416,29 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
             k_scan_add<<<nch, 1024, 0, st>>>(nblocks, P->d_blockoff.p, P->d_scan_tmp.p + nch, nch);
             launches += 3;
         }
-        EOLC_CUDA(cudaMemcpyAsync(P->p_blockoff.p, P->d_blockoff.p, sizeof(int) * (nblocks + 1), cudaMemcpyDeviceToHost, st));
-        EOLC_CUDA(cudaMemcpyAsync(P->p_counter.p, P->d_counter.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        EOLC_CUDA(cudaStreamSynchronize(st));
+        speculated = false;
+        cudaStream_t cs = P->ctx->copy_stream;
+        if (resident && attempt == 0 && P->d_out.n > 1 && P->d_chits.n > 1 && cs && P->ctx->copy_event && !getenv("EOLC_CD_NO_SPECULATION")) {
+            // the sizes travel on the second stream while pass 2 is already queued behind the scan; the host waits for the copy only
+            // and returns with pass 2 still running, as it always did
+            EOLC_CUDA(cudaEventRecord(P->ctx->copy_event, st));
+            EOLC_CUDA(cudaStreamWaitEvent(cs, P->ctx->copy_event, 0));
+            EOLC_CUDA(cudaMemcpyAsync(P->p_blockoff.p, P->d_blockoff.p, sizeof(int) * (nblocks + 1), cudaMemcpyDeviceToHost, cs));
+            EOLC_CUDA(cudaMemcpyAsync(P->p_counter.p, P->d_counter.p, sizeof(int), cudaMemcpyDeviceToHost, cs));   // [1] is pass 2's
+            spec_cap = (int)std::min<size_t>(std::min(P->d_out.n, P->d_chits.n), (size_t)INT32_MAX);
+            const int rc2 = pass2(spec_cap, spec_cap);
+            if (rc2) return rc2;
+            speculated = true;
+            EOLC_CUDA(cudaStreamSynchronize(cs));
+        } else {
+            EOLC_CUDA(cudaMemcpyAsync(P->p_blockoff.p, P->d_blockoff.p, sizeof(int) * (nblocks + 1), cudaMemcpyDeviceToHost, st));
+            EOLC_CUDA(cudaMemcpyAsync(P->p_counter.p, P->d_counter.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            EOLC_CUDA(cudaStreamSynchronize(st));
+        }
         if (!nB || P->p_counter.p[0] <= cap) break;
         if (attempt >= 1) { set_error("internal: the pair list of section C overflowed twice"); return EOLC_ERR_UNSUPPORTED; }
         cap = P->p_counter.p[0];        // the pass counted every surviving pair: this is the exact size
+        speculated = false;             // a speculative pass 2 saw an incomplete pair list: it runs again below
     }
     const int total = P->p_blockoff.p[nblocks];
 
@@ -1397,33 +1450,18 @@ static int cd_run_impl(eolc_cd_plan *plan, int32_t S, const double *x_dev, int32
         return EOLC_ERR_CAPACITY;
     }
 
-    // ---- pass 2: records (incl. step (E) pos1_ and the CD index remap) are written on the device, in final order
-    EOLC_CUDA(P->d_out.ensure(std::max(total, 1)));
-    if (total > 0) {
-        if (doPE) { k_PE_write<<<dim3((unsigned)(nPE / 256), S), 256, 0, st>>>(N, nP, P->d_pxyz.p, P->d_pnorms.p, P->d_xp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, scene_items, secPE); ++launches; }
-        if (nP) { k_PT_write<<<dim3((unsigned)(nPT / 256), S), 256, 0, st>>>(F, nP, 1, nullptr, P->d_pxyz.p, P->d_pnorms.p, P->d_fn.p, P->d_xp.p, P->d_fnp.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secPT, 0, 0, nP); ++launches; }
-        if (nB) {
-            {
-                const long long nvb = (long long)(nA / 256) * S * nB;
-                const int gridA = (int)std::min<long long>(nvb, (long long)P->ctx->sm_count * 3);
-                const size_t smemA = 256 * sizeof(eolc_contact);
-                if (!P->smem_attr_set) {
-                    EOLC_CUDA(cudaFuncSetAttribute(k_A_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-                    P->smem_attr_set = true;
-                }
-                k_A_write<<<gridA, 256, smemA, st>>>(N, F, nB, S, P->d_xp.p, P->d_fn.p, P->d_boxes.p, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, scene_items, box_items, secBox);
-            }
-            k_PT_write<<<dim3(1, S * nB), 256, 0, st>>>(F, 8, nB, P->d_boxes.p, nullptr, nullptr, P->d_fn.p, P->d_xp.p, nullptr, thr, P->d_info.p, P->d_blockoff.p, P->d_out.p, xs, fs, scene_items, secBox + nA, box_items, remap_box_indices, nP);
-            {
-                // every record has its slot: the work list of section C can hold at most `total` items
-                EOLC_CUDA(P->d_chits.ensure((size_t)total + 1));
-                k_C_expand<<<(unsigned)((nblkC + 7) / 8), 256, 0, st>>>((int)(nC / 256), nblkC, nB, P->d_info.p, P->d_blockoff.p, P->d_chits.p, P->d_counter.p + 1, total, scene_items, box_items, secBox + nA + nBc);
-                const int gridC = std::max(1, std::min((total + 255) / 256, P->ctx->sm_count * 2));
-                k_C_write<<<gridC, 256, 0, st>>>(nB, P->d_edges.p, P->d_xp.p, P->d_fn.p, x_dev, P->d_boxes.p, thr, P->d_chits.p, P->d_counter.p + 1, total, P->d_out.p, xs, remap_box_indices, nP);
-                ++launches;
-            }
-            launches += 3;
+    // ---- pass 2, unless the speculative one has done it (its capacities held)
+    if (!(speculated && total <= spec_cap)) {
+        // the device-resident entry keeps a quarter of headroom, so that the next steps of a simulation can speculate
+        const size_t want = resident ? (size_t)total + (size_t)total / 4 + 1024 : (size_t)std::max(total, 1);
+        if ((size_t)std::max(total, 1) > P->d_out.n) EOLC_CUDA(P->d_out.ensure(want));
+        if ((size_t)total + 1 > P->d_chits.n) EOLC_CUDA(P->d_chits.ensure(want + 1));
+        if (total > 0) {
+            const int rc2 = pass2(total, total);
+            if (rc2) return rc2;
         }
+    }
+    if (total > 0) {
         if (!resident) {
         // pinned caller buffer: DMA straight into it; pageable: via the plan's pinned staging
         cudaPointerAttributes pa;

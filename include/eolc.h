@@ -202,7 +202,11 @@ int eolc_cd_run_batched_dev(eolc_cd_plan *plan, int32_t n_scenes, const double *
 /* Same run, but the records stay on the device (no device-to-host copy of the list; only the per-scene offsets come back):
  * for a consumer that lives on the device too — eolc_cd_contact_rows below (112 B of rows per contact instead of the 264 B
  * record), or any kernel reading eolc_cd_contacts_dev.  Step (D) needs no pass: section Bc emits at most one record per
- * corner by construction (a lexicographic argmin).  The device buffer is owned by the plan and valid until its next run. */
+ * corner by construction (a lexicographic argmin).  The device buffer is owned by the plan and valid until its next run.
+ * The call returns with the offsets known and the records possibly still being written on the context's stream (work queued on
+ * that stream afterwards — the row entry points below, the caller's own kernels — is ordered behind them).  From the plan's
+ * second run on, the record pass is launched before the host has seen the totals, guarded by the existing buffers' capacities,
+ * and repeated if they were too small (EOLC_CD_NO_SPECULATION=1 in the environment switches that off). */
 int eolc_cd_run_batched_resident_dev(eolc_cd_plan *plan, int32_t n_scenes, const double *x_dev, int32_t n_points,
                                      const double *pxyz, const double *pnorms, int32_t n_boxes, const double *box_whd,
                                      const double *box_E, int point_eol_flag, int remap_box_indices, int32_t *scene_offset);

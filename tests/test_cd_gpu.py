@@ -201,6 +201,56 @@ def test_batch_of_20000_small_scenes(ctx):
     plan.close()
 
 
+def _records_on_device(plan):
+    """Copies the records of the plan's last device-resident run to the host."""
+    import torch
+    from cuda.bindings import runtime as cudart
+    torch.cuda.synchronize()                 # pass 2 may still be running on the library's (non-blocking) stream
+    ptr, n = plan.contacts_dev()
+    out = np.zeros(n, dtype=E.CONTACT_DTYPE)
+    if n:
+        (err,) = cudart.cudaMemcpy(out.ctypes.data, ptr, out.nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+        assert int(err) == 0
+    return out
+
+
+def test_resident_run_speculates_pass_2(ctx, monkeypatch):
+    """eolc_cd_run_batched_resident_dev launches pass 2 before the host has seen the totals whenever the plan's record buffers exist
+    from an earlier run (every write guarded by their capacities) and repeats it if they were too small.  Same records as the
+    host-list run in every case: first run (no buffers yet), a run that fits, a run with ~30x the contacts (buffers too small), a
+    run with none, and with the speculation switched off."""
+    import torch
+    X, fn = E.meshgen.regular2(32)
+    c = np.array([0.9175, -0.25, -0.549])
+    obs = make_obstacles(THR, box_whd=E.meshgen.BOX_WHD[None], box_E=E.meshgen.box_frame(c)[None])
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, THR)
+    dev = torch.device("cuda", ctx.device)
+    S = 6
+    draped = np.stack([E.meshgen.box_scene_state(X, seed=s, centre=c) for s in range(S)])
+    few = draped.copy(); few[1:, :, 2] += 5.0                       # only scene 0 touches the box
+    none = draped.copy(); none[:, :, 2] += 5.0
+    order = [("first: few", few), ("fits: few again", few), ("grows: all draped", draped), ("fits: all draped", draped),
+             ("none", none), ("few after none", few)]
+    for what, xs in order:
+        xd = torch.from_numpy(xs).to(dev)
+        torch.cuda.synchronize()
+        off = plan.run_resident(xd.data_ptr(), obs, 0, 0, n_scenes=S)
+        got = _records_on_device(plan)
+        monkeypatch.setenv("EOLC_CD_NO_SPECULATION", "1")
+        off2 = plan.run_resident(xd.data_ptr(), obs, 0, 0, n_scenes=S)
+        got2 = _records_on_device(plan)
+        monkeypatch.delenv("EOLC_CD_NO_SPECULATION")
+        assert np.array_equal(off, off2) and got.tobytes() == got2.tobytes(), what
+        assert off[-1] == len(got), what
+        for s_ in (0, S - 1):
+            single = E.CollisionPlan(ctx, X.shape[0], fn, THR)
+            one = single.run(xs[s_], obs, 0, 0)
+            single.close()
+            assert got[off[s_]:off[s_ + 1]].tobytes() == one.tobytes(), f"{what}: scene {s_}"
+    assert len(got) > 0
+    plan.close()
+
+
 def test_ensemble_4096_scenes_sampled_against_reference(ctx, oracle):
     """BASELINE configs[4]: the full batch of 4096 independent 64x64 scenes (state seed = scene id) against the box, one batched
     call per chunk; 40 sampled scenes are compared bit for bit with the reference's own code (libbtc_ref.so) and the oracle."""
