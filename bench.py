@@ -640,6 +640,7 @@ def bench_ensemble(ctx, dev, stream, rank, world, barrier, total_scenes=4096, n=
     N_, F_, _, Ei_, nM_, nK_ = sheet_counts(n)
     abytes = algorithmic_bytes(N_, F_, Ei_, nM_, nK_) * S
     peak, _ = measured_peak()
+    cd_bytes = 24.0 * N * S + 264.0 * contacts       # this rank
     checksum = float(K_d[0].sum().item()) + float(off[1])
     out = {"workload": "ensemble of %d independent regular2 %dx%d scenes (BASELINE configs[4]): batched Forces::fill + batched CD2 over the box" % (total_scenes, n, n),
            "scaling": "strong", "scenes_total": total_scenes, "scenes_this_rank": S, "shard": "contiguous, rank r owns [r S/G, (r+1) S/G)",
@@ -650,6 +651,10 @@ def bench_ensemble(ctx, dev, stream, rank, world, barrier, total_scenes=4096, n=
            "load_balance": (sum(per_rank) / len(per_rank)) / step_ms,
            "contacts_total": int(tot_contacts), "launches_per_step": plan.launches_per_fill + cd_launches,
            "fill_roofline": {"achieved_GBps": abytes / (fill_ms * 1e-3) / 1e9, "frac_of_hbm_peak": abytes / (fill_ms * 1e-3) / 1e9 / peak},
+           "cd_roofline": {"algorithmic_bytes": cd_bytes, "achieved_GBps": cd_bytes / (cd_ms * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": cd_bytes / (cd_ms * 1e-3) / 1e9 / peak,
+                           "what": "positions in (24 B per node and scene) + records out (264 B per contact); not HBM-bound: its kernels are "
+                                   "chains of dependent gathers and FP64 tests (DESIGN.md 4)"},
            "timing": "CUDA events on the library stream, max over ranks; contacts stay on the device (eolc_cd_run_batched_resident_dev)",
            "parity": "tests/test_cd_gpu.py::test_ensemble_4096_scenes_sampled_against_reference, tests/test_forces_gpu.py (batched fill)",
            "checksum": checksum}
