@@ -251,6 +251,33 @@ def test_resident_run_speculates_pass_2(ctx, monkeypatch):
     plan.close()
 
 
+def test_resident_speculation_with_points_and_two_boxes(ctx):
+    """The same with every section present (obstacle points with the EOL flag, two boxes, CD's index remap): second and third runs
+    on the plan speculate; records equal to the host-list run."""
+    import torch
+    X, fn = E.meshgen.regular2(30)
+    dev = torch.device("cuda", ctx.device)
+    states = [E.meshgen.box_scene_state(X, seed=s, centre=np.array([0.9175, -0.25, -0.549])) for s in (5, 6, 7)]
+    x0 = states[0]
+    pxyz = np.array([[0.25, 0.25, x0[:, 2].max() - 4e-3], [0.1, 0.8, -0.2], x0[5] + 1e-3, x0[100] - 2e-3])
+    pn = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0], [0, 0.6, 0.8]])
+    whd = np.stack([E.meshgen.BOX_WHD, [0.3, 0.3, 0.3]])
+    Em = np.stack([E.meshgen.box_frame(np.array([0.9175, -0.25, -0.549])), E.meshgen.box_frame(np.array([0.15, 0.8, -0.36]))])
+    obs = make_obstacles(THR, pxyz, pn, whd, Em)
+    plan = E.CollisionPlan(ctx, X.shape[0], fn, THR)
+    ref_plan = E.CollisionPlan(ctx, X.shape[0], fn, THR)
+    for flag, remap in ((1, 1), (0, 0)):
+        for x in states:
+            xd = torch.from_numpy(x).to(dev)
+            torch.cuda.synchronize()
+            off = plan.run_resident(xd.data_ptr(), obs, flag, remap)
+            got = _records_on_device(plan)
+            ref = ref_plan.run(x, obs, flag, remap)
+            assert off[-1] == len(ref) and got.tobytes() == ref.tobytes()
+    assert {(1, 3), (2, 2), (3, 1)} <= set(zip(ref["count1"].tolist(), ref["count2"].tolist()))
+    plan.close(); ref_plan.close()
+
+
 def test_ensemble_4096_scenes_sampled_against_reference(ctx, oracle):
     """BASELINE configs[4]: the full batch of 4096 independent 64x64 scenes (state seed = scene id) against the box, one batched
     call per chunk; 40 sampled scenes are compared bit for bit with the reference's own code (libbtc_ref.so) and the oracle."""
