@@ -1051,6 +1051,7 @@ int eolc_forces_plan_create(eolc_ctx *ctx, int32_t N, int32_t F, const int32_t *
     eolc_forces_plan *P = new eolc_forces_plan;
     P->ctx = ctx; P->device = ctx->device; P->N = N; P->F = F; P->E = E; P->dof = 3 * N;
     P->h_face_nodes.assign(face_nodes, face_nodes + 3 * (size_t)F);
+    P->h_iedge.reserve(4 * (size_t)E);
     for (int32_t e = 0; e < E; ++e) {
         const int32_t *s = edge_stencil + 4 * (size_t)e;
         if (s[2] < 0 || s[3] < 0) continue;  // boundary edge, Forces.cpp:688-690

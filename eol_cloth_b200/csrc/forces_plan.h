@@ -63,14 +63,29 @@ struct NodeCSR {
     std::vector<int32_t> nfp, nep;
     std::vector<uint32_t> nfl, nel;
     NodeCSR(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int32_t *ie) {
-        nfp.assign(N + 1, 0); nep.assign(N + 1, 0);
-        for (int64_t i = 0; i < 3 * (int64_t)F; ++i) nfp[fn[i] + 1]++;
-        for (int64_t i = 0; i < 4 * (int64_t)Ei; ++i) nep[ie[i] + 1]++;
-        for (int32_t a = 0; a < N; ++a) { nfp[a + 1] += nfp[a]; nep[a + 1] += nep[a]; }
-        nfl.resize(nfp[N]); nel.resize(nep[N]);
-        std::vector<int32_t> pf(nfp.begin(), nfp.end() - 1), pe(nep.begin(), nep.end() - 1);
-        for (int32_t i = 0; i < F; ++i) for (int v = 0; v < 3; ++v) nfl[pf[fn[3 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
-        for (int32_t i = 0; i < Ei; ++i) for (int v = 0; v < 4; ++v) nel[pe[ie[4 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
+        // the face lists and the stencil lists are independent counting sorts: one thread each.  (Counting and filling on all the
+        // plan-build threads with relaxed atomics + a sort of every node's list measured slower: 11.3 instead of 6.6-9.9 ms at 512^2.)
+        auto faces = [&]() {
+            nfp.assign(N + 1, 0);
+            for (int64_t i = 0; i < 3 * (int64_t)F; ++i) nfp[fn[i] + 1]++;
+            for (int32_t a = 0; a < N; ++a) nfp[a + 1] += nfp[a];
+            nfl.resize(nfp[N]);
+            std::vector<int32_t> pf(nfp.begin(), nfp.end() - 1);
+            for (int32_t i = 0; i < F; ++i) for (int v = 0; v < 3; ++v) nfl[pf[fn[3 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
+        };
+        auto stencils = [&]() {
+            nep.assign(N + 1, 0);
+            for (int64_t i = 0; i < 4 * (int64_t)Ei; ++i) nep[ie[i] + 1]++;
+            for (int32_t a = 0; a < N; ++a) nep[a + 1] += nep[a];
+            nel.resize(nep[N]);
+            std::vector<int32_t> pe(nep.begin(), nep.end() - 1);
+            for (int32_t i = 0; i < Ei; ++i) for (int v = 0; v < 4; ++v) nel[pe[ie[4 * (size_t)i + v]]++] = ((uint32_t)i << 2) | v;
+        };
+        if ((int64_t)F + Ei > 65536 && n_workers_hw() > 1) {
+            std::thread t(stencils);
+            faces();
+            t.join();
+        } else { faces(); stencils(); }
     }
 };
 
@@ -90,24 +105,28 @@ inline void build_pattern(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, c
         const size_t lo = (size_t)N * (size_t)w / (size_t)nw, hi = (size_t)N * (size_t)(w + 1) / (size_t)nw;
         std::vector<int32_t> &oM = partM[(size_t)w], &oK = partK[(size_t)w];
         oM.reserve((hi - lo) * 8); oK.reserve((hi - lo) * 14);
+        // a node's neighbour set is small (7 / 13 on a regular sheet): kept sorted and unique by insertion as the elements are walked
+        // (the first version collected, std::sort-ed and std::unique-d two vectors per node: a third of the plan build at 512^2)
         std::vector<int32_t> bm, bk;
+        auto insert_sorted = [](std::vector<int32_t> &v, int32_t x) {
+            size_t i = v.size();
+            while (i > 0 && v[i - 1] > x) --i;
+            if (i > 0 && v[i - 1] == x) return;
+            v.insert(v.begin() + (std::ptrdiff_t)i, x);
+        };
         for (size_t a = lo; a < hi; ++a) {
             if (c.nfp[a + 1] == c.nfp[a]) continue;          // isolated: no block
-            bm.clear(); bk.clear();
+            bm.clear();
             bm.push_back((int32_t)a);
             for (int32_t k = c.nfp[a]; k < c.nfp[a + 1]; ++k) {
                 const int32_t *v = fn + 3 * (size_t)(c.nfl[k] >> 2);
-                for (int j = 0; j < 3; ++j) if (v[j] != (int32_t)a) bm.push_back(v[j]);
+                for (int j = 0; j < 3; ++j) insert_sorted(bm, v[j]);
             }
-            std::sort(bm.begin(), bm.end());
-            bm.erase(std::unique(bm.begin(), bm.end()), bm.end());
             bk = bm;
             for (int32_t k = c.nep[a]; k < c.nep[a + 1]; ++k) {
                 const int32_t *v = ie + 4 * (size_t)(c.nel[k] >> 2);
-                for (int j = 0; j < 4; ++j) if (v[j] != (int32_t)a) bk.push_back(v[j]);
+                for (int j = 0; j < 4; ++j) insert_sorted(bk, v[j]);
             }
-            std::sort(bk.begin(), bk.end());
-            bk.erase(std::unique(bk.begin(), bk.end()), bk.end());
             P.blkptrM[a + 1] = (int64_t)bm.size(); P.blkptrK[a + 1] = (int64_t)bk.size();
             oM.insert(oM.end(), bm.begin(), bm.end()); oK.insert(oK.end(), bk.begin(), bk.end());
         }
