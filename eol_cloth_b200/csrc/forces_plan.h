@@ -766,7 +766,8 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
     // One worker builds the tiles [t0, t1) into its own partial plan Q (templates deduplicated within the range, geometry blobs
     // back to back with offsets in geo_off); the ranges are merged in tile order below, so the result does not depend on the
     // number of workers.
-    auto build_range = [&](Builder &Bw, size_t t0, size_t t1, Plan &Q, std::vector<uint32_t> &geo_off, std::vector<std::pair<uint32_t, uint32_t>> &unique_tmpl) -> bool {
+    auto build_range = [&](Builder &Bw, size_t t0, size_t t1, Plan &Q, std::vector<uint32_t> &geo_off, std::vector<std::pair<uint32_t, uint32_t>> &unique_tmpl,
+                           std::vector<uint64_t> &unique_hash) -> bool {
         std::vector<int32_t> faces, edges;
         std::unordered_map<uint64_t, std::vector<uint32_t>> seen;   // hash -> template offsets (16-byte units)
         // Structural shortcut: the template of a tile is a function of its LOCAL structure only — the element -> local node lists, the
@@ -1088,6 +1089,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                 if (dedup) seen[h].push_back(toff);
                 ++Q.n_templates;
                 unique_tmpl.push_back({toff, sizeA16});
+                unique_hash.push_back(h);          // of the template's words (dedup only): the merge does not hash them again
             }
             if (reuse) {   // EOLC_PLAN_VERIFY_DEDUP: the shortcut would have reused this template — it must be the one just built
                 if (reuse->toff != toff || reuse->sizeA16 != sizeA16 || reuse->sizeB16 != sizeB16) {
@@ -1122,17 +1124,18 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
     std::vector<Plan> parts((size_t)n_workers);
     std::vector<std::vector<uint32_t>> part_geo_off((size_t)n_workers);
     std::vector<std::vector<std::pair<uint32_t, uint32_t>>> part_unique((size_t)n_workers);
+    std::vector<std::vector<uint64_t>> part_hash((size_t)n_workers);
     std::vector<char> part_ok((size_t)n_workers, 1);
     auto range_of = [&](int w) { return std::make_pair(leaves.size() * (size_t)w / (size_t)n_workers, leaves.size() * (size_t)(w + 1) / (size_t)n_workers); };
     if (n_workers == 1) {
-        part_ok[0] = build_range(B, 0, leaves.size(), parts[0], part_geo_off[0], part_unique[0]) ? 1 : 0;
+        part_ok[0] = build_range(B, 0, leaves.size(), parts[0], part_geo_off[0], part_unique[0], part_hash[0]) ? 1 : 0;
     } else {
         std::vector<std::thread> th;
         for (int w = 0; w < n_workers; ++w)
             th.emplace_back([&, w]() {
                 // own scratch (stamps, slot maps), created for the capacity check above; the node CSR is shared
                 const auto r = range_of(w);
-                part_ok[w] = build_range(*wb[(size_t)w], r.first, r.second, parts[w], part_geo_off[w], part_unique[w]) ? 1 : 0;
+                part_ok[w] = build_range(*wb[(size_t)w], r.first, r.second, parts[w], part_geo_off[w], part_unique[w], part_hash[w]) ? 1 : 0;
             });
         for (auto &t : th) t.join();
     }
@@ -1151,15 +1154,24 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
     {
         std::unordered_map<uint64_t, std::vector<uint32_t>> seen;
         std::vector<uint32_t> fixed((size_t)P.n_tiles * P.max_geo16 * 4, 0u);
+        {   // one allocation for the templates (an unstructured mesh brings one per tile: ~100 MB at 512^2, appended range by range)
+            size_t total_words = 0;
+            for (int w = 0; w < n_workers; ++w) total_words += parts[w].tmpl.size();
+            P.tmpl.reserve(P.tmpl.size() + total_words);
+        }
         size_t t = 0;
         for (int w = 0; w < n_workers; ++w) {
             const Plan &Q = parts[w];
             // local template offset -> global offset (first use in tile order decides the global order)
             std::unordered_map<uint32_t, uint32_t> remap;
-            std::vector<std::pair<uint32_t, uint32_t>> local_sorted = part_unique[w];   // (local offset, sizeA16), ascending offsets
+            // local templates lie back to back in the order they were stored: offset -> (words, hash of the words from the worker)
+            const std::vector<std::pair<uint32_t, uint32_t>> &lu = part_unique[w];
+            std::unordered_map<uint32_t, size_t> local_index;
+            local_index.reserve(lu.size() * 2);
+            for (size_t q = 0; q < lu.size(); ++q) local_index.emplace(lu[q].first, q);
             auto tmpl_words = [&](uint32_t loff) {     // length of the local template starting at loff: up to the next one
-                size_t end = Q.tmpl.size() / 4;
-                for (const auto &u : local_sorted) if (u.first > loff) { end = std::min<size_t>(end, u.first); }
+                const size_t q = local_index.at(loff);
+                const size_t end = q + 1 < lu.size() ? (size_t)lu[q + 1].first : Q.tmpl.size() / 4;
                 return (end - loff) * 4;
             };
             const size_t ntw = part_geo_off[w].size() - 1;
@@ -1173,8 +1185,7 @@ inline bool build(int32_t N, int32_t F, const int32_t *fn, int32_t Ei, const int
                 if (it == remap.end()) {
                     const size_t words = tmpl_words(loff);
                     const uint32_t *src = Q.tmpl.data() + (size_t)loff * 4;
-                    uint64_t h = 1469598103934665603ull;
-                    for (size_t q = 0; q < words; ++q) { h ^= src[q]; h *= 1099511628211ull; }
+                    const uint64_t h = dedup ? part_hash[w][local_index.at(loff)] : 0;      // FNV-1a of the words, computed by the worker
                     uint32_t goff = 0;
                     bool found = false;
                     if (dedup) {
